@@ -1,0 +1,137 @@
+/* mast_b200.h -- C-ABI of the B200-native element-assembly + sensitivity path.
+ *
+ * This is the drop-in boundary: MAST's host classes (MAST::NonlinearImplicitAssembly & co., mirrored
+ * in mast-multiphysics_b200/host/) pull plain arrays out of libMesh/PETSc objects once per mesh and
+ * call these entry points once per sweep.  Plain pointers and sizes only, int status returns, no
+ * exceptions cross the boundary.  One context per rank/GPU; calls on one context are stream-ordered
+ * and not thread-safe (the reference is single-threaded per MPI rank and not re-entrant,
+ * /root/reference/src/base/assembly_elem_operation.cpp:48-78).
+ *
+ * Every data pointer marked [h|d] may be a host pointer or a CUDA device pointer; the library detects
+ * which (cudaPointerGetAttributes).  Host buffers are copied inside the call; device buffers are used
+ * in place.  There is no CPU fallback: every compute entry point fails with MASTB200_ERR_CUDA if no
+ * sm_100 device is usable.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference):
+ *   mastb200_residual_and_jacobian   <- MAST::NonlinearImplicitAssembly::residual_and_jacobian
+ *                                       src/base/nonlinear_implicit_assembly.cpp:64-266 (assembly_base.h:226-232)
+ *   mastb200_sensitivity_sweep       <- MAST::NonlinearImplicitAssembly::sensitivity_assemble
+ *                                       src/base/nonlinear_implicit_assembly.cpp:515-686, folded with
+ *                                       AssemblyBase::calculate_output_adjoint_sensitivity_multiple_parameters_no_direct
+ *                                       src/base/assembly_base.cpp:594-639 (all DVs in one sweep)
+ *   mastb200_compliance / _derivative<- AssemblyBase::calculate_output / calculate_output_derivative with
+ *                                       MAST::ComplianceOutput, src/base/assembly_base.cpp:253-430,
+ *                                       src/elasticity/compliance_output.cpp:71-102, 265-296
+ *   mastb200_apply_dv_map_transpose  <- the per-DV loop of assembly_base.cpp:618-638 with the filter columns of
+ *                                       src/level_set/filter_base.cpp:59-97 as the nodal-density sensitivities
+ *   mastb200_res_l2_norm             <- NonlinearImplicitAssembly::res_l2_norm (nonlinear_implicit_assembly.cpp:258-264)
+ *   mastb200_build_pattern/_get_*    <- libMesh DofMap sparsity + PETSc AIJ preallocation consumed at
+ *                                       nonlinear_implicit_assembly.cpp:182-183
+ */
+#ifndef MAST_B200_H
+#define MAST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MASTB200_OK 0
+#define MASTB200_ERR_ARG 1      /* bad argument / call order */
+#define MASTB200_ERR_CUDA 2     /* CUDA runtime error or no usable device */
+#define MASTB200_ERR_UNSUPPORTED 3 /* valid MAST configuration not (yet) on the device path */
+#define MASTB200_ERR_PLAN 4     /* mesh cannot be tiled within shared-memory limits */
+
+/* element types (libMesh node ordering) */
+#define MASTB200_HEX8 8
+#define MASTB200_HEX27 27
+#define MASTB200_QUAD4 4 /* 2D heat conduction in the xy-plane */
+
+typedef struct mastb200_context mastb200_context;
+
+/* Isotropic property card + strain type.  E(x) = E0, or the SIMP law of
+ * examples/structural/example_6/example_6.cpp:100-137 when a nodal density field is set. */
+typedef struct mastb200_material {
+  double E0, nu, alpha;
+  double rho_min, penalty;     /* SIMP: E = E0*(rho_min + (1-rho_min)*rho^penalty) */
+  int32_t nonlinear_strain;    /* 0 LINEAR_STRAIN, 1 NONLINEAR_STRAIN (Green-Lagrange) */
+  /* heat conduction card (QUAD4): k(T) = k0*(1+k_beta*T) if k_of_T, section thickness */
+  double k0, k_beta, thickness;
+  int32_t k_of_T;
+  double heat_source;
+} mastb200_material;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int mastb200_create(int device, mastb200_context** ctx);
+int mastb200_destroy(mastb200_context* ctx);
+const char* mastb200_last_error(const mastb200_context* ctx); /* never NULL; ctx may be NULL for create errors */
+const char* mastb200_version(void);
+
+/* ---- problem definition (host pointers; copied) -------------------------------------------- */
+/* conn: [n_elem][nn] node ids; xyz: [n_nodes][3]; diag_elem: [n_elem] or NULL
+ * (AssemblyBase::diagonal_elem_subdomain_id members). */
+int mastb200_set_mesh(mastb200_context* ctx, int32_t elem_type, int64_t n_elem, int64_t n_nodes,
+                      const double* xyz, const int32_t* conn, const uint8_t* diag_elem);
+/* dof(node,var) = nv*node + var (one libMesh variable group).  nv = 6 (MAST structural system), 3 (compact)
+ * or 1 (heat).  constrained: [n_nodes*nv] homogeneous-Dirichlet flags or NULL.
+ * owned: [n_nodes] or NULL (all owned): rows are produced only for owned nodes (the rank's row block);
+ * the other nodes are ghosts whose values arrive in X (AssemblyBase::build_localized_vector). */
+int mastb200_set_dof_map(mastb200_context* ctx, int32_t nv, const uint8_t* constrained, const uint8_t* owned);
+int mastb200_set_material(mastb200_context* ctx, const mastb200_material* mat);
+/* SURFACE_PRESSURE side loads on (element, libMesh side) pairs; n = 0 clears. */
+int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                               const double* pressure);
+/* TEMPERATURE volume load: nodal field [h|d] (or NULL => constant), reference temperature. enable=0 clears. */
+int mastb200_set_temperature(mastb200_context* ctx, int32_t enable, const double* T_nodal, double T_const,
+                             double T_ref);
+/* nodal density field [h|d] for the SIMP law (NULL => homogeneous E0). Cheap: call every design iteration. */
+int mastb200_set_density(mastb200_context* ctx, const double* rho_nodal);
+
+/* Builds the sparsity pattern (every dof pair sharing an element, columns sorted) and the device
+ * assembly plan (node tiles, element visit lists, element->nnz slot maps).  Call after mesh/dof map. */
+int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz);
+/* Copies the CSR pattern of the owned rows out (host pointers): row_ptr[n_rows+1], col_idx[nnz]. */
+int mastb200_get_pattern(const mastb200_context* ctx, int64_t* row_ptr, int32_t* col_idx);
+/* dof id of each CSR row: row_dof[n_rows] (owned nodes ascending, nv rows per node). */
+int mastb200_get_row_dofs(const mastb200_context* ctx, int64_t* row_dof);
+
+/* ---- sweeps --------------------------------------------------------------------------------- */
+/* X: [n_nodes*nv] localized solution (owned + ghost values) [h|d].
+ * R: [n_nodes*nv] or NULL [h|d] -- entries of owned rows are written, ghost rows are zeroed.
+ * J_vals: [nnz] or NULL [h|d], in the order of mastb200_get_pattern.  Outputs are overwritten (the
+ * reference zeroes R and J first, nonlinear_implicit_assembly.cpp:81-82) and left "closed". */
+int mastb200_residual_and_jacobian(mastb200_context* ctx, const double* X, double* R, double* J_vals);
+int mastb200_res_l2_norm(mastb200_context* ctx, double* norm); /* of the last R (owned rows) */
+
+/* One fused sweep for all density design variables:  G[n] = adj . dR/d(rho_n)  for every owned node n
+ * (SURVEY 8a row S), optionally together with R/J of the same state (either may be NULL).
+ * adj: [n_nodes*nv] localized adjoint [h|d] (compliance: adj == X).  G: [n_nodes] [h|d]. */
+int mastb200_sensitivity_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G,
+                               double* R, double* J_vals);
+/* sens[i] = sum_k dv_weight[k] * G[dv_node[k]], k in [dv_ptr[i], dv_ptr[i+1])   (host CSC arrays; G [h|d]) */
+int mastb200_apply_dv_map_transpose(mastb200_context* ctx, const double* G, int64_t n_dv, const int64_t* dv_ptr,
+                                    const int32_t* dv_node, const double* dv_weight, double* sens);
+
+/* ComplianceOutput: q = -sum f_ext . u  (owned part; caller sums over ranks unless skip_comm_sum) */
+int mastb200_compliance(mastb200_context* ctx, const double* X, double* q);
+/* dq_dX[n_nodes*nv] [h|d] = -f_ext with constrained rows zeroed */
+int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, double* dq_dX);
+
+/* ---- introspection for bench / tests -------------------------------------------------------- */
+typedef struct mastb200_stats {
+  int64_t n_tiles, n_visits, n_owned_nodes, n_elem;
+  int64_t kernel_launches;       /* cumulative count of this library's kernel launches */
+  double last_sweep_ms;          /* CUDA-event time of the last sweep's kernels on the context stream */
+  double last_main_kernel_ms;    /* ... of the dominant (tile sweep) kernel alone */
+  int64_t plan_bytes;            /* device bytes of the static plan streamed per sweep */
+  int32_t smem_bytes, threads_per_cta, ctas;
+} mastb200_stats;
+int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s);
+/* the CUDA stream all work of this context is ordered on (cudaStream_t as void*) */
+void* mastb200_stream(const mastb200_context* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

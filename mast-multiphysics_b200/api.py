@@ -1,0 +1,226 @@
+"""ctypes binding of the C-ABI in ``include/mast_b200.h`` (``libmast_b200.so``).
+
+Thin by design: argument marshalling only.  All arithmetic happens in the CUDA library; if the
+library is missing or no B200 is present the calls raise -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["Context", "Material", "MastB200Error", "lib_path", "load_library", "HEX8", "HEX27", "QUAD4",
+           "EXPORTED_SYMBOLS"]
+
+HEX8, HEX27, QUAD4 = 8, 27, 4
+
+EXPORTED_SYMBOLS = [
+    "mastb200_create", "mastb200_destroy", "mastb200_last_error", "mastb200_version", "mastb200_set_mesh",
+    "mastb200_set_dof_map", "mastb200_set_material", "mastb200_set_side_pressure", "mastb200_set_temperature",
+    "mastb200_set_density", "mastb200_build_pattern", "mastb200_get_pattern", "mastb200_get_row_dofs",
+    "mastb200_residual_and_jacobian", "mastb200_res_l2_norm", "mastb200_sensitivity_sweep",
+    "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
+    "mastb200_get_stats", "mastb200_stream",
+]
+
+
+class MastB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"mast_b200 error {code}: {msg}")
+        self.code = code
+
+
+class Material(C.Structure):
+    _fields_ = [("E0", C.c_double), ("nu", C.c_double), ("alpha", C.c_double), ("rho_min", C.c_double),
+                ("penalty", C.c_double), ("nonlinear_strain", C.c_int32), ("k0", C.c_double),
+                ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32),
+                ("heat_source", C.c_double)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_tiles", C.c_int64), ("n_visits", C.c_int64), ("n_owned_nodes", C.c_int64),
+                ("n_elem", C.c_int64), ("kernel_launches", C.c_int64), ("last_sweep_ms", C.c_double),
+                ("last_main_kernel_ms", C.c_double), ("plan_bytes", C.c_int64), ("smem_bytes", C.c_int32),
+                ("threads_per_cta", C.c_int32), ("ctas", C.c_int32)]
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmast_b200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads libmast_b200.so (built in-tree by __graft_entry__.build()). Fails loudly if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise MastB200Error(-1, f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+    try:  # make sure the CUDA runtime torch ships is the one that gets resolved
+        import torch  # noqa: F401
+    except Exception:  # pragma: no cover
+        pass
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.mastb200_create.argtypes = [C.c_int, C.POINTER(vp)]
+    lib.mastb200_destroy.argtypes = [vp]
+    lib.mastb200_last_error.argtypes = [vp]
+    lib.mastb200_last_error.restype = C.c_char_p
+    lib.mastb200_version.restype = C.c_char_p
+    lib.mastb200_set_mesh.argtypes = [vp, i32, i64, i64, vp, vp, vp]
+    lib.mastb200_set_dof_map.argtypes = [vp, i32, vp, vp]
+    lib.mastb200_set_material.argtypes = [vp, C.POINTER(Material)]
+    lib.mastb200_set_side_pressure.argtypes = [vp, i64, vp, vp, vp]
+    lib.mastb200_set_temperature.argtypes = [vp, i32, vp, dbl, dbl]
+    lib.mastb200_set_density.argtypes = [vp, vp]
+    lib.mastb200_build_pattern.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.mastb200_get_pattern.argtypes = [vp, vp, vp]
+    lib.mastb200_get_row_dofs.argtypes = [vp, vp]
+    lib.mastb200_residual_and_jacobian.argtypes = [vp, vp, vp, vp]
+    lib.mastb200_res_l2_norm.argtypes = [vp, C.POINTER(dbl)]
+    lib.mastb200_sensitivity_sweep.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.mastb200_apply_dv_map_transpose.argtypes = [vp, vp, i64, vp, vp, vp, vp]
+    lib.mastb200_compliance.argtypes = [vp, vp, C.POINTER(dbl)]
+    lib.mastb200_compliance_derivative.argtypes = [vp, vp, vp]
+    lib.mastb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.mastb200_stream.argtypes = [vp]
+    lib.mastb200_stream.restype = vp
+    _LIB = lib
+    return lib
+
+
+def _ptr(a):
+    """void* of a numpy array, a torch tensor (host or CUDA), or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        assert a.is_contiguous()
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def _np(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    """One assembly context per GPU (``device=-1``: host-only planning context, no sweeps)."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        rc = self._lib.mastb200_create(int(device), C.byref(self._h))
+        if rc:
+            raise MastB200Error(rc, self._lib.mastb200_last_error(None).decode())
+        self.nv = 0
+        self.n_nodes = 0
+        self.n_rows = 0
+        self.nnz = 0
+        self._keep = {}
+
+    def close(self):
+        if self._h:
+            self._lib.mastb200_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise MastB200Error(rc, self._lib.mastb200_last_error(self._h).decode())
+
+    # ---- problem definition ----
+    def set_mesh(self, elem_type, xyz, conn, diag_elem=None):
+        xyz = _np(xyz, np.float64); conn = _np(conn, np.int32); diag_elem = _np(diag_elem, np.uint8)
+        self.n_nodes = xyz.shape[0]
+        self.n_elem = conn.shape[0]
+        self._ck(self._lib.mastb200_set_mesh(self._h, elem_type, conn.shape[0], xyz.shape[0], _ptr(xyz), _ptr(conn),
+                                             _ptr(diag_elem)))
+
+    def set_dof_map(self, nv, constrained=None, owned=None):
+        self.nv = nv
+        self._ck(self._lib.mastb200_set_dof_map(self._h, nv, _ptr(_np(constrained, np.uint8)),
+                                                _ptr(_np(owned, np.uint8))))
+
+    def set_material(self, **kw):
+        m = Material(E0=kw.get("E0", 72e9), nu=kw.get("nu", 0.33), alpha=kw.get("alpha", 0.0),
+                     rho_min=kw.get("rho_min", 0.0), penalty=kw.get("penalty", 1.0),
+                     nonlinear_strain=int(kw.get("nonlinear_strain", 0)), k0=kw.get("k0", 0.0),
+                     k_beta=kw.get("k_beta", 0.0), thickness=kw.get("thickness", 1.0),
+                     k_of_T=int(kw.get("k_of_T", 0)), heat_source=kw.get("heat_source", 0.0))
+        self._ck(self._lib.mastb200_set_material(self._h, C.byref(m)))
+
+    def set_side_pressure(self, elem, side, pressure):
+        elem = _np(elem, np.int32); side = _np(side, np.int32); pressure = _np(pressure, np.float64)
+        self._ck(self._lib.mastb200_set_side_pressure(self._h, len(elem), _ptr(elem), _ptr(side), _ptr(pressure)))
+
+    def set_temperature(self, enable, T_nodal=None, T_const=0.0, T_ref=0.0):
+        self._keep["T"] = T_nodal
+        self._ck(self._lib.mastb200_set_temperature(self._h, int(enable), _ptr(T_nodal), T_const, T_ref))
+
+    def set_density(self, rho):
+        self._keep["rho"] = rho  # a device tensor is used in place: keep it alive
+        self._ck(self._lib.mastb200_set_density(self._h, _ptr(rho)))
+
+    def build_pattern(self):
+        n_rows, nnz = C.c_int64(), C.c_int64()
+        self._ck(self._lib.mastb200_build_pattern(self._h, C.byref(n_rows), C.byref(nnz)))
+        self.n_rows, self.nnz = n_rows.value, nnz.value
+        return self.n_rows, self.nnz
+
+    def get_pattern(self, with_cols=True):
+        row_ptr = np.empty(self.n_rows + 1, np.int64)
+        col_idx = np.empty(self.nnz, np.int32) if with_cols else None
+        self._ck(self._lib.mastb200_get_pattern(self._h, _ptr(row_ptr), _ptr(col_idx)))
+        return row_ptr, col_idx
+
+    def get_row_dofs(self):
+        out = np.empty(self.n_rows, np.int64)
+        self._ck(self._lib.mastb200_get_row_dofs(self._h, _ptr(out)))
+        return out
+
+    # ---- sweeps (arrays: numpy = host buffers, torch CUDA tensors = device buffers used in place) ----
+    def residual_and_jacobian(self, X, R=None, J=None):
+        self._ck(self._lib.mastb200_residual_and_jacobian(self._h, _ptr(X), _ptr(R), _ptr(J)))
+
+    def res_l2_norm(self):
+        v = C.c_double()
+        self._ck(self._lib.mastb200_res_l2_norm(self._h, C.byref(v)))
+        return v.value
+
+    def sensitivity_sweep(self, X, adj, G, R=None, J=None):
+        self._ck(self._lib.mastb200_sensitivity_sweep(self._h, _ptr(X), _ptr(adj), _ptr(G), _ptr(R), _ptr(J)))
+
+    def apply_dv_map_transpose(self, G, dv_ptr, dv_node, dv_weight):
+        dv_ptr = _np(dv_ptr, np.int64); dv_node = _np(dv_node, np.int32); dv_weight = _np(dv_weight, np.float64)
+        sens = np.empty(len(dv_ptr) - 1, np.float64)
+        self._ck(self._lib.mastb200_apply_dv_map_transpose(self._h, _ptr(G), len(dv_ptr) - 1, _ptr(dv_ptr),
+                                                           _ptr(dv_node), _ptr(dv_weight), _ptr(sens)))
+        return sens
+
+    def compliance(self, X):
+        v = C.c_double()
+        self._ck(self._lib.mastb200_compliance(self._h, _ptr(X), C.byref(v)))
+        return v.value
+
+    def compliance_derivative(self, X, dq_dX):
+        self._ck(self._lib.mastb200_compliance_derivative(self._h, _ptr(X), _ptr(dq_dX)))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._lib.mastb200_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    @property
+    def stream(self):
+        return self._lib.mastb200_stream(self._h)

@@ -1,0 +1,664 @@
+// context.cu -- implementation of the C-ABI in include/mast_b200.h.
+//
+// Owns the device copies of mesh, dof map, plan and state; resolves host-or-device pointers; orders all
+// work on one CUDA stream.  There is no CPU compute path: without a usable CUDA device every sweep
+// entry point fails with MASTB200_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mast_b200.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "plan.h"
+
+using namespace mastb200;
+
+namespace {
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p) return cudaSuccess;
+    release();
+    if (count == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e == cudaSuccess) n = count;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = ensure(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+};
+
+bool is_device_ptr(const void* ptr) {
+  if (!ptr) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+const int H8_SIDE[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct mastb200_context {
+  int device = 0;
+  bool planning_only = false;  // device == -1: pattern/plan construction on the host only, no sweeps
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timed = false;
+  std::string err;
+  int sm_count = 0;
+
+  // mesh / dof map (host)
+  int32_t elem_type = 0, nn = 0, nv = 0;
+  int64_t n_elem = 0, n_nodes = 0;
+  std::vector<double> xyz;
+  std::vector<int32_t> conn;
+  std::vector<uint8_t> diag_elem, owned, cmask;
+  bool has_constraints = false, has_ghosts = false, has_diag = false;
+  mastb200_material mat{};
+  bool have_mesh = false, have_dofs = false, have_mat = false, have_plan = false;
+
+  Plan plan;
+  PlanLimits lim{};
+
+  // device: plan
+  DevBuf<TileDesc> d_tiles;
+  DevBuf<StepDesc> d_steps;
+  DevBuf<int32_t> d_tile_nodes, d_tile_acc_off, d_tile_nbr_cnt, d_visit_elem, d_node_row, d_n_adj, d_n_adj_diag, d_owned_nodes;
+  DevBuf<uint16_t> d_nbr_local, d_visit_ln;
+  DevBuf<uint8_t> d_visit_slot, d_cmask;
+  DevBuf<int64_t> d_nbr_ptr;
+  // device: mesh + state + staging for host pointers
+  DevBuf<double> d_xyz, d_X, d_adj, d_rho, d_T, d_R, d_J, d_G, d_dq, d_partial, d_scalar;
+  bool rho_set = false, T_nodal = false, thermal = false;
+  const double* rho_ext = nullptr;  // caller-owned device density
+  const double* T_ext = nullptr;
+  double T_const = 0., T_ref = 0.;
+  const double* last_R = nullptr;   // device pointer of the last residual
+  // face loads
+  std::vector<int32_t> fl_node, fl_ptr, fl_face_nodes;
+  std::vector<uint8_t> fl_k;
+  std::vector<double> fl_p;
+  DevBuf<int32_t> d_fl_node, d_fl_ptr, d_fl_face_nodes;
+  DevBuf<uint8_t> d_fl_k;
+  DevBuf<double> d_fl_p;
+  // dv map staging
+  DevBuf<int64_t> d_dv_ptr;
+  DevBuf<int32_t> d_dv_node;
+  DevBuf<double> d_dv_w, d_sens;
+
+  int64_t launches = 0;
+  int n_ctas = 0;
+  size_t smem = 0;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    err = buf;
+    return code;
+  }
+  int cuda_fail(cudaError_t e, const char* what) {
+    return fail(MASTB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+};
+
+#define CU(call)                                                   \
+  do {                                                             \
+    cudaError_t e_ = (call);                                       \
+    if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call);       \
+  } while (0)
+
+namespace {
+
+// device view of an input array: device pointers pass through, host pointers are copied into `stage`
+int resolve_in(mastb200_context* ctx, const double* ptr, size_t n, DevBuf<double>& stage, const double** out) {
+  if (!ptr) { *out = nullptr; return MASTB200_OK; }
+  if (is_device_ptr(ptr)) { *out = ptr; return MASTB200_OK; }
+  CU(stage.ensure(n));
+  CU(cudaMemcpyAsync(stage.p, ptr, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  *out = stage.p;
+  return MASTB200_OK;
+}
+int resolve_out(mastb200_context* ctx, double* ptr, size_t n, DevBuf<double>& stage, double** out) {
+  if (!ptr) { *out = nullptr; return MASTB200_OK; }
+  if (is_device_ptr(ptr)) { *out = ptr; return MASTB200_OK; }
+  CU(stage.ensure(n));
+  *out = stage.p;
+  return MASTB200_OK;
+}
+int finish_out(mastb200_context* ctx, double* ptr, size_t n, const double* dev) {
+  if (!ptr || ptr == dev) return MASTB200_OK;
+  CU(cudaMemcpyAsync(ptr, dev, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return MASTB200_OK;
+}
+
+int64_t plan_nnz(const mastb200_context* ctx) {
+  return ctx->plan.nbr_ptr[ctx->plan.n_owned] * int64_t(ctx->nv) * ctx->nv;
+}
+
+void fill_params(mastb200_context* ctx, SweepParams& p) {
+  std::memset(&p, 0, sizeof p);
+  p.tiles = ctx->d_tiles.p; p.n_tiles = (int32_t)ctx->plan.tiles.size();
+  p.steps = ctx->d_steps.p;
+  p.tile_nodes = ctx->d_tile_nodes.p; p.tile_acc_off = ctx->d_tile_acc_off.p; p.tile_nbr_cnt = ctx->d_tile_nbr_cnt.p;
+  p.nbr_local = ctx->d_nbr_local.p;
+  p.visit_elem = ctx->d_visit_elem.p; p.visit_ln = ctx->d_visit_ln.p; p.visit_slot = ctx->d_visit_slot.p;
+  p.nbr_ptr = ctx->d_nbr_ptr.p; p.node_row = ctx->d_node_row.p;
+  p.n_adj_elem = ctx->d_n_adj.p; p.n_adj_diag = ctx->d_n_adj_diag.p;
+  p.xyz = ctx->d_xyz.p;
+  p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+  const mastb200_material& m = ctx->mat;
+  p.E0 = m.E0;
+  // unit-modulus Lame constants written as the reference writes D (isotropic_material_property_card.cpp:512-528)
+  p.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu);
+  p.mu1 = 1. / 2. / (1. + m.nu);
+  p.rho_min = m.rho_min; p.penalty = m.penalty;
+  p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
+  p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
+  p.k0 = m.k0; p.k_beta = m.k_beta; p.thickness = m.thickness; p.heat_source = m.heat_source; p.k_of_T = m.k_of_T;
+  p.nv = ctx->nv;
+  p.thermal = ctx->thermal ? 1 : 0;
+  p.nonlinear = m.nonlinear_strain;
+  p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+  p.temperature = (ctx->thermal && ctx->T_nodal) ? (ctx->T_ext ? ctx->T_ext : ctx->d_T.p) : nullptr;
+  p.arena_doubles = ctx->lim.arena_doubles;
+  p.max_tile_nodes = ctx->lim.max_tile_nodes;
+}
+
+FaceLoadPlan face_plan(const mastb200_context* ctx) {
+  FaceLoadPlan fp;
+  fp.n_loaded_nodes = (int32_t)ctx->fl_node.size();
+  fp.node = ctx->d_fl_node.p; fp.ptr = ctx->d_fl_ptr.p; fp.face_nodes = ctx->d_fl_face_nodes.p;
+  fp.face_k = ctx->d_fl_k.p; fp.pressure = ctx->d_fl_p.p;
+  return fp;
+}
+
+int check_ready(mastb200_context* ctx) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (ctx->planning_only)
+    return ctx->fail(MASTB200_ERR_CUDA, "planning-only context (device -1): sweeps need a B200; there is no CPU fallback");
+  if (!ctx->have_plan) return ctx->fail(MASTB200_ERR_ARG, "call set_mesh, set_dof_map and build_pattern first");
+  if (!ctx->have_mat) return ctx->fail(MASTB200_ERR_ARG, "call set_material first");
+  return MASTB200_OK;
+}
+
+// the common sweep: any of R, J, G may be null
+int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G, double* R, double* J) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!X) return ctx->fail(MASTB200_ERR_ARG, "X is NULL");
+  if (G && !adj) return ctx->fail(MASTB200_ERR_ARG, "adjoint vector is NULL");
+  if (ctx->elem_type != MASTB200_HEX8)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "element type %d has no device sweep yet", ctx->elem_type);
+  if (ctx->mat.nonlinear_strain)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain has no device sweep yet");
+  if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
+  if (G && ctx->thermal)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED,
+                     "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const size_t nnz = (size_t)plan_nnz(ctx);
+  SweepParams p;
+  fill_params(ctx, p);
+  const double *dX = nullptr, *dadj = nullptr;
+  double *dR = nullptr, *dJ = nullptr, *dG = nullptr;
+  if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if (G && (rc = resolve_in(ctx, adj, n_dof, ctx->d_adj, &dadj))) return rc;
+  if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
+  if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
+  if ((rc = resolve_out(ctx, G, (size_t)ctx->n_nodes, ctx->d_G, &dG))) return rc;
+  p.X = dX; p.adj = dadj; p.R = dR; p.J = dJ; p.G = dG;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (ctx->has_ghosts) {
+    if (dR) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
+    if (dG) CU(cudaMemsetAsync(dG, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
+  }
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_hex8_sweep(p, ctx->n_ctas, ctx->stream));
+  ctx->launches++;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (dR && !ctx->fl_node.empty()) {
+    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, p.cmask, ctx->nv, dR, nullptr, nullptr, nullptr, ctx->stream));
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->last_R = dR;
+  if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
+  if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
+  if ((rc = finish_out(ctx, G, (size_t)ctx->n_nodes, dG))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* mastb200_version(void) { return "mast_b200 0.1 (sm_100a)"; }
+
+int mastb200_create(int device, mastb200_context** out) {
+  if (!out) return MASTB200_ERR_ARG;
+  *out = nullptr;
+  if (device == -1) {  // host planning context: sparsity pattern and assembly plan only
+    mastb200_context* ctx = new mastb200_context();
+    ctx->device = -1;
+    ctx->planning_only = true;
+    ctx->sm_count = 148;
+    *out = ctx;
+    return MASTB200_OK;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+    cudaGetLastError();
+    return MASTB200_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return MASTB200_ERR_ARG; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MASTB200_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "device is not sm_100 (Blackwell B200); this library carries sm_100a code only";
+    return MASTB200_ERR_CUDA;
+  }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return MASTB200_ERR_CUDA; }
+  mastb200_context* ctx = new mastb200_context();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete ctx;
+    return MASTB200_ERR_CUDA;
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  *out = ctx;
+  return MASTB200_OK;
+}
+
+int mastb200_destroy(mastb200_context* ctx) {
+  if (!ctx) return MASTB200_OK;
+  if (ctx->planning_only) { delete ctx; return MASTB200_OK; }
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  delete ctx;
+  return MASTB200_OK;
+}
+
+const char* mastb200_last_error(const mastb200_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void* mastb200_stream(const mastb200_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int mastb200_set_mesh(mastb200_context* ctx, int32_t elem_type, int64_t n_elem, int64_t n_nodes, const double* xyz,
+                      const int32_t* conn, const uint8_t* diag_elem) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  int nn = 0;
+  switch (elem_type) {
+    case MASTB200_HEX8: nn = 8; break;
+    case MASTB200_HEX27: nn = 27; break;
+    case MASTB200_QUAD4: nn = 4; break;
+    default: return ctx->fail(MASTB200_ERR_ARG, "unknown element type %d", elem_type);
+  }
+  if (n_elem <= 0 || n_nodes <= 0 || !xyz || !conn) return ctx->fail(MASTB200_ERR_ARG, "empty mesh or NULL arrays");
+  if (!ctx->planning_only) CU(cudaSetDevice(ctx->device));
+  ctx->elem_type = elem_type; ctx->nn = nn; ctx->n_elem = n_elem; ctx->n_nodes = n_nodes;
+  ctx->xyz.assign(xyz, xyz + n_nodes * 3);
+  ctx->conn.assign(conn, conn + n_elem * nn);
+  ctx->has_diag = false;
+  if (diag_elem) {
+    ctx->diag_elem.assign(diag_elem, diag_elem + n_elem);
+    for (uint8_t d : ctx->diag_elem) ctx->has_diag = ctx->has_diag || d;
+  } else {
+    ctx->diag_elem.clear();
+  }
+  if (!ctx->planning_only) CU(ctx->d_xyz.upload(ctx->xyz, ctx->stream));
+  ctx->have_mesh = true; ctx->have_plan = false;
+  ctx->fl_node.clear();
+  return MASTB200_OK;
+}
+
+int mastb200_set_dof_map(mastb200_context* ctx, int32_t nv, const uint8_t* constrained, const uint8_t* owned) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+  if (nv != 1 && nv != 3 && nv != 6) return ctx->fail(MASTB200_ERR_ARG, "nv must be 1, 3 or 6");
+  if (!ctx->planning_only) CU(cudaSetDevice(ctx->device));
+  ctx->nv = nv;
+  ctx->cmask.assign(ctx->n_nodes, 0);
+  ctx->has_constraints = false;
+  if (constrained)
+    for (int64_t n = 0; n < ctx->n_nodes; ++n) {
+      unsigned m = 0;
+      for (int v = 0; v < nv; ++v)
+        if (constrained[n * nv + v]) m |= 1u << v;
+      ctx->cmask[n] = (uint8_t)m;
+      ctx->has_constraints = ctx->has_constraints || m;
+    }
+  ctx->has_ghosts = false;
+  if (owned) {
+    ctx->owned.assign(owned, owned + ctx->n_nodes);
+    for (uint8_t o : ctx->owned) ctx->has_ghosts = ctx->has_ghosts || !o;
+  } else {
+    ctx->owned.clear();
+  }
+  if (!ctx->planning_only) CU(ctx->d_cmask.upload(ctx->cmask, ctx->stream));
+  ctx->have_dofs = true; ctx->have_plan = false;
+  return MASTB200_OK;
+}
+
+int mastb200_set_material(mastb200_context* ctx, const mastb200_material* mat) {
+  if (!ctx || !mat) return MASTB200_ERR_ARG;
+  ctx->mat = *mat;
+  ctx->have_mat = true;
+  return MASTB200_OK;
+}
+
+int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                               const double* pressure) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+  ctx->fl_node.clear(); ctx->fl_ptr.clear(); ctx->fl_face_nodes.clear(); ctx->fl_k.clear(); ctx->fl_p.clear();
+  if (n == 0) return MASTB200_OK;
+  if (ctx->elem_type != MASTB200_HEX8) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "side pressure: HEX8 only for now");
+  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
+  CU(cudaSetDevice(ctx->device));
+  // entries ordered by (element, side): the order in which the reference's element loop meets the loads
+  std::vector<int64_t> order(n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (elem[i] < 0 || elem[i] >= ctx->n_elem || side[i] < 0 || side[i] > 5) return ctx->fail(MASTB200_ERR_ARG, "bad side load %lld", (long long)i);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return elem[a] != elem[b] ? elem[a] < elem[b] : side[a] < side[b];
+  });
+  struct Ent { int32_t node; int64_t seq; int32_t fn[4]; uint8_t k; double p; };
+  std::vector<Ent> ents;
+  ents.reserve(n * 4);
+  for (int64_t s = 0; s < n; ++s) {
+    const int64_t i = order[s];
+    Ent e;
+    for (int k = 0; k < 4; ++k) e.fn[k] = ctx->conn[(int64_t)elem[i] * 8 + H8_SIDE[side[i]][k]];
+    e.p = pressure[i];
+    for (int k = 0; k < 4; ++k) { e.node = e.fn[k]; e.k = (uint8_t)k; e.seq = s; ents.push_back(e); }
+  }
+  std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.node < b.node; });
+  for (size_t i = 0; i < ents.size(); ++i) {
+    if (i == 0 || ents[i].node != ents[i - 1].node) {
+      ctx->fl_node.push_back(ents[i].node);
+      ctx->fl_ptr.push_back((int32_t)i);
+    }
+    for (int k = 0; k < 4; ++k) ctx->fl_face_nodes.push_back(ents[i].fn[k]);
+    ctx->fl_k.push_back(ents[i].k);
+    ctx->fl_p.push_back(ents[i].p);
+  }
+  ctx->fl_ptr.push_back((int32_t)ents.size());
+  CU(ctx->d_fl_node.upload(ctx->fl_node, ctx->stream));
+  CU(ctx->d_fl_ptr.upload(ctx->fl_ptr, ctx->stream));
+  CU(ctx->d_fl_face_nodes.upload(ctx->fl_face_nodes, ctx->stream));
+  CU(ctx->d_fl_k.upload(ctx->fl_k, ctx->stream));
+  CU(ctx->d_fl_p.upload(ctx->fl_p, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_set_temperature(mastb200_context* ctx, int32_t enable, const double* T_nodal, double T_const, double T_ref) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
+  CU(cudaSetDevice(ctx->device));
+  ctx->thermal = enable != 0;
+  ctx->T_const = T_const; ctx->T_ref = T_ref;
+  ctx->T_nodal = false; ctx->T_ext = nullptr;
+  if (enable && T_nodal) {
+    ctx->T_nodal = true;
+    if (is_device_ptr(T_nodal)) ctx->T_ext = T_nodal;
+    else {
+      CU(ctx->d_T.ensure(ctx->n_nodes));
+      CU(cudaMemcpyAsync(ctx->d_T.p, T_nodal, ctx->n_nodes * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  return MASTB200_OK;
+}
+
+int mastb200_set_density(mastb200_context* ctx, const double* rho) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
+  CU(cudaSetDevice(ctx->device));
+  ctx->rho_set = rho != nullptr; ctx->rho_ext = nullptr;
+  if (!rho) return MASTB200_OK;
+  if (is_device_ptr(rho)) ctx->rho_ext = rho;
+  else {
+    CU(ctx->d_rho.ensure(ctx->n_nodes));
+    CU(cudaMemcpyAsync(ctx->d_rho.p, rho, ctx->n_nodes * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return MASTB200_OK;
+}
+
+int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh || !ctx->have_dofs) return ctx->fail(MASTB200_ERR_ARG, "set_mesh and set_dof_map first");
+  const bool solid = ctx->elem_type != MASTB200_QUAD4;
+  // shared-memory budget of the sweep kernel: whatever the staging areas leave of 227 KB goes to the accumulators
+  int max_optin = 232448;  // sm_100: 227 KB opt-in per CTA
+  if (!ctx->planning_only) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+  }
+  const size_t fixed = hex8_sweep_smem_bytes(0);
+  if ((size_t)max_optin <= fixed + 4096) return ctx->fail(MASTB200_ERR_CUDA, "device shared memory too small");
+  ctx->lim.arena_doubles = (int32_t)((max_optin - fixed) / 8);
+  ctx->lim.max_tile_nodes = kMaxTileNodes;
+  ctx->lim.acc_per_block = solid ? 9 : 1;
+  ctx->lim.acc_per_node = kAccPerNode;
+  ctx->smem = hex8_sweep_smem_bytes(ctx->lim.arena_doubles);
+  const std::string e = build_plan(ctx->nn, ctx->n_nodes, ctx->n_elem, ctx->xyz.data(), ctx->conn.data(),
+                                   ctx->owned.empty() ? nullptr : ctx->owned.data(),
+                                   ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), ctx->lim, ctx->plan);
+  if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+  Plan& P = ctx->plan;
+  if (ctx->planning_only) {
+    ctx->n_ctas = (int)std::min<int64_t>((int64_t)P.tiles.size(), ctx->sm_count);
+    ctx->have_plan = true;
+    if (n_rows) *n_rows = P.n_owned * ctx->nv;
+    if (nnz) *nnz = plan_nnz(ctx);
+    return MASTB200_OK;
+  }
+  CU(ctx->d_tiles.upload(P.tiles, ctx->stream));
+  CU(ctx->d_steps.upload(P.steps, ctx->stream));
+  CU(ctx->d_tile_nodes.upload(P.tile_nodes, ctx->stream));
+  CU(ctx->d_tile_acc_off.upload(P.tile_acc_off, ctx->stream));
+  CU(ctx->d_tile_nbr_cnt.upload(P.tile_nbr_cnt, ctx->stream));
+  CU(ctx->d_nbr_local.upload(P.nbr_local, ctx->stream));
+  CU(ctx->d_visit_elem.upload(P.visit_elem, ctx->stream));
+  CU(ctx->d_visit_ln.upload(P.visit_ln, ctx->stream));
+  CU(ctx->d_visit_slot.upload(P.visit_slot, ctx->stream));
+  CU(ctx->d_nbr_ptr.upload(P.nbr_ptr, ctx->stream));
+  CU(ctx->d_node_row.upload(P.node_row, ctx->stream));
+  CU(ctx->d_n_adj.upload(P.n_adj_elem, ctx->stream));
+  CU(ctx->d_n_adj_diag.upload(P.n_adj_diag_elem, ctx->stream));
+  CU(ctx->d_owned_nodes.upload(P.owned_nodes, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->n_ctas = (int)std::min<int64_t>((int64_t)P.tiles.size(), ctx->sm_count);
+  ctx->have_plan = true;
+  if (n_rows) *n_rows = P.n_owned * ctx->nv;
+  if (nnz) *nnz = plan_nnz(ctx);
+  return MASTB200_OK;
+}
+
+int mastb200_get_pattern(const mastb200_context* ctx, int64_t* row_ptr, int32_t* col_idx) {
+  if (!ctx || !ctx->have_plan || !row_ptr) return MASTB200_ERR_ARG;
+  const Plan& P = ctx->plan;
+  const int nv = ctx->nv;
+  int64_t k = 0;
+  row_ptr[0] = 0;
+  for (int64_t r = 0; r < P.n_owned; ++r) {
+    const int64_t b = P.nbr_ptr[r], e = P.nbr_ptr[r + 1];
+    for (int v = 0; v < nv; ++v) {
+      if (col_idx)
+        for (int64_t j = b; j < e; ++j)
+          for (int w = 0; w < nv; ++w) col_idx[k++] = P.nbr[j] * nv + w;
+      else
+        k += (e - b) * nv;
+      row_ptr[r * nv + v + 1] = k;
+    }
+  }
+  return MASTB200_OK;
+}
+
+int mastb200_get_row_dofs(const mastb200_context* ctx, int64_t* row_dof) {
+  if (!ctx || !ctx->have_plan || !row_dof) return MASTB200_ERR_ARG;
+  for (int64_t r = 0; r < ctx->plan.n_owned; ++r)
+    for (int v = 0; v < ctx->nv; ++v) row_dof[r * ctx->nv + v] = (int64_t)ctx->plan.owned_nodes[r] * ctx->nv + v;
+  return MASTB200_OK;
+}
+
+int mastb200_residual_and_jacobian(mastb200_context* ctx, const double* X, double* R, double* J_vals) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (int rc0 = check_ready(ctx)) return rc0;
+  CU(cudaSetDevice(ctx->device));
+  return run_sweep(ctx, X, nullptr, nullptr, R, J_vals);
+}
+
+int mastb200_sensitivity_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G, double* R,
+                               double* J_vals) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!G) return ctx->fail(MASTB200_ERR_ARG, "G is NULL");
+  if (int rc0 = check_ready(ctx)) return rc0;
+  CU(cudaSetDevice(ctx->device));
+  return run_sweep(ctx, X, adj, G, R, J_vals);
+}
+
+int mastb200_res_l2_norm(mastb200_context* ctx, double* norm) {
+  if (!ctx || !norm) return MASTB200_ERR_ARG;
+  if (int rc0 = check_ready(ctx)) return rc0;
+  if (!ctx->last_R) return ctx->fail(MASTB200_ERR_ARG, "no residual has been assembled");
+  CU(cudaSetDevice(ctx->device));
+  const int nb = 1024;
+  CU(ctx->d_partial.ensure(4096));
+  CU(ctx->d_scalar.ensure(8));
+  CU(launch_sumsq_owned(ctx->last_R, ctx->d_owned_nodes.p, ctx->plan.n_owned, ctx->nv, ctx->d_partial.p, nb, ctx->stream));
+  CU(launch_reduce_partials(ctx->d_partial.p, nb, ctx->d_scalar.p, ctx->stream));
+  ctx->launches += 2;
+  double ss = 0.;
+  CU(cudaMemcpyAsync(&ss, ctx->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *norm = std::sqrt(ss);
+  return MASTB200_OK;
+}
+
+int mastb200_apply_dv_map_transpose(mastb200_context* ctx, const double* G, int64_t n_dv, const int64_t* dv_ptr,
+                                    const int32_t* dv_node, const double* dv_weight, double* sens) {
+  if (!ctx || !G || !dv_ptr || !sens || n_dv < 0) return MASTB200_ERR_ARG;
+  if (int rc0 = check_ready(ctx)) return rc0;
+  CU(cudaSetDevice(ctx->device));
+  if (n_dv == 0) return MASTB200_OK;
+  const int64_t nnzw = dv_ptr[n_dv];
+  const double* dG = nullptr;
+  int rc = resolve_in(ctx, G, (size_t)ctx->n_nodes, ctx->d_G, &dG);
+  if (rc) return rc;
+  CU(ctx->d_dv_ptr.ensure(n_dv + 1));
+  CU(ctx->d_dv_node.ensure(nnzw));
+  CU(ctx->d_dv_w.ensure(nnzw));
+  CU(ctx->d_sens.ensure(n_dv));
+  CU(cudaMemcpyAsync(ctx->d_dv_ptr.p, dv_ptr, (n_dv + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_dv_node.p, dv_node, nnzw * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_dv_w.p, dv_weight, nnzw * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_dv_map_transpose(dG, n_dv, ctx->d_dv_ptr.p, ctx->d_dv_node.p, ctx->d_dv_w.p, ctx->d_sens.p, ctx->stream));
+  ctx->launches++;
+  CU(cudaMemcpyAsync(sens, ctx->d_sens.p, n_dv * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_compliance(mastb200_context* ctx, const double* X, double* q) {
+  if (!ctx || !q || !X) return MASTB200_ERR_ARG;
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->thermal) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance with a thermoelastic load is not on the device path yet");
+  CU(cudaSetDevice(ctx->device));
+  *q = 0.;
+  if (ctx->fl_node.empty()) return MASTB200_OK;
+  const double* dX = nullptr;
+  if ((rc = resolve_in(ctx, X, size_t(ctx->n_nodes) * ctx->nv, ctx->d_X, &dX))) return rc;
+  const int nb = face_loads_blocks((int)ctx->fl_node.size());
+  CU(ctx->d_partial.ensure(std::max(nb, 4096)));
+  CU(ctx->d_scalar.ensure(8));
+  CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, dX, nullptr, ctx->nv, nullptr, nullptr, ctx->d_partial.p, nullptr, ctx->stream));
+  CU(launch_reduce_partials(ctx->d_partial.p, nb, ctx->d_scalar.p, ctx->stream));
+  ctx->launches += 2;
+  CU(cudaMemcpyAsync(q, ctx->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, double* dq_dX) {
+  if (!ctx || !dq_dX) return MASTB200_ERR_ARG;
+  (void)X;  // linear in X: -f_ext does not depend on the state for non-follower pressure loads
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->thermal) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance with a thermoelastic load is not on the device path yet");
+  CU(cudaSetDevice(ctx->device));
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  double* d = nullptr;
+  if ((rc = resolve_out(ctx, dq_dX, n_dof, ctx->d_dq, &d))) return rc;
+  CU(cudaMemsetAsync(d, 0, n_dof * sizeof(double), ctx->stream));
+  if (!ctx->fl_node.empty()) {
+    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, ctx->has_constraints ? ctx->d_cmask.p : nullptr, ctx->nv,
+                         nullptr, d, nullptr, nullptr, ctx->stream));
+    ctx->launches++;
+  }
+  if ((rc = finish_out(ctx, dq_dX, n_dof, d))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
+  if (!ctx || !s) return MASTB200_ERR_ARG;
+  std::memset(s, 0, sizeof *s);
+  s->n_tiles = (int64_t)ctx->plan.tiles.size();
+  s->n_visits = ctx->plan.n_visits();
+  s->n_owned_nodes = ctx->plan.n_owned;
+  s->n_elem = ctx->n_elem;
+  s->kernel_launches = ctx->launches;
+  s->plan_bytes = ctx->plan.bytes();
+  s->smem_bytes = (int32_t)ctx->smem;
+  s->threads_per_cta = hex8_sweep_threads();
+  s->ctas = ctx->n_ctas;
+  if (ctx->timed) {
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a;
+    if (cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]) == cudaSuccess) s->last_main_kernel_ms = b;
+  }
+  return MASTB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1167 @@
+// mast_oracle.cpp -- CPU ORACLE (test infrastructure only; see mast_oracle.h for the contract).
+//
+// A scalar, dynamic-size restatement of the reference's element-assembly + sensitivity path.
+// Loop and summation orders follow the cited reference code so that the oracle is the closest
+// thing to "MAST on one MPI rank" that can be built without libMesh/PETSc/Eigen:
+//   * element dof order is variable-major (src/numerics/fem_operator_matrix.h:277-296)
+//   * quadrature points ascending inside an element, elements in id order into each CSR entry
+//     (src/base/nonlinear_implicit_assembly.cpp:111-186)
+// Paths in comments are relative to /root/reference.
+#include "mast_oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <set>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// tiny dense helpers (stand-ins for Eigen RealMatrixX/RealVectorX, row-major, plain loops)
+// ---------------------------------------------------------------------------------------------
+struct Mat {
+  int r = 0, c = 0;
+  std::vector<double> a;
+  Mat() {}
+  Mat(int r_, int c_) : r(r_), c(c_), a(size_t(r_) * c_, 0.0) {}
+  double& operator()(int i, int j) { return a[size_t(i) * c + j]; }
+  double operator()(int i, int j) const { return a[size_t(i) * c + j]; }
+  void zero() { std::fill(a.begin(), a.end(), 0.0); }
+  void resize(int r_, int c_) { r = r_; c = c_; a.assign(size_t(r_) * c_, 0.0); }
+};
+typedef std::vector<double> Vec;
+
+static Mat matmul(const Mat& A, const Mat& B) {  // C = A*B
+  Mat C(A.r, B.c);
+  for (int i = 0; i < A.r; ++i)
+    for (int j = 0; j < B.c; ++j) {
+      double s = 0.;
+      for (int k = 0; k < A.c; ++k) s += A(i, k) * B(k, j);
+      C(i, j) = s;
+    }
+  return C;
+}
+static Mat matmul_tn(const Mat& A, const Mat& B) {  // C = A^T * B
+  Mat C(A.c, B.c);
+  for (int i = 0; i < A.c; ++i)
+    for (int j = 0; j < B.c; ++j) {
+      double s = 0.;
+      for (int k = 0; k < A.r; ++k) s += A(k, i) * B(k, j);
+      C(i, j) = s;
+    }
+  return C;
+}
+static Vec matvec(const Mat& A, const Vec& x) {
+  Vec y(A.r, 0.);
+  for (int i = 0; i < A.r; ++i) {
+    double s = 0.;
+    for (int k = 0; k < A.c; ++k) s += A(i, k) * x[k];
+    y[i] = s;
+  }
+  return y;
+}
+static Vec matvec_t(const Mat& A, const Vec& x) {  // A^T x
+  Vec y(A.c, 0.);
+  for (int i = 0; i < A.c; ++i) {
+    double s = 0.;
+    for (int k = 0; k < A.r; ++k) s += A(k, i) * x[k];
+    y[i] = s;
+  }
+  return y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FEMOperatorMatrix  (src/numerics/fem_operator_matrix.h:33-467)
+// Block-sparse operator: rows = interpolated variables, columns = (discrete var, dof) pairs,
+// column index j*n_dofs_per_var+k.  Each product below keeps the reference's loop nest
+// (interpolated var outer, discrete var next, then dof) because that fixes the summation order.
+// ---------------------------------------------------------------------------------------------
+class OperatorMatrix {
+ public:
+  void reinit(int n_interp, int n_disc, int n_dofs) {  // fem_operator_matrix.h:207-221
+    ni_ = n_interp; nd_ = n_disc; nk_ = n_dofs;
+    has_.assign(size_t(ni_) * nd_, 0);
+    blk_.assign(size_t(ni_) * nd_ * nk_, 0.);
+  }
+  void reinit_diag(int n_vars, const Vec& shape) {  // fem_operator_matrix.h:253-272
+    reinit(n_vars, n_vars, int(shape.size()));
+    for (int i = 0; i < n_vars; ++i) set_shape_function(i, i, shape);
+  }
+  void set_shape_function(int interp, int disc, const Vec& shape) {  // :225-249
+    has_[size_t(disc) * ni_ + interp] = 1;
+    std::copy(shape.begin(), shape.end(), blk_.begin() + (size_t(disc) * ni_ + interp) * nk_);
+  }
+  int m() const { return ni_; }
+  int n() const { return nd_ * nk_; }
+
+  void vector_mult(Vec& res, const Vec& v) const {  // :276-296
+    res.assign(ni_, 0.);
+    for (int i = 0; i < ni_; ++i)
+      for (int j = 0; j < nd_; ++j)
+        if (has(i, j)) {
+          const double* s = blk(i, j);
+          for (int k = 0; k < nk_; ++k) res[i] += s[k] * v[j * nk_ + k];
+        }
+  }
+  void vector_mult_transpose(Vec& res, const Vec& v) const {  // :299-319
+    res.assign(n(), 0.);
+    for (int i = 0; i < ni_; ++i)
+      for (int j = 0; j < nd_; ++j)
+        if (has(i, j)) {
+          const double* s = blk(i, j);
+          for (int k = 0; k < nk_; ++k) res[j * nk_ + k] += s[k] * v[i];
+        }
+  }
+  void right_multiply(Mat& r, const Mat& mm) const {  // r = B * m   :323-346
+    r.resize(ni_, mm.c);
+    for (int i = 0; i < ni_; ++i)
+      for (int j = 0; j < nd_; ++j)
+        if (has(i, j)) {
+          const double* s = blk(i, j);
+          for (int l = 0; l < mm.c; ++l)
+            for (int k = 0; k < nk_; ++k) r(i, l) += s[k] * mm(j * nk_ + k, l);
+        }
+  }
+  void right_multiply_transpose(Mat& r, const Mat& mm) const {  // r = B^T * m   :351-374
+    r.resize(n(), mm.c);
+    for (int i = 0; i < ni_; ++i)
+      for (int j = 0; j < nd_; ++j)
+        if (has(i, j)) {
+          const double* s = blk(i, j);
+          for (int l = 0; l < mm.c; ++l)
+            for (int k = 0; k < nk_; ++k) r(j * nk_ + k, l) += s[k] * mm(i, l);
+        }
+  }
+  void right_multiply_transpose(Mat& r, const OperatorMatrix& o) const {  // r = B^T * O   :378-406
+    r.resize(n(), o.n());
+    for (int i = 0; i < nd_; ++i)
+      for (int j = 0; j < o.nd_; ++j)
+        for (int k = 0; k < ni_; ++k)
+          if (has(k, i) && o.has(k, j)) {
+            const double *n1 = blk(k, i), *n2 = o.blk(k, j);
+            for (int a = 0; a < nk_; ++a)
+              for (int b = 0; b < o.nk_; ++b) r(i * nk_ + a, j * o.nk_ + b) += n1[a] * n2[b];
+          }
+  }
+  void left_multiply(Mat& r, const Mat& mm) const {  // r = m * B   :411-434
+    r.resize(mm.r, n());
+    for (int i = 0; i < ni_; ++i)
+      for (int j = 0; j < nd_; ++j)
+        if (has(i, j)) {
+          const double* s = blk(i, j);
+          for (int l = 0; l < mm.r; ++l)
+            for (int k = 0; k < nk_; ++k) r(l, j * nk_ + k) += s[k] * mm(l, i);
+        }
+  }
+
+ private:
+  bool has(int interp, int disc) const { return has_[size_t(disc) * ni_ + interp] != 0; }
+  const double* blk(int interp, int disc) const { return &blk_[(size_t(disc) * ni_ + interp) * nk_]; }
+  int ni_ = 0, nd_ = 0, nk_ = 0;
+  std::vector<char> has_;
+  Vec blk_;
+};
+
+// ---------------------------------------------------------------------------------------------
+// libMesh FE restatement (un-vendored dependency; libMesh 1.5.1 per .travis.yml).
+// Lagrange shape functions on [-1,1]^d with libMesh node ordering, Gauss tensor rules with the
+// default order 2p+1 (fe_base.cpp:103-105 -> FEType::default_quadrature_rule), i fastest.
+// ---------------------------------------------------------------------------------------------
+static const double GP2[2] = {-0.57735026918962576451, 0.57735026918962576451};
+static const double GW2[2] = {1., 1.};
+static const double GP3[3] = {-0.77459666924148337704, 0., 0.77459666924148337704};
+static const double GW3[3] = {5. / 9., 8. / 9., 5. / 9.};
+
+// 1D Lagrange: linear idx 0 -> node at -1, 1 -> node at +1; quadratic adds idx 2 -> node at 0
+static double lag1(int order, int idx, double x) {
+  if (order == 1) return idx == 0 ? 0.5 * (1. - x) : 0.5 * (1. + x);
+  switch (idx) {
+    case 0: return 0.5 * x * (x - 1.);
+    case 1: return 0.5 * x * (x + 1.);
+    default: return (1. - x * x);
+  }
+}
+static double dlag1(int order, int idx, double x) {
+  if (order == 1) return idx == 0 ? -0.5 : 0.5;
+  switch (idx) {
+    case 0: return x - 0.5;
+    case 1: return x + 0.5;
+    default: return -2. * x;
+  }
+}
+// tensor index of each node along xi/eta/zeta
+static const int H8_I[8] = {0, 1, 1, 0, 0, 1, 1, 0};
+static const int H8_J[8] = {0, 0, 1, 1, 0, 0, 1, 1};
+static const int H8_K[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+static const int H27_I[27] = {0, 1, 1, 0, 0, 1, 1, 0, 2, 1, 2, 0, 0, 1, 1, 0, 2, 1, 2, 0, 2, 2, 1, 2, 0, 2, 2};
+static const int H27_J[27] = {0, 0, 1, 1, 0, 0, 1, 1, 0, 2, 1, 2, 0, 0, 1, 1, 0, 2, 1, 2, 2, 0, 2, 1, 2, 2, 2};
+static const int H27_K[27] = {0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0, 2, 2, 2, 2, 1, 1, 1, 1, 0, 2, 2, 2, 2, 1, 2};
+static const int Q4_I[4] = {0, 1, 1, 0};
+static const int Q4_J[4] = {0, 0, 1, 1};
+static const int Q9_I[9] = {0, 1, 1, 0, 2, 1, 2, 0, 2};
+static const int Q9_J[9] = {0, 0, 1, 1, 0, 2, 1, 2, 2};
+// libMesh side -> element node maps (outward-normal ordering)
+static const int H8_SIDE[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+static const int H27_SIDE[6][9] = {{0, 3, 2, 1, 11, 10, 9, 8, 20},  {0, 1, 5, 4, 8, 13, 16, 12, 21},
+                                   {1, 2, 6, 5, 9, 14, 17, 13, 22}, {2, 3, 7, 6, 10, 15, 18, 14, 23},
+                                   {3, 0, 4, 7, 11, 12, 19, 15, 24}, {4, 5, 6, 7, 16, 17, 18, 19, 25}};
+
+struct ElemInfo {
+  int nn, dim, order, n1d, nq;
+};
+static ElemInfo elem_info(int type) {
+  switch (type) {
+    case ORACLE_HEX8: return {8, 3, 1, 2, 8};
+    case ORACLE_HEX27: return {27, 3, 2, 3, 27};
+    case ORACLE_QUAD4: return {4, 2, 1, 2, 4};
+  }
+  return {0, 0, 0, 0, 0};
+}
+
+// what MAST::FEBase exposes after init (fe_base.cpp:64-131): phi, dphi (physical), JxW, xyz
+struct FE {
+  int nn = 0, nq = 0, dim = 0;
+  std::vector<double> phi;   // [a][qp]
+  std::vector<double> dphi;  // [a][qp][3]
+  std::vector<double> JxW;   // [qp]
+  std::vector<double> xyz;   // [qp][3]
+  std::vector<double> normal;  // side FE only: [qp][3]
+  double N(int a, int q) const { return phi[size_t(a) * nq + q]; }
+  double dN(int a, int q, int d) const { return dphi[(size_t(a) * nq + q) * 3 + d]; }
+};
+
+static void fe_init(int type, const double* X /*[nn][3]*/, FE& fe) {
+  const ElemInfo ei = elem_info(type);
+  fe.nn = ei.nn; fe.nq = ei.nq; fe.dim = ei.dim;
+  fe.phi.assign(size_t(ei.nn) * ei.nq, 0.);
+  fe.dphi.assign(size_t(ei.nn) * ei.nq * 3, 0.);
+  fe.JxW.assign(ei.nq, 0.);
+  fe.xyz.assign(size_t(ei.nq) * 3, 0.);
+  const double* gp = ei.n1d == 2 ? GP2 : GP3;
+  const double* gw = ei.n1d == 2 ? GW2 : GW3;
+  const int *I, *J, *K = nullptr;
+  if (type == ORACLE_HEX8) { I = H8_I; J = H8_J; K = H8_K; }
+  else if (type == ORACLE_HEX27) { I = H27_I; J = H27_J; K = H27_K; }
+  else { I = Q4_I; J = Q4_J; }
+  std::vector<double> dref(size_t(ei.nn) * 3);
+  int q = 0;
+  const int nk = ei.dim == 3 ? ei.n1d : 1;
+  for (int kq = 0; kq < nk; ++kq)
+    for (int jq = 0; jq < ei.n1d; ++jq)
+      for (int iq = 0; iq < ei.n1d; ++iq, ++q) {
+        const double xi = gp[iq], eta = gp[jq], zeta = ei.dim == 3 ? gp[kq] : 0.;
+        const double w = gw[iq] * gw[jq] * (ei.dim == 3 ? gw[kq] : 1.);
+        double Jm[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // Jm[r][c] = d x_c / d xi_r
+        double pt[3] = {0, 0, 0};
+        for (int a = 0; a < ei.nn; ++a) {
+          const double li = lag1(ei.order, I[a], xi), lj = lag1(ei.order, J[a], eta);
+          const double lk = ei.dim == 3 ? lag1(ei.order, K[a], zeta) : 1.;
+          const double N = li * lj * lk;
+          fe.phi[size_t(a) * ei.nq + q] = N;
+          double* d = &dref[size_t(a) * 3];
+          d[0] = dlag1(ei.order, I[a], xi) * lj * lk;
+          d[1] = li * dlag1(ei.order, J[a], eta) * lk;
+          d[2] = ei.dim == 3 ? li * lj * dlag1(ei.order, K[a], zeta) : 0.;
+          for (int c = 0; c < 3; ++c) {
+            pt[c] += N * X[a * 3 + c];
+            for (int r = 0; r < ei.dim; ++r) Jm[r][c] += d[r] * X[a * 3 + c];
+          }
+        }
+        for (int c = 0; c < 3; ++c) fe.xyz[size_t(q) * 3 + c] = pt[c];
+        if (ei.dim == 3) {
+          const double dx_dxi = Jm[0][0], dy_dxi = Jm[0][1], dz_dxi = Jm[0][2];
+          const double dx_deta = Jm[1][0], dy_deta = Jm[1][1], dz_deta = Jm[1][2];
+          const double dx_dzeta = Jm[2][0], dy_dzeta = Jm[2][1], dz_dzeta = Jm[2][2];
+          const double det = dx_dxi * (dy_deta * dz_dzeta - dz_deta * dy_dzeta) +
+                             dy_dxi * (dz_deta * dx_dzeta - dx_deta * dz_dzeta) +
+                             dz_dxi * (dx_deta * dy_dzeta - dy_deta * dx_dzeta);
+          const double inv = 1. / det;
+          fe.JxW[q] = det * w;
+          const double dxidx = (dy_deta * dz_dzeta - dz_deta * dy_dzeta) * inv;
+          const double dxidy = (dz_deta * dx_dzeta - dx_deta * dz_dzeta) * inv;
+          const double dxidz = (dx_deta * dy_dzeta - dy_deta * dx_dzeta) * inv;
+          const double detadx = (dz_dxi * dy_dzeta - dy_dxi * dz_dzeta) * inv;
+          const double detady = (dx_dxi * dz_dzeta - dz_dxi * dx_dzeta) * inv;
+          const double detadz = (dy_dxi * dx_dzeta - dx_dxi * dy_dzeta) * inv;
+          const double dzetadx = (dy_dxi * dz_deta - dz_dxi * dy_deta) * inv;
+          const double dzetady = (dz_dxi * dx_deta - dx_dxi * dz_deta) * inv;
+          const double dzetadz = (dx_dxi * dy_deta - dy_dxi * dx_deta) * inv;
+          for (int a = 0; a < ei.nn; ++a) {
+            const double* d = &dref[size_t(a) * 3];
+            double* g = &fe.dphi[(size_t(a) * ei.nq + q) * 3];
+            g[0] = d[0] * dxidx + d[1] * detadx + d[2] * dzetadx;
+            g[1] = d[0] * dxidy + d[1] * detady + d[2] * dzetady;
+            g[2] = d[0] * dxidz + d[1] * detadz + d[2] * dzetadz;
+          }
+        } else {  // planar element in the xy-plane (GeomElem uses the element itself, geom_elem.cpp:358-374)
+          const double dx_dxi = Jm[0][0], dy_dxi = Jm[0][1], dx_deta = Jm[1][0], dy_deta = Jm[1][1];
+          const double det = dx_dxi * dy_deta - dx_deta * dy_dxi;
+          const double inv = 1. / det;
+          fe.JxW[q] = det * w;
+          const double dxidx = dy_deta * inv, dxidy = -dx_deta * inv;
+          const double detadx = -dy_dxi * inv, detady = dx_dxi * inv;
+          for (int a = 0; a < ei.nn; ++a) {
+            const double* d = &dref[size_t(a) * 3];
+            double* g = &fe.dphi[(size_t(a) * ei.nq + q) * 3];
+            g[0] = d[0] * dxidx + d[1] * detadx;
+            g[1] = d[0] * dxidy + d[1] * detady;
+            g[2] = 0.;
+          }
+        }
+      }
+}
+
+// MAST::FEBase::init_for_side (fe_base.cpp:137-204): element shape functions evaluated at the
+// side's Gauss points (libMesh FE::reinit(elem, side)), side JxW and outward normals.
+static void fe_init_side(int type, const double* X, int side, FE& fe) {
+  const ElemInfo ei = elem_info(type);
+  const int nfn = type == ORACLE_HEX8 ? 4 : 9;
+  const int forder = type == ORACLE_HEX8 ? 1 : 2;
+  const int n1d = type == ORACLE_HEX8 ? 2 : 3;
+  const int* smap = type == ORACLE_HEX8 ? H8_SIDE[side] : H27_SIDE[side];
+  const int *FI = type == ORACLE_HEX8 ? Q4_I : Q9_I, *FJ = type == ORACLE_HEX8 ? Q4_J : Q9_J;
+  const double* gp = n1d == 2 ? GP2 : GP3;
+  const double* gw = n1d == 2 ? GW2 : GW3;
+  fe.nn = ei.nn; fe.nq = n1d * n1d; fe.dim = 3;
+  fe.phi.assign(size_t(ei.nn) * fe.nq, 0.);
+  fe.dphi.clear();
+  fe.JxW.assign(fe.nq, 0.);
+  fe.xyz.assign(size_t(fe.nq) * 3, 0.);
+  fe.normal.assign(size_t(fe.nq) * 3, 0.);
+  int q = 0;
+  for (int jq = 0; jq < n1d; ++jq)
+    for (int iq = 0; iq < n1d; ++iq, ++q) {
+      double t1[3] = {0, 0, 0}, t2[3] = {0, 0, 0}, pt[3] = {0, 0, 0};
+      for (int k = 0; k < nfn; ++k) {
+        const double li = lag1(forder, FI[k], gp[iq]), lj = lag1(forder, FJ[k], gp[jq]);
+        const double N = li * lj;
+        const double dxi = dlag1(forder, FI[k], gp[iq]) * lj, deta = li * dlag1(forder, FJ[k], gp[jq]);
+        fe.phi[size_t(smap[k]) * fe.nq + q] = N;  // element shape fn of a face node == face shape fn
+        for (int c = 0; c < 3; ++c) {
+          const double x = X[smap[k] * 3 + c];
+          pt[c] += N * x; t1[c] += dxi * x; t2[c] += deta * x;
+        }
+      }
+      double n[3] = {t1[1] * t2[2] - t1[2] * t2[1], t1[2] * t2[0] - t1[0] * t2[2], t1[0] * t2[1] - t1[1] * t2[0]};
+      const double len = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      fe.JxW[q] = len * gw[iq] * gw[jq];
+      for (int c = 0; c < 3; ++c) {
+        fe.normal[size_t(q) * 3 + c] = n[c] / len;
+        fe.xyz[size_t(q) * 3 + c] = pt[c];
+      }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// property cards
+// ---------------------------------------------------------------------------------------------
+// IsotropicMaterialProperty::StiffnessMatrix3D::operator()  (isotropic_material_property_card.cpp:512-528)
+static void stiffness_3d(double E, double nu, Mat& m) {
+  m.resize(6, 6);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      if (i == j) m(i, i) = E * (1. - nu) / (1. - nu - 2. * nu * nu);
+      else m(i, j) = E * nu / (1. - nu - 2. * nu * nu);
+    m(i + 3, i + 3) = E / 2. / (1. + nu);
+  }
+}
+// ...::derivative  (isotropic_material_property_card.cpp:533-567)
+static void stiffness_3d_derivative(double E, double nu, double dEdf, double dnudf, Mat& m) {
+  m.resize(6, 6);
+  Mat dm(6, 6);
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      if (i == j) dm(i, i) = (1. - nu) / (1. - nu - 2. * nu * nu);
+      else dm(i, j) = nu / (1. - nu - 2. * nu * nu);
+    dm(i + 3, i + 3) = 1. / 2. / (1. + nu);
+  }
+  for (size_t k = 0; k < m.a.size(); ++k) m.a[k] += dEdf * dm.a[k];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      if (i == j)
+        dm(i, i) = -E / (1. - nu - 2. * nu * nu) + E * (1. - nu) / std::pow(1. - nu - 2. * nu * nu, 2) * (1. + 4. * nu);
+      else
+        dm(i, j) = E / (1. - nu - 2. * nu * nu) + E * nu / std::pow(1. - nu - 2. * nu * nu, 2) * (1. + 4. * nu);
+    dm(i + 3, i + 3) = -E / 2. / std::pow(1. + nu, 2);
+  }
+  for (size_t k = 0; k < m.a.size(); ++k) m.a[k] += dnudf * dm.a[k];
+}
+// IsotropicElementProperty3D::ThermalExpansionMatrix::operator() = D * {alpha,alpha,alpha,0,0,0}
+// (isotropic_element_property_card_3D.cpp:275-282; material part isotropic_material_property_card.cpp:613-637)
+static Vec thermal_expansion_A_3d(double E, double nu, double alpha) {
+  Mat D;
+  stiffness_3d(E, nu, D);
+  Vec a(6, 0.);
+  for (int i = 0; i < 3; ++i) a[i] = alpha;
+  return matvec(D, a);
+}
+
+// SIMP modulus and its derivative at a quadrature point
+// (examples/structural/example_6/example_6.cpp:100-137; density through MeshFieldFunction =
+//  FE interpolation of the nodal field at the point, src/base/mesh_field_function.cpp:72-100)
+struct Modulus {
+  const OracleProblem* p;
+  double rho_at(const FE& fe, const int32_t* en, int q) const {
+    double r = 0.;
+    for (int a = 0; a < fe.nn; ++a) r += fe.N(a, q) * p->rho[en[a]];
+    return r;
+  }
+  double E(const FE& fe, const int32_t* en, int q) const {
+    if (!p->rho) return p->E0;
+    return p->E0 * (p->rho_min + (1. - p->rho_min) * std::pow(rho_at(fe, en, q), p->penalty));
+  }
+  // dE/dp for a DV whose nodal density sensitivity on this element is drho_nodal[a]
+  double dE(const FE& fe, const int32_t* en, int q, const double* drho_nodal) const {
+    if (!p->rho) return 0.;
+    double dr = 0.;
+    for (int a = 0; a < fe.nn; ++a) dr += fe.N(a, q) * drho_nodal[a];
+    return p->E0 * (1. - p->rho_min) * p->penalty * std::pow(rho_at(fe, en, q), p->penalty - 1.) * dr;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// StructuralElement3D
+// ---------------------------------------------------------------------------------------------
+struct StrainOps {
+  OperatorMatrix lin, nl_x, nl_y, nl_z, nl_u, nl_v, nl_w;
+  Mat mat_x, mat_y, mat_z;
+  Vec eps;
+};
+
+// StructuralElement3D::initialize_green_lagrange_strain_operator  (solid_element_3d.cpp:1308-1463)
+static void init_strain_operator(const FE& fe, int qp, bool nonlinear, const Vec& disp, StrainOps& s) {
+  const int nn = fe.nn;
+  s.eps.assign(6, 0.);
+  s.mat_x.resize(6, 3); s.mat_y.resize(6, 3); s.mat_z.resize(6, 3);
+  Vec phi(nn);
+  for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 0);
+  s.lin.set_shape_function(0, 0, phi);
+  s.lin.set_shape_function(3, 1, phi);
+  s.lin.set_shape_function(5, 2, phi);
+  if (nonlinear) {
+    s.nl_x.set_shape_function(0, 0, phi); s.nl_x.set_shape_function(1, 1, phi); s.nl_x.set_shape_function(2, 2, phi);
+    s.nl_u.set_shape_function(0, 0, phi); s.nl_v.set_shape_function(0, 1, phi); s.nl_w.set_shape_function(0, 2, phi);
+  }
+  for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 1);
+  s.lin.set_shape_function(1, 1, phi);
+  s.lin.set_shape_function(3, 0, phi);
+  s.lin.set_shape_function(4, 2, phi);
+  if (nonlinear) {
+    s.nl_y.set_shape_function(0, 0, phi); s.nl_y.set_shape_function(1, 1, phi); s.nl_y.set_shape_function(2, 2, phi);
+    s.nl_u.set_shape_function(1, 0, phi); s.nl_v.set_shape_function(1, 1, phi); s.nl_w.set_shape_function(1, 2, phi);
+  }
+  for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 2);
+  s.lin.set_shape_function(2, 2, phi);
+  s.lin.set_shape_function(4, 1, phi);
+  s.lin.set_shape_function(5, 0, phi);
+  if (nonlinear) {
+    s.nl_z.set_shape_function(0, 0, phi); s.nl_z.set_shape_function(1, 1, phi); s.nl_z.set_shape_function(2, 2, phi);
+    s.nl_u.set_shape_function(2, 0, phi); s.nl_v.set_shape_function(2, 1, phi); s.nl_w.set_shape_function(2, 2, phi);
+    Vec ddx, ddy, ddz;
+    s.nl_x.vector_mult(ddx, disp);  // {du/dx, dv/dx, dw/dx}
+    s.nl_y.vector_mult(ddy, disp);
+    s.nl_z.vector_mult(ddz, disp);
+    double F[3][3], E[3][3];
+    for (int i = 0; i < 3; ++i) { F[i][0] = ddx[i]; F[i][1] = ddy[i]; F[i][2] = ddz[i]; }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double ftf = 0.;
+        for (int k = 0; k < 3; ++k) ftf += F[k][i] * F[k][j];
+        E[i][j] = 0.5 * (F[i][j] + F[j][i] + ftf);
+      }
+    s.eps[0] = E[0][0]; s.eps[1] = E[1][1]; s.eps[2] = E[2][2];
+    s.eps[3] = E[0][1] + E[1][0]; s.eps[4] = E[1][2] + E[2][1]; s.eps[5] = E[0][2] + E[2][0];
+    for (int c = 0; c < 3; ++c) {
+      s.mat_x(0, c) = ddx[c]; s.mat_x(3, c) = ddy[c]; s.mat_x(5, c) = ddz[c];
+      s.mat_y(1, c) = ddy[c]; s.mat_y(3, c) = ddx[c]; s.mat_y(4, c) = ddz[c];
+      s.mat_z(2, c) = ddz[c]; s.mat_z(4, c) = ddy[c]; s.mat_z(5, c) = ddx[c];
+    }
+  } else {
+    s.lin.vector_mult(s.eps, disp);
+  }
+}
+
+static void strain_ops_reinit(StrainOps& s, int nn) {
+  s.lin.reinit(6, 3, nn);
+  s.nl_x.reinit(3, 3, nn); s.nl_y.reinit(3, 3, nn); s.nl_z.reinit(3, 3, nn);
+  s.nl_u.reinit(3, 3, nn); s.nl_v.reinit(3, 3, nn); s.nl_w.reinit(3, 3, nn);
+}
+
+static void add_scaled_top_left(Mat& jac, const Mat& m, double s) {  // jac.topLeftCorner(n2,n2) += s*m
+  for (int i = 0; i < m.r; ++i)
+    for (int j = 0; j < m.c; ++j) jac(i, j) += s * m(i, j);
+}
+
+// StructuralElement3D::internal_residual (solid_element_3d.cpp:135-423) and, with sens != nullptr,
+// ::internal_residual_sensitivity (:566-788: identical except D <- dD/dp at :640).
+// f has nd entries, jac nd x nd (nd = nv*nn); only the leading 3nn block is touched, plus the
+// rotational diagonal when nv == 6 (:413-417).
+static void solid3d_internal_residual(const OracleProblem* p, const FE& fe, const int32_t* en, const Vec& sol,
+                                      bool request_jacobian, Vec& f, Mat& jac, const double* drho_nodal /*sens*/) {
+  const int nn = fe.nn, n2 = 3 * nn;
+  const bool nl = p->nonlinear_strain != 0;
+  Vec disp(sol.begin(), sol.begin() + n2), stress, vec2, vec3;
+  Mat D, mat1, mat2, mat3, mat4(3, 3);
+  StrainOps s;
+  strain_ops_reinit(s, nn);
+  Modulus mod{p};
+  for (int qp = 0; qp < fe.nq; ++qp) {
+    if (!drho_nodal) stiffness_3d(mod.E(fe, en, qp), p->nu, D);                                  // :272
+    else stiffness_3d_derivative(mod.E(fe, en, qp), p->nu, mod.dE(fe, en, qp, drho_nodal), 0., D);  // :640
+    init_strain_operator(fe, qp, nl, disp, s);
+    stress = matvec(D, s.eps);  // :289 (Gmat*alpha == 0: incompatible modes are inert)
+    const double JxW = fe.JxW[qp];
+    s.lin.vector_mult_transpose(vec2, stress);
+    for (int i = 0; i < n2; ++i) f[i] += JxW * vec2[i];  // :296-297
+    if (nl) {                                             // :299-316
+      vec3 = matvec_t(s.mat_x, stress); s.nl_x.vector_mult_transpose(vec2, vec3);
+      for (int i = 0; i < n2; ++i) f[i] += JxW * vec2[i];
+      vec3 = matvec_t(s.mat_y, stress); s.nl_y.vector_mult_transpose(vec2, vec3);
+      for (int i = 0; i < n2; ++i) f[i] += JxW * vec2[i];
+      vec3 = matvec_t(s.mat_z, stress); s.nl_z.vector_mult_transpose(vec2, vec3);
+      for (int i = 0; i < n2; ++i) f[i] += JxW * vec2[i];
+    }
+    if (request_jacobian) {
+      s.lin.left_multiply(mat1, D);                    // :327  D*B_lin
+      s.lin.right_multiply_transpose(mat2, mat1);      // :328  B_lin^T D B_lin
+      add_scaled_top_left(jac, mat2, JxW);             // :329
+      if (nl) {
+        mat3 = matmul_tn(s.mat_x, mat1); s.nl_x.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);  // :334-336
+        mat3 = matmul_tn(s.mat_y, mat1); s.nl_y.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+        mat3 = matmul_tn(s.mat_z, mat1); s.nl_z.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+        for (int idim = 0; idim < 3; ++idim) {           // :349-384
+          if (idim == 0) s.nl_x.left_multiply(mat1, s.mat_x);
+          else if (idim == 1) s.nl_y.left_multiply(mat1, s.mat_y);
+          else s.nl_z.left_multiply(mat1, s.mat_z);
+          mat1 = matmul(D, mat1);
+          s.lin.right_multiply_transpose(mat2, mat1); add_scaled_top_left(jac, mat2, JxW);
+          mat3 = matmul_tn(s.mat_x, mat1); s.nl_x.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+          mat3 = matmul_tn(s.mat_y, mat1); s.nl_y.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+          mat3 = matmul_tn(s.mat_z, mat1); s.nl_z.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+        }
+        mat4(0, 0) = stress[0]; mat4(1, 1) = stress[1]; mat4(2, 2) = stress[2];  // :388-393
+        mat4(0, 1) = mat4(1, 0) = stress[3];
+        mat4(1, 2) = mat4(2, 1) = stress[4];
+        mat4(0, 2) = mat4(2, 0) = stress[5];
+        s.nl_u.left_multiply(mat3, mat4); s.nl_u.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+        s.nl_v.left_multiply(mat3, mat4); s.nl_v.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+        s.nl_w.left_multiply(mat3, mat4); s.nl_w.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, JxW);
+      }
+    }
+  }
+  if (request_jacobian && p->nv == 6) {  // :413-417  rotational dofs get 1e-20*max(diag)
+    double mx = jac(0, 0);
+    for (int i = 1; i < jac.r; ++i) mx = std::max(mx, jac(i, i));
+    for (int i = 0; i < n2; ++i) jac(n2 + i, n2 + i) += 1.0e-20 * mx;
+  }
+}
+
+// StructuralElement3D::surface_pressure_residual (side version, solid_element_3d.cpp:815-876)
+static void solid3d_surface_pressure_residual(const OracleProblem* p, const double* X, int side, double press, Vec& f) {
+  FE fe;
+  fe_init_side(p->elem_type, X, side, fe);
+  const int nn = fe.nn, n2 = 3 * nn;
+  OperatorMatrix B;
+  Vec phi(nn), force(3), vec, local_f(n2, 0.);
+  for (int qp = 0; qp < fe.nq; ++qp) {
+    for (int a = 0; a < nn; ++a) phi[a] = fe.N(a, qp);
+    B.reinit_diag(3, phi);
+    for (int d = 0; d < 3; ++d) force[d] = press * fe.normal[size_t(qp) * 3 + d];
+    B.vector_mult_transpose(vec, force);
+    for (int i = 0; i < n2; ++i) local_f[i] += fe.JxW[qp] * vec[i];
+  }
+  for (int i = 0; i < n2; ++i) f[i] -= local_f[i];
+}
+
+// StructuralElement3D::thermal_residual (solid_element_3d.cpp:950-1089)
+static void solid3d_thermal_residual(const OracleProblem* p, const FE& fe, const int32_t* en, const Vec& sol,
+                                     bool request_jacobian, Vec& f, Mat& jac) {
+  const int nn = fe.nn, n2 = 3 * nn;
+  const bool nl = p->nonlinear_strain != 0;
+  Vec disp(sol.begin(), sol.begin() + n2), vec1, vec2, vec3;
+  Mat mat2, mat3, mat4(3, 3);
+  StrainOps s;
+  strain_ops_reinit(s, nn);
+  Modulus mod{p};
+  for (int qp = 0; qp < fe.nq; ++qp) {
+    Vec A = thermal_expansion_A_3d(mod.E(fe, en, qp), p->nu, p->alpha);
+    double t = p->temperature_const;
+    if (p->temperature) {  // nodal temperature field interpolated at the point (MeshFieldFunction)
+      t = 0.;
+      for (int a = 0; a < nn; ++a) t += fe.N(a, qp) * p->temperature[en[a]];
+    }
+    const double dT = t - p->ref_temperature;
+    vec1.assign(6, 0.);
+    for (int i = 0; i < 6; ++i) vec1[i] = A[i] * dT;  // :1016
+    init_strain_operator(fe, qp, nl, disp, s);
+    const double JxW = fe.JxW[qp];
+    s.lin.vector_mult_transpose(vec3, vec1);
+    for (int i = 0; i < n2; ++i) f[i] -= JxW * vec3[i];  // :1032-1033
+    if (nl) {
+      vec2 = matvec_t(s.mat_x, vec1); s.nl_x.vector_mult_transpose(vec3, vec2);
+      for (int i = 0; i < n2; ++i) f[i] -= JxW * vec3[i];
+      vec2 = matvec_t(s.mat_y, vec1); s.nl_y.vector_mult_transpose(vec3, vec2);
+      for (int i = 0; i < n2; ++i) f[i] -= JxW * vec3[i];
+      vec2 = matvec_t(s.mat_z, vec1); s.nl_z.vector_mult_transpose(vec3, vec2);
+      for (int i = 0; i < n2; ++i) f[i] -= JxW * vec3[i];
+      if (request_jacobian) {  // :1054-1082
+        mat4(0, 0) = vec1[0]; mat4(1, 1) = vec1[1]; mat4(2, 2) = vec1[2];
+        mat4(0, 1) = mat4(1, 0) = vec1[3];
+        mat4(1, 2) = mat4(2, 1) = vec1[4];
+        mat4(0, 2) = mat4(2, 0) = vec1[5];
+        s.nl_u.left_multiply(mat3, mat4); s.nl_u.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, -JxW);
+        s.nl_v.left_multiply(mat3, mat4); s.nl_v.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, -JxW);
+        s.nl_w.left_multiply(mat3, mat4); s.nl_w.right_multiply_transpose(mat2, mat3); add_scaled_top_left(jac, mat2, -JxW);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// HeatConductionElementBase::internal_residual (heat_conduction_elem_base.cpp:53-149), QUAD4 with
+// Solid2DSectionProperty::ThermalConductanceMatrix = k*h (solid_2d_section_element_property_card.cpp:940-953)
+// and volume_heat_source_residual (:1709-1745)
+// ---------------------------------------------------------------------------------------------
+static void heat_elem_calculations(const OracleProblem* p, const FE& fe, const Vec& sol, bool request_jacobian,
+                                   Vec& f, Mat& jac) {
+  const int nn = fe.nn, dim = fe.dim;
+  OperatorMatrix Bmat;
+  std::vector<OperatorMatrix> dB(dim);
+  Vec phi(nn), vec2;
+  Mat vec1, mat_n2n2, solm(nn, 1);
+  for (int a = 0; a < nn; ++a) solm(a, 0) = sol[a];
+  for (int qp = 0; qp < fe.nq; ++qp) {
+    for (int a = 0; a < nn; ++a) phi[a] = fe.N(a, qp);
+    Bmat.reinit_diag(1, phi);
+    Bmat.right_multiply(vec1, solm);  // T at the quadrature point  (:84)
+    const double Tqp = vec1(0, 0);
+    const double k = (p->k_of_T ? p->k0 * (1. + p->k_beta * Tqp) : p->k0) * p->thickness;
+    const double dk = p->k_of_T ? p->k0 * p->k_beta * p->thickness : 0.;
+    for (int d = 0; d < dim; ++d) {
+      for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, d);
+      dB[d].reinit_diag(1, phi);
+    }
+    Vec flux(dim, 0.);
+    for (int j = 0; j < dim; ++j) {
+      dB[j].right_multiply(vec1, solm);  // dT/dx_j
+      for (int i = 0; i < dim; ++i) flux[i] += vec1(0, 0) * (i == j ? k : 0.);
+    }
+    for (int i = 0; i < dim; ++i) {
+      Vec v1(1, flux[i]);
+      dB[i].vector_mult_transpose(vec2, v1);
+      for (int a = 0; a < nn; ++a) f[a] += fe.JxW[qp] * vec2[a];
+    }
+    if (request_jacobian) {
+      for (int i = 0; i < dim; ++i)
+        for (int j = 0; j < dim; ++j) {
+          dB[i].right_multiply_transpose(mat_n2n2, dB[j]);
+          const double kij = (i == j ? k : 0.);
+          for (int a = 0; a < nn; ++a)
+            for (int b = 0; b < nn; ++b) jac(a, b) += fe.JxW[qp] * kij * mat_n2n2(a, b);
+        }
+      if (p->k_of_T) {  // :125-141
+        for (int j = 0; j < dim; ++j) {
+          dB[j].right_multiply(vec1, solm);
+          for (int i = 0; i < dim; ++i) {
+            const double dkij = (i == j ? dk : 0.);
+            if (dkij != 0.) {
+              dB[i].right_multiply_transpose(mat_n2n2, Bmat);
+              for (int a = 0; a < nn; ++a)
+                for (int b = 0; b < nn; ++b) jac(a, b) += fe.JxW[qp] * vec1(0, 0) * dkij * mat_n2n2(a, b);
+            }
+          }
+        }
+      }
+    }
+  }
+  if (p->heat_source != 0.) {  // volume_heat_source_residual
+    for (int qp = 0; qp < fe.nq; ++qp)
+      for (int a = 0; a < nn; ++a) f[a] -= fe.JxW[qp] * fe.N(a, qp) * p->heat_source * p->thickness;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elem-ops layer
+// ---------------------------------------------------------------------------------------------
+struct SideLoadIndex {  // (element -> its loaded sides), GeomElem::external_side_loads_for_quadrature_elem
+  std::vector<int64_t> ptr;
+  std::vector<int32_t> side;
+  std::vector<double> press;
+  void build(const OracleProblem* p) {
+    ptr.assign(p->n_elem + 1, 0);
+    for (int64_t l = 0; l < p->n_side_loads; ++l) ptr[p->side_elem[l] + 1]++;
+    for (int64_t e = 0; e < p->n_elem; ++e) ptr[e + 1] += ptr[e];
+    side.resize(p->n_side_loads); press.resize(p->n_side_loads);
+    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    // std::map<unsigned, ...> iteration is by ascending side id; stable within a side
+    std::vector<int64_t> order(p->n_side_loads);
+    for (int64_t l = 0; l < p->n_side_loads; ++l) order[l] = l;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      if (p->side_elem[a] != p->side_elem[b]) return p->side_elem[a] < p->side_elem[b];
+      return p->side_id[a] < p->side_id[b];
+    });
+    for (int64_t l : order) {
+      const int64_t k = pos[p->side_elem[l]]++;
+      side[k] = p->side_id[l]; press[k] = p->side_pressure[l];
+    }
+  }
+};
+
+static void gather_coords(const OracleProblem* p, int64_t e, int nn, std::vector<double>& X) {
+  X.resize(size_t(nn) * 3);
+  for (int a = 0; a < nn; ++a)
+    for (int c = 0; c < 3; ++c) X[a * 3 + c] = p->xyz[size_t(p->conn[e * nn + a]) * 3 + c];
+}
+// dof_map.dof_indices(elem): variable-major list, dof(node,var) = nv*node+var
+static void dof_indices(const OracleProblem* p, int64_t e, int nn, std::vector<int64_t>& di) {
+  di.resize(size_t(p->nv) * nn);
+  for (int v = 0; v < p->nv; ++v)
+    for (int a = 0; a < nn; ++a) di[v * nn + a] = int64_t(p->nv) * p->conn[e * nn + a] + v;
+}
+
+// StructuralNonlinearAssemblyElemOperations::elem_calculations (structural_nonlinear_assembly.cpp:112-139)
+// HeatConductionNonlinearAssemblyElemOperations::elem_calculations (heat_conduction_nonlinear_assembly.cpp:83-101)
+static void elem_calculations(const OracleProblem* p, const SideLoadIndex& sl, int64_t e, const Vec& sol, bool if_jac,
+                              Vec& vec, Mat& mat) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  std::vector<double> X;
+  gather_coords(p, e, ei.nn, X);
+  FE fe;
+  fe_init(p->elem_type, X.data(), fe);
+  const int nd = p->nv * ei.nn;
+  vec.assign(nd, 0.);
+  mat.resize(nd, nd);
+  if (p->elem_type == ORACLE_QUAD4) {
+    heat_elem_calculations(p, fe, sol, if_jac, vec, mat);
+    return;
+  }
+  const int32_t* en = &p->conn[e * ei.nn];
+  solid3d_internal_residual(p, fe, en, sol, if_jac, vec, mat, nullptr);
+  for (int64_t k = sl.ptr[e]; k < sl.ptr[e + 1]; ++k)  // side_external_residual (structural_element_base.cpp:628-701)
+    solid3d_surface_pressure_residual(p, X.data(), sl.side[k], sl.press[k], vec);
+  if (p->thermal)  // volume_external_residual (structural_element_base.cpp:803-855)
+    solid3d_thermal_residual(p, fe, en, sol, if_jac, vec, mat);
+}
+
+// external (side + volume) residual only, as ComplianceOutput uses it (compliance_output.cpp:71-102)
+static void elem_external_residual(const OracleProblem* p, const SideLoadIndex& sl, int64_t e, const Vec& sol, Vec& vec) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  std::vector<double> X;
+  gather_coords(p, e, ei.nn, X);
+  const int nd = p->nv * ei.nn;
+  vec.assign(nd, 0.);
+  for (int64_t k = sl.ptr[e]; k < sl.ptr[e + 1]; ++k)
+    solid3d_surface_pressure_residual(p, X.data(), sl.side[k], sl.press[k], vec);
+  if (p->thermal) {
+    FE fe;
+    fe_init(p->elem_type, X.data(), fe);
+    Mat dummy(nd, nd);
+    solid3d_thermal_residual(p, fe, &p->conn[e * ei.nn], sol, false, vec, dummy);
+  }
+}
+
+// libMesh DofMap::constrain_element_matrix_and_vector for homogeneous Dirichlet rows without
+// dependencies: K <- C^T K C (row & column zeroed), K(i,i) = 1, f(i) = 0.
+static void constrain(const OracleProblem* p, const std::vector<int64_t>& di, Mat* m, Vec* v) {
+  if (!p->constrained) return;
+  const int nd = int(di.size());
+  for (int i = 0; i < nd; ++i)
+    if (p->constrained[di[i]]) {
+      if (m) {
+        for (int j = 0; j < nd; ++j) { (*m)(i, j) = 0.; (*m)(j, i) = 0.; }
+        (*m)(i, i) = 1.;
+      }
+      if (v) (*v)[i] = 0.;
+    }
+}
+
+static inline int64_t csr_find(const int64_t* row_ptr, const int32_t* col_idx, int64_t row, int64_t col) {
+  const int32_t* b = col_idx + row_ptr[row];
+  const int32_t* e = col_idx + row_ptr[row + 1];
+  const int32_t* it = std::lower_bound(b, e, int32_t(col));  // PETSc MatSetValues row search
+  return (it != e && *it == col) ? (it - col_idx) : -1;
+}
+
+// the element loop of NonlinearImplicitAssembly::residual_and_jacobian (nonlinear_implicit_assembly.cpp:111-186)
+// restricted to elements [e0,e1) and rows [r0,r1) (r0=0,r1=n_dof for the whole system)
+static int assemble_range(const OracleProblem* p, const SideLoadIndex& sl, const double* Xg, double* R, double* Jv,
+                          const int64_t* row_ptr, const int32_t* col_idx, int64_t e0, int64_t e1) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  std::vector<int64_t> di;
+  Vec sol, vec;
+  Mat mat;
+  for (int64_t e = e0; e < e1; ++e) {
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size());
+    if (p->diag_elem && p->diag_elem[e]) {  // :117-130
+      if (Jv) {
+        mat.resize(nd, nd);
+        for (int i = 0; i < nd; ++i) mat(i, i) = 1.e-24;
+        constrain(p, di, &mat, nullptr);
+        for (int i = 0; i < nd; ++i)
+          for (int j = 0; j < nd; ++j) {
+            const int64_t k = csr_find(row_ptr, col_idx, di[i], di[j]);
+            if (k < 0) return 2;
+            Jv[k] += mat(i, j);
+          }
+      }
+      continue;
+    }
+    sol.resize(nd);
+    for (int i = 0; i < nd; ++i) sol[i] = Xg[di[i]];  // :145-146
+    elem_calculations(p, sl, e, sol, Jv != nullptr, vec, mat);  // :157
+    constrain(p, di, Jv ? &mat : nullptr, R ? &vec : nullptr);  // :174-179
+    if (R)
+      for (int i = 0; i < nd; ++i) R[di[i]] += vec[i];  // :182
+    if (Jv)
+      for (int i = 0; i < nd; ++i)
+        for (int j = 0; j < nd; ++j) {  // :183 (MatSetValues ADD_VALUES, explicit zeros kept)
+          const int64_t k = csr_find(row_ptr, col_idx, di[i], di[j]);
+          if (k < 0) return 2;
+          Jv[k] += mat(i, j);
+        }
+  }
+  return 0;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C API
+// =============================================================================================
+extern "C" {
+
+int64_t oracle_build_pattern(const OracleProblem* p, int64_t* row_ptr, int32_t* col_idx) {
+  // libMesh SparsityPattern::Build: a row couples to every dof of every element touching it (all
+  // variables couple); PETSc AIJ keeps columns sorted.  Done node-wise: dofs of a node share columns.
+  const ElemInfo ei = elem_info(p->elem_type);
+  std::vector<std::vector<int32_t>> nbr(p->n_nodes);
+  for (int64_t e = 0; e < p->n_elem; ++e)
+    for (int a = 0; a < ei.nn; ++a) {
+      std::vector<int32_t>& l = nbr[p->conn[e * ei.nn + a]];
+      for (int b = 0; b < ei.nn; ++b) l.push_back(p->conn[e * ei.nn + b]);
+    }
+  const int nv = p->nv;
+  int64_t nnz = 0;
+  row_ptr[0] = 0;
+  for (int64_t n = 0; n < p->n_nodes; ++n) {
+    std::vector<int32_t>& l = nbr[n];
+    std::sort(l.begin(), l.end());
+    l.erase(std::unique(l.begin(), l.end()), l.end());
+    for (int v = 0; v < nv; ++v) {
+      if (col_idx) {
+        int64_t k = nnz;
+        for (int32_t m : l)
+          for (int w = 0; w < nv; ++w) col_idx[k++] = m * nv + w;
+      }
+      nnz += int64_t(l.size()) * nv;
+      row_ptr[n * nv + v + 1] = nnz;
+    }
+  }
+  return nnz;
+}
+
+int oracle_residual_and_jacobian(const OracleProblem* p, const double* X, double* R, double* J_vals,
+                                 const int64_t* row_ptr, const int32_t* col_idx) {
+  const int64_t n_dof = p->n_nodes * p->nv;
+  if (R) std::fill(R, R + n_dof, 0.);                       // nonlinear_implicit_assembly.cpp:81
+  if (J_vals) std::fill(J_vals, J_vals + row_ptr[n_dof], 0.);  // :82
+  SideLoadIndex sl;
+  sl.build(p);
+  return assemble_range(p, sl, X, R, J_vals, row_ptr, col_idx, 0, p->n_elem);
+}
+
+int oracle_elem_calculations(const OracleProblem* p, int64_t e, const double* X, int want_jac, double* vec, double* mat) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  SideLoadIndex sl;
+  sl.build(p);
+  std::vector<int64_t> di;
+  dof_indices(p, e, ei.nn, di);
+  Vec sol(di.size()), v;
+  for (size_t i = 0; i < di.size(); ++i) sol[i] = X[di[i]];
+  Mat m;
+  elem_calculations(p, sl, e, sol, want_jac != 0, v, m);
+  std::copy(v.begin(), v.end(), vec);
+  if (want_jac && mat) std::copy(m.a.begin(), m.a.end(), mat);
+  return 0;
+}
+
+// NonlinearImplicitAssembly::sensitivity_assemble (nonlinear_implicit_assembly.cpp:515-686) for one DV whose
+// nodal density sensitivity is the sparse vector (dv_node, dv_weight)[dv_begin:dv_end]
+int oracle_sensitivity_assemble(const OracleProblem* p, const double* X, int64_t dv_begin, int64_t dv_end,
+                                const int32_t* dv_node, const double* dv_weight, double* dres_dp) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  if (p->elem_type == ORACLE_QUAD4) return 3;
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::fill(dres_dp, dres_dp + n_dof, 0.);  // :529
+  // elements in the DV's support (ElemParameterDependence, :570-573): here the elements touching a node
+  // with non-zero density sensitivity; everywhere else dD/dp == 0 identically.
+  std::vector<double> drho(p->n_nodes, 0.);
+  std::vector<char> touched(p->n_nodes, 0);
+  for (int64_t k = dv_begin; k < dv_end; ++k) { drho[dv_node[k]] += dv_weight[k]; touched[dv_node[k]] = 1; }
+  std::vector<int64_t> di;
+  std::vector<double> Xe, dre(ei.nn);
+  Vec sol, vec;
+  Mat dummy;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;  // :566-567
+    bool dep = false;
+    for (int a = 0; a < ei.nn; ++a) dep = dep || touched[p->conn[e * ei.nn + a]];
+    if (!dep) continue;
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size());
+    sol.resize(nd);
+    for (int i = 0; i < nd; ++i) sol[i] = X[di[i]];
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    for (int a = 0; a < ei.nn; ++a) dre[a] = drho[p->conn[e * ei.nn + a]];
+    // StructuralNonlinearAssemblyElemOperations::elem_sensitivity_calculations (structural_nonlinear_assembly.cpp:172-197):
+    // internal_residual_sensitivity; pressure loads are parameter independent (surface_pressure_residual_sensitivity
+    // differentiates the pressure field only); 3D thermal_residual_sensitivity is libmesh_error() (solid_element_3d.cpp:1093-1104)
+    if (p->thermal) return 4;
+    vec.assign(nd, 0.);
+    dummy.resize(nd, nd);
+    solid3d_internal_residual(p, fe, &p->conn[e * ei.nn], sol, false, vec, dummy, dre.data());
+    constrain(p, di, nullptr, &vec);                          // :613
+    for (int i = 0; i < nd; ++i) dres_dp[di[i]] += vec[i];  // :616
+  }
+  return 0;
+}
+
+// AssemblyBase::calculate_output_adjoint_sensitivity_multiple_parameters_no_direct (assembly_base.cpp:594-639)
+int oracle_adjoint_sensitivity(const OracleProblem* p, const double* X, const double* adj, int64_t n_dv,
+                               const int64_t* dv_ptr, const int32_t* dv_node, const double* dv_weight, double* sens) {
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::vector<double> dres(n_dof);
+  for (int64_t i = 0; i < n_dv; ++i) {
+    const int rc = oracle_sensitivity_assemble(p, X, dv_ptr[i], dv_ptr[i + 1], dv_node, dv_weight, dres.data());
+    if (rc) return rc;
+    double s = 0.;
+    for (int64_t k = 0; k < n_dof; ++k) s += adj[k] * dres[k];  // adj_sol.dot(dres_dp)  :636-637
+    sens[i] = s;
+  }
+  return 0;
+}
+
+// AssemblyBase::calculate_output (assembly_base.cpp:253-333) with ComplianceOutput::evaluate (compliance_output.cpp:71-102)
+double oracle_compliance(const OracleProblem* p, const double* X) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  SideLoadIndex sl;
+  sl.build(p);
+  std::vector<int64_t> di;
+  Vec sol, vec;
+  double q = 0.;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;
+    dof_indices(p, e, ei.nn, di);
+    sol.resize(di.size());
+    for (size_t i = 0; i < di.size(); ++i) sol[i] = X[di[i]];
+    elem_external_residual(p, sl, e, sol, vec);
+    double d = 0.;
+    for (size_t i = 0; i < di.size(); ++i) d += vec[i] * sol[i];
+    q -= d;  // _compliance -= vec.dot(e.sol())
+  }
+  return q;
+}
+
+// AssemblyBase::calculate_output_derivative (assembly_base.cpp:338-430) with
+// ComplianceOutput::output_derivative_for_elem (compliance_output.cpp:265-296)
+int oracle_compliance_derivative(const OracleProblem* p, const double* X, double* dq_dX) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::fill(dq_dX, dq_dX + n_dof, 0.);
+  SideLoadIndex sl;
+  sl.build(p);
+  std::vector<int64_t> di;
+  Vec sol, vec;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;
+    dof_indices(p, e, ei.nn, di);
+    sol.resize(di.size());
+    for (size_t i = 0; i < di.size(); ++i) sol[i] = X[di[i]];
+    elem_external_residual(p, sl, e, sol, vec);
+    for (double& v : vec) v *= -1.;
+    constrain(p, di, nullptr, &vec);
+    for (size_t i = 0; i < di.size(); ++i) dq_dX[di[i]] += vec[i];
+  }
+  return 0;
+}
+
+// StructuralElement3D::calculate_stress (solid_element_3d.cpp:1146-1265) + Data::von_Mises_stress
+// (stress_output_base.cpp:182-195)
+static double von_mises(const double* s) {
+  return std::pow(0.5 * (std::pow(s[0] - s[1], 2) + std::pow(s[1] - s[2], 2) + std::pow(s[2] - s[0], 2)) +
+                      3.0 * (std::pow(s[3], 2) + std::pow(s[4], 2) + std::pow(s[5], 2)),
+                  0.5);
+}
+
+int oracle_stress(const OracleProblem* p, const double* X, double* stress, double* strain, double* vm, double* jxw) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  if (ei.dim != 3) return 3;
+  std::vector<int64_t> di;
+  std::vector<double> Xe;
+  Vec sol;
+  Mat D;
+  StrainOps s;
+  Modulus mod{p};
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    dof_indices(p, e, ei.nn, di);
+    sol.resize(di.size());
+    for (size_t i = 0; i < di.size(); ++i) sol[i] = X[di[i]];
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    Vec disp(sol.begin(), sol.begin() + 3 * ei.nn);
+    strain_ops_reinit(s, ei.nn);
+    for (int qp = 0; qp < fe.nq; ++qp) {
+      stiffness_3d(mod.E(fe, &p->conn[e * ei.nn], qp), p->nu, D);
+      init_strain_operator(fe, qp, p->nonlinear_strain != 0, disp, s);
+      Vec sig = matvec(D, s.eps);
+      const size_t o = size_t(e) * ei.nq + qp;
+      for (int i = 0; i < 6; ++i) { stress[o * 6 + i] = sig[i]; strain[o * 6 + i] = s.eps[i]; }
+      vm[o] = von_mises(sig.data());
+      jxw[o] = fe.JxW[qp];
+    }
+  }
+  return 0;
+}
+
+// StressStrainOutputBase::functional_for_all_elems (stress_output_base.cpp:851-909) and, if dq_dX,
+// functional_state_derivartive_for_elem (:1100-1172) with dstress/dX = D*B_lin (the 3D derivative is
+// libmesh_error() in the reference, solid_element_3d.cpp:1258-1261; pattern of structural_element_2d.cpp:555-611),
+// driven by AssemblyBase::calculate_output_derivative (assembly_base.cpp:338-430).
+double oracle_stress_functional(const OracleProblem* p, const double* X, double p_norm, double rho_exp, double sigma0,
+                                double* dq_dX) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  const double p_norm_weight = 1., exp_arg_lim = 1.e2;  // stress_output_base.cpp:278-281
+  const size_t nqp = size_t(p->n_elem) * ei.nq;
+  std::vector<double> st(nqp * 6), en_(nqp * 6), vm(nqp), jw(nqp);
+  if (oracle_stress(p, X, st.data(), en_.data(), vm.data(), jw.data())) return std::nan("");
+  double sigma_vm_int = 0., JxW_val = 0.;
+  for (size_t k = 0; k < nqp; ++k) {
+    const double e_val = vm[k];
+    const double sp = std::pow((e_val - sigma0) / sigma0, p_norm_weight);
+    const double exp_sp = (rho_exp * sp > exp_arg_lim) ? std::exp(exp_arg_lim) : std::exp(rho_exp * sp);
+    sigma_vm_int += std::pow(e_val / sigma0, p_norm) * exp_sp * jw[k];
+    JxW_val += exp_sp * jw[k];
+  }
+  const double q = sigma0 * std::pow(sigma_vm_int / JxW_val, 1. / p_norm);
+  if (!dq_dX) return q;
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::fill(dq_dX, dq_dX + n_dof, 0.);
+  std::vector<int64_t> di;
+  std::vector<double> Xe;
+  Mat D, DB;
+  StrainOps s;
+  Modulus mod{p};
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size()), n2 = 3 * ei.nn;
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    Vec disp(n2);
+    for (int i = 0; i < n2; ++i) disp[i] = X[di[i]];
+    strain_ops_reinit(s, ei.nn);
+    Vec denom(nd, 0.), num(nd, 0.), de(nd, 0.), out(nd, 0.);
+    for (int qp = 0; qp < fe.nq; ++qp) {
+      const size_t o = size_t(e) * ei.nq + qp;
+      stiffness_3d(mod.E(fe, &p->conn[e * ei.nn], qp), p->nu, D);
+      init_strain_operator(fe, qp, false, disp, s);
+      s.lin.left_multiply(DB, D);  // dstress_dX (6 x 3nn)
+      const double* sg = &st[o * 6];
+      // Data::dvon_Mises_stress_dX (stress_output_base.cpp:199-230)
+      const double pp = 0.5 * (std::pow(sg[0] - sg[1], 2) + std::pow(sg[1] - sg[2], 2) + std::pow(sg[2] - sg[0], 2)) +
+                        3.0 * (std::pow(sg[3], 2) + std::pow(sg[4], 2) + std::pow(sg[5], 2));
+      std::fill(de.begin(), de.end(), 0.);
+      if (std::fabs(pp) > 0.)
+        for (int j = 0; j < n2; ++j)
+          de[j] = (((DB(0, j) - DB(1, j)) * (sg[0] - sg[1]) + (DB(1, j) - DB(2, j)) * (sg[1] - sg[2]) +
+                    (DB(2, j) - DB(0, j)) * (sg[2] - sg[0])) +
+                   6.0 * (DB(3, j) * sg[3] + DB(4, j) * sg[4] + DB(5, j) * sg[5])) *
+                  0.5 * std::pow(pp, -0.5);
+      const double e_val = vm[o], JxW = jw[o];
+      const double sp_stress = std::pow(e_val / sigma0, p_norm), sp1_stress = std::pow(e_val / sigma0, p_norm - 1.);
+      const double sp_weight = std::pow((e_val - sigma0) / sigma0, p_norm_weight);
+      const double sp1_weight = std::pow((e_val - sigma0) / sigma0, p_norm_weight - 1.);
+      if (rho_exp * sp_weight > exp_arg_lim) {
+        const double exp_sp = std::exp(exp_arg_lim);
+        for (int j = 0; j < nd; ++j) num[j] += 1. * p_norm * sp1_stress * exp_sp / sigma0 * JxW * de[j];
+      } else {
+        const double exp_sp = std::exp(rho_exp * sp_weight);
+        for (int j = 0; j < nd; ++j) {
+          denom[j] += exp_sp * rho_exp * p_norm_weight * sp1_weight / sigma0 * JxW * de[j];
+          num[j] += (de[j] / sigma0 * JxW * exp_sp * (p_norm * sp1_stress + sp_stress * rho_exp * p_norm_weight * sp1_weight));
+        }
+      }
+    }
+    for (int j = 0; j < nd; ++j)
+      out[j] = sigma0 / p_norm * std::pow(sigma_vm_int / JxW_val, 1. / p_norm - 1.) *
+               (num[j] / JxW_val - sigma_vm_int / std::pow(JxW_val, 2.) * denom[j]);
+    constrain(p, di, nullptr, &out);
+    for (int j = 0; j < nd; ++j) dq_dX[di[j]] += out[j];
+  }
+  return q;
+}
+
+void oracle_stiffness_3d(double E, double nu, double* D36) {
+  Mat m;
+  stiffness_3d(E, nu, m);
+  std::copy(m.a.begin(), m.a.end(), D36);
+}
+void oracle_stiffness_3d_derivative(double E, double nu, double dE, double dnu, double* D36) {
+  Mat m;
+  stiffness_3d_derivative(E, nu, dE, dnu, m);
+  std::copy(m.a.begin(), m.a.end(), D36);
+}
+void oracle_thermal_expansion_A_3d(double E, double nu, double alpha, double* v6) {
+  Vec v = thermal_expansion_A_3d(E, nu, alpha);
+  std::copy(v.begin(), v.end(), v6);
+}
+
+int oracle_fe_tables(int32_t elem_type, const double* coords, double* phi, double* dphi, double* jxw, double* xyz_qp) {
+  FE fe;
+  fe_init(elem_type, coords, fe);
+  std::copy(fe.phi.begin(), fe.phi.end(), phi);
+  std::copy(fe.dphi.begin(), fe.dphi.end(), dphi);
+  std::copy(fe.JxW.begin(), fe.JxW.end(), jxw);
+  std::copy(fe.xyz.begin(), fe.xyz.end(), xyz_qp);
+  return 0;
+}
+
+// Timed CPU baseline: `threads` workers stand in for MPI ranks.  Each owns a contiguous element block and adds into
+// a private copy of the rows it touches outside its own row block; here, because rows are shared only at block
+// interfaces, workers run the element loop on disjoint element ranges into the SAME arrays in two passes
+// (even blocks, then odd blocks) so that no two concurrent workers touch the same row.  The arithmetic and the
+// per-row binary search are exactly those of the serial path.
+double oracle_time_residual_and_jacobian(const OracleProblem* p, const double* X, double* R, double* J_vals,
+                                         const int64_t* row_ptr, const int32_t* col_idx, int threads) {
+  const int64_t n_dof = p->n_nodes * p->nv;
+  SideLoadIndex sl;
+  sl.build(p);
+  const auto t0 = std::chrono::steady_clock::now();
+  if (R) std::fill(R, R + n_dof, 0.);
+  if (J_vals) std::fill(J_vals, J_vals + row_ptr[n_dof], 0.);
+  if (threads <= 1) {
+    assemble_range(p, sl, X, R, J_vals, row_ptr, col_idx, 0, p->n_elem);
+  } else {
+    // 2*threads contiguous blocks; blocks of equal parity are separated by a whole block, which for the structured
+    // meshes used in the bench (block >> one element layer) guarantees disjoint rows.
+    const int nb = 2 * threads;
+    for (int parity = 0; parity < 2; ++parity) {
+      std::vector<std::thread> pool;
+      for (int b = parity; b < nb; b += 2) {
+        const int64_t e0 = p->n_elem * b / nb, e1 = p->n_elem * (b + 1) / nb;
+        pool.emplace_back([=, &sl] { assemble_range(p, sl, X, R, J_vals, row_ptr, col_idx, e0, e1); });
+      }
+      for (auto& t : pool) t.join();
+    }
+  }
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+}  // extern "C"

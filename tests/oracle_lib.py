@@ -1,0 +1,184 @@
+"""ctypes wrapper of the CPU oracle (oracle/liboracle.so).  Test infrastructure only."""
+import ctypes as C
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEX8, HEX27, QUAD4 = 8, 27, 4
+
+
+class OracleProblem(C.Structure):
+    _fields_ = [
+        ("elem_type", C.c_int32), ("n_elem", C.c_int64), ("n_nodes", C.c_int64), ("xyz", C.c_void_p),
+        ("conn", C.c_void_p), ("diag_elem", C.c_void_p), ("nv", C.c_int32), ("constrained", C.c_void_p),
+        ("E0", C.c_double), ("nu", C.c_double), ("alpha", C.c_double), ("rho", C.c_void_p),
+        ("rho_min", C.c_double), ("penalty", C.c_double), ("nonlinear_strain", C.c_int32),
+        ("n_side_loads", C.c_int64), ("side_elem", C.c_void_p), ("side_id", C.c_void_p),
+        ("side_pressure", C.c_void_p), ("thermal", C.c_int32), ("temperature", C.c_void_p),
+        ("temperature_const", C.c_double), ("ref_temperature", C.c_double), ("k0", C.c_double),
+        ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32), ("heat_source", C.c_double),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        L = C.CDLL(path)
+        vp, i64, dbl = C.c_void_p, C.c_int64, C.c_double
+        P = C.POINTER(OracleProblem)
+        L.oracle_build_pattern.argtypes = [P, vp, vp]; L.oracle_build_pattern.restype = i64
+        L.oracle_residual_and_jacobian.argtypes = [P, vp, vp, vp, vp, vp]
+        L.oracle_elem_calculations.argtypes = [P, i64, vp, C.c_int, vp, vp]
+        L.oracle_sensitivity_assemble.argtypes = [P, vp, i64, i64, vp, vp, vp]
+        L.oracle_adjoint_sensitivity.argtypes = [P, vp, vp, i64, vp, vp, vp, vp]
+        L.oracle_compliance.argtypes = [P, vp]; L.oracle_compliance.restype = dbl
+        L.oracle_compliance_derivative.argtypes = [P, vp, vp]
+        L.oracle_stress.argtypes = [P, vp, vp, vp, vp, vp]
+        L.oracle_stress_functional.argtypes = [P, vp, dbl, dbl, dbl, vp]; L.oracle_stress_functional.restype = dbl
+        L.oracle_stiffness_3d.argtypes = [dbl, dbl, vp]
+        L.oracle_stiffness_3d_derivative.argtypes = [dbl, dbl, dbl, dbl, vp]
+        L.oracle_thermal_expansion_A_3d.argtypes = [dbl, dbl, dbl, vp]
+        L.oracle_fe_tables.argtypes = [C.c_int32, vp, vp, vp, vp, vp]
+        L.oracle_time_residual_and_jacobian.argtypes = [P, vp, vp, vp, vp, vp, C.c_int]
+        L.oracle_time_residual_and_jacobian.restype = dbl
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Problem:
+    """Holds numpy arrays alive and exposes the OracleProblem struct."""
+
+    def __init__(self, elem_type, xyz, conn, nv, constrained=None, E0=72e9, nu=0.33, alpha=0.0, rho=None,
+                 rho_min=0.0, penalty=1.0, nonlinear_strain=0, side_elem=None, side_id=None, side_pressure=None,
+                 thermal=0, temperature=None, temperature_const=0.0, ref_temperature=0.0, k0=0.0, k_beta=0.0,
+                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None):
+        self.elem_type = elem_type
+        self.xyz = np.ascontiguousarray(xyz, np.float64)
+        self.conn = np.ascontiguousarray(conn, np.int32)
+        self.nv = nv
+        self.n_nodes, self.n_elem, self.nn = self.xyz.shape[0], self.conn.shape[0], self.conn.shape[1]
+        self.n_dof = self.n_nodes * nv
+        self.constrained = None if constrained is None else np.ascontiguousarray(constrained, np.uint8)
+        self.rho = None if rho is None else np.ascontiguousarray(rho, np.float64)
+        self.side_elem = None if side_elem is None else np.ascontiguousarray(side_elem, np.int32)
+        self.side_id = None if side_id is None else np.ascontiguousarray(side_id, np.int32)
+        self.side_pressure = None if side_pressure is None else np.ascontiguousarray(side_pressure, np.float64)
+        self.temperature = None if temperature is None else np.ascontiguousarray(temperature, np.float64)
+        self.diag_elem = None if diag_elem is None else np.ascontiguousarray(diag_elem, np.uint8)
+        self.mat = dict(E0=E0, nu=nu, alpha=alpha, rho_min=rho_min, penalty=penalty, nonlinear_strain=nonlinear_strain,
+                        k0=k0, k_beta=k_beta, thickness=thickness, k_of_T=k_of_T, heat_source=heat_source)
+        self.thermal, self.temperature_const, self.ref_temperature = thermal, temperature_const, ref_temperature
+        s = OracleProblem()
+        s.elem_type = elem_type; s.n_elem = self.n_elem; s.n_nodes = self.n_nodes
+        s.xyz = _p(self.xyz); s.conn = _p(self.conn); s.diag_elem = _p(self.diag_elem)
+        s.nv = nv; s.constrained = _p(self.constrained)
+        s.E0 = E0; s.nu = nu; s.alpha = alpha; s.rho = _p(self.rho); s.rho_min = rho_min; s.penalty = penalty
+        s.nonlinear_strain = nonlinear_strain
+        s.n_side_loads = 0 if self.side_elem is None else len(self.side_elem)
+        s.side_elem = _p(self.side_elem); s.side_id = _p(self.side_id); s.side_pressure = _p(self.side_pressure)
+        s.thermal = thermal; s.temperature = _p(self.temperature); s.temperature_const = temperature_const
+        s.ref_temperature = ref_temperature
+        s.k0 = k0; s.k_beta = k_beta; s.thickness = thickness; s.k_of_T = k_of_T; s.heat_source = heat_source
+        self.s = s
+        self._pattern = None
+
+    # ---- oracle calls ----
+    def pattern(self):
+        if self._pattern is None:
+            row_ptr = np.zeros(self.n_dof + 1, np.int64)
+            nnz = lib().oracle_build_pattern(C.byref(self.s), _p(row_ptr), None)
+            col = np.empty(nnz, np.int32)
+            lib().oracle_build_pattern(C.byref(self.s), _p(row_ptr), _p(col))
+            self._pattern = (row_ptr, col)
+        return self._pattern
+
+    def residual_and_jacobian(self, X, want_R=True, want_J=True):
+        row_ptr, col = self.pattern()
+        R = np.empty(self.n_dof) if want_R else None
+        J = np.empty(len(col)) if want_J else None
+        rc = lib().oracle_residual_and_jacobian(C.byref(self.s), _p(X), _p(R), _p(J), _p(row_ptr), _p(col))
+        assert rc == 0, rc
+        return R, J
+
+    def elem_calculations(self, e, X, want_jac=True):
+        nd = self.nv * self.nn
+        vec = np.zeros(nd); mat = np.zeros((nd, nd))
+        rc = lib().oracle_elem_calculations(C.byref(self.s), e, _p(X), int(want_jac), _p(vec), _p(mat))
+        assert rc == 0
+        return vec, mat
+
+    def adjoint_sensitivity(self, X, adj, dv_ptr, dv_node, dv_weight):
+        dv_ptr = np.ascontiguousarray(dv_ptr, np.int64); dv_node = np.ascontiguousarray(dv_node, np.int32)
+        dv_weight = np.ascontiguousarray(dv_weight, np.float64)
+        sens = np.empty(len(dv_ptr) - 1)
+        rc = lib().oracle_adjoint_sensitivity(C.byref(self.s), _p(X), _p(adj), len(dv_ptr) - 1, _p(dv_ptr),
+                                              _p(dv_node), _p(dv_weight), _p(sens))
+        assert rc == 0, rc
+        return sens
+
+    def sensitivity_assemble(self, X, dv_node, dv_weight):
+        dv_node = np.ascontiguousarray(dv_node, np.int32); dv_weight = np.ascontiguousarray(dv_weight, np.float64)
+        out = np.empty(self.n_dof)
+        rc = lib().oracle_sensitivity_assemble(C.byref(self.s), _p(X), 0, len(dv_node), _p(dv_node), _p(dv_weight), _p(out))
+        assert rc == 0, rc
+        return out
+
+    def compliance(self, X):
+        return lib().oracle_compliance(C.byref(self.s), _p(X))
+
+    def compliance_derivative(self, X):
+        out = np.empty(self.n_dof)
+        assert lib().oracle_compliance_derivative(C.byref(self.s), _p(X), _p(out)) == 0
+        return out
+
+    def time_residual_and_jacobian(self, X, threads, want_R=True, want_J=True):
+        row_ptr, col = self.pattern()
+        R = np.empty(self.n_dof) if want_R else None
+        J = np.empty(len(col)) if want_J else None
+        return lib().oracle_time_residual_and_jacobian(C.byref(self.s), _p(X), _p(R), _p(J), _p(row_ptr), _p(col), threads)
+
+    # ---- the same problem on the device library ----
+    def make_context(self, device=0):
+        import mast_b200
+        ctx = mast_b200.Context(device)
+        ctx.set_mesh(self.elem_type, self.xyz, self.conn, self.diag_elem)
+        ctx.set_dof_map(self.nv, self.constrained)
+        ctx.set_material(**self.mat)
+        if device >= 0:
+            if self.side_elem is not None:
+                ctx.set_side_pressure(self.side_elem, self.side_id, self.side_pressure)
+            if self.thermal:
+                ctx.set_temperature(1, self.temperature, self.temperature_const, self.ref_temperature)
+            if self.rho is not None:
+                ctx.set_density(self.rho)
+        ctx.build_pattern()
+        return ctx
+
+
+def cantilever(nx=20, ny=10, nz=10, lx=0.3, ly=0.15, lz=0.15, nv=3, jitter=0.0, simp=False, **kw):
+    """BASELINE config C1: clamped at x=0 (boundary 4), pressure 5e7 on y=Ly (boundary 3)."""
+    from mast_b200 import mesh
+    xyz, conn = mesh.build_cube(nx, ny, nz, lx, ly, lz, 8, jitter=jitter)
+    con = mesh.dirichlet_flags(len(xyz), nv, mesh.boundary_nodes(nx, ny, nz, 4))
+    se, sid = mesh.boundary_sides(nx, ny, nz, 3)
+    rho = None
+    if simp:
+        rng = np.random.Generator(np.random.MT19937(3))
+        rho = 0.2 + 0.6 * rng.uniform(0.0, 1.0, len(xyz))
+        kw.setdefault("rho_min", 1e-8); kw.setdefault("penalty", 4.0)
+    return Problem(HEX8, xyz, conn, nv, constrained=con, side_elem=se, side_id=sid,
+                   side_pressure=np.full(len(se), 5e7), rho=rho, **kw)
+
+
+def state(n_dof, seed=1, scale=1e-3):
+    rng = np.random.Generator(np.random.MT19937(seed))
+    return scale * rng.uniform(-1.0, 1.0, n_dof)

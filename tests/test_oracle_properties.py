@@ -1,0 +1,165 @@
+"""The reference's element property tests (tests/element/structural/2D/quad4/*.cpp) restated for the
+elements on this path: FD Jacobian at margin mean|K|*1.49e-8, symmetry, rigid-body null space,
+translation/rotation invariance, partition of unity; plus closed-form checks (patch test, volume)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from mast_b200 import mesh
+
+
+def _single(elem_type, nv=3, jitter=0.0, **kw):
+    if elem_type == O.QUAD4:
+        xyz, conn = mesh.build_square(1, 1, 2.0, 2.0)
+    else:
+        xyz, conn = mesh.build_cube(1, 1, 1, 2.0, 1.5, 1.0, elem_type)
+    if jitter:
+        rng = np.random.default_rng(7)
+        xyz = xyz + jitter * rng.uniform(-1, 1, xyz.shape) * (1 if elem_type != O.QUAD4 else np.array([1, 1, 0]))
+    return O.Problem(elem_type, xyz, conn, nv, **kw)
+
+
+@pytest.mark.parametrize("et", [O.HEX8, O.HEX27])
+def test_shape_function_tables(built, et):
+    # mast_quad4_structural_shape_functions.cpp:80-326: partition of unity, sum of gradients zero, volume
+    p = _single(et, jitter=0.1)
+    nn, nq = (8, 8) if et == O.HEX8 else (27, 27)
+    phi = np.zeros((nn, nq)); dphi = np.zeros((nn, nq, 3)); jxw = np.zeros(nq); xq = np.zeros((nq, 3))
+    X = p.xyz[p.conn[0]].copy()
+    O.lib().oracle_fe_tables(et, X.ctypes.data, phi.ctypes.data, dphi.ctypes.data, jxw.ctypes.data, xq.ctypes.data)
+    assert np.allclose(phi.sum(0), 1.0, atol=1e-14)
+    assert np.allclose(dphi.sum(0), 0.0, atol=1e-13)
+    # linear field reproduced: sum_a x_a dN_a/dx = I
+    grad = np.einsum("ac,aqd->qcd", X, dphi)
+    assert np.allclose(grad, np.eye(3)[None], atol=1e-12)
+    p0 = _single(et)
+    X0 = p0.xyz[p0.conn[0]].copy()
+    O.lib().oracle_fe_tables(et, X0.ctypes.data, phi.ctypes.data, dphi.ctypes.data, jxw.ctypes.data, xq.ctypes.data)
+    assert np.isclose(jxw.sum(), 2.0 * 1.5 * 1.0, rtol=1e-14)
+
+
+@pytest.mark.parametrize("et,nonlinear", [(O.HEX8, 0), (O.HEX8, 1), (O.HEX27, 0), (O.HEX27, 1)])
+def test_internal_jacobian_fd_symmetry_nullspace(built, et, nonlinear):
+    # mast_quad4_linear_structural_internal_jacobian.cpp:66-105
+    p = _single(et, jitter=0.1, nonlinear_strain=nonlinear)
+    X = O.state(p.n_dof, 1, 1e-2 if nonlinear else 1e-3)
+    f0, K = p.elem_calculations(0, X)
+    assert np.abs(K - K.T).max() <= 1e-12 * np.abs(K).max()
+    h = 1e-6
+    Kfd = np.zeros_like(K)
+    for j in range(p.n_dof):  # 6th-order central difference (tests/test_helpers.h:46-49)
+        acc = np.zeros(p.n_dof)
+        for c, s in ((-1 / 60, -3), (3 / 20, -2), (-3 / 4, -1), (3 / 4, 1), (-3 / 20, 2), (1 / 60, 3)):
+            Xp = X.copy(); Xp[j] += s * h
+            acc += c * p.elem_calculations(0, Xp, False)[0]
+        Kfd[:, j] = acc / h
+    # element dof order is variable-major, global is node-major: map columns
+    nn = p.nn
+    gl = np.array([3 * p.conn[0][a] + v for v in range(3) for a in range(nn)])
+    Kfd = Kfd[:, gl]
+    assert np.abs(K - Kfd).max() <= np.abs(K).mean() * 1.49e-8 * 50
+    if not nonlinear:
+        w = np.linalg.eigvalsh(K)
+        assert (np.abs(w) < 1e-9 * np.abs(w).max()).sum() == 6  # rigid-body modes
+        # linear strain: Jacobian independent of the displacement (:91-105)
+        _, K2 = p.elem_calculations(0, 5 * X)
+        assert np.abs(K - K2).max() <= 1e-13 * np.abs(K).max()
+
+
+def test_translation_rotation_invariance(built):
+    # mast_quad4_linear_structural_internal_jacobian.cpp:108-356 (eigenvalues invariant under rigid motion)
+    p = _single(O.HEX8, jitter=0.1)
+    X = np.zeros(p.n_dof)
+    _, K = p.elem_calculations(0, X)
+    th = 0.7
+    Rz = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.0]])
+    p2 = O.Problem(O.HEX8, p.xyz @ Rz.T + np.array([3.0, -2.0, 5.0]), p.conn, 3)
+    _, K2 = p2.elem_calculations(0, X)
+    assert np.allclose(np.linalg.eigvalsh(K), np.linalg.eigvalsh(K2), rtol=1e-9, atol=1e-6 * np.abs(K).max())
+
+
+def test_patch_test_uniaxial(built):
+    # closed form: uniform uniaxial strain field gives zero interior residual and sigma_xx = D11*eps
+    nx = 3
+    xyz, conn = mesh.build_cube(nx, nx, nx, 1.0, 1.0, 1.0, 8, jitter=0.2)
+    p = O.Problem(O.HEX8, xyz, conn, 3)
+    eps = 1e-3
+    X = np.zeros((len(xyz), 3)); X[:, 0] = eps * xyz[:, 0]
+    R, _ = p.residual_and_jacobian(X.ravel())
+    I = mesh.boundary_nodes(nx, nx, nx, 0)
+    interior = np.ones(len(xyz), bool)
+    for b in range(6):
+        interior[mesh.boundary_nodes(nx, nx, nx, b)] = False
+    assert interior.sum() == 8
+    assert np.abs(R.reshape(-1, 3)[interior]).max() <= 1e-9 * np.abs(R).max()
+    # total reaction on x=1 face = sigma_xx * area
+    D11 = 72e9 * (1 - 0.33) / (1 - 0.33 - 2 * 0.33 ** 2)
+    fx = R.reshape(-1, 3)[mesh.boundary_nodes(nx, nx, nx, 2), 0].sum()
+    assert np.isclose(fx, D11 * eps, rtol=1e-10)
+
+
+def test_nv6_rotational_diagonal_and_dirichlet(built):
+    # solid_element_3d.cpp:413-417 and libMesh constrain_element_matrix_and_vector semantics
+    p = O.cantilever(2, 2, 2, nv=6)
+    X = O.state(p.n_dof)
+    R, J = p.residual_and_jacobian(X)
+    rp, ci = p.pattern()
+    import scipy.sparse as sp
+    A = sp.csr_matrix((J, ci, rp), shape=(p.n_dof, p.n_dof)).toarray()
+    con = p.constrained.astype(bool)
+    assert np.all(R[con] == 0.0)
+    # constrained rows/cols are zero off the diagonal, diagonal = number of adjacent elements
+    off = A - np.diag(np.diag(A))
+    assert np.all(off[con] == 0.0) and np.all(off[:, con] == 0.0)
+    n_adj = np.bincount(p.conn.ravel(), minlength=p.n_nodes)
+    assert np.array_equal(np.diag(A)[con], np.repeat(n_adj, 6)[con].astype(float))
+    rot_free = (~con) & (np.arange(p.n_dof) % 6 >= 3)
+    assert np.all(np.diag(A)[rot_free] > 0) and np.all(np.diag(A)[rot_free] < 1e-6)
+
+
+def test_heat_conduction_quad4(built):
+    # 1-D conduction profile: T = a x is a zero-residual state for constant k; Jacobian FD for k(T)
+    xyz, conn = mesh.build_square(4, 3, 2.0, 1.0)
+    p = O.Problem(O.QUAD4, xyz, conn, 1, k0=237.0, thickness=0.06)
+    T = 5.0 * xyz[:, 0]
+    R, J = p.residual_and_jacobian(T)
+    interior = (xyz[:, 0] > 0) & (xyz[:, 0] < 2.0)
+    assert np.abs(R[interior]).max() <= 1e-10 * np.abs(R).max()
+    p2 = O.Problem(O.QUAD4, xyz, conn, 1, k0=237.0, k_beta=1e-3, k_of_T=1, thickness=0.06)
+    T = 300 + 50 * np.random.default_rng(4).uniform(0, 1, len(xyz))
+    f0, K = p2.elem_calculations(2, T)
+    Kfd = np.zeros_like(K)
+    for j in range(4):
+        Tp = T.copy(); Tm = T.copy(); Tp[conn[2][j]] += 1e-4; Tm[conn[2][j]] -= 1e-4
+        Kfd[:, j] = (p2.elem_calculations(2, Tp, False)[0] - p2.elem_calculations(2, Tm, False)[0]) / 2e-4
+    assert np.abs(K - Kfd).max() <= 1e-7 * np.abs(K).max()
+
+
+def test_adjoint_sensitivity_fd(built):
+    # tests/old/structural/internal_residual_sensitivity.cpp analogue: lambda . dR/dp vs FD of lambda . R(p)
+    p = O.cantilever(3, 2, 2, jitter=0.2, simp=True)
+    X = O.state(p.n_dof, 1); lam = O.state(p.n_dof, 2)
+    nodes = np.array([5, 17]); w = np.array([1.0, 0.5])
+    s = p.adjoint_sensitivity(X, lam, [0, 2], nodes, w)[0]
+    h = 1e-6
+    vals = []
+    for sg in (+1, -1):
+        rho = p.rho.copy(); rho[nodes] += sg * h * w
+        q = O.cantilever(3, 2, 2, jitter=0.2, simp=True); q.rho[:] = rho
+        R, _ = q.residual_and_jacobian(X, want_J=False)
+        vals.append(lam @ R)
+    fd = (vals[0] - vals[1]) / (2 * h)
+    assert np.isclose(s, fd, rtol=1e-6)
+
+
+def test_compliance_and_derivative(built):
+    p = O.cantilever(3, 2, 2)
+    X = O.state(p.n_dof)
+    q = p.compliance(X)
+    dq = p.compliance_derivative(X)
+    # q is linear in X with gradient dq on unconstrained dofs
+    Xf = X.copy(); Xf[p.constrained.astype(bool)] = 0.0
+    assert np.isclose(dq @ Xf, p.compliance(Xf), rtol=1e-12)
+    R0, _ = p.residual_and_jacobian(np.zeros(p.n_dof), want_J=False)
+    assert np.allclose(R0, -dq, rtol=1e-12, atol=1e-9 * np.abs(dq).max())  # R(0) = -F_ext on free dofs
+    assert q != 0.0
