@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- HEX8 elasticity residual+Jacobian assembly throughput (BASELINE.json metric, config C3).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n 200] [--impl ours|reference]
+
+A "step" is one fused residual_and_jacobian sweep (R and J both requested) over the whole mesh:
+200^3 HEX8 elements on [0,1]^3, interior nodes jittered by 0.2h (general geometry), 3 dofs/node,
+clamped at x=0, pressure on y=1.  N>1 (torchrun): strong scaling -- the same mesh is cut into z-slabs by
+element ownership, every rank assembles the CSR rows of its own nodes (one redundant ghost element layer,
+no exchange of matrix rows) and ghost nodal values of X travel over NCCL before each sweep.
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the C-ABI with
+host buffers (H2D of X, D2H of R and J inside the timed region), `roofline` is the tile-sweep kernel
+against the measured HBM copy bandwidth, `cpu_baseline` times the CPU oracle on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "hex8_elasticity_residual_jacobian_elems_per_s"
+UNIT = "elements/s"
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks and throttle reasons sampled during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].startswith("Active") for r in self.rows)]
+        busy = sorted(s for s in sm if s > 500) or sorted(sm)
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def slab_problem(n, rank, world, jitter, nv=3):
+    """Rank-local view of the n^3 cantilever: local xyz/conn/owned/constrained + halo bookkeeping."""
+    from mast_b200 import mesh
+    xyz, conn = mesh.build_cube(n, n, n, 1.0, 1.0, 1.0, 8, jitter=jitter)
+    npl = (n + 1) * (n + 1)
+    p0 = (n + 1) * rank // world            # owned node planes [p0, p1)
+    p1 = (n + 1) * (rank + 1) // world
+    l0, l1 = max(p0 - 1, 0), min(p1 - 1, n - 1)   # element layers touching owned planes
+    q0, q1 = l0, l1 + 1                            # local node planes [q0, q1]
+    node_lo = q0 * npl
+    lxyz = xyz[node_lo:(q1 + 1) * npl]
+    lconn = conn[l0 * n * n:(l1 + 1) * n * n] - node_lo
+    plane = np.arange(len(lxyz)) // npl + q0
+    owned = ((plane >= p0) & (plane < p1)).astype(np.uint8)
+    con = np.zeros((len(lxyz), nv), np.uint8)
+    con[np.isclose(lxyz[:, 0], 0.0)] = 1
+    # pressure on y = 1 (libMesh side 3) of the local elements
+    j = (np.arange(len(lconn)) // n) % n
+    se = np.flatnonzero(j == n - 1).astype(np.int32)
+    info = dict(p0=p0, p1=p1, q0=q0, q1=q1, npl=npl, n_owned_elem=None)
+    # elements "owned" by the rank for the throughput count: layers [p0, p1) clipped (each element counted once)
+    e0, e1 = min(p0, n), min(p1, n)
+    info["n_owned_elem"] = (e1 - e0) * n * n
+    return lxyz, lconn.astype(np.int32), owned, con.ravel(), se, info
+
+
+def make_context(lxyz, lconn, owned, con, se, device, nv=3):
+    import mast_b200
+    ctx = mast_b200.Context(device)
+    ctx.set_mesh(mast_b200.HEX8, lxyz, lconn)
+    ctx.set_dof_map(nv, con, owned if not owned.all() else None)
+    ctx.set_material(E0=72e9, nu=0.33, alpha=1.5e-5)
+    ctx.set_side_pressure(se, np.full(len(se), 3, np.int32), np.full(len(se), 5e7))
+    ctx.build_pattern()
+    return ctx
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the CPU restatement of MAST's assembly loop (the reference itself cannot be built:
+    libMesh/PETSc/Eigen/MPI are absent) on all host cores, bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import __graft_entry__ as g
+    g.build(force=False)
+    import oracle_lib as O
+    cores = os.cpu_count() or 1
+    m = args.cpu_n
+    prob = O.cantilever(m, m, m, 1.0, 1.0, 1.0, nv=3, jitter=0.2)
+    X = O.state(prob.n_dof, 1)
+    prob.pattern()
+    for _ in range(max(args.warmup, 1) if args.quick_ref else 1):
+        prob.time_residual_and_jacobian(X, cores)
+    ts = [prob.time_residual_and_jacobian(X, cores) for _ in range(args.steps)]
+    t = float(np.sum(ts))
+    val = prob.n_elem * args.steps / t
+    out = {"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": f"C3 sample: {m}^3 of the 200^3 HEX8 linear-elastic cantilever, jittered, nv=3, R+J",
+                      "elements_per_step": prob.n_elem},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                            "sample": f"{m}^3 elements per step, {args.steps} steps, {cores} threads"},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--n", type=int, default=200, help="elements per direction (C3: 200)")
+    ap.add_argument("--jitter", type=float, default=0.2)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-n", type=int, default=48, help="edge of the CPU-baseline sample mesh")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick-ref", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(ROOT, "mast-multiphysics_b200", "libmast_b200.so")):
+        g.build(force=False)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the assembly path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n, nv = args.n, 3
+    t0 = time.time()
+    lxyz, lconn, owned, con, se, info = slab_problem(n, rank, world, args.jitter, nv)
+    ctx = make_context(lxyz, lconn, owned, con, se, local_rank, nv)
+    plan_s = time.time() - t0
+    n_loc_dof = len(lxyz) * nv
+    npl = info["npl"]
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    # state: the global seeded vector restricted to the local node range
+    rng = np.random.Generator(np.random.MT19937(1))
+    Xg = 1e-3 * rng.uniform(-1.0, 1.0, (n + 1) ** 3 * nv)
+    Xl = Xg[info["q0"] * npl * nv:(info["q1"] + 1) * npl * nv].copy()
+    dX = torch.from_numpy(Xl).cuda()
+    dR = torch.empty(n_loc_dof, dtype=torch.float64, device="cuda")
+    dJ = torch.empty(ctx.nnz, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+
+    def halo_exchange():
+        """AssemblyBase::build_localized_vector: ghost planes of X from the neighbouring ranks (NCCL P2P)."""
+        if world == 1:
+            return
+        ops = []
+        w = npl * nv
+        p0, p1, q0 = info["p0"], info["p1"], info["q0"]
+        if rank > 0:      # my first owned plane -> rank-1's upper ghost; its last owned plane -> my lower ghost
+            ops.append(dist.P2POp(dist.isend, dX[(p0 - q0) * w:(p0 - q0 + 1) * w], rank - 1))
+            ops.append(dist.P2POp(dist.irecv, dX[(p0 - 1 - q0) * w:(p0 - q0) * w], rank - 1))
+        if rank < world - 1:
+            ops.append(dist.P2POp(dist.isend, dX[(p1 - 1 - q0) * w:(p1 - q0) * w], rank + 1))
+            ops.append(dist.P2POp(dist.irecv, dX[(p1 - q0) * w:(p1 - q0 + 1) * w], rank + 1))
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        stream.wait_stream(torch.cuda.current_stream())
+
+    def step_device():
+        halo_exchange()
+        ctx.residual_and_jacobian(dX, dR, dJ)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kern_ms, sweep_ms = [], []
+    launches0 = ctx.stats()["kernel_launches"]
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        s = ctx.stats()
+        kern_ms.append(s["last_main_kernel_ms"]); sweep_ms.append(s["last_sweep_ms"])
+    ev1.record(stream)
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = ctx.stats()["kernel_launches"] - launches0
+    clocks = sampler.finish() if sampler else None
+
+    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([float(info["n_owned_elem"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    total_ms = float(tt.item())
+    n_elem_global = int(cnt.item())
+    value = n_elem_global * args.steps / (total_ms * 1e-3)
+
+    # ---- end-to-end through the C-ABI with host buffers (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            hX = torch.from_numpy(Xl).pin_memory()
+            hR = torch.empty(n_loc_dof, dtype=torch.float64).pin_memory()
+            hJ = torch.empty(ctx.nnz, dtype=torch.float64).pin_memory()
+            pinned = True
+        except Exception:
+            hX = torch.from_numpy(Xl); hR = torch.empty(n_loc_dof, dtype=torch.float64)
+            hJ = torch.empty(ctx.nnz, dtype=torch.float64); pinned = False
+        nX, nR, nJ = hX.numpy(), hR.numpy(), hJ.numpy()
+        del dJ
+        torch.cuda.empty_cache()
+        e_steps = max(1, min(args.steps, 3))
+        ctx.residual_and_jacobian(nX, nR, nJ)  # warm-up (allocates the library's staging buffers)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(e_steps):
+            ctx.residual_and_jacobian(nX, nR, nJ)
+        f1.record(stream)
+        barrier()
+        ems = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_elem_global * e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(nX.nbytes), "d2h_bytes_per_step": int(nR.nbytes + nJ.nbytes),
+               "steps": e_steps, "pinned": pinned,
+               "note": "host X in; host R and all CSR values out (PCIe copies inside the timed region); per-rank bytes"}
+        check = float(np.abs(nJ).max())
+        assert np.isfinite(check) and check > 0
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nnz = ctx.nnz
+        n_loc_elem = len(lconn)
+        # algorithmic bytes per launch: CSR values once + R + X + coordinates + connectivity
+        alg_bytes = nnz * 8 + ctx.n_rows * 8 + n_loc_dof * 8 + len(lxyz) * 24 + n_loc_elem * 32
+        k_ms = float(np.mean(kern_ms))
+        achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic_bytes_per_launch.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get("hex8_sweep_kernel")
+            except Exception:
+                traffic = None
+        st = ctx.stats()
+        # fp64 work actually executed per launch (visits incl. ghost recompute): DMMA 18*512 + geometry/strain ~ 2.6k
+        flops_exec = st["n_visits"] * (18 * 512 + 8 * 2 * 330)
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"C3: {n}^3 HEX8 linear elasticity, residual+Jacobian, full CSR (nv=3, "
+                                   f"{(n + 1) ** 3 * 3} dof), interior nodes jittered {args.jitter}h",
+                       "elements": n_elem_global, "nnz_rank0": int(nnz), "partition": f"z-slabs x{world}",
+                       "l2_policy": "inputs and outputs larger than L2 (15.6 GB of CSR values streamed per step)",
+                       "plan_build_s": round(plan_s, 1)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "hex8_sweep_kernel",
+                         "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "bytes_per_element": alg_bytes / n_loc_elem,
+                         "fp64": {"executed_tflops": flops_exec / (k_ms * 1e-3) / 1e12, "peak_tflops": 36.7,
+                                  "peak_source": "profiles/r01_fp64_pipes.md (DFMA = DMMA = 36.7-37.1 TF, one shared pipe)"}},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "kernel_share_of_step": float(np.sum(kern_ms) / total_ms),
+        }
+        if not args.no_cpu:
+            import oracle_lib as O
+            cores = os.cpu_count() or 1
+            m = args.cpu_n
+            prob = O.cantilever(m, m, m, 1.0, 1.0, 1.0, nv=3, jitter=args.jitter)
+            Xc = O.state(prob.n_dof, 1)
+            prob.pattern()
+            t1 = prob.time_residual_and_jacobian(Xc, 1) if m <= 32 else None
+            tc = min(prob.time_residual_and_jacobian(Xc, cores) for _ in range(2))
+            out["cpu_baseline"] = {"value": prob.n_elem / tc, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{m}^3-element block of the same workload, oracle (C++ restatement of MAST's "
+                                             f"loop) with {cores} threads, best of 2",
+                                   "single_core_value": (prob.n_elem / t1) if t1 else None}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -86,10 +86,10 @@ struct mastb200_context {
 
   // device: plan
   DevBuf<TileDesc> d_tiles;
-  DevBuf<StepDesc> d_steps;
-  DevBuf<int32_t> d_tile_nodes, d_tile_acc_off, d_tile_nbr_cnt, d_visit_elem, d_node_row, d_n_adj, d_n_adj_diag, d_owned_nodes;
-  DevBuf<uint16_t> d_nbr_local, d_visit_ln;
-  DevBuf<uint8_t> d_visit_slot, d_cmask;
+  DevBuf<VisitRec8> d_visits;
+  DevBuf<int32_t> d_tile_nodes, d_tile_acc_off, d_tile_nbr_cnt, d_node_row, d_n_adj, d_n_adj_diag, d_owned_nodes;
+  DevBuf<uint16_t> d_nbr_local;
+  DevBuf<uint8_t> d_cmask;
   DevBuf<int64_t> d_nbr_ptr;
   // device: mesh + state + staging for host pointers
   DevBuf<double> d_xyz, d_X, d_adj, d_rho, d_T, d_R, d_J, d_G, d_dq, d_partial, d_scalar;
@@ -165,10 +165,9 @@ int64_t plan_nnz(const mastb200_context* ctx) {
 void fill_params(mastb200_context* ctx, SweepParams& p) {
   std::memset(&p, 0, sizeof p);
   p.tiles = ctx->d_tiles.p; p.n_tiles = (int32_t)ctx->plan.tiles.size();
-  p.steps = ctx->d_steps.p;
   p.tile_nodes = ctx->d_tile_nodes.p; p.tile_acc_off = ctx->d_tile_acc_off.p; p.tile_nbr_cnt = ctx->d_tile_nbr_cnt.p;
   p.nbr_local = ctx->d_nbr_local.p;
-  p.visit_elem = ctx->d_visit_elem.p; p.visit_ln = ctx->d_visit_ln.p; p.visit_slot = ctx->d_visit_slot.p;
+  p.visits = ctx->d_visits.p;
   p.nbr_ptr = ctx->d_nbr_ptr.p; p.node_row = ctx->d_node_row.p;
   p.n_adj_elem = ctx->d_n_adj.p; p.n_adj_diag = ctx->d_n_adj_diag.p;
   p.xyz = ctx->d_xyz.p;
@@ -493,14 +492,11 @@ int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz)
     return MASTB200_OK;
   }
   CU(ctx->d_tiles.upload(P.tiles, ctx->stream));
-  CU(ctx->d_steps.upload(P.steps, ctx->stream));
   CU(ctx->d_tile_nodes.upload(P.tile_nodes, ctx->stream));
   CU(ctx->d_tile_acc_off.upload(P.tile_acc_off, ctx->stream));
   CU(ctx->d_tile_nbr_cnt.upload(P.tile_nbr_cnt, ctx->stream));
   CU(ctx->d_nbr_local.upload(P.nbr_local, ctx->stream));
-  CU(ctx->d_visit_elem.upload(P.visit_elem, ctx->stream));
-  CU(ctx->d_visit_ln.upload(P.visit_ln, ctx->stream));
-  CU(ctx->d_visit_slot.upload(P.visit_slot, ctx->stream));
+  CU(ctx->d_visits.upload(P.visits8, ctx->stream));
   CU(ctx->d_nbr_ptr.upload(P.nbr_ptr, ctx->stream));
   CU(ctx->d_node_row.upload(P.node_row, ctx->stream));
   CU(ctx->d_n_adj.upload(P.n_adj_elem, ctx->stream));

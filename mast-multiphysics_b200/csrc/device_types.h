@@ -10,14 +10,11 @@ struct SweepParams {
   // ---- static plan (device pointers) ----
   const TileDesc* tiles;
   int32_t n_tiles;
-  const StepDesc* steps;
   const int32_t* tile_nodes;
   const int32_t* tile_acc_off;
   const int32_t* tile_nbr_cnt;
   const uint16_t* nbr_local;
-  const int32_t* visit_elem;
-  const uint16_t* visit_ln;
-  const uint8_t* visit_slot;
+  const VisitRec8* visits;
   const int64_t* nbr_ptr;     // per owned row: offset (in node blocks) of its first neighbour
   const int32_t* node_row;    // global node -> owned row or -1
   const int32_t* n_adj_elem;  // per node

@@ -3,15 +3,15 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <thread>
 
 namespace mastb200 {
 
 int64_t Plan::bytes() const {
-  return (int64_t)(tiles.size() * sizeof(TileDesc) + steps.size() * sizeof(StepDesc) + tile_nodes.size() * 4 +
-                   tile_acc_off.size() * 4 + tile_nbr_cnt.size() * 4 + nbr_local.size() * 2 + visit_elem.size() * 4 +
-                   visit_ln.size() * 2 + visit_slot.size());
+  return (int64_t)(tiles.size() * sizeof(TileDesc) + tile_nodes.size() * 4 + tile_acc_off.size() * 4 +
+                   tile_nbr_cnt.size() * 4 + nbr_local.size() * 2 + visits8.size() * sizeof(VisitRec8));
 }
 
 namespace {
@@ -28,10 +28,9 @@ void parallel_for(int64_t n, F f) {
 }
 
 struct TileBuild {
-  std::vector<int32_t> nodes, acc_off, nbr_cnt, velem;
-  std::vector<uint16_t> nbrl, vln;
-  std::vector<uint8_t> vslot;
-  std::vector<int32_t> step_sizes;
+  std::vector<int32_t> nodes, acc_off, nbr_cnt;
+  std::vector<uint16_t> nbrl;
+  std::vector<VisitRec8> visits;
   int32_t n_owned = 0, arena = 0, blocks = 0;
 };
 
@@ -101,6 +100,8 @@ std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double
     });
   }
 
+  if (nn != 8) return "";  // pattern only: the tile plan below is laid out for HEX8 visit records
+
   // ---- recursive coordinate bisection of the owned nodes into tiles ---------------------------
   // A leaf is accepted when its accumulators fit the arena; the halo limit is verified when the tile is built
   // and the leaf is split again if it fails.
@@ -126,19 +127,32 @@ std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double
     int ax = 0;
     for (int c = 1; c < 3; ++c)
       if (hi[c] - lo[c] > hi[ax] - lo[ax]) ax = c;
-    const int64_t mid = r.b + (r.e - r.b) / 2;
+    const int64_t cnt = r.e - r.b;
+    const int64_t mid = r.b + cnt / 2;
     auto key = [&](int32_t n) { return xyz[(int64_t)n * 3 + ax]; };
-    std::nth_element(perm.begin() + r.b, perm.begin() + mid, perm.begin() + r.e,
-                     [&](int32_t a, int32_t b) { return key(a) < key(b) || (key(a) == key(b) && a < b); });
-    // keep coordinate planes together: move the cut to a place where the coordinate changes
-    const double vmid = key(perm[mid]);
-    const double tol = 1e-9 * std::max(hi[ax] - lo[ax], 1e-300);
-    auto it_lo = std::partition(perm.begin() + r.b, perm.begin() + mid, [&](int32_t n) { return key(n) < vmid - tol; });
-    auto it_hi = std::partition(perm.begin() + mid, perm.begin() + r.e, [&](int32_t n) { return key(n) <= vmid + tol; });
-    const int64_t cut_lo = it_lo - perm.begin(), cut_hi = it_hi - perm.begin();
-    int64_t cut = (mid - cut_lo <= cut_hi - mid) ? cut_lo : cut_hi;
-    if (cut <= r.b || cut >= r.e) cut = (cut == cut_lo) ? cut_hi : cut_lo;
-    if (cut <= r.b || cut >= r.e) cut = mid;  // all nodes on one plane along this axis: plain median
+    auto less = [&](int32_t a, int32_t b) { return key(a) < key(b) || (key(a) == key(b) && a < b); };
+    // Cut near the median but at the widest coordinate gap inside a window of about one mesh "plane" of nodes, so
+    // that tiles of (possibly jittered) structured meshes end on whole node planes and keep a small halo.
+    int64_t W = (int64_t)std::ceil(std::pow((double)cnt, 2.0 / 3.0)) + 1;
+    W = std::min(W, std::min(mid - r.b, r.e - mid) - 1);
+    int64_t cut = mid;
+    if (W >= 1) {
+      auto b0 = perm.begin() + (mid - W), b1 = perm.begin() + (mid + W);
+      std::nth_element(perm.begin() + r.b, b0, perm.begin() + r.e, less);
+      std::nth_element(b0, b1, perm.begin() + r.e, less);
+      std::sort(b0, b1, less);
+      double best = -1.;
+      for (int64_t k = mid - W + 1; k < mid + W; ++k) {
+        const double gap = key(perm[k]) - key(perm[k - 1]);
+        const bool closer = std::llabs(k - mid) < std::llabs(cut - mid);
+        if (gap > best * (1. + 1e-9) + 1e-300 || (gap >= best * (1. - 1e-9) && closer)) {
+          if (gap > best) best = gap;
+          cut = k;
+        }
+      }
+    } else {
+      std::nth_element(perm.begin() + r.b, perm.begin() + mid, perm.begin() + r.e, less);
+    }
     out.push_back({r.b, cut});
     out.push_back({cut, r.e});
   };
@@ -230,33 +244,40 @@ std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double
             if (l < T.n_owned) used[l] |= 1u << c;
           }
         }
-        T.step_sizes.assign(ncol, 0);
-        for (size_t v = 0; v < elems.size(); ++v) T.step_sizes[colour[v]]++;
-        std::vector<int32_t> start(ncol + 1, 0);
-        for (int32_t c = 0; c < ncol; ++c) start[c + 1] = start[c] + T.step_sizes[c];
+        // accumulation order: colour-major (conflicting visits end up far apart in the order), ascending element id
+        // within a colour; rank = position of the visit among the visits of each of its owned nodes
+        std::vector<int32_t> csize(ncol, 0), start(ncol + 1, 0);
+        for (size_t v = 0; v < elems.size(); ++v) csize[colour[v]]++;
+        for (int32_t c = 0; c < ncol; ++c) start[c + 1] = start[c] + csize[c];
         const size_t nv_ = elems.size();
-        T.velem.resize(nv_);
-        T.vln.resize(nv_ * nn);
-        T.vslot.assign(nv_ * nn * nn, 0);
-        for (size_t v = 0; v < nv_; ++v) {
-          const size_t o = (size_t)start[colour[v]]++;
-          const int32_t* c = conn + (int64_t)elems[v] * nn;
-          T.velem[o] = elems[v];
-          for (int a = 0; a < nn; ++a) T.vln[o * nn + a] = (uint16_t)local[c[a]];
+        std::vector<int32_t> order(nv_);
+        for (size_t v = 0; v < nv_; ++v) order[start[colour[v]]++] = (int32_t)v;
+        T.visits.resize(nv_);
+        used.assign(T.n_owned, 0u);  // reused as per-node visit counter
+        for (size_t o = 0; o < nv_; ++o) {
+          const int32_t e = elems[order[o]];
+          const int32_t* c = conn + (int64_t)e * nn;
+          VisitRec8& V = T.visits[o];
+          std::memset(&V, 0, sizeof V);
+          V.elem = e;
+          for (int a = 0; a < nn; ++a) V.ln[a] = (uint16_t)local[c[a]];
           for (int a = 0; a < nn; ++a) {
-            if (local[c[a]] >= T.n_owned) continue;
+            const int32_t l = local[c[a]];
+            if (l >= T.n_owned) continue;
+            if (used[l] > 250) fail = 3;
+            V.rank[a] = (uint8_t)used[l]++;
             const int32_t row = P.node_row[c[a]];
             const int32_t* nb = P.nbr.data() + P.nbr_ptr[row];
             const int32_t* ne = P.nbr.data() + P.nbr_ptr[row + 1];
-            for (int b = 0; b < nn; ++b)
-              T.vslot[(o * nn + a) * nn + b] = (uint8_t)(std::lower_bound(nb, ne, c[b]) - nb);
+            for (int b = 0; b < nn; ++b) V.slot[a * nn + b] = (uint8_t)(std::lower_bound(nb, ne, c[b]) - nb);
           }
         }
         for (int32_t n : T.nodes) local[n] = -1;
       }
     });
     if (fail == 1) return "a single node does not fit the shared-memory arena";
-    if (fail == 2) return "tile needs more than 32 steps";
+    if (fail == 2) return "tile needs more than 32 colours";
+    if (fail == 3) return "node touched by more than 250 elements";
     std::vector<Range> next;
     for (size_t t = 0; t < leaves.size(); ++t) {
       if (too_big[t]) split(leaves[t], next);
@@ -268,38 +289,33 @@ std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double
   std::sort(built.begin(), built.end(), [](const TileBuild& a, const TileBuild& b) { return a.nodes[0] < b.nodes[0]; });
 
   // ---- concatenate ---------------------------------------------------------------------------------
-  size_t tot_nodes = 0, tot_vis = 0, tot_steps = 0, tot_nbrl = 0;
+  size_t tot_nodes = 0, tot_vis = 0, tot_nbrl = 0;
   for (const TileBuild& T : built) {
-    tot_nodes += T.nodes.size(); tot_vis += T.velem.size(); tot_steps += T.step_sizes.size(); tot_nbrl += T.nbrl.size();
+    tot_nodes += T.nodes.size(); tot_vis += T.visits.size(); tot_nbrl += T.nbrl.size();
   }
   if (tot_nodes >= (size_t(1) << 31) || tot_vis >= (size_t(1) << 31) || tot_nbrl >= (size_t(1) << 31)) return "plan too large";
   P.tiles.reserve(built.size());
-  P.steps.reserve(tot_steps);
   P.tile_nodes.reserve(tot_nodes); P.tile_acc_off.reserve(tot_nodes); P.tile_nbr_cnt.reserve(tot_nodes);
   P.nbr_local.reserve(tot_nbrl);
-  P.visit_elem.reserve(tot_vis); P.visit_ln.reserve(tot_vis * nn); P.visit_slot.reserve(tot_vis * nn * nn);
+  P.visits8.reserve(tot_vis);
   for (TileBuild& T : built) {
     TileDesc d;
     d.node_begin = (int32_t)P.tile_nodes.size();
     d.n_owned = T.n_owned;
     d.n_nodes = (int32_t)T.nodes.size();
-    d.step_begin = (int32_t)P.steps.size();
-    d.n_steps = (int32_t)T.step_sizes.size();
+    d.visit_begin = (int32_t)P.visits8.size();
+    d.n_visits = (int32_t)T.visits.size();
     d.arena_doubles = T.arena;
     d.nbrl_begin = (int32_t)P.nbr_local.size();
     d.blocks_total = T.blocks;
-    int32_t vb = (int32_t)P.visit_elem.size();
-    for (int32_t s : T.step_sizes) { P.steps.push_back({vb, s}); vb += s; }
     P.tile_nodes.insert(P.tile_nodes.end(), T.nodes.begin(), T.nodes.end());
     P.tile_acc_off.insert(P.tile_acc_off.end(), T.acc_off.begin(), T.acc_off.end());
     P.tile_nbr_cnt.insert(P.tile_nbr_cnt.end(), T.nbr_cnt.begin(), T.nbr_cnt.end());
     P.nbr_local.insert(P.nbr_local.end(), T.nbrl.begin(), T.nbrl.end());
-    P.visit_elem.insert(P.visit_elem.end(), T.velem.begin(), T.velem.end());
-    P.visit_ln.insert(P.visit_ln.end(), T.vln.begin(), T.vln.end());
-    P.visit_slot.insert(P.visit_slot.end(), T.vslot.begin(), T.vslot.end());
+    P.visits8.insert(P.visits8.end(), T.visits.begin(), T.visits.end());
     P.tiles.push_back(d);
     TileBuild().nodes.swap(T.nodes);  // release memory early
-    std::vector<uint8_t>().swap(T.vslot);
+    std::vector<VisitRec8>().swap(T.visits);
   }
   return err;
 }

@@ -21,17 +21,25 @@ struct TileDesc {
   int32_t node_begin;     // offset into tile_nodes (owned nodes first, sorted by id; then halo nodes)
   int32_t n_owned;
   int32_t n_nodes;        // owned + halo
-  int32_t step_begin;
-  int32_t n_steps;
+  int32_t visit_begin;    // visits of the tile, in the order in which they are accumulated
+  int32_t n_visits;
   int32_t arena_doubles;  // shared-memory accumulator doubles used by this tile
   int32_t nbrl_begin;     // offset into nbr_local of the first owned node's neighbour list
   int32_t blocks_total;   // sum over owned nodes of their neighbour counts
 };
 
-struct StepDesc {
-  int32_t visit_begin;
-  int32_t n_visits;
+// One element visit of a HEX8 tile, 96 bytes (six 16-byte words; a chunk of 4 visits is loaded with 3 coalesced
+// 4-byte loads per lane).  rank[a] is the number of earlier visits of the same tile that touch owned node a: the
+// device accumulates into node a only once its per-node counter equals rank[a], which fixes the summation order
+// into every CSR entry without CTA-wide barriers.
+struct alignas(16) VisitRec8 {
+  uint16_t ln[8];    // tile-local node ids
+  uint8_t rank[8];
+  int32_t elem;
+  int32_t pad;
+  uint8_t slot[64];  // [a][b]: position of node b in the neighbour list (CSR row) of node a, for owned a
 };
+static_assert(sizeof(VisitRec8) == 96, "VisitRec8 must be 96 bytes");
 
 struct PlanLimits {
   int32_t arena_doubles;    // accumulator capacity in doubles
@@ -52,15 +60,12 @@ struct Plan {
   std::vector<int32_t> n_adj_diag_elem;  // [n_nodes] number of diagonal_elem_subdomain elements touching it
   // tiles
   std::vector<TileDesc> tiles;
-  std::vector<StepDesc> steps;
   std::vector<int32_t> tile_nodes;       // global node id per tile-local node
   std::vector<int32_t> tile_acc_off;     // per tile-local node: accumulator offset (owned) or -1
   std::vector<int32_t> tile_nbr_cnt;     // per tile-local node: neighbour count (owned) or 0
   std::vector<uint16_t> nbr_local;       // per owned tile node, per neighbour: tile-local id of the neighbour
-  std::vector<int32_t> visit_elem;       // [n_visits]
-  std::vector<uint16_t> visit_ln;        // [n_visits][nn] tile-local node ids
-  std::vector<uint8_t> visit_slot;       // [n_visits][nn][nn] column slot of node b in the row of node a
-  int64_t n_visits() const { return (int64_t)visit_elem.size(); }
+  std::vector<VisitRec8> visits8;        // HEX8 visit records
+  int64_t n_visits() const { return (int64_t)visits8.size(); }
   int64_t bytes() const;
 };
 

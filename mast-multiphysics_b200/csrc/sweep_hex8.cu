@@ -60,9 +60,16 @@ struct Smem {
   double* stage;
   int32_t* accoff;
   int32_t* gid;
+  int32_t* cnt;     // per owned node: number of element contributions accumulated so far
+  uint32_t* rec;    // per warp: the 4 visit records of the current chunk
   uint8_t* nbrcnt;
   uint8_t* cm;
 };
+
+constexpr int REC_WORDS = 24;  // sizeof(VisitRec8) / 4
+
+__device__ __forceinline__ int ld_volatile_s32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
+__device__ __forceinline__ void st_volatile_s32(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
 
 struct Flags {
   bool J, R, G, simp, thermal, nv6;
@@ -201,11 +208,16 @@ __device__ __forceinline__ void stage_write(double* st, int q, const QpData& d) 
 }
 
 // ---- matrix phase: all 32 lanes on one element; lane = (row node a, qp q4 | q4+4) ------------------------------
+// rec: the visit record in shared memory.  All arithmetic (DMMA, lane reductions) happens first; the adds into the
+// tile's rows wait until the per-node counters say that every earlier visit of the plan order has landed.
 __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const double* st,
-                                              int64_t v, int extras_base, int lane) {
+                                              const uint32_t* rec, int extras_base, int lane) {
   const int a = lane >> 2, q4 = lane & 3;
-  const int la = p.visit_ln[v * 8 + a];
-  const unsigned slots = *reinterpret_cast<const uint16_t*>(p.visit_slot + v * 64 + a * 8 + 2 * q4);
+  const uint16_t* rec16 = reinterpret_cast<const uint16_t*>(rec);
+  const uint8_t* rec8 = reinterpret_cast<const uint8_t*>(rec);
+  const int la = rec16[a];
+  const int rank = rec8[16 + a];
+  const unsigned slots = rec16[16 + a * 4 + q4];  // bytes 32 + a*8 + 2*q4
   const int accoff = sm.accoff[la];
   const int nnb = sm.nbrcnt[la];
   double A[3][2];
@@ -214,12 +226,13 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
     A[i][0] = st[(i * 2 + 0) * V_HALF + lane];
     A[i][1] = st[(i * 2 + 1) * V_HALF + lane];
   }
+  double C[3][3][2];
+  double mx = 0., t0 = 0., t1 = 0., t2 = 0., tg = 0.;
   if (fl.J) {
     const double w0 = st[OFF_W + q4], w1 = st[OFF_W + 4 + q4];
     double B[3][2];
 #pragma unroll
     for (int j = 0; j < 3; ++j) { B[j][0] = A[j][0] * w0; B[j][1] = A[j][1] * w1; }
-    double C[3][3][2];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -230,21 +243,9 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) dmma8x8x4(C[i][j][0], C[i][j][1], A[i][h], B[j][h]);
-    if (accoff >= 0) {
-      const int rs = 3 * nnb;
-#pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        double* dst = sm.arena + accoff + 3 * ((slots >> (8 * bb)) & 255u);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) dst[i * rs + j] += C[i][j][bb];
-      }
-    }
     if (fl.nv6) {
       // 1e-20*max(diag K_e) on the rotational diagonal (solid_element_3d.cpp:413-417); diag of K_e from S_aa
-      double mx = 0.;  // the rotational diagonal itself is zero, so the max is at least 0
-      const int bself = a - 2 * q4;
+      const int bself = a - 2 * q4;  // the rotational diagonal itself is zero, so the max is at least 0
       if (bself == 0 || bself == 1) {
         const double s0 = C[0][0][bself & 1], s1 = C[1][1][bself & 1], s2 = C[2][2][bself & 1];
         const double trm = p.mu1 * (s0 + s1 + s2);
@@ -252,24 +253,19 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (q4 == 0 && accoff >= 0) sm.arena[extras_base + la * EXTRA + 4] += 1.0e-20 * mx;
     }
   }
   if (fl.R) {
     const double* P0 = st + OFF_P + q4 * 6;
     const double* P1 = P0 + 24;
-    double t0 = P0[0] * A[0][0] + P0[3] * A[1][0] + P0[5] * A[2][0] + P1[0] * A[0][1] + P1[3] * A[1][1] + P1[5] * A[2][1];
-    double t1 = P0[3] * A[0][0] + P0[1] * A[1][0] + P0[4] * A[2][0] + P1[3] * A[0][1] + P1[1] * A[1][1] + P1[4] * A[2][1];
-    double t2 = P0[5] * A[0][0] + P0[4] * A[1][0] + P0[2] * A[2][0] + P1[5] * A[0][1] + P1[4] * A[1][1] + P1[2] * A[2][1];
+    t0 = P0[0] * A[0][0] + P0[3] * A[1][0] + P0[5] * A[2][0] + P1[0] * A[0][1] + P1[3] * A[1][1] + P1[5] * A[2][1];
+    t1 = P0[3] * A[0][0] + P0[1] * A[1][0] + P0[4] * A[2][0] + P1[3] * A[0][1] + P1[1] * A[1][1] + P1[4] * A[2][1];
+    t2 = P0[5] * A[0][0] + P0[4] * A[1][0] + P0[2] * A[2][0] + P1[5] * A[0][1] + P1[4] * A[1][1] + P1[2] * A[2][1];
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
       t0 += __shfl_xor_sync(0xffffffffu, t0, o);
       t1 += __shfl_xor_sync(0xffffffffu, t1, o);
       t2 += __shfl_xor_sync(0xffffffffu, t2, o);
-    }
-    if (q4 == 0 && accoff >= 0) {
-      double* f = sm.arena + extras_base + la * EXTRA;
-      f[0] += t0; f[1] += t1; f[2] += t2;
     }
   }
   if (fl.G) {
@@ -280,11 +276,39 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
     const double fy = ((a == 2 || a == 3 || a == 6 || a == 7) ? 1. + eta : 1. - eta);
     const double nlo = 0.125 * fx * fy * (a >= 4 ? 1. - gp : 1. + gp);  // zeta = -gp for q < 4
     const double nhi = 0.125 * fx * fy * (a >= 4 ? 1. + gp : 1. - gp);  // zeta = +gp for q >= 4
-    double t = nlo * st[OFF_S + q4] + nhi * st[OFF_S + 4 + q4];
-    t += __shfl_xor_sync(0xffffffffu, t, 1);
-    t += __shfl_xor_sync(0xffffffffu, t, 2);
-    if (q4 == 0 && accoff >= 0) sm.arena[extras_base + la * EXTRA + 3] += t;
+    tg = nlo * st[OFF_S + q4] + nhi * st[OFF_S + 4 + q4];
+    tg += __shfl_xor_sync(0xffffffffu, tg, 1);
+    tg += __shfl_xor_sync(0xffffffffu, tg, 2);
   }
+
+  // ---- ordered accumulation ----
+  const bool own = accoff >= 0;
+  if (own && q4 == 0)
+    while (ld_volatile_s32(sm.cnt + la) != rank) {}
+  __threadfence_block();
+  __syncwarp();
+  if (own) {
+    if (fl.J) {
+      const int rs = 3 * nnb;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        double* dst = sm.arena + accoff + 3 * ((slots >> (8 * bb)) & 255u);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) dst[i * rs + j] += C[i][j][bb];
+      }
+    }
+    if (q4 == 0) {
+      double* ex = sm.arena + extras_base + la * EXTRA;
+      if (fl.R) { ex[0] += t0; ex[1] += t1; ex[2] += t2; }
+      if (fl.G) ex[3] += tg;
+      if (fl.J && fl.nv6) ex[4] += 1.0e-20 * mx;
+    }
+  }
+  __threadfence_block();
+  __syncwarp();
+  if (own && q4 == 0) st_volatile_s32(sm.cnt + la, rank + 1);
 }
 
 // ---- tile flush: S -> K, Dirichlet semantics, coalesced write of the tile's CSR rows -----------------------
@@ -366,8 +390,11 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
   sm.stage = sm.T + MAXN;
   sm.accoff = reinterpret_cast<int32_t*>(sm.stage + WARPS * STAGE_EL * EL_STRIDE);
   sm.gid = sm.accoff + MAXN;
-  sm.nbrcnt = reinterpret_cast<uint8_t*>(sm.gid + MAXN);
+  sm.cnt = sm.gid + MAXN;
+  sm.rec = reinterpret_cast<uint32_t*>(sm.cnt + MAXN);
+  sm.nbrcnt = reinterpret_cast<uint8_t*>(sm.rec + WARPS * 4 * REC_WORDS);
   sm.cm = sm.nbrcnt + MAXN;
+  int& s_next = *reinterpret_cast<int*>(sm.cm + MAXN);  // chunk dispenser of the current tile
 
   Flags fl;
   fl.J = p.J != nullptr; fl.R = p.R != nullptr; fl.G = p.G != nullptr;
@@ -376,10 +403,11 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int el = lane >> 3, q = lane & 7;
   double* my_stage = sm.stage + warp * STAGE_EL * EL_STRIDE;
+  uint32_t* my_rec = sm.rec + warp * 4 * REC_WORDS;
 
   for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
     const TileDesc td = p.tiles[tile];
-    // stage node state of the tile (owned + halo) and clear the accumulators
+    // stage node state of the tile (owned + halo), clear accumulators and counters
     for (int l = tid; l < td.n_nodes; l += THREADS) {
       const int n = p.tile_nodes[td.node_begin + l];
       const unsigned cm = p.cmask ? p.cmask[n] : 0u;
@@ -387,6 +415,7 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
       sm.accoff[l] = p.tile_acc_off[td.node_begin + l];
       sm.nbrcnt[l] = (uint8_t)p.tile_nbr_cnt[td.node_begin + l];
       sm.cm[l] = (uint8_t)cm;
+      sm.cnt[l] = 0;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         sm.xyz[l * 3 + c] = p.xyz[(int64_t)n * 3 + c];
@@ -398,36 +427,63 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
       sm.T[l] = p.temperature ? p.temperature[n] : p.T_const;
     }
     for (int k = tid; k < td.arena_doubles; k += THREADS) sm.arena[k] = 0.;
+    if (tid == 0) s_next = 0;
     __syncthreads();
     const int extras_base = td.arena_doubles - td.n_owned * EXTRA;
+    const int n_chunks = (td.n_visits + 3) >> 2;
+    const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + td.visit_begin);
 
-    for (int s = 0; s < td.n_steps; ++s) {
-      const StepDesc sd = p.steps[td.step_begin + s];
-      for (int base = warp * 4; base < sd.n_visits; base += WARPS * 4) {
-        const bool active = base + el < sd.n_visits;
-        const int64_t v = (int64_t)sd.visit_begin + base + el;
-        QpData d;
-        if (active) {
-          const uint4 pk = *reinterpret_cast<const uint4*>(p.visit_ln + v * 8);
-          int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
-                       int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
-          geometry_phase(p, sm, fl, ln, q, d);
-        }
+    // warps take chunks of 4 consecutive visits in plan order; the records of the next chunk are prefetched into
+    // registers while the current one is processed
+    int c = 0;
+    if (lane == 0) c = atomicAdd(&s_next, 1);
+    c = __shfl_sync(0xffffffffu, c, 0);
+    uint32_t r0 = 0, r1 = 0, r2 = 0;
+    if (c < n_chunks) {
+      const int nw = min(4, td.n_visits - 4 * c) * REC_WORDS;
+      const uint32_t* src = recs + (int64_t)c * 4 * REC_WORDS;
+      if (lane < nw) r0 = src[lane];
+      if (lane + 32 < nw) r1 = src[lane + 32];
+      if (lane + 64 < nw) r2 = src[lane + 64];
+    }
+    while (c < n_chunks) {
+      const int nvis = min(4, td.n_visits - 4 * c);
+      my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
+      __syncwarp();
+      int cn = 0;
+      if (lane == 0) cn = atomicAdd(&s_next, 1);
+      cn = __shfl_sync(0xffffffffu, cn, 0);
+      if (cn < n_chunks) {
+        const int nw = min(4, td.n_visits - 4 * cn) * REC_WORDS;
+        const uint32_t* src = recs + (int64_t)cn * 4 * REC_WORDS;
+        r0 = r1 = r2 = 0;
+        if (lane < nw) r0 = src[lane];
+        if (lane + 32 < nw) r1 = src[lane + 32];
+        if (lane + 64 < nw) r2 = src[lane + 64];
+      }
+      const bool active = el < nvis;
+      QpData d;
+      if (active) {
+        const uint4 pk = *reinterpret_cast<const uint4*>(my_rec + el * REC_WORDS);
+        int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
+                     int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
+        geometry_phase(p, sm, fl, ln, q, d);
+      }
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          __syncwarp();
-          if (active && (el >> 1) == half) stage_write(my_stage + (el & 1) * EL_STRIDE, q, d);
-          __syncwarp();
+      for (int half = 0; half < 2; ++half) {
+        __syncwarp();
+        if (active && (el >> 1) == half) stage_write(my_stage + (el & 1) * EL_STRIDE, q, d);
+        __syncwarp();
 #pragma unroll
-          for (int e2 = 0; e2 < 2; ++e2) {
-            const int ecur = half * 2 + e2;
-            if (base + ecur < sd.n_visits)
-              element_phase(p, sm, fl, my_stage + e2 * EL_STRIDE, (int64_t)sd.visit_begin + base + ecur, extras_base, lane);
-          }
+        for (int e2 = 0; e2 < 2; ++e2) {
+          const int ecur = half * 2 + e2;
+          if (ecur < nvis) element_phase(p, sm, fl, my_stage + e2 * EL_STRIDE, my_rec + ecur * REC_WORDS, extras_base, lane);
         }
       }
-      __syncthreads();
+      __syncwarp();
+      c = cn;
     }
+    __syncthreads();
     flush_tile(p, sm, fl, td, extras_base, warp, lane);
     __syncthreads();
   }
@@ -437,7 +493,7 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
 
 size_t hex8_sweep_smem_bytes(int arena_doubles) {
   return size_t(arena_doubles) * 8 + size_t(MAXN) * 11 * 8 + size_t(WARPS) * STAGE_EL * EL_STRIDE * 8 +
-         size_t(MAXN) * (4 + 4 + 1 + 1);
+         size_t(MAXN) * (4 + 4 + 4 + 1 + 1) + size_t(WARPS) * 4 * REC_WORDS * 4 + 64;  // +64: chunk dispenser, padding
 }
 
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream) {
