@@ -81,16 +81,31 @@ struct mastb200_context {
   mastb200_material mat{};
   bool have_mesh = false, have_dofs = false, have_mat = false, have_plan = false;
 
-  Plan plan;
-  PlanLimits lim{};
-
-  // device: plan
-  DevBuf<TileDesc> d_tiles;
-  DevBuf<VisitRec8> d_visits;
-  DevBuf<int32_t> d_tile_nodes, d_tile_acc_off, d_tile_nbr_cnt, d_node_row, d_n_adj, d_n_adj_diag, d_owned_nodes;
-  DevBuf<uint16_t> d_nbr_local;
+  Pattern pat;
+  // streaming plans: [0] plain layout (R/J of the 3-dof system), [1] aux layout (adjoint, density, temperature, nv=6)
+  struct DevicePlan {
+    bool built = false;
+    PlanLimits lim{};
+    size_t smem = 0;
+    int n_ctas = 0;
+    int64_t n_tiles = 0, n_visits = 0, bytes = 0;
+    int32_t max_live_blocks = 0, max_live_slots = 0;
+    StreamPlan host;  // kept only by planning-only contexts (tests inspect it)
+    DevBuf<TileDesc> tiles;
+    DevBuf<StepDesc> steps;
+    DevBuf<VisitRec8> visits;
+    DevBuf<FlushRow> frows;
+    DevBuf<uint32_t> fent;
+    DevBuf<LoadRec> loads;
+    void reset() {
+      built = false; host = StreamPlan();
+      tiles.release(); steps.release(); visits.release(); frows.release(); fent.release(); loads.release();
+    }
+  } dplan[2];
+  int last_plan = 0;
+  int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
+  DevBuf<int32_t> d_tile_counter, d_owned_nodes;
   DevBuf<uint8_t> d_cmask;
-  DevBuf<int64_t> d_nbr_ptr;
   // device: mesh + state + staging for host pointers
   DevBuf<double> d_xyz, d_X, d_adj, d_rho, d_T, d_R, d_J, d_G, d_dq, d_partial, d_scalar;
   bool rho_set = false, T_nodal = false, thermal = false;
@@ -111,8 +126,6 @@ struct mastb200_context {
   DevBuf<double> d_dv_w, d_sens;
 
   int64_t launches = 0;
-  int n_ctas = 0;
-  size_t smem = 0;
 
   int fail(int code, const char* fmt, ...) {
     char buf[512];
@@ -159,17 +172,50 @@ int finish_out(mastb200_context* ctx, double* ptr, size_t n, const double* dev) 
 }
 
 int64_t plan_nnz(const mastb200_context* ctx) {
-  return ctx->plan.nbr_ptr[ctx->plan.n_owned] * int64_t(ctx->nv) * ctx->nv;
+  return ctx->pat.nbr_ptr[ctx->pat.n_owned] * int64_t(ctx->nv) * ctx->nv;
 }
 
-void fill_params(mastb200_context* ctx, SweepParams& p) {
+// builds (once) the streaming plan for the plain or the aux shared-memory layout and uploads it
+int ensure_plan(mastb200_context* ctx, int aux) {
+  mastb200_context::DevicePlan& D = ctx->dplan[aux];
+  if (D.built) return MASTB200_OK;
+  if (ctx->elem_type != MASTB200_HEX8) return MASTB200_OK;  // pattern only: no device sweep for the type yet
+  const size_t fixed = hex8_sweep_smem_bytes(0, kMaxSlots, kFlushBufBytes, aux != 0);
+  if ((size_t)ctx->max_optin <= fixed + 8192) return ctx->fail(MASTB200_ERR_CUDA, "device shared memory too small");
+  D.lim.arena_blocks = (int32_t)std::min<size_t>((ctx->max_optin - fixed) / 72, 4094) & ~1;
+  D.lim.max_slots = kMaxSlots;
+  D.lim.flush_buf_bytes = kFlushBufBytes;
+  D.lim.sm_count = ctx->sm_count;
+  D.smem = hex8_sweep_smem_bytes(D.lim.arena_blocks, kMaxSlots, kFlushBufBytes, aux != 0);
+  StreamPlan P;
+  const std::string e = build_stream_plan(ctx->pat, ctx->xyz.data(), ctx->conn.data(),
+                                          ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), D.lim, P);
+  if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+  D.n_tiles = (int64_t)P.tiles.size(); D.n_visits = P.n_visits(); D.bytes = P.bytes();
+  D.max_live_blocks = P.max_live_blocks; D.max_live_slots = P.max_live_slots;
+  D.n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(D.n_tiles, ctx->sm_count));
+  if (ctx->planning_only) {
+    D.host = std::move(P);
+  } else {
+    CU(D.tiles.upload(P.tiles, ctx->stream));
+    CU(D.steps.upload(P.steps, ctx->stream));
+    CU(D.visits.upload(P.visits, ctx->stream));
+    CU(D.frows.upload(P.flush_rows, ctx->stream));
+    CU(D.fent.upload(P.flush_ent, ctx->stream));
+    CU(D.loads.upload(P.loads, ctx->stream));
+    CU(ctx->d_tile_counter.ensure(4));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  D.built = true;
+  return MASTB200_OK;
+}
+
+void fill_params(mastb200_context* ctx, int aux, SweepParams& p) {
   std::memset(&p, 0, sizeof p);
-  p.tiles = ctx->d_tiles.p; p.n_tiles = (int32_t)ctx->plan.tiles.size();
-  p.tile_nodes = ctx->d_tile_nodes.p; p.tile_acc_off = ctx->d_tile_acc_off.p; p.tile_nbr_cnt = ctx->d_tile_nbr_cnt.p;
-  p.nbr_local = ctx->d_nbr_local.p;
-  p.visits = ctx->d_visits.p;
-  p.nbr_ptr = ctx->d_nbr_ptr.p; p.node_row = ctx->d_node_row.p;
-  p.n_adj_elem = ctx->d_n_adj.p; p.n_adj_diag = ctx->d_n_adj_diag.p;
+  mastb200_context::DevicePlan& D = ctx->dplan[aux];
+  p.tiles = D.tiles.p; p.n_tiles = (int32_t)D.n_tiles;
+  p.steps = D.steps.p; p.visits = D.visits.p; p.flush_rows = D.frows.p; p.flush_ent = D.fent.p; p.loads = D.loads.p;
+  p.tile_counter = ctx->d_tile_counter.p;
   p.xyz = ctx->d_xyz.p;
   p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
   const mastb200_material& m = ctx->mat;
@@ -180,14 +226,14 @@ void fill_params(mastb200_context* ctx, SweepParams& p) {
   p.rho_min = m.rho_min; p.penalty = m.penalty;
   p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
   p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
-  p.k0 = m.k0; p.k_beta = m.k_beta; p.thickness = m.thickness; p.heat_source = m.heat_source; p.k_of_T = m.k_of_T;
   p.nv = ctx->nv;
   p.thermal = ctx->thermal ? 1 : 0;
-  p.nonlinear = m.nonlinear_strain;
   p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
   p.temperature = (ctx->thermal && ctx->T_nodal) ? (ctx->T_ext ? ctx->T_ext : ctx->d_T.p) : nullptr;
-  p.arena_doubles = ctx->lim.arena_doubles;
-  p.max_tile_nodes = ctx->lim.max_tile_nodes;
+  p.arena_blocks = D.lim.arena_blocks;
+  p.max_slots = D.lim.max_slots;
+  p.flush_buf_bytes = D.lim.flush_buf_bytes;
+  p.aux = aux;
 }
 
 FaceLoadPlan face_plan(const mastb200_context* ctx) {
@@ -223,8 +269,13 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
                      "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
   const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
   const size_t nnz = (size_t)plan_nnz(ctx);
+  // the plain shared-memory layout serves residual/Jacobian sweeps of the 3-dof system with a homogeneous modulus and
+  // no thermal load; everything else stages the auxiliary nodal fields and per-node extras
+  const int aux = (G || ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
+  if ((rc = ensure_plan(ctx, aux))) return rc;
+  ctx->last_plan = aux;
   SweepParams p;
-  fill_params(ctx, p);
+  fill_params(ctx, aux, p);
   const double *dX = nullptr, *dadj = nullptr;
   double *dR = nullptr, *dJ = nullptr, *dG = nullptr;
   if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
@@ -239,7 +290,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     if (dG) CU(cudaMemsetAsync(dG, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
   }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CU(launch_hex8_sweep(p, ctx->n_ctas, ctx->stream));
+  CU(launch_hex8_sweep(p, ctx->dplan[aux].n_ctas, ctx->stream));
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (dR && !ctx->fl_node.empty()) {
@@ -465,54 +516,32 @@ int mastb200_set_density(mastb200_context* ctx, const double* rho) {
 int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz) {
   if (!ctx) return MASTB200_ERR_ARG;
   if (!ctx->have_mesh || !ctx->have_dofs) return ctx->fail(MASTB200_ERR_ARG, "set_mesh and set_dof_map first");
-  const bool solid = ctx->elem_type != MASTB200_QUAD4;
-  // shared-memory budget of the sweep kernel: whatever the staging areas leave of 227 KB goes to the accumulators
-  int max_optin = 232448;  // sm_100: 227 KB opt-in per CTA
   if (!ctx->planning_only) {
     CU(cudaSetDevice(ctx->device));
-    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    CU(cudaDeviceGetAttribute(&ctx->max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   }
-  const size_t fixed = hex8_sweep_smem_bytes(0);
-  if ((size_t)max_optin <= fixed + 4096) return ctx->fail(MASTB200_ERR_CUDA, "device shared memory too small");
-  ctx->lim.arena_doubles = (int32_t)((max_optin - fixed) / 8);
-  ctx->lim.max_tile_nodes = kMaxTileNodes;
-  ctx->lim.acc_per_block = solid ? 9 : 1;
-  ctx->lim.acc_per_node = kAccPerNode;
-  ctx->smem = hex8_sweep_smem_bytes(ctx->lim.arena_doubles);
-  const std::string e = build_plan(ctx->nn, ctx->n_nodes, ctx->n_elem, ctx->xyz.data(), ctx->conn.data(),
-                                   ctx->owned.empty() ? nullptr : ctx->owned.data(),
-                                   ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), ctx->lim, ctx->plan);
-  if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
-  Plan& P = ctx->plan;
-  if (ctx->planning_only) {
-    ctx->n_ctas = (int)std::min<int64_t>((int64_t)P.tiles.size(), ctx->sm_count);
-    ctx->have_plan = true;
-    if (n_rows) *n_rows = P.n_owned * ctx->nv;
-    if (nnz) *nnz = plan_nnz(ctx);
-    return MASTB200_OK;
-  }
-  CU(ctx->d_tiles.upload(P.tiles, ctx->stream));
-  CU(ctx->d_tile_nodes.upload(P.tile_nodes, ctx->stream));
-  CU(ctx->d_tile_acc_off.upload(P.tile_acc_off, ctx->stream));
-  CU(ctx->d_tile_nbr_cnt.upload(P.tile_nbr_cnt, ctx->stream));
-  CU(ctx->d_nbr_local.upload(P.nbr_local, ctx->stream));
-  CU(ctx->d_visits.upload(P.visits8, ctx->stream));
-  CU(ctx->d_nbr_ptr.upload(P.nbr_ptr, ctx->stream));
-  CU(ctx->d_node_row.upload(P.node_row, ctx->stream));
-  CU(ctx->d_n_adj.upload(P.n_adj_elem, ctx->stream));
-  CU(ctx->d_n_adj_diag.upload(P.n_adj_diag_elem, ctx->stream));
-  CU(ctx->d_owned_nodes.upload(P.owned_nodes, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  ctx->n_ctas = (int)std::min<int64_t>((int64_t)P.tiles.size(), ctx->sm_count);
+  for (auto& D : ctx->dplan) D.reset();
+  const std::string e = build_pattern(ctx->nn, ctx->n_nodes, ctx->n_elem, ctx->conn.data(),
+                                      ctx->owned.empty() ? nullptr : ctx->owned.data(),
+                                      ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), ctx->pat);
+  if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "pattern: %s", e.c_str());
   ctx->have_plan = true;
-  if (n_rows) *n_rows = P.n_owned * ctx->nv;
+  // the plan of the layout this problem will most likely sweep with is built now; the other one on first use
+  const int aux = (ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
+  if (int rc = ensure_plan(ctx, aux)) { ctx->have_plan = false; return rc; }
+  ctx->last_plan = aux;
+  if (!ctx->planning_only) {
+    CU(ctx->d_owned_nodes.upload(ctx->pat.owned_nodes, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (n_rows) *n_rows = ctx->pat.n_owned * ctx->nv;
   if (nnz) *nnz = plan_nnz(ctx);
   return MASTB200_OK;
 }
 
 int mastb200_get_pattern(const mastb200_context* ctx, int64_t* row_ptr, int32_t* col_idx) {
   if (!ctx || !ctx->have_plan || !row_ptr) return MASTB200_ERR_ARG;
-  const Plan& P = ctx->plan;
+  const Pattern& P = ctx->pat;
   const int nv = ctx->nv;
   int64_t k = 0;
   row_ptr[0] = 0;
@@ -532,8 +561,8 @@ int mastb200_get_pattern(const mastb200_context* ctx, int64_t* row_ptr, int32_t*
 
 int mastb200_get_row_dofs(const mastb200_context* ctx, int64_t* row_dof) {
   if (!ctx || !ctx->have_plan || !row_dof) return MASTB200_ERR_ARG;
-  for (int64_t r = 0; r < ctx->plan.n_owned; ++r)
-    for (int v = 0; v < ctx->nv; ++v) row_dof[r * ctx->nv + v] = (int64_t)ctx->plan.owned_nodes[r] * ctx->nv + v;
+  for (int64_t r = 0; r < ctx->pat.n_owned; ++r)
+    for (int v = 0; v < ctx->nv; ++v) row_dof[r * ctx->nv + v] = (int64_t)ctx->pat.owned_nodes[r] * ctx->nv + v;
   return MASTB200_OK;
 }
 
@@ -561,7 +590,7 @@ int mastb200_res_l2_norm(mastb200_context* ctx, double* norm) {
   const int nb = 1024;
   CU(ctx->d_partial.ensure(4096));
   CU(ctx->d_scalar.ensure(8));
-  CU(launch_sumsq_owned(ctx->last_R, ctx->d_owned_nodes.p, ctx->plan.n_owned, ctx->nv, ctx->d_partial.p, nb, ctx->stream));
+  CU(launch_sumsq_owned(ctx->last_R, ctx->d_owned_nodes.p, ctx->pat.n_owned, ctx->nv, ctx->d_partial.p, nb, ctx->stream));
   CU(launch_reduce_partials(ctx->d_partial.p, nb, ctx->d_scalar.p, ctx->stream));
   ctx->launches += 2;
   double ss = 0.;
@@ -640,20 +669,47 @@ int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, doubl
 int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   if (!ctx || !s) return MASTB200_ERR_ARG;
   std::memset(s, 0, sizeof *s);
-  s->n_tiles = (int64_t)ctx->plan.tiles.size();
-  s->n_visits = ctx->plan.n_visits();
-  s->n_owned_nodes = ctx->plan.n_owned;
+  const mastb200_context::DevicePlan& D = ctx->dplan[ctx->last_plan];
+  s->n_tiles = D.n_tiles;
+  s->n_visits = D.n_visits;
+  s->n_owned_nodes = ctx->pat.n_owned;
   s->n_elem = ctx->n_elem;
   s->kernel_launches = ctx->launches;
-  s->plan_bytes = ctx->plan.bytes();
-  s->smem_bytes = (int32_t)ctx->smem;
+  s->plan_bytes = D.bytes;
+  s->smem_bytes = (int32_t)D.smem;
   s->threads_per_cta = hex8_sweep_threads();
-  s->ctas = ctx->n_ctas;
+  s->ctas = D.n_ctas;
   if (ctx->timed) {
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a;
     if (cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]) == cudaSuccess) s->last_main_kernel_ms = b;
   }
+  return MASTB200_OK;
+}
+
+int mastb200_debug_plan_sizes(mastb200_context* ctx, int32_t aux, int64_t* sizes) {
+  if (!ctx || !sizes || aux < 0 || aux > 1) return MASTB200_ERR_ARG;
+  if (!ctx->planning_only) return ctx->fail(MASTB200_ERR_ARG, "plan introspection needs a planning-only context (device -1)");
+  if (!ctx->have_plan) return ctx->fail(MASTB200_ERR_ARG, "build_pattern first");
+  if (int rc = ensure_plan(ctx, aux)) return rc;
+  const StreamPlan& P = ctx->dplan[aux].host;
+  sizes[0] = (int64_t)P.tiles.size(); sizes[1] = (int64_t)P.steps.size(); sizes[2] = (int64_t)P.visits.size();
+  sizes[3] = (int64_t)P.flush_rows.size(); sizes[4] = (int64_t)P.flush_ent.size(); sizes[5] = (int64_t)P.loads.size();
+  sizes[6] = P.lim.arena_blocks; sizes[7] = P.lim.max_slots;
+  return MASTB200_OK;
+}
+
+int mastb200_debug_plan_copy(mastb200_context* ctx, int32_t aux, void* tiles, void* steps, void* visits, void* flush_rows,
+                             void* flush_ent, void* loads) {
+  int64_t sz[8];
+  if (int rc = mastb200_debug_plan_sizes(ctx, aux, sz)) return rc;
+  const StreamPlan& P = ctx->dplan[aux].host;
+  if (tiles) std::memcpy(tiles, P.tiles.data(), P.tiles.size() * sizeof(TileDesc));
+  if (steps) std::memcpy(steps, P.steps.data(), P.steps.size() * sizeof(StepDesc));
+  if (visits) std::memcpy(visits, P.visits.data(), P.visits.size() * sizeof(VisitRec8));
+  if (flush_rows) std::memcpy(flush_rows, P.flush_rows.data(), P.flush_rows.size() * sizeof(FlushRow));
+  if (flush_ent) std::memcpy(flush_ent, P.flush_ent.data(), P.flush_ent.size() * 4);
+  if (loads) std::memcpy(loads, P.loads.data(), P.loads.size() * sizeof(LoadRec));
   return MASTB200_OK;
 }
 

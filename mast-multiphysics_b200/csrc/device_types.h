@@ -10,15 +10,12 @@ struct SweepParams {
   // ---- static plan (device pointers) ----
   const TileDesc* tiles;
   int32_t n_tiles;
-  const int32_t* tile_nodes;
-  const int32_t* tile_acc_off;
-  const int32_t* tile_nbr_cnt;
-  const uint16_t* nbr_local;
+  const StepDesc* steps;
   const VisitRec8* visits;
-  const int64_t* nbr_ptr;     // per owned row: offset (in node blocks) of its first neighbour
-  const int32_t* node_row;    // global node -> owned row or -1
-  const int32_t* n_adj_elem;  // per node
-  const int32_t* n_adj_diag;  // per node (diagonal_elem_subdomain_id elements)
+  const FlushRow* flush_rows;
+  const uint32_t* flush_ent;
+  const LoadRec* loads;
+  int32_t* tile_counter;      // dynamic tile scheduler (zeroed before every launch)
   // ---- mesh + state ----
   const double* xyz;          // [n_nodes][3]
   const double* X;            // [n_nodes*nv]
@@ -35,14 +32,13 @@ struct SweepParams {
   double rho_min, penalty;
   double alpha_k;             // alpha*(3*lam1+2*mu1): thermal stress per unit modulus per kelvin
   double T_const, T_ref;
-  double k0, k_beta, thickness, heat_source;  // heat conduction
   int32_t nv;
   int32_t thermal;            // TEMPERATURE volume load active
-  int32_t nonlinear;          // Green-Lagrange strain
-  int32_t k_of_T;
   // ---- shared-memory layout (set by the launcher) ----
-  int32_t arena_doubles;
-  int32_t max_tile_nodes;
+  int32_t arena_blocks;
+  int32_t max_slots;
+  int32_t flush_buf_bytes;
+  int32_t aux;                // 1: adjoint / density / temperature state and per-node extras are staged
 };
 
 }  // namespace mastb200

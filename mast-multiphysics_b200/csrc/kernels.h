@@ -9,11 +9,11 @@
 
 namespace mastb200 {
 
-constexpr int kMaxTileNodes = 256;  // owned + halo nodes staged in shared memory per tile
-constexpr int kAccPerNode = 5;      // per owned node accumulators besides the matrix blocks: f[3], G, rot-diag
+constexpr int kMaxSlots = 448;         // node state slots staged in shared memory per strip (about four fronts)
+constexpr int kFlushBufBytes = 10240;  // flush records of one step staged in shared memory
 
-// HEX8 linear-elastic sweep (sweep_hex8.cu)
-size_t hex8_sweep_smem_bytes(int arena_doubles);
+// HEX8 linear-elastic sweep (sweep_hex8.cu).  aux: adjoint / density / temperature state and per-node extras staged
+size_t hex8_sweep_smem_bytes(int arena_blocks, int max_slots, int flush_buf_bytes, bool aux);
 int hex8_sweep_threads();
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream);
 

@@ -1,25 +1,33 @@
-// plan.cpp -- host-side construction of the assembly plan (see plan.h).
+// plan.cpp -- host-side construction of the sparsity pattern and the streaming assembly plan (see plan.h).
 #include "plan.h"
 
 #include <algorithm>
 #include <atomic>
+#include <climits>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 namespace mastb200 {
 
-int64_t Plan::bytes() const {
-  return (int64_t)(tiles.size() * sizeof(TileDesc) + tile_nodes.size() * 4 + tile_acc_off.size() * 4 +
-                   tile_nbr_cnt.size() * 4 + nbr_local.size() * 2 + visits8.size() * sizeof(VisitRec8));
+int64_t StreamPlan::bytes() const {
+  return (int64_t)(tiles.size() * sizeof(TileDesc) + steps.size() * sizeof(StepDesc) + visits.size() * sizeof(VisitRec8) +
+                   flush_rows.size() * sizeof(FlushRow) + flush_ent.size() * 4 + loads.size() * sizeof(LoadRec));
 }
 
 namespace {
 
+int hw_threads() {
+  unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+}
+
 template <typename F>
 void parallel_for(int64_t n, F f) {
-  unsigned hw = std::thread::hardware_concurrency();
-  int nt = (int)std::max(1u, std::min(hw ? hw : 1u, 32u));
+  int nt = hw_threads();
   if (n < 4096) nt = 1;
   if (nt == 1) { f(0, n, 0); return; }
   std::vector<std::thread> pool;
@@ -27,18 +35,29 @@ void parallel_for(int64_t n, F f) {
   for (auto& th : pool) th.join();
 }
 
-struct TileBuild {
-  std::vector<int32_t> nodes, acc_off, nbr_cnt;
-  std::vector<uint16_t> nbrl;
-  std::vector<VisitRec8> visits;
-  int32_t n_owned = 0, arena = 0, blocks = 0;
-};
+// dynamic work queue over items [0,n): f(item, thread)
+template <typename F>
+void parallel_items(int64_t n, F f) {
+  int nt = (int)std::min<int64_t>(hw_threads(), std::max<int64_t>(n, 1));
+  if (nt <= 1) { for (int64_t i = 0; i < n; ++i) f(i, 0); return; }
+  std::atomic<int64_t> next(0);
+  std::vector<std::thread> pool;
+  for (int t = 0; t < nt; ++t)
+    pool.emplace_back([&, t] {
+      for (;;) {
+        const int64_t i = next.fetch_add(1);
+        if (i >= n) break;
+        f(i, t);
+      }
+    });
+  for (auto& th : pool) th.join();
+}
 
 }  // namespace
 
-std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double* xyz, const int32_t* conn,
-                       const uint8_t* owned, const uint8_t* diag_elem, const PlanLimits& lim, Plan& P) {
-  P = Plan();
+std::string build_pattern(int32_t nn, int64_t n_nodes, int64_t n_elem, const int32_t* conn, const uint8_t* owned,
+                          const uint8_t* diag_elem, Pattern& P) {
+  P = Pattern();
   P.nn = nn; P.n_nodes = n_nodes; P.n_elem = n_elem;
   if (n_nodes <= 0 || n_elem <= 0) return "empty mesh";
   if (n_nodes >= (int64_t(1) << 31) || n_elem >= (int64_t(1) << 31)) return "mesh too large for 32-bit ids";
@@ -46,20 +65,20 @@ std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double
     if (conn[k] < 0 || conn[k] >= n_nodes) return "connectivity entry out of range";
 
   // ---- node -> element adjacency (ascending element id) -------------------------------------
-  std::vector<int64_t> n2e_ptr(n_nodes + 1, 0);
-  for (int64_t k = 0; k < n_elem * nn; ++k) n2e_ptr[conn[k] + 1]++;
-  for (int64_t n = 0; n < n_nodes; ++n) n2e_ptr[n + 1] += n2e_ptr[n];
-  std::vector<int32_t> n2e(n2e_ptr[n_nodes]);
+  P.n2e_ptr.assign(n_nodes + 1, 0);
+  for (int64_t k = 0; k < n_elem * nn; ++k) P.n2e_ptr[conn[k] + 1]++;
+  for (int64_t n = 0; n < n_nodes; ++n) P.n2e_ptr[n + 1] += P.n2e_ptr[n];
+  P.n2e.resize(P.n2e_ptr[n_nodes]);
   {
-    std::vector<int64_t> pos(n2e_ptr.begin(), n2e_ptr.end() - 1);
+    std::vector<int64_t> pos(P.n2e_ptr.begin(), P.n2e_ptr.end() - 1);
     for (int64_t e = 0; e < n_elem; ++e)
-      for (int a = 0; a < nn; ++a) n2e[pos[conn[e * nn + a]]++] = (int32_t)e;
+      for (int a = 0; a < nn; ++a) P.n2e[pos[conn[e * nn + a]]++] = (int32_t)e;
   }
   P.n_adj_elem.assign(n_nodes, 0);
   P.n_adj_diag_elem.assign(n_nodes, 0);
   for (int64_t n = 0; n < n_nodes; ++n)
-    for (int64_t k = n2e_ptr[n]; k < n2e_ptr[n + 1]; ++k) {
-      if (diag_elem && diag_elem[n2e[k]]) P.n_adj_diag_elem[n]++;
+    for (int64_t k = P.n2e_ptr[n]; k < P.n2e_ptr[n + 1]; ++k) {
+      if (diag_elem && diag_elem[P.n2e[k]]) P.n_adj_diag_elem[n]++;
       else P.n_adj_elem[n]++;
     }
 
@@ -70,254 +89,555 @@ std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double
   P.n_owned = (int64_t)P.owned_nodes.size();
   if (P.n_owned == 0) return "no owned nodes";
   P.nbr_ptr.assign(P.n_owned + 1, 0);
-  {
-    // pass 1: counts; pass 2: fill (both parallel over owned rows)
-    std::vector<int32_t> cnt(P.n_owned);
-    auto gather = [&](int64_t n, std::vector<int32_t>& l) {
-      l.clear();
-      for (int64_t k = n2e_ptr[n]; k < n2e_ptr[n + 1]; ++k) {
-        const int32_t* c = conn + (int64_t)n2e[k] * nn;
-        l.insert(l.end(), c, c + nn);
-      }
-      std::sort(l.begin(), l.end());
-      l.erase(std::unique(l.begin(), l.end()), l.end());
-    };
-    parallel_for(P.n_owned, [&](int64_t b, int64_t e, int) {
-      std::vector<int32_t> l;
-      for (int64_t r = b; r < e; ++r) { gather(P.owned_nodes[r], l); cnt[r] = (int32_t)l.size(); }
-    });
-    for (int64_t r = 0; r < P.n_owned; ++r) {
-      if (cnt[r] > 255) return "node with more than 255 neighbours";
-      P.nbr_ptr[r + 1] = P.nbr_ptr[r] + cnt[r];
+  // pass 1: counts; pass 2: fill (both parallel over owned rows)
+  std::vector<int32_t> cnt(P.n_owned);
+  auto gather = [&](int64_t n, std::vector<int32_t>& l) {
+    l.clear();
+    for (int64_t k = P.n2e_ptr[n]; k < P.n2e_ptr[n + 1]; ++k) {
+      const int32_t* c = conn + (int64_t)P.n2e[k] * nn;
+      l.insert(l.end(), c, c + nn);
     }
-    P.nbr.resize(P.nbr_ptr[P.n_owned]);
-    parallel_for(P.n_owned, [&](int64_t b, int64_t e, int) {
-      std::vector<int32_t> l;
-      for (int64_t r = b; r < e; ++r) {
-        gather(P.owned_nodes[r], l);
-        std::copy(l.begin(), l.end(), P.nbr.begin() + P.nbr_ptr[r]);
-      }
-    });
+    std::sort(l.begin(), l.end());
+    l.erase(std::unique(l.begin(), l.end()), l.end());
+  };
+  parallel_for(P.n_owned, [&](int64_t b, int64_t e, int) {
+    std::vector<int32_t> l;
+    for (int64_t r = b; r < e; ++r) { gather(P.owned_nodes[r], l); cnt[r] = (int32_t)l.size(); }
+  });
+  for (int64_t r = 0; r < P.n_owned; ++r) {
+    if (cnt[r] > 4000) return "node with more than 4000 neighbours";
+    P.nbr_ptr[r + 1] = P.nbr_ptr[r] + cnt[r];
+  }
+  P.nbr.resize(P.nbr_ptr[P.n_owned]);
+  parallel_for(P.n_owned, [&](int64_t b, int64_t e, int) {
+    std::vector<int32_t> l;
+    for (int64_t r = b; r < e; ++r) {
+      gather(P.owned_nodes[r], l);
+      std::copy(l.begin(), l.end(), P.nbr.begin() + P.nbr_ptr[r]);
+    }
+  });
+  return "";
+}
+
+// ================================================================================================================
+// streaming plan
+// ================================================================================================================
+namespace {
+
+struct Range { int64_t b, e; };
+
+struct TileOut {
+  std::vector<StepDesc> steps;
+  std::vector<VisitRec8> visits;
+  std::vector<FlushRow> frows;
+  std::vector<uint32_t> fent;
+  std::vector<LoadRec> loads;
+  int32_t n_owned = 0, max_blocks = 0, max_slots = 0;
+};
+
+struct Scratch {
+  std::vector<int32_t> local;  // global node -> tile-local id or -1 (dense, reset after every tile)
+};
+
+struct Builder {
+  const Pattern& pat;
+  const double* xyz;
+  const int32_t* conn;
+  const uint8_t* diag;
+  PlanLimits lim;
+  int sweep = 2, cu = 0, cv = 1;  // sweep axis and the two cross axes
+  double h[3] = {1., 1., 1.};     // typical node spacing per axis
+  std::string error;              // hard (non-capacity) failure
+  std::atomic<int> why{0};        // which limit the last oversized tile hit (1 slots, 2 arena, 3 flush buffer)
+  std::mutex mu;
+
+  Builder(const Pattern& p, const double* x, const int32_t* c, const uint8_t* d, const PlanLimits& l)
+      : pat(p), xyz(x), conn(c), diag(d), lim(l) {}
+
+  void fail(const std::string& s) {
+    std::lock_guard<std::mutex> g(mu);
+    if (error.empty()) error = s;
   }
 
-  if (nn != 8) return "";  // pattern only: the tile plan below is laid out for HEX8 visit records
+  // ---- one tile: owned nodes `own` (sorted by (front, gid)) with front index `fr` in [0, n_fronts) --------------
+  // returns false if the tile does not fit the shared-memory limits (caller splits the strip)
+  bool build_tile(const int32_t* own, const int32_t* fr, int32_t n_owned, int32_t n_fronts, Scratch& sc, TileOut& T) {
+    constexpr int nn = 8;
+    T = TileOut();
+    T.n_owned = n_owned;
+    std::vector<int32_t>& local = sc.local;
+    std::vector<int32_t> nodes(own, own + n_owned);  // tile-local -> gid
+    for (int32_t l = 0; l < n_owned; ++l) local[own[l]] = l;
+    auto cleanup = [&] { for (int32_t n : nodes) local[n] = -1; };
 
-  // ---- recursive coordinate bisection of the owned nodes into tiles ---------------------------
-  // A leaf is accepted when its accumulators fit the arena; the halo limit is verified when the tile is built
-  // and the leaf is split again if it fails.
-  std::vector<int32_t> perm(P.owned_nodes);
-  struct Range { int64_t b, e; };
-  std::vector<Range> leaves, work;
-  work.push_back({0, P.n_owned});
-  auto arena_need = [&](int64_t b, int64_t e) {
-    int64_t s = 0;
-    for (int64_t k = b; k < e; ++k) {
-      const int32_t r = P.node_row[perm[k]];
-      s += (P.nbr_ptr[r + 1] - P.nbr_ptr[r]) * lim.acc_per_block + lim.acc_per_node;
+    // elements of the tile: every non-diagonal element touching an owned node
+    std::vector<int32_t> elems;
+    for (int32_t l = 0; l < n_owned; ++l) {
+      const int32_t n = own[l];
+      for (int64_t k = pat.n2e_ptr[n]; k < pat.n2e_ptr[n + 1]; ++k)
+        if (!(diag && diag[pat.n2e[k]])) elems.push_back(pat.n2e[k]);
     }
-    return s;
-  };
-  auto split = [&](Range r, std::vector<Range>& out) {
-    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int64_t k = r.b; k < r.e; ++k)
-      for (int c = 0; c < 3; ++c) {
-        const double v = xyz[(int64_t)perm[k] * 3 + c];
-        lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v);
+    std::sort(elems.begin(), elems.end());
+    elems.erase(std::unique(elems.begin(), elems.end()), elems.end());
+    const size_t nvis = elems.size();
+    // step of a visit: the last front among its owned nodes; an element whose owned nodes all lie in one front and
+    // which sits beyond that front along the sweep goes one step later, so that every step completes one front only
+    std::vector<int32_t> vstep(nvis);
+    int32_t S = n_fronts;
+    for (size_t v = 0; v < nvis; ++v) {
+      const int32_t* c = conn + (int64_t)elems[v] * nn;
+      int32_t smin = INT_MAX, smax = 0, no = 0;
+      double cen = 0., own_c = 0.;
+      for (int a = 0; a < nn; ++a) {
+        const double x = xyz[(int64_t)c[a] * 3 + sweep];
+        cen += x;
+        const int32_t l = local[c[a]];
+        if (l >= 0) { smin = std::min(smin, fr[l]); smax = std::max(smax, fr[l]); own_c += x; ++no; }
       }
-    int ax = 0;
-    for (int c = 1; c < 3; ++c)
-      if (hi[c] - lo[c] > hi[ax] - lo[ax]) ax = c;
+      if (smin == smax && cen / nn > own_c / no) ++smax;
+      vstep[v] = smax;
+      S = std::max(S, smax + 1);
+    }
+    // order: (step, colour, element id); colours spread visits that share an owned node apart
+    std::vector<int32_t> order(nvis);
+    {
+      std::vector<int32_t> idx(nvis);
+      for (size_t v = 0; v < nvis; ++v) idx[v] = (int32_t)v;
+      std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return vstep[a] < vstep[b]; });
+      std::vector<uint32_t> used(n_owned, 0u);
+      std::vector<int32_t> colour(nvis, 0), touched;
+      size_t i0 = 0;
+      while (i0 < nvis) {
+        size_t i1 = i0;
+        while (i1 < nvis && vstep[idx[i1]] == vstep[idx[i0]]) ++i1;
+        touched.clear();
+        for (size_t i = i0; i < i1; ++i) {
+          const int32_t* c = conn + (int64_t)elems[idx[i]] * nn;
+          uint32_t m = 0;
+          for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l >= 0) m |= used[l]; }
+          int32_t col = 0;
+          while (col < 31 && (m >> col & 1u)) ++col;
+          colour[idx[i]] = col;
+          for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l >= 0) { used[l] |= 1u << col; touched.push_back(l); } }
+        }
+        for (int32_t l : touched) used[l] = 0u;
+        std::stable_sort(idx.begin() + i0, idx.begin() + i1, [&](int32_t a, int32_t b) { return colour[a] < colour[b]; });
+        i0 = i1;
+      }
+      order.swap(idx);
+    }
+    // halo nodes: tile-local ids in first-touch order
+    for (size_t o = 0; o < nvis; ++o) {
+      const int32_t* c = conn + (int64_t)elems[order[o]] * nn;
+      for (int a = 0; a < nn; ++a)
+        if (local[c[a]] < 0) { local[c[a]] = (int32_t)nodes.size(); nodes.push_back(c[a]); }
+    }
+    const int32_t n_tile_nodes = (int32_t)nodes.size();
+
+    // lifetimes
+    std::vector<int32_t> first(n_tile_nodes, INT_MAX), last(n_tile_nodes, -1), flush_step(n_owned), state_end(n_tile_nodes);
+    for (size_t o = 0; o < nvis; ++o) {
+      const int32_t s = vstep[order[o]];
+      const int32_t* c = conn + (int64_t)elems[order[o]] * nn;
+      for (int a = 0; a < nn; ++a) {
+        const int32_t l = local[c[a]];
+        first[l] = std::min(first[l], s); last[l] = std::max(last[l], s);
+      }
+    }
+    for (int32_t l = 0; l < n_owned; ++l) {
+      if (last[l] < 0) { first[l] = fr[l]; last[l] = fr[l]; }  // owned node without (non-diagonal) elements
+      // rows of front f are written after step f+1 even where the mesh ends, so that no step writes two fronts
+      flush_step[l] = std::max(last[l], fr[l] + 1);
+      S = std::max(S, flush_step[l] + 1);
+    }
+    for (int32_t l = 0; l < n_tile_nodes; ++l) state_end[l] = l < n_owned ? std::max(last[l], flush_step[l]) : last[l];
+    for (size_t o = 0; o < nvis; ++o) {
+      const int32_t* c = conn + (int64_t)elems[order[o]] * nn;
+      int32_t m = -1;
+      for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l < n_owned) m = std::max(m, flush_step[l]); }
+      for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; state_end[l] = std::max(state_end[l], m); }
+    }
+
+    // ---- state slots: a slot read by the flush after step t may be reloaded for a node first used at step >= t+2
+    std::vector<int32_t> slot(n_tile_nodes, -1);
+    {
+      std::vector<std::vector<int32_t>> by_first(S), release(S + 3);
+      for (int32_t l = 0; l < n_tile_nodes; ++l) by_first[first[l]].push_back(l);
+      std::vector<int32_t> free_slots;
+      int32_t next_new = 0, live = 0;
+      for (int32_t s = 0; s < S; ++s) {
+        for (int32_t sl : release[s]) { free_slots.push_back(sl); --live; }
+        for (int32_t l : by_first[s]) {
+          int32_t sl;
+          if (!free_slots.empty()) { sl = free_slots.back(); free_slots.pop_back(); }
+          else if (next_new < lim.max_slots) sl = next_new++;
+          else { cleanup(); why = 1; return false; }
+          slot[l] = sl;
+          ++live;
+          T.max_slots = std::max(T.max_slots, live);
+          if (state_end[l] + 2 < S + 3) release[std::min(state_end[l] + 2, S + 2)].push_back(sl);
+        }
+      }
+    }
+
+    // ---- pair blocks ------------------------------------------------------------------------------------------
+    std::vector<int64_t> base(n_owned + 1, 0);  // block index space: (owned node, neighbour position)
+    for (int32_t l = 0; l < n_owned; ++l) {
+      const int32_t row = pat.node_row[nodes[l]];
+      base[l + 1] = base[l] + (pat.nbr_ptr[row + 1] - pat.nbr_ptr[row]);
+    }
+    auto nbr_pos = [&](int32_t l, int32_t gid) {  // position of gid in the neighbour list of owned tile node l
+      const int32_t row = pat.node_row[nodes[l]];
+      const int32_t* nb = pat.nbr.data() + pat.nbr_ptr[row];
+      const int32_t* ne = pat.nbr.data() + pat.nbr_ptr[row + 1];
+      return (int32_t)(std::lower_bound(nb, ne, gid) - nb);
+    };
+    std::vector<int32_t> blk_slot(base[n_owned], -1);
+    T.visits.resize(nvis);
+    T.steps.assign(S, StepDesc{0, 0, 0, 0, 0, 0, 0, 0});
+    {
+      std::vector<std::vector<int32_t>> release(S + 2);
+      std::vector<int32_t> free_blocks;
+      int32_t next_new = 0, live = 0;
+      std::vector<uint32_t> rank(n_owned, 0u);
+      int32_t cur_step = -1;
+      for (size_t o = 0; o < nvis; ++o) {
+        const int32_t s = vstep[order[o]];
+        while (cur_step < s) {
+          ++cur_step;
+          for (int32_t b : release[cur_step]) { free_blocks.push_back(b); --live; }
+          T.steps[cur_step].visit_begin = (int32_t)o;
+        }
+        T.steps[s].n_visits++;
+        const int32_t* c = conn + (int64_t)elems[order[o]] * nn;
+        VisitRec8& V = T.visits[o];
+        int32_t ll[8];
+        for (int a = 0; a < nn; ++a) {
+          ll[a] = local[c[a]];
+          V.ln[a] = (uint16_t)slot[ll[a]];
+          if (ll[a] < n_owned) {
+            if (rank[ll[a]] > 250) { cleanup(); fail("node touched by more than 250 elements"); return true; }
+            V.rank[a] = (uint8_t)rank[ll[a]]++;
+          } else {
+            V.rank[a] = 0xFF;
+          }
+        }
+        for (int a = 0; a < nn; ++a)
+          for (int b = a; b < nn; ++b) {
+            uint16_t& out = V.pair[a * (15 - a) / 2 + b];
+            const bool oa = ll[a] < n_owned, ob = ll[b] < n_owned;
+            if (!oa && !ob) { out = kPairNone; continue; }
+            // the block is stored as S_(P,Q): P the owned endpoint, the lower global id if both are owned
+            const bool p_is_a = (oa && ob) ? (c[a] <= c[b]) : oa;
+            const int p = p_is_a ? a : b, q = p_is_a ? b : a;
+            const int64_t blk = base[ll[p]] + nbr_pos(ll[p], c[q]);
+            uint16_t e = p_is_a ? 0 : kPairTransposed;
+            if (blk_slot[blk] < 0) {
+              int32_t bs;
+              if (!free_blocks.empty()) { bs = free_blocks.back(); free_blocks.pop_back(); }
+              else if (next_new < lim.arena_blocks) bs = next_new++;
+              else { cleanup(); why = 2; return false; }
+              blk_slot[blk] = bs;
+              ++live;
+              T.max_blocks = std::max(T.max_blocks, live);
+              int32_t end = flush_step[ll[p]];
+              if (ll[q] < n_owned) end = std::max(end, flush_step[ll[q]]);
+              release[end + 1].push_back(bs);
+              e |= kPairInit;
+            }
+            out = (uint16_t)(e | (uint16_t)blk_slot[blk]);
+          }
+      }
+      while (cur_step < S - 1) { ++cur_step; T.steps[cur_step].visit_begin = (int32_t)nvis; }
+    }
+
+    // ---- loads and flush rows per step ------------------------------------------------------------------------------
+    {
+      std::vector<std::vector<int32_t>> by_first(S), by_flush(S);
+      for (int32_t l = 0; l < n_tile_nodes; ++l) by_first[first[l]].push_back(l);
+      for (int32_t l = 0; l < n_owned; ++l) by_flush[flush_step[l]].push_back(l);
+      for (int32_t s = 0; s < S; ++s) {
+        StepDesc& sd = T.steps[s];
+        sd.load_begin = (int32_t)T.loads.size();
+        std::sort(by_first[s].begin(), by_first[s].end(), [&](int32_t a, int32_t b) { return nodes[a] < nodes[b]; });
+        for (int32_t l : by_first[s]) T.loads.push_back(LoadRec{nodes[l], (uint16_t)slot[l], (uint16_t)(l < n_owned ? 1 : 0)});
+        sd.n_loads = (int32_t)by_first[s].size();
+        sd.flush_begin = (int32_t)T.frows.size();
+        while (T.fent.size() % 4) T.fent.push_back(0u);  // 16-byte aligned per step: the device copies uint4
+        sd.fent_begin = (int32_t)T.fent.size();
+        std::sort(by_flush[s].begin(), by_flush[s].end(), [&](int32_t a, int32_t b) { return nodes[a] < nodes[b]; });
+        for (int32_t l : by_flush[s]) {
+          const int32_t ga = nodes[l];
+          const int32_t row = pat.node_row[ga];
+          const int64_t nb0 = pat.nbr_ptr[row], nb1 = pat.nbr_ptr[row + 1];
+          FlushRow fr_;
+          std::memset(&fr_, 0, sizeof fr_);
+          fr_.dst_block = nb0; fr_.gid = ga; fr_.ent_rel = (int32_t)T.fent.size() - sd.fent_begin;
+          fr_.slot = (uint16_t)slot[l]; fr_.nnb = (uint16_t)(nb1 - nb0);
+          fr_.nadj = (uint16_t)std::min(pat.n_adj_elem[ga], 65535); fr_.nadjd = (uint16_t)std::min(pat.n_adj_diag_elem[ga], 65535);
+          T.frows.push_back(fr_);
+          for (int64_t k = nb0; k < nb1; ++k) {
+            const int32_t gq = pat.nbr[k];
+            const int32_t lq = local[gq];
+            uint32_t fl = (gq == ga) ? kFlushSelf : 0u, bsl = kFlushNoBlock, st = 0xFFFFu;
+            if (lq >= 0) {
+              int64_t blk;
+              if (lq < n_owned && gq < ga) { blk = base[lq] + nbr_pos(lq, ga); fl |= kFlushTransposed; }
+              else blk = base[l] + (k - nb0);
+              if (blk_slot[blk] >= 0) { bsl = (uint32_t)blk_slot[blk]; st = (uint32_t)slot[lq]; }
+            }
+            if (gq == ga) st = (uint32_t)slot[l];  // the row's own state is always staged
+            const uint32_t e = bsl | fl | (st << 16);
+            T.fent.push_back(e);
+          }
+        }
+        sd.n_flush = (int32_t)by_flush[s].size();
+        sd.n_fent = (int32_t)T.fent.size() - sd.fent_begin;
+        if ((int64_t)sd.n_flush * (int64_t)sizeof(FlushRow) + (int64_t)(sd.n_fent + 3) / 4 * 16 > lim.flush_buf_bytes) { cleanup(); why = 3; return false; }
+      }
+      while (T.fent.size() % 4) T.fent.push_back(0u);
+    }
+    cleanup();
+    return true;
+  }
+
+  // ---- strip handling ---------------------------------------------------------------------------------------------
+  double coord(int32_t n, int ax) const { return xyz[(int64_t)n * 3 + ax]; }
+
+  // splits perm[r.b, r.e) along axis ax at about fraction num/den of the nodes, snapping to the widest coordinate gap
+  // within a window of about one node plane so that strips of (possibly jittered) structured meshes end on whole planes
+  int64_t split(std::vector<int32_t>& perm, Range r, int ax, int64_t num, int64_t den, double planes) const {
     const int64_t cnt = r.e - r.b;
-    const int64_t mid = r.b + cnt / 2;
-    auto key = [&](int32_t n) { return xyz[(int64_t)n * 3 + ax]; };
+    const int64_t pos = r.b + std::max<int64_t>(1, std::min<int64_t>(cnt - 1, cnt * num / den));
+    auto key = [&](int32_t n) { return coord(n, ax); };
     auto less = [&](int32_t a, int32_t b) { return key(a) < key(b) || (key(a) == key(b) && a < b); };
-    // Cut near the median but at the widest coordinate gap inside a window of about one mesh "plane" of nodes, so
-    // that tiles of (possibly jittered) structured meshes end on whole node planes and keep a small halo.
-    int64_t W = (int64_t)std::ceil(std::pow((double)cnt, 2.0 / 3.0)) + 1;
-    W = std::min(W, std::min(mid - r.b, r.e - mid) - 1);
-    int64_t cut = mid;
+    int64_t W = (int64_t)std::ceil((double)cnt / std::max(1.0, planes)) + 1;
+    W = std::min(W, std::min(pos - r.b, r.e - pos) - 1);
+    int64_t cut = pos;
     if (W >= 1) {
-      auto b0 = perm.begin() + (mid - W), b1 = perm.begin() + (mid + W);
+      auto b0 = perm.begin() + (pos - W), b1 = perm.begin() + (pos + W);
       std::nth_element(perm.begin() + r.b, b0, perm.begin() + r.e, less);
       std::nth_element(b0, b1, perm.begin() + r.e, less);
       std::sort(b0, b1, less);
+      // prefer the plane boundary (gap of more than half a node spacing) closest to pos; else the widest gap
       double best = -1.;
-      for (int64_t k = mid - W + 1; k < mid + W; ++k) {
+      int64_t best_k = pos, near_k = -1;
+      for (int64_t k = pos - W + 1; k < pos + W; ++k) {
         const double gap = key(perm[k]) - key(perm[k - 1]);
-        const bool closer = std::llabs(k - mid) < std::llabs(cut - mid);
-        if (gap > best * (1. + 1e-9) + 1e-300 || (gap >= best * (1. - 1e-9) && closer)) {
-          if (gap > best) best = gap;
-          cut = k;
-        }
+        if (gap > 0.5 * h[ax] && (near_k < 0 || std::llabs(k - pos) < std::llabs(near_k - pos))) near_k = k;
+        if (gap > best) { best = gap; best_k = k; }
       }
+      cut = near_k >= 0 ? near_k : best_k;
     } else {
-      std::nth_element(perm.begin() + r.b, perm.begin() + mid, perm.begin() + r.e, less);
+      std::nth_element(perm.begin() + r.b, perm.begin() + pos, perm.begin() + r.e, less);
     }
-    out.push_back({r.b, cut});
-    out.push_back({cut, r.e});
+    return cut;
+  }
+
+  void extent(const std::vector<int32_t>& perm, Range r, double lo[3], double hi[3]) const {
+    for (int c = 0; c < 3; ++c) { lo[c] = 1e300; hi[c] = -1e300; }
+    for (int64_t k = r.b; k < r.e; ++k)
+      for (int c = 0; c < 3; ++c) {
+        const double v = coord(perm[k], c);
+        lo[c] = std::min(lo[c], v); hi[c] = std::max(hi[c], v);
+      }
+  }
+  double planes_of(double lo, double hi, int ax) const { return std::floor((hi - lo) / h[ax] + 0.5) + 1.; }
+};
+
+}  // namespace
+
+std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
+                              const PlanLimits& lim, StreamPlan& plan) {
+  plan = StreamPlan();
+  plan.lim = lim;
+  if (pat.nn != 8) return "streaming plan: HEX8 only";
+  if (lim.arena_blocks < 64 || lim.arena_blocks > (int)kFlushNoBlock - 1) return "arena size out of range";
+  Builder B(pat, xyz, conn, diag_elem, lim);
+  constexpr int nn = 8;
+
+  // ---- typical node spacing per axis from element edges (every edge is attributed to its dominant axis) ----------
+  {
+    static const int EDGE[12][2] = {{0, 1}, {3, 2}, {4, 5}, {7, 6}, {0, 3}, {1, 2}, {4, 7}, {5, 6}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+    double sum[3] = {0., 0., 0.};
+    int64_t num[3] = {0, 0, 0};
+    const int64_t stride = std::max<int64_t>(1, pat.n_elem / 50000);
+    for (int64_t e = 0; e < pat.n_elem; e += stride) {
+      const int32_t* c = conn + e * nn;
+      for (auto& ed : EDGE) {
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = std::fabs(xyz[(int64_t)c[ed[1]] * 3 + k] - xyz[(int64_t)c[ed[0]] * 3 + k]);
+        const int ax = d[0] >= d[1] ? (d[0] >= d[2] ? 0 : 2) : (d[1] >= d[2] ? 1 : 2);
+        sum[ax] += d[ax]; num[ax]++;
+      }
+    }
+    double all = 0.; int64_t nall = 0;
+    for (int k = 0; k < 3; ++k) { all += sum[k]; nall += num[k]; }
+    for (int k = 0; k < 3; ++k) B.h[k] = num[k] ? sum[k] / num[k] : (nall ? all / nall : 1.);
+    for (int k = 0; k < 3; ++k) if (!(B.h[k] > 0.)) B.h[k] = 1.;
+  }
+
+  std::vector<int32_t> perm(pat.owned_nodes);
+  double lo[3], hi[3];
+  B.extent(perm, {0, pat.n_owned}, lo, hi);
+  double pl[3];
+  for (int k = 0; k < 3; ++k) pl[k] = B.planes_of(lo[k], hi[k], k);
+  // sweep along the axis with most node planes (ties: the highest axis, whose planes are contiguous in libMesh numbering)
+  B.sweep = 2;
+  for (int k = 1; k >= 0; --k) if (pl[k] > pl[B.sweep]) B.sweep = k;
+  B.cu = (B.sweep + 1) % 3; B.cv = (B.sweep + 2) % 3;
+  if (B.cu > B.cv) std::swap(B.cu, B.cv);
+
+  // cross-section target: the largest mu x mv node columns whose live pair blocks fit the arena.  On a hexahedral grid
+  // a strip holds two fronts of in-plane pairs and two layers of cross-plane pairs at a time.
+  int mu = 1, mv = 1;
+  {
+    auto blocks = [](int a, int b) {
+      const int both = (3 * a - 2) * (3 * b - 2), halo = 9 * a * b - both;
+      return 2 * ((both + a * b) / 2 + halo) + 2 * (9 * a * b + halo);
+    };
+    const double cap = 1.03 * lim.arena_blocks;
+    for (int a = 1; a <= 24; ++a)
+      for (int b = a; b <= 24; ++b) {
+        if (blocks(a, b) > cap || (a + 2) * (b + 2) * 4 > lim.max_slots) continue;
+        if (a * b > mu * mv || (a * b == mu * mv && b - a < mv - mu)) { mu = a; mv = b; }
+      }
+    if (const char* ev = std::getenv("MASTB200_PLAN_COLS")) {
+      const int cols = std::max(1, std::atoi(ev));
+      mu = std::max(1, (int)std::floor(std::sqrt((double)cols)));
+      mv = std::max(1, cols / mu);
+    }
+  }
+  const int cols = mu * mv;
+  // ---- cross partition into strips ----------------------------------------------------------------------------------
+  std::vector<Range> strips, work;
+  work.push_back({0, pat.n_owned});
+  auto cross_split = [&](Range r, bool force, std::vector<Range>& out_leaf, std::vector<Range>& out_work) {
+    double l[3], hh[3];
+    B.extent(perm, r, l, hh);
+    const double pu = B.planes_of(l[B.cu], hh[B.cu], B.cu), pv = B.planes_of(l[B.cv], hh[B.cv], B.cv);
+    if (r.e - r.b <= 1 || (!force && pu <= mu && pv <= mv)) { out_leaf.push_back(r); return; }
+    int ax; double p; int m;
+    if (pu / mu >= pv / mv) { ax = B.cu; p = pu; m = mu; } else { ax = B.cv; p = pv; m = mv; }
+    int64_t k = std::max<int64_t>(2, (int64_t)std::ceil(p / m));
+    if (force && p <= 1.5) {  // a single node plane left in both cross directions: split by count
+      ax = (hh[B.cu] - l[B.cu]) / B.h[B.cu] >= (hh[B.cv] - l[B.cv]) / B.h[B.cv] ? B.cu : B.cv;
+      k = 2;
+    }
+    const int64_t cut = B.split(perm, r, ax, k / 2, k, p);
+    out_work.push_back({r.b, cut});
+    out_work.push_back({cut, r.e});
   };
   while (!work.empty()) {
     Range r = work.back();
     work.pop_back();
-    if (r.e - r.b <= 1 || (arena_need(r.b, r.e) <= lim.arena_doubles && r.e - r.b <= lim.max_tile_nodes)) leaves.push_back(r);
-    else split(r, work);
+    cross_split(r, false, strips, work);
   }
 
-  // ---- build tiles (parallel), splitting leaves whose halo does not fit -------------------------
-  std::vector<TileBuild> built;
-  std::string err;
-  while (!leaves.empty()) {
-    std::sort(leaves.begin(), leaves.end(), [](const Range& a, const Range& b) { return a.b < b.b; });
-    std::vector<TileBuild> tb(leaves.size());
-    std::vector<char> too_big(leaves.size(), 0);
-    std::atomic<int> fail(0);
-    parallel_for((int64_t)leaves.size(), [&](int64_t tb0, int64_t tb1, int) {
-      std::vector<int32_t> local(n_nodes, -1);  // global -> tile-local
-      std::vector<int32_t> elems;
-      std::vector<uint32_t> used;  // per owned node: bitmask of steps (colours) already taken
-      for (int64_t t = tb0; t < tb1; ++t) {
-        TileBuild& T = tb[t];
-        const Range r = leaves[t];
-        T.nodes.assign(perm.begin() + r.b, perm.begin() + r.e);
-        std::sort(T.nodes.begin(), T.nodes.end());
-        T.n_owned = (int32_t)T.nodes.size();
-        for (int32_t l = 0; l < T.n_owned; ++l) local[T.nodes[l]] = l;
-        // visits: every non-diagonal element touching an owned node, ascending id
-        elems.clear();
-        for (int32_t l = 0; l < T.n_owned; ++l) {
-          const int32_t n = T.nodes[l];
-          for (int64_t k = n2e_ptr[n]; k < n2e_ptr[n + 1]; ++k)
-            if (!(diag_elem && diag_elem[n2e[k]])) elems.push_back(n2e[k]);
-        }
-        std::sort(elems.begin(), elems.end());
-        elems.erase(std::unique(elems.begin(), elems.end()), elems.end());
-        // halo nodes in first-touch order
-        for (int32_t e : elems)
-          for (int a = 0; a < nn; ++a) {
-            const int32_t n = conn[(int64_t)e * nn + a];
-            if (local[n] < 0) { local[n] = (int32_t)T.nodes.size(); T.nodes.push_back(n); }
-          }
-        // neighbours of owned nodes always belong to the tile, except through diagonal elements
-        bool ok = (int64_t)T.nodes.size() <= lim.max_tile_nodes;
-        if (ok) {
-          // accumulator layout: node blocks in owned order, then per-node extras
-          T.acc_off.assign(T.nodes.size(), -1);
-          T.nbr_cnt.assign(T.nodes.size(), 0);
-          int32_t off = 0;
-          for (int32_t l = 0; l < T.n_owned; ++l) {
-            const int32_t row = P.node_row[T.nodes[l]];
-            const int32_t cnt = (int32_t)(P.nbr_ptr[row + 1] - P.nbr_ptr[row]);
-            T.acc_off[l] = off; T.nbr_cnt[l] = cnt;
-            off += cnt * lim.acc_per_block;
-            T.blocks += cnt;
-            for (int64_t k = P.nbr_ptr[row]; k < P.nbr_ptr[row + 1]; ++k) {
-              const int32_t ll = local[P.nbr[k]];
-              T.nbrl.push_back(ll < 0 ? (uint16_t)0xFFFF : (uint16_t)ll);  // 0xFFFF: neighbour only through a diagonal element
-            }
-          }
-          T.arena = off + T.n_owned * lim.acc_per_node;
-          if (T.arena > lim.arena_doubles) ok = false;
-        }
-        if (!ok) {
-          for (int32_t n : T.nodes) local[n] = -1;
-          if (T.n_owned <= 1) fail = 1;
-          too_big[t] = 1;
-          continue;
-        }
-        // greedy colouring: visits of one step share no owned node
-        used.assign(T.n_owned, 0u);
-        std::vector<int32_t> colour(elems.size());
-        int32_t ncol = 0;
-        for (size_t v = 0; v < elems.size(); ++v) {
-          uint32_t m = 0;
-          for (int a = 0; a < nn; ++a) {
-            const int32_t l = local[conn[(int64_t)elems[v] * nn + a]];
-            if (l < T.n_owned) m |= used[l];
-          }
-          int32_t c = 0;
-          while (c < 32 && (m >> c & 1u)) ++c;
-          if (c >= 32) { fail = 2; c = 31; }
-          colour[v] = c;
-          ncol = std::max(ncol, c + 1);
-          for (int a = 0; a < nn; ++a) {
-            const int32_t l = local[conn[(int64_t)elems[v] * nn + a]];
-            if (l < T.n_owned) used[l] |= 1u << c;
-          }
-        }
-        // accumulation order: colour-major (conflicting visits end up far apart in the order), ascending element id
-        // within a colour; rank = position of the visit among the visits of each of its owned nodes
-        std::vector<int32_t> csize(ncol, 0), start(ncol + 1, 0);
-        for (size_t v = 0; v < elems.size(); ++v) csize[colour[v]]++;
-        for (int32_t c = 0; c < ncol; ++c) start[c + 1] = start[c] + csize[c];
-        const size_t nv_ = elems.size();
-        std::vector<int32_t> order(nv_);
-        for (size_t v = 0; v < nv_; ++v) order[start[colour[v]]++] = (int32_t)v;
-        T.visits.resize(nv_);
-        used.assign(T.n_owned, 0u);  // reused as per-node visit counter
-        for (size_t o = 0; o < nv_; ++o) {
-          const int32_t e = elems[order[o]];
-          const int32_t* c = conn + (int64_t)e * nn;
-          VisitRec8& V = T.visits[o];
-          std::memset(&V, 0, sizeof V);
-          V.elem = e;
-          for (int a = 0; a < nn; ++a) V.ln[a] = (uint16_t)local[c[a]];
-          for (int a = 0; a < nn; ++a) {
-            const int32_t l = local[c[a]];
-            if (l >= T.n_owned) continue;
-            if (used[l] > 250) fail = 3;
-            V.rank[a] = (uint8_t)used[l]++;
-            const int32_t row = P.node_row[c[a]];
-            const int32_t* nb = P.nbr.data() + P.nbr_ptr[row];
-            const int32_t* ne = P.nbr.data() + P.nbr_ptr[row + 1];
-            for (int b = 0; b < nn; ++b) V.slot[a * nn + b] = (uint8_t)(std::lower_bound(nb, ne, c[b]) - nb);
-          }
-        }
-        for (int32_t n : T.nodes) local[n] = -1;
+  // ---- segment length along the sweep -----------------------------------------------------------------------------------
+  const double total_fronts = (double)strips.size() * pl[B.sweep];
+  const int seg_len = (int)std::max(3.0, std::min(128.0, std::floor(total_fronts / (6.0 * std::max(1, lim.sm_count)))));
+
+  // ---- build the tiles of every strip (parallel over strips; a strip that does not fit is split and retried) -----------
+  std::vector<std::vector<TileOut>> built;   // per finished strip
+  const double gap_thresh = 0.5 * B.h[B.sweep];
+  const int max_front = std::max(8, 2 * cols);
+  int guard = 0;
+  while (!strips.empty() && B.error.empty()) {
+    if (++guard > 64) return "plan: strips keep failing to fit shared memory";
+    std::sort(strips.begin(), strips.end(), [](const Range& a, const Range& b) { return a.b < b.b; });
+    const size_t ns = strips.size();
+    std::vector<std::vector<TileOut>> out(ns);
+    std::vector<char> too_big(ns, 0);
+    std::vector<Scratch> scratch(hw_threads());
+    parallel_items((int64_t)ns, [&](int64_t si, int th) {
+      Scratch& sc = scratch[th];
+      if (sc.local.empty()) sc.local.assign(pat.n_nodes, -1);
+      const Range r = strips[si];
+      const int ax = B.sweep;
+      std::sort(perm.begin() + r.b, perm.begin() + r.e, [&](int32_t a, int32_t b) {
+        const double ka = B.coord(a, ax), kb = B.coord(b, ax);
+        return ka < kb || (ka == kb && a < b);
+      });
+      // fronts: cut at coordinate gaps of more than half a node spacing, or when a front gets too large
+      const int64_t cnt = r.e - r.b;
+      std::vector<int32_t> front(cnt);
+      int32_t f = 0, fsz = 0;
+      for (int64_t k = 0; k < cnt; ++k) {
+        if (k > 0 && (B.coord(perm[r.b + k], ax) - B.coord(perm[r.b + k - 1], ax) > gap_thresh || fsz >= max_front)) { ++f; fsz = 0; }
+        front[k] = f; ++fsz;
+      }
+      const int32_t n_fronts = f + 1;
+      const int32_t n_seg = std::max(1, (n_fronts + seg_len / 2) / seg_len);
+      std::vector<int32_t> own, fr;
+      int64_t k0 = 0;
+      for (int32_t sg = 0; sg < n_seg && !too_big[si]; ++sg) {
+        const int32_t f0 = (int32_t)((int64_t)n_fronts * sg / n_seg), f1 = (int32_t)((int64_t)n_fronts * (sg + 1) / n_seg);
+        int64_t k1 = k0;
+        while (k1 < cnt && front[k1] < f1) ++k1;
+        // nodes sorted by (front, gid)
+        std::vector<std::pair<int32_t, int32_t>> tmp;
+        tmp.reserve(k1 - k0);
+        for (int64_t k = k0; k < k1; ++k) tmp.emplace_back(front[k] - f0, perm[r.b + k]);
+        std::sort(tmp.begin(), tmp.end());
+        own.resize(tmp.size()); fr.resize(tmp.size());
+        for (size_t i = 0; i < tmp.size(); ++i) { fr[i] = tmp[i].first; own[i] = tmp[i].second; }
+        out[si].emplace_back();
+        if (!B.build_tile(own.data(), fr.data(), (int32_t)own.size(), f1 - f0, sc, out[si].back())) too_big[si] = 1;
+        k0 = k1;
       }
     });
-    if (fail == 1) return "a single node does not fit the shared-memory arena";
-    if (fail == 2) return "tile needs more than 32 colours";
-    if (fail == 3) return "node touched by more than 250 elements";
-    std::vector<Range> next;
-    for (size_t t = 0; t < leaves.size(); ++t) {
-      if (too_big[t]) split(leaves[t], next);
-      else built.push_back(std::move(tb[t]));
+    if (!B.error.empty()) break;
+    if (std::getenv("MASTB200_PLAN_DEBUG")) {
+      size_t nf = 0;
+      for (char c : too_big) nf += c;
+      std::fprintf(stderr, "[plan] round %d: %zu strips, %zu too big; sweep axis %d, h = %g %g %g, target %dx%d, seg_len %d, limit hit %d\n",
+                   guard, ns, nf, B.sweep, B.h[0], B.h[1], B.h[2], mu, mv, seg_len, (int)B.why);
     }
-    leaves.swap(next);
+    std::vector<Range> next;
+    for (size_t si = 0; si < ns; ++si) {
+      if (!too_big[si]) { built.push_back(std::move(out[si])); continue; }
+      if (strips[si].e - strips[si].b <= 1) return "plan: a single node does not fit the shared-memory arena";
+      std::vector<Range> leaf;
+      cross_split(strips[si], true, leaf, next);
+      for (const Range& l : leaf) next.push_back(l);  // cannot happen for ranges of more than one node
+    }
+    strips.swap(next);
   }
-  // deterministic tile order: by smallest owned node id
-  std::sort(built.begin(), built.end(), [](const TileBuild& a, const TileBuild& b) { return a.nodes[0] < b.nodes[0]; });
+  if (!B.error.empty()) return B.error;
 
-  // ---- concatenate ---------------------------------------------------------------------------------
-  size_t tot_nodes = 0, tot_vis = 0, tot_nbrl = 0;
-  for (const TileBuild& T : built) {
-    tot_nodes += T.nodes.size(); tot_vis += T.visits.size(); tot_nbrl += T.nbrl.size();
+  // ---- concatenate; tiles ordered by descending cost for the dynamic scheduler -----------------------------------------
+  std::vector<TileOut*> all;
+  for (auto& s : built) for (auto& t : s) all.push_back(&t);
+  std::stable_sort(all.begin(), all.end(), [](const TileOut* a, const TileOut* b) { return a->visits.size() > b->visits.size(); });
+  size_t n_steps = 0, n_vis = 0, n_fr = 0, n_fe = 0, n_ld = 0;
+  for (const TileOut* t : all) {
+    n_steps += t->steps.size(); n_vis += t->visits.size(); n_fr += t->frows.size(); n_fe += t->fent.size(); n_ld += t->loads.size();
   }
-  if (tot_nodes >= (size_t(1) << 31) || tot_vis >= (size_t(1) << 31) || tot_nbrl >= (size_t(1) << 31)) return "plan too large";
-  P.tiles.reserve(built.size());
-  P.tile_nodes.reserve(tot_nodes); P.tile_acc_off.reserve(tot_nodes); P.tile_nbr_cnt.reserve(tot_nodes);
-  P.nbr_local.reserve(tot_nbrl);
-  P.visits8.reserve(tot_vis);
-  for (TileBuild& T : built) {
-    TileDesc d;
-    d.node_begin = (int32_t)P.tile_nodes.size();
-    d.n_owned = T.n_owned;
-    d.n_nodes = (int32_t)T.nodes.size();
-    d.visit_begin = (int32_t)P.visits8.size();
-    d.n_visits = (int32_t)T.visits.size();
-    d.arena_doubles = T.arena;
-    d.nbrl_begin = (int32_t)P.nbr_local.size();
-    d.blocks_total = T.blocks;
-    P.tile_nodes.insert(P.tile_nodes.end(), T.nodes.begin(), T.nodes.end());
-    P.tile_acc_off.insert(P.tile_acc_off.end(), T.acc_off.begin(), T.acc_off.end());
-    P.tile_nbr_cnt.insert(P.tile_nbr_cnt.end(), T.nbr_cnt.begin(), T.nbr_cnt.end());
-    P.nbr_local.insert(P.nbr_local.end(), T.nbrl.begin(), T.nbrl.end());
-    P.visits8.insert(P.visits8.end(), T.visits.begin(), T.visits.end());
-    P.tiles.push_back(d);
-    TileBuild().nodes.swap(T.nodes);  // release memory early
-    std::vector<VisitRec8>().swap(T.visits);
+  const size_t lim31 = size_t(1) << 31;
+  if (n_steps >= lim31 || n_vis >= lim31 || n_fr >= lim31 || n_fe >= lim31 || n_ld >= lim31) return "plan too large";
+  plan.tiles.reserve(all.size()); plan.steps.reserve(n_steps); plan.visits.reserve(n_vis);
+  plan.flush_rows.reserve(n_fr); plan.flush_ent.reserve(n_fe); plan.loads.reserve(n_ld);
+  for (TileOut* t : all) {
+    TileDesc td;
+    td.step_begin = (int32_t)plan.steps.size(); td.n_steps = (int32_t)t->steps.size();
+    td.n_visits = (int32_t)t->visits.size(); td.n_owned = t->n_owned;
+    const int32_t v0 = (int32_t)plan.visits.size(), l0 = (int32_t)plan.loads.size(), f0 = (int32_t)plan.flush_rows.size(),
+                  e0 = (int32_t)plan.flush_ent.size();
+    for (StepDesc sd : t->steps) {
+      sd.visit_begin += v0; sd.load_begin += l0; sd.flush_begin += f0; sd.fent_begin += e0;
+      plan.steps.push_back(sd);
+    }
+    plan.visits.insert(plan.visits.end(), t->visits.begin(), t->visits.end());
+    plan.flush_rows.insert(plan.flush_rows.end(), t->frows.begin(), t->frows.end());
+    plan.flush_ent.insert(plan.flush_ent.end(), t->fent.begin(), t->fent.end());
+    plan.loads.insert(plan.loads.end(), t->loads.begin(), t->loads.end());
+    plan.max_live_blocks = std::max(plan.max_live_blocks, t->max_blocks);
+    plan.max_live_slots = std::max(plan.max_live_slots, t->max_slots);
+    plan.tiles.push_back(td);
+    *t = TileOut();  // release memory early
   }
-  return err;
+  return "";
 }
 
 }  // namespace mastb200

@@ -1,12 +1,21 @@
-// plan.h -- static assembly plan: sparsity pattern + node tiles + element visit lists.
+// plan.h -- static assembly plan: sparsity pattern + streaming node tiles ("strips") + element visit lists.
 //
-// The device sweep is a row-owner gather: the owned nodes are cut into compact
-// tiles; a CTA keeps the CSR rows of one tile in shared memory, visits every element adjacent to the
-// tile ("visit"), adds the element's contribution at precomputed slots (the element-to-nnz map of
-// BASELINE.json's north_star, at node-block granularity) and writes each CSR value exactly once.
-// Within a tile, visits are grouped into steps; the visits of one step share no owned node, so warps
-// can accumulate concurrently and the summation order into every CSR entry is fixed by the plan
-// (ascending step, i.e. deterministic and independent of scheduling).
+// The device sweep is a row-owner gather.  The owned nodes are cut into strips: a small
+// cross-section of node columns swept along the mesh's longest axis, one "front" (node plane) per step.
+// A CTA walks a strip step by step; per step it visits every element whose last owned front is that step,
+// accumulates the element's contributions in shared memory and, after the step, writes out every CSR row that
+// has just become complete -- each CSR value goes to HBM exactly once and K_e is never stored.
+//
+// Shared-memory accumulators are kept per unordered node pair {A,B} ("pair block", 9 doubles of
+// S_AB = sum_q w_q grad N_A (x) grad N_B; S_BA = S_AB^T, so one block serves rows A and B).  A pair block lives
+// from the first visit that touches it until the rows of its owned endpoints are written; slots are handed out
+// by the planner, so a strip only ever holds about two fronts of pairs no matter how long it is.  The same
+// holds for the staged nodal state (coordinates, solution, ...), which lives in planner-assigned "state slots".
+//
+// Ordering: visits of a strip are totally ordered (step, colour, element id).  rank[a] of a visit is the number
+// of earlier visits of the strip touching owned node a; the device adds into the pairs of node a only once the
+// node's counter equals rank[a], which fixes the summation order into every CSR entry (deterministic,
+// independent of scheduling) without CTA-wide barriers inside a step.
 //
 // Everything here is integer bookkeeping built once per mesh, like libMesh's sparsity pattern /
 // PETSc preallocation that the reference relies on (nonlinear_implicit_assembly.cpp:182-183).
@@ -17,38 +26,63 @@
 
 namespace mastb200 {
 
-struct TileDesc {
-  int32_t node_begin;     // offset into tile_nodes (owned nodes first, sorted by id; then halo nodes)
+// ---- device records ------------------------------------------------------------------------------------------
+struct TileDesc {       // one strip segment
+  int32_t step_begin;   // into steps
+  int32_t n_steps;
+  int32_t n_visits;     // total, for scheduling (tiles are sorted by descending cost)
   int32_t n_owned;
-  int32_t n_nodes;        // owned + halo
-  int32_t visit_begin;    // visits of the tile, in the order in which they are accumulated
-  int32_t n_visits;
-  int32_t arena_doubles;  // shared-memory accumulator doubles used by this tile
-  int32_t nbrl_begin;     // offset into nbr_local of the first owned node's neighbour list
-  int32_t blocks_total;   // sum over owned nodes of their neighbour counts
 };
 
-// One element visit of a HEX8 tile, 96 bytes (six 16-byte words; a chunk of 4 visits is loaded with 3 coalesced
-// 4-byte loads per lane).  rank[a] is the number of earlier visits of the same tile that touch owned node a: the
-// device accumulates into node a only once its per-node counter equals rank[a], which fixes the summation order
-// into every CSR entry without CTA-wide barriers.
+struct StepDesc {
+  int32_t visit_begin, n_visits;   // visits of the step in accumulation order
+  int32_t load_begin, n_loads;     // node states that must be resident before the step's visits start
+  int32_t flush_begin, n_flush;    // rows written after the step
+  int32_t fent_begin, n_fent;      // flush entries of those rows
+};
+
+// One element visit of a HEX8 strip, 96 bytes (a chunk of 4 visits = 3 coalesced 4-byte loads per lane).
 struct alignas(16) VisitRec8 {
-  uint16_t ln[8];    // tile-local node ids
-  uint8_t rank[8];
-  int32_t elem;
-  int32_t pad;
-  uint8_t slot[64];  // [a][b]: position of node b in the neighbour list (CSR row) of node a, for owned a
+  uint16_t ln[8];     // state slots of the element's nodes (libMesh node order)
+  uint8_t rank[8];    // accumulation rank per node; 0xFF: node not owned by the strip
+  uint16_t pair[36];  // local node pairs (a<=b), index a*(15-a)/2+b: kPairNone, or
+                      // bits 0-11 arena block, bit 12: stored block is S_(b,a) (transposed), bit 13: first touch (store, don't add)
 };
 static_assert(sizeof(VisitRec8) == 96, "VisitRec8 must be 96 bytes");
+constexpr uint16_t kPairNone = 0xFFFF;
+constexpr uint16_t kPairSlotMask = 0x0FFF, kPairTransposed = 0x1000, kPairInit = 0x2000;
 
-struct PlanLimits {
-  int32_t arena_doubles;    // accumulator capacity in doubles
-  int32_t max_tile_nodes;   // owned + halo nodes whose state is staged in shared memory
-  int32_t acc_per_block;    // doubles accumulated per (row node, column node) pair: 9 solid, 1 heat
-  int32_t acc_per_node;     // extra doubles per owned node (f, G, rot-diag)
+struct alignas(16) FlushRow {   // one owned node whose 3 (nv=3) or 6 CSR rows are complete
+  int64_t dst_block;    // offset of the node's first neighbour block in the node-level CSR (nbr_ptr[row])
+  int32_t gid;          // global node id
+  int32_t ent_rel;      // first flush entry of the row, relative to the step's fent_begin
+  uint16_t slot;        // state slot of the node
+  uint16_t nnb;         // neighbour count (== number of flush entries)
+  uint16_t nadj;        // elements adjacent to the node (not in diagonal_elem_subdomain_id)
+  uint16_t nadjd;       // adjacent elements of diagonal_elem_subdomain_id
+  int32_t pad[2];
+};
+static_assert(sizeof(FlushRow) == 32, "FlushRow must be 32 bytes");
+// flush entry (uint32), one per neighbour in CSR column order:
+//   bits 0-11 arena block (kFlushNoBlock: neighbour only through diagonal elements), bit 12: block holds S_(nbr,row),
+//   bit 13: self pair (upper triangle valid), bits 16-31: state slot of the neighbour (0xFFFF: not staged)
+constexpr uint32_t kFlushNoBlock = 0x0FFF, kFlushTransposed = 0x1000, kFlushSelf = 0x2000;
+
+struct LoadRec {        // node state to stage: global id -> slot
+  int32_t gid;
+  uint16_t slot;
+  uint16_t owned;
 };
 
-struct Plan {
+// ---- host plan -----------------------------------------------------------------------------------------------
+struct PlanLimits {
+  int32_t arena_blocks;     // pair blocks (9 doubles each) that fit the shared-memory arena (<= 4095)
+  int32_t max_slots;        // node state slots
+  int32_t flush_buf_bytes;  // per-step flush records staged in shared memory
+  int32_t sm_count;         // for the tile count heuristic
+};
+
+struct Pattern {
   int32_t nn = 0;           // nodes per element
   int64_t n_nodes = 0, n_elem = 0, n_owned = 0;
   // node-level sparsity of the owned rows: neighbours of owned node k (ascending node id)
@@ -58,21 +92,31 @@ struct Plan {
   std::vector<int32_t> node_row;         // [n_nodes] index into owned_nodes or -1
   std::vector<int32_t> n_adj_elem;       // [n_nodes] number of (non-diagonal) elements touching the node
   std::vector<int32_t> n_adj_diag_elem;  // [n_nodes] number of diagonal_elem_subdomain elements touching it
-  // tiles
+  std::vector<int64_t> n2e_ptr;          // node -> element adjacency (ascending element id)
+  std::vector<int32_t> n2e;
+};
+
+struct StreamPlan {
+  PlanLimits lim{};
   std::vector<TileDesc> tiles;
-  std::vector<int32_t> tile_nodes;       // global node id per tile-local node
-  std::vector<int32_t> tile_acc_off;     // per tile-local node: accumulator offset (owned) or -1
-  std::vector<int32_t> tile_nbr_cnt;     // per tile-local node: neighbour count (owned) or 0
-  std::vector<uint16_t> nbr_local;       // per owned tile node, per neighbour: tile-local id of the neighbour
-  std::vector<VisitRec8> visits8;        // HEX8 visit records
-  int64_t n_visits() const { return (int64_t)visits8.size(); }
+  std::vector<StepDesc> steps;
+  std::vector<VisitRec8> visits;
+  std::vector<FlushRow> flush_rows;
+  std::vector<uint32_t> flush_ent;
+  std::vector<LoadRec> loads;
+  int32_t max_live_blocks = 0, max_live_slots = 0;
+  int64_t n_visits() const { return (int64_t)visits.size(); }
   int64_t bytes() const;
 };
 
-// Builds pattern and tiles. conn: [n_elem][nn]; owned: [n_nodes] flags or nullptr; diag_elem: [n_elem] or nullptr
-// (elements of AssemblyBase::diagonal_elem_subdomain_id take no part in the sweep but are in the pattern).
-// Returns empty string on success, else an error message.
-std::string build_plan(int32_t nn, int64_t n_nodes, int64_t n_elem, const double* xyz, const int32_t* conn,
-                       const uint8_t* owned, const uint8_t* diag_elem, const PlanLimits& lim, Plan& plan);
+// Sparsity pattern of the owned rows. conn: [n_elem][nn]; owned: [n_nodes] flags or nullptr;
+// diag_elem: [n_elem] or nullptr (elements of AssemblyBase::diagonal_elem_subdomain_id take no part in the sweep
+// but are in the pattern).  Returns empty string on success, else an error message.
+std::string build_pattern(int32_t nn, int64_t n_nodes, int64_t n_elem, const int32_t* conn, const uint8_t* owned,
+                          const uint8_t* diag_elem, Pattern& pat);
+
+// Streaming plan for HEX8 (nn == 8) within the given shared-memory limits.
+std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
+                              const PlanLimits& lim, StreamPlan& plan);
 
 }  // namespace mastb200

@@ -6,21 +6,24 @@
 // ::thermal_residual (:950-1089) and the sensitivity sweep of SURVEY 8a row S
 // (sensitivity_assemble, nonlinear_implicit_assembly.cpp:515-686, for all nodal-density DVs at once).
 //
-// One CTA owns one node tile at a time (plan.h).  Per element visit:
-//   geometry phase : one lane per (element, quadrature point) -- 4 elements x 8 points per warp -- builds
-//                    J, det, the physical gradients g_b of the 8 shape functions, the weight
-//                    w = JxW*E(rho_q), the weighted stress P = JxW*sigma and the sensitivity density s.
-//   matrix phase   : S_ij[a][b] = sum_q w_q g_a[i] g_b[j] is a 24x24x8 product done with 18
-//                    mma.sync.m8n8k4.f64 (DMMA); lane (a, q) holds exactly the (a, q) operand entry, so
-//                    the A and B fragments are the same registers (B = w*A) and each lane ends with the
-//                    complete 3x3 blocks S[a][b], b in {2(lane%4), 2(lane%4)+1}.
-//   accumulate     : blocks are added to the tile's CSR rows in shared memory at plan slots; visits of
-//                    one step touch disjoint owned nodes, so no atomics and a fixed summation order.
-// At tile end the accumulated S is turned into K = lam*S + mu*S^T + mu*tr(S)*I (isotropic D,
-// src/property_cards/isotropic_material_property_card.cpp:512-528, modulus folded into w), the per-element
-// Dirichlet semantics of libMesh's constrain_element_matrix_and_vector are applied (row/column zeroed,
-// diagonal = number of adjacent elements, rhs zeroed) and every CSR value is written to HBM exactly once
-// with contiguous, coalesced stores.  K_e is never stored.
+// One persistent CTA per SM walks strips of the mesh (plan.h) front by front.  Per step:
+//   visits   : warps take chunks of 4 element visits in plan order.
+//     geometry phase : one lane per (element, quadrature point) builds J, det, the physical gradients g_b of the
+//                      8 shape functions and the weight w = JxW*E(rho_q); gradients are staged in shared memory.
+//     matrix phase   : S_ij[a][b] = sum_q w_q g_a[i] g_b[j] is a 24x24x8 product.  Only the six component pairs
+//                      i<=j are formed (S_ji[a][b] = S_ij[b][a]) with 12 mma.sync.m8n8k4.f64 (DMMA); lane (a, q)
+//                      holds exactly the (a, q) operand entry, so the A and B fragments are the same registers
+//                      (B = w*A).
+//     accumulate     : the 3x3 block S_ab of every node pair {a,b} with an owned end is added to the pair's
+//                      shared-memory block (one block per unordered pair; S_ba = S_ab^T).  Per-node counters
+//                      enforce the plan's visit order, so there are no atomics and the summation order into every
+//                      CSR entry is fixed.
+//   flush    : every node whose last element has been visited gets its rows written: K_ab = lam*S + mu*S^T +
+//              mu*tr(S)*I (isotropic D, src/property_cards/isotropic_material_property_card.cpp:512-528, modulus
+//              folded into w), the per-element Dirichlet semantics of libMesh's constrain_element_matrix_and_vector
+//              (row/column zeroed, diagonal = number of adjacent elements, rhs zeroed), the internal force
+//              f_a = sum_b K_ab u_b (linear strain) and one store of every CSR value to HBM.  K_e is never stored.
+//   Warp 0 stages the nodal state of the next step and the flush records of the current one while the others compute.
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -30,14 +33,15 @@ namespace mastb200 {
 
 namespace {
 
-constexpr int WARPS = 8;
+constexpr int WARPS = 12;
 constexpr int THREADS = WARPS * 32;
-constexpr int MAXN = kMaxTileNodes;  // staged tile nodes
-constexpr int EL_STRIDE = 280;       // doubles staged per element: V 216 | w 8 | P 48 | s 8   (== 8 mod 16: conflict-free)
 constexpr int STAGE_EL = 2;          // elements staged per warp at a time
 constexpr int V_HALF = 36;           // stride of one (component, qp-half) 8x4 operand panel (32 + 4 pad)
-constexpr int OFF_W = 216, OFF_P = 224, OFF_S = 272;
-constexpr int EXTRA = kAccPerNode;   // per owned node: f[3], G, rot-diag
+constexpr int OFF_W = 216, OFF_PTH = 224, OFF_S = 232;
+constexpr int STRIDE_PLAIN = 232;    // V 216 | w 8 | pad      (== 8 mod 16: the two staged elements hit disjoint banks)
+constexpr int STRIDE_AUX = 248;      // V 216 | w 8 | pth 8 | s 8 | pad
+constexpr int EXTRA = 5;             // per slot (aux layout): thermal f[3], G, rot-diag
+constexpr int REC_WORDS = 24;        // sizeof(VisitRec8) / 4
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -51,41 +55,42 @@ __device__ __forceinline__ constexpr int sgy(int b) { return (b == 2 || b == 3 |
 __device__ __forceinline__ constexpr int sgz(int b) { return (b >= 4) ? 1 : -1; }
 
 struct Smem {
-  double* arena;
+  double* arena;   // pair blocks
   double* xyz;
   double* u;
-  double* adj;
-  double* rho;
-  double* T;
+  double* adj;     // aux
+  double* rho;     // aux
+  double* T;       // aux
+  double* extras;  // aux
   double* stage;
-  int32_t* accoff;
+  unsigned char* fbuf;
+  uint32_t* rec;   // per warp: the 4 visit records of the current chunk
   int32_t* gid;
-  int32_t* cnt;     // per owned node: number of element contributions accumulated so far
-  uint32_t* rec;    // per warp: the 4 visit records of the current chunk
-  uint8_t* nbrcnt;
+  int32_t* cnt;    // per slot: number of element contributions accumulated so far
   uint8_t* cm;
+  StepDesc* sd;    // [2]
+  int* misc;       // [0] chunk dispenser, [1] current tile
 };
-
-constexpr int REC_WORDS = 24;  // sizeof(VisitRec8) / 4
 
 __device__ __forceinline__ int ld_volatile_s32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
 __device__ __forceinline__ void st_volatile_s32(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
 
 struct Flags {
-  bool J, R, G, simp, thermal, nv6;
+  bool J, R, G, simp, thermal, nv6, S;  // S: pair blocks are accumulated (J or R requested)
 };
 
 // ---- geometry phase: lane = (element slot el, quadrature point q) ---------------------------------------
+template <bool AUX>
 struct QpData {
   double g[8][3];  // physical shape-function gradients
   double w;        // JxW * E(rho_q)
-  double P[6];     // JxW * stress (xx,yy,zz,xy,yz,zx), thermal part subtracted
-  double s;        // sensitivity density  JxW * dE/drho * eps(adj)^T Dhat eps(u)
-  double N[8];
+  double pth;      // AUX: -JxW * E * alpha_k * (T - Tref)   (thermal stress, isotropic)
+  double s;        // AUX: sensitivity density  JxW * dE/drho * eps(adj)^T Dhat eps(u)
 };
 
+template <bool AUX>
 __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const int ln[8],
-                                               int q, QpData& d) {
+                                               int q, QpData<AUX>& d) {
   constexpr double gp = 0.57735026918962576451;
   const double xi = (q & 1) ? gp : -gp, eta = (q & 2) ? gp : -gp, zeta = (q & 4) ? gp : -gp;
   const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
@@ -97,7 +102,6 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
     dref[b][0] = 0.125 * sgx(b) * fy * fz;
     dref[b][1] = 0.125 * sgy(b) * fx * fz;
     dref[b][2] = 0.125 * sgz(b) * fx * fy;
-    d.N[b] = 0.125 * fx * fy * fz;
     const double* X = sm.xyz + ln[b] * 3;
     const double x0 = X[0], x1 = X[1], x2 = X[2];
 #pragma unroll
@@ -127,127 +131,114 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
     for (int c = 0; c < 3; ++c)
       d.g[b][c] = dref[b][0] * inv[c][0] + dref[b][1] * inv[c][1] + dref[b][2] * inv[c][2];
 
-  // modulus at the point: constant or SIMP of the interpolated nodal density (example_6.cpp:100-137)
-  double E = p.E0, dE = 0.;
-  if (fl.simp) {
-    double r = 0.;
-#pragma unroll
-    for (int b = 0; b < 8; ++b) r = fma(d.N[b], sm.rho[ln[b]], r);
-    E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(r, p.penalty));
-    if (fl.G) dE = p.E0 * (1. - p.rho_min) * p.penalty * pow(r, p.penalty - 1.);
-  }
   const double JxW = det;  // Gauss weights are 1 for the 2x2x2 rule
-  d.w = JxW * E;
-  d.s = 0.;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) d.P[k] = 0.;
-  if (fl.R || fl.G) {
-    double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // H[i][j] = d u_i / d x_j
+  double E = p.E0;
+  d.pth = 0.; d.s = 0.;
+  if (AUX) {
+    double N[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
-      const double* U = sm.u + ln[b] * 3;
-      const double u0 = U[0], u1 = U[1], u2 = U[2];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        H[0][j] = fma(u0, d.g[b][j], H[0][j]);
-        H[1][j] = fma(u1, d.g[b][j], H[1][j]);
-        H[2][j] = fma(u2, d.g[b][j], H[2][j]);
-      }
+      const double fx = sgx(b) > 0 ? xp : xm, fy = sgy(b) > 0 ? yp : ym, fz = sgz(b) > 0 ? zp : zm;
+      N[b] = 0.125 * fx * fy * fz;
     }
-    const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
-    const double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
-    const double tr = e0 + e1 + e2;
-    if (fl.R) {
-      const double lw = p.lam1 * d.w, mw = p.mu1 * d.w;
-      double th = 0.;
-      if (fl.thermal) {  // thermal_residual: f -= JxW B^T (D alpha dT)
-        double t = 0.;
+    // modulus at the point: constant or SIMP of the interpolated nodal density (example_6.cpp:100-137)
+    double dE = 0.;
+    if (fl.simp) {
+      double r = 0.;
 #pragma unroll
-        for (int b = 0; b < 8; ++b) t = fma(d.N[b], sm.T[ln[b]], t);
-        th = d.w * p.alpha_k * (t - p.T_ref);
-      }
-      d.P[0] = lw * tr + 2. * mw * e0 - th;
-      d.P[1] = lw * tr + 2. * mw * e1 - th;
-      d.P[2] = lw * tr + 2. * mw * e2 - th;
-      d.P[3] = mw * e3;
-      d.P[4] = mw * e4;
-      d.P[5] = mw * e5;
+      for (int b = 0; b < 8; ++b) r = fma(N[b], sm.rho[ln[b]], r);
+      E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(r, p.penalty));
+      if (fl.G) dE = p.E0 * (1. - p.rho_min) * p.penalty * pow(r, p.penalty - 1.);
+    }
+    if (fl.thermal && fl.R) {  // thermal_residual: f -= JxW B^T (D alpha dT)
+      double t = 0.;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) t = fma(N[b], sm.T[ln[b]], t);
+      d.pth = -(JxW * E) * p.alpha_k * (t - p.T_ref);
     }
     if (fl.G) {
+      double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // H[i][j] = d u_i / d x_j
       double A[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
-        const double* U = sm.adj + ln[b] * 3;
-        const double u0 = U[0], u1 = U[1], u2 = U[2];
+        const double* U = sm.u + ln[b] * 3;
+        const double* L = sm.adj + ln[b] * 3;
+        const double u0 = U[0], u1 = U[1], u2 = U[2], l0 = L[0], l1 = L[1], l2 = L[2];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          A[0][j] = fma(u0, d.g[b][j], A[0][j]);
-          A[1][j] = fma(u1, d.g[b][j], A[1][j]);
-          A[2][j] = fma(u2, d.g[b][j], A[2][j]);
+          H[0][j] = fma(u0, d.g[b][j], H[0][j]);
+          H[1][j] = fma(u1, d.g[b][j], H[1][j]);
+          H[2][j] = fma(u2, d.g[b][j], H[2][j]);
+          A[0][j] = fma(l0, d.g[b][j], A[0][j]);
+          A[1][j] = fma(l1, d.g[b][j], A[1][j]);
+          A[2][j] = fma(l2, d.g[b][j], A[2][j]);
         }
       }
+      const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
+      const double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
       const double a0 = A[0][0], a1 = A[1][1], a2 = A[2][2];
       const double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
-      const double dens = p.lam1 * (a0 + a1 + a2) * tr +
+      const double dens = p.lam1 * (a0 + a1 + a2) * (e0 + e1 + e2) +
                           p.mu1 * (2. * (a0 * e0 + a1 * e1 + a2 * e2) + a3 * e3 + a4 * e4 + a5 * e5);
       d.s = JxW * dE * dens;
     }
   }
+  d.w = JxW * E;
 }
 
-__device__ __forceinline__ void stage_write(double* st, int q, const QpData& d) {
+template <bool AUX>
+__device__ __forceinline__ void stage_write(double* st, int q, const QpData<AUX>& d) {
   const int h = q >> 2, q4 = q & 3;
 #pragma unroll
   for (int b = 0; b < 8; ++b)
 #pragma unroll
     for (int i = 0; i < 3; ++i) st[(i * 2 + h) * V_HALF + b * 4 + q4] = d.g[b][i];
   st[OFF_W + q] = d.w;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) st[OFF_P + q * 6 + k] = d.P[k];
-  st[OFF_S + q] = d.s;
+  if (AUX) { st[OFF_PTH + q] = d.pth; st[OFF_S + q] = d.s; }
 }
 
 // ---- matrix phase: all 32 lanes on one element; lane = (row node a, qp q4 | q4+4) ------------------------------
 // rec: the visit record in shared memory.  All arithmetic (DMMA, lane reductions) happens first; the adds into the
-// tile's rows wait until the per-node counters say that every earlier visit of the plan order has landed.
+// pair blocks wait until the per-node counters say that every earlier visit of the plan order has landed.
+template <bool AUX>
 __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const double* st,
-                                              const uint32_t* rec, int extras_base, int lane) {
+                                              const uint32_t* rec, int lane) {
   const int a = lane >> 2, q4 = lane & 3;
   const uint16_t* rec16 = reinterpret_cast<const uint16_t*>(rec);
   const uint8_t* rec8 = reinterpret_cast<const uint8_t*>(rec);
   const int la = rec16[a];
   const int rank = rec8[16 + a];
-  const unsigned slots = rec16[16 + a * 4 + q4];  // bytes 32 + a*8 + 2*q4
-  const int accoff = sm.accoff[la];
-  const int nnb = sm.nbrcnt[la];
+  const bool own = rank != 0xFF;
   double A[3][2];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
     A[i][0] = st[(i * 2 + 0) * V_HALF + lane];
     A[i][1] = st[(i * 2 + 1) * V_HALF + lane];
   }
-  double C[3][3][2];
+  // C[k][bb]: component pairs k = 0..5 <-> (0,0),(1,1),(2,2),(0,1),(0,2),(1,2); columns b = 2*q4 + bb
+  double C[6][2];
   double mx = 0., t0 = 0., t1 = 0., t2 = 0., tg = 0.;
-  if (fl.J) {
+  if (fl.S) {
     const double w0 = st[OFF_W + q4], w1 = st[OFF_W + 4 + q4];
     double B[3][2];
 #pragma unroll
     for (int j = 0; j < 3; ++j) { B[j][0] = A[j][0] * w0; B[j][1] = A[j][1] * w1; }
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 6; ++k) { C[k][0] = 0.; C[k][1] = 0.; }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) { C[i][j][0] = 0.; C[i][j][1] = 0.; }
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) dmma8x8x4(C[i][j][0], C[i][j][1], A[i][h], B[j][h]);
-    if (fl.nv6) {
+    for (int h = 0; h < 2; ++h) {
+      dmma8x8x4(C[0][0], C[0][1], A[0][h], B[0][h]);
+      dmma8x8x4(C[1][0], C[1][1], A[1][h], B[1][h]);
+      dmma8x8x4(C[2][0], C[2][1], A[2][h], B[2][h]);
+      dmma8x8x4(C[3][0], C[3][1], A[0][h], B[1][h]);
+      dmma8x8x4(C[4][0], C[4][1], A[0][h], B[2][h]);
+      dmma8x8x4(C[5][0], C[5][1], A[1][h], B[2][h]);
+    }
+    if (AUX && fl.nv6) {
       // 1e-20*max(diag K_e) on the rotational diagonal (solid_element_3d.cpp:413-417); diag of K_e from S_aa
       const int bself = a - 2 * q4;  // the rotational diagonal itself is zero, so the max is at least 0
       if (bself == 0 || bself == 1) {
-        const double s0 = C[0][0][bself & 1], s1 = C[1][1][bself & 1], s2 = C[2][2][bself & 1];
+        const double s0 = C[0][bself & 1], s1 = C[1][bself & 1], s2 = C[2][bself & 1];
         const double trm = p.mu1 * (s0 + s1 + s2);
         mx = fmax(mx, fmax((p.lam1 + p.mu1) * s0 + trm, fmax((p.lam1 + p.mu1) * s1 + trm, (p.lam1 + p.mu1) * s2 + trm)));
       }
@@ -255,12 +246,11 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
       for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     }
   }
-  if (fl.R) {
-    const double* P0 = st + OFF_P + q4 * 6;
-    const double* P1 = P0 + 24;
-    t0 = P0[0] * A[0][0] + P0[3] * A[1][0] + P0[5] * A[2][0] + P1[0] * A[0][1] + P1[3] * A[1][1] + P1[5] * A[2][1];
-    t1 = P0[3] * A[0][0] + P0[1] * A[1][0] + P0[4] * A[2][0] + P1[3] * A[0][1] + P1[1] * A[1][1] + P1[4] * A[2][1];
-    t2 = P0[5] * A[0][0] + P0[4] * A[1][0] + P0[2] * A[2][0] + P1[5] * A[0][1] + P1[4] * A[1][1] + P1[2] * A[2][1];
+  if (AUX && fl.thermal && fl.R) {
+    const double p0 = st[OFF_PTH + q4], p1 = st[OFF_PTH + 4 + q4];
+    t0 = p0 * A[0][0] + p1 * A[0][1];
+    t1 = p0 * A[1][0] + p1 * A[1][1];
+    t2 = p0 * A[2][0] + p1 * A[2][1];
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
       t0 += __shfl_xor_sync(0xffffffffu, t0, o);
@@ -268,7 +258,7 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
       t2 += __shfl_xor_sync(0xffffffffu, t2, o);
     }
   }
-  if (fl.G) {
+  if (AUX && fl.G) {
     // N_a at qp q4 and q4+4
     constexpr double gp = 0.57735026918962576451;
     const double xi = (q4 & 1) ? gp : -gp, eta = (q4 & 2) ? gp : -gp;
@@ -282,225 +272,339 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
   }
 
   // ---- ordered accumulation ----
-  const bool own = accoff >= 0;
   if (own && q4 == 0)
     while (ld_volatile_s32(sm.cnt + la) != rank) {}
   __threadfence_block();
   __syncwarp();
-  if (own) {
-    if (fl.J) {
-      const int rs = 3 * nnb;
+  if (fl.S) {
 #pragma unroll
-      for (int bb = 0; bb < 2; ++bb) {
-        double* dst = sm.arena + accoff + 3 * ((slots >> (8 * bb)) & 255u);
-#pragma unroll
-        for (int i = 0; i < 3; ++i)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) dst[i * rs + j] += C[i][j][bb];
+    for (int bb = 0; bb < 2; ++bb) {
+      const int b = 2 * q4 + bb;
+      const int lo = min(a, b), hi = max(a, b);
+      const unsigned e = rec16[12 + lo * (15 - lo) / 2 + hi];
+      if (e != kPairNone) {
+        double* blk = sm.arena + (e & kPairSlotMask) * 9;
+        const bool tr = (((e & kPairTransposed) != 0) != (a > b));  // stored block is S_(hi,lo)-oriented relative to (a,b)
+        const bool init = (e & kPairInit) != 0;
+        // off-diagonal components (i<j): S_ab[i][j] = C_ij[a][b] goes to [i][j], or to [j][i] of the transposed block
+        const int o01 = tr ? 3 : 1, o02 = tr ? 6 : 2, o12 = tr ? 7 : 5;
+        if (init) {
+          blk[o01] = C[3][bb]; blk[o02] = C[4][bb]; blk[o12] = C[5][bb];
+          if (a <= b) { blk[0] = C[0][bb]; blk[4] = C[1][bb]; blk[8] = C[2][bb]; }
+        } else {
+          blk[o01] += C[3][bb]; blk[o02] += C[4][bb]; blk[o12] += C[5][bb];
+          if (a <= b) { blk[0] += C[0][bb]; blk[4] += C[1][bb]; blk[8] += C[2][bb]; }
+        }
       }
     }
-    if (q4 == 0) {
-      double* ex = sm.arena + extras_base + la * EXTRA;
-      if (fl.R) { ex[0] += t0; ex[1] += t1; ex[2] += t2; }
-      if (fl.G) ex[3] += tg;
-      if (fl.J && fl.nv6) ex[4] += 1.0e-20 * mx;
-    }
+  }
+  if (AUX && own && q4 == 0) {
+    double* ex = sm.extras + la * EXTRA;
+    if (fl.thermal && fl.R) { ex[0] += t0; ex[1] += t1; ex[2] += t2; }
+    if (fl.G) ex[3] += tg;
+    if (fl.S && fl.nv6) ex[4] += 1.0e-20 * mx;
   }
   __threadfence_block();
   __syncwarp();
   if (own && q4 == 0) st_volatile_s32(sm.cnt + la, rank + 1);
 }
 
-// ---- tile flush: S -> K, Dirichlet semantics, coalesced write of the tile's CSR rows -----------------------
-__device__ __forceinline__ void flush_tile(const SweepParams& p, const Smem& sm, const Flags& fl, const TileDesc& td,
-                                           int extras_base, int warp, int lane) {
-  for (int l = warp; l < td.n_owned; l += WARPS) {
-    const int n = sm.gid[l];
-    const int nnb = sm.nbrcnt[l];
-    const int base = sm.accoff[l];
-    const int rs = 3 * nnb;
-    const unsigned cmn = sm.cm[l];
-    const int nadj = p.n_adj_elem[n], nadjd = p.n_adj_diag[n];
-    const int64_t row = p.node_row[n];
-    const double* ex = sm.arena + extras_base + l * EXTRA;
-    int self_c = -1;
-    if (fl.J) {
-      const uint16_t* nl = p.nbr_local + td.nbrl_begin + base / 9;
-      for (int c0 = 0; c0 < nnb; c0 += 32) {
-        const int c = c0 + lane;
-        bool self = false;
-        if (c < nnb) {
-          double* blk = sm.arena + base + 3 * c;
-          double S[3][3];
+// ---- staging of nodal state (loads of one step) by `nthr` threads, this thread being number `t` ---------------
+template <bool AUX>
+__device__ __forceinline__ void load_states(const SweepParams& p, const Smem& sm, int begin, int n, int t, int nthr) {
+  constexpr int UN = 4;
+  for (int i0 = t; i0 < n; i0 += nthr * UN) {
+    LoadRec lr[UN];
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      const int i = i0 + k * nthr;
+      if (i < n) lr[k] = p.loads[begin + i];
+    }
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      const int i = i0 + k * nthr;
+      if (i >= n) continue;
+      const int n_ = lr[k].gid, sl = lr[k].slot;
+      const unsigned cm = p.cmask ? p.cmask[n_] : 0u;
+      sm.gid[sl] = n_;
+      sm.cnt[sl] = 0;
+      sm.cm[sl] = (uint8_t)cm;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        sm.xyz[sl * 3 + c] = p.xyz[(int64_t)n_ * 3 + c];
+        sm.u[sl * 3 + c] = p.X[(int64_t)n_ * p.nv + c];
+      }
+      if (AUX) {
+        // constrain_element_vector zeroes constrained rows of dR/dp, i.e. the adjoint never sees them
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm.adj[sl * 3 + c] = (p.adj && !((cm >> c) & 1u)) ? p.adj[(int64_t)n_ * p.nv + c] : 0.;
+        sm.rho[sl] = p.rho ? p.rho[n_] : 1.;
+        sm.T[sl] = p.temperature ? p.temperature[n_] : p.T_const;
+#pragma unroll
+        for (int c = 0; c < EXTRA; ++c) sm.extras[sl * EXTRA + c] = 0.;
+      }
+    }
+  }
+}
+
+// ---- flush: S -> K, Dirichlet semantics, f = K u, one store of every CSR value of the finished rows --------------
+template <bool AUX>
+__device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm, const Flags& fl, const StepDesc& sd,
+                                           int warp, int lane) {
+  const FlushRow* rows = reinterpret_cast<const FlushRow*>(sm.fbuf);
+  const uint32_t* ents = reinterpret_cast<const uint32_t*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
+  for (int r = warp; r < sd.n_flush; r += WARPS) {
+    const FlushRow fr = rows[r];
+    const int nnb = fr.nnb;
+    const int sa = fr.slot;
+    const unsigned cmn = sm.cm[sa];
+    const int n = fr.gid;
+    const double nadj = double(fr.nadj + fr.nadjd), nadjd = double(fr.nadjd);
+    const double* ex = AUX ? sm.extras + sa * EXTRA : nullptr;
+    double r0 = 0., r1 = 0., r2 = 0.;
+    for (int c0 = 0; c0 < nnb; c0 += 32) {
+      const int c = c0 + lane;
+      if (c < nnb) {
+        const uint32_t e = ents[fr.ent_rel + c];
+        const unsigned bs = e & kFlushNoBlock;
+        const bool self = (e & kFlushSelf) != 0;
+        const unsigned ns = e >> 16;
+        double S[3][3];
+        if (bs != kFlushNoBlock) {
+          const double* blk = sm.arena + bs * 9;
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) S[i][j] = blk[i * rs + j];
-          const double trm = p.mu1 * (S[0][0] + S[1][1] + S[2][2]);
-          const int ml = nl[c];
-          self = (ml == l);
-          const unsigned cmm = (ml != 0xFFFF) ? sm.cm[ml] : 0u;
+            for (int j = 0; j < 3; ++j) S[i][j] = blk[i * 3 + j];
+          if (self) { S[1][0] = S[0][1]; S[2][0] = S[0][2]; S[2][1] = S[1][2]; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) S[i][j] = 0.;
+        }
+        // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
+        const bool tr = (e & kFlushTransposed) != 0;
+        const double l1 = tr ? p.mu1 : p.lam1, l2 = tr ? p.lam1 : p.mu1;
+        const double trm = p.mu1 * (S[0][0] + S[1][1] + S[2][2]);
+        double K[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i][j] + l2 * S[j][i] + (i == j ? trm : 0.);
+        unsigned cmm = 0u;
+        if (ns != 0xFFFFu) {
+          cmm = sm.cm[ns];
+          if (fl.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
+            const double u0 = sm.u[ns * 3], u1 = sm.u[ns * 3 + 1], u2 = sm.u[ns * 3 + 2];
+            r0 += K[0][0] * u0 + K[0][1] * u1 + K[0][2] * u2;
+            r1 += K[1][0] * u0 + K[1][1] * u1 + K[1][2] * u2;
+            r2 += K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
+          }
+        }
+        if (fl.J) {
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
-              double k = p.lam1 * S[i][j] + p.mu1 * S[j][i] + (i == j ? trm : 0.);
+              double k = K[i][j];
               if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
               if (self && i == j) {
-                if ((cmn >> i) & 1u) k = double(nadj + nadjd);  // each adjacent element sets the diagonal to 1
-                else k += 1.0e-24 * nadjd;                      // diagonal_elem_subdomain_id elements
+                if ((cmn >> i) & 1u) k = nadj;       // each adjacent element sets the diagonal to 1
+                else k += 1.0e-24 * nadjd;           // diagonal_elem_subdomain_id elements
               }
-              blk[i * rs + j] = k;
+              K[i][j] = k;
             }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, self);
-        if (bal) self_c = c0 + __ffs(bal) - 1;
-      }
-      __syncwarp();
-      if (!fl.nv6) {
-        double* dst = p.J + 9 * p.nbr_ptr[row];
-        const double* src = sm.arena + base;
-        for (int k = lane; k < 9 * nnb; k += 32) dst[k] = src[k];
-      } else {
-        double* dst = p.J + 36 * p.nbr_ptr[row];
-        const int rl = 6 * nnb;
-        for (int k = lane; k < 36 * nnb; k += 32) {
-          const int i = k / rl, r = k - i * rl, c = r / 6, j = r - 6 * c;
-          double val = 0.;
-          if (i < 3 && j < 3) val = sm.arena[base + i * rs + 3 * c + j];
-          else if (i == j && c == self_c) val = ((cmn >> i) & 1u) ? double(nadj + nadjd) : ex[4] + 1.0e-24 * nadjd;
-          dst[k] = val;
+          if (!fl.nv6) {
+            double* dst = p.J + 9 * fr.dst_block + 3 * c;
+            const int rs = 3 * nnb;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+          } else {
+            double* dst = p.J + 36 * fr.dst_block + 6 * c;
+            const int rl = 6 * nnb;
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+#pragma unroll
+              for (int j = 0; j < 6; ++j) {
+                double val = 0.;
+                if (i < 3 && j < 3) val = K[i][j];
+                else if (i == j && self) val = ((cmn >> i) & 1u) ? nadj : (AUX ? ex[4] : 0.) + 1.0e-24 * nadjd;
+                dst[i * rl + j] = val;
+              }
+          }
         }
       }
     }
-    if (fl.R && lane < p.nv) p.R[(int64_t)n * p.nv + lane] = (lane < 3 && !((cmn >> lane) & 1u)) ? ex[lane] : 0.;
-    if (fl.G && lane == 0) p.G[n] = ex[3];
+    if (fl.R) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (lane < p.nv) {
+        double v = lane == 0 ? r0 : (lane == 1 ? r1 : r2);
+        if (AUX && lane < 3) v += ex[lane];
+        p.R[(int64_t)n * p.nv + lane] = (lane < 3 && !((cmn >> lane) & 1u)) ? v : 0.;
+      }
+    }
+    if (AUX && fl.G && lane == 0) p.G[n] = ex[3];
   }
 }
 
+template <bool AUX>
 __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int STRIDE = AUX ? STRIDE_AUX : STRIDE_PLAIN;
   Smem sm;
+  const int MS = p.max_slots;
   sm.arena = reinterpret_cast<double*>(smem_raw);
-  sm.xyz = sm.arena + p.arena_doubles;
-  sm.u = sm.xyz + MAXN * 3;
-  sm.adj = sm.u + MAXN * 3;
-  sm.rho = sm.adj + MAXN * 3;
-  sm.T = sm.rho + MAXN;
-  sm.stage = sm.T + MAXN;
-  sm.accoff = reinterpret_cast<int32_t*>(sm.stage + WARPS * STAGE_EL * EL_STRIDE);
-  sm.gid = sm.accoff + MAXN;
-  sm.cnt = sm.gid + MAXN;
-  sm.rec = reinterpret_cast<uint32_t*>(sm.cnt + MAXN);
-  sm.nbrcnt = reinterpret_cast<uint8_t*>(sm.rec + WARPS * 4 * REC_WORDS);
-  sm.cm = sm.nbrcnt + MAXN;
-  int& s_next = *reinterpret_cast<int*>(sm.cm + MAXN);  // chunk dispenser of the current tile
+  sm.xyz = sm.arena + (size_t)p.arena_blocks * 9;
+  sm.u = sm.xyz + MS * 3;
+  double* nxt = sm.u + MS * 3;
+  if (AUX) {
+    sm.adj = nxt; sm.rho = sm.adj + MS * 3; sm.T = sm.rho + MS; sm.extras = sm.T + MS;
+    nxt = sm.extras + MS * EXTRA;
+  } else {
+    sm.adj = sm.rho = sm.T = sm.extras = nullptr;
+  }
+  sm.stage = nxt;
+  sm.fbuf = reinterpret_cast<unsigned char*>(sm.stage + WARPS * STAGE_EL * STRIDE);
+  sm.rec = reinterpret_cast<uint32_t*>(sm.fbuf + p.flush_buf_bytes);
+  sm.gid = reinterpret_cast<int32_t*>(sm.rec + WARPS * 4 * REC_WORDS);
+  sm.cnt = sm.gid + MS;
+  sm.sd = reinterpret_cast<StepDesc*>(sm.cnt + MS);
+  sm.misc = reinterpret_cast<int*>(sm.sd + 2);
+  sm.cm = reinterpret_cast<uint8_t*>(sm.misc + 4);
 
   Flags fl;
   fl.J = p.J != nullptr; fl.R = p.R != nullptr; fl.G = p.G != nullptr;
   fl.simp = p.rho != nullptr; fl.thermal = p.thermal != 0; fl.nv6 = p.nv == 6;
+  fl.S = fl.J || fl.R;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int el = lane >> 3, q = lane & 7;
-  double* my_stage = sm.stage + warp * STAGE_EL * EL_STRIDE;
+  double* my_stage = sm.stage + warp * STAGE_EL * STRIDE;
   uint32_t* my_rec = sm.rec + warp * 4 * REC_WORDS;
+  int& s_next = sm.misc[0];
+  int& s_tile = sm.misc[1];
 
-  for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+  for (;;) {
+    if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
+    __syncthreads();
+    const int tile = s_tile;
+    if (tile >= p.n_tiles) break;
     const TileDesc td = p.tiles[tile];
-    // stage node state of the tile (owned + halo), clear accumulators and counters
-    for (int l = tid; l < td.n_nodes; l += THREADS) {
-      const int n = p.tile_nodes[td.node_begin + l];
-      const unsigned cm = p.cmask ? p.cmask[n] : 0u;
-      sm.gid[l] = n;
-      sm.accoff[l] = p.tile_acc_off[td.node_begin + l];
-      sm.nbrcnt[l] = (uint8_t)p.tile_nbr_cnt[td.node_begin + l];
-      sm.cm[l] = (uint8_t)cm;
-      sm.cnt[l] = 0;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        sm.xyz[l * 3 + c] = p.xyz[(int64_t)n * 3 + c];
-        sm.u[l * 3 + c] = p.X[(int64_t)n * p.nv + c];
-        // constrain_element_vector zeroes constrained rows of dR/dp, i.e. the adjoint never sees them
-        sm.adj[l * 3 + c] = (p.adj && !((cm >> c) & 1u)) ? p.adj[(int64_t)n * p.nv + c] : 0.;
-      }
-      sm.rho[l] = p.rho ? p.rho[n] : 1.;
-      sm.T[l] = p.temperature ? p.temperature[n] : p.T_const;
-    }
-    for (int k = tid; k < td.arena_doubles; k += THREADS) sm.arena[k] = 0.;
+    if (tid < 8) reinterpret_cast<int*>(&sm.sd[0])[tid] = reinterpret_cast<const int*>(p.steps + td.step_begin)[tid];
     if (tid == 0) s_next = 0;
     __syncthreads();
-    const int extras_base = td.arena_doubles - td.n_owned * EXTRA;
-    const int n_chunks = (td.n_visits + 3) >> 2;
-    const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + td.visit_begin);
+    load_states<AUX>(p, sm, sm.sd[0].load_begin, sm.sd[0].n_loads, tid, THREADS);
+    __syncthreads();
 
-    // warps take chunks of 4 consecutive visits in plan order; the records of the next chunk are prefetched into
-    // registers while the current one is processed
-    int c = 0;
-    if (lane == 0) c = atomicAdd(&s_next, 1);
-    c = __shfl_sync(0xffffffffu, c, 0);
-    uint32_t r0 = 0, r1 = 0, r2 = 0;
-    if (c < n_chunks) {
-      const int nw = min(4, td.n_visits - 4 * c) * REC_WORDS;
-      const uint32_t* src = recs + (int64_t)c * 4 * REC_WORDS;
-      if (lane < nw) r0 = src[lane];
-      if (lane + 32 < nw) r1 = src[lane + 32];
-      if (lane + 64 < nw) r2 = src[lane + 64];
-    }
-    while (c < n_chunks) {
-      const int nvis = min(4, td.n_visits - 4 * c);
-      my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
-      __syncwarp();
-      int cn = 0;
-      if (lane == 0) cn = atomicAdd(&s_next, 1);
-      cn = __shfl_sync(0xffffffffu, cn, 0);
-      if (cn < n_chunks) {
-        const int nw = min(4, td.n_visits - 4 * cn) * REC_WORDS;
-        const uint32_t* src = recs + (int64_t)cn * 4 * REC_WORDS;
-        r0 = r1 = r2 = 0;
+    for (int s = 0; s < td.n_steps; ++s) {
+      const StepDesc sd = sm.sd[s & 1];
+      if (warp == 0) {
+        // stage the flush records of this step and the nodal state of the next one
+        if (s + 1 < td.n_steps) {
+          StepDesc* nsd = &sm.sd[(s + 1) & 1];
+          if (lane < 8) reinterpret_cast<int*>(nsd)[lane] = reinterpret_cast<const int*>(p.steps + td.step_begin + s + 1)[lane];
+          __syncwarp();
+          load_states<AUX>(p, sm, nsd->load_begin, nsd->n_loads, lane, 32);
+        }
+        const uint4* src_r = reinterpret_cast<const uint4*>(p.flush_rows + sd.flush_begin);
+        uint4* dst_r = reinterpret_cast<uint4*>(sm.fbuf);
+        for (int k = lane; k < sd.n_flush * 2; k += 32) dst_r[k] = src_r[k];
+        const uint4* src_e = reinterpret_cast<const uint4*>(p.flush_ent + sd.fent_begin);
+        uint4* dst_e = reinterpret_cast<uint4*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
+        for (int k = lane; k < (sd.n_fent + 3) / 4; k += 32) dst_e[k] = src_e[k];
+      }
+      // warps take chunks of 4 consecutive visits in plan order; the records of the next chunk are prefetched into
+      // registers while the current one is processed
+      const int n_chunks = (sd.n_visits + 3) >> 2;
+      const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + sd.visit_begin);
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_next, 1);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      uint32_t r0 = 0, r1 = 0, r2 = 0;
+      if (c < n_chunks) {
+        const int nw = min(4, sd.n_visits - 4 * c) * REC_WORDS;
+        const uint32_t* src = recs + (int64_t)c * 4 * REC_WORDS;
         if (lane < nw) r0 = src[lane];
         if (lane + 32 < nw) r1 = src[lane + 32];
         if (lane + 64 < nw) r2 = src[lane + 64];
       }
-      const bool active = el < nvis;
-      QpData d;
-      if (active) {
-        const uint4 pk = *reinterpret_cast<const uint4*>(my_rec + el * REC_WORDS);
-        int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
-                     int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
-        geometry_phase(p, sm, fl, ln, q, d);
-      }
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      while (c < n_chunks) {
+        const int nvis = min(4, sd.n_visits - 4 * c);
+        my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
         __syncwarp();
-        if (active && (el >> 1) == half) stage_write(my_stage + (el & 1) * EL_STRIDE, q, d);
-        __syncwarp();
-#pragma unroll
-        for (int e2 = 0; e2 < 2; ++e2) {
-          const int ecur = half * 2 + e2;
-          if (ecur < nvis) element_phase(p, sm, fl, my_stage + e2 * EL_STRIDE, my_rec + ecur * REC_WORDS, extras_base, lane);
+        int cn = 0;
+        if (lane == 0) cn = atomicAdd(&s_next, 1);
+        cn = __shfl_sync(0xffffffffu, cn, 0);
+        if (cn < n_chunks) {
+          const int nw = min(4, sd.n_visits - 4 * cn) * REC_WORDS;
+          const uint32_t* src = recs + (int64_t)cn * 4 * REC_WORDS;
+          r0 = r1 = r2 = 0;
+          if (lane < nw) r0 = src[lane];
+          if (lane + 32 < nw) r1 = src[lane + 32];
+          if (lane + 64 < nw) r2 = src[lane + 64];
         }
+        const bool active = el < nvis;
+        QpData<AUX> d;
+        if (active) {
+          const uint4 pk = *reinterpret_cast<const uint4*>(my_rec + el * REC_WORDS);
+          int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
+                       int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
+          geometry_phase<AUX>(p, sm, fl, ln, q, d);
+        }
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          __syncwarp();
+          if (active && (el >> 1) == half) stage_write<AUX>(my_stage + (el & 1) * STRIDE, q, d);
+          __syncwarp();
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int ecur = half * 2 + e2;
+            if (ecur < nvis) element_phase<AUX>(p, sm, fl, my_stage + e2 * STRIDE, my_rec + ecur * REC_WORDS, lane);
+          }
+        }
+        __syncwarp();
+        c = cn;
       }
-      __syncwarp();
-      c = cn;
+      __syncthreads();
+      if (tid == 0) s_next = 0;
+      flush_rows<AUX>(p, sm, fl, sd, warp, lane);
+      __syncthreads();
     }
-    __syncthreads();
-    flush_tile(p, sm, fl, td, extras_base, warp, lane);
-    __syncthreads();
   }
 }
 
 }  // namespace
 
-size_t hex8_sweep_smem_bytes(int arena_doubles) {
-  return size_t(arena_doubles) * 8 + size_t(MAXN) * 11 * 8 + size_t(WARPS) * STAGE_EL * EL_STRIDE * 8 +
-         size_t(MAXN) * (4 + 4 + 4 + 1 + 1) + size_t(WARPS) * 4 * REC_WORDS * 4 + 64;  // +64: chunk dispenser, padding
+size_t hex8_sweep_smem_bytes(int arena_blocks, int max_slots, int flush_buf_bytes, bool aux) {
+  const size_t stride = aux ? STRIDE_AUX : STRIDE_PLAIN;
+  size_t doubles = size_t(arena_blocks) * 9 + size_t(max_slots) * 6 + size_t(WARPS) * STAGE_EL * stride;
+  if (aux) doubles += size_t(max_slots) * (3 + 1 + 1 + EXTRA);
+  size_t bytes = doubles * 8 + size_t(flush_buf_bytes) + size_t(WARPS) * 4 * REC_WORDS * 4 + size_t(max_slots) * 8 +
+                 2 * sizeof(StepDesc) + 16 + size_t(max_slots);
+  return (bytes + 15) & ~size_t(15);
 }
 
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream) {
-  const size_t smem = hex8_sweep_smem_bytes(p.arena_doubles);
-  cudaError_t e = cudaFuncSetAttribute(hex8_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = hex8_sweep_smem_bytes(p.arena_blocks, p.max_slots, p.flush_buf_bytes, p.aux != 0);
+  cudaError_t e = cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  hex8_sweep_kernel<<<n_ctas, THREADS, smem, stream>>>(p);
+  if (p.aux) {
+    e = cudaFuncSetAttribute(hex8_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hex8_sweep_kernel<true><<<n_ctas, THREADS, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(hex8_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    hex8_sweep_kernel<false><<<n_ctas, THREADS, smem, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
