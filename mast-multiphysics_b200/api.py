@@ -44,7 +44,8 @@ class Stats(C.Structure):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmast_b200.so")
+    # MASTB200_LIB: alternative build of the same library (kernel-tuning experiments)
+    return os.environ.get("MASTB200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmast_b200.so")
 
 
 _LIB = None

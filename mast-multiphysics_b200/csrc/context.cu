@@ -180,13 +180,12 @@ int ensure_plan(mastb200_context* ctx, int aux) {
   mastb200_context::DevicePlan& D = ctx->dplan[aux];
   if (D.built) return MASTB200_OK;
   if (ctx->elem_type != MASTB200_HEX8) return MASTB200_OK;  // pattern only: no device sweep for the type yet
-  const size_t fixed = hex8_sweep_smem_bytes(0, kMaxSlots, kFlushBufBytes, aux != 0);
-  if ((size_t)ctx->max_optin <= fixed + 8192) return ctx->fail(MASTB200_ERR_CUDA, "device shared memory too small");
-  D.lim.arena_blocks = (int32_t)std::min<size_t>((ctx->max_optin - fixed) / 72, 4094) & ~1;
+  D.smem = hex8_sweep_smem_bytes(aux != 0);
+  if ((size_t)ctx->max_optin < D.smem) return ctx->fail(MASTB200_ERR_CUDA, "device shared memory too small");
+  D.lim.arena_blocks = hex8_sweep_arena_blocks(aux != 0);
   D.lim.max_slots = kMaxSlots;
   D.lim.flush_buf_bytes = kFlushBufBytes;
   D.lim.sm_count = ctx->sm_count;
-  D.smem = hex8_sweep_smem_bytes(D.lim.arena_blocks, kMaxSlots, kFlushBufBytes, aux != 0);
   StreamPlan P;
   const std::string e = build_stream_plan(ctx->pat, ctx->xyz.data(), ctx->conn.data(),
                                           ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), D.lim, P);
@@ -230,9 +229,6 @@ void fill_params(mastb200_context* ctx, int aux, SweepParams& p) {
   p.thermal = ctx->thermal ? 1 : 0;
   p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
   p.temperature = (ctx->thermal && ctx->T_nodal) ? (ctx->T_ext ? ctx->T_ext : ctx->d_T.p) : nullptr;
-  p.arena_blocks = D.lim.arena_blocks;
-  p.max_slots = D.lim.max_slots;
-  p.flush_buf_bytes = D.lim.flush_buf_bytes;
   p.aux = aux;
 }
 

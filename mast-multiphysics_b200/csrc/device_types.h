@@ -34,11 +34,7 @@ struct SweepParams {
   double T_const, T_ref;
   int32_t nv;
   int32_t thermal;            // TEMPERATURE volume load active
-  // ---- shared-memory layout (set by the launcher) ----
-  int32_t arena_blocks;
-  int32_t max_slots;
-  int32_t flush_buf_bytes;
-  int32_t aux;                // 1: adjoint / density / temperature state and per-node extras are staged
+  int32_t aux;                // 1: adjoint / density / temperature state and per-node extras are staged (kernel variant)
 };
 
 }  // namespace mastb200

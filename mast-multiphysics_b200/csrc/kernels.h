@@ -13,7 +13,8 @@ constexpr int kMaxSlots = 448;         // node state slots staged in shared memo
 constexpr int kFlushBufBytes = 10240;  // flush records of one step staged in shared memory
 
 // HEX8 linear-elastic sweep (sweep_hex8.cu).  aux: adjoint / density / temperature state and per-node extras staged
-size_t hex8_sweep_smem_bytes(int arena_blocks, int max_slots, int flush_buf_bytes, bool aux);
+size_t hex8_sweep_smem_bytes(bool aux);
+int hex8_sweep_arena_blocks(bool aux);  // pair blocks of the shared-memory arena (compile-time layout)
 int hex8_sweep_threads();
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream);
 

@@ -33,7 +33,10 @@ namespace mastb200 {
 
 namespace {
 
-constexpr int WARPS = 12;
+#ifndef MASTB200_WARPS
+#define MASTB200_WARPS 12
+#endif
+constexpr int WARPS = MASTB200_WARPS;  // 12 warps x 168 registers fill the register file of one SM
 constexpr int THREADS = WARPS * 32;
 constexpr int STAGE_EL = 2;          // elements staged per warp at a time
 constexpr int V_HALF = 36;           // stride of one (component, qp-half) 8x4 operand panel (32 + 4 pad)
@@ -54,6 +57,35 @@ __device__ __forceinline__ constexpr int sgx(int b) { return (b == 1 || b == 2 |
 __device__ __forceinline__ constexpr int sgy(int b) { return (b == 2 || b == 3 || b == 6 || b == 7) ? 1 : -1; }
 __device__ __forceinline__ constexpr int sgz(int b) { return (b >= 4) ? 1 : -1; }
 
+// Shared-memory layout: every offset is a compile-time constant, so all staged data is addressed as base + immediate.
+template <bool AUX>
+struct Lay {
+  static constexpr int MS = kMaxSlots;
+  static constexpr int STRIDE = AUX ? STRIDE_AUX : STRIDE_PLAIN;
+  static constexpr int SMEM_TOTAL = 232448;  // sm_100: 227 KB opt-in per CTA
+  static constexpr int FIXED = MS * 48 + (AUX ? MS * (24 + 8 + 8 + 8 * EXTRA) : 0) + WARPS * STAGE_EL * STRIDE * 8 +
+                               kFlushBufBytes + WARPS * 4 * REC_WORDS * 4 + MS * 8 + 2 * 32 + 16 + MS;
+  static constexpr int ARENA_RAW = ((SMEM_TOTAL - FIXED) / 72) & ~1;
+  static constexpr int ARENA_BLOCKS = ARENA_RAW > 4094 ? 4094 : ARENA_RAW;
+  static constexpr int O_XYZ = ARENA_BLOCKS * 72;
+  static constexpr int O_U = O_XYZ + MS * 24;
+  static constexpr int O_ADJ = O_U + MS * 24;
+  static constexpr int O_RHO = O_ADJ + MS * 24;
+  static constexpr int O_T = O_RHO + MS * 8;
+  static constexpr int O_EX = O_T + MS * 8;
+  static constexpr int O_STAGE = AUX ? O_EX + MS * 8 * EXTRA : O_ADJ;
+  static constexpr int O_FBUF = O_STAGE + WARPS * STAGE_EL * STRIDE * 8;
+  static constexpr int O_REC = O_FBUF + kFlushBufBytes;
+  static constexpr int O_GID = O_REC + WARPS * 4 * REC_WORDS * 4;
+  static constexpr int O_CNT = O_GID + MS * 4;
+  static constexpr int O_SD = O_CNT + MS * 4;
+  static constexpr int O_MISC = O_SD + 2 * 32;
+  static constexpr int O_CM = O_MISC + 16;
+  static constexpr int TOTAL = (O_CM + MS + 15) & ~15;
+  static_assert(TOTAL <= SMEM_TOTAL, "shared-memory layout exceeds 227 KB");
+  static_assert(O_FBUF % 16 == 0 && O_REC % 16 == 0 && O_STAGE % 16 == 0, "16-byte alignment of vector-accessed regions");
+};
+
 struct Smem {
   double* arena;   // pair blocks
   double* xyz;
@@ -71,6 +103,28 @@ struct Smem {
   StepDesc* sd;    // [2]
   int* misc;       // [0] chunk dispenser, [1] current tile
 };
+
+template <bool AUX>
+__device__ __forceinline__ Smem make_smem(unsigned char* base) {
+  using L = Lay<AUX>;
+  Smem sm;
+  sm.arena = reinterpret_cast<double*>(base);
+  sm.xyz = reinterpret_cast<double*>(base + L::O_XYZ);
+  sm.u = reinterpret_cast<double*>(base + L::O_U);
+  sm.adj = reinterpret_cast<double*>(base + L::O_ADJ);
+  sm.rho = reinterpret_cast<double*>(base + L::O_RHO);
+  sm.T = reinterpret_cast<double*>(base + L::O_T);
+  sm.extras = reinterpret_cast<double*>(base + L::O_EX);
+  sm.stage = reinterpret_cast<double*>(base + L::O_STAGE);
+  sm.fbuf = base + L::O_FBUF;
+  sm.rec = reinterpret_cast<uint32_t*>(base + L::O_REC);
+  sm.gid = reinterpret_cast<int32_t*>(base + L::O_GID);
+  sm.cnt = reinterpret_cast<int32_t*>(base + L::O_CNT);
+  sm.sd = reinterpret_cast<StepDesc*>(base + L::O_SD);
+  sm.misc = reinterpret_cast<int*>(base + L::O_MISC);
+  sm.cm = base + L::O_CM;
+  return sm;
+}
 
 __device__ __forceinline__ int ld_volatile_s32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
 __device__ __forceinline__ void st_volatile_s32(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
@@ -200,9 +254,29 @@ __device__ __forceinline__ void stage_write(double* st, int q, const QpData<AUX>
 // ---- matrix phase: all 32 lanes on one element; lane = (row node a, qp q4 | q4+4) ------------------------------
 // rec: the visit record in shared memory.  All arithmetic (DMMA, lane reductions) happens first; the adds into the
 // pair blocks wait until the per-node counters say that every earlier visit of the plan order has landed.
+struct LaneConst {     // matrix-phase constants of lane (a = lane/4, q4 = lane%4), columns b = 2*q4 + bb
+  int pidx[2];         // index of pair {a,b} in VisitRec8::pair
+  unsigned swap[2];    // a > b: the lane holds the transposed orientation of the pair's (lo,hi) order
+  bool le[2];          // a <= b: the lane owns the symmetric components (i,i) of the pair
+};
+
+__device__ __forceinline__ LaneConst make_lane_const(int lane) {
+  LaneConst lc;
+  const int a = lane >> 2, q4 = lane & 3;
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int b = 2 * q4 + bb;
+    const int lo = min(a, b), hi = max(a, b);
+    lc.pidx[bb] = lo * (15 - lo) / 2 + hi;
+    lc.swap[bb] = a > b ? 1u : 0u;
+    lc.le[bb] = a <= b;
+  }
+  return lc;
+}
+
 template <bool AUX>
-__device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const double* st,
-                                              const uint32_t* rec, int lane) {
+__device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const LaneConst& lc,
+                                              const double* st, const uint32_t* rec, int lane) {
   const int a = lane >> 2, q4 = lane & 3;
   const uint16_t* rec16 = reinterpret_cast<const uint16_t*>(rec);
   const uint8_t* rec8 = reinterpret_cast<const uint8_t*>(rec);
@@ -273,28 +347,31 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
 
   // ---- ordered accumulation ----
   if (own && q4 == 0)
-    while (ld_volatile_s32(sm.cnt + la) != rank) {}
+    while (ld_volatile_s32(sm.cnt + la) != rank) __nanosleep(20);
   __threadfence_block();
   __syncwarp();
   if (fl.S) {
+    // both pair entries of the lane: columns b = 2*q4 and 2*q4+1 of row a
+    const unsigned e2[2] = {rec16[12 + lc.pidx[0]], rec16[12 + lc.pidx[1]]};
 #pragma unroll
     for (int bb = 0; bb < 2; ++bb) {
-      const int b = 2 * q4 + bb;
-      const int lo = min(a, b), hi = max(a, b);
-      const unsigned e = rec16[12 + lo * (15 - lo) / 2 + hi];
+      const unsigned e = e2[bb];
       if (e != kPairNone) {
         double* blk = sm.arena + (e & kPairSlotMask) * 9;
-        const bool tr = (((e & kPairTransposed) != 0) != (a > b));  // stored block is S_(hi,lo)-oriented relative to (a,b)
-        const bool init = (e & kPairInit) != 0;
-        // off-diagonal components (i<j): S_ab[i][j] = C_ij[a][b] goes to [i][j], or to [j][i] of the transposed block
-        const int o01 = tr ? 3 : 1, o02 = tr ? 6 : 2, o12 = tr ? 7 : 5;
-        if (init) {
-          blk[o01] = C[3][bb]; blk[o02] = C[4][bb]; blk[o12] = C[5][bb];
-          if (a <= b) { blk[0] = C[0][bb]; blk[4] = C[1][bb]; blk[8] = C[2][bb]; }
-        } else {
-          blk[o01] += C[3][bb]; blk[o02] += C[4][bb]; blk[o12] += C[5][bb];
-          if (a <= b) { blk[0] += C[0][bb]; blk[4] += C[1][bb]; blk[8] += C[2][bb]; }
+        // stored block oriented as S_(a,b) (tr = 0) or S_(b,a) (tr = 1): off-diagonal components (i<j) of C_ij[a][b]
+        // go to [i][j] = {1, 2, 5} or to [j][i] = {3, 6, 7}
+        const unsigned tr = ((e >> 12) & 1u) ^ lc.swap[bb];
+        double* p1 = blk + 2 * tr;  // [1]|[3] and [5]|[7]
+        double* p2 = blk + 4 * tr;  // [2]|[6]
+        const bool add = (e & kPairInit) == 0;
+        const bool dg = lc.le[bb];
+        double v01 = 0., v02 = 0., v12 = 0., v00 = 0., v11 = 0., v22 = 0.;
+        if (add) {
+          v01 = p1[1]; v02 = p2[2]; v12 = p1[5];
+          if (dg) { v00 = blk[0]; v11 = blk[4]; v22 = blk[8]; }
         }
+        p1[1] = v01 + C[3][bb]; p2[2] = v02 + C[4][bb]; p1[5] = v12 + C[5][bb];
+        if (dg) { blk[0] = v00 + C[0][bb]; blk[4] = v11 + C[1][bb]; blk[8] = v22 + C[2][bb]; }
       }
     }
   }
@@ -403,18 +480,20 @@ __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm,
           }
         }
         if (fl.J) {
+          if (cmn | cmm | (unsigned)fr.nadjd) {  // Dirichlet rows/columns and diagonal_elem_subdomain_id terms (rare)
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              double k = K[i][j];
-              if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
-              if (self && i == j) {
-                if ((cmn >> i) & 1u) k = nadj;       // each adjacent element sets the diagonal to 1
-                else k += 1.0e-24 * nadjd;           // diagonal_elem_subdomain_id elements
+              for (int j = 0; j < 3; ++j) {
+                double k = K[i][j];
+                if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
+                if (self && i == j) {
+                  if ((cmn >> i) & 1u) k = nadj;       // each adjacent element sets the diagonal to 1
+                  else k += 1.0e-24 * nadjd;           // diagonal_elem_subdomain_id elements
+                }
+                K[i][j] = k;
               }
-              K[i][j] = k;
-            }
+          }
           if (!fl.nv6) {
             double* dst = p.J + 9 * fr.dst_block + 3 * c;
             const int rs = 3 * nnb;
@@ -439,16 +518,22 @@ __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm,
       }
     }
     if (fl.R) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
-        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
-        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
-      }
-      if (lane < p.nv) {
-        double v = lane == 0 ? r0 : (lane == 1 ? r1 : r2);
-        if (AUX && lane < 3) v += ex[lane];
-        p.R[(int64_t)n * p.nv + lane] = (lane < 3 && !((cmn >> lane) & 1u)) ? v : 0.;
+      // deterministic butterfly over the 32 lanes for the three sums at once: lanes 0, 8 and 16 end with r0, r1, r2
+      const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
+      const double g0 = __shfl_xor_sync(0xffffffffu, hi16 ? r0 : r2, 16);
+      const double g1 = __shfl_xor_sync(0xffffffffu, hi16 ? r1 : 0., 16);
+      const double x0 = (hi16 ? r2 : r0) + g0, x1 = (hi16 ? 0. : r1) + g1;
+      double y = (hi8 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, hi8 ? x0 : x1, 8);
+      y += __shfl_xor_sync(0xffffffffu, y, 4);
+      y += __shfl_xor_sync(0xffffffffu, y, 2);
+      y += __shfl_xor_sync(0xffffffffu, y, 1);
+      if ((lane & 7) == 0 && lane < 24) {
+        const int i = lane >> 3;
+        double v = y;
+        if (AUX) v += ex[i];
+        p.R[(int64_t)n * p.nv + i] = ((cmn >> i) & 1u) ? 0. : v;
+      } else if (fl.nv6 && lane >= 25 && lane < 28) {
+        p.R[(int64_t)n * p.nv + (lane - 22)] = 0.;  // rotational dofs of the 6-variable system carry no residual
       }
     }
     if (AUX && fl.G && lane == 0) p.G[n] = ex[3];
@@ -458,27 +543,8 @@ __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm,
 template <bool AUX>
 __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int STRIDE = AUX ? STRIDE_AUX : STRIDE_PLAIN;
-  Smem sm;
-  const int MS = p.max_slots;
-  sm.arena = reinterpret_cast<double*>(smem_raw);
-  sm.xyz = sm.arena + (size_t)p.arena_blocks * 9;
-  sm.u = sm.xyz + MS * 3;
-  double* nxt = sm.u + MS * 3;
-  if (AUX) {
-    sm.adj = nxt; sm.rho = sm.adj + MS * 3; sm.T = sm.rho + MS; sm.extras = sm.T + MS;
-    nxt = sm.extras + MS * EXTRA;
-  } else {
-    sm.adj = sm.rho = sm.T = sm.extras = nullptr;
-  }
-  sm.stage = nxt;
-  sm.fbuf = reinterpret_cast<unsigned char*>(sm.stage + WARPS * STAGE_EL * STRIDE);
-  sm.rec = reinterpret_cast<uint32_t*>(sm.fbuf + p.flush_buf_bytes);
-  sm.gid = reinterpret_cast<int32_t*>(sm.rec + WARPS * 4 * REC_WORDS);
-  sm.cnt = sm.gid + MS;
-  sm.sd = reinterpret_cast<StepDesc*>(sm.cnt + MS);
-  sm.misc = reinterpret_cast<int*>(sm.sd + 2);
-  sm.cm = reinterpret_cast<uint8_t*>(sm.misc + 4);
+  constexpr int STRIDE = Lay<AUX>::STRIDE;
+  const Smem sm = make_smem<AUX>(smem_raw);
 
   Flags fl;
   fl.J = p.J != nullptr; fl.R = p.R != nullptr; fl.G = p.G != nullptr;
@@ -487,6 +553,7 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int el = lane >> 3, q = lane & 7;
+  const LaneConst lc = make_lane_const(lane);
   double* my_stage = sm.stage + warp * STAGE_EL * STRIDE;
   uint32_t* my_rec = sm.rec + warp * 4 * REC_WORDS;
   int& s_next = sm.misc[0];
@@ -521,31 +588,43 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
         uint4* dst_e = reinterpret_cast<uint4*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
         for (int k = lane; k < (sd.n_fent + 3) / 4; k += 32) dst_e[k] = src_e[k];
       }
-      // warps take chunks of 4 consecutive visits in plan order; the records of the next chunk are prefetched into
-      // registers while the current one is processed
-      const int n_chunks = (sd.n_visits + 3) >> 2;
+      // warps take chunks of consecutive visits in plan order: 4 visits while more than a round of work is left, then
+      // the remainder split evenly over the warps so that the step ends without a tail; the records of the next chunk
+      // are prefetched into registers while the current one is processed
+      const int full = sd.n_visits / (4 * WARPS) * WARPS;          // chunks of 4
+      const int rem = sd.n_visits - 4 * full;
+      const int base = rem / WARPS, extra = rem - base * WARPS;     // last round: `extra` chunks of base+1, then base
+      const int n_chunks = full + (base ? WARPS : extra);
       const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + sd.visit_begin);
+      auto chunk_range = [&](int c, int& begin, int& size) {
+        if (c < full) { begin = 4 * c; size = 4; }
+        else { const int j = c - full; begin = 4 * full + j * base + min(j, extra); size = base + (j < extra ? 1 : 0); }
+      };
       int c = 0;
       if (lane == 0) c = atomicAdd(&s_next, 1);
       c = __shfl_sync(0xffffffffu, c, 0);
       uint32_t r0 = 0, r1 = 0, r2 = 0;
+      int nvis = 0, nvis_next = 0;
       if (c < n_chunks) {
-        const int nw = min(4, sd.n_visits - 4 * c) * REC_WORDS;
-        const uint32_t* src = recs + (int64_t)c * 4 * REC_WORDS;
+        int b0;
+        chunk_range(c, b0, nvis);
+        const int nw = nvis * REC_WORDS;
+        const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
         if (lane < nw) r0 = src[lane];
         if (lane + 32 < nw) r1 = src[lane + 32];
         if (lane + 64 < nw) r2 = src[lane + 64];
       }
       while (c < n_chunks) {
-        const int nvis = min(4, sd.n_visits - 4 * c);
         my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
         __syncwarp();
         int cn = 0;
         if (lane == 0) cn = atomicAdd(&s_next, 1);
         cn = __shfl_sync(0xffffffffu, cn, 0);
         if (cn < n_chunks) {
-          const int nw = min(4, sd.n_visits - 4 * cn) * REC_WORDS;
-          const uint32_t* src = recs + (int64_t)cn * 4 * REC_WORDS;
+          int b0;
+          chunk_range(cn, b0, nvis_next);
+          const int nw = nvis_next * REC_WORDS;
+          const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
           r0 = r1 = r2 = 0;
           if (lane < nw) r0 = src[lane];
           if (lane + 32 < nw) r1 = src[lane + 32];
@@ -567,11 +646,11 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
 #pragma unroll
           for (int e2 = 0; e2 < 2; ++e2) {
             const int ecur = half * 2 + e2;
-            if (ecur < nvis) element_phase<AUX>(p, sm, fl, my_stage + e2 * STRIDE, my_rec + ecur * REC_WORDS, lane);
+            if (ecur < nvis) element_phase<AUX>(p, sm, fl, lc, my_stage + e2 * STRIDE, my_rec + ecur * REC_WORDS, lane);
           }
         }
         __syncwarp();
-        c = cn;
+        c = cn; nvis = nvis_next;
       }
       __syncthreads();
       if (tid == 0) s_next = 0;
@@ -583,17 +662,11 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
 
 }  // namespace
 
-size_t hex8_sweep_smem_bytes(int arena_blocks, int max_slots, int flush_buf_bytes, bool aux) {
-  const size_t stride = aux ? STRIDE_AUX : STRIDE_PLAIN;
-  size_t doubles = size_t(arena_blocks) * 9 + size_t(max_slots) * 6 + size_t(WARPS) * STAGE_EL * stride;
-  if (aux) doubles += size_t(max_slots) * (3 + 1 + 1 + EXTRA);
-  size_t bytes = doubles * 8 + size_t(flush_buf_bytes) + size_t(WARPS) * 4 * REC_WORDS * 4 + size_t(max_slots) * 8 +
-                 2 * sizeof(StepDesc) + 16 + size_t(max_slots);
-  return (bytes + 15) & ~size_t(15);
-}
+size_t hex8_sweep_smem_bytes(bool aux) { return aux ? Lay<true>::TOTAL : Lay<false>::TOTAL; }
+int hex8_sweep_arena_blocks(bool aux) { return aux ? Lay<true>::ARENA_BLOCKS : Lay<false>::ARENA_BLOCKS; }
 
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream) {
-  const size_t smem = hex8_sweep_smem_bytes(p.arena_blocks, p.max_slots, p.flush_buf_bytes, p.aux != 0);
+  const size_t smem = hex8_sweep_smem_bytes(p.aux != 0);
   cudaError_t e = cudaMemsetAsync(p.tile_counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
   if (p.aux) {
