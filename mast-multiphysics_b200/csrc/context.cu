@@ -185,14 +185,14 @@ int ensure_plan(mastb200_context* ctx, int aux) {
   D.lim.arena_blocks = hex8_sweep_arena_blocks(aux != 0);
   D.lim.max_slots = kMaxSlots;
   D.lim.flush_buf_bytes = kFlushBufBytes;
-  D.lim.sm_count = ctx->sm_count;
+  D.lim.sm_count = ctx->sm_count * kCtasPerSm;
   StreamPlan P;
   const std::string e = build_stream_plan(ctx->pat, ctx->xyz.data(), ctx->conn.data(),
                                           ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), D.lim, P);
   if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
   D.n_tiles = (int64_t)P.tiles.size(); D.n_visits = P.n_visits(); D.bytes = P.bytes();
   D.max_live_blocks = P.max_live_blocks; D.max_live_slots = P.max_live_slots;
-  D.n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(D.n_tiles, ctx->sm_count));
+  D.n_ctas = (int)std::max<int64_t>(1, std::min<int64_t>(D.n_tiles, (int64_t)ctx->sm_count * kCtasPerSm));
   if (ctx->planning_only) {
     D.host = std::move(P);
   } else {

@@ -9,8 +9,12 @@
 
 namespace mastb200 {
 
-constexpr int kMaxSlots = 448;         // node state slots staged in shared memory per strip (about four fronts)
-constexpr int kFlushBufBytes = 10240;  // flush records of one step staged in shared memory
+#ifndef MASTB200_CTAS
+#define MASTB200_CTAS 1                // resident CTAs per SM of the sweep kernel (tuning knob; shared memory is split)
+#endif
+constexpr int kCtasPerSm = MASTB200_CTAS;
+constexpr int kMaxSlots = kCtasPerSm == 1 ? 448 : 288;           // node state slots staged in shared memory per strip
+constexpr int kFlushBufBytes = kCtasPerSm == 1 ? 10240 : 6144;   // flush records of one step staged in shared memory
 
 // HEX8 linear-elastic sweep (sweep_hex8.cu).  aux: adjoint / density / temperature state and per-node extras staged
 size_t hex8_sweep_smem_bytes(bool aux);

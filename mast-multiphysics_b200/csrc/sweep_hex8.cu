@@ -62,7 +62,7 @@ template <bool AUX>
 struct Lay {
   static constexpr int MS = kMaxSlots;
   static constexpr int STRIDE = AUX ? STRIDE_AUX : STRIDE_PLAIN;
-  static constexpr int SMEM_TOTAL = 232448;  // sm_100: 227 KB opt-in per CTA
+  static constexpr int SMEM_TOTAL = kCtasPerSm == 1 ? 232448 : 233472 / kCtasPerSm - 1024;  // sm_100: 227 KB opt-in per CTA, 228 KB per SM
   static constexpr int FIXED = MS * 48 + (AUX ? MS * (24 + 8 + 8 + 8 * EXTRA) : 0) + WARPS * STAGE_EL * STRIDE * 8 +
                                kFlushBufBytes + WARPS * 4 * REC_WORDS * 4 + MS * 8 + 2 * 32 + 16 + MS;
   static constexpr int ARENA_RAW = ((SMEM_TOTAL - FIXED) / 72) & ~1;
@@ -126,8 +126,16 @@ __device__ __forceinline__ Smem make_smem(unsigned char* base) {
   return sm;
 }
 
-__device__ __forceinline__ int ld_volatile_s32(const int32_t* p) { return *reinterpret_cast<const volatile int32_t*>(p); }
-__device__ __forceinline__ void st_volatile_s32(int32_t* p, int v) { *reinterpret_cast<volatile int32_t*>(p) = v; }
+// per-node accumulation counters in shared memory: acquire load / release store at CTA scope order the pair-block
+// updates of successive visits without full fences
+__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s32(int32_t* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
 
 struct Flags {
   bool J, R, G, simp, thermal, nv6, S;  // S: pair blocks are accumulated (J or R requested)
@@ -170,7 +178,7 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
   const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
   const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
   const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
-  const double idet = 1. / det;
+  const double idet = __drcp_rn(det);
   double inv[3][3];
   inv[0][0] = c00 * idet; inv[1][0] = c01 * idet; inv[2][0] = c02 * idet;
   inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
@@ -347,8 +355,7 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
 
   // ---- ordered accumulation ----
   if (own && q4 == 0)
-    while (ld_volatile_s32(sm.cnt + la) != rank) __nanosleep(20);
-  __threadfence_block();
+    while (ld_acquire_s32(sm.cnt + la) != rank) __nanosleep(20);
   __syncwarp();
   if (fl.S) {
     // both pair entries of the lane: columns b = 2*q4 and 2*q4+1 of row a
@@ -381,9 +388,8 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
     if (fl.G) ex[3] += tg;
     if (fl.S && fl.nv6) ex[4] += 1.0e-20 * mx;
   }
-  __threadfence_block();
   __syncwarp();
-  if (own && q4 == 0) st_volatile_s32(sm.cnt + la, rank + 1);
+  if (own && q4 == 0) st_release_s32(sm.cnt + la, rank + 1);
 }
 
 // ---- staging of nodal state (loads of one step) by `nthr` threads, this thread being number `t` ---------------
@@ -541,7 +547,7 @@ __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm,
 }
 
 template <bool AUX>
-__global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(THREADS, kCtasPerSm) hex8_sweep_kernel(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int STRIDE = Lay<AUX>::STRIDE;
   const Smem sm = make_smem<AUX>(smem_raw);
