@@ -296,7 +296,7 @@ struct Builder {
     T.visits.resize(nvis);
     T.steps.assign(S, StepDesc{0, 0, 0, 0, 0, 0, 0, 0});
     {
-      std::vector<std::vector<int32_t>> release(S + 2);
+      std::vector<std::vector<int32_t>> release(S + 3);
       std::vector<int32_t> free_blocks;
       int32_t next_new = 0, live = 0;
       std::vector<uint32_t> rank(n_owned, 0u);
@@ -342,7 +342,7 @@ struct Builder {
               T.max_blocks = std::max(T.max_blocks, live);
               int32_t end = flush_step[ll[p]];
               if (ll[q] < n_owned) end = std::max(end, flush_step[ll[q]]);
-              release[end + 1].push_back(bs);
+              release[end + 2].push_back(bs);  // the flush of step `end` runs while step end+1 is being visited
               e |= kPairInit;
             }
             out = (uint16_t)(e | (uint16_t)blk_slot[blk]);
@@ -489,12 +489,13 @@ std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32
   if (B.cu > B.cv) std::swap(B.cu, B.cv);
 
   // cross-section target: the largest mu x mv node columns whose live pair blocks fit the arena.  On a hexahedral grid
-  // a strip holds two fronts of in-plane pairs and two layers of cross-plane pairs at a time.
+  // a strip holds three fronts of in-plane pairs and three layers of cross-plane pairs at a time: two being
+  // accumulated / waiting for their rows, one being flushed behind the visits.
   int mu = 1, mv = 1;
   {
     auto blocks = [](int a, int b) {
       const int both = (3 * a - 2) * (3 * b - 2), halo = 9 * a * b - both;
-      return 2 * ((both + a * b) / 2 + halo) + 2 * (9 * a * b + halo);
+      return 3 * ((both + a * b) / 2 + halo) + 3 * (9 * a * b + halo);
     };
     const double cap = 1.03 * lim.arena_blocks;
     for (int a = 1; a <= 24; ++a)

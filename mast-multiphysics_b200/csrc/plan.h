@@ -3,8 +3,13 @@
 // The device sweep is a row-owner gather.  The owned nodes are cut into strips: a small
 // cross-section of node columns swept along the mesh's longest axis, one "front" (node plane) per step.
 // A CTA walks a strip step by step; per step it visits every element whose last owned front is that step,
-// accumulates the element's contributions in shared memory and, after the step, writes out every CSR row that
-// has just become complete -- each CSR value goes to HBM exactly once and K_e is never stored.
+// accumulates the element's contributions in shared memory and, one step behind the visits, writes out every CSR
+// row that has become complete -- each CSR value goes to HBM exactly once and K_e is never stored.
+//
+// Device timeline the lifetimes below are planned for (sweep_hex8.cu): the flush of step s runs concurrently with
+// the visits of step s+1; the visits of step s+2 start only after it has finished.  Hence a pair block whose last
+// reader is the flush of step t may be re-initialised by visits of step >= t+2, and a state slot last read in
+// step t (visit or flush) may be reloaded for a node first visited in step >= t+2.
 //
 // Shared-memory accumulators are kept per unordered node pair {A,B} ("pair block", 9 doubles of
 // S_AB = sum_q w_q grad N_A (x) grad N_B; S_BA = S_AB^T, so one block serves rows A and B).  A pair block lives

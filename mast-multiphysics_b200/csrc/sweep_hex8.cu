@@ -6,24 +6,25 @@
 // ::thermal_residual (:950-1089) and the sensitivity sweep of SURVEY 8a row S
 // (sensitivity_assemble, nonlinear_implicit_assembly.cpp:515-686, for all nodal-density DVs at once).
 //
-// One persistent CTA per SM walks strips of the mesh (plan.h) front by front.  Per step:
-//   visits   : warps take chunks of 4 element visits in plan order.
-//     geometry phase : one lane per (element, quadrature point) builds J, det, the physical gradients g_b of the
-//                      8 shape functions and the weight w = JxW*E(rho_q); gradients are staged in shared memory.
-//     matrix phase   : S_ij[a][b] = sum_q w_q g_a[i] g_b[j] is a 24x24x8 product.  Only the six component pairs
-//                      i<=j are formed (S_ji[a][b] = S_ij[b][a]) with 12 mma.sync.m8n8k4.f64 (DMMA); lane (a, q)
-//                      holds exactly the (a, q) operand entry, so the A and B fragments are the same registers
-//                      (B = w*A).
+// One persistent CTA per SM walks strips of the mesh (plan.h) front by front.  The CTA is warp-specialised:
+//   12 compute warps take chunks of 4 element visits in plan order.
+//     geometry phase : one lane per (element, quadrature point) builds J, its inverse and the weight
+//                      w = JxW*E(rho_q) and stages them (10 doubles) in shared memory.
+//     matrix phase   : all 32 lanes on one element, lane = (node a, quadrature points q4 and q4+4).  The lane forms
+//                      its own operand entries g_a = J^-T dN_a (the reference gradients are lane constants);
+//                      S_ij[a][b] = sum_q w_q g_a[i] g_b[j] is a 24x24x8 product of which only the six component
+//                      pairs i<=j are formed (S_ji[a][b] = S_ij[b][a]) with 12 mma.sync.m8n8k4.f64 (DMMA); the A and
+//                      B fragments are the same registers (B = w*A).
 //     accumulate     : the 3x3 block S_ab of every node pair {a,b} with an owned end is added to the pair's
 //                      shared-memory block (one block per unordered pair; S_ba = S_ab^T).  Per-node counters
-//                      enforce the plan's visit order, so there are no atomics and the summation order into every
-//                      CSR entry is fixed.
-//   flush    : every node whose last element has been visited gets its rows written: K_ab = lam*S + mu*S^T +
-//              mu*tr(S)*I (isotropic D, src/property_cards/isotropic_material_property_card.cpp:512-528, modulus
-//              folded into w), the per-element Dirichlet semantics of libMesh's constrain_element_matrix_and_vector
-//              (row/column zeroed, diagonal = number of adjacent elements, rhs zeroed), the internal force
-//              f_a = sum_b K_ab u_b (linear strain) and one store of every CSR value to HBM.  K_e is never stored.
-//   Warp 0 stages the nodal state of the next step and the flush records of the current one while the others compute.
+//                      (acquire/release) enforce the plan's visit order: no atomics, fixed summation order.
+//   4 flush warps run one step behind: every node whose last element has been visited gets its rows written:
+//              K_ab = lam*S + mu*S^T + mu*tr(S)*I (isotropic D, src/property_cards/isotropic_material_property_card.cpp:
+//              512-528, modulus folded into w), the per-element Dirichlet semantics of libMesh's
+//              constrain_element_matrix_and_vector (row/column zeroed, diagonal = number of adjacent elements, rhs
+//              zeroed), the internal force f_a = sum_b K_ab u_b (linear strain) and one store of every CSR value to
+//              HBM.  K_e is never stored.  They also stage the nodal state two steps ahead.
+//   The two groups meet only at named barriers (visits of step s done -> flush s; flush s done -> visits s+2).
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -33,18 +34,23 @@ namespace mastb200 {
 
 namespace {
 
-#ifndef MASTB200_WARPS
-#define MASTB200_WARPS 12
-#endif
-constexpr int WARPS = MASTB200_WARPS;  // 12 warps x 168 registers fill the register file of one SM
+constexpr int NC = 12;               // compute warps
+constexpr int NF = 4;                // flush / staging warps
+constexpr int WARPS = NC + NF;
 constexpr int THREADS = WARPS * 32;
-constexpr int STAGE_EL = 2;          // elements staged per warp at a time
-constexpr int V_HALF = 36;           // stride of one (component, qp-half) 8x4 operand panel (32 + 4 pad)
-constexpr int OFF_W = 216, OFF_PTH = 224, OFF_S = 232;
-constexpr int STRIDE_PLAIN = 232;    // V 216 | w 8 | pad      (== 8 mod 16: the two staged elements hit disjoint banks)
-constexpr int STRIDE_AUX = 248;      // V 216 | w 8 | pth 8 | s 8 | pad
+constexpr int QS_PLAIN = 10;         // doubles staged per (element, qp): inv[3][3], w
+constexpr int QS_AUX = 14;           // + pth, s, pad (stride of 28 words keeps the 128-bit stores conflict-free)
 constexpr int EXTRA = 5;             // per slot (aux layout): thermal f[3], G, rot-diag
 constexpr int REC_WORDS = 24;        // sizeof(VisitRec8) / 4
+constexpr double GP = 0.57735026918962576451;
+
+// named barriers (0 is __syncthreads)
+constexpr int BAR_VISITS = 1;        // +parity: visits of step s done          (compute arrive, flush sync)
+constexpr int BAR_FLUSH = 3;         // +parity: flush of step s done, state of step s+2 staged (flush arrive, compute sync)
+constexpr int BAR_FGROUP = 5;        // flush warps among themselves
+
+__device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -61,10 +67,11 @@ __device__ __forceinline__ constexpr int sgz(int b) { return (b >= 4) ? 1 : -1; 
 template <bool AUX>
 struct Lay {
   static constexpr int MS = kMaxSlots;
-  static constexpr int STRIDE = AUX ? STRIDE_AUX : STRIDE_PLAIN;
-  static constexpr int SMEM_TOTAL = kCtasPerSm == 1 ? 232448 : 233472 / kCtasPerSm - 1024;  // sm_100: 227 KB opt-in per CTA, 228 KB per SM
-  static constexpr int FIXED = MS * 48 + (AUX ? MS * (24 + 8 + 8 + 8 * EXTRA) : 0) + WARPS * STAGE_EL * STRIDE * 8 +
-                               kFlushBufBytes + WARPS * 4 * REC_WORDS * 4 + MS * 8 + 2 * 32 + 16 + MS;
+  static constexpr int QS = AUX ? QS_AUX : QS_PLAIN;
+  static constexpr int STAGE_WARP = 4 * 8 * QS * 8;   // bytes staged per compute warp: 4 elements x 8 qps
+  static constexpr int SMEM_TOTAL = 232448;            // sm_100: 227 KB opt-in per CTA
+  static constexpr int FIXED = MS * 48 + (AUX ? MS * (24 + 8 + 8 + 8 * EXTRA) : 0) + NC * STAGE_WARP + kFlushBufBytes +
+                               NC * 4 * REC_WORDS * 4 + MS * 8 + 4 * 32 + 16 + MS;
   static constexpr int ARENA_RAW = ((SMEM_TOTAL - FIXED) / 72) & ~1;
   static constexpr int ARENA_BLOCKS = ARENA_RAW > 4094 ? 4094 : ARENA_RAW;
   static constexpr int O_XYZ = ARENA_BLOCKS * 72;
@@ -74,12 +81,12 @@ struct Lay {
   static constexpr int O_T = O_RHO + MS * 8;
   static constexpr int O_EX = O_T + MS * 8;
   static constexpr int O_STAGE = AUX ? O_EX + MS * 8 * EXTRA : O_ADJ;
-  static constexpr int O_FBUF = O_STAGE + WARPS * STAGE_EL * STRIDE * 8;
+  static constexpr int O_FBUF = O_STAGE + NC * STAGE_WARP;
   static constexpr int O_REC = O_FBUF + kFlushBufBytes;
-  static constexpr int O_GID = O_REC + WARPS * 4 * REC_WORDS * 4;
+  static constexpr int O_GID = O_REC + NC * 4 * REC_WORDS * 4;
   static constexpr int O_CNT = O_GID + MS * 4;
   static constexpr int O_SD = O_CNT + MS * 4;
-  static constexpr int O_MISC = O_SD + 2 * 32;
+  static constexpr int O_MISC = O_SD + 4 * 32;
   static constexpr int O_CM = O_MISC + 16;
   static constexpr int TOTAL = (O_CM + MS + 15) & ~15;
   static_assert(TOTAL <= SMEM_TOTAL, "shared-memory layout exceeds 227 KB");
@@ -96,12 +103,12 @@ struct Smem {
   double* extras;  // aux
   double* stage;
   unsigned char* fbuf;
-  uint32_t* rec;   // per warp: the 4 visit records of the current chunk
+  uint32_t* rec;   // per compute warp: the 4 visit records of the current chunk
   int32_t* gid;
   int32_t* cnt;    // per slot: number of element contributions accumulated so far
   uint8_t* cm;
-  StepDesc* sd;    // [2]
-  int* misc;       // [0] chunk dispenser, [1] current tile
+  StepDesc* sd;    // ring of 4
+  int* misc;       // [0..1] chunk dispensers (step parity), [2] current tile
 };
 
 template <bool AUX>
@@ -141,39 +148,23 @@ struct Flags {
   bool J, R, G, simp, thermal, nv6, S;  // S: pair blocks are accumulated (J or R requested)
 };
 
-// ---- geometry phase: lane = (element slot el, quadrature point q) ---------------------------------------
-template <bool AUX>
-struct QpData {
-  double g[8][3];  // physical shape-function gradients
-  double w;        // JxW * E(rho_q)
-  double pth;      // AUX: -JxW * E * alpha_k * (T - Tref)   (thermal stress, isotropic)
-  double s;        // AUX: sensitivity density  JxW * dE/drho * eps(adj)^T Dhat eps(u)
-};
-
+// ---- geometry phase: lane = (element el, quadrature point q); stages inv = J^-1 (inv[c][r] = d xi_r / d x_c) and w ---
 template <bool AUX>
 __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const int ln[8],
-                                               int q, QpData<AUX>& d) {
-  constexpr double gp = 0.57735026918962576451;
-  const double xi = (q & 1) ? gp : -gp, eta = (q & 2) ? gp : -gp, zeta = (q & 4) ? gp : -gp;
+                                               int q, double* out) {
+  const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP, zeta = (q & 4) ? GP : -GP;
   const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
   double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
-  double dref[8][3];
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     const double fx = sgx(b) > 0 ? xp : xm, fy = sgy(b) > 0 ? yp : ym, fz = sgz(b) > 0 ? zp : zm;
-    dref[b][0] = 0.125 * sgx(b) * fy * fz;
-    dref[b][1] = 0.125 * sgy(b) * fx * fz;
-    dref[b][2] = 0.125 * sgz(b) * fx * fy;
+    const double d0 = 0.125 * sgx(b) * fy * fz, d1 = 0.125 * sgy(b) * fx * fz, d2 = 0.125 * sgz(b) * fx * fy;
     const double* X = sm.xyz + ln[b] * 3;
     const double x0 = X[0], x1 = X[1], x2 = X[2];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      Jm[r][0] = fma(dref[b][r], x0, Jm[r][0]);
-      Jm[r][1] = fma(dref[b][r], x1, Jm[r][1]);
-      Jm[r][2] = fma(dref[b][r], x2, Jm[r][2]);
-    }
+    Jm[0][0] = fma(d0, x0, Jm[0][0]); Jm[0][1] = fma(d0, x1, Jm[0][1]); Jm[0][2] = fma(d0, x2, Jm[0][2]);
+    Jm[1][0] = fma(d1, x0, Jm[1][0]); Jm[1][1] = fma(d1, x1, Jm[1][1]); Jm[1][2] = fma(d1, x2, Jm[1][2]);
+    Jm[2][0] = fma(d2, x0, Jm[2][0]); Jm[2][1] = fma(d2, x1, Jm[2][1]); Jm[2][2] = fma(d2, x2, Jm[2][2]);
   }
-  // cofactors: inv[c][r] = d xi_r / d x_c
   const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
   const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
   const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
@@ -187,15 +178,9 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
   inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
   inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
   inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
-#pragma unroll
-  for (int b = 0; b < 8; ++b)
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      d.g[b][c] = dref[b][0] * inv[c][0] + dref[b][1] * inv[c][1] + dref[b][2] * inv[c][2];
 
   const double JxW = det;  // Gauss weights are 1 for the 2x2x2 rule
-  double E = p.E0;
-  d.pth = 0.; d.s = 0.;
+  double E = p.E0, pth = 0., s = 0.;
   if (AUX) {
     double N[8];
 #pragma unroll
@@ -216,24 +201,25 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
       double t = 0.;
 #pragma unroll
       for (int b = 0; b < 8; ++b) t = fma(N[b], sm.T[ln[b]], t);
-      d.pth = -(JxW * E) * p.alpha_k * (t - p.T_ref);
+      pth = -(JxW * E) * p.alpha_k * (t - p.T_ref);
     }
     if (fl.G) {
       double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // H[i][j] = d u_i / d x_j
       double A[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
 #pragma unroll
       for (int b = 0; b < 8; ++b) {
+        const double fx = sgx(b) > 0 ? xp : xm, fy = sgy(b) > 0 ? yp : ym, fz = sgz(b) > 0 ? zp : zm;
+        const double d0 = 0.125 * sgx(b) * fy * fz, d1 = 0.125 * sgy(b) * fx * fz, d2 = 0.125 * sgz(b) * fx * fy;
+        double g[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) g[c] = d0 * inv[c][0] + d1 * inv[c][1] + d2 * inv[c][2];
         const double* U = sm.u + ln[b] * 3;
         const double* L = sm.adj + ln[b] * 3;
         const double u0 = U[0], u1 = U[1], u2 = U[2], l0 = L[0], l1 = L[1], l2 = L[2];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          H[0][j] = fma(u0, d.g[b][j], H[0][j]);
-          H[1][j] = fma(u1, d.g[b][j], H[1][j]);
-          H[2][j] = fma(u2, d.g[b][j], H[2][j]);
-          A[0][j] = fma(l0, d.g[b][j], A[0][j]);
-          A[1][j] = fma(l1, d.g[b][j], A[1][j]);
-          A[2][j] = fma(l2, d.g[b][j], A[2][j]);
+          H[0][j] = fma(u0, g[j], H[0][j]); H[1][j] = fma(u1, g[j], H[1][j]); H[2][j] = fma(u2, g[j], H[2][j]);
+          A[0][j] = fma(l0, g[j], A[0][j]); A[1][j] = fma(l1, g[j], A[1][j]); A[2][j] = fma(l2, g[j], A[2][j]);
         }
       }
       const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
@@ -242,69 +228,80 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
       const double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
       const double dens = p.lam1 * (a0 + a1 + a2) * (e0 + e1 + e2) +
                           p.mu1 * (2. * (a0 * e0 + a1 * e1 + a2 * e2) + a3 * e3 + a4 * e4 + a5 * e5);
-      d.s = JxW * dE * dens;
+      s = JxW * dE * dens;
     }
   }
-  d.w = JxW * E;
-}
-
-template <bool AUX>
-__device__ __forceinline__ void stage_write(double* st, int q, const QpData<AUX>& d) {
-  const int h = q >> 2, q4 = q & 3;
-#pragma unroll
-  for (int b = 0; b < 8; ++b)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) st[(i * 2 + h) * V_HALF + b * 4 + q4] = d.g[b][i];
-  st[OFF_W + q] = d.w;
-  if (AUX) { st[OFF_PTH + q] = d.pth; st[OFF_S + q] = d.s; }
+  double2* o = reinterpret_cast<double2*>(out);
+  o[0] = make_double2(inv[0][0], inv[0][1]);
+  o[1] = make_double2(inv[0][2], inv[1][0]);
+  o[2] = make_double2(inv[1][1], inv[1][2]);
+  o[3] = make_double2(inv[2][0], inv[2][1]);
+  o[4] = make_double2(inv[2][2], JxW * E);
+  if (AUX) o[5] = make_double2(pth, s);
 }
 
 // ---- matrix phase: all 32 lanes on one element; lane = (row node a, qp q4 | q4+4) ------------------------------
-// rec: the visit record in shared memory.  All arithmetic (DMMA, lane reductions) happens first; the adds into the
-// pair blocks wait until the per-node counters say that every earlier visit of the plan order has landed.
-struct LaneConst {     // matrix-phase constants of lane (a = lane/4, q4 = lane%4), columns b = 2*q4 + bb
-  int pidx[2];         // index of pair {a,b} in VisitRec8::pair
-  unsigned swap[2];    // a > b: the lane holds the transposed orientation of the pair's (lo,hi) order
-  bool le[2];          // a <= b: the lane owns the symmetric components (i,i) of the pair
+struct LaneConst {     // constants of lane (a = lane/4, q4 = lane%4); columns b = 2*q4 + bb
+  double d0[2], d1[2], d2;  // reference gradients of N_a at qps q4 (h = 0) and q4+4 (h = 1)
+  double nlo, nhi;          // N_a at those qps (aux)
+  unsigned bits;            // pair indices (bits 0-5, 8-13), a > b flags (16, 17), a <= b flags (18, 19)
 };
 
 __device__ __forceinline__ LaneConst make_lane_const(int lane) {
   LaneConst lc;
   const int a = lane >> 2, q4 = lane & 3;
+  const double sx = (((a + 1) >> 1) & 1) ? 1. : -1., sy = ((a >> 1) & 1) ? 1. : -1., sz = (a >> 2) ? 1. : -1.;
+  const double fx = 1. + sx * ((q4 & 1) ? GP : -GP), fy = 1. + sy * ((q4 & 2) ? GP : -GP);
+  const double fz0 = 1. - sz * GP, fz1 = 1. + sz * GP;
+  lc.d0[0] = 0.125 * sx * fy * fz0; lc.d0[1] = 0.125 * sx * fy * fz1;
+  lc.d1[0] = 0.125 * sy * fx * fz0; lc.d1[1] = 0.125 * sy * fx * fz1;
+  lc.d2 = 0.125 * sz * fx * fy;
+  lc.nlo = 0.125 * fx * fy * fz0; lc.nhi = 0.125 * fx * fy * fz1;
+  unsigned bits = 0;
 #pragma unroll
   for (int bb = 0; bb < 2; ++bb) {
     const int b = 2 * q4 + bb;
     const int lo = min(a, b), hi = max(a, b);
-    lc.pidx[bb] = lo * (15 - lo) / 2 + hi;
-    lc.swap[bb] = a > b ? 1u : 0u;
-    lc.le[bb] = a <= b;
+    bits |= (unsigned)(lo * (15 - lo) / 2 + hi) << (8 * bb);
+    bits |= (a > b ? 1u : 0u) << (16 + bb);
+    bits |= (a <= b ? 1u : 0u) << (18 + bb);
   }
+  lc.bits = bits;
   return lc;
 }
 
+// st: the element's staged qp data; rec: the visit record in shared memory.  All arithmetic (DMMA, lane reductions)
+// happens first; the adds into the pair blocks wait until the per-node counters say that every earlier visit of the
+// plan order has landed.
 template <bool AUX>
 __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& sm, const Flags& fl, const LaneConst& lc,
                                               const double* st, const uint32_t* rec, int lane) {
+  constexpr int QS = Lay<AUX>::QS;
   const int a = lane >> 2, q4 = lane & 3;
   const uint16_t* rec16 = reinterpret_cast<const uint16_t*>(rec);
   const uint8_t* rec8 = reinterpret_cast<const uint8_t*>(rec);
   const int la = rec16[a];
   const int rank = rec8[16 + a];
   const bool own = rank != 0xFF;
-  double A[3][2];
+  // operand entries of the lane: g_a[i] at its two quadrature points, A[i][h] = sum_r inv_h[i][r] * dN_a/dxi_r
+  double A[3][2], w[2], pth[2], ss[2];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    A[i][0] = st[(i * 2 + 0) * V_HALF + lane];
-    A[i][1] = st[(i * 2 + 1) * V_HALF + lane];
+  for (int h = 0; h < 2; ++h) {
+    const double2* s2 = reinterpret_cast<const double2*>(st + (q4 + 4 * h) * QS);
+    const double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3 = s2[3], v4 = s2[4];
+    A[0][h] = v0.x * lc.d0[h] + v0.y * lc.d1[h] + v1.x * lc.d2;
+    A[1][h] = v1.y * lc.d0[h] + v2.x * lc.d1[h] + v2.y * lc.d2;
+    A[2][h] = v3.x * lc.d0[h] + v3.y * lc.d1[h] + v4.x * lc.d2;
+    w[h] = v4.y;
+    if (AUX) { const double2 v5 = s2[5]; pth[h] = v5.x; ss[h] = v5.y; }
   }
   // C[k][bb]: component pairs k = 0..5 <-> (0,0),(1,1),(2,2),(0,1),(0,2),(1,2); columns b = 2*q4 + bb
   double C[6][2];
   double mx = 0., t0 = 0., t1 = 0., t2 = 0., tg = 0.;
   if (fl.S) {
-    const double w0 = st[OFF_W + q4], w1 = st[OFF_W + 4 + q4];
     double B[3][2];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { B[j][0] = A[j][0] * w0; B[j][1] = A[j][1] * w1; }
+    for (int j = 0; j < 3; ++j) { B[j][0] = A[j][0] * w[0]; B[j][1] = A[j][1] * w[1]; }
 #pragma unroll
     for (int k = 0; k < 6; ++k) { C[k][0] = 0.; C[k][1] = 0.; }
 #pragma unroll
@@ -329,10 +326,9 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
     }
   }
   if (AUX && fl.thermal && fl.R) {
-    const double p0 = st[OFF_PTH + q4], p1 = st[OFF_PTH + 4 + q4];
-    t0 = p0 * A[0][0] + p1 * A[0][1];
-    t1 = p0 * A[1][0] + p1 * A[1][1];
-    t2 = p0 * A[2][0] + p1 * A[2][1];
+    t0 = pth[0] * A[0][0] + pth[1] * A[0][1];
+    t1 = pth[0] * A[1][0] + pth[1] * A[1][1];
+    t2 = pth[0] * A[2][0] + pth[1] * A[2][1];
 #pragma unroll
     for (int o = 1; o < 4; o <<= 1) {
       t0 += __shfl_xor_sync(0xffffffffu, t0, o);
@@ -341,14 +337,7 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
     }
   }
   if (AUX && fl.G) {
-    // N_a at qp q4 and q4+4
-    constexpr double gp = 0.57735026918962576451;
-    const double xi = (q4 & 1) ? gp : -gp, eta = (q4 & 2) ? gp : -gp;
-    const double fx = ((a == 1 || a == 2 || a == 5 || a == 6) ? 1. + xi : 1. - xi);
-    const double fy = ((a == 2 || a == 3 || a == 6 || a == 7) ? 1. + eta : 1. - eta);
-    const double nlo = 0.125 * fx * fy * (a >= 4 ? 1. - gp : 1. + gp);  // zeta = -gp for q < 4
-    const double nhi = 0.125 * fx * fy * (a >= 4 ? 1. + gp : 1. - gp);  // zeta = +gp for q >= 4
-    tg = nlo * st[OFF_S + q4] + nhi * st[OFF_S + 4 + q4];
+    tg = lc.nlo * ss[0] + lc.nhi * ss[1];
     tg += __shfl_xor_sync(0xffffffffu, tg, 1);
     tg += __shfl_xor_sync(0xffffffffu, tg, 2);
   }
@@ -358,20 +347,18 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
     while (ld_acquire_s32(sm.cnt + la) != rank) __nanosleep(20);
   __syncwarp();
   if (fl.S) {
-    // both pair entries of the lane: columns b = 2*q4 and 2*q4+1 of row a
-    const unsigned e2[2] = {rec16[12 + lc.pidx[0]], rec16[12 + lc.pidx[1]]};
 #pragma unroll
     for (int bb = 0; bb < 2; ++bb) {
-      const unsigned e = e2[bb];
+      const unsigned e = rec16[12 + ((lc.bits >> (8 * bb)) & 63u)];  // pair {a, b = 2*q4 + bb}
       if (e != kPairNone) {
         double* blk = sm.arena + (e & kPairSlotMask) * 9;
         // stored block oriented as S_(a,b) (tr = 0) or S_(b,a) (tr = 1): off-diagonal components (i<j) of C_ij[a][b]
         // go to [i][j] = {1, 2, 5} or to [j][i] = {3, 6, 7}
-        const unsigned tr = ((e >> 12) & 1u) ^ lc.swap[bb];
+        const unsigned tr = ((e >> 12) ^ (lc.bits >> (16 + bb))) & 1u;
         double* p1 = blk + 2 * tr;  // [1]|[3] and [5]|[7]
         double* p2 = blk + 4 * tr;  // [2]|[6]
         const bool add = (e & kPairInit) == 0;
-        const bool dg = lc.le[bb];
+        const bool dg = ((lc.bits >> (18 + bb)) & 1u) != 0;
         double v01 = 0., v02 = 0., v12 = 0., v00 = 0., v11 = 0., v22 = 0.;
         if (add) {
           v01 = p1[1]; v02 = p2[2]; v12 = p1[5];
@@ -395,60 +382,63 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
 // ---- staging of nodal state (loads of one step) by `nthr` threads, this thread being number `t` ---------------
 template <bool AUX>
 __device__ __forceinline__ void load_states(const SweepParams& p, const Smem& sm, int begin, int n, int t, int nthr) {
-  constexpr int UN = 4;
-  for (int i0 = t; i0 < n; i0 += nthr * UN) {
-    LoadRec lr[UN];
+  for (int i = t; i < n; i += nthr) {
+    const LoadRec lr = p.loads[begin + i];
+    const int n_ = lr.gid, sl = lr.slot;
+    const unsigned cm = p.cmask ? p.cmask[n_] : 0u;
+    sm.gid[sl] = n_;
+    sm.cnt[sl] = 0;
+    sm.cm[sl] = (uint8_t)cm;
 #pragma unroll
-    for (int k = 0; k < UN; ++k) {
-      const int i = i0 + k * nthr;
-      if (i < n) lr[k] = p.loads[begin + i];
+    for (int c = 0; c < 3; ++c) {
+      sm.xyz[sl * 3 + c] = p.xyz[(int64_t)n_ * 3 + c];
+      sm.u[sl * 3 + c] = p.X[(int64_t)n_ * p.nv + c];
     }
+    if (AUX) {
+      // constrain_element_vector zeroes constrained rows of dR/dp, i.e. the adjoint never sees them
 #pragma unroll
-    for (int k = 0; k < UN; ++k) {
-      const int i = i0 + k * nthr;
-      if (i >= n) continue;
-      const int n_ = lr[k].gid, sl = lr[k].slot;
-      const unsigned cm = p.cmask ? p.cmask[n_] : 0u;
-      sm.gid[sl] = n_;
-      sm.cnt[sl] = 0;
-      sm.cm[sl] = (uint8_t)cm;
+      for (int c = 0; c < 3; ++c) sm.adj[sl * 3 + c] = (p.adj && !((cm >> c) & 1u)) ? p.adj[(int64_t)n_ * p.nv + c] : 0.;
+      sm.rho[sl] = p.rho ? p.rho[n_] : 1.;
+      sm.T[sl] = p.temperature ? p.temperature[n_] : p.T_const;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        sm.xyz[sl * 3 + c] = p.xyz[(int64_t)n_ * 3 + c];
-        sm.u[sl * 3 + c] = p.X[(int64_t)n_ * p.nv + c];
-      }
-      if (AUX) {
-        // constrain_element_vector zeroes constrained rows of dR/dp, i.e. the adjoint never sees them
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.adj[sl * 3 + c] = (p.adj && !((cm >> c) & 1u)) ? p.adj[(int64_t)n_ * p.nv + c] : 0.;
-        sm.rho[sl] = p.rho ? p.rho[n_] : 1.;
-        sm.T[sl] = p.temperature ? p.temperature[n_] : p.T_const;
-#pragma unroll
-        for (int c = 0; c < EXTRA; ++c) sm.extras[sl * EXTRA + c] = 0.;
-      }
+      for (int c = 0; c < EXTRA; ++c) sm.extras[sl * EXTRA + c] = 0.;
     }
   }
 }
 
+// flush records of one step -> shared memory (by `nthr` threads)
+__device__ __forceinline__ void load_flush_records(const SweepParams& p, const Smem& sm, const StepDesc& sd, int t, int nthr) {
+  const uint4* src_r = reinterpret_cast<const uint4*>(p.flush_rows + sd.flush_begin);
+  uint4* dst_r = reinterpret_cast<uint4*>(sm.fbuf);
+  for (int k = t; k < sd.n_flush * 2; k += nthr) dst_r[k] = src_r[k];
+  const uint4* src_e = reinterpret_cast<const uint4*>(p.flush_ent + sd.fent_begin);
+  uint4* dst_e = reinterpret_cast<uint4*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
+  for (int k = t; k < (sd.n_fent + 3) / 4; k += nthr) dst_e[k] = src_e[k];
+}
+
 // ---- flush: S -> K, Dirichlet semantics, f = K u, one store of every CSR value of the finished rows --------------
+// four rows per warp at a time, eight lanes per row; a lane walks the row's neighbour blocks c = l8, l8+8, ...
 template <bool AUX>
 __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm, const Flags& fl, const StepDesc& sd,
-                                           int warp, int lane) {
+                                           int fwarp, int lane) {
   const FlushRow* rows = reinterpret_cast<const FlushRow*>(sm.fbuf);
   const uint32_t* ents = reinterpret_cast<const uint32_t*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
-  for (int r = warp; r < sd.n_flush; r += WARPS) {
-    const FlushRow fr = rows[r];
-    const int nnb = fr.nnb;
+  const int sub = lane >> 3, l8 = lane & 7;
+  for (int rbase = fwarp * 4; rbase < sd.n_flush; rbase += NF * 4) {
+    const int r = rbase + sub;
+    const bool valid = r < sd.n_flush;
+    const FlushRow fr = rows[valid ? r : rbase];
+    const int nnb = valid ? fr.nnb : 0;
     const int sa = fr.slot;
     const unsigned cmn = sm.cm[sa];
     const int n = fr.gid;
     const double nadj = double(fr.nadj + fr.nadjd), nadjd = double(fr.nadjd);
     const double* ex = AUX ? sm.extras + sa * EXTRA : nullptr;
+    const uint32_t* ent = ents + fr.ent_rel;
     double r0 = 0., r1 = 0., r2 = 0.;
-    for (int c0 = 0; c0 < nnb; c0 += 32) {
-      const int c = c0 + lane;
+    for (int c = l8; __any_sync(0xffffffffu, c < nnb); c += 8) {
       if (c < nnb) {
-        const uint32_t e = ents[fr.ent_rel + c];
+        const uint32_t e = ent[c];
         const unsigned bs = e & kFlushNoBlock;
         const bool self = (e & kFlushSelf) != 0;
         const unsigned ns = e >> 16;
@@ -524,32 +514,33 @@ __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm,
       }
     }
     if (fl.R) {
-      // deterministic butterfly over the 32 lanes for the three sums at once: lanes 0, 8 and 16 end with r0, r1, r2
-      const bool hi16 = (lane & 16) != 0, hi8 = (lane & 8) != 0;
-      const double g0 = __shfl_xor_sync(0xffffffffu, hi16 ? r0 : r2, 16);
-      const double g1 = __shfl_xor_sync(0xffffffffu, hi16 ? r1 : 0., 16);
-      const double x0 = (hi16 ? r2 : r0) + g0, x1 = (hi16 ? 0. : r1) + g1;
-      double y = (hi8 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, hi8 ? x0 : x1, 8);
-      y += __shfl_xor_sync(0xffffffffu, y, 4);
-      y += __shfl_xor_sync(0xffffffffu, y, 2);
+      // deterministic butterfly over the 8 lanes of a row for the three sums at once: lanes 0, 2 and 4 of the group end
+      // with r0, r1, r2
+      const bool hi4 = (lane & 4) != 0, hi2 = (lane & 2) != 0;
+      const double g0 = __shfl_xor_sync(0xffffffffu, hi4 ? r0 : r2, 4);
+      const double g1 = __shfl_xor_sync(0xffffffffu, hi4 ? r1 : 0., 4);
+      const double x0 = (hi4 ? r2 : r0) + g0, x1 = (hi4 ? 0. : r1) + g1;
+      double y = (hi2 ? x1 : x0) + __shfl_xor_sync(0xffffffffu, hi2 ? x0 : x1, 2);
       y += __shfl_xor_sync(0xffffffffu, y, 1);
-      if ((lane & 7) == 0 && lane < 24) {
-        const int i = lane >> 3;
-        double v = y;
-        if (AUX) v += ex[i];
-        p.R[(int64_t)n * p.nv + i] = ((cmn >> i) & 1u) ? 0. : v;
-      } else if (fl.nv6 && lane >= 25 && lane < 28) {
-        p.R[(int64_t)n * p.nv + (lane - 22)] = 0.;  // rotational dofs of the 6-variable system carry no residual
+      if (valid) {
+        if ((l8 & 1) == 0 && l8 < 6) {
+          const int i = l8 >> 1;
+          double v = y;
+          if (AUX) v += ex[i];
+          p.R[(int64_t)n * p.nv + i] = ((cmn >> i) & 1u) ? 0. : v;
+        } else if (fl.nv6 && (l8 & 1)) {
+          if (l8 < 6) p.R[(int64_t)n * p.nv + 3 + (l8 >> 1)] = 0.;  // rotational dofs of the 6-variable system: no residual
+        }
       }
     }
-    if (AUX && fl.G && lane == 0) p.G[n] = ex[3];
+    if (AUX && fl.G && valid && l8 == 0) p.G[n] = ex[3];
   }
 }
 
 template <bool AUX>
-__global__ void __launch_bounds__(THREADS, kCtasPerSm) hex8_sweep_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int STRIDE = Lay<AUX>::STRIDE;
+  constexpr int QS = Lay<AUX>::QS;
   const Smem sm = make_smem<AUX>(smem_raw);
 
   Flags fl;
@@ -558,12 +549,7 @@ __global__ void __launch_bounds__(THREADS, kCtasPerSm) hex8_sweep_kernel(const S
   fl.S = fl.J || fl.R;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int el = lane >> 3, q = lane & 7;
-  const LaneConst lc = make_lane_const(lane);
-  double* my_stage = sm.stage + warp * STAGE_EL * STRIDE;
-  uint32_t* my_rec = sm.rec + warp * 4 * REC_WORDS;
-  int& s_next = sm.misc[0];
-  int& s_tile = sm.misc[1];
+  int& s_tile = sm.misc[2];
 
   for (;;) {
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -571,98 +557,102 @@ __global__ void __launch_bounds__(THREADS, kCtasPerSm) hex8_sweep_kernel(const S
     const int tile = s_tile;
     if (tile >= p.n_tiles) break;
     const TileDesc td = p.tiles[tile];
-    if (tid < 8) reinterpret_cast<int*>(&sm.sd[0])[tid] = reinterpret_cast<const int*>(p.steps + td.step_begin)[tid];
-    if (tid == 0) s_next = 0;
+    // prologue: descriptors of the first three steps, state of the first two, flush records of the first
+    if (tid < 24 && (tid >> 3) < td.n_steps)
+      reinterpret_cast<int*>(&sm.sd[tid >> 3])[tid & 7] = reinterpret_cast<const int*>(p.steps + td.step_begin + (tid >> 3))[tid & 7];
+    if (tid < 2) sm.misc[tid] = 0;
     __syncthreads();
     load_states<AUX>(p, sm, sm.sd[0].load_begin, sm.sd[0].n_loads, tid, THREADS);
+    if (td.n_steps > 1) load_states<AUX>(p, sm, sm.sd[1].load_begin, sm.sd[1].n_loads, tid, THREADS);
+    load_flush_records(p, sm, sm.sd[0], tid, THREADS);
     __syncthreads();
 
-    for (int s = 0; s < td.n_steps; ++s) {
-      const StepDesc sd = sm.sd[s & 1];
-      if (warp == 0) {
-        // stage the flush records of this step and the nodal state of the next one
-        if (s + 1 < td.n_steps) {
-          StepDesc* nsd = &sm.sd[(s + 1) & 1];
-          if (lane < 8) reinterpret_cast<int*>(nsd)[lane] = reinterpret_cast<const int*>(p.steps + td.step_begin + s + 1)[lane];
-          __syncwarp();
-          load_states<AUX>(p, sm, nsd->load_begin, nsd->n_loads, lane, 32);
-        }
-        const uint4* src_r = reinterpret_cast<const uint4*>(p.flush_rows + sd.flush_begin);
-        uint4* dst_r = reinterpret_cast<uint4*>(sm.fbuf);
-        for (int k = lane; k < sd.n_flush * 2; k += 32) dst_r[k] = src_r[k];
-        const uint4* src_e = reinterpret_cast<const uint4*>(p.flush_ent + sd.fent_begin);
-        uint4* dst_e = reinterpret_cast<uint4*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
-        for (int k = lane; k < (sd.n_fent + 3) / 4; k += 32) dst_e[k] = src_e[k];
-      }
-      // warps take chunks of consecutive visits in plan order: 4 visits while more than a round of work is left, then
-      // the remainder split evenly over the warps so that the step ends without a tail; the records of the next chunk
-      // are prefetched into registers while the current one is processed
-      const int full = sd.n_visits / (4 * WARPS) * WARPS;          // chunks of 4
-      const int rem = sd.n_visits - 4 * full;
-      const int base = rem / WARPS, extra = rem - base * WARPS;     // last round: `extra` chunks of base+1, then base
-      const int n_chunks = full + (base ? WARPS : extra);
-      const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + sd.visit_begin);
-      auto chunk_range = [&](int c, int& begin, int& size) {
-        if (c < full) { begin = 4 * c; size = 4; }
-        else { const int j = c - full; begin = 4 * full + j * base + min(j, extra); size = base + (j < extra ? 1 : 0); }
-      };
-      int c = 0;
-      if (lane == 0) c = atomicAdd(&s_next, 1);
-      c = __shfl_sync(0xffffffffu, c, 0);
-      uint32_t r0 = 0, r1 = 0, r2 = 0;
-      int nvis = 0, nvis_next = 0;
-      if (c < n_chunks) {
-        int b0;
-        chunk_range(c, b0, nvis);
-        const int nw = nvis * REC_WORDS;
-        const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
-        if (lane < nw) r0 = src[lane];
-        if (lane + 32 < nw) r1 = src[lane + 32];
-        if (lane + 64 < nw) r2 = src[lane + 64];
-      }
-      while (c < n_chunks) {
-        my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
-        __syncwarp();
-        int cn = 0;
-        if (lane == 0) cn = atomicAdd(&s_next, 1);
-        cn = __shfl_sync(0xffffffffu, cn, 0);
-        if (cn < n_chunks) {
+    if (warp < NC) {
+      // ================================ compute warps ================================
+      const int el = lane >> 3, q = lane & 7;
+      const LaneConst lc = make_lane_const(lane);
+      double* my_stage = sm.stage + warp * (4 * 8 * QS);
+      uint32_t* my_rec = sm.rec + warp * 4 * REC_WORDS;
+      for (int s = 0; s < td.n_steps; ++s) {
+        if (s >= 2) bar_sync(BAR_FLUSH + (s & 1), THREADS);  // flush of step s-2 done, state of step s staged
+        const StepDesc sd = sm.sd[s & 3];
+        int& s_next = sm.misc[s & 1];
+        // warps take chunks of consecutive visits in plan order: 4 visits while more than a round of work is left, then
+        // the remainder split evenly over the warps so that the step ends without a tail; the records of the next chunk
+        // are prefetched into registers while the current one is processed
+        const int full = sd.n_visits / (4 * NC) * NC;              // chunks of 4
+        const int rem = sd.n_visits - 4 * full;
+        const int base = rem / NC, extra = rem - base * NC;        // last round: `extra` chunks of base+1, then base
+        const int n_chunks = full + (base ? NC : extra);
+        const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + sd.visit_begin);
+        auto chunk_range = [&](int c, int& begin, int& size) {
+          if (c < full) { begin = 4 * c; size = 4; }
+          else { const int j = c - full; begin = 4 * full + j * base + min(j, extra); size = base + (j < extra ? 1 : 0); }
+        };
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&s_next, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        uint32_t r0 = 0, r1 = 0, r2 = 0;
+        int nvis = 0, nvis_next = 0;
+        if (c < n_chunks) {
           int b0;
-          chunk_range(cn, b0, nvis_next);
-          const int nw = nvis_next * REC_WORDS;
+          chunk_range(c, b0, nvis);
+          const int nw = nvis * REC_WORDS;
           const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
-          r0 = r1 = r2 = 0;
           if (lane < nw) r0 = src[lane];
           if (lane + 32 < nw) r1 = src[lane + 32];
           if (lane + 64 < nw) r2 = src[lane + 64];
         }
-        const bool active = el < nvis;
-        QpData<AUX> d;
-        if (active) {
-          const uint4 pk = *reinterpret_cast<const uint4*>(my_rec + el * REC_WORDS);
-          int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
-                       int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
-          geometry_phase<AUX>(p, sm, fl, ln, q, d);
-        }
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        while (c < n_chunks) {
+          my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
           __syncwarp();
-          if (active && (el >> 1) == half) stage_write<AUX>(my_stage + (el & 1) * STRIDE, q, d);
-          __syncwarp();
-#pragma unroll
-          for (int e2 = 0; e2 < 2; ++e2) {
-            const int ecur = half * 2 + e2;
-            if (ecur < nvis) element_phase<AUX>(p, sm, fl, lc, my_stage + e2 * STRIDE, my_rec + ecur * REC_WORDS, lane);
+          int cn = 0;
+          if (lane == 0) cn = atomicAdd(&s_next, 1);
+          cn = __shfl_sync(0xffffffffu, cn, 0);
+          if (cn < n_chunks) {
+            int b0;
+            chunk_range(cn, b0, nvis_next);
+            const int nw = nvis_next * REC_WORDS;
+            const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
+            r0 = r1 = r2 = 0;
+            if (lane < nw) r0 = src[lane];
+            if (lane + 32 < nw) r1 = src[lane + 32];
+            if (lane + 64 < nw) r2 = src[lane + 64];
           }
+          if (el < nvis) {
+            const uint4 pk = *reinterpret_cast<const uint4*>(my_rec + el * REC_WORDS);
+            int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
+                         int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
+            geometry_phase<AUX>(p, sm, fl, ln, q, my_stage + lane * QS);
+          }
+          __syncwarp();
+          for (int e = 0; e < nvis; ++e)
+            element_phase<AUX>(p, sm, fl, lc, my_stage + e * 8 * QS, my_rec + e * REC_WORDS, lane);
+          __syncwarp();
+          c = cn; nvis = nvis_next;
         }
-        __syncwarp();
-        c = cn; nvis = nvis_next;
+        bar_arrive(BAR_VISITS + (s & 1), THREADS);
       }
-      __syncthreads();
-      if (tid == 0) s_next = 0;
-      flush_rows<AUX>(p, sm, fl, sd, warp, lane);
-      __syncthreads();
+    } else {
+      // ================================ flush / staging warps ================================
+      const int fw = warp - NC, ft = tid - NC * 32;
+      for (int s = 0; s < td.n_steps; ++s) {
+        bar_sync(BAR_VISITS + (s & 1), THREADS);   // every visit of step s has landed (also orders the staging below)
+        const StepDesc sd = sm.sd[s & 3];
+        flush_rows<AUX>(p, sm, fl, sd, fw, lane);
+        bar_sync(BAR_FGROUP, NF * 32);             // flush records and freed state slots may be overwritten now
+        if (s + 1 < td.n_steps) load_flush_records(p, sm, sm.sd[(s + 1) & 3], ft, NF * 32);
+        if (s + 2 < td.n_steps) {
+          const StepDesc nsd = sm.sd[(s + 2) & 3];
+          load_states<AUX>(p, sm, nsd.load_begin, nsd.n_loads, ft, NF * 32);
+          if (s + 3 < td.n_steps && ft < 8)
+            reinterpret_cast<int*>(&sm.sd[(s + 3) & 3])[ft] = reinterpret_cast<const int*>(p.steps + td.step_begin + s + 3)[ft];
+          if (ft == 0) sm.misc[s & 1] = 0;         // chunk dispenser of step s+2
+          bar_arrive(BAR_FLUSH + (s & 1), THREADS);
+        }
+      }
     }
+    __syncthreads();
   }
 }
 

@@ -23,7 +23,7 @@ def _fe(prob, e):
     return phi, dphi, jxw
 
 
-def replay(prob, plan, ctx, X=None):
+def replay(prob, plan, ctx, X=None, late_flush=True):
     """Returns (J node-block CSR values in device layout, R or None, per-node flush count)."""
     nv = prob.nv
     E0, nu = prob.mat["E0"], prob.mat["nu"]
@@ -66,10 +66,7 @@ def replay(prob, plan, ctx, X=None):
             for lr in LD[sd["load_begin"]:sd["load_begin"] + sd["n_loads"]]:
                 slot_gid[lr["slot"]] = lr["gid"]; slot_owned[lr["slot"]] = bool(lr["owned"]); cnt[lr["slot"]] = 0
 
-        load(steps[0])
-        for si, sd in enumerate(steps):
-            if si + 1 < len(steps):   # warp 0 stages the next step's state while this step's visits run
-                load(steps[si + 1])
+        def visits(sd):
             for v in V[sd["visit_begin"]:sd["visit_begin"] + sd["n_visits"]]:
                 gids = slot_gid[v["ln"]]
                 e = elem_of[tuple(int(g) for g in gids)]
@@ -102,6 +99,8 @@ def replay(prob, plan, ctx, X=None):
                     if v["rank"][a] != 0xFF:
                         cnt[v["ln"][a]] += 1
                         visited_by_node.setdefault(int(gids[a]), set()).add(e)
+
+        def flush(sd):
             rows_ = FR[sd["flush_begin"]:sd["flush_begin"] + sd["n_flush"]]
             ents = FE[sd["fent_begin"]:sd["fent_begin"] + sd["n_fent"]]
             for fr in rows_:
@@ -145,6 +144,25 @@ def replay(prob, plan, ctx, X=None):
                 if R is not None:
                     for i in range(3):
                         R[n * nv + i] = 0. if (cm[n] >> i) & 1 else f[i]
+        # device timeline (sweep_hex8.cu): the flush of step s runs concurrently with the visits of step s+1 and is
+        # followed by the staging of step s+2.  Both extreme interleavings are legal and must give the same result.
+        load(steps[0])
+        if len(steps) > 1:
+            load(steps[1])
+        if late_flush:
+            for si, sd in enumerate(steps):
+                visits(sd)
+                if si >= 1:
+                    flush(steps[si - 1])
+                    if si + 1 < len(steps):
+                        load(steps[si + 1])
+            flush(steps[-1])
+        else:
+            for si, sd in enumerate(steps):
+                visits(sd)
+                flush(sd)
+                if si + 2 < len(steps):
+                    load(steps[si + 2])
     # every (non-diagonal) element adjacent to an owned node was visited on behalf of that node
     for n in row_of_node:
         want = {e for e in range(prob.n_elem) if n in prob.conn[e] and not diag[e]} if prob.n_elem < 400 else None

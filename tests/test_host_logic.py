@@ -99,8 +99,8 @@ def _replay_case(prob, X):
     rows = ctx.get_row_dofs()
     orp, _ = prob.pattern()
     Jref = np.concatenate([Jo[orp[r]:orp[r + 1]] for r in rows])
-    for aux in (0, 1):
-        J, R, flushed = plan_replay.replay(prob, ctx.debug_plan(aux), ctx, X)
+    for aux, late in ((0, True), (0, False), (1, True)):
+        J, R, flushed = plan_replay.replay(prob, ctx.debug_plan(aux), ctx, X, late_flush=late)
         own = np.zeros(prob.n_nodes, bool); own[rows[::prob.nv] // prob.nv] = True
         assert np.array_equal(flushed, own.astype(np.int64))
         assert not np.isnan(J).any()
