@@ -130,8 +130,8 @@ typedef struct mastb200_stats {
 int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s);
 /* Streaming assembly plan of a planning-only context (device -1), for host-side verification of the integer
  * bookkeeping (tests/test_host_logic.py replays it on the CPU).  aux: 0 plain, 1 auxiliary shared-memory layout.
- * sizes[8]: number of tiles, steps, visits, flush rows, flush entries, loads; arena blocks; state slots.
- * Record layouts: mast-multiphysics_b200/csrc/plan.h (TileDesc 16 B, StepDesc 32 B, VisitRec8 96 B, FlushRow 32 B,
+ * sizes[9]: number of tiles, steps, visit records, flush rows, flush entries, loads; arena blocks; state slots;
+ * compute warps.  Record layouts: mast-multiphysics_b200/csrc/plan.h (TileDesc 16 B, StepDesc 48 B, VisitRec8 96 B, FlushRow 32 B,
  * flush entry 4 B, LoadRec 8 B). */
 int mastb200_debug_plan_sizes(mastb200_context* ctx, int32_t aux, int64_t* sizes);
 int mastb200_debug_plan_copy(mastb200_context* ctx, int32_t aux, void* tiles, void* steps, void* visits,

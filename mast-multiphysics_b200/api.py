@@ -226,21 +226,22 @@ class Context:
 
     def debug_plan(self, aux=0):
         """Streaming plan of a planning-only context as numpy structured arrays (layouts: csrc/plan.h)."""
-        sz = np.zeros(8, np.int64)
+        sz = np.zeros(9, np.int64)
         self._ck(self._lib.mastb200_debug_plan_sizes(self._h, int(aux), _ptr(sz)))
         tiles = np.zeros(sz[0], np.dtype([("step_begin", "i4"), ("n_steps", "i4"), ("n_visits", "i4"), ("n_owned", "i4")]))
         steps = np.zeros(sz[1], np.dtype([("visit_begin", "i4"), ("n_visits", "i4"), ("load_begin", "i4"), ("n_loads", "i4"),
-                                          ("flush_begin", "i4"), ("n_flush", "i4"), ("fent_begin", "i4"), ("n_fent", "i4")]))
+                                          ("flush_begin", "i4"), ("n_flush", "i4"), ("fent_begin", "i4"), ("n_fent", "i4"),
+                                          ("n_pos", "i4"), ("pad", "i4", 3)]))
         visits = np.zeros(sz[2], np.dtype([("ln", "u2", 8), ("rank", "u1", 8), ("pair", "u2", 36)]))
         frows = np.zeros(sz[3], np.dtype([("dst_block", "i8"), ("gid", "i4"), ("ent_rel", "i4"), ("slot", "u2"),
                                           ("nnb", "u2"), ("nadj", "u2"), ("nadjd", "u2"), ("pad", "i4", 2)]))
         fent = np.zeros(sz[4], np.uint32)
         loads = np.zeros(sz[5], np.dtype([("gid", "i4"), ("slot", "u2"), ("owned", "u2")]))
-        assert visits.itemsize == 96 and frows.itemsize == 32 and steps.itemsize == 32 and loads.itemsize == 8
+        assert visits.itemsize == 96 and frows.itemsize == 32 and steps.itemsize == 48 and loads.itemsize == 8
         self._ck(self._lib.mastb200_debug_plan_copy(self._h, int(aux), _ptr(tiles), _ptr(steps), _ptr(visits),
                                                     _ptr(frows), _ptr(fent), _ptr(loads)))
         return dict(tiles=tiles, steps=steps, visits=visits, flush_rows=frows, flush_ent=fent, loads=loads,
-                    arena_blocks=int(sz[6]), max_slots=int(sz[7]))
+                    arena_blocks=int(sz[6]), max_slots=int(sz[7]), n_workers=int(sz[8]))
 
     @property
     def stream(self):

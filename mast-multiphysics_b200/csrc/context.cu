@@ -186,6 +186,7 @@ int ensure_plan(mastb200_context* ctx, int aux) {
   D.lim.max_slots = kMaxSlots;
   D.lim.flush_buf_bytes = kFlushBufBytes;
   D.lim.sm_count = ctx->sm_count * kCtasPerSm;
+  D.lim.n_workers = hex8_sweep_workers();
   StreamPlan P;
   const std::string e = build_stream_plan(ctx->pat, ctx->xyz.data(), ctx->conn.data(),
                                           ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), D.lim, P);
@@ -691,13 +692,13 @@ int mastb200_debug_plan_sizes(mastb200_context* ctx, int32_t aux, int64_t* sizes
   const StreamPlan& P = ctx->dplan[aux].host;
   sizes[0] = (int64_t)P.tiles.size(); sizes[1] = (int64_t)P.steps.size(); sizes[2] = (int64_t)P.visits.size();
   sizes[3] = (int64_t)P.flush_rows.size(); sizes[4] = (int64_t)P.flush_ent.size(); sizes[5] = (int64_t)P.loads.size();
-  sizes[6] = P.lim.arena_blocks; sizes[7] = P.lim.max_slots;
+  sizes[6] = P.lim.arena_blocks; sizes[7] = P.lim.max_slots; sizes[8] = P.lim.n_workers;
   return MASTB200_OK;
 }
 
 int mastb200_debug_plan_copy(mastb200_context* ctx, int32_t aux, void* tiles, void* steps, void* visits, void* flush_rows,
                              void* flush_ent, void* loads) {
-  int64_t sz[8];
+  int64_t sz[9];
   if (int rc = mastb200_debug_plan_sizes(ctx, aux, sz)) return rc;
   const StreamPlan& P = ctx->dplan[aux].host;
   if (tiles) std::memcpy(tiles, P.tiles.data(), P.tiles.size() * sizeof(TileDesc));

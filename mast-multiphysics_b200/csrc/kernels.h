@@ -14,12 +14,13 @@ namespace mastb200 {
 #endif
 constexpr int kCtasPerSm = MASTB200_CTAS;
 constexpr int kMaxSlots = kCtasPerSm == 1 ? 448 : 288;           // node state slots staged in shared memory per strip
-constexpr int kFlushBufBytes = kCtasPerSm == 1 ? 10240 : 6144;   // flush records of one step staged in shared memory
+constexpr int kFlushBufBytes = kCtasPerSm == 1 ? 8192 : 6144;    // flush records of one step staged in shared memory (x2)
 
 // HEX8 linear-elastic sweep (sweep_hex8.cu).  aux: adjoint / density / temperature state and per-node extras staged
 size_t hex8_sweep_smem_bytes(bool aux);
 int hex8_sweep_arena_blocks(bool aux);  // pair blocks of the shared-memory arena (compile-time layout)
 int hex8_sweep_threads();
+int hex8_sweep_workers();  // compute warps = rows of the plan's per-step visit grid
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream);
 
 // SURFACE_PRESSURE side loads gathered per loaded node (loads.cu)

@@ -132,7 +132,7 @@ struct TileOut {
   std::vector<FlushRow> frows;
   std::vector<uint32_t> fent;
   std::vector<LoadRec> loads;
-  int32_t n_owned = 0, max_blocks = 0, max_slots = 0;
+  int32_t n_owned = 0, max_blocks = 0, max_slots = 0, n_real_visits = 0;
 };
 
 struct Scratch {
@@ -198,30 +198,81 @@ struct Builder {
       vstep[v] = smax;
       S = std::max(S, smax + 1);
     }
-    // order: (step, colour, element id); colours spread visits that share an owned node apart
-    std::vector<int32_t> order(nvis);
+    // Static lock-step schedule: the visits of a step are laid out on a grid of `n_workers`
+    // compute warps x K positions.  Visits at the same position share no owned node, so they never touch the same
+    // pair block; a visit only has to wait for visits at earlier positions, which the other warps -- walking their own
+    // rows of the grid in step -- have normally finished.  Accumulation order: (step, position, worker).
+    const int32_t NW = lim.n_workers;
+    std::vector<int32_t> order(nvis), colour(nvis, 0), worker(nvis, 0), n_pos(S, 0);
     {
       std::vector<int32_t> idx(nvis);
       for (size_t v = 0; v < nvis; ++v) idx[v] = (int32_t)v;
       std::stable_sort(idx.begin(), idx.end(), [&](int32_t a, int32_t b) { return vstep[a] < vstep[b]; });
-      std::vector<uint32_t> used(n_owned, 0u);
-      std::vector<int32_t> colour(nvis, 0), touched;
+      std::vector<uint64_t> used(n_owned, 0ull);
+      std::vector<int32_t> touched, cls(nvis, 0);
+      auto owned_mask = [&](int32_t v) {
+        const int32_t* c = conn + (int64_t)elems[v] * nn;
+        uint64_t m = 0;
+        for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l >= 0) m |= used[l]; }
+        return m;
+      };
+      auto mark = [&](int32_t v, int bit) {
+        const int32_t* c = conn + (int64_t)elems[v] * nn;
+        for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l >= 0) { used[l] |= 1ull << bit; touched.push_back(l); } }
+      };
       size_t i0 = 0;
       while (i0 < nvis) {
         size_t i1 = i0;
-        while (i1 < nvis && vstep[idx[i1]] == vstep[idx[i0]]) ++i1;
+        const int32_t st = vstep[idx[i0]];
+        while (i1 < nvis && vstep[idx[i1]] == st) ++i1;
+        // (1) proper colouring of the step's conflict graph (visits sharing an owned node), greedy in element order
         touched.clear();
+        std::vector<std::vector<int32_t>> classes;
         for (size_t i = i0; i < i1; ++i) {
-          const int32_t* c = conn + (int64_t)elems[idx[i]] * nn;
-          uint32_t m = 0;
-          for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l >= 0) m |= used[l]; }
+          const uint64_t m = owned_mask(idx[i]);
           int32_t col = 0;
-          while (col < 31 && (m >> col & 1u)) ++col;
-          colour[idx[i]] = col;
-          for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; if (l >= 0) { used[l] |= 1u << col; touched.push_back(l); } }
+          while (col < 64 && (m >> col & 1ull)) ++col;
+          if (col >= 64) { cleanup(); why = 4; return false; }  // a node with more than 64 elements in one step
+          if ((size_t)col >= classes.size()) classes.resize(col + 1);
+          classes[col].push_back(idx[i]);
+          mark(idx[i], col);
         }
-        for (int32_t l : touched) used[l] = 0u;
-        std::stable_sort(idx.begin() + i0, idx.begin() + i1, [&](int32_t a, int32_t b) { return colour[a] < colour[b]; });
+        for (int32_t l : touched) used[l] = 0ull;
+        touched.clear();
+        // (2) positions: full groups of NW visits of one class; the remainders of all classes are packed together
+        // into extra positions (taken alternately from the two ends of the classes, i.e. from far-apart regions)
+        int32_t K = 0;
+        std::vector<int32_t> overflow;
+        int flip = 0;
+        for (auto& cl : classes) {
+          const int32_t n = (int32_t)cl.size();
+          int32_t rem = n % NW;
+          if (rem * 4 >= NW * 3) rem = 0;  // nearly a full position: keep it whole
+          const int32_t b = (flip & 1) ? rem : 0, e = (flip & 1) ? n : n - rem;
+          if (rem) ++flip;
+          for (int32_t k = 0; k < n; ++k)
+            if (k < b || k >= e) overflow.push_back(cl[k]);
+          for (int32_t k = b; k < e; ++k) { colour[cl[k]] = K + (k - b) / NW; worker[cl[k]] = (k - b) % NW; }
+          K += (e - b + NW - 1) / NW;
+        }
+        {
+          std::vector<int32_t> count(64, 0);
+          const int32_t K0 = K;
+          for (int32_t v : overflow) {
+            const uint64_t m = owned_mask(v);
+            int32_t col = 0;
+            while (col < 64 && ((m >> col & 1ull) || count[col] >= NW)) ++col;
+            if (K0 + col >= 64 || col >= 64) { cleanup(); why = 4; return false; }
+            colour[v] = K0 + col; worker[v] = count[col]++;
+            K = std::max(K, K0 + col + 1);
+            mark(v, col);
+          }
+          for (int32_t l : touched) used[l] = 0ull;
+        }
+        n_pos[st] = K;
+        std::stable_sort(idx.begin() + i0, idx.begin() + i1, [&](int32_t a, int32_t b) {
+          return colour[a] != colour[b] ? colour[a] < colour[b] : worker[a] < worker[b];
+        });
         i0 = i1;
       }
       order.swap(idx);
@@ -258,7 +309,8 @@ struct Builder {
       for (int a = 0; a < nn; ++a) { const int32_t l = local[c[a]]; state_end[l] = std::max(state_end[l], m); }
     }
 
-    // ---- state slots: a slot read by the flush after step t may be reloaded for a node first used at step >= t+2
+    // ---- state slots: a slot last read in step t (visit or flush) may be reloaded for a node first used at step >= t+3
+    // (the state of step s+2 is staged while step s is being visited and step s-1 flushed)
     std::vector<int32_t> slot(n_tile_nodes, -1);
     {
       std::vector<std::vector<int32_t>> by_first(S), release(S + 3);
@@ -275,7 +327,7 @@ struct Builder {
           slot[l] = sl;
           ++live;
           T.max_slots = std::max(T.max_slots, live);
-          if (state_end[l] + 2 < S + 3) release[std::min(state_end[l] + 2, S + 2)].push_back(sl);
+          release[std::min(state_end[l] + 3, S + 2)].push_back(sl);  // staged two steps ahead of its first visit
         }
       }
     }
@@ -293,8 +345,16 @@ struct Builder {
       return (int32_t)(std::lower_bound(nb, ne, gid) - nb);
     };
     std::vector<int32_t> blk_slot(base[n_owned], -1);
-    T.visits.resize(nvis);
-    T.steps.assign(S, StepDesc{0, 0, 0, 0, 0, 0, 0, 0});
+    n_pos.resize(S, 0);  // S may have grown by the trailing flush-only step
+    T.steps.assign(S, StepDesc{0, 0, 0, 0, 0, 0, 0, 0, 0, {0, 0, 0}});
+    {
+      int32_t g = 0;
+      for (int32_t st = 0; st < S; ++st) { T.steps[st].visit_begin = g; T.steps[st].n_pos = n_pos[st]; g += NW * n_pos[st]; }
+      VisitRec8 empty;
+      std::memset(&empty, 0xFF, sizeof empty);  // ln = 0xFFFF: no visit at this grid position
+      T.visits.assign((size_t)g, empty);
+    }
+    T.n_real_visits = (int32_t)nvis;
     {
       std::vector<std::vector<int32_t>> release(S + 3);
       std::vector<int32_t> free_blocks;
@@ -306,11 +366,10 @@ struct Builder {
         while (cur_step < s) {
           ++cur_step;
           for (int32_t b : release[cur_step]) { free_blocks.push_back(b); --live; }
-          T.steps[cur_step].visit_begin = (int32_t)o;
         }
         T.steps[s].n_visits++;
         const int32_t* c = conn + (int64_t)elems[order[o]] * nn;
-        VisitRec8& V = T.visits[o];
+        VisitRec8& V = T.visits[(size_t)T.steps[s].visit_begin + (size_t)worker[order[o]] * n_pos[s] + colour[order[o]]];
         int32_t ll[8];
         for (int a = 0; a < nn; ++a) {
           ll[a] = local[c[a]];
@@ -348,7 +407,6 @@ struct Builder {
             out = (uint16_t)(e | (uint16_t)blk_slot[blk]);
           }
       }
-      while (cur_step < S - 1) { ++cur_step; T.steps[cur_step].visit_begin = (int32_t)nvis; }
     }
 
     // ---- loads and flush rows per step ------------------------------------------------------------------------------
@@ -453,6 +511,7 @@ std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32
   plan.lim = lim;
   if (pat.nn != 8) return "streaming plan: HEX8 only";
   if (lim.arena_blocks < 64 || lim.arena_blocks > (int)kFlushNoBlock - 1) return "arena size out of range";
+  if (lim.n_workers < 1 || lim.n_workers > 64) return "worker count out of range";
   Builder B(pat, xyz, conn, diag_elem, lim);
   constexpr int nn = 8;
 
@@ -500,7 +559,7 @@ std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32
     const double cap = 1.03 * lim.arena_blocks;
     for (int a = 1; a <= 24; ++a)
       for (int b = a; b <= 24; ++b) {
-        if (blocks(a, b) > cap || (a + 2) * (b + 2) * 4 > lim.max_slots) continue;
+        if (blocks(a, b) > cap || (a + 2) * (b + 2) * 5 > lim.max_slots) continue;
         if (a * b > mu * mv || (a * b == mu * mv && b - a < mv - mu)) { mu = a; mv = b; }
       }
     if (const char* ev = std::getenv("MASTB200_PLAN_COLS")) {
@@ -610,7 +669,7 @@ std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32
   // ---- concatenate; tiles ordered by descending cost for the dynamic scheduler -----------------------------------------
   std::vector<TileOut*> all;
   for (auto& s : built) for (auto& t : s) all.push_back(&t);
-  std::stable_sort(all.begin(), all.end(), [](const TileOut* a, const TileOut* b) { return a->visits.size() > b->visits.size(); });
+  std::stable_sort(all.begin(), all.end(), [](const TileOut* a, const TileOut* b) { return a->n_real_visits > b->n_real_visits; });
   size_t n_steps = 0, n_vis = 0, n_fr = 0, n_fe = 0, n_ld = 0;
   for (const TileOut* t : all) {
     n_steps += t->steps.size(); n_vis += t->visits.size(); n_fr += t->frows.size(); n_fe += t->fent.size(); n_ld += t->loads.size();
@@ -622,7 +681,7 @@ std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32
   for (TileOut* t : all) {
     TileDesc td;
     td.step_begin = (int32_t)plan.steps.size(); td.n_steps = (int32_t)t->steps.size();
-    td.n_visits = (int32_t)t->visits.size(); td.n_owned = t->n_owned;
+    td.n_visits = t->n_real_visits; td.n_owned = t->n_owned;
     const int32_t v0 = (int32_t)plan.visits.size(), l0 = (int32_t)plan.loads.size(), f0 = (int32_t)plan.flush_rows.size(),
                   e0 = (int32_t)plan.flush_ent.size();
     for (StepDesc sd : t->steps) {

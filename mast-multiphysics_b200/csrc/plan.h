@@ -8,8 +8,9 @@
 //
 // Device timeline the lifetimes below are planned for (sweep_hex8.cu): the flush of step s runs concurrently with
 // the visits of step s+1; the visits of step s+2 start only after it has finished.  Hence a pair block whose last
-// reader is the flush of step t may be re-initialised by visits of step >= t+2, and a state slot last read in
-// step t (visit or flush) may be reloaded for a node first visited in step >= t+2.
+// reader is the flush of step t may be re-initialised by visits of step >= t+2.  Nodal state is staged two steps
+// ahead (state of step s+2 while step s is visited), so a state slot last read in step t (visit or flush) may be
+// reloaded for a node first visited in step >= t+3.
 //
 // Shared-memory accumulators are kept per unordered node pair {A,B} ("pair block", 9 doubles of
 // S_AB = sum_q w_q grad N_A (x) grad N_B; S_BA = S_AB^T, so one block serves rows A and B).  A pair block lives
@@ -17,10 +18,12 @@
 // by the planner, so a strip only ever holds about two fronts of pairs no matter how long it is.  The same
 // holds for the staged nodal state (coordinates, solution, ...), which lives in planner-assigned "state slots".
 //
-// Ordering: visits of a strip are totally ordered (step, colour, element id).  rank[a] of a visit is the number
-// of earlier visits of the strip touching owned node a; the device adds into the pairs of node a only once the
-// node's counter equals rank[a], which fixes the summation order into every CSR entry (deterministic,
-// independent of scheduling) without CTA-wide barriers inside a step.
+// Ordering: the visits of a step are laid out on a grid of n_workers (compute warps) x positions; visits at the same
+// position share no owned node.  The accumulation order is (step, position, worker): rank[a] of a visit is the
+// number of earlier visits of the strip touching owned node a; the device adds into the pairs of node a only once
+// the node's counter equals rank[a], which fixes the summation order into every CSR entry (deterministic,
+// independent of scheduling) without CTA-wide barriers inside a step.  Each warp walks its own row of the grid,
+// so a visit only waits for visits at earlier positions, which the other warps have normally already finished.
 //
 // Everything here is integer bookkeeping built once per mesh, like libMesh's sparsity pattern /
 // PETSc preallocation that the reference relies on (nonlinear_implicit_assembly.cpp:182-183).
@@ -40,15 +43,18 @@ struct TileDesc {       // one strip segment
 };
 
 struct StepDesc {
-  int32_t visit_begin, n_visits;   // visits of the step in accumulation order
+  int32_t visit_begin, n_visits;   // grid of visit records [worker][position] (n_workers x n_pos); n_visits real ones
   int32_t load_begin, n_loads;     // node states that must be resident before the step's visits start
   int32_t flush_begin, n_flush;    // rows written after the step
   int32_t fent_begin, n_fent;      // flush entries of those rows
+  int32_t n_pos;                   // positions per worker in this step
+  int32_t pad[3];
 };
+static_assert(sizeof(StepDesc) == 48, "StepDesc must be 48 bytes");
 
 // One element visit of a HEX8 strip, 96 bytes (a chunk of 4 visits = 3 coalesced 4-byte loads per lane).
 struct alignas(16) VisitRec8 {
-  uint16_t ln[8];     // state slots of the element's nodes (libMesh node order)
+  uint16_t ln[8];     // state slots of the element's nodes (libMesh node order); ln[0] == 0xFFFF: empty grid position
   uint8_t rank[8];    // accumulation rank per node; 0xFF: node not owned by the strip
   uint16_t pair[36];  // local node pairs (a<=b), index a*(15-a)/2+b: kPairNone, or
                       // bits 0-11 arena block, bit 12: stored block is S_(b,a) (transposed), bit 13: first touch (store, don't add)
@@ -85,6 +91,7 @@ struct PlanLimits {
   int32_t max_slots;        // node state slots
   int32_t flush_buf_bytes;  // per-step flush records staged in shared memory
   int32_t sm_count;         // for the tile count heuristic
+  int32_t n_workers;        // compute warps of the sweep kernel: rows of the per-step visit grid
 };
 
 struct Pattern {
@@ -110,7 +117,7 @@ struct StreamPlan {
   std::vector<uint32_t> flush_ent;
   std::vector<LoadRec> loads;
   int32_t max_live_blocks = 0, max_live_slots = 0;
-  int64_t n_visits() const { return (int64_t)visits.size(); }
+  int64_t n_visits() const { int64_t n = 0; for (const TileDesc& t : tiles) n += t.n_visits; return n; }
   int64_t bytes() const;
 };
 

@@ -7,7 +7,7 @@
 // (sensitivity_assemble, nonlinear_implicit_assembly.cpp:515-686, for all nodal-density DVs at once).
 //
 // One persistent CTA per SM walks strips of the mesh (plan.h) front by front.  The CTA is warp-specialised:
-//   12 compute warps take chunks of 4 element visits in plan order.
+//   12 compute warps each walk their own row of the plan's per-step visit grid, four visits at a time.
 //     geometry phase : one lane per (element, quadrature point) builds J, its inverse and the weight
 //                      w = JxW*E(rho_q) and stages them (10 doubles) in shared memory.
 //     matrix phase   : all 32 lanes on one element, lane = (node a, quadrature points q4 and q4+4).  The lane forms
@@ -23,8 +23,9 @@
 //              512-528, modulus folded into w), the per-element Dirichlet semantics of libMesh's
 //              constrain_element_matrix_and_vector (row/column zeroed, diagonal = number of adjacent elements, rhs
 //              zeroed), the internal force f_a = sum_b K_ab u_b (linear strain) and one store of every CSR value to
-//              HBM.  K_e is never stored.  They also stage the nodal state two steps ahead.
-//   The two groups meet only at named barriers (visits of step s done -> flush s; flush s done -> visits s+2).
+//              HBM.  K_e is never stored.
+//   1 staging warp fetches flush records, nodal state and step descriptors one to three steps ahead.
+//   The groups meet only at named barriers (visits of step s done -> flush s; flush s done -> visits s+2).
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -34,9 +35,12 @@ namespace mastb200 {
 
 namespace {
 
-constexpr int NC = 12;               // compute warps
-constexpr int NF = 4;                // flush / staging warps
-constexpr int WARPS = NC + NF;
+#ifndef MASTB200_NC
+#define MASTB200_NC 11
+#endif
+constexpr int NC = MASTB200_NC;      // compute warps (11 + 4 + 1 = 16 warps x 128 registers fill the register file)
+constexpr int NF = 4;                // flush warps
+constexpr int WARPS = NC + NF + 1;   // + one staging warp
 constexpr int THREADS = WARPS * 32;
 constexpr int QS_PLAIN = 10;         // doubles staged per (element, qp): inv[3][3], w
 constexpr int QS_AUX = 14;           // + pth, s, pad (stride of 28 words keeps the 128-bit stores conflict-free)
@@ -45,9 +49,9 @@ constexpr int REC_WORDS = 24;        // sizeof(VisitRec8) / 4
 constexpr double GP = 0.57735026918962576451;
 
 // named barriers (0 is __syncthreads)
-constexpr int BAR_VISITS = 1;        // +parity: visits of step s done          (compute arrive, flush sync)
-constexpr int BAR_FLUSH = 3;         // +parity: flush of step s done, state of step s+2 staged (flush arrive, compute sync)
-constexpr int BAR_FGROUP = 5;        // flush warps among themselves
+constexpr int BAR_VISITS = 1;        // +parity: visits of step s done, its flush records staged (compute, stager arrive; flush sync)
+constexpr int BAR_FLUSH = 3;         // +parity: flush of step s done, state of step s+2 staged (flush, stager arrive; compute sync)
+constexpr int BAR_FDONE = 5;         // +parity: flush of step s done (flush arrive; stager sync)
 
 __device__ __forceinline__ void bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
@@ -70,8 +74,8 @@ struct Lay {
   static constexpr int QS = AUX ? QS_AUX : QS_PLAIN;
   static constexpr int STAGE_WARP = 4 * 8 * QS * 8;   // bytes staged per compute warp: 4 elements x 8 qps
   static constexpr int SMEM_TOTAL = 232448;            // sm_100: 227 KB opt-in per CTA
-  static constexpr int FIXED = MS * 48 + (AUX ? MS * (24 + 8 + 8 + 8 * EXTRA) : 0) + NC * STAGE_WARP + kFlushBufBytes +
-                               NC * 4 * REC_WORDS * 4 + MS * 8 + 4 * 32 + 16 + MS;
+  static constexpr int FIXED = MS * 48 + (AUX ? MS * (24 + 8 + 8 + 8 * EXTRA) : 0) + NC * STAGE_WARP + 2 * kFlushBufBytes +
+                               NC * 4 * REC_WORDS * 4 + MS * 8 + 4 * 48 + 16 + MS;
   static constexpr int ARENA_RAW = ((SMEM_TOTAL - FIXED) / 72) & ~1;
   static constexpr int ARENA_BLOCKS = ARENA_RAW > 4094 ? 4094 : ARENA_RAW;
   static constexpr int O_XYZ = ARENA_BLOCKS * 72;
@@ -82,11 +86,11 @@ struct Lay {
   static constexpr int O_EX = O_T + MS * 8;
   static constexpr int O_STAGE = AUX ? O_EX + MS * 8 * EXTRA : O_ADJ;
   static constexpr int O_FBUF = O_STAGE + NC * STAGE_WARP;
-  static constexpr int O_REC = O_FBUF + kFlushBufBytes;
+  static constexpr int O_REC = O_FBUF + 2 * kFlushBufBytes;
   static constexpr int O_GID = O_REC + NC * 4 * REC_WORDS * 4;
   static constexpr int O_CNT = O_GID + MS * 4;
   static constexpr int O_SD = O_CNT + MS * 4;
-  static constexpr int O_MISC = O_SD + 4 * 32;
+  static constexpr int O_MISC = O_SD + 4 * 48;
   static constexpr int O_CM = O_MISC + 16;
   static constexpr int TOTAL = (O_CM + MS + 15) & ~15;
   static_assert(TOTAL <= SMEM_TOTAL, "shared-memory layout exceeds 227 KB");
@@ -102,13 +106,13 @@ struct Smem {
   double* T;       // aux
   double* extras;  // aux
   double* stage;
-  unsigned char* fbuf;
+  unsigned char* fbuf;   // two buffers of kFlushBufBytes (step parity)
   uint32_t* rec;   // per compute warp: the 4 visit records of the current chunk
   int32_t* gid;
   int32_t* cnt;    // per slot: number of element contributions accumulated so far
   uint8_t* cm;
   StepDesc* sd;    // ring of 4
-  int* misc;       // [0..1] chunk dispensers (step parity), [2] current tile
+  int* misc;       // [0] current tile
 };
 
 template <bool AUX>
@@ -406,13 +410,13 @@ __device__ __forceinline__ void load_states(const SweepParams& p, const Smem& sm
   }
 }
 
-// flush records of one step -> shared memory (by `nthr` threads)
-__device__ __forceinline__ void load_flush_records(const SweepParams& p, const Smem& sm, const StepDesc& sd, int t, int nthr) {
+// flush records of one step -> shared memory buffer `buf` (by `nthr` threads)
+__device__ __forceinline__ void load_flush_records(const SweepParams& p, unsigned char* buf, const StepDesc& sd, int t, int nthr) {
   const uint4* src_r = reinterpret_cast<const uint4*>(p.flush_rows + sd.flush_begin);
-  uint4* dst_r = reinterpret_cast<uint4*>(sm.fbuf);
+  uint4* dst_r = reinterpret_cast<uint4*>(buf);
   for (int k = t; k < sd.n_flush * 2; k += nthr) dst_r[k] = src_r[k];
   const uint4* src_e = reinterpret_cast<const uint4*>(p.flush_ent + sd.fent_begin);
-  uint4* dst_e = reinterpret_cast<uint4*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
+  uint4* dst_e = reinterpret_cast<uint4*>(buf + (size_t)sd.n_flush * sizeof(FlushRow));
   for (int k = t; k < (sd.n_fent + 3) / 4; k += nthr) dst_e[k] = src_e[k];
 }
 
@@ -420,9 +424,9 @@ __device__ __forceinline__ void load_flush_records(const SweepParams& p, const S
 // four rows per warp at a time, eight lanes per row; a lane walks the row's neighbour blocks c = l8, l8+8, ...
 template <bool AUX>
 __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm, const Flags& fl, const StepDesc& sd,
-                                           int fwarp, int lane) {
-  const FlushRow* rows = reinterpret_cast<const FlushRow*>(sm.fbuf);
-  const uint32_t* ents = reinterpret_cast<const uint32_t*>(sm.fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
+                                           const unsigned char* fbuf, int fwarp, int lane) {
+  const FlushRow* rows = reinterpret_cast<const FlushRow*>(fbuf);
+  const uint32_t* ents = reinterpret_cast<const uint32_t*>(fbuf + (size_t)sd.n_flush * sizeof(FlushRow));
   const int sub = lane >> 3, l8 = lane & 7;
   for (int rbase = fwarp * 4; rbase < sd.n_flush; rbase += NF * 4) {
     const int r = rbase + sub;
@@ -538,7 +542,11 @@ __device__ __forceinline__ void flush_rows(const SweepParams& p, const Smem& sm,
 }
 
 template <bool AUX>
+#ifdef MASTB200_MAXNREG
+__global__ void __maxnreg__(MASTB200_MAXNREG) hex8_sweep_kernel(const SweepParams p) {
+#else
 __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParams p) {
+#endif
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int QS = Lay<AUX>::QS;
   const Smem sm = make_smem<AUX>(smem_raw);
@@ -549,7 +557,8 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
   fl.S = fl.J || fl.R;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  int& s_tile = sm.misc[2];
+  int& s_tile = sm.misc[0];
+  constexpr int SDW = sizeof(StepDesc) / 4;
 
   for (;;) {
     if (tid == 0) s_tile = atomicAdd(p.tile_counter, 1);
@@ -558,98 +567,87 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
     if (tile >= p.n_tiles) break;
     const TileDesc td = p.tiles[tile];
     // prologue: descriptors of the first three steps, state of the first two, flush records of the first
-    if (tid < 24 && (tid >> 3) < td.n_steps)
-      reinterpret_cast<int*>(&sm.sd[tid >> 3])[tid & 7] = reinterpret_cast<const int*>(p.steps + td.step_begin + (tid >> 3))[tid & 7];
-    if (tid < 2) sm.misc[tid] = 0;
+    if (tid < 3 * SDW && tid / SDW < td.n_steps)
+      reinterpret_cast<int*>(sm.sd)[tid] = reinterpret_cast<const int*>(p.steps + td.step_begin)[tid];
     __syncthreads();
     load_states<AUX>(p, sm, sm.sd[0].load_begin, sm.sd[0].n_loads, tid, THREADS);
     if (td.n_steps > 1) load_states<AUX>(p, sm, sm.sd[1].load_begin, sm.sd[1].n_loads, tid, THREADS);
-    load_flush_records(p, sm, sm.sd[0], tid, THREADS);
+    load_flush_records(p, sm.fbuf, sm.sd[0], tid, THREADS);
     __syncthreads();
 
     if (warp < NC) {
       // ================================ compute warps ================================
+      // Warp w walks row w of every step's visit grid, four positions at a time; the records of the next group (of this
+      // or the next step) are prefetched into registers while the current one is processed.
       const int el = lane >> 3, q = lane & 7;
       const LaneConst lc = make_lane_const(lane);
       double* my_stage = sm.stage + warp * (4 * 8 * QS);
       uint32_t* my_rec = sm.rec + warp * 4 * REC_WORDS;
+      uint32_t r0 = 0, r1 = 0, r2 = 0;
+      int pf_s = -1, pf_g = -1;
+      auto fetch = [&](const StepDesc& d, int s_, int g) {
+        const int nw = min(4, d.n_pos - g) * REC_WORDS;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.visits + d.visit_begin + (int64_t)warp * d.n_pos + g);
+        r0 = r1 = r2 = 0;
+        if (lane < nw) r0 = src[lane];
+        if (lane + 32 < nw) r1 = src[lane + 32];
+        if (lane + 64 < nw) r2 = src[lane + 64];
+        pf_s = s_; pf_g = g;
+      };
       for (int s = 0; s < td.n_steps; ++s) {
         if (s >= 2) bar_sync(BAR_FLUSH + (s & 1), THREADS);  // flush of step s-2 done, state of step s staged
         const StepDesc sd = sm.sd[s & 3];
-        int& s_next = sm.misc[s & 1];
-        // warps take chunks of consecutive visits in plan order: 4 visits while more than a round of work is left, then
-        // the remainder split evenly over the warps so that the step ends without a tail; the records of the next chunk
-        // are prefetched into registers while the current one is processed
-        const int full = sd.n_visits / (4 * NC) * NC;              // chunks of 4
-        const int rem = sd.n_visits - 4 * full;
-        const int base = rem / NC, extra = rem - base * NC;        // last round: `extra` chunks of base+1, then base
-        const int n_chunks = full + (base ? NC : extra);
-        const uint32_t* recs = reinterpret_cast<const uint32_t*>(p.visits + sd.visit_begin);
-        auto chunk_range = [&](int c, int& begin, int& size) {
-          if (c < full) { begin = 4 * c; size = 4; }
-          else { const int j = c - full; begin = 4 * full + j * base + min(j, extra); size = base + (j < extra ? 1 : 0); }
-        };
-        int c = 0;
-        if (lane == 0) c = atomicAdd(&s_next, 1);
-        c = __shfl_sync(0xffffffffu, c, 0);
-        uint32_t r0 = 0, r1 = 0, r2 = 0;
-        int nvis = 0, nvis_next = 0;
-        if (c < n_chunks) {
-          int b0;
-          chunk_range(c, b0, nvis);
-          const int nw = nvis * REC_WORDS;
-          const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
-          if (lane < nw) r0 = src[lane];
-          if (lane + 32 < nw) r1 = src[lane + 32];
-          if (lane + 64 < nw) r2 = src[lane + 64];
-        }
-        while (c < n_chunks) {
+        for (int g0 = 0; g0 < sd.n_pos; g0 += 4) {
+          const int nvis = min(4, sd.n_pos - g0);
+          if (pf_s != s || pf_g != g0) fetch(sd, s, g0);
           my_rec[lane] = r0; my_rec[lane + 32] = r1; my_rec[lane + 64] = r2;
           __syncwarp();
-          int cn = 0;
-          if (lane == 0) cn = atomicAdd(&s_next, 1);
-          cn = __shfl_sync(0xffffffffu, cn, 0);
-          if (cn < n_chunks) {
-            int b0;
-            chunk_range(cn, b0, nvis_next);
-            const int nw = nvis_next * REC_WORDS;
-            const uint32_t* src = recs + (int64_t)b0 * REC_WORDS;
-            r0 = r1 = r2 = 0;
-            if (lane < nw) r0 = src[lane];
-            if (lane + 32 < nw) r1 = src[lane + 32];
-            if (lane + 64 < nw) r2 = src[lane + 64];
-          }
+          if (g0 + 4 < sd.n_pos) fetch(sd, s, g0 + 4);
+          else if (s + 1 < td.n_steps && sm.sd[(s + 1) & 3].n_pos > 0) fetch(sm.sd[(s + 1) & 3], s + 1, 0);
           if (el < nvis) {
             const uint4 pk = *reinterpret_cast<const uint4*>(my_rec + el * REC_WORDS);
-            int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
-                         int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
-            geometry_phase<AUX>(p, sm, fl, ln, q, my_stage + lane * QS);
+            if ((pk.x & 0xffffu) != 0xffffu) {
+              int ln[8] = {int(pk.x & 0xffffu), int(pk.x >> 16), int(pk.y & 0xffffu), int(pk.y >> 16),
+                           int(pk.z & 0xffffu), int(pk.z >> 16), int(pk.w & 0xffffu), int(pk.w >> 16)};
+              geometry_phase<AUX>(p, sm, fl, ln, q, my_stage + lane * QS);
+            }
           }
           __syncwarp();
-          for (int e = 0; e < nvis; ++e)
+          for (int e = 0; e < nvis; ++e) {
+            if ((my_rec[e * REC_WORDS] & 0xffffu) == 0xffffu) continue;  // empty grid position
             element_phase<AUX>(p, sm, fl, lc, my_stage + e * 8 * QS, my_rec + e * REC_WORDS, lane);
+          }
           __syncwarp();
-          c = cn; nvis = nvis_next;
         }
         bar_arrive(BAR_VISITS + (s & 1), THREADS);
       }
-    } else {
-      // ================================ flush / staging warps ================================
-      const int fw = warp - NC, ft = tid - NC * 32;
+    } else if (warp < NC + NF) {
+      // ================================ flush warps ================================
+      const int fw = warp - NC;
       for (int s = 0; s < td.n_steps; ++s) {
-        bar_sync(BAR_VISITS + (s & 1), THREADS);   // every visit of step s has landed (also orders the staging below)
+        bar_sync(BAR_VISITS + (s & 1), THREADS);   // every visit of step s has landed; its flush records are staged
         const StepDesc sd = sm.sd[s & 3];
-        flush_rows<AUX>(p, sm, fl, sd, fw, lane);
-        bar_sync(BAR_FGROUP, NF * 32);             // flush records and freed state slots may be overwritten now
-        if (s + 1 < td.n_steps) load_flush_records(p, sm, sm.sd[(s + 1) & 3], ft, NF * 32);
+        flush_rows<AUX>(p, sm, fl, sd, sm.fbuf + (s & 1) * kFlushBufBytes, fw, lane);
+        if (s + 1 < td.n_steps) bar_arrive(BAR_FDONE + (s & 1), (NF + 1) * 32);
+        if (s + 2 < td.n_steps) bar_arrive(BAR_FLUSH + (s & 1), THREADS);
+      }
+    } else {
+      // ================================ staging warp ================================
+      // everything later steps need from global memory, fetched in the shadow of the visits: at iteration s the flush
+      // records of step s+1, the nodal state of step s+2 and the descriptor of step s+3
+      bar_arrive(BAR_VISITS + 0, THREADS);         // step 0 was staged by the prologue
+      for (int s = 0; s < td.n_steps; ++s) {
+        if (s >= 1) bar_sync(BAR_FDONE + ((s - 1) & 1), (NF + 1) * 32);  // flush of step s-1 done: buffers and slots are free
+        if (s + 1 < td.n_steps) load_flush_records(p, sm.fbuf + ((s + 1) & 1) * kFlushBufBytes, sm.sd[(s + 1) & 3], lane, 32);
         if (s + 2 < td.n_steps) {
           const StepDesc nsd = sm.sd[(s + 2) & 3];
-          load_states<AUX>(p, sm, nsd.load_begin, nsd.n_loads, ft, NF * 32);
-          if (s + 3 < td.n_steps && ft < 8)
-            reinterpret_cast<int*>(&sm.sd[(s + 3) & 3])[ft] = reinterpret_cast<const int*>(p.steps + td.step_begin + s + 3)[ft];
-          if (ft == 0) sm.misc[s & 1] = 0;         // chunk dispenser of step s+2
-          bar_arrive(BAR_FLUSH + (s & 1), THREADS);
+          load_states<AUX>(p, sm, nsd.load_begin, nsd.n_loads, lane, 32);
         }
+        if (s + 3 < td.n_steps && lane < SDW)
+          reinterpret_cast<int*>(&sm.sd[(s + 3) & 3])[lane] = reinterpret_cast<const int*>(p.steps + td.step_begin + s + 3)[lane];
+        __syncwarp();
+        if (s + 1 < td.n_steps) bar_arrive(BAR_VISITS + ((s + 1) & 1), THREADS);
+        if (s + 2 < td.n_steps) bar_arrive(BAR_FLUSH + (s & 1), THREADS);
       }
     }
     __syncthreads();
@@ -678,5 +676,6 @@ cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t str
 }
 
 int hex8_sweep_threads() { return THREADS; }
+int hex8_sweep_workers() { return NC; }
 
 }  // namespace mastb200

@@ -67,7 +67,21 @@ def replay(prob, plan, ctx, X=None, late_flush=True):
                 slot_gid[lr["slot"]] = lr["gid"]; slot_owned[lr["slot"]] = bool(lr["owned"]); cnt[lr["slot"]] = 0
 
         def visits(sd):
-            for v in V[sd["visit_begin"]:sd["visit_begin"] + sd["n_visits"]]:
+            # grid [worker][position]; accumulation order (position, worker); empty positions have ln[0] == 0xFFFF
+            K = int(sd["n_pos"])
+            grid = V[sd["visit_begin"]:sd["visit_begin"] + plan["n_workers"] * K].reshape(plan["n_workers"], K)
+            seq = [grid[w, k] for k in range(K) for w in range(plan["n_workers"]) if grid[w, k]["ln"][0] != 0xFFFF]
+            assert len(seq) == sd["n_visits"]
+            for k in range(K):   # visits at the same position share no owned node
+                seen = set()
+                for w in range(plan["n_workers"]):
+                    v = grid[w, k]
+                    if v["ln"][0] == 0xFFFF:
+                        continue
+                    mine = {int(v["ln"][a]) for a in range(8) if v["rank"][a] != 0xFF}
+                    assert not (mine & seen), "visits at one position share an owned node"
+                    seen |= mine
+            for v in seq:
                 gids = slot_gid[v["ln"]]
                 e = elem_of[tuple(int(g) for g in gids)]
                 assert not diag[e]
@@ -150,19 +164,22 @@ def replay(prob, plan, ctx, X=None, late_flush=True):
         if len(steps) > 1:
             load(steps[1])
         if late_flush:
+            # visits running maximally ahead of the flush; state of step s+2 staged at the top of flush iteration s
             for si, sd in enumerate(steps):
+                if si >= 1:
+                    if si + 1 < len(steps):
+                        load(steps[si + 1])
                 visits(sd)
                 if si >= 1:
                     flush(steps[si - 1])
-                    if si + 1 < len(steps):
-                        load(steps[si + 1])
             flush(steps[-1])
         else:
+            # flush right behind the visits; state staged as early as the device may stage it
             for si, sd in enumerate(steps):
-                visits(sd)
-                flush(sd)
                 if si + 2 < len(steps):
                     load(steps[si + 2])
+                visits(sd)
+                flush(sd)
     # every (non-diagonal) element adjacent to an owned node was visited on behalf of that node
     for n in row_of_node:
         want = {e for e in range(prob.n_elem) if n in prob.conn[e] and not diag[e]} if prob.n_elem < 400 else None

@@ -86,8 +86,12 @@ def test_plan_statistics(built):
         assert P["tiles"]["n_owned"].sum() == 25 ** 3          # every owned node belongs to exactly one strip
         assert P["steps"]["n_flush"].sum() == 25 ** 3          # ... and is written exactly once
         assert np.all(P["steps"]["fent_begin"] % 4 == 0)
-        used = P["visits"]["pair"][P["visits"]["pair"] != 0xFFFF] & 0xFFF
-        assert used.max() < P["arena_blocks"] and P["visits"]["ln"].max() < P["max_slots"]
+        real = P["visits"][P["visits"]["ln"][:, 0] != 0xFFFF]          # the grid has empty positions
+        assert len(real) == P["tiles"]["n_visits"].sum() == P["steps"]["n_visits"].sum()
+        assert len(P["visits"]) == (P["steps"]["n_pos"] * P["n_workers"]).sum()
+        assert len(real) >= 0.7 * len(P["visits"])                     # balanced: few idle grid positions
+        used = real["pair"][real["pair"] != 0xFFFF] & 0xFFF
+        assert used.max() < P["arena_blocks"] and real["ln"].max() < P["max_slots"]
         assert np.all(np.diff(P["tiles"]["n_visits"]) <= 0)   # longest strips first for the dynamic scheduler
 
 
