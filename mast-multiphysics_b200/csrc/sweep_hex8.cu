@@ -384,40 +384,69 @@ __device__ __forceinline__ void element_phase(const SweepParams& p, const Smem& 
 }
 
 // ---- staging of nodal state (loads of one step) by `nthr` threads, this thread being number `t` ---------------
+// The records and then the nodal data of up to four nodes per thread are fetched together so that the two dependent
+// global-memory latencies are paid once per call, not once per node.
 template <bool AUX>
 __device__ __forceinline__ void load_states(const SweepParams& p, const Smem& sm, int begin, int n, int t, int nthr) {
-  for (int i = t; i < n; i += nthr) {
-    const LoadRec lr = p.loads[begin + i];
-    const int n_ = lr.gid, sl = lr.slot;
-    const unsigned cm = p.cmask ? p.cmask[n_] : 0u;
-    sm.gid[sl] = n_;
-    sm.cnt[sl] = 0;
-    sm.cm[sl] = (uint8_t)cm;
+  constexpr int UN = 4;
+  for (int i0 = t; i0 < n; i0 += nthr * UN) {
+    LoadRec lr[UN];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      sm.xyz[sl * 3 + c] = p.xyz[(int64_t)n_ * 3 + c];
-      sm.u[sl * 3 + c] = p.X[(int64_t)n_ * p.nv + c];
+    for (int k = 0; k < UN; ++k) {
+      const int i = i0 + k * nthr;
+      lr[k] = p.loads[begin + min(i, n - 1)];
     }
-    if (AUX) {
-      // constrain_element_vector zeroes constrained rows of dR/dp, i.e. the adjoint never sees them
+    double x[UN][3], u[UN][3], ad[UN][3], rho[UN], T[UN];
+    unsigned cm[UN];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) sm.adj[sl * 3 + c] = (p.adj && !((cm >> c) & 1u)) ? p.adj[(int64_t)n_ * p.nv + c] : 0.;
-      sm.rho[sl] = p.rho ? p.rho[n_] : 1.;
-      sm.T[sl] = p.temperature ? p.temperature[n_] : p.T_const;
+    for (int k = 0; k < UN; ++k) {
+      const int64_t g = lr[k].gid;
+      cm[k] = p.cmask ? p.cmask[g] : 0u;
 #pragma unroll
-      for (int c = 0; c < EXTRA; ++c) sm.extras[sl * EXTRA + c] = 0.;
+      for (int c = 0; c < 3; ++c) { x[k][c] = p.xyz[g * 3 + c]; u[k][c] = p.X[g * p.nv + c]; }
+      if (AUX) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ad[k][c] = p.adj ? p.adj[g * p.nv + c] : 0.;
+        rho[k] = p.rho ? p.rho[g] : 1.;
+        T[k] = p.temperature ? p.temperature[g] : p.T_const;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < UN; ++k) {
+      if (i0 + k * nthr >= n) continue;
+      const int sl = lr[k].slot;
+      sm.gid[sl] = lr[k].gid;
+      sm.cnt[sl] = 0;
+      sm.cm[sl] = (uint8_t)cm[k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { sm.xyz[sl * 3 + c] = x[k][c]; sm.u[sl * 3 + c] = u[k][c]; }
+      if (AUX) {
+        // constrain_element_vector zeroes constrained rows of dR/dp, i.e. the adjoint never sees them
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm.adj[sl * 3 + c] = ((cm[k] >> c) & 1u) ? 0. : ad[k][c];
+        sm.rho[sl] = rho[k];
+        sm.T[sl] = T[k];
+#pragma unroll
+        for (int c = 0; c < EXTRA; ++c) sm.extras[sl * EXTRA + c] = 0.;
+      }
     }
   }
 }
 
-// flush records of one step -> shared memory buffer `buf` (by `nthr` threads)
+// flush records of one step -> shared memory buffer `buf` (by `nthr` threads), as asynchronous 16-byte copies: all of
+// them are in flight at once; the caller waits with cp_async_wait_all() before publishing the buffer
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 __device__ __forceinline__ void load_flush_records(const SweepParams& p, unsigned char* buf, const StepDesc& sd, int t, int nthr) {
   const uint4* src_r = reinterpret_cast<const uint4*>(p.flush_rows + sd.flush_begin);
   uint4* dst_r = reinterpret_cast<uint4*>(buf);
-  for (int k = t; k < sd.n_flush * 2; k += nthr) dst_r[k] = src_r[k];
+  for (int k = t; k < sd.n_flush * 2; k += nthr) cp_async16(dst_r + k, src_r + k);
   const uint4* src_e = reinterpret_cast<const uint4*>(p.flush_ent + sd.fent_begin);
   uint4* dst_e = reinterpret_cast<uint4*>(buf + (size_t)sd.n_flush * sizeof(FlushRow));
-  for (int k = t; k < (sd.n_fent + 3) / 4; k += nthr) dst_e[k] = src_e[k];
+  for (int k = t; k < (sd.n_fent + 3) / 4; k += nthr) cp_async16(dst_e + k, src_e + k);
 }
 
 // ---- flush: S -> K, Dirichlet semantics, f = K u, one store of every CSR value of the finished rows --------------
@@ -573,6 +602,7 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
     load_states<AUX>(p, sm, sm.sd[0].load_begin, sm.sd[0].n_loads, tid, THREADS);
     if (td.n_steps > 1) load_states<AUX>(p, sm, sm.sd[1].load_begin, sm.sd[1].n_loads, tid, THREADS);
     load_flush_records(p, sm.fbuf, sm.sd[0], tid, THREADS);
+    cp_async_wait_all();
     __syncthreads();
 
     if (warp < NC) {
@@ -645,6 +675,7 @@ __global__ void __launch_bounds__(THREADS, 1) hex8_sweep_kernel(const SweepParam
         }
         if (s + 3 < td.n_steps && lane < SDW)
           reinterpret_cast<int*>(&sm.sd[(s + 3) & 3])[lane] = reinterpret_cast<const int*>(p.steps + td.step_begin + s + 3)[lane];
+        cp_async_wait_all();
         __syncwarp();
         if (s + 1 < td.n_steps) bar_arrive(BAR_VISITS + ((s + 1) & 1), THREADS);
         if (s + 2 < td.n_steps) bar_arrive(BAR_FLUSH + (s & 1), THREADS);
