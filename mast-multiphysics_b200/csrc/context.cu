@@ -103,6 +103,20 @@ struct mastb200_context {
     }
   } dplan[2];
   int last_plan = 0;
+  // device plan of the gather (QUAD4 heat) and coloured-scatter (HEX27) sweeps
+  struct GenericPlan {
+    bool built = false;
+    DevBuf<int32_t> conn, n2e, nbr, node_row, color_elems;
+    DevBuf<int64_t> n2e_ptr, nbr_ptr;
+    DevBuf<uint8_t> diag, posmap;
+    DevBuf<double> tab;
+    std::vector<int32_t> color_ptr;
+    void reset() {
+      built = false; color_ptr.clear();
+      conn.release(); n2e.release(); nbr.release(); node_row.release(); color_elems.release();
+      n2e_ptr.release(); nbr_ptr.release(); diag.release(); posmap.release(); tab.release();
+    }
+  } gplan;
   int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
   DevBuf<int32_t> d_tile_counter, d_owned_nodes;
   DevBuf<uint8_t> d_cmask;
@@ -250,14 +264,145 @@ int check_ready(mastb200_context* ctx) {
   return MASTB200_OK;
 }
 
+
+// HEX27 shape tables (libMesh node order, 3x3x3 Gauss rule, xi fastest): N[q][b], dN[q][b][r], w[q]
+void hex27_tables(std::vector<double>& tab) {
+  static const int8_t C[27][3] = {
+      {-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1},
+      {0, -1, -1},  {1, 0, -1},  {0, 1, -1}, {-1, 0, -1}, {-1, -1, 0}, {1, -1, 0}, {1, 1, 0}, {-1, 1, 0},
+      {0, -1, 1},   {1, 0, 1},   {0, 1, 1},  {-1, 0, 1},  {0, 0, -1},  {0, -1, 0}, {1, 0, 0}, {0, 1, 0},
+      {-1, 0, 0},   {0, 0, 1},   {0, 0, 0}};
+  auto l = [](int c, double x) { return c < 0 ? 0.5 * x * (x - 1.) : c > 0 ? 0.5 * x * (x + 1.) : (1. - x * x); };
+  auto dl = [](int c, double x) { return c < 0 ? x - 0.5 : c > 0 ? x + 0.5 : -2. * x; };
+  const double gp[3] = {-0.77459666924148337704, 0., 0.77459666924148337704};
+  const double gw[3] = {5. / 9., 8. / 9., 5. / 9.};
+  tab.assign(27 * 27 * 4 + 27, 0.);
+  for (int q = 0; q < 27; ++q) {
+    const double xi = gp[q % 3], eta = gp[(q / 3) % 3], zeta = gp[q / 9];
+    for (int b = 0; b < 27; ++b) {
+      const double li = l(C[b][0], xi), lj = l(C[b][1], eta), lk = l(C[b][2], zeta);
+      tab[q * 27 + b] = li * lj * lk;
+      double* d = &tab[27 * 27 + (q * 27 + b) * 3];
+      d[0] = dl(C[b][0], xi) * lj * lk;
+      d[1] = li * dl(C[b][1], eta) * lk;
+      d[2] = li * lj * dl(C[b][2], zeta);
+    }
+    tab[27 * 27 * 4 + q] = gw[q % 3] * gw[(q / 3) % 3] * gw[q / 9];
+  }
+}
+
+int ensure_generic_plan(mastb200_context* ctx) {
+  mastb200_context::GenericPlan& G = ctx->gplan;
+  if (G.built || ctx->planning_only) return MASTB200_OK;
+  const Pattern& P = ctx->pat;
+  CU(G.conn.upload(ctx->conn, ctx->stream));
+  CU(G.nbr_ptr.upload(P.nbr_ptr, ctx->stream));
+  if (ctx->has_diag) CU(G.diag.upload(ctx->diag_elem, ctx->stream));
+  if (ctx->elem_type == MASTB200_QUAD4) {
+    for (int64_t r = 0; r < P.n_owned; ++r)
+      if (P.nbr_ptr[r + 1] - P.nbr_ptr[r] > kGatherMaxNbr)
+        return ctx->fail(MASTB200_ERR_PLAN, "plan: a node has more than %d neighbours", kGatherMaxNbr);
+    CU(G.nbr.upload(P.nbr, ctx->stream));
+    CU(G.n2e_ptr.upload(P.n2e_ptr, ctx->stream));
+    CU(G.n2e.upload(P.n2e, ctx->stream));
+  } else {  // HEX27
+    std::vector<int32_t> color_elems;
+    std::string e = build_coloring(P, ctx->conn.data(), G.color_ptr, color_elems);
+    if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+    std::vector<uint8_t> posmap;
+    e = build_posmap(P, ctx->conn.data(), posmap);
+    if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+    std::vector<double> tab;
+    hex27_tables(tab);
+    CU(G.color_elems.upload(color_elems, ctx->stream));
+    CU(G.posmap.upload(posmap, ctx->stream));
+    CU(G.node_row.upload(P.node_row, ctx->stream));
+    CU(G.tab.upload(tab, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  G.built = true;
+  return MASTB200_OK;
+}
+
+// QUAD4 heat conduction (row gather) and HEX27 elasticity (coloured DMMA scatter)
+int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
+  int rc;
+  const bool heat = ctx->elem_type == MASTB200_QUAD4;
+  if (heat && ctx->nv != 1) return ctx->fail(MASTB200_ERR_ARG, "QUAD4 heat conduction needs nv = 1");
+  if (!heat && ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX27 elasticity needs nv = 3 or 6");
+  if (!heat && ctx->mat.nonlinear_strain)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain has no device sweep yet");
+  if ((rc = ensure_generic_plan(ctx))) return rc;
+  mastb200_context::GenericPlan& G = ctx->gplan;
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const size_t nnz = (size_t)plan_nnz(ctx);
+  const double* dX = nullptr;
+  double *dR = nullptr, *dJ = nullptr;
+  if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
+  if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
+  const mastb200_material& m = ctx->mat;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (heat) {
+    if (dR && ctx->has_ghosts) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    GatherParams p;
+    p.n_owned = ctx->pat.n_owned; p.owned_nodes = ctx->d_owned_nodes.p;
+    p.nbr_ptr = G.nbr_ptr.p; p.nbr = G.nbr.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p; p.conn = G.conn.p;
+    p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+    p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+    p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
+    p.k0 = m.k0; p.k_beta = m.k_beta; p.thickness = m.thickness; p.heat_source = m.heat_source; p.k_of_T = m.k_of_T;
+    CU(launch_quad4_heat(p, ctx->stream));
+    ctx->launches++;
+  } else {
+    // the coloured scatter accumulates: R and J start from zero (nonlinear_implicit_assembly.cpp:81-82)
+    if (dR) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
+    if (dJ) CU(cudaMemsetAsync(dJ, 0, nnz * sizeof(double), ctx->stream));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    Hex27Params p;
+    p.conn = G.conn.p; p.posmap = G.posmap.p; p.node_row = G.node_row.p; p.nbr_ptr = G.nbr_ptr.p; p.tab = G.tab.p;
+    p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+    p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+    p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
+    p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+    p.temperature = (ctx->thermal && ctx->T_nodal) ? (ctx->T_ext ? ctx->T_ext : ctx->d_T.p) : nullptr;
+    p.E0 = m.E0;
+    p.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu);
+    p.mu1 = 1. / 2. / (1. + m.nu);
+    p.rho_min = m.rho_min; p.penalty = m.penalty;
+    p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
+    p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
+    p.nv = ctx->nv; p.thermal = ctx->thermal ? 1 : 0;
+    const int nc = (int)G.color_ptr.size() - 1;
+    for (int c = 0; c < nc; ++c) {
+      p.elems = G.color_elems.p + G.color_ptr[c];
+      p.n_elems = G.color_ptr[c + 1] - G.color_ptr[c];
+      CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
+      ctx->launches++;
+    }
+  }
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->last_R = dR;
+  if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
+  if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
 // the common sweep: any of R, J, G may be null
 int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G, double* R, double* J) {
   int rc = check_ready(ctx);
   if (rc) return rc;
   if (!X) return ctx->fail(MASTB200_ERR_ARG, "X is NULL");
   if (G && !adj) return ctx->fail(MASTB200_ERR_ARG, "adjoint vector is NULL");
-  if (ctx->elem_type != MASTB200_HEX8)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "element type %d has no device sweep yet", ctx->elem_type);
+  if (ctx->elem_type != MASTB200_HEX8) {
+    if (G) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities: HEX8 only for now");
+    return run_generic_sweep(ctx, X, R, J);
+  }
+  if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX8 elasticity needs nv = 3 or 6");
   if (ctx->mat.nonlinear_strain)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain has no device sweep yet");
   if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
@@ -518,6 +663,7 @@ int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz)
     CU(cudaDeviceGetAttribute(&ctx->max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
   }
   for (auto& D : ctx->dplan) D.reset();
+  ctx->gplan.reset();
   const std::string e = build_pattern(ctx->nn, ctx->n_nodes, ctx->n_elem, ctx->conn.data(),
                                       ctx->owned.empty() ? nullptr : ctx->owned.data(),
                                       ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), ctx->pat);

@@ -23,6 +23,50 @@ int hex8_sweep_threads();
 int hex8_sweep_workers();  // compute warps = rows of the plan's per-step visit grid
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream);
 
+// ---- row-owner gather kernels for small elements (sweep_quad4_heat.cu) ---------------------------------------------
+constexpr int kGatherMaxNbr = 24;      // neighbours per row the gather kernels keep in shared memory
+struct GatherParams {
+  int64_t n_owned = 0;
+  const int32_t* owned_nodes = nullptr;  // [n_owned]
+  const int64_t* nbr_ptr = nullptr;      // node-level CSR of the owned rows
+  const int32_t* nbr = nullptr;
+  const int64_t* n2e_ptr = nullptr;      // node -> adjacent elements (ascending id)
+  const int32_t* n2e = nullptr;
+  const int32_t* conn = nullptr;         // [n_elem][nn]
+  const uint8_t* diag_elem = nullptr;    // [n_elem] or null
+  const uint8_t* cmask = nullptr;        // [n_nodes] or null
+  const double* xyz = nullptr;
+  const double* X = nullptr;
+  double* J = nullptr;
+  double* R = nullptr;
+  double k0 = 0., k_beta = 0., thickness = 1., heat_source = 0.;
+  int32_t k_of_T = 0;
+};
+cudaError_t launch_quad4_heat(const GatherParams& p, cudaStream_t stream);
+
+// ---- HEX27 coloured DMMA sweep (sweep_hex27.cu) -----------------------------------------------------------------------
+struct Hex27Params {
+  const int32_t* elems = nullptr;        // element ids of the colour being swept
+  int32_t n_elems = 0;
+  const int32_t* conn = nullptr;         // [n_elem][27]
+  const uint8_t* posmap = nullptr;       // [n_elem][27][27] position of node b in the neighbour list of node a
+  const int32_t* node_row = nullptr;     // [n_nodes] owned-row index or -1
+  const int64_t* nbr_ptr = nullptr;
+  const double* tab = nullptr;           // N[27][27] (q,b), dN[27][27][3] (q,b,r), w[27]
+  const uint8_t* diag_elem = nullptr;
+  const uint8_t* cmask = nullptr;
+  const double* xyz = nullptr;
+  const double* X = nullptr;
+  const double* rho = nullptr;
+  const double* temperature = nullptr;
+  double* J = nullptr;
+  double* R = nullptr;
+  double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1., alpha_k = 0., T_const = 0., T_ref = 0.;
+  int32_t nv = 3, thermal = 0;
+};
+size_t hex27_sweep_smem_bytes();
+cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t stream);
+
 // SURFACE_PRESSURE side loads gathered per loaded node (loads.cu)
 struct FaceLoadPlan {
   int32_t n_loaded_nodes = 0;

@@ -700,4 +700,58 @@ std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32
   return "";
 }
 
+// ================================================================================================================
+// coloured scatter plan (HEX27)
+// ================================================================================================================
+std::string build_coloring(const Pattern& pat, const int32_t* conn, std::vector<int32_t>& color_ptr,
+                           std::vector<int32_t>& color_elems) {
+  const int nn = pat.nn;
+  std::vector<uint64_t> used(pat.n_nodes, 0);  // colours taken by the elements around each node
+  std::vector<int8_t> color(pat.n_elem, -1);
+  int n_colors = 0;
+  for (int64_t e = 0; e < pat.n_elem; ++e) {
+    const int32_t* c = conn + e * nn;
+    bool any_owned = false;
+    uint64_t m = 0;
+    for (int a = 0; a < nn; ++a) { m |= used[c[a]]; any_owned = any_owned || pat.node_row[c[a]] >= 0; }
+    if (!any_owned) continue;
+    if (m == ~uint64_t(0)) return "more than 64 colours needed";
+    int k = 0;
+    while ((m >> k) & 1u) ++k;
+    color[e] = (int8_t)k;
+    n_colors = std::max(n_colors, k + 1);
+    for (int a = 0; a < nn; ++a) used[c[a]] |= uint64_t(1) << k;
+  }
+  color_ptr.assign(n_colors + 1, 0);
+  for (int64_t e = 0; e < pat.n_elem; ++e)
+    if (color[e] >= 0) color_ptr[color[e] + 1]++;
+  for (int k = 0; k < n_colors; ++k) color_ptr[k + 1] += color_ptr[k];
+  color_elems.resize(color_ptr[n_colors]);
+  std::vector<int32_t> pos(color_ptr.begin(), color_ptr.end() - 1);
+  for (int64_t e = 0; e < pat.n_elem; ++e)
+    if (color[e] >= 0) color_elems[pos[color[e]]++] = (int32_t)e;
+  return "";
+}
+
+std::string build_posmap(const Pattern& pat, const int32_t* conn, std::vector<uint8_t>& posmap) {
+  const int nn = pat.nn;
+  for (int64_t r = 0; r < pat.n_owned; ++r)
+    if (pat.nbr_ptr[r + 1] - pat.nbr_ptr[r] > 255) return "row with more than 255 neighbouring nodes";
+  posmap.assign((size_t)pat.n_elem * nn * nn, 0);
+  parallel_for(pat.n_elem, [&](int64_t b0, int64_t e0, int) {
+    for (int64_t e = b0; e < e0; ++e) {
+      const int32_t* c = conn + e * nn;
+      for (int a = 0; a < nn; ++a) {
+        const int32_t r = pat.node_row[c[a]];
+        if (r < 0) continue;
+        const int32_t* lb = pat.nbr.data() + pat.nbr_ptr[r];
+        const int32_t* le = pat.nbr.data() + pat.nbr_ptr[r + 1];
+        for (int b = 0; b < nn; ++b)
+          posmap[((size_t)e * nn + a) * nn + b] = (uint8_t)(std::lower_bound(lb, le, c[b]) - lb);
+      }
+    }
+  });
+  return "";
+}
+
 }  // namespace mastb200

@@ -131,4 +131,14 @@ std::string build_pattern(int32_t nn, int64_t n_nodes, int64_t n_elem, const int
 std::string build_stream_plan(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
                               const PlanLimits& lim, StreamPlan& plan);
 
+// ---- coloured scatter plan (HEX27) -----------------------------------------------------------------------------
+// Greedy colouring in element id order (smallest colour no node-sharing element has taken): no two elements of a colour
+// share a node, so a colour can be scattered into the CSR without atomics.  Elements without an owned node get no colour.
+// color_ptr[n_colors+1] indexes color_elems (element ids, ascending within a colour).
+std::string build_coloring(const Pattern& pat, const int32_t* conn, std::vector<int32_t>& color_ptr,
+                           std::vector<int32_t>& color_elems);
+// element -> nnz map: posmap[e][a][b] = position of node conn[e][b] in the neighbour list of the owned node conn[e][a]
+// (0 for unowned a).  One byte per node pair; fails if a row has more than 255 neighbours.
+std::string build_posmap(const Pattern& pat, const int32_t* conn, std::vector<uint8_t>& posmap);
+
 }  // namespace mastb200

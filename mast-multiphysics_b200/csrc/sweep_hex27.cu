@@ -1,0 +1,264 @@
+// sweep_hex27.cu -- HEX27 (tri-quadratic) linear-elastic residual + Jacobian sweep (sm_100a, fp64, DMMA).
+//
+// Device counterpart of the element loop of MAST::NonlinearImplicitAssembly::residual_and_jacobian
+// (/root/reference/src/base/nonlinear_implicit_assembly.cpp:111-186) with StructuralElement3D::internal_residual
+// (src/elasticity/solid_element_3d.cpp:135-423, linear strain; 3x3x3 Gauss rule = libMesh's default for SECOND order,
+// src/mesh/fe_base.cpp:103-105) and ::thermal_residual (:950-1089).
+//
+// The path is fp64-compute-bound (K_e is 81x81 from 27 quadrature points), so the contraction runs on the fp64 tensor
+// pipe.  With an isotropic D the element matrix is K_ab = lam*S_ab + mu*S_ab^T + mu*tr(S_ab)*I with
+//   S_ij[a][b] = sum_q w_q (dN_a/dx_i)(q) (dN_b/dx_j)(q),   w_q = JxW_q * E(x_q),
+// i.e. nine 27x27x27 products (padded to 32x32x28) instead of B^T D B with K = 162: 1008 mma.sync.m8n8k4.f64 per
+// element (516 kflop) against 2.1 Mflop for the dense form.
+//
+// One CTA (4 warps) per element, four CTAs per SM; elements are processed colour by colour (no two elements of a colour
+// share a node), so the adds into the CSR values and the residual are plain read-modify-writes without atomics and the
+// summation order into every entry is the colour order -- fixed by the plan, independent of scheduling.  K_e is never
+// stored: the accumulator fragments go from registers straight to their CSR slots through the per-element position map
+// (a precomputed element -> nnz map, one byte per node pair).
+//   phase 1  one thread per quadrature point: J, J^-1, w_q (SIMP modulus of the interpolated nodal density), thermal
+//            stress factor
+//   phase 2  gradients g_i[q][a] = J^-T dN_a, staged in shared memory in three arrays with a q-stride of 36 doubles so
+//            that both DMMA operand fetches are bank-conflict-free
+//   phase 3  warp w owns node rows 8w..8w+7: two passes over column tiles, 9 component pairs x 2 tiles x 7 k-steps of
+//            DMMA each, B operand = w_q * g formed on the fly
+//   phase 4  epilogue per pass: K from S, f_a += K_ab u_b, libMesh's per-element Dirichlet semantics, scatter.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace mastb200 {
+namespace {
+
+constexpr int TB = 128;
+constexpr int QSTR = 36;              // q-stride of the gradient arrays (doubles): 36 = 4 mod 16 -> conflict-free fragments
+constexpr int GSZ = 28 * QSTR;        // one component array: 28 (27 + zero pad) quadrature points x 36 columns
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct Smem27 {
+  double tabN[27 * 27];       // N_b(q)            [q][b]
+  double tabD[27 * 27 * 3];   // dN_b/dxi_r(q)     [q][b][r]
+  double tabW[28];            // Gauss weights
+  double g[3][GSZ];           // physical gradients [i][q*36 + a]
+  double wq[28];              // JxW * E at the point (0 for the pad point)
+  double pth[28];             // thermal stress factor at the point
+  double inv[27 * 9];         // J^-1 per point: inv[q][c*3+r] = d xi_r / d x_c
+  double xs[27 * 3], us[27 * 3], rho[27], T[27], fth[27 * 3];
+  double red[4];
+  int64_t base[27];           // nbr_ptr[row] of each node (node-level CSR offset)
+  int32_t gid[27], row[27], nnb[27];
+  uint8_t cm[32];
+  uint8_t pos[27 * 27 + 7];   // position of node b in the neighbour list of node a
+};
+
+__global__ void __launch_bounds__(TB, 4) hex27_sweep_kernel(const Hex27Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nv = p.nv;
+  const bool wantJ = p.J != nullptr, wantR = p.R != nullptr;
+
+  // tables and the zero padding of the operand arrays: once per CTA
+  for (int k = tid; k < 27 * 27; k += TB) s.tabN[k] = p.tab[k];
+  for (int k = tid; k < 27 * 27 * 3; k += TB) s.tabD[k] = p.tab[27 * 27 + k];
+  if (tid < 27) s.tabW[tid] = p.tab[27 * 27 * 4 + tid];
+  for (int k = tid; k < 3 * GSZ; k += TB) (&s.g[0][0])[k] = 0.;
+  if (tid < 28) { s.wq[tid] = 0.; s.pth[tid] = 0.; }
+
+  for (int idx = blockIdx.x; idx < p.n_elems; idx += gridDim.x) {
+    const int e = p.elems[idx];
+    __syncthreads();  // previous element done with the staging arrays
+    if (tid < 27) {
+      const int n = p.conn[(int64_t)e * 27 + tid];
+      s.gid[tid] = n;
+      const int r = p.node_row[n];
+      s.row[tid] = r;
+      s.base[tid] = r >= 0 ? p.nbr_ptr[r] : 0;
+      s.nnb[tid] = r >= 0 ? (int)(p.nbr_ptr[r + 1] - p.nbr_ptr[r]) : 0;
+      s.cm[tid] = p.cmask ? p.cmask[n] : 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        s.xs[tid * 3 + c] = p.xyz[(int64_t)n * 3 + c];
+        s.us[tid * 3 + c] = p.X[(int64_t)n * nv + c];
+      }
+      s.rho[tid] = p.rho ? p.rho[n] : 1.;
+      s.T[tid] = p.temperature ? p.temperature[n] : p.T_const;
+    }
+    for (int k = tid; k < 27 * 27; k += TB) s.pos[k] = p.posmap[(int64_t)e * 729 + k];
+    __syncthreads();
+
+    if (p.diag_elem && p.diag_elem[e]) {  // diagonal_elem_subdomain_id (nonlinear_implicit_assembly.cpp:117-130)
+      if (wantJ && tid < 27 && s.row[tid] >= 0) {
+        const int64_t rl = (int64_t)s.nnb[tid] * nv;
+        double* blk = p.J + s.base[tid] * nv * nv + (int64_t)s.pos[tid * 27 + tid] * nv;
+        for (int i = 0; i < nv; ++i) blk[i * rl + i] += ((s.cm[tid] >> i) & 1u) ? 1. : 1.0e-24;
+      }
+      continue;
+    }
+
+    // ---- phase 1: geometry at the quadrature points ----
+    if (tid < 27) {
+      const int q = tid;
+      double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
+      double rq = 0., tq = 0.;
+      for (int b = 0; b < 27; ++b) {
+        const double* d = s.tabD + (q * 27 + b) * 3;
+        const double x0 = s.xs[b * 3], x1 = s.xs[b * 3 + 1], x2 = s.xs[b * 3 + 2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          Jm[r][0] = fma(d[r], x0, Jm[r][0]); Jm[r][1] = fma(d[r], x1, Jm[r][1]); Jm[r][2] = fma(d[r], x2, Jm[r][2]);
+        }
+        const double N = s.tabN[q * 27 + b];
+        rq = fma(N, s.rho[b], rq);
+        tq = fma(N, s.T[b], tq);
+      }
+      const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+      const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+      const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+      const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+      const double idet = 1. / det;
+      double* inv = s.inv + q * 9;
+      inv[0] = c00 * idet; inv[3] = c01 * idet; inv[6] = c02 * idet;
+      inv[1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+      inv[4] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+      inv[7] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+      inv[2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+      inv[5] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+      inv[8] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+      const double JxW = det * s.tabW[q];
+      double E = p.E0;
+      if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(rq, p.penalty));  // example_6.cpp:100-137
+      s.wq[q] = JxW * E;
+      s.pth[q] = p.thermal ? -(JxW * E) * p.alpha_k * (tq - p.T_ref) : 0.;  // f -= JxW B^T (D alpha dT)
+    }
+    __syncthreads();
+
+    // ---- phase 2: physical gradients g_i[q][a] ----
+    for (int k = tid; k < 27 * 27; k += TB) {
+      const int q = k / 27, a = k - q * 27;
+      const double* d = s.tabD + k * 3;
+      const double* inv = s.inv + q * 9;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s.g[c][q * QSTR + a] = d[0] * inv[c * 3] + d[1] * inv[c * 3 + 1] + d[2] * inv[c * 3 + 2];
+    }
+    __syncthreads();
+    if (p.thermal && wantR && tid < 81) {
+      const int a = tid / 3, i = tid - a * 3;
+      double t = 0.;
+      for (int q = 0; q < 27; ++q) t = fma(s.pth[q], s.g[i][q * QSTR + a], t);
+      s.fth[tid] = t;
+    }
+
+    // ---- phases 3 + 4 ----
+    const int al = lane >> 2, kq = lane & 3;
+    const int a = 8 * warp + al;
+    const bool a_ok = a < 27;
+    const int rowa = a_ok ? s.row[a] : -1;
+    const unsigned cma = a_ok ? s.cm[a] : 0u;
+    const int64_t rl = a_ok ? (int64_t)s.nnb[a] * nv : 0;
+    double* rowJ = (wantJ && rowa >= 0) ? p.J + s.base[a] * nv * nv : nullptr;
+    double f0 = 0., f1 = 0., f2 = 0., mx = 0.;
+    for (int pass = 0; pass < 2; ++pass) {
+      double C[9][2][2];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { C[k][0][0] = C[k][0][1] = C[k][1][0] = C[k][1][1] = 0.; }
+#pragma unroll 1
+      for (int ks = 0; ks < 7; ++ks) {
+        const int q = 4 * ks + kq;
+        const double w = s.wq[q];
+        const double A0 = s.g[0][q * QSTR + a], A1 = s.g[1][q * QSTR + a], A2 = s.g[2][q * QSTR + a];
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const int bc = 8 * (2 * pass + t) + al;
+          const double B0 = w * s.g[0][q * QSTR + bc], B1 = w * s.g[1][q * QSTR + bc], B2 = w * s.g[2][q * QSTR + bc];
+          dmma8x8x4(C[0][t][0], C[0][t][1], A0, B0);
+          dmma8x8x4(C[1][t][0], C[1][t][1], A0, B1);
+          dmma8x8x4(C[2][t][0], C[2][t][1], A0, B2);
+          dmma8x8x4(C[3][t][0], C[3][t][1], A1, B0);
+          dmma8x8x4(C[4][t][0], C[4][t][1], A1, B1);
+          dmma8x8x4(C[5][t][0], C[5][t][1], A1, B2);
+          dmma8x8x4(C[6][t][0], C[6][t][1], A2, B0);
+          dmma8x8x4(C[7][t][0], C[7][t][1], A2, B1);
+          dmma8x8x4(C[8][t][0], C[8][t][1], A2, B2);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+#pragma unroll
+        for (int bb = 0; bb < 2; ++bb) {
+          const int b = 8 * (2 * pass + t) + 2 * kq + bb;
+          if (!a_ok || b >= 27) continue;
+          double K[3][3];
+          const double trm = p.mu1 * (C[0][t][bb] + C[4][t][bb] + C[8][t][bb]);
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              K[i][j] = p.lam1 * C[i * 3 + j][t][bb] + p.mu1 * C[j * 3 + i][t][bb] + (i == j ? trm : 0.);
+          if (wantR) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrix)
+            const double u0 = s.us[b * 3], u1 = s.us[b * 3 + 1], u2 = s.us[b * 3 + 2];
+            f0 += K[0][0] * u0 + K[0][1] * u1 + K[0][2] * u2;
+            f1 += K[1][0] * u0 + K[1][1] * u1 + K[1][2] * u2;
+            f2 += K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
+          }
+          if (a == b) mx = fmax(mx, fmax(K[0][0], fmax(K[1][1], K[2][2])));
+          if (rowJ) {
+            const unsigned cmb = s.cm[b];
+            double* dst = rowJ + (int64_t)s.pos[a * 27 + b] * nv;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                double k = K[i][j];
+                if (((cma >> i) | (cmb >> j)) & 1u) k = (a == b && i == j && ((cma >> i) & 1u)) ? 1. : 0.;
+                dst[i * rl + j] += k;
+              }
+          }
+        }
+    }
+    if (nv == 6 && wantJ) {  // 1e-20*max(diag K_e) on the rotational diagonal (solid_element_3d.cpp:413-417)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) s.red[warp] = mx;
+    }
+    __syncthreads();  // red and fth complete
+    if (wantR) {
+      f0 += __shfl_xor_sync(0xffffffffu, f0, 1); f0 += __shfl_xor_sync(0xffffffffu, f0, 2);
+      f1 += __shfl_xor_sync(0xffffffffu, f1, 1); f1 += __shfl_xor_sync(0xffffffffu, f1, 2);
+      f2 += __shfl_xor_sync(0xffffffffu, f2, 1); f2 += __shfl_xor_sync(0xffffffffu, f2, 2);
+      if (kq == 0 && rowa >= 0) {
+        if (p.thermal) { f0 += s.fth[a * 3]; f1 += s.fth[a * 3 + 1]; f2 += s.fth[a * 3 + 2]; }
+        double* r = p.R + (int64_t)s.gid[a] * nv;
+        if (!(cma & 1u)) r[0] += f0;
+        if (!(cma & 2u)) r[1] += f1;
+        if (!(cma & 4u)) r[2] += f2;
+      }
+    }
+    if (nv == 6 && wantJ && tid < 27 && s.row[tid] >= 0) {
+      const double m = fmax(fmax(s.red[0], s.red[1]), fmax(s.red[2], s.red[3]));
+      const int64_t rl6 = (int64_t)s.nnb[tid] * 6;
+      double* blk = p.J + s.base[tid] * 36 + (int64_t)s.pos[tid * 27 + tid] * 6;
+      for (int i = 3; i < 6; ++i) blk[i * rl6 + i] += ((s.cm[tid] >> i) & 1u) ? 1. : 1.0e-20 * m;
+    }
+  }
+}
+
+}  // namespace
+
+size_t hex27_sweep_smem_bytes() { return sizeof(Smem27); }
+
+cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t stream) {
+  if (p.n_elems <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(hex27_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem27));
+  if (e != cudaSuccess) return e;
+  const int grid = p.n_elems < 4 * sm_count ? p.n_elems : 4 * sm_count;
+  hex27_sweep_kernel<<<grid, TB, sizeof(Smem27), stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mastb200

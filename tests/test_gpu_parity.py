@@ -209,3 +209,116 @@ def test_large_mesh_properties(built):
     for r in interior:
         assert np.array_equal(ci[rp[r]:rp[r + 1]], oci[orp[r]:orp[r + 1]])
         _close(J[rp[r]:rp[r + 1]], Jo[orp[r]:orp[r + 1]])
+
+
+# ---- QUAD4 heat conduction (BASELINE config C2) ---------------------------------------------------------------------
+def _heat_problem(nx, ny, k_of_T=1, jitter=0.0, diag=False, source=0.0):
+    xyz, conn = mesh.build_square(nx, ny, 1.0, 1.0)
+    if jitter:
+        rng = np.random.Generator(np.random.MT19937(12345))
+        h = np.array([1.0 / nx, 1.0 / ny, 0.0])
+        interior = (xyz[:, 0] > 0) & (xyz[:, 0] < 1) & (xyz[:, 1] > 0) & (xyz[:, 1] < 1)
+        xyz[interior] += (jitter * h * rng.uniform(-1, 1, xyz.shape))[interior]
+    con = np.isclose(xyz[:, 0], 0.0).astype(np.uint8)  # fixed temperature on the edge x = 0
+    de = None
+    if diag:
+        de = np.zeros(len(conn), np.uint8); de[[1, nx + 2, len(conn) - 1]] = 1
+    return O.Problem(O.QUAD4, xyz, conn, 1, constrained=con, k0=237.0, k_beta=1e-3, k_of_T=k_of_T, thickness=0.06,
+                     heat_source=source, diag_elem=de)
+
+
+def _temperature(n):
+    return 300 + 50 * np.random.Generator(np.random.MT19937(4)).uniform(0, 1, n)
+
+
+@pytest.mark.parametrize("k_of_T", [0, 1])
+def test_quad4_heat_residual_and_jacobian(built, k_of_T):
+    prob = _heat_problem(37, 23, k_of_T=k_of_T, jitter=0.2, source=1.0e4)
+    T = _temperature(prob.n_dof)
+    ctx, R, J = _check_RJ(prob, T)
+    assert np.isclose(ctx.res_l2_norm(), np.linalg.norm(R), rtol=1e-13)
+    _check_RJ(prob, T, want_R=False)
+    _check_RJ(prob, T, want_J=False)
+
+
+def test_quad4_heat_diag_elems_and_unstructured_numbering(built):
+    prob = _heat_problem(9, 7, diag=True)
+    _check_RJ(prob, _temperature(prob.n_dof))
+    rng = np.random.default_rng(0)
+    xyz, conn = mesh.build_square(11, 8)
+    perm = rng.permutation(len(xyz))
+    xyz2 = np.empty_like(xyz); xyz2[perm] = xyz
+    conn2 = perm[conn].astype(np.int32)[rng.permutation(len(conn))]
+    con = (rng.uniform(size=len(xyz)) < 0.1).astype(np.uint8)
+    p2 = O.Problem(O.QUAD4, xyz2, conn2, 1, constrained=con, k0=237.0, k_beta=1e-3, k_of_T=1, thickness=0.06)
+    _check_RJ(p2, _temperature(p2.n_dof))
+
+
+def test_quad4_heat_c2_full_size_properties(built):
+    # C2: 1024^2 QUAD4, k(T); nnz = 3073^2; for constant k the matrix is symmetric and K.1 = 0 on free rows
+    import scipy.sparse as sp
+    n = 1024
+    xyz, conn = mesh.build_square(n, n)
+    import mast_b200
+    ctx = mast_b200.Context(0)
+    ctx.set_mesh(mast_b200.QUAD4, xyz, conn)
+    ctx.set_dof_map(1)
+    ctx.set_material(k0=237.0, k_beta=1e-3, k_of_T=0, thickness=1.0)
+    ctx.build_pattern()
+    assert ctx.nnz == 3073 ** 2
+    T = _temperature(len(xyz))
+    R = np.empty(len(xyz)); J = np.empty(ctx.nnz)
+    ctx.residual_and_jacobian(T, R, J)
+    rp, ci = ctx.get_pattern()
+    A = sp.csr_matrix((J, ci, rp), shape=(len(xyz),) * 2)
+    assert abs(A - A.T).max() <= 1e-12 * np.abs(J).max()
+    assert np.abs(A @ np.ones(len(xyz))).max() <= 1e-11 * np.abs(J).max()
+    assert np.abs(R - A @ T).max() <= 1e-11 * np.abs(R).max()  # linear conduction: R = K T
+    ctx.set_material(k0=237.0, k_beta=1e-3, k_of_T=1, thickness=1.0)
+    J2 = np.empty(ctx.nnz)
+    ctx.residual_and_jacobian(T, None, J2)
+    assert np.abs(J2 - J).max() > 1e-3 * np.abs(J).max()  # the dk/dT tangent is there
+
+
+# ---- HEX27 quadratic elasticity (BASELINE config C5) ---------------------------------------------------------------
+def _hex27_problem(nx, ny, nz, nv=3, jitter=0.0, **kw):
+    xyz, conn = mesh.build_cube(nx, ny, nz, 0.3, 0.15, 0.15, 27, jitter=jitter)
+    con = mesh.dirichlet_flags(len(xyz), nv, mesh.boundary_nodes(nx, ny, nz, 4, 27))
+    return O.Problem(O.HEX27, xyz, conn, nv, constrained=con, **kw)
+
+
+@pytest.mark.parametrize("nv", [3, 6])
+def test_hex27_residual_and_jacobian(built, nv):
+    prob = _hex27_problem(5, 3, 3, nv=nv, jitter=0.1)
+    X = O.state(prob.n_dof, 1)
+    ctx, R, J = _check_RJ(prob, X)
+    assert np.isclose(ctx.res_l2_norm(), np.linalg.norm(R), rtol=1e-13)
+    _check_RJ(prob, X, want_R=False)
+    _check_RJ(prob, X, want_J=False)
+
+
+def test_hex27_thermoelastic_simp_and_diag_elems(built):
+    nx, ny, nz = 4, 3, 2
+    n_nodes = (2 * nx + 1) * (2 * ny + 1) * (2 * nz + 1)
+    rho = 0.2 + 0.6 * np.random.Generator(np.random.MT19937(3)).uniform(0, 1, n_nodes)
+    diag = np.zeros(nx * ny * nz, np.uint8); diag[[0, 5, 23]] = 1
+    prob = _hex27_problem(nx, ny, nz, jitter=0.1, alpha=1.5e-5, thermal=1, temperature=_temperature(n_nodes),
+                          ref_temperature=300.0, rho=rho, rho_min=1e-8, penalty=4.0, diag_elem=diag)
+    _check_RJ(prob, O.state(prob.n_dof, 1))
+    prob2 = _hex27_problem(3, 2, 2, nv=6, alpha=1.5e-5, thermal=1, temperature_const=350.0, ref_temperature=300.0)
+    _check_RJ(prob2, O.state(prob2.n_dof, 1))
+
+
+def test_hex27_determinism_and_unstructured_numbering(built):
+    xyz, conn = mesh.build_cube(4, 3, 3, elem_type=27, jitter=0.1)
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(len(xyz))
+    xyz2 = np.empty_like(xyz); xyz2[perm] = xyz
+    conn2 = perm[conn].astype(np.int32)[rng.permutation(len(conn))]
+    con = (rng.uniform(size=len(xyz) * 3) < 0.1).astype(np.uint8)
+    prob = O.Problem(O.HEX27, xyz2, conn2, 3, constrained=con)
+    X = O.state(prob.n_dof, 1)
+    ctx, R, J = _check_RJ(prob, X)
+    R2 = np.empty_like(R); J2 = np.empty_like(J)
+    ctx.residual_and_jacobian(X, R2, J2)
+    assert np.array_equal(R, R2) and np.array_equal(J, J2)  # colour order fixes the summation order
