@@ -79,29 +79,8 @@ class ClockSampler(threading.Thread):
 
 
 def slab_problem(n, rank, world, jitter, nv=3):
-    """Rank-local view of the n^3 cantilever: local xyz/conn/owned/constrained + halo bookkeeping."""
-    from mast_b200 import mesh
-    xyz, conn = mesh.build_cube(n, n, n, 1.0, 1.0, 1.0, 8, jitter=jitter)
-    npl = (n + 1) * (n + 1)
-    p0 = (n + 1) * rank // world            # owned node planes [p0, p1)
-    p1 = (n + 1) * (rank + 1) // world
-    l0, l1 = max(p0 - 1, 0), min(p1 - 1, n - 1)   # element layers touching owned planes
-    q0, q1 = l0, l1 + 1                            # local node planes [q0, q1]
-    node_lo = q0 * npl
-    lxyz = xyz[node_lo:(q1 + 1) * npl]
-    lconn = conn[l0 * n * n:(l1 + 1) * n * n] - node_lo
-    plane = np.arange(len(lxyz)) // npl + q0
-    owned = ((plane >= p0) & (plane < p1)).astype(np.uint8)
-    con = np.zeros((len(lxyz), nv), np.uint8)
-    con[np.isclose(lxyz[:, 0], 0.0)] = 1
-    # pressure on y = 1 (libMesh side 3) of the local elements
-    j = (np.arange(len(lconn)) // n) % n
-    se = np.flatnonzero(j == n - 1).astype(np.int32)
-    info = dict(p0=p0, p1=p1, q0=q0, q1=q1, npl=npl, n_owned_elem=None)
-    # elements "owned" by the rank for the throughput count: layers [p0, p1) clipped (each element counted once)
-    e0, e1 = min(p0, n), min(p1, n)
-    info["n_owned_elem"] = (e1 - e0) * n * n
-    return lxyz, lconn.astype(np.int32), owned, con.ravel(), se, info
+    from mast_b200 import partition
+    return partition.slab_problem(n, rank, world, jitter, nv)
 
 
 def make_context(lxyz, lconn, owned, con, se, device, nv=3):
@@ -200,17 +179,8 @@ def main():
         """AssemblyBase::build_localized_vector: ghost planes of X from the neighbouring ranks (NCCL P2P)."""
         if world == 1:
             return
-        ops = []
-        w = npl * nv
-        p0, p1, q0 = info["p0"], info["p1"], info["q0"]
-        if rank > 0:      # my first owned plane -> rank-1's upper ghost; its last owned plane -> my lower ghost
-            ops.append(dist.P2POp(dist.isend, dX[(p0 - q0) * w:(p0 - q0 + 1) * w], rank - 1))
-            ops.append(dist.P2POp(dist.irecv, dX[(p0 - 1 - q0) * w:(p0 - q0) * w], rank - 1))
-        if rank < world - 1:
-            ops.append(dist.P2POp(dist.isend, dX[(p1 - 1 - q0) * w:(p1 - q0) * w], rank + 1))
-            ops.append(dist.P2POp(dist.irecv, dX[(p1 - q0) * w:(p1 - q0 + 1) * w], rank + 1))
-        for r in dist.batch_isend_irecv(ops):
-            r.wait()
+        from mast_b200 import partition
+        partition.exchange_halo(dist, dX, info, rank, world, nv)
         stream.wait_stream(torch.cuda.current_stream())
 
     def step_device():

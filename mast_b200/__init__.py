@@ -6,3 +6,4 @@ __path__.append(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), ".."
 
 from .api import *  # noqa: E402,F401,F403
 from . import mesh  # noqa: E402,F401
+from . import partition  # noqa: E402,F401
