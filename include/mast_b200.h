@@ -118,6 +118,28 @@ int mastb200_compliance(mastb200_context* ctx, const double* X, double* q);
 /* dq_dX[n_nodes*nv] [h|d] = -f_ext with constrained rows zeroed */
 int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, double* dq_dX);
 
+/* StressStrainOutputBase (3D solids): stress[n_elem*nq][6], strain[...][6] (Voigt xx,yy,zz,xy,yz,zx; engineering
+ * shear), von_mises[n_elem*nq], jxw[n_elem*nq] at the quadrature points, any may be NULL [h|d]
+ *   <- StructuralElement3D::calculate_stress, src/elasticity/solid_element_3d.cpp:1146-1265;
+ *      Data::von_Mises_stress, src/elasticity/stress_output_base.cpp:182-195 */
+int mastb200_stress(mastb200_context* ctx, const double* X, double* stress, double* strain, double* von_mises,
+                    double* jxw);
+/* p-norm / KS-weighted von Mises aggregate  q = sigma0 * (num/den)^(1/p_norm),
+ *   num = sum (vm/sigma0)^p_norm e^{rho_exp (vm-sigma0)/sigma0} JxW,  den = sum e^{...} JxW
+ * over the participating elements (elem_mask[n_elem] or NULL = all; OutputAssemblyElemOperations::
+ * set_participating_elements).  sums[2] = {num, den} of this rank (the caller adds them over ranks, the reference's
+ * comm().sum at stress_output_base.cpp:903-904); q (may be NULL) from this rank's sums.
+ *   <- AssemblyBase::calculate_output + StressStrainOutputBase::functional_for_all_elems,
+ *      src/base/assembly_base.cpp:253-333, src/elasticity/stress_output_base.cpp:851-909 */
+int mastb200_stress_functional(mastb200_context* ctx, const double* X, double p_norm, double rho_exp, double sigma0,
+                               const uint8_t* elem_mask, double* sums, double* q);
+/* dq_dX[n_nodes*nv] [h|d] of that aggregate given the global sums {num, den}; rows of owned nodes, constrained
+ * dofs zeroed per element
+ *   <- AssemblyBase::calculate_output_derivative + StressStrainOutputBase::functional_state_derivartive_for_elem,
+ *      src/base/assembly_base.cpp:338-430, src/elasticity/stress_output_base.cpp:1104-1172 */
+int mastb200_stress_functional_derivative(mastb200_context* ctx, const double* X, double p_norm, double rho_exp,
+                                          double sigma0, const uint8_t* elem_mask, const double* sums, double* dq_dX);
+
 /* ---- introspection for bench / tests -------------------------------------------------------- */
 typedef struct mastb200_stats {
   int64_t n_tiles, n_visits, n_owned_nodes, n_elem;

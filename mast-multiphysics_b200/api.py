@@ -19,6 +19,7 @@ EXPORTED_SYMBOLS = [
     "mastb200_set_density", "mastb200_build_pattern", "mastb200_get_pattern", "mastb200_get_row_dofs",
     "mastb200_residual_and_jacobian", "mastb200_res_l2_norm", "mastb200_sensitivity_sweep",
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
+    "mastb200_stress", "mastb200_stress_functional", "mastb200_stress_functional_derivative",
     "mastb200_get_stats", "mastb200_stream", "mastb200_debug_plan_sizes", "mastb200_debug_plan_copy",
 ]
 
@@ -86,6 +87,9 @@ def load_library():
     lib.mastb200_apply_dv_map_transpose.argtypes = [vp, vp, i64, vp, vp, vp, vp]
     lib.mastb200_compliance.argtypes = [vp, vp, C.POINTER(dbl)]
     lib.mastb200_compliance_derivative.argtypes = [vp, vp, vp]
+    lib.mastb200_stress.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.mastb200_stress_functional.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, C.POINTER(dbl)]
+    lib.mastb200_stress_functional_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
     lib.mastb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mastb200_debug_plan_sizes.argtypes = [vp, i32, vp]
     lib.mastb200_debug_plan_copy.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
@@ -218,6 +222,22 @@ class Context:
 
     def compliance_derivative(self, X, dq_dX):
         self._ck(self._lib.mastb200_compliance_derivative(self._h, _ptr(X), _ptr(dq_dX)))
+
+    def stress(self, X, stress=None, strain=None, von_mises=None, jxw=None):
+        self._ck(self._lib.mastb200_stress(self._h, _ptr(X), _ptr(stress), _ptr(strain), _ptr(von_mises), _ptr(jxw)))
+
+    def stress_functional(self, X, p_norm, rho_exp, sigma0, elem_mask=None):
+        """Returns (q, sums) with sums = [numerator, denominator] of this rank."""
+        sums = np.zeros(2)
+        q = C.c_double()
+        self._ck(self._lib.mastb200_stress_functional(self._h, _ptr(X), p_norm, rho_exp, sigma0,
+                                                      _ptr(_np(elem_mask, np.uint8)), _ptr(sums), C.byref(q)))
+        return q.value, sums
+
+    def stress_functional_derivative(self, X, p_norm, rho_exp, sigma0, sums, dq_dX, elem_mask=None):
+        sums = _np(sums, np.float64)
+        self._ck(self._lib.mastb200_stress_functional_derivative(self._h, _ptr(X), p_norm, rho_exp, sigma0,
+                                                                 _ptr(_np(elem_mask, np.uint8)), _ptr(sums), _ptr(dq_dX)))
 
     def stats(self):
         s = Stats()

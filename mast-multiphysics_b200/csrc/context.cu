@@ -121,7 +121,8 @@ struct mastb200_context {
   DevBuf<int32_t> d_tile_counter, d_owned_nodes;
   DevBuf<uint8_t> d_cmask;
   // device: mesh + state + staging for host pointers
-  DevBuf<double> d_xyz, d_X, d_adj, d_rho, d_T, d_R, d_J, d_G, d_dq, d_partial, d_scalar;
+  DevBuf<double> d_xyz, d_X, d_adj, d_rho, d_T, d_R, d_J, d_G, d_dq, d_partial, d_scalar, d_scratch, d_st[4];
+  DevBuf<uint8_t> d_elem_mask;
   bool rho_set = false, T_nodal = false, thermal = false;
   const double* rho_ext = nullptr;  // caller-owned device density
   const double* T_ext = nullptr;
@@ -291,6 +292,25 @@ void hex27_tables(std::vector<double>& tab) {
   }
 }
 
+// HEX8 shape tables in the same layout (2x2x2 Gauss rule, xi fastest, unit weights)
+void hex8_tables(std::vector<double>& tab) {
+  static const int8_t C[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+  const double gp = 0.57735026918962576451;
+  tab.assign(8 * 8 * 4 + 8, 0.);
+  for (int q = 0; q < 8; ++q) {
+    const double xi = (q & 1) ? gp : -gp, eta = (q & 2) ? gp : -gp, zeta = (q & 4) ? gp : -gp;
+    for (int b = 0; b < 8; ++b) {
+      const double fx = 1. + C[b][0] * xi, fy = 1. + C[b][1] * eta, fz = 1. + C[b][2] * zeta;
+      tab[q * 8 + b] = 0.125 * fx * fy * fz;
+      double* d = &tab[8 * 8 + (q * 8 + b) * 3];
+      d[0] = 0.125 * C[b][0] * fy * fz;
+      d[1] = 0.125 * C[b][1] * fx * fz;
+      d[2] = 0.125 * C[b][2] * fx * fy;
+    }
+    tab[8 * 8 * 4 + q] = 1.;
+  }
+}
+
 int ensure_generic_plan(mastb200_context* ctx) {
   mastb200_context::GenericPlan& G = ctx->gplan;
   if (G.built || ctx->planning_only) return MASTB200_OK;
@@ -298,13 +318,18 @@ int ensure_generic_plan(mastb200_context* ctx) {
   CU(G.conn.upload(ctx->conn, ctx->stream));
   CU(G.nbr_ptr.upload(P.nbr_ptr, ctx->stream));
   if (ctx->has_diag) CU(G.diag.upload(ctx->diag_elem, ctx->stream));
+  CU(G.n2e_ptr.upload(P.n2e_ptr, ctx->stream));
+  CU(G.n2e.upload(P.n2e, ctx->stream));
   if (ctx->elem_type == MASTB200_QUAD4) {
     for (int64_t r = 0; r < P.n_owned; ++r)
       if (P.nbr_ptr[r + 1] - P.nbr_ptr[r] > kGatherMaxNbr)
         return ctx->fail(MASTB200_ERR_PLAN, "plan: a node has more than %d neighbours", kGatherMaxNbr);
     CU(G.nbr.upload(P.nbr, ctx->stream));
-    CU(G.n2e_ptr.upload(P.n2e_ptr, ctx->stream));
-    CU(G.n2e.upload(P.n2e, ctx->stream));
+  } else if (ctx->elem_type == MASTB200_HEX8) {  // gather sweep (Green-Lagrange strain) and stress output
+    CU(G.nbr.upload(P.nbr, ctx->stream));
+    std::vector<double> tab;
+    hex8_tables(tab);
+    CU(G.tab.upload(tab, ctx->stream));
   } else {  // HEX27
     std::vector<int32_t> color_elems;
     std::string e = build_coloring(P, ctx->conn.data(), G.color_ptr, color_elems);
@@ -331,7 +356,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
   if (heat && ctx->nv != 1) return ctx->fail(MASTB200_ERR_ARG, "QUAD4 heat conduction needs nv = 1");
   if (!heat && ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX27 elasticity needs nv = 3 or 6");
   if (!heat && ctx->mat.nonlinear_strain)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain has no device sweep yet");
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain: HEX8 only on the device path");
   if ((rc = ensure_generic_plan(ctx))) return rc;
   mastb200_context::GenericPlan& G = ctx->gplan;
   const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
@@ -392,6 +417,57 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
   return MASTB200_OK;
 }
 
+// HEX8 with Green-Lagrange strain: row-owner gather (sweep_hex8_gather.cu)
+int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J) {
+  int rc;
+  if ((rc = ensure_generic_plan(ctx))) return rc;
+  mastb200_context::GenericPlan& G = ctx->gplan;
+  const Pattern& P = ctx->pat;
+  for (int64_t r = 0; r < P.n_owned; ++r)
+    if (P.nbr_ptr[r + 1] - P.nbr_ptr[r] > 32)
+      return ctx->fail(MASTB200_ERR_PLAN, "plan: a node has more than 32 neighbours (gather sweep)");
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const size_t nnz = (size_t)plan_nnz(ctx);
+  const double* dX = nullptr;
+  double *dR = nullptr, *dJ = nullptr;
+  if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
+  if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
+  const mastb200_material& m = ctx->mat;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (dR && ctx->has_ghosts) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  SolidGatherParams p;
+  p.n_owned = P.n_owned; p.owned_nodes = ctx->d_owned_nodes.p;
+  p.nbr_ptr = G.nbr_ptr.p; p.nbr = G.nbr.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p; p.conn = G.conn.p;
+  p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+  p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+  p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
+  p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+  p.temperature = (ctx->thermal && ctx->T_nodal) ? (ctx->T_ext ? ctx->T_ext : ctx->d_T.p) : nullptr;
+  p.E0 = m.E0;
+  p.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu);
+  p.mu1 = 1. / 2. / (1. + m.nu);
+  p.rho_min = m.rho_min; p.penalty = m.penalty;
+  p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
+  p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
+  p.nv = ctx->nv; p.thermal = ctx->thermal ? 1 : 0; p.nonlinear = m.nonlinear_strain ? 1 : 0;
+  CU(launch_hex8_gather(p, ctx->stream));
+  ctx->launches++;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (dR && !ctx->fl_node.empty()) {
+    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, p.cmask, ctx->nv, dR, nullptr, nullptr, nullptr, ctx->stream));
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->last_R = dR;
+  if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
+  if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
 // the common sweep: any of R, J, G may be null
 int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G, double* R, double* J) {
   int rc = check_ready(ctx);
@@ -403,8 +479,10 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     return run_generic_sweep(ctx, X, R, J);
   }
   if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX8 elasticity needs nv = 3 or 6");
-  if (ctx->mat.nonlinear_strain)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain has no device sweep yet");
+  if (ctx->mat.nonlinear_strain) {
+    if (G) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities with Green-Lagrange strain are not on the device path");
+    return run_hex8_gather(ctx, X, R, J);
+  }
   if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
   if (G && ctx->thermal)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED,
@@ -805,6 +883,120 @@ int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, doubl
     ctx->launches++;
   }
   if ((rc = finish_out(ctx, dq_dX, n_dof, d))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+namespace {
+int fill_stress_params(mastb200_context* ctx, const double* X, StressParams& p) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!X) return ctx->fail(MASTB200_ERR_ARG, "X is NULL");
+  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "stress output: 3D solids (HEX8, HEX27) only");
+  if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "stress output needs nv = 3 or 6");
+  CU(cudaSetDevice(ctx->device));
+  if ((rc = ensure_generic_plan(ctx))) return rc;
+  mastb200_context::GenericPlan& G = ctx->gplan;
+  const double* dX = nullptr;
+  if ((rc = resolve_in(ctx, X, size_t(ctx->n_nodes) * ctx->nv, ctx->d_X, &dX))) return rc;
+  p = StressParams();
+  p.n_elem = ctx->n_elem; p.n_owned = ctx->pat.n_owned;
+  p.nn = ctx->nn; p.nq = ctx->nn; p.nv = ctx->nv; p.nonlinear = ctx->mat.nonlinear_strain ? 1 : 0;
+  p.conn = G.conn.p; p.tab = G.tab.p; p.xyz = ctx->d_xyz.p; p.X = dX;
+  p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+  p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+  p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+  p.owned_nodes = ctx->d_owned_nodes.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p;
+  const mastb200_material& m = ctx->mat;
+  p.E0 = m.E0;
+  p.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu);
+  p.mu1 = 1. / 2. / (1. + m.nu);
+  p.rho_min = m.rho_min; p.penalty = m.penalty;
+  return MASTB200_OK;
+}
+int upload_elem_mask(mastb200_context* ctx, const uint8_t* elem_mask, const uint8_t** out) {
+  *out = nullptr;
+  if (!elem_mask) return MASTB200_OK;
+  if (is_device_ptr(elem_mask)) { *out = elem_mask; return MASTB200_OK; }
+  CU(ctx->d_elem_mask.ensure(ctx->n_elem));
+  CU(cudaMemcpyAsync(ctx->d_elem_mask.p, elem_mask, ctx->n_elem, cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->d_elem_mask.p;
+  return MASTB200_OK;
+}
+}  // namespace
+
+int mastb200_stress(mastb200_context* ctx, const double* X, double* stress, double* strain, double* von_mises,
+                    double* jxw) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  StressParams p;
+  int rc = fill_stress_params(ctx, X, p);
+  if (rc) return rc;
+  const size_t nqp = size_t(ctx->n_elem) * p.nq;
+  if ((rc = resolve_out(ctx, stress, nqp * 6, ctx->d_st[0], &p.out_stress))) return rc;
+  if ((rc = resolve_out(ctx, strain, nqp * 6, ctx->d_st[1], &p.out_strain))) return rc;
+  if ((rc = resolve_out(ctx, von_mises, nqp, ctx->d_st[2], &p.out_vm))) return rc;
+  if ((rc = resolve_out(ctx, jxw, nqp, ctx->d_st[3], &p.out_jxw))) return rc;
+  CU(launch_stress_qp(p, ctx->stream));
+  ctx->launches++;
+  if ((rc = finish_out(ctx, stress, nqp * 6, p.out_stress))) return rc;
+  if ((rc = finish_out(ctx, strain, nqp * 6, p.out_strain))) return rc;
+  if ((rc = finish_out(ctx, von_mises, nqp, p.out_vm))) return rc;
+  if ((rc = finish_out(ctx, jxw, nqp, p.out_jxw))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_stress_functional(mastb200_context* ctx, const double* X, double p_norm, double rho_exp, double sigma0,
+                               const uint8_t* elem_mask, double* sums, double* q) {
+  if (!ctx || !sums) return MASTB200_ERR_ARG;
+  if (!(sigma0 > 0.) || !(p_norm > 0.)) return ctx->fail(MASTB200_ERR_ARG, "sigma0 and p_norm must be positive");
+  StressParams p;
+  int rc = fill_stress_params(ctx, X, p);
+  if (rc) return rc;
+  if ((rc = upload_elem_mask(ctx, elem_mask, &p.elem_mask))) return rc;
+  p.p_norm = p_norm; p.rho_exp = rho_exp; p.sigma0 = sigma0;
+  const int nb = stress_blocks(p.n_elem, p.nq);
+  CU(ctx->d_partial.ensure(std::max<size_t>(2 * (size_t)nb, 4096)));
+  CU(ctx->d_scalar.ensure(8));
+  p.partial = ctx->d_partial.p;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_stress_qp(p, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(launch_reduce_pairs(ctx->d_partial.p, nb, ctx->d_scalar.p, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 2;
+  CU(cudaMemcpyAsync(sums, ctx->d_scalar.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (q) *q = sigma0 * std::pow(sums[0] / sums[1], 1. / p_norm);
+  return MASTB200_OK;
+}
+
+int mastb200_stress_functional_derivative(mastb200_context* ctx, const double* X, double p_norm, double rho_exp,
+                                          double sigma0, const uint8_t* elem_mask, const double* sums, double* dq_dX) {
+  if (!ctx || !sums || !dq_dX) return MASTB200_ERR_ARG;
+  if (!(sigma0 > 0.) || !(p_norm > 0.)) return ctx->fail(MASTB200_ERR_ARG, "sigma0 and p_norm must be positive");
+  StressParams p;
+  int rc = fill_stress_params(ctx, X, p);
+  if (rc) return rc;
+  if ((rc = upload_elem_mask(ctx, elem_mask, &p.elem_mask))) return rc;
+  p.p_norm = p_norm; p.rho_exp = rho_exp; p.sigma0 = sigma0;
+  p.sum_num = sums[0]; p.sum_den = sums[1];
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  CU(ctx->d_scratch.ensure(size_t(ctx->n_elem) * p.nq * 9));
+  p.scratch = ctx->d_scratch.p;
+  if ((rc = resolve_out(ctx, dq_dX, n_dof, ctx->d_dq, &p.dq_dX))) return rc;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (ctx->has_ghosts) CU(cudaMemsetAsync(p.dq_dX, 0, n_dof * sizeof(double), ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_stress_derivative(p, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->launches += 2;
+  if ((rc = finish_out(ctx, dq_dX, n_dof, p.dq_dX))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   return MASTB200_OK;
 }

@@ -67,6 +67,59 @@ struct Hex27Params {
 size_t hex27_sweep_smem_bytes();
 cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t stream);
 
+
+// ---- HEX8 row-owner gather with Green-Lagrange (or linear) strain (sweep_hex8_gather.cu) ----------------------------
+struct SolidGatherParams {
+  int64_t n_owned = 0;
+  const int32_t* owned_nodes = nullptr;
+  const int64_t* nbr_ptr = nullptr;      // node-level CSR of the owned rows (at most 32 neighbours per row)
+  const int32_t* nbr = nullptr;
+  const int64_t* n2e_ptr = nullptr;
+  const int32_t* n2e = nullptr;
+  const int32_t* conn = nullptr;         // [n_elem][8]
+  const uint8_t* diag_elem = nullptr;
+  const uint8_t* cmask = nullptr;
+  const double* xyz = nullptr;
+  const double* X = nullptr;
+  const double* rho = nullptr;
+  const double* temperature = nullptr;
+  double* J = nullptr;
+  double* R = nullptr;
+  double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1., alpha_k = 0., T_const = 0., T_ref = 0.;
+  int32_t nv = 3, thermal = 0, nonlinear = 0;
+};
+cudaError_t launch_hex8_gather(const SolidGatherParams& p, cudaStream_t stream);
+
+// ---- stress output: per-qp stress/strain/von Mises, p-norm aggregate and its state derivative (stress_output.cu) ----
+struct StressParams {
+  int64_t n_elem = 0, n_owned = 0;
+  int32_t nn = 8, nq = 8, nv = 3, nonlinear = 0;
+  const int32_t* conn = nullptr;
+  const double* tab = nullptr;           // N[nq][nn], dN[nq][nn][3], w[nq]
+  const double* xyz = nullptr;
+  const double* X = nullptr;
+  const double* rho = nullptr;
+  const uint8_t* elem_mask = nullptr;    // participating elements or null (all)
+  const uint8_t* diag_elem = nullptr;
+  const uint8_t* cmask = nullptr;
+  const int32_t* owned_nodes = nullptr;
+  const int64_t* n2e_ptr = nullptr;
+  const int32_t* n2e = nullptr;
+  double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1.;
+  double p_norm = 2., rho_exp = 0., sigma0 = 1., sum_num = 0., sum_den = 0.;
+  double* out_stress = nullptr;          // [n_elem*nq][6] or null
+  double* out_strain = nullptr;
+  double* out_vm = nullptr;              // [n_elem*nq]
+  double* out_jxw = nullptr;
+  double* partial = nullptr;             // [2*blocks] block sums of (numerator, denominator) or null
+  double* scratch = nullptr;             // [n_elem*nq][9] (derivative passes)
+  double* dq_dX = nullptr;               // [n_nodes*nv]
+};
+int stress_blocks(int64_t n_elem, int nq);
+cudaError_t launch_stress_qp(const StressParams& p, cudaStream_t stream);
+cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaStream_t stream);
+cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream);  // two launches
+
 // SURFACE_PRESSURE side loads gathered per loaded node (loads.cu)
 struct FaceLoadPlan {
   int32_t n_loaded_nodes = 0;

@@ -1,0 +1,262 @@
+// stress_output.cu -- stress / strain at the quadrature points, von Mises p-norm aggregate and its state derivative
+// for 3D solids (HEX8, HEX27), sm_100a fp64.
+//
+// Device counterpart of StructuralElement3D::calculate_stress (/root/reference/src/elasticity/solid_element_3d.cpp:
+// 1146-1265: sigma = D eps at every quadrature point, stored with JxW), StressStrainOutputBase::Data::von_Mises_stress
+// and ::dvon_Mises_stress_dX (src/elasticity/stress_output_base.cpp:182-230), the aggregate of
+// ::functional_for_all_elems (:851-909) and ::functional_state_derivartive_for_elem (:1104-1172) as driven by
+// AssemblyBase::calculate_output / calculate_output_derivative (src/base/assembly_base.cpp:253-430).
+// The 3D dstress/dX is libmesh_error() in the reference (solid_element_3d.cpp:1258-1261); as in the 2D element
+// (structural_element_2d.cpp:555-611) it is D B_lin.
+//
+//   pass 1  one thread per (element, quadrature point): geometry, strain, stress, von Mises; deterministic block sums of
+//           (vm/s0)^p e^{rho (vm-s0)/s0} JxW and e^{...} JxW  (two-stage reduction, no atomics).
+//   pass 2  same thread layout with the global sums known: the derivative of the aggregate w.r.t. the dofs of node a of
+//           the element is sum_q T_q dN_a/dxi(q) with T_q = kappa_q M_q J^-T (M_q the symmetric tensor of D dvm/dsigma),
+//           one 3x3 matrix per point, written to a scratch array.
+//   pass 3  row-owner gather: one thread per owned node sums its adjacent elements in ascending id (the reference's
+//           ADD order), constrained dofs zeroed per element (constrain_element_vector).
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace mastb200 {
+namespace {
+
+constexpr int TB = 128;
+
+struct QpGeom {
+  double inv[3][3];  // inv[c][r] = d xi_r / d x_c
+  double det, wq;
+  double eps[6], sig[6];
+  double E;
+};
+
+// geometry + linear/Green-Lagrange strain + stress at (e, q); tab: N[q][b], dN[q][b][3], w[q]
+__device__ __forceinline__ void eval_qp(const StressParams& p, int64_t e, int q, QpGeom& g) {
+  const int nn = p.nn, nq = p.nq;
+  const double* Nt = p.tab + (size_t)q * nn;
+  const double* dNt = p.tab + (size_t)nq * nn + (size_t)q * nn * 3;
+  const int32_t* en = p.conn + e * nn;
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+  for (int b = 0; b < nn; ++b) {
+    const double* X = p.xyz + (int64_t)en[b] * 3;
+    const double d0 = dNt[b * 3], d1 = dNt[b * 3 + 1], d2 = dNt[b * 3 + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      Jm[0][c] = fma(d0, X[c], Jm[0][c]); Jm[1][c] = fma(d1, X[c], Jm[1][c]); Jm[2][c] = fma(d2, X[c], Jm[2][c]);
+    }
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = 1. / det;
+  g.inv[0][0] = c00 * idet; g.inv[1][0] = c01 * idet; g.inv[2][0] = c02 * idet;
+  g.inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+  g.inv[1][1] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+  g.inv[2][1] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+  g.inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+  g.inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+  g.inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+  g.det = det;
+  g.wq = p.tab[(size_t)nq * nn * 4 + q];
+  double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+  double rho = 0.;
+  for (int b = 0; b < nn; ++b) {
+    const double d0 = dNt[b * 3], d1 = dNt[b * 3 + 1], d2 = dNt[b * 3 + 2];
+    double gr[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) gr[c] = d0 * g.inv[c][0] + d1 * g.inv[c][1] + d2 * g.inv[c][2];
+    const double* U = p.X + (int64_t)en[b] * p.nv;
+    const double u0 = U[0], u1 = U[1], u2 = U[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      H[0][j] = fma(u0, gr[j], H[0][j]); H[1][j] = fma(u1, gr[j], H[1][j]); H[2][j] = fma(u2, gr[j], H[2][j]);
+    }
+    if (p.rho) rho = fma(Nt[b], p.rho[en[b]], rho);
+  }
+  double E = p.E0;
+  if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(rho, p.penalty));
+  g.E = E;
+  if (p.nonlinear) {
+    double Eg[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Eg[i][j] = 0.5 * (H[i][j] + H[j][i] + (H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j]));
+    g.eps[0] = Eg[0][0]; g.eps[1] = Eg[1][1]; g.eps[2] = Eg[2][2];
+    g.eps[3] = Eg[0][1] + Eg[1][0]; g.eps[4] = Eg[1][2] + Eg[2][1]; g.eps[5] = Eg[0][2] + Eg[2][0];
+  } else {
+    g.eps[0] = H[0][0]; g.eps[1] = H[1][1]; g.eps[2] = H[2][2];
+    g.eps[3] = H[0][1] + H[1][0]; g.eps[4] = H[1][2] + H[2][1]; g.eps[5] = H[0][2] + H[2][0];
+  }
+  const double lam = E * p.lam1, mu = E * p.mu1, tr = g.eps[0] + g.eps[1] + g.eps[2];
+  g.sig[0] = lam * tr + 2. * mu * g.eps[0]; g.sig[1] = lam * tr + 2. * mu * g.eps[1]; g.sig[2] = lam * tr + 2. * mu * g.eps[2];
+  g.sig[3] = mu * g.eps[3]; g.sig[4] = mu * g.eps[4]; g.sig[5] = mu * g.eps[5];
+}
+
+__device__ __forceinline__ double vm_pp(const double* s) {
+  const double a = s[0] - s[1], b = s[1] - s[2], c = s[2] - s[0];
+  return 0.5 * (a * a + b * b + c * c) + 3.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
+}
+
+// deterministic CTA sum of two values -> partial[2*block], partial[2*block+1]
+__device__ __forceinline__ void block_sum2(double a, double b, double* partial) {
+  __shared__ double sa[TB / 32], sb[TB / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sa[threadIdx.x >> 5] = a; sb[threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double x = 0., y = 0.;
+    for (int w = 0; w < TB / 32; ++w) { x += sa[w]; y += sb[w]; }
+    partial[2 * blockIdx.x] = x;
+    partial[2 * blockIdx.x + 1] = y;
+  }
+}
+
+__global__ void __launch_bounds__(TB) stress_qp_kernel(const StressParams p) {
+  const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int64_t nqp = p.n_elem * p.nq;
+  double num = 0., den = 0.;
+  if (t < nqp) {
+    const int64_t e = t / p.nq;
+    const int q = (int)(t - e * p.nq);
+    QpGeom g;
+    eval_qp(p, e, q, g);
+    const double vm = sqrt(vm_pp(g.sig));
+    const double JxW = g.det * g.wq;
+    if (p.out_stress)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) p.out_stress[t * 6 + i] = g.sig[i];
+    if (p.out_strain)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) p.out_strain[t * 6 + i] = g.eps[i];
+    if (p.out_vm) p.out_vm[t] = vm;
+    if (p.out_jxw) p.out_jxw[t] = JxW;
+    if (p.partial && (!p.elem_mask || p.elem_mask[e])) {
+      const double sp = (vm - p.sigma0) / p.sigma0;  // p_norm_weight = 1 (stress_output_base.cpp:278-281)
+      const double ex = (p.rho_exp * sp > 1.e2) ? exp(1.e2) : exp(p.rho_exp * sp);
+      num = pow(vm / p.sigma0, p.p_norm) * ex * JxW;
+      den = ex * JxW;
+    }
+  }
+  if (p.partial) block_sum2(num, den, p.partial);
+}
+
+// pass 2: T_q = kappa_q * M_q * J^-T per (element, qp), 9 doubles
+__global__ void __launch_bounds__(TB) stress_dq_qp_kernel(const StressParams p) {
+  const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int64_t nqp = p.n_elem * p.nq;
+  if (t >= nqp) return;
+  const int64_t e = t / p.nq;
+  const int q = (int)(t - e * p.nq);
+  double* T = p.scratch + t * 9;
+  if (p.elem_mask && !p.elem_mask[e]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T[i] = 0.;
+    return;
+  }
+  QpGeom g;
+  eval_qp(p, e, q, g);  // the stress follows the strain measure; its derivative uses B_lin (the reference's 2D pattern)
+  const double pp = vm_pp(g.sig);
+  const double vm = sqrt(pp);
+  const double JxW = g.det * g.wq;
+  const double Sn = p.sum_num, Sd = p.sum_den;
+  const double sp_w = (vm - p.sigma0) / p.sigma0;
+  const double sp_s = pow(vm / p.sigma0, p.p_norm), sp1_s = pow(vm / p.sigma0, p.p_norm - 1.);
+  double cn, cd;
+  if (p.rho_exp * sp_w > 1.e2) {
+    cn = p.p_norm * sp1_s * exp(1.e2) / p.sigma0 * JxW;
+    cd = 0.;
+  } else {
+    const double ex = exp(p.rho_exp * sp_w);
+    cd = ex * p.rho_exp / p.sigma0 * JxW;
+    cn = 1. / p.sigma0 * JxW * ex * (p.p_norm * sp1_s + sp_s * p.rho_exp);
+  }
+  const double kappa = p.sigma0 / p.p_norm * pow(Sn / Sd, 1. / p.p_norm - 1.) * (cn / Sd - Sn / (Sd * Sd) * cd);
+  double dv[6] = {0., 0., 0., 0., 0., 0.};
+  if (fabs(pp) > 0.) {
+    const double h = 0.5 / sqrt(pp);
+    const double a = g.sig[0] - g.sig[1], b = g.sig[1] - g.sig[2], c = g.sig[2] - g.sig[0];
+    dv[0] = (a - c) * h; dv[1] = (b - a) * h; dv[2] = (c - b) * h;
+    dv[3] = 6. * g.sig[3] * h; dv[4] = 6. * g.sig[4] * h; dv[5] = 6. * g.sig[5] * h;
+  }
+  // m = D dv (D symmetric): de_j = m^T B_lin[:, j]
+  const double lam = g.E * p.lam1, mu = g.E * p.mu1, tr = dv[0] + dv[1] + dv[2];
+  const double m0 = lam * tr + 2. * mu * dv[0], m1 = lam * tr + 2. * mu * dv[1], m2 = lam * tr + 2. * mu * dv[2];
+  const double m3 = mu * dv[3], m4 = mu * dv[4], m5 = mu * dv[5];
+  const double M[3][3] = {{m0, m3, m5}, {m3, m1, m4}, {m5, m4, m2}};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+      T[k * 3 + r] = kappa * (M[k][0] * g.inv[0][r] + M[k][1] * g.inv[1][r] + M[k][2] * g.inv[2][r]);
+}
+
+// pass 3: dq_dX rows of the owned nodes
+__global__ void __launch_bounds__(TB) stress_dq_gather_kernel(const StressParams p) {
+  const int64_t r = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (r >= p.n_owned) return;
+  const int n = p.owned_nodes[r];
+  const unsigned cm = p.cmask ? p.cmask[n] : 0u;
+  const int nn = p.nn, nq = p.nq;
+  double acc[3] = {0., 0., 0.};
+  for (int64_t ke = p.n2e_ptr[n]; ke < p.n2e_ptr[n + 1]; ++ke) {
+    const int64_t e = p.n2e[ke];
+    if (p.diag_elem && p.diag_elem[e]) continue;
+    const int32_t* en = p.conn + e * nn;
+    int a = 0;
+    for (int b = 0; b < nn; ++b)
+      if (en[b] == n) a = b;
+    double o[3] = {0., 0., 0.};
+    for (int q = 0; q < nq; ++q) {
+      const double* T = p.scratch + (e * nq + q) * 9;
+      const double* d = p.tab + (size_t)nq * nn + ((size_t)q * nn + a) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) o[k] += T[k * 3] * d[0] + T[k * 3 + 1] * d[1] + T[k * 3 + 2] * d[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc[k] += o[k];
+  }
+  for (int k = 0; k < p.nv; ++k) p.dq_dX[(int64_t)n * p.nv + k] = (k < 3 && !((cm >> k) & 1u)) ? acc[k] : 0.;
+}
+
+__global__ void reduce_pairs_kernel(const double* partial, int n, double* out) {
+  // single warp, fixed order: lane-strided partial sums, then a butterfly
+  double a = 0., b = 0.;
+  for (int i = threadIdx.x; i < n; i += 32) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  if (threadIdx.x == 0) { out[0] = a; out[1] = b; }
+}
+
+}  // namespace
+
+int stress_blocks(int64_t n_elem, int nq) { return (int)((n_elem * nq + TB - 1) / TB); }
+
+cudaError_t launch_stress_qp(const StressParams& p, cudaStream_t stream) {
+  stress_qp_kernel<<<stress_blocks(p.n_elem, p.nq), TB, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaStream_t stream) {
+  reduce_pairs_kernel<<<1, 32, 0, stream>>>(partial, n, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream) {
+  stress_dq_qp_kernel<<<stress_blocks(p.n_elem, p.nq), TB, 0, stream>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  stress_dq_gather_kernel<<<(int)((p.n_owned + TB - 1) / TB), TB, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mastb200

@@ -140,6 +140,18 @@ class Problem:
         assert lib().oracle_compliance_derivative(C.byref(self.s), _p(X), _p(out)) == 0
         return out
 
+    def stress(self, X):
+        nq = self.nn
+        n = self.n_elem * nq
+        st = np.empty((n, 6)); en = np.empty((n, 6)); vm = np.empty(n); jw = np.empty(n)
+        assert lib().oracle_stress(C.byref(self.s), _p(X), _p(st), _p(en), _p(vm), _p(jw)) == 0
+        return st, en, vm, jw
+
+    def stress_functional(self, X, p_norm, rho_exp, sigma0, want_derivative=False):
+        dq = np.empty(self.n_dof) if want_derivative else None
+        q = lib().oracle_stress_functional(C.byref(self.s), _p(X), p_norm, rho_exp, sigma0, _p(dq))
+        return (q, dq) if want_derivative else q
+
     def time_residual_and_jacobian(self, X, threads, want_R=True, want_J=True):
         row_ptr, col = self.pattern()
         R = np.empty(self.n_dof) if want_R else None
