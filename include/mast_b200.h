@@ -46,7 +46,7 @@ extern "C" {
 /* element types (libMesh node ordering) */
 #define MASTB200_HEX8 8
 #define MASTB200_HEX27 27
-#define MASTB200_QUAD4 4 /* 2D heat conduction in the xy-plane */
+#define MASTB200_QUAD4 4 /* in the xy-plane: nv = 1 heat conduction, nv = 6 Mindlin plate */
 
 typedef struct mastb200_context mastb200_context;
 
@@ -60,6 +60,11 @@ typedef struct mastb200_material {
   double k0, k_beta, thickness;
   int32_t k_of_T;
   double heat_source;
+  /* 2D plate section (QUAD4 with nv = 6: StructuralElement2D, Mindlin bending): thickness above, mid-plane offset,
+   * shear correction factor, plane_strain = 0 (plane stress) | 1
+   * (solid_2d_section_element_property_card.cpp:395-510, isotropic_material_property_card.cpp:395-426) */
+  double offset, kappa;
+  int32_t plane_strain;
 } mastb200_material;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */

@@ -34,7 +34,8 @@ class Material(C.Structure):
     _fields_ = [("E0", C.c_double), ("nu", C.c_double), ("alpha", C.c_double), ("rho_min", C.c_double),
                 ("penalty", C.c_double), ("nonlinear_strain", C.c_int32), ("k0", C.c_double),
                 ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32),
-                ("heat_source", C.c_double)]
+                ("heat_source", C.c_double), ("offset", C.c_double), ("kappa", C.c_double),
+                ("plane_strain", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -164,7 +165,9 @@ class Context:
                      rho_min=kw.get("rho_min", 0.0), penalty=kw.get("penalty", 1.0),
                      nonlinear_strain=int(kw.get("nonlinear_strain", 0)), k0=kw.get("k0", 0.0),
                      k_beta=kw.get("k_beta", 0.0), thickness=kw.get("thickness", 1.0),
-                     k_of_T=int(kw.get("k_of_T", 0)), heat_source=kw.get("heat_source", 0.0))
+                     k_of_T=int(kw.get("k_of_T", 0)), heat_source=kw.get("heat_source", 0.0),
+                     offset=kw.get("offset", 0.0), kappa=kw.get("kappa", 5.0 / 6.0),
+                     plane_strain=int(kw.get("plane_strain", 0)))
         self._ck(self._lib.mastb200_set_material(self._h, C.byref(m)))
 
     def set_side_pressure(self, elem, side, pressure):

@@ -349,11 +349,61 @@ int ensure_generic_plan(mastb200_context* ctx) {
   return MASTB200_OK;
 }
 
+// QUAD4 Mindlin plate in the xy-plane (row-block gather)
+int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
+  int rc;
+  if (ctx->mat.nonlinear_strain)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "von Karman strain of the plate element is not on the device path");
+  for (int64_t n = 1; n < ctx->n_nodes; ++n)
+    if (ctx->xyz[n * 3 + 2] != ctx->xyz[2])
+      return ctx->fail(MASTB200_ERR_UNSUPPORTED, "plate elements out of the xy-plane are not on the device path");
+  if ((rc = ensure_generic_plan(ctx))) return rc;
+  mastb200_context::GenericPlan& G = ctx->gplan;
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const size_t nnz = (size_t)plan_nnz(ctx);
+  const double* dX = nullptr;
+  double *dR = nullptr, *dJ = nullptr;
+  if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
+  if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
+  const mastb200_material& m = ctx->mat;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (dR && ctx->has_ghosts) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  PlateParams p;
+  p.n_owned = ctx->pat.n_owned; p.n_entries = ctx->pat.nbr_ptr[ctx->pat.n_owned];
+  p.owned_nodes = ctx->d_owned_nodes.p;
+  p.nbr_ptr = G.nbr_ptr.p; p.nbr = G.nbr.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p; p.conn = G.conn.p;
+  p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+  p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+  p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
+  // StiffnessMatrix2D (isotropic_material_property_card.cpp:395-426)
+  if (!m.plane_strain) {
+    p.c11 = m.E0 / (1. - m.nu * m.nu); p.c12 = m.E0 * m.nu / (1. - m.nu * m.nu);
+  } else {
+    p.c11 = m.E0 * (1. - m.nu) / ((1. + m.nu) * (1. - 2. * m.nu)); p.c12 = m.E0 * m.nu / ((1. + m.nu) * (1. - 2. * m.nu));
+  }
+  p.c33 = m.E0 / 2. / (1. + m.nu);
+  p.shear_G = m.E0 / 2. / (1. + m.nu);
+  p.thickness = m.thickness; p.offset = m.offset; p.kappa = m.kappa;
+  CU(launch_quad4_plate(p, ctx->stream));
+  ctx->launches++;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->last_R = dR;
+  if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
+  if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
 // QUAD4 heat conduction (row gather) and HEX27 elasticity (coloured DMMA scatter)
 int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
   int rc;
   const bool heat = ctx->elem_type == MASTB200_QUAD4;
-  if (heat && ctx->nv != 1) return ctx->fail(MASTB200_ERR_ARG, "QUAD4 heat conduction needs nv = 1");
+  if (heat && ctx->nv == 6) return run_plate_sweep(ctx, X, R, J);
+  if (heat && ctx->nv != 1) return ctx->fail(MASTB200_ERR_ARG, "QUAD4: nv = 1 (heat conduction) or 6 (Mindlin plate)");
   if (!heat && ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX27 elasticity needs nv = 3 or 6");
   if (!heat && ctx->mat.nonlinear_strain)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain: HEX8 only on the device path");

@@ -68,6 +68,26 @@ size_t hex27_sweep_smem_bytes();
 cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t stream);
 
 
+// ---- QUAD4 Mindlin plate in the xy-plane (sweep_quad4_plate.cu): one thread per (owned node, neighbour) block ------
+struct PlateParams {
+  int64_t n_owned = 0, n_entries = 0;    // n_entries = nbr_ptr[n_owned]
+  const int32_t* owned_nodes = nullptr;
+  const int64_t* nbr_ptr = nullptr;
+  const int32_t* nbr = nullptr;
+  const int64_t* n2e_ptr = nullptr;
+  const int32_t* n2e = nullptr;
+  const int32_t* conn = nullptr;         // [n_elem][4]
+  const uint8_t* diag_elem = nullptr;
+  const uint8_t* cmask = nullptr;
+  const double* xyz = nullptr;
+  const double* X = nullptr;             // [n_nodes*6]
+  double* J = nullptr;
+  double* R = nullptr;
+  double c11 = 0., c12 = 0., c33 = 0.;   // plane-stress / plane-strain material matrix C
+  double shear_G = 0., thickness = 1., offset = 0., kappa = 5. / 6.;
+};
+cudaError_t launch_quad4_plate(const PlateParams& p, cudaStream_t stream);
+
 // ---- HEX8 row-owner gather with Green-Lagrange (or linear) strain (sweep_hex8_gather.cu) ----------------------------
 struct SolidGatherParams {
   int64_t n_owned = 0;

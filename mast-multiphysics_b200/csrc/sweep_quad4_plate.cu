@@ -1,0 +1,197 @@
+// sweep_quad4_plate.cu -- QUAD4 Mindlin plate residual + Jacobian, linear strain, elements in the xy-plane
+// (sm_100a, fp64).
+//
+// Device counterpart of the element loop of MAST::NonlinearImplicitAssembly::residual_and_jacobian
+// (/root/reference/src/base/nonlinear_implicit_assembly.cpp:111-186) with StructuralElement2D::internal_residual
+// (src/elasticity/structural_element_2d.cpp:1075-1227) and ::_internal_residual_operation (:1765-2019): membrane
+// B_lin^T A B_lin, coupling B_lin^T B B_bend + B_bend^T B^T B_lin, bending B_bend^T D B_bend with the Mindlin bending
+// strain operator (src/elasticity/mindlin_bending_operator.cpp:47-80), the transverse shear energy integrated with
+// the rule two orders lower -- one Gauss point for QUAD4 (:94-160, 314-361), the section matrices A = C h, B = C h off,
+// D = C (h^3/12 + h off^2), G kappa h (src/property_cards/solid_2d_section_element_property_card.cpp:395-510, 122-134;
+// C of isotropic_material_property_card.cpp:395-426) and the 1e-8 drilling diagonal (:1217-1221).
+// Elements out of the xy-plane (T K T^T of structural_element_base.cpp:1565-1601) are refused by the host.
+//
+// Row-owner gather: one thread per (owned node, neighbour) pair, i.e. per 6x6 block of the node-level CSR.  The thread
+// walks the elements adjacent to the row node in ascending id (the order of the reference's element loop) and adds
+// K_ab of every element that also holds its neighbour; the diagonal pair also forms the node's force.  No atomics, no
+// colours; every CSR value is accumulated in registers in a fixed order and stored once.
+// Algorithmic bytes per element on a structured mesh: 9 blocks x 36 values x 8 B = 2592 B of J + vectors: HBM-bound.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace mastb200 {
+namespace {
+
+constexpr int TB = 128;
+constexpr double GP = 0.57735026918962576451;
+
+struct Q4 {
+  double N[4], gx[4], gy[4], JxW;
+};
+
+__device__ __forceinline__ void q4_eval(const double* x, const double* y, double xi, double eta, double w, Q4& o) {
+  const double sx[4] = {-1., 1., 1., -1.}, sy[4] = {-1., -1., 1., 1.};
+  double d0[4], d1[4];
+  double j00 = 0., j01 = 0., j10 = 0., j11 = 0.;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    const double fx = 0.5 * (1. + sx[b] * xi), fy = 0.5 * (1. + sy[b] * eta);
+    o.N[b] = fx * fy;
+    d0[b] = 0.5 * sx[b] * fy;
+    d1[b] = fx * 0.5 * sy[b];
+    j00 += d0[b] * x[b]; j01 += d0[b] * y[b];
+    j10 += d1[b] * x[b]; j11 += d1[b] * y[b];
+  }
+  const double det = j00 * j11 - j10 * j01;
+  const double inv = 1. / det;
+  o.JxW = det * w;
+  const double dxidx = j11 * inv, dxidy = -j10 * inv, detadx = -j01 * inv, detady = j00 * inv;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    o.gx[b] = d0[b] * dxidx + d1[b] * detadx;
+    o.gy[b] = d0[b] * dxidy + d1[b] * detady;
+  }
+}
+
+__global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
+  const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (t >= p.n_entries) return;
+  // row of this neighbour entry: last r with nbr_ptr[r] <= t
+  int64_t lo = 0, hi = p.n_owned;
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (p.nbr_ptr[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int64_t r = lo;
+  const int n = p.owned_nodes[r];
+  const int64_t nb0 = p.nbr_ptr[r];
+  const int nnb = (int)(p.nbr_ptr[r + 1] - nb0);
+  const int c = (int)(t - nb0);
+  const int m = p.nbr[t];
+  const bool self = m == n;
+  const unsigned cmn = p.cmask ? p.cmask[n] : 0u, cmm = p.cmask ? p.cmask[m] : 0u;
+
+  const double c11 = p.c11, c12 = p.c12, c33 = p.c33;
+  const double h = p.thickness, hoff = p.thickness * p.offset;
+  const double hD = p.thickness * p.thickness * p.thickness / 12. + p.thickness * p.offset * p.offset;
+  const double Gs = p.shear_G * p.thickness * p.kappa;
+
+  double K[6][6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) K[i][j] = 0.;
+  double f[6] = {0., 0., 0., 0., 0., 0.};
+  int nadj = 0, nadjd = 0;
+
+  for (int64_t ke = p.n2e_ptr[n]; ke < p.n2e_ptr[n + 1]; ++ke) {
+    const int e = p.n2e[ke];
+    if (p.diag_elem && p.diag_elem[e]) { ++nadjd; continue; }
+    ++nadj;
+    int en[4], a = 0, b = -1;
+    double x[4], y[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      en[k] = p.conn[(int64_t)e * 4 + k];
+      x[k] = p.xyz[(int64_t)en[k] * 3];
+      y[k] = p.xyz[(int64_t)en[k] * 3 + 1];
+      if (en[k] == n) a = k;
+      if (en[k] == m) b = k;
+    }
+    if (b < 0) continue;
+    const bool want_f = self && p.R;
+    double U[4][6];
+    if (want_f)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int v = 0; v < 6; ++v) U[k][v] = p.X[(int64_t)en[k] * 6 + v];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      Q4 g;
+      q4_eval(x, y, (q & 1) ? GP : -GP, (q & 2) ? GP : -GP, 1., g);
+      const double gxa = g.gx[a], gya = g.gy[a], gxb = g.gx[b], gyb = g.gy[b];
+      if (p.J) {
+        // M[p][q] = s_p(a)^T C s_q(b),  s_1 = [gx, 0, gy], s_2 = [0, gy, gx]
+        const double M00 = gxa * c11 * gxb + gya * c33 * gyb, M01 = gxa * c12 * gyb + gya * c33 * gxb;
+        const double M10 = gya * c12 * gxb + gxa * c33 * gyb, M11 = gya * c11 * gyb + gxa * c33 * gxb;
+        const double wA = g.JxW * h, wB = g.JxW * hoff, wD = g.JxW * hD;
+        K[0][0] += wA * M00; K[0][1] += wA * M01; K[1][0] += wA * M10; K[1][1] += wA * M11;      // membrane
+        K[0][3] += wB * (-M01); K[0][4] += wB * M00; K[1][3] += wB * (-M11); K[1][4] += wB * M10;  // membrane - bending
+        K[3][0] += wB * (-M10); K[3][1] += wB * (-M11); K[4][0] += wB * M00; K[4][1] += wB * M01;  // bending - membrane
+        K[3][3] += wD * M11; K[3][4] += wD * (-M10); K[4][3] += wD * (-M01); K[4][4] += wD * M00;  // bending
+      }
+      if (want_f) {
+        double e0 = 0., e1 = 0., e2 = 0., k0 = 0., k1 = 0., k2 = 0.;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          e0 += g.gx[k] * U[k][0]; e1 += g.gy[k] * U[k][1]; e2 += g.gy[k] * U[k][0] + g.gx[k] * U[k][1];
+          k0 += g.gx[k] * U[k][4]; k1 += -g.gy[k] * U[k][3]; k2 += -g.gx[k] * U[k][3] + g.gy[k] * U[k][4];
+        }
+        const double Ce0 = c11 * e0 + c12 * e1, Ce1 = c12 * e0 + c11 * e1, Ce2 = c33 * e2;
+        const double Ck0 = c11 * k0 + c12 * k1, Ck1 = c12 * k0 + c11 * k1, Ck2 = c33 * k2;
+        const double N0 = h * Ce0 + hoff * Ck0, N1 = h * Ce1 + hoff * Ck1, N2 = h * Ce2 + hoff * Ck2;
+        const double Q0 = hoff * Ce0 + hD * Ck0, Q1 = hoff * Ce1 + hD * Ck1, Q2 = hoff * Ce2 + hD * Ck2;
+        f[0] += g.JxW * (gxa * N0 + gya * N2);
+        f[1] += g.JxW * (gya * N1 + gxa * N2);
+        f[3] += g.JxW * (-(gya * Q1 + gxa * Q2));
+        f[4] += g.JxW * (gxa * Q0 + gya * Q2);
+      }
+    }
+    {  // transverse shear at the single point of the reduced rule (weight 4)
+      Q4 g;
+      q4_eval(x, y, 0., 0., 4., g);
+      const double w = g.JxW * Gs;
+      const double gxa = g.gx[a], gya = g.gy[a], Na = g.N[a], gxb = g.gx[b], gyb = g.gy[b], Nb = g.N[b];
+      if (p.J) {
+        K[2][2] += w * (gxa * gxb + gya * gyb); K[2][3] += w * (-(gya * Nb)); K[2][4] += w * (gxa * Nb);
+        K[3][2] += w * (-(Na * gyb)); K[3][3] += w * (Na * Nb);
+        K[4][2] += w * (Na * gxb); K[4][4] += w * (Na * Nb);
+      }
+      if (want_f) {
+        double g0 = 0., g1 = 0.;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          g0 += g.gx[k] * U[k][2] + g.N[k] * U[k][4];
+          g1 += g.gy[k] * U[k][2] - g.N[k] * U[k][3];
+        }
+        f[2] += w * (gxa * g0 + gya * g1);
+        f[3] += w * (-(Na * g1));
+        f[4] += w * (Na * g0);
+      }
+    }
+    if (self) K[5][5] += 1.0e-8;  // drilling dof (structural_element_2d.cpp:1217-1221)
+  }
+
+  if (p.J) {
+    const double nadj_all = double(nadj + nadjd);
+    double* dst = p.J + 36 * nb0 + 6 * c;
+    const int rl = 6 * nnb;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        double k = K[i][j];
+        if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
+        if (self && i == j) {
+          if ((cmn >> i) & 1u) k = nadj_all;
+          else k += 1.0e-24 * nadjd;
+        }
+        dst[i * rl + j] = k;
+      }
+  }
+  if (p.R && self)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) p.R[(int64_t)n * 6 + i] = ((cmn >> i) & 1u) ? 0. : f[i];
+}
+
+}  // namespace
+
+cudaError_t launch_quad4_plate(const PlateParams& p, cudaStream_t stream) {
+  const int blocks = (int)((p.n_entries + TB - 1) / TB);
+  quad4_plate_kernel<<<blocks, TB, 0, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mastb200

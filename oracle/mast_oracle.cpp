@@ -621,6 +621,142 @@ static void solid3d_thermal_residual(const OracleProblem* p, const FE& fe, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// StructuralElement2D::internal_residual for a QUAD4 Mindlin plate in the xy-plane, linear strain
+// (structural_element_2d.cpp:1075-1227, ::_internal_residual_operation :1765-2019,
+//  ::initialize_green_lagrange_strain_operator :141-250, MindlinBendingOperator
+//  mindlin_bending_operator.cpp:47-80 (bending strain), :94-160 + :314-361 (transverse shear with the
+//  quadrature order reduced by two: one Gauss point for QUAD4), section matrices A = C h,
+//  B = C h off, D = C (h^3/12 + h off^2) of solid_2d_section_element_property_card.cpp:395-510,
+//  transverse shear G kappa h (:122-134; isotropic_material_property_card.cpp:336-345), plane-stress /
+//  plane-strain C of isotropic_material_property_card.cpp:395-426, drilling diagonal 1e-8 (:1217-1221)).
+// Elements out of the xy-plane would need the T K T^T transform of structural_element_base.cpp:1565-1601;
+// the element is in the plane here (geom_elem.cpp:358-374), so local == global.
+// ---------------------------------------------------------------------------------------------
+static void stiffness_2d(double E, double nu, bool plane_stress, Mat& m) {
+  m.resize(3, 3);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) {
+      if (plane_stress) m(i, j) = (i == j) ? E / (1. - nu * nu) : E * nu / (1. - nu * nu);
+      else m(i, j) = (i == j) ? E * (1. - nu) / ((1. + nu) * (1. - 2. * nu)) : E * nu / ((1. + nu) * (1. - 2. * nu));
+    }
+  m(2, 2) = E / 2. / (1. + nu);
+}
+
+static Mat scaled(const Mat& m, double s) {
+  Mat r = m;
+  for (double& v : r.a) v *= s;
+  return r;
+}
+static Mat transposed(const Mat& m) {
+  Mat r(m.c, m.r);
+  for (int i = 0; i < m.r; ++i)
+    for (int j = 0; j < m.c; ++j) r(j, i) = m(i, j);
+  return r;
+}
+
+// FE of the QUAD4 at the single point of the order-1 Gauss rule (xi = eta = 0, weight 4)
+static void fe_init_quad4_reduced(const double* X, FE& fe) {
+  fe.nn = 4; fe.nq = 1; fe.dim = 2;
+  fe.phi.assign(4, 0.); fe.dphi.assign(12, 0.); fe.JxW.assign(1, 0.); fe.xyz.assign(3, 0.);
+  double Jm[2][2] = {{0, 0}, {0, 0}}, dref[4][2];
+  for (int a = 0; a < 4; ++a) {
+    const double li = lag1(1, Q4_I[a], 0.), lj = lag1(1, Q4_J[a], 0.);
+    fe.phi[a] = li * lj;
+    dref[a][0] = dlag1(1, Q4_I[a], 0.) * lj;
+    dref[a][1] = li * dlag1(1, Q4_J[a], 0.);
+    for (int c = 0; c < 2; ++c) {
+      Jm[0][c] += dref[a][0] * X[a * 3 + c];
+      Jm[1][c] += dref[a][1] * X[a * 3 + c];
+    }
+    for (int c = 0; c < 3; ++c) fe.xyz[c] += fe.phi[a] * X[a * 3 + c];
+  }
+  const double det = Jm[0][0] * Jm[1][1] - Jm[1][0] * Jm[0][1], inv = 1. / det;
+  fe.JxW[0] = det * 4.;
+  const double dxidx = Jm[1][1] * inv, dxidy = -Jm[1][0] * inv, detadx = -Jm[0][1] * inv, detady = Jm[0][0] * inv;
+  for (int a = 0; a < 4; ++a) {
+    fe.dphi[a * 3 + 0] = dref[a][0] * dxidx + dref[a][1] * detadx;
+    fe.dphi[a * 3 + 1] = dref[a][0] * dxidy + dref[a][1] * detady;
+  }
+}
+
+static void plate_internal_residual(const OracleProblem* p, const FE& fe, const double* X, const Vec& sol,
+                                    bool request_jacobian, Vec& f, Mat& jac) {
+  const int nn = fe.nn, n2 = 6 * nn;
+  Mat C, A, B, D, mat1, mat2, mat3;
+  stiffness_2d(p->E0, p->nu, p->plane_strain == 0, C);
+  const double h = p->thickness, off = p->offset;
+  A = scaled(C, h);                                    // ExtensionStiffnessMatrix
+  B = scaled(C, h * off);                              // ExtensionBendingStiffnessMatrix
+  D = scaled(C, std::pow(h, 3) / 12. + h * std::pow(off, 2));  // BendingStiffnessMatrix
+  OperatorMatrix Bl, Bb;
+  Bl.reinit(3, 6, nn); Bb.reinit(3, 6, nn);
+  Vec phi(nn), strain, vec1, vec2, vec3, local_f(n2, 0.);
+  Mat local_jac(n2, n2);
+  for (int qp = 0; qp < fe.nq; ++qp) {
+    const double JxW = fe.JxW[qp];
+    for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 0);
+    Bl.set_shape_function(0, 0, phi); Bl.set_shape_function(2, 1, phi);     // :184-186
+    Bb.set_shape_function(0, 4, phi);                                       // mindlin :69
+    for (int a = 0; a < nn; ++a) phi[a] = -fe.dN(a, qp, 0);
+    Bb.set_shape_function(2, 3, phi);                                       // :71
+    for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 1);
+    Bl.set_shape_function(1, 1, phi); Bl.set_shape_function(2, 0, phi);     // :203-204
+    Bb.set_shape_function(2, 4, phi);                                       // :78
+    for (int a = 0; a < nn; ++a) phi[a] = -fe.dN(a, qp, 1);
+    Bb.set_shape_function(1, 3, phi);                                       // :81
+    Bl.vector_mult(strain, sol);
+    vec2 = matvec(A, strain);                       // membrane stress  :1815
+    Bb.vector_mult(vec1, sol);
+    { const Vec t = matvec(B, vec1); for (int i = 0; i < 3; ++i) vec2[i] += t[i]; }  // :1822
+    Bl.vector_mult_transpose(vec3, vec2);
+    for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];               // :1846-1847
+    vec1 = matvec_t(B, strain);                                             // :1875
+    Bb.vector_mult_transpose(vec3, vec1);
+    for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];
+    Bb.vector_mult(vec2, sol);                                              // :1880-1883
+    vec1 = matvec(D, vec2);
+    Bb.vector_mult_transpose(vec3, vec1);
+    for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];
+    if (request_jacobian) {
+      Bl.left_multiply(mat1, A); Bl.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);  // :1888-1890
+      mat3 = transposed(B);
+      Bl.left_multiply(mat1, mat3); Bb.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);  // :2001-2004
+      Bb.left_multiply(mat1, B); Bl.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);     // :2007-2009
+      Bb.left_multiply(mat1, D); Bb.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);     // :2012-2014
+    }
+  }
+  {  // MindlinBendingOperator::calculate_transverse_shear_residual  (mindlin_bending_operator.cpp:94-160, 314-361)
+    FE fs;
+    fe_init_quad4_reduced(X, fs);
+    Mat G(2, 2);
+    G(0, 0) = G(1, 1) = p->E0 / 2. / (1. + p->nu);
+    G = scaled(scaled(G, h), p->kappa);
+    OperatorMatrix Bt;
+    Bt.reinit(2, 6, nn);
+    for (int a = 0; a < nn; ++a) phi[a] = fs.dN(a, 0, 0);
+    Bt.set_shape_function(0, 2, phi);
+    for (int a = 0; a < nn; ++a) phi[a] = fs.dN(a, 0, 1);
+    Bt.set_shape_function(1, 2, phi);
+    for (int a = 0; a < nn; ++a) phi[a] = fs.N(a, 0);
+    Bt.set_shape_function(0, 4, phi);
+    for (int a = 0; a < nn; ++a) phi[a] = -fs.N(a, 0);
+    Bt.set_shape_function(1, 3, phi);
+    Bt.vector_mult(vec1, sol);
+    vec1 = matvec(G, vec1);
+    Bt.vector_mult_transpose(vec3, vec1);
+    for (int i = 0; i < n2; ++i) local_f[i] += fs.JxW[0] * vec3[i];
+    if (request_jacobian) {
+      Bt.left_multiply(mat1, G); Bt.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, fs.JxW[0]);
+    }
+  }
+  for (int i = 0; i < n2; ++i) f[i] += local_f[i];  // transform_vector_to_global_system: identity in the xy-plane
+  if (request_jacobian) {
+    for (int i = 0; i < nn; ++i) local_jac(5 * nn + i, 5 * nn + i) = 1.0e-8;  // :1217-1221
+    add_scaled_top_left(jac, local_jac, 1.);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // HeatConductionElementBase::internal_residual (heat_conduction_elem_base.cpp:53-149), QUAD4 with
 // Solid2DSectionProperty::ThermalConductanceMatrix = k*h (solid_2d_section_element_property_card.cpp:940-953)
 // and volume_heat_source_residual (:1709-1745)
@@ -735,7 +871,8 @@ static void elem_calculations(const OracleProblem* p, const SideLoadIndex& sl, i
   vec.assign(nd, 0.);
   mat.resize(nd, nd);
   if (p->elem_type == ORACLE_QUAD4) {
-    heat_elem_calculations(p, fe, sol, if_jac, vec, mat);
+    if (p->nv == 6) plate_internal_residual(p, fe, X.data(), sol, if_jac, vec, mat);  // StructuralElement2D
+    else heat_elem_calculations(p, fe, sol, if_jac, vec, mat);
     return;
   }
   const int32_t* en = &p->conn[e * ei.nn];
@@ -1106,6 +1243,20 @@ double oracle_stress_functional(const OracleProblem* p, const double* X, double 
     for (int j = 0; j < nd; ++j) dq_dX[di[j]] += out[j];
   }
   return q;
+}
+
+void oracle_plate_section_matrices(double E, double nu, double h, double off, double kappa, int plane_strain,
+                                   double* A9, double* B9, double* D9, double* S4) {
+  Mat C;
+  stiffness_2d(E, nu, plane_strain == 0, C);
+  const Mat A = scaled(C, h), B = scaled(C, h * off), D = scaled(C, std::pow(h, 3) / 12. + h * std::pow(off, 2));
+  std::copy(A.a.begin(), A.a.end(), A9);
+  std::copy(B.a.begin(), B.a.end(), B9);
+  std::copy(D.a.begin(), D.a.end(), D9);
+  Mat G(2, 2);
+  G(0, 0) = G(1, 1) = E / 2. / (1. + nu);
+  G = scaled(scaled(G, h), kappa);
+  std::copy(G.a.begin(), G.a.end(), S4);
 }
 
 void oracle_stiffness_3d(double E, double nu, double* D36) {

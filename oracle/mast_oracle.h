@@ -29,7 +29,7 @@ enum { ORACLE_HEX8 = 8, ORACLE_HEX27 = 27, ORACLE_QUAD4 = 4 };
 /* One analysis: mesh + dof layout + property card + loads.  All arrays are caller-owned. */
 typedef struct OracleProblem {
   /* mesh (libMesh node ordering of each element) */
-  int32_t elem_type;          /* ORACLE_HEX8 | ORACLE_HEX27 (3D solid) | ORACLE_QUAD4 (2D heat conduction) */
+  int32_t elem_type;          /* ORACLE_HEX8 | ORACLE_HEX27 (3D solid) | ORACLE_QUAD4 (nv=1: 2D heat conduction; nv=6: Mindlin plate) */
   int64_t n_elem, n_nodes;
   const double* xyz;          /* [n_nodes][3] */
   const int32_t* conn;        /* [n_elem][nn] */
@@ -55,6 +55,10 @@ typedef struct OracleProblem {
   double k0, k_beta, thickness;
   int32_t k_of_T;             /* 1 => attach the active solution function (dk/dT tangent term) */
   double heat_source;         /* volumetric heat source q (HEAT_SOURCE volume load), 0 = none */
+  /* 2D plate section (elem_type QUAD4, nv=6: StructuralElement2D with Mindlin bending): thickness above, mid-plane
+   * offset, shear correction factor kappa, plane_strain = 0 (plane stress) | 1 */
+  double offset, kappa;
+  int32_t plane_strain;
 } OracleProblem;
 
 /* libMesh-style sparsity: every (row,col) pair of dofs that share an element; columns sorted.
@@ -95,6 +99,11 @@ double oracle_stress_functional(const OracleProblem* p, const double* X, double 
 void oracle_stiffness_3d(double E, double nu, double* D36);
 void oracle_stiffness_3d_derivative(double E, double nu, double dE, double dnu, double* D36);
 void oracle_thermal_expansion_A_3d(double E, double nu, double alpha, double* v6);
+
+/* Solid2DSectionProperty matrices (solid_2d_section_element_property_card.cpp:395-510, :122-134): A = C h,
+ * B = C h off, D = C (h^3/12 + h off^2) (3x3 row-major each), transverse shear S = G kappa h (2x2) */
+void oracle_plate_section_matrices(double E, double nu, double h, double off, double kappa, int plane_strain,
+                                   double* A9, double* B9, double* D9, double* S4);
 
 /* FE tables of one element (libMesh FE restatement): phi[nn*nq], dphi[nn*nq*3], JxW[nq], xyz[nq*3] */
 int oracle_fe_tables(int32_t elem_type, const double* coords /* [nn][3] */, double* phi, double* dphi,

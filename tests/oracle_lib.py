@@ -18,6 +18,7 @@ class OracleProblem(C.Structure):
         ("side_pressure", C.c_void_p), ("thermal", C.c_int32), ("temperature", C.c_void_p),
         ("temperature_const", C.c_double), ("ref_temperature", C.c_double), ("k0", C.c_double),
         ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32), ("heat_source", C.c_double),
+        ("offset", C.c_double), ("kappa", C.c_double), ("plane_strain", C.c_int32),
     ]
 
 
@@ -43,6 +44,7 @@ def lib():
         L.oracle_stiffness_3d.argtypes = [dbl, dbl, vp]
         L.oracle_stiffness_3d_derivative.argtypes = [dbl, dbl, dbl, dbl, vp]
         L.oracle_thermal_expansion_A_3d.argtypes = [dbl, dbl, dbl, vp]
+        L.oracle_plate_section_matrices.argtypes = [dbl, dbl, dbl, dbl, dbl, C.c_int, vp, vp, vp, vp]
         L.oracle_fe_tables.argtypes = [C.c_int32, vp, vp, vp, vp, vp]
         L.oracle_time_residual_and_jacobian.argtypes = [P, vp, vp, vp, vp, vp, C.c_int]
         L.oracle_time_residual_and_jacobian.restype = dbl
@@ -60,7 +62,7 @@ class Problem:
     def __init__(self, elem_type, xyz, conn, nv, constrained=None, E0=72e9, nu=0.33, alpha=0.0, rho=None,
                  rho_min=0.0, penalty=1.0, nonlinear_strain=0, side_elem=None, side_id=None, side_pressure=None,
                  thermal=0, temperature=None, temperature_const=0.0, ref_temperature=0.0, k0=0.0, k_beta=0.0,
-                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None):
+                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None, offset=0.0, kappa=5.0 / 6.0, plane_strain=0):
         self.elem_type = elem_type
         self.xyz = np.ascontiguousarray(xyz, np.float64)
         self.conn = np.ascontiguousarray(conn, np.int32)
@@ -75,7 +77,8 @@ class Problem:
         self.temperature = None if temperature is None else np.ascontiguousarray(temperature, np.float64)
         self.diag_elem = None if diag_elem is None else np.ascontiguousarray(diag_elem, np.uint8)
         self.mat = dict(E0=E0, nu=nu, alpha=alpha, rho_min=rho_min, penalty=penalty, nonlinear_strain=nonlinear_strain,
-                        k0=k0, k_beta=k_beta, thickness=thickness, k_of_T=k_of_T, heat_source=heat_source)
+                        k0=k0, k_beta=k_beta, thickness=thickness, k_of_T=k_of_T, heat_source=heat_source,
+                        offset=offset, kappa=kappa, plane_strain=plane_strain)
         self.thermal, self.temperature_const, self.ref_temperature = thermal, temperature_const, ref_temperature
         s = OracleProblem()
         s.elem_type = elem_type; s.n_elem = self.n_elem; s.n_nodes = self.n_nodes
@@ -88,6 +91,7 @@ class Problem:
         s.thermal = thermal; s.temperature = _p(self.temperature); s.temperature_const = temperature_const
         s.ref_temperature = ref_temperature
         s.k0 = k0; s.k_beta = k_beta; s.thickness = thickness; s.k_of_T = k_of_T; s.heat_source = heat_source
+        s.offset = offset; s.kappa = kappa; s.plane_strain = plane_strain
         self.s = s
         self._pattern = None
 

@@ -394,3 +394,53 @@ def test_hex27_stress_output_and_aggregate(built):
     # BASELINE config C5's output: stress aggregate + its adjoint right-hand side on HEX27
     prob = _hex27_problem(3, 2, 2, jitter=0.1)
     _stress_case(prob, O.state(prob.n_dof, 1), p_norm=6.0, rho_exp=1.0)
+
+
+# ---- QUAD4 Mindlin plate (StructuralElement2D) -----------------------------------------------------------------------
+def _plate_problem(nx, ny, jitter=0.0, offset=0.03, plane_strain=0, diag=False, scramble=False):
+    xyz, conn = mesh.build_square(nx, ny, 1.5, 1.0)
+    rng = np.random.default_rng(11)
+    if jitter:
+        inner = (xyz[:, 0] > 0) & (xyz[:, 0] < 1.5) & (xyz[:, 1] > 0) & (xyz[:, 1] < 1.0)
+        xyz[inner, :2] += jitter * np.array([1.5 / nx, 1.0 / ny]) * rng.uniform(-1, 1, (inner.sum(), 2))
+    con = mesh.dirichlet_flags(len(xyz), 6, np.flatnonzero(xyz[:, 0] == 0.0))
+    con2 = con.reshape(-1, 6); con2[np.flatnonzero(xyz[:, 1] == 1.0)[::2], 2] = 1  # a few w-only supports
+    con = con2.ravel()
+    d = None
+    if diag:
+        d = np.zeros(len(conn), np.uint8); d[[1, 5]] = 1
+    if scramble:
+        perm = rng.permutation(len(xyz))
+        xyz2 = np.empty_like(xyz); xyz2[perm] = xyz
+        c6 = np.empty_like(con2); c6[perm] = con2
+        xyz, con = xyz2, c6.ravel()
+        conn = perm[conn].astype(np.int32)[rng.permutation(len(conn))]
+    return O.Problem(O.QUAD4, xyz, conn, 6, constrained=con, E0=72e9, nu=0.33, thickness=0.06, offset=offset,
+                     kappa=5.0 / 6.0, plane_strain=plane_strain, diag_elem=d)
+
+
+@pytest.mark.parametrize("offset,plane_strain", [(0.0, 0), (0.03, 0), (0.03, 1)])
+def test_quad4_mindlin_plate_residual_and_jacobian(built, offset, plane_strain):
+    prob = _plate_problem(9, 6, jitter=0.2, offset=offset, plane_strain=plane_strain)
+    X = O.state(prob.n_dof, 1)
+    ctx, R, J = _check_RJ(prob, X)
+    assert np.isclose(ctx.res_l2_norm(), np.linalg.norm(R), rtol=1e-13)
+    _check_RJ(prob, X, want_R=False)
+    _check_RJ(prob, X, want_J=False)
+
+
+def test_quad4_mindlin_plate_diag_elems_unstructured_and_size(built):
+    prob = _plate_problem(7, 5, jitter=0.2, diag=True, scramble=True)
+    _check_RJ(prob, O.state(prob.n_dof, 1))
+    # a larger mesh: symmetry and the rigid-body null space of the assembled operator (no constraints)
+    xyz, conn = mesh.build_square(160, 120, 1.5, 1.0)
+    prob = O.Problem(O.QUAD4, xyz, conn, 6, E0=72e9, nu=0.33, thickness=0.06, offset=0.0, kappa=5.0 / 6.0)
+    ctx = prob.make_context(0)
+    rp, ci = ctx.get_pattern()
+    J = np.empty(ctx.nnz); R = np.empty(prob.n_dof)
+    U = np.zeros((len(xyz), 6)); U[:, 2] = 1.0 + 0.3 * xyz[:, 0] - 0.2 * xyz[:, 1]; U[:, 3] = -0.2; U[:, 4] = -0.3
+    ctx.residual_and_jacobian(U.ravel(), R, J)           # rigid rotation + translation: no internal force
+    import scipy.sparse as sp
+    A = sp.csr_matrix((J, ci, rp), shape=(prob.n_dof, prob.n_dof))
+    assert abs(A - A.T).max() <= 1e-12 * np.abs(J).max()
+    assert np.abs(R).max() <= 1e-9 * np.abs(J).max()
