@@ -42,7 +42,7 @@ class Stats(C.Structure):
     _fields_ = [("n_tiles", C.c_int64), ("n_visits", C.c_int64), ("n_owned_nodes", C.c_int64),
                 ("n_elem", C.c_int64), ("kernel_launches", C.c_int64), ("last_sweep_ms", C.c_double),
                 ("last_main_kernel_ms", C.c_double), ("plan_bytes", C.c_int64), ("smem_bytes", C.c_int32),
-                ("threads_per_cta", C.c_int32), ("ctas", C.c_int32)]
+                ("threads_per_cta", C.c_int32), ("ctas", C.c_int32), ("structured", C.c_int32)]
 
 
 def lib_path():

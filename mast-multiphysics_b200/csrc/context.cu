@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -103,6 +104,7 @@ struct mastb200_context {
     }
   } dplan[2];
   int last_plan = 0;
+  bool last_struct = false;
   // device plan of the gather (QUAD4 heat) and coloured-scatter (HEX27) sweeps
   struct GenericPlan {
     bool built = false;
@@ -117,6 +119,16 @@ struct mastb200_context {
       n2e_ptr.release(); nbr_ptr.release(); diag.release(); posmap.release(); tab.release();
     }
   } gplan;
+  // implicit-connectivity sweep of ijk-numbered (build_cube) HEX8 meshes (sweep_hex8_struct.cu)
+  struct StructPlan {
+    bool tried = false, ok = false;
+    int32_t nx = 0, ny = 0, nz = 0, oz0 = 0, oz1 = 0, n_units = 0, n_ctas = 0;
+    int64_t n_visits = 0;
+    DevBuf<StructUnit> units;
+    DevBuf<int32_t> arr_off;
+    DevBuf<int64_t> nbr_ptr;
+    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); }
+  } splan;
   int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
   DevBuf<int32_t> d_tile_counter, d_owned_nodes;
   DevBuf<uint8_t> d_cmask;
@@ -467,6 +479,107 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
   return MASTB200_OK;
 }
 
+// Recognises libMesh build_cube numbering (node id i + j(nx+1) + k(nx+1)(ny+1), element id i + j nx + k nx ny, HEX8
+// node order) with every node owned or the owned nodes forming a range of z-planes, and builds the work units of the
+// implicit-connectivity sweep: columns of <= 7x7 owned nodes cut into z-segments.  MASTB200_NO_STRUCT=1 disables it.
+int ensure_struct_plan(mastb200_context* ctx) {
+  mastb200_context::StructPlan& S = ctx->splan;
+  if (S.tried) return MASTB200_OK;
+  S.tried = true;
+  if (ctx->elem_type != MASTB200_HEX8 || ctx->has_diag || ctx->planning_only) return MASTB200_OK;
+  if (const char* e = getenv("MASTB200_NO_STRUCT")) if (e[0] == '1') return MASTB200_OK;
+  if ((size_t)ctx->max_optin < hex8_struct_smem_bytes()) return MASTB200_OK;
+  const int32_t* c = ctx->conn.data();
+  const int64_t ne = ctx->n_elem, nn = ctx->n_nodes;
+  if (c[0] != 0 || c[1] != 1) return MASTB200_OK;
+  const int64_t npx = c[3], npxy = c[4];
+  if (npx < 2 || npxy < 2 * npx || npxy % npx) return MASTB200_OK;
+  const int64_t nx = npx - 1, ny = npxy / npx - 1;
+  if (ny < 1 || ne % (nx * ny)) return MASTB200_OK;
+  const int64_t nz = ne / (nx * ny);
+  if (npxy * (nz + 1) != nn || nx > 32000 || ny > 32000) return MASTB200_OK;
+  bool match = true;
+  for (int64_t e = 0; e < ne && match; ++e) {
+    const int64_t i = e % nx, j = (e / nx) % ny, k = e / (nx * ny);
+    const int64_t n0 = i + j * npx + k * npxy;
+    const int32_t* q = c + e * 8;
+    match = q[0] == n0 && q[1] == n0 + 1 && q[2] == n0 + npx + 1 && q[3] == n0 + npx && q[4] == n0 + npxy &&
+            q[5] == n0 + npxy + 1 && q[6] == n0 + npxy + npx + 1 && q[7] == n0 + npxy + npx;
+  }
+  if (!match) return MASTB200_OK;
+  int64_t oz0 = 0, oz1 = nz + 1;
+  if (!ctx->owned.empty()) {  // owned nodes must be whole z-planes [oz0, oz1)
+    oz0 = -1; oz1 = -1;
+    for (int64_t k = 0; k <= nz; ++k) {
+      const bool o = ctx->owned[k * npxy] != 0;
+      for (int64_t n = k * npxy; n < (k + 1) * npxy; ++n)
+        if ((ctx->owned[n] != 0) != o) return MASTB200_OK;
+      if (o) {
+        if (oz0 < 0) oz0 = k;
+        else if (oz1 >= 0) return MASTB200_OK;  // second range
+      } else if (oz0 >= 0 && oz1 < 0) {
+        oz1 = k;
+      }
+    }
+    if (oz0 < 0) return MASTB200_OK;
+    if (oz1 < 0) oz1 = nz + 1;
+  }
+  // owned nodes of a direction in chunks of at most 7, as even as possible
+  auto chunks = [](int64_t n_nodes_dir, std::vector<std::pair<int, int>>& out) {
+    const int64_t nt = (n_nodes_dir + 6) / 7, base = n_nodes_dir / nt, rem = n_nodes_dir % nt;
+    int64_t o = 0;
+    for (int64_t t = 0; t < nt; ++t) {
+      const int64_t len = base + (t < rem ? 1 : 0);
+      out.emplace_back((int)o, (int)len);
+      o += len;
+    }
+  };
+  std::vector<std::pair<int, int>> cx, cy;
+  chunks(nx + 1, cx);
+  chunks(ny + 1, cy);
+  const int64_t n_tiles = (int64_t)cx.size() * cy.size(), planes = oz1 - oz0;
+  int64_t nseg = (20 * (int64_t)ctx->sm_count + n_tiles - 1) / n_tiles;
+  nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, std::max<int64_t>(1, planes / 24)));
+  std::vector<StructUnit> units;
+  std::vector<int64_t> cost;
+  S.n_visits = 0;
+  for (size_t ty = 0; ty < cy.size(); ++ty)
+    for (size_t tx = 0; tx < cx.size(); ++tx)
+      for (int64_t sg = 0; sg < nseg; ++sg) {
+        StructUnit u;
+        u.o0x = (int16_t)cx[tx].first; u.nox = (int16_t)cx[tx].second;
+        u.o0y = (int16_t)cy[ty].first; u.noy = (int16_t)cy[ty].second;
+        const int64_t e0x = std::max<int64_t>(u.o0x - 1, 0), e1x = std::min<int64_t>(u.o0x + u.nox, nx);
+        const int64_t e0y = std::max<int64_t>(u.o0y - 1, 0), e1y = std::min<int64_t>(u.o0y + u.noy, ny);
+        u.e0x = (int16_t)e0x; u.nex = (int16_t)(e1x - e0x);
+        u.e0y = (int16_t)e0y; u.ney = (int16_t)(e1y - e0y);
+        u.z0 = (int32_t)(oz0 + planes * sg / nseg); u.z1 = (int32_t)(oz0 + planes * (sg + 1) / nseg);
+        if (u.z1 <= u.z0) continue;
+        const int64_t s_begin = u.z0 > 0 ? u.z0 - 1 : 0, e_planes = std::min<int64_t>(u.z1, nz) - s_begin;
+        units.push_back(u);
+        cost.push_back((int64_t)u.nex * u.ney * (u.z1 - s_begin));
+        S.n_visits += (int64_t)u.nex * u.ney * std::max<int64_t>(e_planes, 0);
+      }
+  std::vector<int32_t> order(units.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+  std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
+  std::vector<StructUnit> sorted(units.size());
+  for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
+  std::vector<int32_t> arr_off(124, 0);
+  for (int a = 0; a < 42; ++a) arr_off[a] = kStructPosIn[a] * 81;
+  for (int a = 0; a < 81; ++a) arr_off[42 + a] = kStructPosCr[a] * 81;
+  CU(S.units.upload(sorted, ctx->stream));
+  CU(S.arr_off.upload(arr_off, ctx->stream));
+  CU(S.nbr_ptr.upload(ctx->pat.nbr_ptr, ctx->stream));
+  CU(ctx->d_tile_counter.ensure(4));
+  CU(cudaStreamSynchronize(ctx->stream));
+  S.nx = (int32_t)nx; S.ny = (int32_t)ny; S.nz = (int32_t)nz; S.oz0 = (int32_t)oz0; S.oz1 = (int32_t)oz1;
+  S.n_units = (int32_t)sorted.size();
+  S.n_ctas = std::max(1, std::min(S.n_units, ctx->sm_count));
+  S.ok = true;
+  return MASTB200_OK;
+}
+
 // HEX8 with Green-Lagrange strain: row-owner gather (sweep_hex8_gather.cu)
 int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J) {
   int rc;
@@ -542,8 +655,11 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   // the plain shared-memory layout serves residual/Jacobian sweeps of the 3-dof system with a homogeneous modulus and
   // no thermal load; everything else stages the auxiliary nodal fields and per-node extras
   const int aux = (G || ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
-  if ((rc = ensure_plan(ctx, aux))) return rc;
+  if (!aux && (rc = ensure_struct_plan(ctx))) return rc;
+  const bool use_struct = !aux && ctx->splan.ok;
+  if (!use_struct && (rc = ensure_plan(ctx, aux))) return rc;
   ctx->last_plan = aux;
+  ctx->last_struct = use_struct;
   SweepParams p;
   fill_params(ctx, aux, p);
   const double *dX = nullptr, *dadj = nullptr;
@@ -560,7 +676,19 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     if (dG) CU(cudaMemsetAsync(dG, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
   }
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CU(launch_hex8_sweep(p, ctx->dplan[aux].n_ctas, ctx->stream));
+  if (use_struct) {
+    const mastb200_context::StructPlan& S = ctx->splan;
+    StructParams sp;
+    sp.units = S.units.p; sp.n_units = S.n_units; sp.counter = ctx->d_tile_counter.p;
+    sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0;
+    sp.nbr_ptr = S.nbr_ptr.p; sp.arr_off = S.arr_off.p;
+    sp.in1_off = kStructIn1Off; sp.cr0_off = kStructCr0Off; sp.cr1_off = kStructCr1Off;
+    sp.xyz = p.xyz; sp.X = dX; sp.cmask = p.cmask; sp.J = dJ; sp.R = dR;
+    sp.E0 = p.E0; sp.lam1 = p.lam1; sp.mu1 = p.mu1;
+    CU(launch_hex8_struct(sp, S.n_ctas, ctx->stream));
+  } else {
+    CU(launch_hex8_sweep(p, ctx->dplan[aux].n_ctas, ctx->stream));
+  }
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (dR && !ctx->fl_node.empty()) {
@@ -792,6 +920,7 @@ int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz)
   }
   for (auto& D : ctx->dplan) D.reset();
   ctx->gplan.reset();
+  ctx->splan.reset();
   const std::string e = build_pattern(ctx->nn, ctx->n_nodes, ctx->n_elem, ctx->conn.data(),
                                       ctx->owned.empty() ? nullptr : ctx->owned.data(),
                                       ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), ctx->pat);
@@ -799,7 +928,12 @@ int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz)
   ctx->have_plan = true;
   // the plan of the layout this problem will most likely sweep with is built now; the other one on first use
   const int aux = (ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
-  if (int rc = ensure_plan(ctx, aux)) { ctx->have_plan = false; return rc; }
+  if (!aux && ctx->elem_type == MASTB200_HEX8 && ctx->nv == 3) {
+    if (int rc = ensure_struct_plan(ctx)) { ctx->have_plan = false; return rc; }
+  }
+  if (!(ctx->splan.ok && !aux)) {
+    if (int rc = ensure_plan(ctx, aux)) { ctx->have_plan = false; return rc; }
+  }
   ctx->last_plan = aux;
   if (!ctx->planning_only) {
     CU(ctx->d_owned_nodes.upload(ctx->pat.owned_nodes, ctx->stream));
@@ -1055,15 +1189,16 @@ int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   if (!ctx || !s) return MASTB200_ERR_ARG;
   std::memset(s, 0, sizeof *s);
   const mastb200_context::DevicePlan& D = ctx->dplan[ctx->last_plan];
-  s->n_tiles = D.n_tiles;
-  s->n_visits = D.n_visits;
+  s->n_tiles = ctx->last_struct ? ctx->splan.n_units : D.n_tiles;
+  s->n_visits = ctx->last_struct ? ctx->splan.n_visits : D.n_visits;
   s->n_owned_nodes = ctx->pat.n_owned;
   s->n_elem = ctx->n_elem;
   s->kernel_launches = ctx->launches;
-  s->plan_bytes = D.bytes;
-  s->smem_bytes = (int32_t)D.smem;
-  s->threads_per_cta = hex8_sweep_threads();
-  s->ctas = D.n_ctas;
+  s->plan_bytes = ctx->last_struct ? (int64_t)ctx->splan.n_units * (int64_t)sizeof(StructUnit) : D.bytes;
+  s->smem_bytes = ctx->last_struct ? (int32_t)hex8_struct_smem_bytes() : (int32_t)D.smem;
+  s->threads_per_cta = ctx->last_struct ? hex8_struct_threads() : hex8_sweep_threads();
+  s->ctas = ctx->last_struct ? ctx->splan.n_ctas : D.n_ctas;
+  s->structured = ctx->last_struct ? 1 : 0;
   if (ctx->timed) {
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a;

@@ -6,6 +6,7 @@
 #include <cstdint>
 
 #include "device_types.h"
+#include "struct_layout.h"
 
 namespace mastb200 {
 
@@ -22,6 +23,33 @@ int hex8_sweep_arena_blocks(bool aux);  // pair blocks of the shared-memory aren
 int hex8_sweep_threads();
 int hex8_sweep_workers();  // compute warps = rows of the plan's per-step visit grid
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream);
+
+// ---- HEX8 sweep for ijk-numbered (build_cube) meshes with implicit connectivity (sweep_hex8_struct.cu) --------------
+struct StructUnit {          // a column of owned nodes over a z-range, with the elements that touch it
+  int16_t e0x, nex;          // first visited element / number of visited elements in x (<= 8)
+  int16_t o0x, nox;          // first owned node / number of owned nodes in x (<= 7)
+  int16_t e0y, ney, o0y, noy;
+  int32_t z0, z1;            // owned node planes [z0, z1)
+};
+struct StructParams {
+  const StructUnit* units = nullptr;
+  int32_t n_units = 0;
+  int32_t* counter = nullptr;            // dynamic unit scheduler (zeroed before every launch)
+  int32_t nx = 0, ny = 0, nz = 0;        // elements per direction of the (local) box
+  int32_t oz0 = 0;                       // first owned node plane: CSR rows start there
+  const int64_t* nbr_ptr = nullptr;      // node-level CSR row pointer of the owned rows
+  const int32_t* arr_off = nullptr;      // [123] offsets of the pair arrays within an IN (42) / CR (81) region
+  int32_t in1_off = 0, cr0_off = 0, cr1_off = 0;
+  const double* xyz = nullptr;
+  const double* X = nullptr;
+  const uint8_t* cmask = nullptr;
+  double* J = nullptr;
+  double* R = nullptr;
+  double E0 = 0., lam1 = 0., mu1 = 0.;
+};
+size_t hex8_struct_smem_bytes();
+int hex8_struct_threads();
+cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream);
 
 // ---- row-owner gather kernels for small elements (sweep_quad4_heat.cu) ---------------------------------------------
 constexpr int kGatherMaxNbr = 24;      // neighbours per row the gather kernels keep in shared memory

@@ -1,0 +1,442 @@
+// sweep_hex8_struct.cu -- HEX8 linear-elastic residual + Jacobian sweep for ijk-numbered (build_cube) meshes with
+// implicit connectivity (sm_100a, fp64).
+//
+// Same device counterpart as sweep_hex8.cu -- the element loop of MAST::NonlinearImplicitAssembly::
+// residual_and_jacobian (/root/reference/src/base/nonlinear_implicit_assembly.cpp:111-186) with
+// StructuralElement3D::internal_residual (src/elasticity/solid_element_3d.cpp:135-423, linear strain) and the
+// isotropic D of src/property_cards/isotropic_material_property_card.cpp:512-528 -- for the meshes libMesh's
+// MeshTools::Generation::build_cube produces (examples/structural/base/bracket_3d_model.h:172-177): node id
+// i + j(nx+1) + k(nx+1)(ny+1), element id i + j nx + k nx ny.  The host recognises that numbering (context.cu) and
+// uses this kernel for the plain 3-dof R/J sweep; any other mesh takes the plan-driven kernel of sweep_hex8.cu.
+// Geometry is general (every element's Jacobian is evaluated at its 8 Gauss points); only the integer bookkeeping
+// is implicit, so no plan is streamed from HBM.
+//
+// Row-owner streaming gather.  A work unit is a column of <= 7x7 owned nodes over a z-range; the CTA (16 warps) sweeps
+// it plane by plane, visiting the <= 8x8 elements of each element plane that touch its nodes (elements on the column
+// boundary are visited by the neighbouring columns too).  Per element plane:
+//   compute : warp w owns a 2x2 block of elements.  Geometry: lane = (element, qp) -> J^-1 and w = JxW E staged in
+//             shared memory.  Matrix: all 32 lanes on one element, S_ij[a][b] = sum_q w g_a[i] g_b[j] for the six
+//             component pairs i<=j with 12 mma.sync.m8n8k4.f64 (rows/columns = the element's nodes in ijk order).
+//             Accumulate: the 3x3 block S_AB of every node pair goes to structure-of-arrays accumulators in shared
+//             memory, arena[(direction A->B, component)][node column of A], for the lexicographically first node A of
+//             the pair -- addresses are lane constants plus the element's column index.  The four elements sharing a
+//             node column accumulate in colour order (x parity + 2 y parity), enforced by one counter per column
+//             (acquire/release): fixed summation order, no atomics, no CTA barrier inside the plane.
+//   flush   : node plane s is complete once element plane s is done.  Eight lanes per owned node walk its <= 27
+//             neighbour blocks (forward pairs stored at the node, backward pairs at the neighbour, transposed):
+//             K_AB = lam S + mu S^T + mu tr(S) I, libMesh's per-element Dirichlet semantics, f_A = sum_B K_AB u_B, and
+//             one store of every CSR value.  K_e is never formed.
+//   zero    : the accumulators of the flushed plane are cleared for reuse two planes later.
+// Nodal coordinates / displacements of plane s+2 are fetched with cp.async while plane s is processed.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace mastb200 {
+namespace {
+
+constexpr int SW = 16;                 // warps per CTA
+constexpr int ST = SW * 32;
+constexpr int TCX = 9;                 // node columns per tile row (8 elements + 1)
+constexpr int NS = TCX * TCX;          // node-column slots
+constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
+constexpr double GP = 0.57735026918962576451;
+
+// shared-memory carve-up (bytes)
+constexpr int O_ARENA = 0;
+constexpr int ARENA_BYTES = kStructArenaDoubles * 8;
+constexpr int O_XYZ = O_ARENA + ARENA_BYTES;            // [3 planes][3][NS]
+constexpr int O_U = O_XYZ + 3 * 3 * NS * 8;             // [4 planes][3][NS]
+constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;  // [SW][4 el][8 qp][QS]
+constexpr int O_CNT = O_STAGE + SW * 4 * 8 * QS * 8;    // [NS] int32 (+pad)
+constexpr int O_CM = O_CNT + 84 * 4;                    // [4 planes][84] uint8
+constexpr int O_TAB = O_CM + 4 * 84;                    // [124] int32: array offsets within an IN / CR region
+constexpr int O_MISC = O_TAB + 124 * 4;
+constexpr int SMEM_BYTES = O_MISC + 16;
+static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0, "alignment");
+static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_s32(int32_t* p, int v) {
+  asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct Sm {
+  double* arena;
+  double* xyz;
+  double* u;
+  double* stage;
+  int32_t* cnt;
+  uint8_t* cm;
+  int32_t* tab;
+  int* misc;
+};
+
+// in-plane pair direction (A -> B, B after A in ijk order): 0 self, 1 (+1,0), 2 (-1,+1), 3 (0,+1), 4 (+1,+1)
+__device__ __forceinline__ int inplane_dir(int di, int dj) { return dj == 0 ? (di == 0 ? 0 : 1) : 3 + di; }
+// index of the array (direction, component) within an IN region (42 arrays) or CR region (81 arrays, tab offset 42)
+__device__ __forceinline__ int in_array(int dir, int comp) { return dir == 0 ? comp : 6 + (dir - 1) * 9 + comp; }
+__device__ __forceinline__ int cr_array(int di, int dj, int comp) { return 42 + ((dj + 1) * 3 + (di + 1)) * 9 + comp; }
+
+struct LaneK {
+  double d0[2], d1[2], d2;   // reference gradients of N_m at qps q4 (h = 0) and q4 + 4 (h = 1)
+  int off[2][12];            // accumulate offsets per plane parity: region + array + column offset of the pair's first node
+  unsigned pred;             // bit bb*6+k: this lane adds C[k][bb]
+};
+
+// Row / column index m of the DMMA tile is the element node (dx = m&1, dy = (m>>1)&1, dz = m>>2).
+__device__ __forceinline__ void make_lane(const StructParams& p, const int32_t* tab, int lane, LaneK& lk) {
+  const int m = lane >> 2, q4 = lane & 3;
+  const double sx = (m & 1) ? 1. : -1., sy = (m & 2) ? 1. : -1., sz = (m & 4) ? 1. : -1.;
+  const double fx = 1. + sx * ((q4 & 1) ? GP : -GP), fy = 1. + sy * ((q4 & 2) ? GP : -GP);
+  const double fz0 = 1. - sz * GP, fz1 = 1. + sz * GP;
+  lk.d0[0] = 0.125 * sx * fy * fz0; lk.d0[1] = 0.125 * sx * fy * fz1;
+  lk.d1[0] = 0.125 * sy * fx * fz0; lk.d1[1] = 0.125 * sy * fx * fz1;
+  lk.d2 = 0.125 * sz * fx * fy;
+  lk.pred = 0u;
+  const int KI[6] = {0, 1, 2, 0, 0, 1}, KJ[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int b = 2 * q4 + bb;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      int lo = m, hi = b, ci = KI[k], cj = KJ[k];
+      bool on = true;
+      int comp;
+      if (m == b) {
+        comp = k;  // self block: the six components i <= j
+      } else {
+        if (m > b) {  // C_ij[m][b] = S_(b,m)[j][i]
+          lo = b; hi = m; ci = KJ[k]; cj = KI[k];
+          if (KI[k] == KJ[k]) on = false;  // the lane (b, m) holds the same value
+        }
+        comp = ci * 3 + cj;
+      }
+      const int lx = lo & 1, ly = (lo >> 1) & 1, lz = lo >> 2;
+      const int ox = (hi & 1) - lx, oy = ((hi >> 1) & 1) - ly, oz = (hi >> 2) - lz;
+      const int so = ly * TCX + lx;
+#pragma unroll
+      for (int par = 0; par < 2; ++par) {
+        int o;
+        if (oz == 0) {
+          const int plane_par = lz ? (par ^ 1) : par;  // node plane s (bottom) lives in IN[s&1], plane s+1 in the other
+          o = (plane_par ? p.in1_off : 0) + tab[in_array(inplane_dir(ox, oy), comp)] + so;
+        } else {
+          o = (par ? p.cr1_off : p.cr0_off) + tab[cr_array(ox, oy, comp)] + so;
+        }
+        lk.off[par][bb * 6 + k] = o;
+      }
+      if (on) lk.pred |= 1u << (bb * 6 + k);
+    }
+  }
+}
+
+// ---- state staging: coordinates, displacements and constraint masks of node plane z ------------------------------
+__device__ __forceinline__ void load_plane_async(const StructParams& p, const Sm& sm, const StructUnit& u, int z, int tid) {
+  const int ncx = u.nex + 1, ncy = u.ney + 1;
+  const int64_t npx = p.nx + 1, npy = p.ny + 1;
+  double* X = sm.xyz + (z % 3) * 3 * NS;
+  double* U = sm.u + (z & 3) * 3 * NS;
+  for (int it = tid; it < ncx * ncy * 6; it += ST) {
+    const int col = it / 6, c = it - col * 6;
+    const int ly = col / ncx, lx = col - ly * ncx;
+    const int64_t gid = (u.e0x + lx) + (u.e0y + ly) * npx + (int64_t)z * npx * npy;
+    const int slot = ly * TCX + lx;
+    if (c < 3) cp_async8(X + c * NS + slot, p.xyz + gid * 3 + c);
+    else cp_async8(U + (c - 3) * NS + slot, p.X + gid * 3 + (c - 3));
+  }
+  if (p.cmask) {
+    for (int col = tid; col < ncx * ncy; col += ST) {
+      const int ly = col / ncx, lx = col - ly * ncx;
+      const int64_t gid = (u.e0x + lx) + (u.e0y + ly) * npx + (int64_t)z * npx * npy;
+      sm.cm[(z & 3) * 84 + ly * TCX + lx] = p.cmask[gid];
+    }
+  }
+}
+
+// ---- geometry: lane = (element el of the warp's 2x2 block, quadrature point q) ------------------------------------
+__device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& sm, int s, int base, int q, double* out) {
+  const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP, zeta = (q & 4) ? GP : -GP;
+  const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
+    const double d0 = ((m & 1) ? 0.125 : -0.125) * fy * fz, d1 = ((m & 2) ? 0.125 : -0.125) * fx * fz,
+                 d2 = ((m & 4) ? 0.125 : -0.125) * fx * fy;
+    const double* X = sm.xyz + (((m & 4) ? s + 1 : s) % 3) * 3 * NS + base + ((m >> 1) & 1) * TCX + (m & 1);
+    const double x0 = X[0], x1 = X[NS], x2 = X[2 * NS];
+    Jm[0][0] = fma(d0, x0, Jm[0][0]); Jm[0][1] = fma(d0, x1, Jm[0][1]); Jm[0][2] = fma(d0, x2, Jm[0][2]);
+    Jm[1][0] = fma(d1, x0, Jm[1][0]); Jm[1][1] = fma(d1, x1, Jm[1][1]); Jm[1][2] = fma(d1, x2, Jm[1][2]);
+    Jm[2][0] = fma(d2, x0, Jm[2][0]); Jm[2][1] = fma(d2, x1, Jm[2][1]); Jm[2][2] = fma(d2, x2, Jm[2][2]);
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = __drcp_rn(det);
+  double inv[3][3];  // inv[c][r] = d xi_r / d x_c
+  inv[0][0] = c00 * idet; inv[1][0] = c01 * idet; inv[2][0] = c02 * idet;
+  inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+  inv[1][1] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+  inv[2][1] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+  inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+  inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+  inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+  double2* o = reinterpret_cast<double2*>(out);
+  o[0] = make_double2(inv[0][0], inv[0][1]);
+  o[1] = make_double2(inv[0][2], inv[1][0]);
+  o[2] = make_double2(inv[1][1], inv[1][2]);
+  o[3] = make_double2(inv[2][0], inv[2][1]);
+  o[4] = make_double2(inv[2][2], det * p.E0);  // Gauss weights are 1 for the 2x2x2 rule
+}
+
+// ---- matrix + ordered accumulate: all 32 lanes on one element ------------------------------------------------------
+__device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, const StructUnit& u, const double* st, int par,
+                                              int lex, int ley, int color, int lane) {
+  const int m = lane >> 2, q4 = lane & 3;
+  double A[3][2], w[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double2* s2 = reinterpret_cast<const double2*>(st + (q4 + 4 * h) * QS);
+    const double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3 = s2[3], v4 = s2[4];
+    A[0][h] = v0.x * lk.d0[h] + v0.y * lk.d1[h] + v1.x * lk.d2;
+    A[1][h] = v1.y * lk.d0[h] + v2.x * lk.d1[h] + v2.y * lk.d2;
+    A[2][h] = v3.x * lk.d0[h] + v3.y * lk.d1[h] + v4.x * lk.d2;
+    w[h] = v4.y;
+  }
+  double B[3][2], C[6][2];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { B[j][0] = A[j][0] * w[0]; B[j][1] = A[j][1] * w[1]; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { C[k][0] = 0.; C[k][1] = 0.; }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    dmma8x8x4(C[0][0], C[0][1], A[0][h], B[0][h]);
+    dmma8x8x4(C[1][0], C[1][1], A[1][h], B[1][h]);
+    dmma8x8x4(C[2][0], C[2][1], A[2][h], B[2][h]);
+    dmma8x8x4(C[3][0], C[3][1], A[0][h], B[1][h]);
+    dmma8x8x4(C[4][0], C[4][1], A[0][h], B[2][h]);
+    dmma8x8x4(C[5][0], C[5][1], A[1][h], B[2][h]);
+  }
+  // ordered accumulation: the (up to) four elements around a node column add in colour order
+  const int base = ley * TCX + lex;
+  const bool checker = q4 == 0 && m < 4;
+  int col = 0, rank = 0;
+  if (checker) {
+    const int dx = m & 1, dy = m >> 1;
+    col = base + dy * TCX + dx;
+    const int ox = lex - 1 + 2 * dx, oy = ley - 1 + 2 * dy;  // the other elements around the column
+    const bool ex = ox >= 0 && ox < u.nex, ey = oy >= 0 && oy < u.ney;
+    rank = ((ex && (color & 1)) ? 1 : 0) + ((ey && (color & 2)) ? 1 : 0) + ((ex && ey && color >= 2) ? 1 : 0);
+    while (ld_acquire_s32(sm.cnt + col) != rank) __nanosleep(20);
+  }
+  __syncwarp();
+  double* ar = sm.arena + base;
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if ((lk.pred >> (bb * 6 + k)) & 1u) {
+        double* ptr = ar + (par ? lk.off[1][bb * 6 + k] : lk.off[0][bb * 6 + k]);
+        *ptr += C[k][bb];
+      }
+  __syncwarp();
+  if (checker) st_release_s32(sm.cnt + col, rank + 1);
+}
+
+// ---- flush of node plane s: eight lanes per owned node ----------------------------------------------------------------
+__device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm, const StructUnit& u, int s, int warp, int lane) {
+  const int g = warp * 4 + (lane >> 3), l8 = lane & 7;
+  const bool valid = g < u.nox * u.noy;
+  const int oyi = valid ? g / u.nox : 0, oxi = valid ? g - oyi * u.nox : 0;
+  const int ax = u.o0x + oxi, ay = u.o0y + oyi, az = s;
+  const int slotA = (ay - u.e0y) * TCX + (ax - u.e0x);
+  const int64_t npx = p.nx + 1, npy = p.ny + 1;
+  const int64_t gid = ax + ay * npx + (int64_t)az * npx * npy;
+  const int x0 = ax == 0, y0 = ay == 0, z0 = az == 0;
+  const int xcnt = 3 - x0 - (ax == p.nx), ycnt = 3 - y0 - (ay == p.ny), zcnt = 3 - z0 - (az == p.nz);
+  const int nnb = xcnt * ycnt * zcnt;
+  const int64_t nb0 = valid ? p.nbr_ptr[gid - (int64_t)p.oz0 * npx * npy] : 0;
+  const unsigned cmn = p.cmask ? sm.cm[(s & 3) * 84 + slotA] : 0u;
+  const int par = s & 1;
+  const int inS = par ? p.in1_off : 0;                       // IN region of node plane s
+  const int crS = par ? p.cr1_off : p.cr0_off;               // cross s -> s+1
+  const int crD = par ? p.cr0_off : p.cr1_off;               // cross s-1 -> s
+  double r0 = 0., r1 = 0., r2 = 0.;
+#pragma unroll 1
+  for (int c0 = 0; c0 < 32; c0 += 8) {
+    const int d = c0 + l8;
+    const int dk = d / 9 - 1, dj = (d / 3) % 3 - 1, di = d % 3 - 1;
+    const int bx = ax + di, by = ay + dj, bz = az + dk;
+    const bool on = valid && d < 27 && bx >= 0 && bx <= p.nx && by >= 0 && by <= p.ny && bz >= 0 && bz <= p.nz;
+    if (on) {
+      const int c = ((dk + 1 - z0) * ycnt + (dj + 1 - y0)) * xcnt + (di + 1 - x0);
+      const int slotB = slotA + dj * TCX + di;
+      const bool self = d == 13, fwd = d > 13;
+      // where the pair block lives: at the first node of the pair, oriented first -> second
+      int reg, slot, sdi, sdj;
+      if (fwd || self) { slot = slotA; sdi = di; sdj = dj; reg = dk == 0 ? inS : crS; }
+      else { slot = slotB; sdi = -di; sdj = -dj; reg = dk == 0 ? inS : crD; }
+      const double* blk = sm.arena + reg + slot;
+      double S[3][3];
+      if (self) {
+        S[0][0] = blk[sm.tab[0]]; S[1][1] = blk[sm.tab[1]]; S[2][2] = blk[sm.tab[2]];
+        S[0][1] = S[1][0] = blk[sm.tab[3]]; S[0][2] = S[2][0] = blk[sm.tab[4]]; S[1][2] = S[2][1] = blk[sm.tab[5]];
+      } else {
+        const int a0 = dk == 0 ? in_array(inplane_dir(sdi, sdj), 0) : cr_array(sdi, sdj, 0);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) S[i][j] = blk[sm.tab[a0 + i * 3 + j]];
+      }
+      // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
+      const bool tr = !(fwd || self);
+      const double l1 = tr ? p.mu1 : p.lam1, l2 = tr ? p.lam1 : p.mu1;
+      const double trm = p.mu1 * (S[0][0] + S[1][1] + S[2][2]);
+      double K[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i][j] + l2 * S[j][i] + (i == j ? trm : 0.);
+      if (p.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
+        const double* U = sm.u + ((s + dk) & 3) * 3 * NS + slotB;
+        const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
+        r0 += K[0][0] * u0 + K[0][1] * u1 + K[0][2] * u2;
+        r1 += K[1][0] * u0 + K[1][1] * u1 + K[1][2] * u2;
+        r2 += K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
+      }
+      if (p.J) {
+        const unsigned cmm = p.cmask ? sm.cm[((s + dk) & 3) * 84 + slotB] : 0u;
+        if (cmn | cmm) {  // libMesh constrain_element_matrix_and_vector: row/column zeroed, diagonal 1 per adjacent element
+          const double nadj = double((2 - x0 - (ax == p.nx)) * (2 - y0 - (ay == p.ny)) * (2 - z0 - (az == p.nz)));
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+              double k = K[i][j];
+              if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
+              if (self && i == j && ((cmn >> i) & 1u)) k = nadj;
+              K[i][j] = k;
+            }
+        }
+        double* dst = p.J + 9 * nb0 + 3 * c;
+        const int rs = 3 * nnb;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+      }
+    }
+  }
+  if (p.R) {
+    // deterministic butterfly over the 8 lanes of a node for the three sums at once: lanes 0, 2 and 4 end with r0, r1, r2
+    const bool hi4 = (lane & 4) != 0, hi2 = (lane & 2) != 0;
+    const double g0 = __shfl_xor_sync(0xffffffffu, hi4 ? r0 : r2, 4);
+    const double g1 = __shfl_xor_sync(0xffffffffu, hi4 ? r1 : 0., 4);
+    const double x0s = (hi4 ? r2 : r0) + g0, x1s = (hi4 ? 0. : r1) + g1;
+    double y = (hi2 ? x1s : x0s) + __shfl_xor_sync(0xffffffffu, hi2 ? x0s : x1s, 2);
+    y += __shfl_xor_sync(0xffffffffu, y, 1);
+    if (valid && (l8 & 1) == 0 && l8 < 6) {
+      const int i = l8 >> 1;
+      p.R[gid * 3 + i] = ((cmn >> i) & 1u) ? 0. : y;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sm sm;
+  sm.arena = reinterpret_cast<double*>(smem_raw + O_ARENA);
+  sm.xyz = reinterpret_cast<double*>(smem_raw + O_XYZ);
+  sm.u = reinterpret_cast<double*>(smem_raw + O_U);
+  sm.stage = reinterpret_cast<double*>(smem_raw + O_STAGE);
+  sm.cnt = reinterpret_cast<int32_t*>(smem_raw + O_CNT);
+  sm.cm = smem_raw + O_CM;
+  sm.tab = reinterpret_cast<int32_t*>(smem_raw + O_TAB);
+  sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < 123) sm.tab[tid] = p.arr_off[tid];
+  __syncthreads();
+  LaneK lk;
+  make_lane(p, sm.tab, lane, lk);
+  double* my_stage = sm.stage + warp * (4 * 8 * QS);
+  const int bx2 = (warp & 3) * 2, by2 = (warp >> 2) * 2;  // origin of the warp's 2x2 element block
+
+  for (;;) {
+    if (tid == 0) sm.misc[0] = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int unit = sm.misc[0];
+    if (unit >= p.n_units) break;
+    const StructUnit u = p.units[unit];
+    const int s_begin = u.z0 > 0 ? u.z0 - 1 : 0;
+    // prologue: clear the accumulators, stage the first two node planes
+    for (int i = tid; i < kStructArenaDoubles; i += ST) sm.arena[i] = 0.;
+    if (tid < NS) sm.cnt[tid] = 0;
+    load_plane_async(p, sm, u, s_begin, tid);
+    if (s_begin + 1 <= p.nz) load_plane_async(p, sm, u, s_begin + 1, tid);
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int s = s_begin; s < u.z1; ++s) {
+      if (s + 2 <= p.nz) load_plane_async(p, sm, u, s + 2, tid);  // lands while this plane is processed
+      const int par = s & 1;
+      if (s < p.nz) {
+        // ---- compute: the warp's 2x2 block of elements of plane s ----
+        {
+          const int el = lane >> 3, q = lane & 7;
+          const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
+          if (lex < u.nex && ley < u.ney) geometry_phase(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+          if (lex < u.nex && ley < u.ney) element_phase(sm, lk, u, my_stage + c * 8 * QS, par, lex, ley, c, lane);
+        }
+      }
+      __syncthreads();
+      if (s >= u.z0) flush_plane(p, sm, u, s, warp, lane);
+      cp_async_wait_all();
+      __syncthreads();
+      // the accumulators of node plane s (-> plane s+2) and of the cross pairs s-1 -> s (-> s+1 -> s+2) start from zero
+      {
+        double* zi = sm.arena + (par ? p.in1_off : 0);
+        for (int i = tid; i < 42 * NS; i += ST) zi[i] = 0.;
+        double* zc = sm.arena + (par ? p.cr0_off : p.cr1_off);
+        for (int i = tid; i < 81 * NS; i += ST) zc[i] = 0.;
+        if (tid < NS) sm.cnt[tid] = 0;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace
+
+size_t hex8_struct_smem_bytes() { return SMEM_BYTES; }
+int hex8_struct_threads() { return ST; }
+
+cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(hex8_struct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  hex8_struct_kernel<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace mastb200
