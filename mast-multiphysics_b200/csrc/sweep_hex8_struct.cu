@@ -22,10 +22,12 @@
 //             the pair -- addresses are lane constants plus the element's column index.  The four elements sharing a
 //             node column accumulate in colour order (x parity + 2 y parity), enforced by one counter per column
 //             (acquire/release): fixed summation order, no atomics, no CTA barrier inside the plane.
-//   flush   : node plane s is complete once element plane s is done.  Eight lanes per owned node walk its <= 27
-//             neighbour blocks (forward pairs stored at the node, backward pairs at the neighbour, transposed):
-//             K_AB = lam S + mu S^T + mu tr(S) I, libMesh's per-element Dirichlet semantics, f_A = sum_B K_AB u_B, and
-//             one store of every CSR value.  K_e is never formed.
+//   flush   : node plane s is complete once element plane s is done.  Warp = owned node, lane = neighbour direction
+//             (its array offsets are lane constants): the pair block of each of the <= 27 neighbours (forward pairs
+//             stored at the node, backward pairs at the neighbour, transposed) becomes K_AB = lam S + mu S^T + mu tr(S) I
+//             with libMesh's per-element Dirichlet semantics and is stored -- every CSR value exactly once, consecutive
+//             lanes writing consecutive column blocks of a row; f_A = sum_B K_AB u_B by a fixed-order warp reduction.
+//             K_e is never formed.
 //   zero    : the accumulators of the flushed plane are cleared for reuse two planes later.
 // Nodal coordinates / displacements of plane s+2 are fetched with cp.async while plane s is processed.
 #include <cuda_runtime.h>
@@ -51,7 +53,8 @@ constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;  // [SW][4 el][8 qp][
 constexpr int O_CNT = O_STAGE + SW * 4 * 8 * QS * 8;    // [NS] int32 (+pad)
 constexpr int O_CM = O_CNT + 84 * 4;                    // [4 planes][84] uint8
 constexpr int O_TAB = O_CM + 4 * 84;                    // [124] int32: array offsets within an IN / CR region
-constexpr int O_MISC = O_TAB + 124 * 4;
+constexpr int O_NODE = O_TAB + 124 * 4;                 // [64] int2: owned nodes of the unit (in-plane id, slot | boundary flags)
+constexpr int O_MISC = O_NODE + 64 * 8;
 constexpr int SMEM_BYTES = O_MISC + 16;
 static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0, "alignment");
 static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
@@ -69,6 +72,13 @@ __device__ __forceinline__ int ld_acquire_s32(const int32_t* p) {
 __device__ __forceinline__ void st_release_s32(int32_t* p, int v) {
   asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 }
+// 32-bit shared-memory addressing for the accumulators: one integer add per access instead of 64-bit pointer arithmetic
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -82,6 +92,7 @@ struct Sm {
   int32_t* cnt;
   uint8_t* cm;
   int32_t* tab;
+  int2* node;
   int* misc;
 };
 
@@ -93,7 +104,7 @@ __device__ __forceinline__ int cr_array(int di, int dj, int comp) { return 42 + 
 
 struct LaneK {
   double d0[2], d1[2], d2;   // reference gradients of N_m at qps q4 (h = 0) and q4 + 4 (h = 1)
-  int off[2][12];            // accumulate offsets per plane parity: region + array + column offset of the pair's first node
+  int off[2][12];            // accumulate BYTE offsets per plane parity: region + array + column offset of the pair's first node
   unsigned pred;             // bit bb*6+k: this lane adds C[k][bb]
 };
 
@@ -137,32 +148,9 @@ __device__ __forceinline__ void make_lane(const StructParams& p, const int32_t* 
         } else {
           o = (par ? p.cr1_off : p.cr0_off) + tab[cr_array(ox, oy, comp)] + so;
         }
-        lk.off[par][bb * 6 + k] = o;
+        lk.off[par][bb * 6 + k] = o * 8;
       }
       if (on) lk.pred |= 1u << (bb * 6 + k);
-    }
-  }
-}
-
-// ---- state staging: coordinates, displacements and constraint masks of node plane z ------------------------------
-__device__ __forceinline__ void load_plane_async(const StructParams& p, const Sm& sm, const StructUnit& u, int z, int tid) {
-  const int ncx = u.nex + 1, ncy = u.ney + 1;
-  const int64_t npx = p.nx + 1, npy = p.ny + 1;
-  double* X = sm.xyz + (z % 3) * 3 * NS;
-  double* U = sm.u + (z & 3) * 3 * NS;
-  for (int it = tid; it < ncx * ncy * 6; it += ST) {
-    const int col = it / 6, c = it - col * 6;
-    const int ly = col / ncx, lx = col - ly * ncx;
-    const int64_t gid = (u.e0x + lx) + (u.e0y + ly) * npx + (int64_t)z * npx * npy;
-    const int slot = ly * TCX + lx;
-    if (c < 3) cp_async8(X + c * NS + slot, p.xyz + gid * 3 + c);
-    else cp_async8(U + (c - 3) * NS + slot, p.X + gid * 3 + (c - 3));
-  }
-  if (p.cmask) {
-    for (int col = tid; col < ncx * ncy; col += ST) {
-      const int ly = col / ncx, lx = col - ly * ncx;
-      const int64_t gid = (u.e0x + lx) + (u.e0y + ly) * npx + (int64_t)z * npx * npy;
-      sm.cm[(z & 3) * 84 + ly * TCX + lx] = p.cmask[gid];
     }
   }
 }
@@ -205,7 +193,8 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
 }
 
 // ---- matrix + ordered accumulate: all 32 lanes on one element ------------------------------------------------------
-__device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, const StructUnit& u, const double* st, int par,
+template <int PAR>
+__device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, unsigned arena32, int rankpack, const double* st,
                                               int lex, int ley, int color, int lane) {
   const int m = lane >> 2, q4 = lane & 3;
   double A[3][2], w[2];
@@ -235,27 +224,25 @@ __device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, con
   // ordered accumulation: the (up to) four elements around a node column add in colour order
   const int base = ley * TCX + lex;
   const bool checker = q4 == 0 && m < 4;
-  int col = 0, rank = 0;
-  if (checker) {
-    const int dx = m & 1, dy = m >> 1;
-    col = base + dy * TCX + dx;
-    const int ox = lex - 1 + 2 * dx, oy = ley - 1 + 2 * dy;  // the other elements around the column
-    const bool ex = ox >= 0 && ox < u.nex, ey = oy >= 0 && oy < u.ney;
-    rank = ((ex && (color & 1)) ? 1 : 0) + ((ey && (color & 2)) ? 1 : 0) + ((ex && ey && color >= 2) ? 1 : 0);
-    while (ld_acquire_s32(sm.cnt + col) != rank) __nanosleep(20);
+  const int rank = (rankpack >> (2 * color)) & 3;
+  int32_t* cnt = sm.cnt + base + (m >> 1) * TCX + (m & 1);
+  if (checker)
+    while (ld_acquire_s32(cnt) != rank) __nanosleep(20);
+  __syncwarp();
+  // the twelve addresses of a lane are distinct: all loads are issued before the first store so that their latencies
+  // overlap (a load-add-store chain per value would serialise twelve shared-memory round trips)
+  const unsigned ar = arena32 + base * 8;
+  double old[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) {
+    old[t] = 0.;
+    if ((lk.pred >> t) & 1u) old[t] = lds64(ar + lk.off[PAR][t]);
   }
-  __syncwarp();
-  double* ar = sm.arena + base;
 #pragma unroll
-  for (int bb = 0; bb < 2; ++bb)
-#pragma unroll
-    for (int k = 0; k < 6; ++k)
-      if ((lk.pred >> (bb * 6 + k)) & 1u) {
-        double* ptr = ar + (par ? lk.off[1][bb * 6 + k] : lk.off[0][bb * 6 + k]);
-        *ptr += C[k][bb];
-      }
+  for (int t = 0; t < 12; ++t)
+    if ((lk.pred >> t) & 1u) sts64(ar + lk.off[PAR][t], old[t] + C[t % 6][t / 6]);
   __syncwarp();
-  if (checker) st_release_s32(sm.cnt + col, rank + 1);
+  if (checker) st_release_s32(cnt, rank + 1);
 }
 
 // ---- flush of node plane s: eight lanes per owned node ----------------------------------------------------------------
@@ -367,12 +354,14 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
   sm.cnt = reinterpret_cast<int32_t*>(smem_raw + O_CNT);
   sm.cm = smem_raw + O_CM;
   sm.tab = reinterpret_cast<int32_t*>(smem_raw + O_TAB);
+  sm.node = reinterpret_cast<int2*>(smem_raw + O_NODE);
   sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 123) sm.tab[tid] = p.arr_off[tid];
   __syncthreads();
   LaneK lk;
   make_lane(p, sm.tab, lane, lk);
+  const unsigned arena32 = (unsigned)__cvta_generic_to_shared(sm.arena);
   double* my_stage = sm.stage + warp * (4 * 8 * QS);
   const int bx2 = (warp & 3) * 2, by2 = (warp >> 2) * 2;  // origin of the warp's 2x2 element block
 
@@ -383,17 +372,82 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
     if (unit >= p.n_units) break;
     const StructUnit u = p.units[unit];
     const int s_begin = u.z0 > 0 ? u.z0 - 1 : 0;
+    const int64_t npx = p.nx + 1, plane_nodes = npx * (p.ny + 1);
+    // per-thread constants of the unit: the state item this thread stages every plane, its flush node
+    const int ncx = u.nex + 1, ncols = ncx * (u.ney + 1);
+    const bool ld_on = tid < ncols * 6;
+    int ld_dst = 0;
+    int64_t ld_src = 0;
+    bool ld_u = false;
+    {
+      const int col = tid / 6, c = tid - col * 6;
+      const int ly = col / ncx, lx = col - ly * ncx;
+      const int64_t gid0 = (u.e0x + lx) + (u.e0y + ly) * npx;
+      ld_u = c >= 3;
+      ld_dst = (ld_u ? c - 3 : c) * NS + ly * TCX + lx;
+      ld_src = gid0 * 3 + (ld_u ? c - 3 : c);
+    }
+    const bool cm_on = p.cmask != nullptr && tid < ncols;
+    int cm_dst = 0;
+    int64_t cm_src = 0;
+    {
+      const int ly = tid / ncx, lx = tid - ly * ncx;
+      cm_dst = ly * TCX + lx;
+      cm_src = (u.e0x + lx) + (u.e0y + ly) * npx;
+    }
+    auto load_plane = [&](int z) {  // coordinates and displacements of node plane z, asynchronously
+      if (ld_on) {
+        if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * 3 + ld_src);
+        else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
+      }
+    };
+    // accumulation ranks of this lane's node column for the four elements of the warp's block (2 bits per colour)
+    int rankpack = 0;
+    {
+      const int m = lane >> 2, dx = m & 1, dy = (m >> 1) & 1;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+        const int ox = lex - 1 + 2 * dx, oy = ley - 1 + 2 * dy;  // the other elements around the column
+        const bool ex = ox >= 0 && ox < u.nex, ey = oy >= 0 && oy < u.ney;
+        const int rank = ((ex && (c & 1)) ? 1 : 0) + ((ey && (c & 2)) ? 1 : 0) + ((ex && ey && c >= 2) ? 1 : 0);
+        rankpack |= rank << (2 * c);
+      }
+    }
+    // flush: warp w writes the owned nodes w, w + 16, ...; lane r < 4 fetches the CSR row pointer of the r-th of them
+    const int n_own = u.nox * u.noy;
+    if (tid < n_own) {
+      const int oyi = tid / u.nox, oxi = tid - oyi * u.nox;
+      const int ax = u.o0x + oxi, ay = u.o0y + oyi;
+      const int flags = (ax == 0 ? 1 : 0) | (ax == p.nx ? 2 : 0) | (ay == 0 ? 4 : 0) | (ay == p.ny ? 8 : 0);
+      sm.node[tid] = make_int2((int)(ax + ay * npx), ((ay - u.e0y) * TCX + (ax - u.e0x)) | (flags << 8));
+    }
+    int64_t row0 = 0;
+    const bool row_on = lane < 4 && warp + SW * lane < n_own;
+    if (row_on) {
+      const int node = warp + SW * lane, oyi = node / u.nox, oxi = node - oyi * u.nox;
+      row0 = (u.o0x + oxi) + (u.o0y + oyi) * npx - (int64_t)p.oz0 * plane_nodes;
+    }
+
     // prologue: clear the accumulators, stage the first two node planes
     for (int i = tid; i < kStructArenaDoubles; i += ST) sm.arena[i] = 0.;
     if (tid < NS) sm.cnt[tid] = 0;
-    load_plane_async(p, sm, u, s_begin, tid);
-    if (s_begin + 1 <= p.nz) load_plane_async(p, sm, u, s_begin + 1, tid);
+    load_plane(s_begin);
+    if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
+    if (cm_on) {
+      sm.cm[(s_begin & 3) * 84 + cm_dst] = p.cmask[(int64_t)s_begin * plane_nodes + cm_src];
+      if (s_begin + 1 <= p.nz) sm.cm[((s_begin + 1) & 3) * 84 + cm_dst] = p.cmask[(int64_t)(s_begin + 1) * plane_nodes + cm_src];
+    }
     cp_async_wait_all();
     __syncthreads();
 
     for (int s = s_begin; s < u.z1; ++s) {
-      if (s + 2 <= p.nz) load_plane_async(p, sm, u, s + 2, tid);  // lands while this plane is processed
-      const int par = s & 1;
+      // fetched while this plane is processed: state of plane s+2, the CSR row pointer of this lane's flush node
+      unsigned cmv = 0u;
+      if (s + 2 <= p.nz) {
+        load_plane(s + 2);
+        if (cm_on) cmv = p.cmask[(int64_t)(s + 2) * plane_nodes + cm_src];
+      }
       if (s < p.nz) {
         // ---- compute: the warp's 2x2 block of elements of plane s ----
         {
@@ -402,18 +456,29 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
           if (lex < u.nex && ley < u.ney) geometry_phase(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
         }
         __syncwarp();
+        if (s & 1) {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-          if (lex < u.nex && ley < u.ney) element_phase(sm, lk, u, my_stage + c * 8 * QS, par, lex, ley, c, lane);
+          for (int c = 0; c < 4; ++c) {
+            const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+            if (lex < u.nex && ley < u.ney) element_phase<1>(sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
+          }
+        } else {
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+            if (lex < u.nex && ley < u.ney) element_phase<0>(sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
+          }
         }
       }
       __syncthreads();
-      if (s >= u.z0) flush_plane(p, sm, u, s, warp, lane);
+      const bool do_flush = s >= u.z0;
+      if (do_flush) flush_plane(p, sm, u, s, warp, lane);
+      if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * 84 + cm_dst] = (uint8_t)cmv;
       cp_async_wait_all();
       __syncthreads();
       // the accumulators of node plane s (-> plane s+2) and of the cross pairs s-1 -> s (-> s+1 -> s+2) start from zero
       {
+        const int par = s & 1;
         double* zi = sm.arena + (par ? p.in1_off : 0);
         for (int i = tid; i < 42 * NS; i += ST) zi[i] = 0.;
         double* zc = sm.arena + (par ? p.cr0_off : p.cr1_off);
