@@ -272,6 +272,12 @@ def main():
             except Exception:
                 traffic = None
         st = ctx.stats()
+        kname = "hex8_struct_kernel" if st.get("structured") else "hex8_sweep_kernel"
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(kname) if n == 200 and world == 1 else None
+            except Exception:
+                traffic = None
         # fp64 work actually executed per launch (visits incl. ghost recompute): DMMA 18*512 + geometry/strain ~ 2.6k
         flops_exec = st["n_visits"] * (18 * 512 + 8 * 2 * 330)
         out = {
@@ -282,9 +288,12 @@ def main():
                                    f"{(n + 1) ** 3 * 3} dof), interior nodes jittered {args.jitter}h",
                        "elements": n_elem_global, "nnz_rank0": int(nnz), "partition": f"z-slabs x{world}",
                        "l2_policy": "inputs and outputs larger than L2 (15.6 GB of CSR values streamed per step)",
-                       "plan_build_s": round(plan_s, 1)},
+                       "plan_build_s": round(plan_s, 1),
+                       "sweep": ("implicit-connectivity kernel (build_cube numbering recognised)" if st.get("structured")
+                                 else "plan-driven kernel"),
+                       "element_visits_per_launch": int(st["n_visits"])},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "hex8_sweep_kernel",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": kname,
                          "kernel_ms": k_ms, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "bytes_per_element": alg_bytes / n_loc_elem,
                          "fp64": {"executed_tflops": flops_exec / (k_ms * 1e-3) / 1e12, "peak_tflops": 36.7,

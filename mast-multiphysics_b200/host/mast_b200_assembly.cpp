@@ -1,6 +1,8 @@
 // mast_b200_assembly.cpp -- see mast_b200_assembly.h.  Thin adaptors: libMesh objects -> plain arrays -> C-ABI.
 #include "mast_b200_assembly.h"
 
+#include <cmath>
+
 #include <cstring>
 
 #include "../../include/mast_b200.h"
@@ -390,10 +392,39 @@ mastb200_context* AssemblyBase::_device_problem(const libMesh::SparseMatrix<Real
   return _ctx;
 }
 
-// AssemblyBase::calculate_output (assembly_base.cpp:253-333) for ComplianceOutput (compliance_output.cpp:71-102)
+void StressStrainOutputBase::init(const GeomElem&) { _host_element_path("StressStrainOutputBase::init"); }
+void StressStrainOutputBase::evaluate() { _host_element_path("StressStrainOutputBase::evaluate"); }
+void StressStrainOutputBase::evaluate_sensitivity(const FunctionBase&) { _host_element_path("StressStrainOutputBase::evaluate_sensitivity"); }
+void StressStrainOutputBase::output_derivative_for_elem(RealVectorX&) { _host_element_path("StressStrainOutputBase::output_derivative_for_elem"); }
+Real StressStrainOutputBase::output_sensitivity_total(const FunctionBase&) {
+  libmesh_error_msg("StressStrainOutputBase::output_sensitivity_total: use the adjoint path (calculate_output_derivative)");
+}
+// StressStrainOutputBase::functional_for_all_elems (stress_output_base.cpp:851-909); with skip_comm_sum the caller sums
+// the two integrals over the ranks first (here: one rank per context, the sums are this rank's)
+Real StressStrainOutputBase::output_total() {
+  if (!_primal_data_initialized) libmesh_error_msg("StressStrainOutputBase::output_total before calculate_output");
+  return _sigma0 * std::pow(_sigma_vm_int / _JxW_val, 1. / _p_norm_stress);
+}
+
+// AssemblyBase::calculate_output (assembly_base.cpp:253-333) for ComplianceOutput (compliance_output.cpp:71-102) and
+// StressStrainOutputBase (stress_output_base.cpp:318-331, 851-909)
 void AssemblyBase::calculate_output(const libMesh::NumericVector<Real>& X, bool, OutputAssemblyElemOperations& output) {
+  if (StressStrainOutputBase* so = dynamic_cast<StressStrainOutputBase*>(&output)) {
+    if (so->_p_norm_weight != 1.) libmesh_error_msg("StressStrainOutputBase: p_norm_weight != 1 is not on the device path");
+    AssemblyElemOperations* saved0 = _elem_ops;
+    if (!_elem_ops) _elem_ops = &output;
+    mastb200_context* c0 = _device_problem(nullptr);
+    _elem_ops = saved0;
+    so->zero_for_analysis();
+    double sums[2] = {0., 0.};
+    _check(mastb200_stress_functional(c0, X.get_array_read(), so->_p_norm_stress, so->_rho, so->_sigma0, nullptr, sums, nullptr),
+           "stress_functional");
+    so->_sigma_vm_int = sums[0]; so->_JxW_val = sums[1];
+    so->_primal_data_initialized = true;
+    return;
+  }
   ComplianceOutput* c = dynamic_cast<ComplianceOutput*>(&output);
-  if (!c) libmesh_error_msg("calculate_output: only ComplianceOutput is on the device path");
+  if (!c) libmesh_error_msg("calculate_output: only ComplianceOutput and StressStrainOutputBase are on the device path");
   AssemblyElemOperations* saved = _elem_ops;
   if (!_elem_ops) _elem_ops = &output;
   mastb200_context* ctx = _device_problem(nullptr);
@@ -407,7 +438,20 @@ void AssemblyBase::calculate_output(const libMesh::NumericVector<Real>& X, bool,
 // AssemblyBase::calculate_output_derivative (assembly_base.cpp:338-430): dq_dX zeroed, element derivatives added, closed
 void AssemblyBase::calculate_output_derivative(const libMesh::NumericVector<Real>& X, bool, OutputAssemblyElemOperations& output,
                                                libMesh::NumericVector<Real>& dq_dX) {
-  if (!dynamic_cast<ComplianceOutput*>(&output)) libmesh_error_msg("calculate_output_derivative: only ComplianceOutput is on the device path");
+  if (StressStrainOutputBase* so = dynamic_cast<StressStrainOutputBase*>(&output)) {
+    // functional_state_derivartive_for_elem (stress_output_base.cpp:1104-1172) needs the primal sums of calculate_output
+    if (!so->_primal_data_initialized) libmesh_error_msg("calculate_output_derivative: call calculate_output first");
+    AssemblyElemOperations* saved0 = _elem_ops;
+    if (!_elem_ops) _elem_ops = &output;
+    mastb200_context* c0 = _device_problem(nullptr);
+    _elem_ops = saved0;
+    const double sums[2] = {so->_sigma_vm_int, so->_JxW_val};
+    _check(mastb200_stress_functional_derivative(c0, X.get_array_read(), so->_p_norm_stress, so->_rho, so->_sigma0, nullptr, sums,
+                                                 dq_dX.get_array()), "stress_functional_derivative");
+    dq_dX.close();
+    return;
+  }
+  if (!dynamic_cast<ComplianceOutput*>(&output)) libmesh_error_msg("calculate_output_derivative: only ComplianceOutput and StressStrainOutputBase are on the device path");
   AssemblyElemOperations* saved = _elem_ops;
   if (!_elem_ops) _elem_ops = &output;
   mastb200_context* ctx = _device_problem(nullptr);

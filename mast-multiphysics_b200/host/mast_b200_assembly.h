@@ -276,6 +276,29 @@ class ComplianceOutput : public OutputAssemblyElemOperations {
   Real _compliance = 0., _dcompliance_dp = 0.;
 };
 
+// von Mises p-norm / KS aggregate over the quadrature points (src/elasticity/stress_output_base.h:246-252, .cpp:851-909,
+// 1104-1172).  Only p_norm_weight == 1 (the reference's default, stress_output_base.cpp:278-281) is on the device path.
+class StressStrainOutputBase : public OutputAssemblyElemOperations {
+ public:
+  void init(const GeomElem& elem) override;
+  void set_aggregation_coefficients(Real p1, Real p2, Real rho, Real sigma0) {
+    _p_norm_stress = p1; _p_norm_weight = p2; _rho = rho; _sigma0 = sigma0;
+  }
+  Real get_p_stress_val() const { return _p_norm_stress; }
+  void zero_for_analysis() override { _sigma_vm_int = 0.; _JxW_val = 0.; _primal_data_initialized = false; }
+  void zero_for_sensitivity() override {}
+  Real output_total() override;   // functional_for_all_elems
+  Real output_sensitivity_total(const FunctionBase&) override;
+  void evaluate() override;
+  void evaluate_sensitivity(const FunctionBase& f) override;
+  void output_derivative_for_elem(RealVectorX& dq_dX) override;
+ private:
+  friend class AssemblyBase;
+  Real _p_norm_stress = 2., _p_norm_weight = 1., _rho = 1., _sigma0 = 1.;
+  Real _sigma_vm_int = 0., _JxW_val = 0.;   // the two sums of functional_for_all_elems (this rank's part)
+  bool _primal_data_initialized = false;
+};
+
 // ---- assemblies ---------------------------------------------------------------------------------------------------
 class AssemblyBase : public libMesh::NonlinearImplicitSystem::ComputeResidualandJacobian {
  public:

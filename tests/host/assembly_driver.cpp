@@ -140,6 +140,17 @@ int main(int argc, char** argv) {
       }
       compliance.clear_discipline_and_system();
     }
+    if (which == "c1") {  // StressStrainOutputBase: von Mises p-norm aggregate and its state derivative (adjoint rhs)
+      MAST::StressStrainOutputBase stress;
+      stress.set_discipline_and_system(discipline, *sys_init);
+      stress.set_aggregation_coefficients(6., 1., 1.5, 2.0e8);
+      assembly.calculate_output(*system.solution, false, stress);
+      sc << "stress_functional " << stress.output_total() << "\n";
+      libMesh::NumericVector<Real> ds_dX(system.n_dofs());
+      assembly.calculate_output_derivative(*system.solution, false, stress, ds_dX);
+      write_bin(dir + "/ds_dX.bin", ds_dX.get_array_read(), ds_dX.size());
+      stress.clear_discipline_and_system();
+    }
     sc << "kernel_launches " << assembly.device_kernel_launches() << "\n";
 
     // error behaviour: the per-element host virtuals are not a fallback

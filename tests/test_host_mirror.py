@@ -63,6 +63,10 @@ def test_mirror_c1_cantilever_reference_layout(built, tmp_path):
     s = _compare_common(prob, tmp_path, X)
     assert np.isclose(s["compliance"], prob.compliance(X), rtol=1e-12)
     _close(np.fromfile(tmp_path / "dq_dX.bin"), prob.compliance_derivative(X))
+    # StressStrainOutputBase through calculate_output / calculate_output_derivative
+    q, dq = prob.stress_functional(X, 6.0, 1.5, 2.0e8, want_derivative=True)
+    assert np.isclose(s["stress_functional"], q, rtol=1e-12)
+    _close(np.fromfile(tmp_path / "ds_dX.bin"), dq, 1e-11)
 
 
 @pytest.mark.gpu

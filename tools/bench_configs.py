@@ -135,15 +135,82 @@ def c5(a):
            fp64_peak_tflops=36.7)
 
 
+def gl(a):
+    # HEX8 Green-Lagrange strain (row-owner gather kernel), 100^3
+    n = a.gl
+    xyz, conn = mesh.build_cube(n, n, n, 1.0, 1.0, 1.0, 8, jitter=a.jitter)
+    nv = 3
+    ctx = mast_b200.Context(0)
+    ctx.set_mesh(mast_b200.HEX8, xyz, conn)
+    ctx.set_dof_map(nv, mesh.dirichlet_flags(len(xyz), nv, mesh.boundary_nodes(n, n, n, 4)))
+    ctx.set_material(E0=72e9, nu=0.33, nonlinear_strain=1)
+    ctx.build_pattern()
+    X = torch.from_numpy(1e-3 * mt(1, len(xyz) * nv, -1, 1)).cuda()
+    R = torch.empty(len(xyz) * nv, dtype=torch.float64, device="cuda")
+    J = torch.empty(ctx.nnz, dtype=torch.float64, device="cuda")
+    ms, _ = timed(ctx, lambda: ctx.residual_and_jacobian(X, R, J), a.reps)
+    report(f"HEX8 {n}^3 Green-Lagrange R+J (gather kernel)", len(conn), ms,
+           ctx.nnz * 8 + len(xyz) * (nv * 16 + 24) + len(conn) * 32)
+
+
+def plate(a):
+    # QUAD4 Mindlin plate, 1024^2, nv = 6
+    n = a.plate
+    xyz, conn = mesh.build_square(n, n)
+    ctx = mast_b200.Context(0)
+    ctx.set_mesh(mast_b200.QUAD4, xyz, conn)
+    ctx.set_dof_map(6, mesh.dirichlet_flags(len(xyz), 6, np.flatnonzero(xyz[:, 0] == 0.0)))
+    ctx.set_material(E0=72e9, nu=0.33, thickness=0.06, offset=0.0, kappa=5.0 / 6.0)
+    ctx.build_pattern()
+    X = torch.from_numpy(1e-3 * mt(1, len(xyz) * 6, -1, 1)).cuda()
+    R = torch.empty(len(xyz) * 6, dtype=torch.float64, device="cuda")
+    J = torch.empty(ctx.nnz, dtype=torch.float64, device="cuda")
+    ms, _ = timed(ctx, lambda: ctx.residual_and_jacobian(X, R, J), a.reps)
+    report(f"QUAD4 {n}^2 Mindlin plate nv=6 R+J", len(conn), ms, ctx.nnz * 8 + len(xyz) * (6 * 16 + 24) + len(conn) * 16)
+
+
+def stress(a):
+    # C5's output: von Mises p-norm aggregate and its state derivative (the adjoint right-hand side) on HEX27
+    nx, ny, nz = a.c5s
+    xyz, conn = mesh.build_cube(nx, ny, nz, 2.0, 1.0, 1.0, 27, jitter=a.jitter27)
+    nv = 3
+    ctx = mast_b200.Context(0)
+    ctx.set_mesh(mast_b200.HEX27, xyz, conn)
+    ctx.set_dof_map(nv, mesh.dirichlet_flags(len(xyz), nv, mesh.boundary_nodes(nx, ny, nz, 4, 27)))
+    ctx.set_material(E0=72e9, nu=0.33)
+    ctx.build_pattern()
+    n_nodes = len(xyz)
+    X = torch.from_numpy(1e-3 * mt(1, n_nodes * nv, -1, 1)).cuda()
+    dq = torch.empty(n_nodes * nv, dtype=torch.float64, device="cuda")
+    q, sums = ctx.stress_functional(X, 8.0, 2.0, 1.0e8)
+    t = []
+    for _ in range(a.reps):
+        ctx.stress_functional(X, 8.0, 2.0, 1.0e8)
+        t.append(ctx.stats()["last_sweep_ms"])
+    ms = float(np.min(t[1:]))
+    report(f"C5-output {nx}x{ny}x{nz} HEX27 von Mises p-norm aggregate", len(conn), ms,
+           n_nodes * 48 + len(conn) * 27 * 4, q=q)
+    t = []
+    for _ in range(a.reps):
+        ctx.stress_functional_derivative(X, 8.0, 2.0, 1.0e8, sums, dq)
+        t.append(ctx.stats()["last_sweep_ms"])
+    ms = float(np.min(t[1:]))
+    report(f"C5-output {nx}x{ny}x{nz} HEX27 aggregate state derivative (adjoint rhs)", len(conn), ms,
+           n_nodes * 72 + len(conn) * 27 * (4 + 2 * 72))
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", nargs="*", default=["c1", "c2", "c4", "c5"])
     ap.add_argument("--reps", type=int, default=4)
     ap.add_argument("--c4", type=int, default=256)
     ap.add_argument("--c5", type=int, nargs=3, default=[200, 100, 100])
+    ap.add_argument("--gl", type=int, default=100)
+    ap.add_argument("--plate", type=int, default=1024)
+    ap.add_argument("--c5s", type=int, nargs=3, default=[100, 50, 50])
     ap.add_argument("--jitter", type=float, default=0.2)
     ap.add_argument("--jitter27", type=float, default=0.1)
     a = ap.parse_args()
     for name in a.only:
-        {"c1": c1, "c2": c2, "c4": c4, "c5": c5}[name](a)
+        {"c1": c1, "c2": c2, "c4": c4, "c5": c5, "gl": gl, "plate": plate, "stress": stress}[name](a)
         torch.cuda.empty_cache()
