@@ -631,6 +631,75 @@ int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J
   return MASTB200_OK;
 }
 
+int fill_stress_params(mastb200_context* ctx, const double* X, StressParams& p) {
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (!X) return ctx->fail(MASTB200_ERR_ARG, "X is NULL");
+  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "stress output: 3D solids (HEX8, HEX27) only");
+  if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "stress output needs nv = 3 or 6");
+  CU(cudaSetDevice(ctx->device));
+  if ((rc = ensure_generic_plan(ctx))) return rc;
+  mastb200_context::GenericPlan& G = ctx->gplan;
+  const double* dX = nullptr;
+  if ((rc = resolve_in(ctx, X, size_t(ctx->n_nodes) * ctx->nv, ctx->d_X, &dX))) return rc;
+  p = StressParams();
+  p.n_elem = ctx->n_elem; p.n_owned = ctx->pat.n_owned;
+  p.nn = ctx->nn; p.nq = ctx->nn; p.nv = ctx->nv; p.nonlinear = ctx->mat.nonlinear_strain ? 1 : 0;
+  p.conn = G.conn.p; p.tab = G.tab.p; p.xyz = ctx->d_xyz.p; p.X = dX;
+  p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+  p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+  p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+  p.owned_nodes = ctx->d_owned_nodes.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p;
+  const mastb200_material& m = ctx->mat;
+  p.E0 = m.E0;
+  p.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu);
+  p.mu1 = 1. / 2. / (1. + m.nu);
+  p.rho_min = m.rho_min; p.penalty = m.penalty;
+  return MASTB200_OK;
+}
+int upload_elem_mask(mastb200_context* ctx, const uint8_t* elem_mask, const uint8_t** out) {
+  *out = nullptr;
+  if (!elem_mask) return MASTB200_OK;
+  if (is_device_ptr(elem_mask)) { *out = elem_mask; return MASTB200_OK; }
+  CU(ctx->d_elem_mask.ensure(ctx->n_elem));
+  CU(cudaMemcpyAsync(ctx->d_elem_mask.p, elem_mask, ctx->n_elem, cudaMemcpyHostToDevice, ctx->stream));
+  *out = ctx->d_elem_mask.p;
+  return MASTB200_OK;
+}
+
+// density sensitivities alone: two element-parallel launches (stress_output.cu), HEX8 and HEX27, linear strain
+int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, double* G) {
+  int rc;
+  if (!ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
+  if (ctx->mat.nonlinear_strain)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities with Green-Lagrange strain are not on the device path");
+  if (ctx->thermal)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED,
+                     "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
+  StressParams p;
+  if ((rc = fill_stress_params(ctx, X, p))) return rc;
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const double* dadj = nullptr;
+  double* dG = nullptr;
+  if (adj == X) dadj = p.X;  // compliance: the adjoint is the state
+  else if ((rc = resolve_in(ctx, adj, n_dof, ctx->d_adj, &dadj))) return rc;
+  if ((rc = resolve_out(ctx, G, (size_t)ctx->n_nodes, ctx->d_G, &dG))) return rc;
+  CU(ctx->d_scratch.ensure(size_t(ctx->n_elem) * p.nq));
+  p.scratch = ctx->d_scratch.p;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (ctx->has_ghosts) CU(cudaMemsetAsync(dG, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_density_sensitivities(p, dadj, dG, ctx->stream));
+  ctx->launches += 2;
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  if ((rc = finish_out(ctx, G, (size_t)ctx->n_nodes, dG))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
 // the common sweep: any of R, J, G may be null
 int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G, double* R, double* J) {
   int rc = check_ready(ctx);
@@ -638,8 +707,10 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   if (!X) return ctx->fail(MASTB200_ERR_ARG, "X is NULL");
   if (G && !adj) return ctx->fail(MASTB200_ERR_ARG, "adjoint vector is NULL");
   if (ctx->elem_type != MASTB200_HEX8) {
-    if (G) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities: HEX8 only for now");
-    return run_generic_sweep(ctx, X, R, J);
+    if (G && ctx->elem_type != MASTB200_HEX27) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities: 3D solids only");
+    if ((R || J) && (rc = run_generic_sweep(ctx, X, R, J))) return rc;
+    if (G) return run_density_sens(ctx, X, adj, G);
+    return MASTB200_OK;
   }
   if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX8 elasticity needs nv = 3 or 6");
   if (ctx->mat.nonlinear_strain) {
@@ -647,6 +718,10 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     return run_hex8_gather(ctx, X, R, J);
   }
   if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
+  {  // sensitivities alone: element-parallel kernels instead of the streaming sweep (MASTB200_SENS_SWEEP=1: old path)
+    const char* e = getenv("MASTB200_SENS_SWEEP");
+    if (G && !R && !J && !(e && e[0] == '1')) return run_density_sens(ctx, X, adj, G);
+  }
   if (G && ctx->thermal)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED,
                      "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
@@ -1071,44 +1146,6 @@ int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, doubl
   return MASTB200_OK;
 }
 
-namespace {
-int fill_stress_params(mastb200_context* ctx, const double* X, StressParams& p) {
-  int rc = check_ready(ctx);
-  if (rc) return rc;
-  if (!X) return ctx->fail(MASTB200_ERR_ARG, "X is NULL");
-  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "stress output: 3D solids (HEX8, HEX27) only");
-  if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "stress output needs nv = 3 or 6");
-  CU(cudaSetDevice(ctx->device));
-  if ((rc = ensure_generic_plan(ctx))) return rc;
-  mastb200_context::GenericPlan& G = ctx->gplan;
-  const double* dX = nullptr;
-  if ((rc = resolve_in(ctx, X, size_t(ctx->n_nodes) * ctx->nv, ctx->d_X, &dX))) return rc;
-  p = StressParams();
-  p.n_elem = ctx->n_elem; p.n_owned = ctx->pat.n_owned;
-  p.nn = ctx->nn; p.nq = ctx->nn; p.nv = ctx->nv; p.nonlinear = ctx->mat.nonlinear_strain ? 1 : 0;
-  p.conn = G.conn.p; p.tab = G.tab.p; p.xyz = ctx->d_xyz.p; p.X = dX;
-  p.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
-  p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
-  p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
-  p.owned_nodes = ctx->d_owned_nodes.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p;
-  const mastb200_material& m = ctx->mat;
-  p.E0 = m.E0;
-  p.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu);
-  p.mu1 = 1. / 2. / (1. + m.nu);
-  p.rho_min = m.rho_min; p.penalty = m.penalty;
-  return MASTB200_OK;
-}
-int upload_elem_mask(mastb200_context* ctx, const uint8_t* elem_mask, const uint8_t** out) {
-  *out = nullptr;
-  if (!elem_mask) return MASTB200_OK;
-  if (is_device_ptr(elem_mask)) { *out = elem_mask; return MASTB200_OK; }
-  CU(ctx->d_elem_mask.ensure(ctx->n_elem));
-  CU(cudaMemcpyAsync(ctx->d_elem_mask.p, elem_mask, ctx->n_elem, cudaMemcpyHostToDevice, ctx->stream));
-  *out = ctx->d_elem_mask.p;
-  return MASTB200_OK;
-}
-}  // namespace
 
 int mastb200_stress(mastb200_context* ctx, const double* X, double* stress, double* strain, double* von_mises,
                     double* jxw) {

@@ -167,6 +167,8 @@ int stress_blocks(int64_t n_elem, int nq);
 cudaError_t launch_stress_qp(const StressParams& p, cudaStream_t stream);
 cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaStream_t stream);
 cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream);  // two launches
+// density sensitivities alone (no R/J): G[n] = adj . dR/d(rho_n); scratch: [n_elem*nq] doubles (two launches)
+cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream);
 
 // SURFACE_PRESSURE side loads gathered per loaded node (loads.cu)
 struct FaceLoadPlan {

@@ -260,3 +260,108 @@ cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream)
 }
 
 }  // namespace mastb200
+
+// ---- density sensitivities alone (SURVEY 8a row S without R/J): G_n = adj . dR/d(rho_n) for every owned node ------------
+// Device counterpart of NonlinearImplicitAssembly::sensitivity_assemble (/root/reference/src/base/
+// nonlinear_implicit_assembly.cpp:515-686) + StructuralElement3D::internal_residual_sensitivity
+// (src/elasticity/solid_element_3d.cpp:566-788, D <- dD/dp at :640) + the dot products of
+// AssemblyBase::calculate_output_adjoint_sensitivity_multiple_parameters_no_direct (src/base/assembly_base.cpp:594-639)
+// for nodal-density design variables under the SIMP law (examples/structural/example_6/example_6.cpp:100-137), linear
+// strain:  adj . dR_e/d(rho_n) = sum_q N_n(q) JxW E'(rho_q) eps(adj)^T D_1 eps(u), adj zeroed on constrained dofs
+// (constrain_element_vector).  Pass 1: one thread per (element, qp) -> the scalar s_q; pass 2: row-owner gather,
+// one thread per owned node over its adjacent elements in ascending id (the reference's ADD order).
+namespace mastb200 {
+namespace {
+
+__global__ void __launch_bounds__(128) sens_qp_kernel(const StressParams p, const double* __restrict__ adj) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (t >= p.n_elem * p.nq) return;
+  const int64_t e = t / p.nq;
+  const int q = (int)(t - e * p.nq);
+  if (p.diag_elem && p.diag_elem[e]) { p.scratch[t] = 0.; return; }
+  const int nn = p.nn, nq = p.nq;
+  const double* Nt = p.tab + (size_t)q * nn;
+  const double* dNt = p.tab + (size_t)nq * nn + (size_t)q * nn * 3;
+  const int32_t* en = p.conn + e * nn;
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+  for (int b = 0; b < nn; ++b) {
+    const double* X = p.xyz + (int64_t)en[b] * 3;
+    const double d0 = dNt[b * 3], d1 = dNt[b * 3 + 1], d2 = dNt[b * 3 + 2];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      Jm[0][c] = fma(d0, X[c], Jm[0][c]); Jm[1][c] = fma(d1, X[c], Jm[1][c]); Jm[2][c] = fma(d2, X[c], Jm[2][c]);
+    }
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = 1. / det;
+  double inv[3][3];
+  inv[0][0] = c00 * idet; inv[1][0] = c01 * idet; inv[2][0] = c02 * idet;
+  inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+  inv[1][1] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+  inv[2][1] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+  inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+  inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+  inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+  double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}}, A[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+  double rho = 0.;
+  for (int b = 0; b < nn; ++b) {
+    const double d0 = dNt[b * 3], d1 = dNt[b * 3 + 1], d2 = dNt[b * 3 + 2];
+    double g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = d0 * inv[c][0] + d1 * inv[c][1] + d2 * inv[c][2];
+    const int64_t n = en[b];
+    const double* U = p.X + n * p.nv;
+    const double* L = adj + n * p.nv;
+    const unsigned cm = p.cmask ? p.cmask[n] : 0u;
+    const double u0 = U[0], u1 = U[1], u2 = U[2];
+    const double l0 = (cm & 1u) ? 0. : L[0], l1 = (cm & 2u) ? 0. : L[1], l2 = (cm & 4u) ? 0. : L[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      H[0][j] = fma(u0, g[j], H[0][j]); H[1][j] = fma(u1, g[j], H[1][j]); H[2][j] = fma(u2, g[j], H[2][j]);
+      A[0][j] = fma(l0, g[j], A[0][j]); A[1][j] = fma(l1, g[j], A[1][j]); A[2][j] = fma(l2, g[j], A[2][j]);
+    }
+    rho = fma(Nt[b], p.rho[n], rho);
+  }
+  const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
+  const double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
+  const double a0 = A[0][0], a1 = A[1][1], a2 = A[2][2];
+  const double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
+  const double dens = p.lam1 * (a0 + a1 + a2) * (e0 + e1 + e2) +
+                      p.mu1 * (2. * (a0 * e0 + a1 * e1 + a2 * e2) + a3 * e3 + a4 * e4 + a5 * e5);
+  const double dE = p.E0 * (1. - p.rho_min) * p.penalty * pow(rho, p.penalty - 1.);
+  p.scratch[t] = det * p.tab[(size_t)nq * nn * 4 + q] * dE * dens;
+}
+
+__global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, double* __restrict__ G) {
+  const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (r >= p.n_owned) return;
+  const int n = p.owned_nodes[r];
+  const int nn = p.nn, nq = p.nq;
+  double acc = 0.;
+  for (int64_t ke = p.n2e_ptr[n]; ke < p.n2e_ptr[n + 1]; ++ke) {
+    const int64_t e = p.n2e[ke];
+    const int32_t* en = p.conn + e * nn;
+    int a = 0;
+    for (int b = 0; b < nn; ++b)
+      if (en[b] == n) a = b;
+    double o = 0.;
+    for (int q = 0; q < nq; ++q) o = fma(p.tab[(size_t)q * nn + a], p.scratch[e * nq + q], o);
+    acc += o;
+  }
+  G[n] = acc;
+}
+
+}  // namespace
+
+cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream) {
+  sens_qp_kernel<<<stress_blocks(p.n_elem, p.nq), 128, 0, stream>>>(p, adj);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sens_gather_kernel<<<(int)((p.n_owned + 127) / 128), 128, 0, stream>>>(p, G);
+  return cudaGetLastError();
+}
+
+}  // namespace mastb200
