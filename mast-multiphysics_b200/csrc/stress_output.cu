@@ -335,6 +335,105 @@ __global__ void __launch_bounds__(128) sens_qp_kernel(const StressParams p, cons
   p.scratch[t] = det * p.tab[(size_t)nq * nn * 4 + q] * dE * dens;
 }
 
+// HEX8 specialisation: reference gradients from the node signs (no table loads), fully unrolled, one (element, qp) per
+// thread with the eight qps of an element in adjacent lanes (their node loads coalesce into broadcasts)
+__device__ __forceinline__ double pow_penalty_m1(double rho, double pm1) {
+  // E'(rho) needs rho^(penalty-1): small integer exponents (the usual SIMP penalties) by multiplication
+  if (pm1 == 3.) return rho * rho * rho;
+  if (pm1 == 2.) return rho * rho;
+  if (pm1 == 1.) return rho;
+  if (pm1 == 0.) return 1.;
+  return pow(rho, pm1);
+}
+
+__global__ void __launch_bounds__(256, 2) sens_qp_hex8_kernel(const StressParams p, const double* __restrict__ adj) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool live = t < p.n_elem * 8;
+  const int64_t e = live ? (t >> 3) : 0;
+  const int q = (int)(t & 7);
+  const bool skip = !live || (p.diag_elem && p.diag_elem[e]);
+  const double GPq = 0.57735026918962576451;
+  const double xi = (q & 1) ? GPq : -GPq, eta = (q & 2) ? GPq : -GPq, zeta = (q & 4) ? GPq : -GPq;
+  const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
+  int en[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) en[b] = p.conn[e * 8 + b];
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool px = b == 1 || b == 2 || b == 5 || b == 6, py = b == 2 || b == 3 || b == 6 || b == 7, pz = b >= 4;
+    const double fx = px ? xp : xm, fy = py ? yp : ym, fz = pz ? zp : zm;
+    const double d0 = (px ? 0.125 : -0.125) * fy * fz, d1 = (py ? 0.125 : -0.125) * fx * fz, d2 = (pz ? 0.125 : -0.125) * fx * fy;
+    const double* X = p.xyz + (int64_t)en[b] * 3;
+    const double x0 = X[0], x1 = X[1], x2 = X[2];
+    Jm[0][0] = fma(d0, x0, Jm[0][0]); Jm[0][1] = fma(d0, x1, Jm[0][1]); Jm[0][2] = fma(d0, x2, Jm[0][2]);
+    Jm[1][0] = fma(d1, x0, Jm[1][0]); Jm[1][1] = fma(d1, x1, Jm[1][1]); Jm[1][2] = fma(d1, x2, Jm[1][2]);
+    Jm[2][0] = fma(d2, x0, Jm[2][0]); Jm[2][1] = fma(d2, x1, Jm[2][1]); Jm[2][2] = fma(d2, x2, Jm[2][2]);
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = 1. / det;
+  double inv[3][3];
+  inv[0][0] = c00 * idet; inv[1][0] = c01 * idet; inv[2][0] = c02 * idet;
+  inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+  inv[1][1] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+  inv[2][1] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+  inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+  inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+  inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+  double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}}, A[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+  double rho = 0.;
+  const bool same = adj == p.X;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool px = b == 1 || b == 2 || b == 5 || b == 6, py = b == 2 || b == 3 || b == 6 || b == 7, pz = b >= 4;
+    const double fx = px ? xp : xm, fy = py ? yp : ym, fz = pz ? zp : zm;
+    const double d0 = (px ? 0.125 : -0.125) * fy * fz, d1 = (py ? 0.125 : -0.125) * fx * fz, d2 = (pz ? 0.125 : -0.125) * fx * fy;
+    const double Nb = 0.125 * fx * fy * fz;
+    double g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = d0 * inv[c][0] + d1 * inv[c][1] + d2 * inv[c][2];
+    const int64_t n = en[b];
+    const double* U = p.X + n * p.nv;
+    const unsigned cm = p.cmask ? p.cmask[n] : 0u;
+    const double u0 = U[0], u1 = U[1], u2 = U[2];
+    double l0 = u0, l1 = u1, l2 = u2;
+    if (!same) { const double* L = adj + n * p.nv; l0 = L[0]; l1 = L[1]; l2 = L[2]; }
+    if (cm & 1u) l0 = 0.;
+    if (cm & 2u) l1 = 0.;
+    if (cm & 4u) l2 = 0.;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      H[0][j] = fma(u0, g[j], H[0][j]); H[1][j] = fma(u1, g[j], H[1][j]); H[2][j] = fma(u2, g[j], H[2][j]);
+      A[0][j] = fma(l0, g[j], A[0][j]); A[1][j] = fma(l1, g[j], A[1][j]); A[2][j] = fma(l2, g[j], A[2][j]);
+    }
+    rho = fma(Nb, p.rho[n], rho);
+  }
+  const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
+  const double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
+  const double a0 = A[0][0], a1 = A[1][1], a2 = A[2][2];
+  const double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
+  const double dens = p.lam1 * (a0 + a1 + a2) * (e0 + e1 + e2) +
+                      p.mu1 * (2. * (a0 * e0 + a1 * e1 + a2 * e2) + a3 * e3 + a4 * e4 + a5 * e5);
+  const double dE = p.E0 * (1. - p.rho_min) * p.penalty * pow_penalty_m1(rho, p.penalty - 1.);
+  const double sq = skip ? 0. : det * dE * dens;
+  // the eight lanes of the element turn the point values into nodal ones: lane a ends with sum_q N_a(q) s_q (q ascending)
+  const int a = q, lane = threadIdx.x & 31;
+  const bool ax = a == 1 || a == 2 || a == 5 || a == 6, ay = a == 2 || a == 3 || a == 6 || a == 7, az = a >= 4;
+  double acc = 0.;
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq) {
+    const double s = __shfl_sync(0xffffffffu, sq, (lane & ~7) | qq);
+    const double fx = ((qq & 1) != 0) == ax ? 1. + GPq : 1. - GPq;
+    const double fy = ((qq & 2) != 0) == ay ? 1. + GPq : 1. - GPq;
+    const double fz = ((qq & 4) != 0) == az ? 1. + GPq : 1. - GPq;
+    acc = fma(0.125 * fx * fy * fz, s, acc);
+  }
+  if (live) p.scratch[t] = acc;  // [element][node]
+}
+
 __global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, double* __restrict__ G) {
   const int64_t r = (int64_t)blockIdx.x * 128 + threadIdx.x;
   if (r >= p.n_owned) return;
@@ -348,7 +447,9 @@ __global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, 
     for (int b = 0; b < nn; ++b)
       if (en[b] == n) a = b;
     double o = 0.;
-    for (int q = 0; q < nq; ++q) o = fma(p.tab[(size_t)q * nn + a], p.scratch[e * nq + q], o);
+    if (nn == 8) o = p.scratch[e * 8 + a];  // already summed over the points (sens_qp_hex8_kernel)
+    else
+      for (int q = 0; q < nq; ++q) o = fma(p.tab[(size_t)q * nn + a], p.scratch[e * nq + q], o);
     acc += o;
   }
   G[n] = acc;
@@ -357,7 +458,8 @@ __global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, 
 }  // namespace
 
 cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream) {
-  sens_qp_kernel<<<stress_blocks(p.n_elem, p.nq), 128, 0, stream>>>(p, adj);
+  if (p.nn == 8) sens_qp_hex8_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(p, adj);
+  else sens_qp_kernel<<<stress_blocks(p.n_elem, p.nq), 128, 0, stream>>>(p, adj);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   sens_gather_kernel<<<(int)((p.n_owned + 127) / 128), 128, 0, stream>>>(p, G);
