@@ -43,9 +43,10 @@ struct StructParams {
   const double* xyz = nullptr;
   const double* X = nullptr;
   const uint8_t* cmask = nullptr;
+  const double* rho = nullptr;           // nodal density (SIMP modulus) or null
   double* J = nullptr;
   double* R = nullptr;
-  double E0 = 0., lam1 = 0., mu1 = 0.;
+  double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1.;
 };
 size_t hex8_struct_smem_bytes();
 int hex8_struct_threads();

@@ -53,10 +53,11 @@ constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;  // [SW][4 el][8 qp][
 constexpr int O_CNT = O_STAGE + SW * 4 * 8 * QS * 8;    // [NS] int32 (+pad)
 constexpr int O_CM = O_CNT + 84 * 4;                    // [4 planes][84] uint8
 constexpr int O_TAB = O_CM + 4 * 84;                    // [124] int32: array offsets within an IN / CR region
-constexpr int O_NODE = O_TAB + 124 * 4;                 // [64] int2: owned nodes of the unit (in-plane id, slot | boundary flags)
+constexpr int O_RHO = O_TAB + 124 * 4;                  // [3 planes][NS] nodal density (SIMP variant)
+constexpr int O_NODE = O_RHO + 3 * NS * 8;              // [64] int2: owned nodes of the unit (in-plane id, slot | boundary flags)
 constexpr int O_MISC = O_NODE + 64 * 8;
 constexpr int SMEM_BYTES = O_MISC + 16;
-static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0, "alignment");
+static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0, "alignment");
 static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
@@ -92,6 +93,7 @@ struct Sm {
   int32_t* cnt;
   uint8_t* cm;
   int32_t* tab;
+  double* rho;
   int2* node;
   int* misc;
 };
@@ -156,6 +158,7 @@ __device__ __forceinline__ void make_lane(const StructParams& p, const int32_t* 
 }
 
 // ---- geometry: lane = (element el of the warp's 2x2 block, quadrature point q) ------------------------------------
+template <bool SIMP>
 __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& sm, int s, int base, int q, double* out) {
   const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP, zeta = (q & 4) ? GP : -GP;
   const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
@@ -189,7 +192,17 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
   o[1] = make_double2(inv[0][2], inv[1][0]);
   o[2] = make_double2(inv[1][1], inv[1][2]);
   o[3] = make_double2(inv[2][0], inv[2][1]);
-  o[4] = make_double2(inv[2][2], det * p.E0);  // Gauss weights are 1 for the 2x2x2 rule
+  double E = p.E0;
+  if (SIMP) {  // modulus of the interpolated nodal density (examples/structural/example_6/example_6.cpp:100-137)
+    double r = 0.;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
+      r = fma(0.125 * fx * fy * fz, sm.rho[(((m & 4) ? s + 1 : s) % 3) * NS + base + ((m >> 1) & 1) * TCX + (m & 1)], r);
+    }
+    E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(r, p.penalty));
+  }
+  o[4] = make_double2(inv[2][2], det * E);  // Gauss weights are 1 for the 2x2x2 rule
 }
 
 // ---- matrix + ordered accumulate: all 32 lanes on one element ------------------------------------------------------
@@ -344,6 +357,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
   }
 }
 
+template <bool SIMP>
 __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Sm sm;
@@ -354,6 +368,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
   sm.cnt = reinterpret_cast<int32_t*>(smem_raw + O_CNT);
   sm.cm = smem_raw + O_CM;
   sm.tab = reinterpret_cast<int32_t*>(smem_raw + O_TAB);
+  sm.rho = reinterpret_cast<double*>(smem_raw + O_RHO);
   sm.node = reinterpret_cast<int2*>(smem_raw + O_NODE);
   sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -395,7 +410,11 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
       cm_dst = ly * TCX + lx;
       cm_src = (u.e0x + lx) + (u.e0y + ly) * npx;
     }
-    auto load_plane = [&](int z) {  // coordinates and displacements of node plane z, asynchronously
+    auto load_plane = [&](int z) {  // coordinates, displacements (and density) of node plane z, asynchronously
+      if (SIMP && tid < ncols) {
+        const int ly = tid / ncx, lx = tid - ly * ncx;
+        cp_async8(sm.rho + (z % 3) * NS + ly * TCX + lx, p.rho + (int64_t)z * plane_nodes + (u.e0x + lx) + (u.e0y + ly) * npx);
+      }
       if (ld_on) {
         if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * 3 + ld_src);
         else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
@@ -453,7 +472,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
         {
           const int el = lane >> 3, q = lane & 7;
           const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
-          if (lex < u.nex && ley < u.ney) geometry_phase(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
+          if (lex < u.nex && ley < u.ney) geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
         }
         __syncwarp();
         if (s & 1) {
@@ -498,9 +517,15 @@ int hex8_struct_threads() { return ST; }
 cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(hex8_struct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  hex8_struct_kernel<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+  if (p.rho) {
+    e = cudaFuncSetAttribute(hex8_struct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    hex8_struct_kernel<true><<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(hex8_struct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    hex8_struct_kernel<false><<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

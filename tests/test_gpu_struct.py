@@ -118,3 +118,26 @@ def test_struct_large_mesh_properties(built):
     assert np.abs(A @ X - R).max() <= 1e-12 * np.abs(R).max()
     rb = np.zeros((len(xyz), 3)); rb[:, 0] = 1.0 - 0.3 * xyz[:, 1]; rb[:, 1] = 0.3 * xyz[:, 0]  # translation + rotation
     assert np.abs(A @ rb.ravel()).max() <= 1e-9 * np.abs(J).max()
+
+
+def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch):
+    # SIMP modulus in the implicit-connectivity sweep; G requested together with R/J comes from the element-parallel
+    # kernels right after it; same numbers as the plan-driven fused sweep
+    prob = O.cantilever(11, 9, 8, jitter=0.2, simp=True)
+    X = O.state(prob.n_dof, 1); lam = O.state(prob.n_dof, 2)
+    n = prob.n_nodes
+    ctx = prob.make_context(0)
+    G = np.full(n, np.nan); R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
+    ctx.sensitivity_sweep(X, lam, G, R, J)
+    assert ctx.stats()["structured"] == 1
+    Ro, Jo = prob.residual_and_jacobian(X)
+    _close(R, Ro); _close(J, Jo)
+    g_ref = prob.adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
+    _close(G, g_ref, 1e-11)
+    assert np.isclose(ctx.res_l2_norm(), np.linalg.norm(R), rtol=1e-13)
+    monkeypatch.setenv("MASTB200_NO_STRUCT", "1")
+    ctx2 = prob.make_context(0)
+    G2 = np.full(n, np.nan); R2 = np.full(prob.n_dof, np.nan); J2 = np.full(ctx2.nnz, np.nan)
+    ctx2.sensitivity_sweep(X, lam, G2, R2, J2)
+    assert ctx2.stats()["structured"] == 0
+    _close(G2, G, 1e-11); _close(R2, R); _close(J2, J)
