@@ -134,6 +134,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=48, help="edge of the CPU-baseline sample mesh")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sens", action="store_true")
     ap.add_argument("--quick-ref", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -224,6 +225,47 @@ def main():
     n_elem_global = int(cnt.item())
     value = n_elem_global * args.steps / (total_ms * 1e-3)
 
+    # ---- second half of the BASELINE metric: adjoint (compliance) density sensitivities on the same mesh ----
+    sens = None
+    if not args.no_sens:
+        rho = 0.2 + 0.6 * np.random.Generator(np.random.MT19937(3)).uniform(0.0, 1.0, (n + 1) ** 3)
+        rho_l = torch.from_numpy(rho[info["q0"] * npl:(info["q1"] + 1) * npl].copy()).cuda()
+        ctx.set_material(E0=72e9, nu=0.33, alpha=1.5e-5, rho_min=1e-8, penalty=4.0)
+        ctx.set_density(rho_l)
+        dG = torch.empty(len(lxyz), dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            ctx.sensitivity_sweep(dX, dX, dG)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(args.steps):
+            halo_exchange()
+            ctx.sensitivity_sweep(dX, dX, dG)
+        s1.record(stream)
+        barrier()
+        sms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        for _ in range(2):
+            ctx.sensitivity_sweep(dX, dX, dG, dR, dJ)
+        barrier()
+        s0.record(stream)
+        for _ in range(args.steps):
+            halo_exchange()
+            ctx.sensitivity_sweep(dX, dX, dG, dR, dJ)
+        s1.record(stream)
+        barrier()
+        fms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+        sens = {"metric": "hex8_adjoint_density_sensitivity_elems_per_s", "unit": UNIT,
+                "value": n_elem_global * args.steps / (float(sms.item()) * 1e-3),
+                "fused_with_residual_jacobian": n_elem_global * args.steps / (float(fms.item()) * 1e-3),
+                "config": f"same {n}^3 mesh, SIMP (rho_min 1e-8, p 4) of a nodal density field, compliance adjoint = state; "
+                          "value: G alone (two element-parallel kernels); fused: R + J + G of one state",
+                "gpu_launches_per_step": 2}
+        ctx.set_density(None)
+        ctx.set_material(E0=72e9, nu=0.33, alpha=1.5e-5)
+
     # ---- end-to-end through the C-ABI with host buffers (pinned), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -299,7 +341,7 @@ def main():
                          "bytes_per_element": alg_bytes / n_loc_elem,
                          "fp64": {"executed_tflops": flops_exec / (k_ms * 1e-3) / 1e12, "peak_tflops": 36.7,
                                   "peak_source": "profiles/r01_fp64_pipes.md (DFMA = DMMA = 36.7-37.1 TF, one shared pipe)"}},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "adjoint_sensitivity": sens, "gpu_launches": int(launches), "clocks": clocks,
             "kernel_share_of_step": float(np.sum(kern_ms) / total_ms),
         }
         if not args.no_cpu:
