@@ -145,6 +145,17 @@ int mastb200_stress_functional(mastb200_context* ctx, const double* X, double p_
 int mastb200_stress_functional_derivative(mastb200_context* ctx, const double* X, double p_norm, double rho_exp,
                                           double sigma0, const uint8_t* elem_mask, const double* sums, double* dq_dX);
 
+/* dq_drho[n_nodes] [h|d]: partial derivative (fixed state) of that aggregate w.r.t. the nodal densities of the SIMP law,
+ * rows of owned nodes; with mastb200_apply_dv_map_transpose it gives output_sensitivity_total(p) of every density DV,
+ * the dq/dp term that calculate_output_adjoint_sensitivity adds to adj . dR/dp (include_partial_sens = true)
+ *   <- AssemblyBase::calculate_output_direct_sensitivity + StressStrainOutputBase::functional_sensitivity_for_elem,
+ *      src/base/assembly_base.cpp:434-550, src/elasticity/stress_output_base.cpp:911-1043, with
+ *      dstress/dp = dD/dp strain (pattern of src/elasticity/structural_element_2d.cpp:664-677; the 3D element of the
+ *      reference sets no stress sensitivity at all, src/elasticity/solid_element_3d.cpp:1146-1265) */
+int mastb200_stress_functional_density_derivative(mastb200_context* ctx, const double* X, double p_norm, double rho_exp,
+                                                  double sigma0, const uint8_t* elem_mask, const double* sums,
+                                                  double* dq_drho);
+
 /* ---- introspection for bench / tests -------------------------------------------------------- */
 typedef struct mastb200_stats {
   int64_t n_tiles, n_visits, n_owned_nodes, n_elem;

@@ -20,6 +20,7 @@ EXPORTED_SYMBOLS = [
     "mastb200_residual_and_jacobian", "mastb200_res_l2_norm", "mastb200_sensitivity_sweep",
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
     "mastb200_stress", "mastb200_stress_functional", "mastb200_stress_functional_derivative",
+    "mastb200_stress_functional_density_derivative",
     "mastb200_get_stats", "mastb200_stream", "mastb200_debug_plan_sizes", "mastb200_debug_plan_copy",
 ]
 
@@ -91,6 +92,7 @@ def load_library():
     lib.mastb200_stress.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.mastb200_stress_functional.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, C.POINTER(dbl)]
     lib.mastb200_stress_functional_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
+    lib.mastb200_stress_functional_density_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
     lib.mastb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mastb200_debug_plan_sizes.argtypes = [vp, i32, vp]
     lib.mastb200_debug_plan_copy.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
@@ -241,6 +243,12 @@ class Context:
         sums = _np(sums, np.float64)
         self._ck(self._lib.mastb200_stress_functional_derivative(self._h, _ptr(X), p_norm, rho_exp, sigma0,
                                                                  _ptr(_np(elem_mask, np.uint8)), _ptr(sums), _ptr(dq_dX)))
+
+    def stress_functional_density_derivative(self, X, p_norm, rho_exp, sigma0, sums, dq_drho, elem_mask=None):
+        sums = _np(sums, np.float64)
+        self._ck(self._lib.mastb200_stress_functional_density_derivative(self._h, _ptr(X), p_norm, rho_exp, sigma0,
+                                                                         _ptr(_np(elem_mask, np.uint8)), _ptr(sums),
+                                                                         _ptr(dq_drho)))
 
     def stats(self):
         s = Stats()

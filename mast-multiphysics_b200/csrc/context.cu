@@ -1241,6 +1241,34 @@ int mastb200_stress_functional_derivative(mastb200_context* ctx, const double* X
   return MASTB200_OK;
 }
 
+int mastb200_stress_functional_density_derivative(mastb200_context* ctx, const double* X, double p_norm, double rho_exp,
+                                                  double sigma0, const uint8_t* elem_mask, const double* sums, double* dq_drho) {
+  if (!ctx || !sums || !dq_drho) return MASTB200_ERR_ARG;
+  if (!(sigma0 > 0.) || !(p_norm > 0.)) return ctx->fail(MASTB200_ERR_ARG, "sigma0 and p_norm must be positive");
+  StressParams p;
+  int rc = fill_stress_params(ctx, X, p);
+  if (rc) return rc;
+  if (!ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density derivatives need a nodal density field");
+  if ((rc = upload_elem_mask(ctx, elem_mask, &p.elem_mask))) return rc;
+  p.p_norm = p_norm; p.rho_exp = rho_exp; p.sigma0 = sigma0;
+  p.sum_num = sums[0]; p.sum_den = sums[1];
+  CU(ctx->d_scratch.ensure(size_t(ctx->n_elem) * p.nq));
+  p.scratch = ctx->d_scratch.p;
+  double* dG = nullptr;
+  if ((rc = resolve_out(ctx, dq_drho, (size_t)ctx->n_nodes, ctx->d_G, &dG))) return rc;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  if (ctx->has_ghosts) CU(cudaMemsetAsync(dG, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  CU(launch_stress_density_derivative(p, dG, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true; ctx->carry_ms = 0.;
+  ctx->launches += 2;
+  if ((rc = finish_out(ctx, dq_drho, (size_t)ctx->n_nodes, dG))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
 int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   if (!ctx || !s) return MASTB200_ERR_ARG;
   std::memset(s, 0, sizeof *s);

@@ -143,6 +143,7 @@ cudaError_t launch_hex8_gather(const SolidGatherParams& p, cudaStream_t stream);
 struct StressParams {
   int64_t n_elem = 0, n_owned = 0;
   int32_t nn = 8, nq = 8, nv = 3, nonlinear = 0;
+  int32_t scratch_nodal = 0;             // scratch holds [element][node] sums instead of [element][qp] point values
   const int32_t* conn = nullptr;
   const double* tab = nullptr;           // N[nq][nn], dN[nq][nn][3], w[nq]
   const double* xyz = nullptr;
@@ -170,6 +171,8 @@ cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaS
 cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream);  // two launches
 // density sensitivities alone (no R/J): G[n] = adj . dR/d(rho_n); scratch: [n_elem*nq] doubles (two launches)
 cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream);
+// dq/d(rho_n) of the stress aggregate at fixed state (two launches); scratch: [n_elem*nq] doubles
+cudaError_t launch_stress_density_derivative(const StressParams& p, double* G, cudaStream_t stream);
 
 // SURFACE_PRESSURE side loads gathered per loaded node (loads.cu)
 struct FaceLoadPlan {

@@ -29,7 +29,7 @@ struct QpGeom {
   double inv[3][3];  // inv[c][r] = d xi_r / d x_c
   double det, wq;
   double eps[6], sig[6];
-  double E;
+  double E, rho;
 };
 
 // geometry + linear/Green-Lagrange strain + stress at (e, q); tab: N[q][b], dN[q][b][3], w[q]
@@ -78,7 +78,7 @@ __device__ __forceinline__ void eval_qp(const StressParams& p, int64_t e, int q,
   }
   double E = p.E0;
   if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(rho, p.penalty));
-  g.E = E;
+  g.E = E; g.rho = rho;
   if (p.nonlinear) {
     double Eg[3][3];
 #pragma unroll
@@ -149,6 +149,41 @@ __global__ void __launch_bounds__(TB) stress_qp_kernel(const StressParams p) {
   if (p.partial) block_sum2(num, den, p.partial);
 }
 
+// chain-rule factor of one quadrature point: d(aggregate) = kappa_q * d(vm_q)
+// (functional_state_derivartive_for_elem / functional_sensitivity_for_elem, stress_output_base.cpp:978-1043, 1104-1172)
+__device__ __forceinline__ double aggregate_kappa(const StressParams& p, double vm, double JxW) {
+  const double Sn = p.sum_num, Sd = p.sum_den;
+  const double sp_w = (vm - p.sigma0) / p.sigma0;
+  const double sp_s = pow(vm / p.sigma0, p.p_norm), sp1_s = pow(vm / p.sigma0, p.p_norm - 1.);
+  double cn, cd;
+  if (p.rho_exp * sp_w > 1.e2) {
+    cn = p.p_norm * sp1_s * exp(1.e2) / p.sigma0 * JxW;
+    cd = 0.;
+  } else {
+    const double ex = exp(p.rho_exp * sp_w);
+    cd = ex * p.rho_exp / p.sigma0 * JxW;
+    cn = 1. / p.sigma0 * JxW * ex * (p.p_norm * sp1_s + sp_s * p.rho_exp);
+  }
+  return p.sigma0 / p.p_norm * pow(Sn / Sd, 1. / p.p_norm - 1.) * (cn / Sd - Sn / (Sd * Sd) * cd);
+}
+
+// partial derivative of the aggregate w.r.t. the nodal densities at fixed state: dstress/d(rho_n) = N_n E'(rho_q)/E sigma
+// (pattern of structural_element_2d.cpp:664-677), hence d(vm)/d(rho_n) = N_n E'/E vm; point scalar for the nodal gather
+__global__ void __launch_bounds__(TB) stress_drho_qp_kernel(const StressParams p) {
+  const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int64_t nqp = p.n_elem * p.nq;
+  if (t >= nqp) return;
+  const int64_t e = t / p.nq;
+  const int q = (int)(t - e * p.nq);
+  if ((p.elem_mask && !p.elem_mask[e]) || (p.diag_elem && p.diag_elem[e])) { p.scratch[t] = 0.; return; }
+  QpGeom g;
+  eval_qp(p, e, q, g);
+  const double vm = sqrt(vm_pp(g.sig));
+  const double kappa = aggregate_kappa(p, vm, g.det * g.wq);
+  const double dE = p.E0 * (1. - p.rho_min) * p.penalty * pow(g.rho, p.penalty - 1.);
+  p.scratch[t] = kappa * (dE / g.E) * vm;
+}
+
 // pass 2: T_q = kappa_q * M_q * J^-T per (element, qp), 9 doubles
 __global__ void __launch_bounds__(TB) stress_dq_qp_kernel(const StressParams p) {
   const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
@@ -166,20 +201,7 @@ __global__ void __launch_bounds__(TB) stress_dq_qp_kernel(const StressParams p) 
   eval_qp(p, e, q, g);  // the stress follows the strain measure; its derivative uses B_lin (the reference's 2D pattern)
   const double pp = vm_pp(g.sig);
   const double vm = sqrt(pp);
-  const double JxW = g.det * g.wq;
-  const double Sn = p.sum_num, Sd = p.sum_den;
-  const double sp_w = (vm - p.sigma0) / p.sigma0;
-  const double sp_s = pow(vm / p.sigma0, p.p_norm), sp1_s = pow(vm / p.sigma0, p.p_norm - 1.);
-  double cn, cd;
-  if (p.rho_exp * sp_w > 1.e2) {
-    cn = p.p_norm * sp1_s * exp(1.e2) / p.sigma0 * JxW;
-    cd = 0.;
-  } else {
-    const double ex = exp(p.rho_exp * sp_w);
-    cd = ex * p.rho_exp / p.sigma0 * JxW;
-    cn = 1. / p.sigma0 * JxW * ex * (p.p_norm * sp1_s + sp_s * p.rho_exp);
-  }
-  const double kappa = p.sigma0 / p.p_norm * pow(Sn / Sd, 1. / p.p_norm - 1.) * (cn / Sd - Sn / (Sd * Sd) * cd);
+  const double kappa = aggregate_kappa(p, vm, g.det * g.wq);
   double dv[6] = {0., 0., 0., 0., 0., 0.};
   if (fabs(pp) > 0.) {
     const double h = 0.5 / sqrt(pp);
@@ -447,7 +469,7 @@ __global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, 
     for (int b = 0; b < nn; ++b)
       if (en[b] == n) a = b;
     double o = 0.;
-    if (nn == 8) o = p.scratch[e * 8 + a];  // already summed over the points (sens_qp_hex8_kernel)
+    if (p.scratch_nodal) o = p.scratch[e * 8 + a];  // already summed over the points (sens_qp_hex8_kernel)
     else
       for (int q = 0; q < nq; ++q) o = fma(p.tab[(size_t)q * nn + a], p.scratch[e * nq + q], o);
     acc += o;
@@ -458,11 +480,23 @@ __global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, 
 }  // namespace
 
 cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream) {
-  if (p.nn == 8) sens_qp_hex8_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(p, adj);
-  else sens_qp_kernel<<<stress_blocks(p.n_elem, p.nq), 128, 0, stream>>>(p, adj);
+  StressParams q = p;
+  q.scratch_nodal = p.nn == 8 ? 1 : 0;
+  if (p.nn == 8) sens_qp_hex8_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(q, adj);
+  else sens_qp_kernel<<<stress_blocks(p.n_elem, p.nq), 128, 0, stream>>>(q, adj);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  sens_gather_kernel<<<(int)((p.n_owned + 127) / 128), 128, 0, stream>>>(p, G);
+  sens_gather_kernel<<<(int)((p.n_owned + 127) / 128), 128, 0, stream>>>(q, G);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_stress_density_derivative(const StressParams& p, double* G, cudaStream_t stream) {
+  StressParams q = p;
+  q.scratch_nodal = 0;
+  stress_drho_qp_kernel<<<stress_blocks(p.n_elem, p.nq), TB, 0, stream>>>(q);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  sens_gather_kernel<<<(int)((p.n_owned + 127) / 128), 128, 0, stream>>>(q, G);
   return cudaGetLastError();
 }
 

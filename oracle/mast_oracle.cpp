@@ -1245,6 +1245,77 @@ double oracle_stress_functional(const OracleProblem* p, const double* X, double 
   return q;
 }
 
+// StressStrainOutputBase::functional_sensitivity_for_elem / _for_all_elems (stress_output_base.cpp:911-1043) for
+// nodal-density design variables: the partial derivative of the aggregate at fixed state.  The stress sensitivity of
+// the 3D element is absent from the reference (solid_element_3d.cpp:1146-1265 has no parameter branch, so
+// Data::dvon_Mises_stress_dp returns 0 there); as for dstress/dX it follows the 2D element's pattern
+// (structural_element_2d.cpp:664-677): dstress/dp = dD/dp * strain, with dD/dp of
+// isotropic_material_property_card.cpp:533-567 and the SIMP law; dvon_Mises_stress_dp of stress_output_base.cpp:237-271.
+int oracle_stress_functional_density_sensitivity(const OracleProblem* p, const double* X, double p_norm, double rho_exp,
+                                                 double sigma0, int64_t n_dv, const int64_t* dv_ptr, const int32_t* dv_node,
+                                                 const double* dv_weight, double* sens) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  if (ei.dim != 3 || !p->rho) return 3;
+  const double p_norm_weight = 1., exp_arg_lim = 1.e2;
+  const size_t nqp = size_t(p->n_elem) * ei.nq;
+  std::vector<double> st(nqp * 6), en_(nqp * 6), vm(nqp), jw(nqp);
+  if (oracle_stress(p, X, st.data(), en_.data(), vm.data(), jw.data())) return 3;
+  double sigma_vm_int = 0., JxW_val = 0.;
+  for (size_t k = 0; k < nqp; ++k) {
+    const double sp = std::pow((vm[k] - sigma0) / sigma0, p_norm_weight);
+    const double exp_sp = (rho_exp * sp > exp_arg_lim) ? std::exp(exp_arg_lim) : std::exp(rho_exp * sp);
+    sigma_vm_int += std::pow(vm[k] / sigma0, p_norm) * exp_sp * jw[k];
+    JxW_val += exp_sp * jw[k];
+  }
+  std::vector<double> drho(size_t(p->n_nodes));
+  std::vector<double> Xe, dn(ei.nn);
+  Modulus mod{p};
+  Mat dD;
+  for (int64_t i = 0; i < n_dv; ++i) {
+    std::fill(drho.begin(), drho.end(), 0.);
+    for (int64_t k = dv_ptr[i]; k < dv_ptr[i + 1]; ++k) drho[dv_node[k]] += dv_weight[k];
+    double total = 0.;
+    for (int64_t e = 0; e < p->n_elem; ++e) {
+      const int32_t* en = &p->conn[e * ei.nn];
+      bool dep = false;
+      for (int a = 0; a < ei.nn; ++a) { dn[a] = drho[en[a]]; dep = dep || dn[a] != 0.; }
+      if (!dep || (p->diag_elem && p->diag_elem[e])) continue;
+      gather_coords(p, e, ei.nn, Xe);
+      FE fe;
+      fe_init(p->elem_type, Xe.data(), fe);
+      double num_sens = 0., denom_sens = 0.;
+      for (int qp = 0; qp < fe.nq; ++qp) {
+        const size_t o = size_t(e) * ei.nq + qp;
+        stiffness_3d_derivative(mod.E(fe, en, qp), p->nu, mod.dE(fe, en, qp, dn.data()), 0., dD);
+        const Vec eps(en_.begin() + o * 6, en_.begin() + o * 6 + 6);
+        const Vec ds = matvec(dD, eps);  // dstress/dp
+        const double* sg = &st[o * 6];
+        const double pp = 0.5 * (std::pow(sg[0] - sg[1], 2) + std::pow(sg[1] - sg[2], 2) + std::pow(sg[2] - sg[0], 2)) +
+                          3.0 * (std::pow(sg[3], 2) + std::pow(sg[4], 2) + std::pow(sg[5], 2));
+        double de_val = 0.;
+        if (std::fabs(pp) > 0.)
+          de_val = (((ds[0] - ds[1]) * (sg[0] - sg[1]) + (ds[1] - ds[2]) * (sg[1] - sg[2]) + (ds[2] - ds[0]) * (sg[2] - sg[0])) +
+                    6.0 * (ds[3] * sg[3] + ds[4] * sg[4] + ds[5] * sg[5])) * 0.5 * std::pow(pp, -0.5);
+        const double e_val = vm[o], JxW = jw[o];
+        const double sp_stress = std::pow(e_val / sigma0, p_norm), sp1_stress = std::pow(e_val / sigma0, p_norm - 1.);
+        const double sp_weight = std::pow((e_val - sigma0) / sigma0, p_norm_weight);
+        const double sp1_weight = std::pow((e_val - sigma0) / sigma0, p_norm_weight - 1.);
+        if (rho_exp * sp_weight > exp_arg_lim) {
+          num_sens += p_norm * sp1_stress * std::exp(exp_arg_lim) * de_val / sigma0 * JxW;
+        } else {
+          const double exp_sp = std::exp(rho_exp * sp_weight);
+          denom_sens += exp_sp * rho_exp * p_norm_weight * sp1_weight * de_val / sigma0 * JxW;
+          num_sens += (de_val / sigma0 * JxW * exp_sp * (p_norm * sp1_stress + sp_stress * rho_exp * p_norm_weight * sp1_weight));
+        }
+      }
+      total += sigma0 / p_norm * std::pow(sigma_vm_int / JxW_val, 1. / p_norm - 1.) *
+               (num_sens / JxW_val - sigma_vm_int / std::pow(JxW_val, 2.) * denom_sens);
+    }
+    sens[i] = total;
+  }
+  return 0;
+}
+
 void oracle_plate_section_matrices(double E, double nu, double h, double off, double kappa, int plane_strain,
                                    double* A9, double* B9, double* D9, double* S4) {
   Mat C;

@@ -95,6 +95,12 @@ int oracle_stress(const OracleProblem* p, const double* X, double* stress, doubl
 double oracle_stress_functional(const OracleProblem* p, const double* X, double p_norm, double rho_exp,
                                 double sigma0, double* dq_dX /* [n_dof] or NULL */);
 
+/* partial derivative (fixed state) of that aggregate w.r.t. nodal-density design variables (CSC columns as above):
+ * StressStrainOutputBase::functional_sensitivity_for_all_elems with dstress/dp = dD/dp * strain */
+int oracle_stress_functional_density_sensitivity(const OracleProblem* p, const double* X, double p_norm, double rho_exp,
+                                                 double sigma0, int64_t n_dv, const int64_t* dv_ptr, const int32_t* dv_node,
+                                                 const double* dv_weight, double* sens);
+
 /* material matrices for the golden-vector tests */
 void oracle_stiffness_3d(double E, double nu, double* D36);
 void oracle_stiffness_3d_derivative(double E, double nu, double dE, double dnu, double* D36);

@@ -41,6 +41,7 @@ def lib():
         L.oracle_compliance_derivative.argtypes = [P, vp, vp]
         L.oracle_stress.argtypes = [P, vp, vp, vp, vp, vp]
         L.oracle_stress_functional.argtypes = [P, vp, dbl, dbl, dbl, vp]; L.oracle_stress_functional.restype = dbl
+        L.oracle_stress_functional_density_sensitivity.argtypes = [P, vp, dbl, dbl, dbl, i64, vp, vp, vp, vp]
         L.oracle_stiffness_3d.argtypes = [dbl, dbl, vp]
         L.oracle_stiffness_3d_derivative.argtypes = [dbl, dbl, dbl, dbl, vp]
         L.oracle_thermal_expansion_A_3d.argtypes = [dbl, dbl, dbl, vp]
@@ -155,6 +156,15 @@ class Problem:
         dq = np.empty(self.n_dof) if want_derivative else None
         q = lib().oracle_stress_functional(C.byref(self.s), _p(X), p_norm, rho_exp, sigma0, _p(dq))
         return (q, dq) if want_derivative else q
+
+    def stress_functional_density_sensitivity(self, X, p_norm, rho_exp, sigma0, dv_ptr, dv_node, dv_weight):
+        dv_ptr = np.ascontiguousarray(dv_ptr, np.int64); dv_node = np.ascontiguousarray(dv_node, np.int32)
+        dv_weight = np.ascontiguousarray(dv_weight, np.float64)
+        sens = np.empty(len(dv_ptr) - 1)
+        rc = lib().oracle_stress_functional_density_sensitivity(C.byref(self.s), _p(X), p_norm, rho_exp, sigma0,
+                                                                len(dv_ptr) - 1, _p(dv_ptr), _p(dv_node), _p(dv_weight), _p(sens))
+        assert rc == 0, rc
+        return sens
 
     def time_residual_and_jacobian(self, X, threads, want_R=True, want_J=True):
         row_ptr, col = self.pattern()

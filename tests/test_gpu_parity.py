@@ -473,3 +473,26 @@ def test_density_sensitivities_alone_hex8_hex27_and_old_sweep(built, monkeypatch
     _close(G, g_ref, 1e-11)
     Ro, Jo = p27.residual_and_jacobian(X)
     _close(R, Ro); _close(J, Jo)
+
+
+def test_stress_aggregate_density_derivative_hex8_hex27(built):
+    # dq/dp of the von Mises aggregate for density DVs at fixed state (the partial-sensitivity term of the adjoint method)
+    rng = np.random.default_rng(9)
+    for prob in (O.cantilever(7, 5, 4, jitter=0.2, simp=True),
+                 _hex27_problem(3, 2, 2, jitter=0.1, rho=0.2 + 0.6 * rng.uniform(size=7 * 5 * 5), rho_min=1e-8, penalty=4.0)):
+        X = O.state(prob.n_dof, 1)
+        n = prob.n_nodes
+        ctx = prob.make_context(0)
+        st, en, vm, jw = prob.stress(X)
+        sigma0 = float(np.median(vm))
+        q, sums = ctx.stress_functional(X, 6.0, 1.5, sigma0)
+        Gq = np.full(n, np.nan)
+        ctx.stress_functional_density_derivative(X, 6.0, 1.5, sigma0, sums, Gq)
+        n_dv = 25
+        cnt = rng.integers(1, 6, n_dv)
+        dv_ptr = np.concatenate([[0], np.cumsum(cnt)])
+        dv_node = rng.integers(0, n, dv_ptr[-1]).astype(np.int32)
+        dv_w = rng.uniform(0.1, 1.0, dv_ptr[-1])
+        sens = ctx.apply_dv_map_transpose(Gq, dv_ptr, dv_node, dv_w)
+        ref = prob.stress_functional_density_sensitivity(X, 6.0, 1.5, sigma0, dv_ptr, dv_node, dv_w)
+        _close(sens, ref, 1e-11)
