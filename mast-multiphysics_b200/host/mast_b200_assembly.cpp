@@ -352,6 +352,13 @@ mastb200_context* AssemblyBase::_device_problem(const libMesh::SparseMatrix<Real
     } else {
       m.E0 = constant_of(mat, "E", true);
     }
+    if (mesh.elem_type == libMesh::QUAD4) {  // StructuralElement2D: solid 2D section (solid_2d_section_element_property_card.cpp)
+      m.thickness = constant_of(card, "h", true);
+      m.offset = constant_of(card, "off", false, 0.);
+      m.kappa = constant_of(card, "kappa", false, 5. / 6.);
+      const Solid2DSectionElementPropertyCard* c2 = dynamic_cast<const Solid2DSectionElementPropertyCard*>(&card);
+      m.plane_strain = (c2 && !c2->plane_stress()) ? 1 : 0;
+    }
   } else {
     if (const LinearTemperatureFieldFunction* k = mat.get_if<LinearTemperatureFieldFunction>("k_th")) {
       m.k0 = k->k0; m.k_beta = k->beta; m.k_of_T = 1;

@@ -143,7 +143,13 @@ class ElementPropertyCardBase : public FunctionSetBase {
   StrainType _strain = LINEAR_STRAIN;
 };
 class IsotropicElementPropertyCard3D : public ElementPropertyCardBase {};
-class Solid2DSectionElementPropertyCard : public ElementPropertyCardBase {};  // expects "h"
+class Solid2DSectionElementPropertyCard : public ElementPropertyCardBase {  // expects "h" [, "off", "kappa"]
+ public:
+  void set_plane_stress(bool val) { _if_plane_stress = val; }   // src/property_cards/element_property_card_2D.h:73-82
+  bool plane_stress() const { return _if_plane_stress; }
+ private:
+  bool _if_plane_stress = true;
+};
 
 // ---- systems ------------------------------------------------------------------------------------------------------
 class NonlinearSystem : public libMesh::NonlinearImplicitSystem {  // src/base/nonlinear_system.h

@@ -27,12 +27,12 @@ static void write_bin(const std::string& path, const T* p, size_t n) {
 }
 
 int main(int argc, char** argv) {
-  if (argc < 3) { std::fprintf(stderr, "usage: assembly_driver <c1|simp|heat|hex27> <dir>\n"); return 2; }
+  if (argc < 3) { std::fprintf(stderr, "usage: assembly_driver <c1|simp|heat|hex27|plate> <dir>\n"); return 2; }
   const std::string which = argv[1], dir = argv[2];
   try {
     libMesh::ReplicatedMesh mesh;
-    const bool heat = which == "heat";
-    if (heat) libMesh::MeshTools::Generation::build_square(mesh, 24, 16, 0., 1., 0., 1., libMesh::QUAD4);
+    const bool heat = which == "heat", plate = which == "plate";
+    if (heat || plate) libMesh::MeshTools::Generation::build_square(mesh, 24, 16, 0., 1., 0., 1., libMesh::QUAD4);
     else if (which == "hex27") libMesh::MeshTools::Generation::build_cube(mesh, 4, 3, 3, 0., 0.3, 0., 0.15, 0., 0.15, libMesh::HEX27);
     else libMesh::MeshTools::Generation::build_cube(mesh, 20, 10, 10, 0., 0.3, 0., 0.15, 0., 0.15, libMesh::HEX8);
 
@@ -46,8 +46,8 @@ int main(int argc, char** argv) {
 
     // clamp the face x = 0 (boundary id 4 of build_cube, 3 of build_square)
     MAST::DirichletBoundaryCondition dirichlet_bc;
-    dirichlet_bc.init(heat ? 3 : 4, sys_init->vars());
-    discipline.add_dirichlet_bc(heat ? 3 : 4, dirichlet_bc);
+    dirichlet_bc.init((heat || plate) ? 3 : 4, sys_init->vars());
+    discipline.add_dirichlet_bc((heat || plate) ? 3 : 4, dirichlet_bc);
     equation_systems.init();
     discipline.init_system_dirichlet_bc(system);
 
@@ -55,6 +55,8 @@ int main(int argc, char** argv) {
     MAST::Parameter T0("T0", 300.), Tc("T", 350.);
     MAST::ConstantFieldFunction E_f("E", E), nu_f("nu", nu), alpha_f("alpha_expansion", alpha), press_f("pressure", press);
     MAST::ConstantFieldFunction h_f("h", h), T0_f("ref_temperature", T0), T_f("temperature", Tc);
+    MAST::Parameter off("off", 0.03), kappa("kappa", 5. / 6.);
+    MAST::ConstantFieldFunction off_f("off", off), kappa_f("kappa", kappa);
     MAST::LinearTemperatureFieldFunction k_f("k_th", 237., 1.0e-3);
     std::unique_ptr<MAST::NodalFieldFunction> rho_f;
     std::unique_ptr<MAST::SIMPModulusFieldFunction> simp_f;
@@ -66,6 +68,12 @@ int main(int argc, char** argv) {
     if (heat) {
       material.add(k_f);
       section2d.add(h_f);
+      section2d.set_material(material);
+      discipline.set_property_for_subdomain(0, section2d);
+    } else if (plate) {  // Mindlin plate: solid 2D section (h, off, kappa) of an isotropic material, plane stress
+      material.add(E_f);
+      material.add(nu_f);
+      section2d.add(h_f); section2d.add(off_f); section2d.add(kappa_f);
       section2d.set_material(material);
       discipline.set_property_for_subdomain(0, section2d);
     } else {

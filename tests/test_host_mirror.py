@@ -106,3 +106,16 @@ def test_mirror_hex27_thermoelastic(built, tmp_path):
     r = _run("hex27", tmp_path)
     assert r.returncode == 0, r.stderr
     _compare_common(prob, tmp_path, X)
+
+
+@pytest.mark.gpu
+def test_mirror_quad4_mindlin_plate(built, tmp_path):
+    # StructuralNonlinearAssemblyElemOperations on a QUAD4 mesh with a solid 2D section: StructuralElement2D on the device
+    xyz, conn = mesh.build_square(24, 16)
+    con = mesh.dirichlet_flags(len(xyz), 6, np.flatnonzero(np.isclose(xyz[:, 0], 0.0)))
+    prob = O.Problem(O.QUAD4, xyz, conn, 6, constrained=con, E0=72e9, nu=0.33, thickness=0.06, offset=0.03, kappa=5.0 / 6.0)
+    X = O.state(prob.n_dof, 1)
+    X.tofile(tmp_path / "X.bin")
+    r = _run("plate", tmp_path)
+    assert r.returncode == 0, r.stderr
+    _compare_common(prob, tmp_path, X)
