@@ -525,9 +525,9 @@ int ensure_struct_plan(mastb200_context* ctx) {
     if (oz0 < 0) return MASTB200_OK;
     if (oz1 < 0) oz1 = nz + 1;
   }
-  // owned nodes of a direction in chunks of at most 7, as even as possible
-  auto chunks = [](int64_t n_nodes_dir, std::vector<std::pair<int, int>>& out) {
-    const int64_t nt = (n_nodes_dir + 6) / 7, base = n_nodes_dir / nt, rem = n_nodes_dir % nt;
+  // owned nodes of a direction in chunks of at most (tile elements - 1), as even as possible
+  auto chunks = [](int64_t n_nodes_dir, int64_t mx, std::vector<std::pair<int, int>>& out) {
+    const int64_t nt = (n_nodes_dir + mx - 1) / mx, base = n_nodes_dir / nt, rem = n_nodes_dir % nt;
     int64_t o = 0;
     for (int64_t t = 0; t < nt; ++t) {
       const int64_t len = base + (t < rem ? 1 : 0);
@@ -536,8 +536,8 @@ int ensure_struct_plan(mastb200_context* ctx) {
     }
   };
   std::vector<std::pair<int, int>> cx, cy;
-  chunks(nx + 1, cx);
-  chunks(ny + 1, cy);
+  chunks(nx + 1, 7, cx);                  // 8 elements (9 node columns) per tile row
+  chunks(ny + 1, kStructTileY - 1, cy);   // kStructTileY elements per tile column
   const int64_t n_tiles = (int64_t)cx.size() * cy.size(), planes = oz1 - oz0;
   int64_t nseg = (20 * (int64_t)ctx->sm_count + n_tiles - 1) / n_tiles;
   nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, std::max<int64_t>(1, planes / 24)));
@@ -567,8 +567,8 @@ int ensure_struct_plan(mastb200_context* ctx) {
   std::vector<StructUnit> sorted(units.size());
   for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
   std::vector<int32_t> arr_off(124, 0);
-  for (int a = 0; a < 42; ++a) arr_off[a] = kStructPosIn[a] * 81;
-  for (int a = 0; a < 81; ++a) arr_off[42 + a] = kStructPosCr[a] * 81;
+  for (int a = 0; a < 42; ++a) arr_off[a] = kStructPosIn[a] * kStructSlots;
+  for (int a = 0; a < 81; ++a) arr_off[42 + a] = kStructPosCr[a] * kStructSlots;
   CU(S.units.upload(sorted, ctx->stream));
   CU(S.arr_off.upload(arr_off, ctx->stream));
   CU(S.nbr_ptr.upload(ctx->pat.nbr_ptr, ctx->stream));

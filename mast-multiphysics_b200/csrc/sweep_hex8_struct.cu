@@ -37,10 +37,13 @@
 namespace mastb200 {
 namespace {
 
-constexpr int SW = 16;                 // warps per CTA
+constexpr int SW = kStructWarps;       // warps per CTA: 4 x (SW / 4) blocks of 2x2 elements
 constexpr int ST = SW * 32;
 constexpr int TCX = 9;                 // node columns per tile row (8 elements + 1)
-constexpr int NS = TCX * TCX;          // node-column slots
+constexpr int TCY = kStructTileY + 1;  // node columns per tile column
+constexpr int NS = TCX * TCY;          // node-column slots
+constexpr int NSB = (NS + 3) & ~3;     // padded byte-array row
+static_assert(NS == kStructSlots, "layout header out of date");
 constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
 constexpr double GP = 0.57735026918962576451;
 
@@ -51,8 +54,8 @@ constexpr int O_XYZ = O_ARENA + ARENA_BYTES;            // [3 planes][3][NS]
 constexpr int O_U = O_XYZ + 3 * 3 * NS * 8;             // [4 planes][3][NS]
 constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;  // [SW][4 el][8 qp][QS]
 constexpr int O_CNT = O_STAGE + SW * 4 * 8 * QS * 8;    // [NS] int32 (+pad)
-constexpr int O_CM = O_CNT + 84 * 4;                    // [4 planes][84] uint8
-constexpr int O_TAB = O_CM + 4 * 84;                    // [124] int32: array offsets within an IN / CR region
+constexpr int O_CM = O_CNT + NSB * 4;                   // [4 planes][NSB] uint8
+constexpr int O_TAB = O_CM + 4 * NSB;                   // [124] int32: array offsets within an IN / CR region
 constexpr int O_RHO = O_TAB + 124 * 4;                  // [3 planes][NS] nodal density (SIMP variant)
 constexpr int O_NODE = O_RHO + 3 * NS * 8;              // [64] int2: owned nodes of the unit (in-plane id, slot | boundary flags)
 constexpr int O_MISC = O_NODE + 64 * 8;
@@ -271,7 +274,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
   const int xcnt = 3 - x0 - (ax == p.nx), ycnt = 3 - y0 - (ay == p.ny), zcnt = 3 - z0 - (az == p.nz);
   const int nnb = xcnt * ycnt * zcnt;
   const int64_t nb0 = valid ? p.nbr_ptr[gid - (int64_t)p.oz0 * npx * npy] : 0;
-  const unsigned cmn = p.cmask ? sm.cm[(s & 3) * 84 + slotA] : 0u;
+  const unsigned cmn = p.cmask ? sm.cm[(s & 3) * NSB + slotA] : 0u;
   const int par = s & 1;
   const int inS = par ? p.in1_off : 0;                       // IN region of node plane s
   const int crS = par ? p.cr1_off : p.cr0_off;               // cross s -> s+1
@@ -320,7 +323,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
         r2 += K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
       }
       if (p.J) {
-        const unsigned cmm = p.cmask ? sm.cm[((s + dk) & 3) * 84 + slotB] : 0u;
+        const unsigned cmm = p.cmask ? sm.cm[((s + dk) & 3) * NSB + slotB] : 0u;
         if (cmn | cmm) {  // libMesh constrain_element_matrix_and_vector: row/column zeroed, diagonal 1 per adjacent element
           const double nadj = double((2 - x0 - (ax == p.nx)) * (2 - y0 - (ay == p.ny)) * (2 - z0 - (az == p.nz)));
 #pragma unroll
@@ -454,8 +457,8 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
     load_plane(s_begin);
     if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
     if (cm_on) {
-      sm.cm[(s_begin & 3) * 84 + cm_dst] = p.cmask[(int64_t)s_begin * plane_nodes + cm_src];
-      if (s_begin + 1 <= p.nz) sm.cm[((s_begin + 1) & 3) * 84 + cm_dst] = p.cmask[(int64_t)(s_begin + 1) * plane_nodes + cm_src];
+      sm.cm[(s_begin & 3) * NSB + cm_dst] = p.cmask[(int64_t)s_begin * plane_nodes + cm_src];
+      if (s_begin + 1 <= p.nz) sm.cm[((s_begin + 1) & 3) * NSB + cm_dst] = p.cmask[(int64_t)(s_begin + 1) * plane_nodes + cm_src];
     }
     cp_async_wait_all();
     __syncthreads();
@@ -492,7 +495,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
       __syncthreads();
       const bool do_flush = s >= u.z0;
       if (do_flush) flush_plane(p, sm, u, s, warp, lane);
-      if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * 84 + cm_dst] = (uint8_t)cmv;
+      if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
       cp_async_wait_all();
       __syncthreads();
       // the accumulators of node plane s (-> plane s+2) and of the cross pairs s-1 -> s (-> s+1 -> s+2) start from zero

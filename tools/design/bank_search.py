@@ -71,5 +71,6 @@ def run(CX=9, NSP=81, iters=400000, seed=0):
     return best, len(G)
 if __name__ == "__main__":
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 0
-    best, ideal = run(seed=seed)
+    nsp = int(sys.argv[2]) if len(sys.argv) > 2 else 81   # slots per array (81: 9x9 tile, 63: 9x7 tile)
+    best, ideal = run(seed=seed, NSP=nsp)
     print(json.dumps({"cost": best[0], "ideal": ideal, "pin": best[1], "pcr": best[2], "base": best[3]}))
