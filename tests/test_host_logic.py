@@ -166,6 +166,17 @@ def test_no_cpu_fallback(built):
     assert ei.value.code == 2 and "no CPU fallback" in str(ei.value)
     with pytest.raises(mast_b200.MastB200Error):
         ctx.compliance(X)
+    # every compute entry point added later refuses the same way (planning-only context = no device)
+    for call in (lambda: ctx.sensitivity_sweep(X, X, np.zeros(p.n_nodes)),
+                 lambda: ctx.stress(X, von_mises=np.zeros(p.n_elem * 8)),
+                 lambda: ctx.stress_functional(X, 2.0, 0.0, 1.0),
+                 lambda: ctx.stress_functional_derivative(X, 2.0, 0.0, 1.0, np.ones(2), np.zeros(p.n_dof)),
+                 lambda: ctx.stress_functional_density_derivative(X, 2.0, 0.0, 1.0, np.ones(2), np.zeros(p.n_nodes)),
+                 lambda: ctx.compliance_derivative(X, np.zeros(p.n_dof)),
+                 lambda: ctx.res_l2_norm()):
+        with pytest.raises(mast_b200.MastB200Error) as ei:
+            call()
+        assert ei.value.code == 2
     import torch
     if not torch.cuda.is_available():
         with pytest.raises(mast_b200.MastB200Error) as ei:
