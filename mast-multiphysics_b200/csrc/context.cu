@@ -58,6 +58,8 @@ bool is_device_ptr(const void* ptr) {
 }
 
 const int H8_SIDE[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
+const int H27_SIDE[6][9] = {{0, 3, 2, 1, 11, 10, 9, 8, 20},  {0, 1, 5, 4, 8, 13, 16, 12, 21}, {1, 2, 6, 5, 9, 14, 17, 13, 22},
+                            {2, 3, 7, 6, 10, 15, 18, 14, 23}, {3, 0, 4, 7, 11, 12, 19, 15, 24}, {4, 5, 6, 7, 16, 17, 18, 19, 25}};
 
 std::string g_create_error;
 
@@ -264,6 +266,7 @@ void fill_params(mastb200_context* ctx, int aux, SweepParams& p) {
 FaceLoadPlan face_plan(const mastb200_context* ctx) {
   FaceLoadPlan fp;
   fp.n_loaded_nodes = (int32_t)ctx->fl_node.size();
+  fp.nfn = ctx->elem_type == MASTB200_HEX27 ? 9 : 4;
   fp.node = ctx->d_fl_node.p; fp.ptr = ctx->d_fl_ptr.p; fp.face_nodes = ctx->d_fl_face_nodes.p;
   fp.face_k = ctx->d_fl_k.p; fp.pressure = ctx->d_fl_p.p;
   return fp;
@@ -471,6 +474,11 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     }
   }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (!heat && dR && !ctx->fl_node.empty()) {  // side_external_residual: SURFACE_PRESSURE on HEX27 faces
+    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, ctx->has_constraints ? ctx->d_cmask.p : nullptr, ctx->nv, dR,
+                         nullptr, nullptr, nullptr, ctx->stream));
+    ctx->launches++;
+  }
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;
@@ -924,7 +932,9 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
   if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
   ctx->fl_node.clear(); ctx->fl_ptr.clear(); ctx->fl_face_nodes.clear(); ctx->fl_k.clear(); ctx->fl_p.clear();
   if (n == 0) return MASTB200_OK;
-  if (ctx->elem_type != MASTB200_HEX8) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "side pressure: HEX8 only for now");
+  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "side pressure: 3D solids (HEX8, HEX27) only");
+  const int nfn = ctx->elem_type == MASTB200_HEX8 ? 4 : 9, nne = ctx->nn;
   if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
   CU(cudaSetDevice(ctx->device));
   // entries ordered by (element, side): the order in which the reference's element loop meets the loads
@@ -936,15 +946,17 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
     return elem[a] != elem[b] ? elem[a] < elem[b] : side[a] < side[b];
   });
-  struct Ent { int32_t node; int64_t seq; int32_t fn[4]; uint8_t k; double p; };
+  struct Ent { int32_t node; int64_t seq; int32_t fn[9]; uint8_t k; double p; };
   std::vector<Ent> ents;
-  ents.reserve(n * 4);
+  ents.reserve(n * nfn);
   for (int64_t s = 0; s < n; ++s) {
     const int64_t i = order[s];
     Ent e;
-    for (int k = 0; k < 4; ++k) e.fn[k] = ctx->conn[(int64_t)elem[i] * 8 + H8_SIDE[side[i]][k]];
+    for (int k = 0; k < 9; ++k) e.fn[k] = 0;
+    for (int k = 0; k < nfn; ++k)
+      e.fn[k] = ctx->conn[(int64_t)elem[i] * nne + (nfn == 4 ? H8_SIDE[side[i]][k] : H27_SIDE[side[i]][k])];
     e.p = pressure[i];
-    for (int k = 0; k < 4; ++k) { e.node = e.fn[k]; e.k = (uint8_t)k; e.seq = s; ents.push_back(e); }
+    for (int k = 0; k < nfn; ++k) { e.node = e.fn[k]; e.k = (uint8_t)k; e.seq = s; ents.push_back(e); }
   }
   std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.node < b.node; });
   for (size_t i = 0; i < ents.size(); ++i) {
@@ -952,7 +964,7 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
       ctx->fl_node.push_back(ents[i].node);
       ctx->fl_ptr.push_back((int32_t)i);
     }
-    for (int k = 0; k < 4; ++k) ctx->fl_face_nodes.push_back(ents[i].fn[k]);
+    for (int k = 0; k < nfn; ++k) ctx->fl_face_nodes.push_back(ents[i].fn[k]);
     ctx->fl_k.push_back(ents[i].k);
     ctx->fl_p.push_back(ents[i].p);
   }

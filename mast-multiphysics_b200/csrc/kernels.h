@@ -179,7 +179,8 @@ struct FaceLoadPlan {
   int32_t n_loaded_nodes = 0;
   const int32_t* node = nullptr;      // [n_loaded_nodes]
   const int32_t* ptr = nullptr;       // [n_loaded_nodes+1]
-  const int32_t* face_nodes = nullptr;  // [n_entries][4] nodes of the loaded face (libMesh side ordering)
+  int32_t nfn = 4;                    // nodes per face: 4 (HEX8 face, 2x2 Gauss) or 9 (HEX27 face, 3x3 Gauss)
+  const int32_t* face_nodes = nullptr;  // [n_entries][nfn] nodes of the loaded face (libMesh side ordering)
   const uint8_t* face_k = nullptr;    // [n_entries] which face node this entry's node is
   const double* pressure = nullptr;   // [n_entries]
 };

@@ -43,6 +43,35 @@ __device__ void face_node_force(const double* __restrict__ xyz, const int32_t* f
     }
 }
 
+// the same for a bi-quadratic (QUAD9) face of a HEX27 with the 3x3 Gauss rule; libMesh QUAD9 node order: corners,
+// edge midpoints (bottom, right, top, left), centre
+__device__ void face_node_force9(const double* __restrict__ xyz, const int32_t* fn, int k, double press, double F[3]) {
+  const double gp[3] = {-0.77459666924148337704, 0., 0.77459666924148337704};
+  const double gw[3] = {5. / 9., 8. / 9., 5. / 9.};
+  const int FI[9] = {0, 1, 1, 0, 2, 1, 2, 0, 2}, FJ[9] = {0, 0, 1, 1, 0, 2, 1, 2, 2};  // 0: -1, 1: +1, 2: mid
+  auto l = [](int c, double x) { return c == 0 ? 0.5 * x * (x - 1.) : c == 1 ? 0.5 * x * (x + 1.) : (1. - x * x); };
+  auto dl = [](int c, double x) { return c == 0 ? x - 0.5 : c == 1 ? x + 0.5 : -2. * x; };
+  double X[9][3];
+  for (int m = 0; m < 9; ++m)
+    for (int c = 0; c < 3; ++c) X[m][c] = xyz[(int64_t)fn[m] * 3 + c];
+  F[0] = F[1] = F[2] = 0.;
+  for (int jq = 0; jq < 3; ++jq)
+    for (int iq = 0; iq < 3; ++iq) {
+      const double xi = gp[iq], eta = gp[jq];
+      double t1[3] = {0., 0., 0.}, t2[3] = {0., 0., 0.};
+      double Nk = 0.;
+      for (int m = 0; m < 9; ++m) {
+        const double li = l(FI[m], xi), lj = l(FJ[m], eta);
+        const double dxi = dl(FI[m], xi) * lj, deta = li * dl(FJ[m], eta);
+        if (m == k) Nk = li * lj;
+        for (int c = 0; c < 3; ++c) { t1[c] += dxi * X[m][c]; t2[c] += deta * X[m][c]; }
+      }
+      const double n0 = t1[1] * t2[2] - t1[2] * t2[1], n1 = t1[2] * t2[0] - t1[0] * t2[2], n2 = t1[0] * t2[1] - t1[1] * t2[0];
+      const double w = gw[iq] * gw[jq] * Nk * press;
+      F[0] += w * n0; F[1] += w * n1; F[2] += w * n2;
+    }
+}
+
 __global__ void __launch_bounds__(LB) face_load_kernel(FaceLoadPlan fp, const double* __restrict__ xyz,
                                                        const double* __restrict__ X, const uint8_t* __restrict__ cmask,
                                                        int nv, double* R, double* dq, double* partial) {
@@ -54,7 +83,8 @@ __global__ void __launch_bounds__(LB) face_load_kernel(FaceLoadPlan fp, const do
     double F[3] = {0., 0., 0.};
     for (int e = fp.ptr[t]; e < fp.ptr[t + 1]; ++e) {
       double f[3];
-      face_node_force(xyz, fp.face_nodes + (int64_t)e * 4, fp.face_k[e], fp.pressure[e], f);
+      if (fp.nfn == 9) face_node_force9(xyz, fp.face_nodes + (int64_t)e * 9, fp.face_k[e], fp.pressure[e], f);
+      else face_node_force(xyz, fp.face_nodes + (int64_t)e * 4, fp.face_k[e], fp.pressure[e], f);
       F[0] += f[0]; F[1] += f[1]; F[2] += f[2];
     }
     const unsigned cm = cmask ? cmask[n] : 0u;

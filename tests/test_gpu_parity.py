@@ -496,3 +496,21 @@ def test_stress_aggregate_density_derivative_hex8_hex27(built):
         sens = ctx.apply_dv_map_transpose(Gq, dv_ptr, dv_node, dv_w)
         ref = prob.stress_functional_density_sensitivity(X, 6.0, 1.5, sigma0, dv_ptr, dv_node, dv_w)
         _close(sens, ref, 1e-11)
+
+
+def test_hex27_surface_pressure_and_compliance(built):
+    # SURFACE_PRESSURE on QUAD9 faces of HEX27 elements (3x3 Gauss), compliance value and derivative
+    nx, ny, nz = 4, 3, 2
+    xyz, conn = mesh.build_cube(nx, ny, nz, 0.3, 0.15, 0.15, 27, jitter=0.1)
+    con = mesh.dirichlet_flags(len(xyz), 3, mesh.boundary_nodes(nx, ny, nz, 4, 27))
+    se, sid = mesh.boundary_sides(nx, ny, nz, 3)
+    se2, sid2 = mesh.boundary_sides(nx, ny, nz, 5)
+    prob = O.Problem(O.HEX27, xyz, conn, 3, constrained=con, side_elem=np.concatenate([se, se2]),
+                     side_id=np.concatenate([sid, sid2]),
+                     side_pressure=np.concatenate([np.full(len(se), 5e7), np.full(len(se2), -2e7)]))
+    X = O.state(prob.n_dof, 1)
+    ctx, R, J = _check_RJ(prob, X)
+    assert np.isclose(ctx.compliance(X), prob.compliance(X), rtol=1e-12)
+    dq = np.full(prob.n_dof, np.nan)
+    ctx.compliance_derivative(X, dq)
+    _close(dq, prob.compliance_derivative(X))
