@@ -87,6 +87,12 @@ int mastb200_set_material(mastb200_context* ctx, const mastb200_material* mat);
 /* SURFACE_PRESSURE side loads on (element, libMesh side) pairs; n = 0 clears. */
 int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
                                const double* pressure);
+/* Heat-conduction side loads on (element, libMesh side) pairs of a QUAD4 mesh (nv = 1): HEAT_FLUX value and
+ * CONVECTION_HEAT_FLUX coefficient / ambient temperature per entry (conv_coeff, T_amb may be NULL); n = 0 clears.
+ *   <- HeatConductionElementBase::surface_flux_residual, ::surface_convection_residual,
+ *      src/heat_conduction/heat_conduction_elem_base.cpp:876-914, 1100-1155 (dispatch :428-483) */
+int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                                 const double* heat_flux, const double* conv_coeff, const double* T_amb);
 /* TEMPERATURE volume load: nodal field [h|d] (or NULL => constant), reference temperature. enable=0 clears. */
 int mastb200_set_temperature(mastb200_context* ctx, int32_t enable, const double* T_nodal, double T_const,
                              double T_ref);

@@ -150,6 +150,10 @@ struct mastb200_context {
   DevBuf<int32_t> d_fl_node, d_fl_ptr, d_fl_face_nodes;
   DevBuf<uint8_t> d_fl_k;
   DevBuf<double> d_fl_p;
+  // heat side loads (CSR over elements)
+  DevBuf<int32_t> d_hs_ptr, d_hs_side;
+  DevBuf<double> d_hs_val;
+  bool have_heat_sides = false;
   // dv map staging
   DevBuf<int64_t> d_dv_ptr;
   DevBuf<int32_t> d_dv_node;
@@ -444,6 +448,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
     p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
     p.k0 = m.k0; p.k_beta = m.k_beta; p.thickness = m.thickness; p.heat_source = m.heat_source; p.k_of_T = m.k_of_T;
+    if (ctx->have_heat_sides) { p.sl_ptr = ctx->d_hs_ptr.p; p.sl_side = ctx->d_hs_side.p; p.sl_val = ctx->d_hs_val.p; }
     CU(launch_quad4_heat(p, ctx->stream));
     ctx->launches++;
   } else {
@@ -888,6 +893,7 @@ int mastb200_set_mesh(mastb200_context* ctx, int32_t elem_type, int64_t n_elem, 
   if (!ctx->planning_only) CU(ctx->d_xyz.upload(ctx->xyz, ctx->stream));
   ctx->have_mesh = true; ctx->have_plan = false;
   ctx->fl_node.clear();
+  ctx->have_heat_sides = false;
   return MASTB200_OK;
 }
 
@@ -975,6 +981,44 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
   CU(ctx->d_fl_k.upload(ctx->fl_k, ctx->stream));
   CU(ctx->d_fl_p.upload(ctx->fl_p, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                                 const double* heat_flux, const double* conv_coeff, const double* T_amb) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+  ctx->have_heat_sides = false;
+  if (n == 0) return MASTB200_OK;
+  if (ctx->elem_type != MASTB200_QUAD4) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "heat side loads: QUAD4 heat conduction only");
+  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
+  if (!elem || !side) return ctx->fail(MASTB200_ERR_ARG, "NULL side load arrays");
+  CU(cudaSetDevice(ctx->device));
+  std::vector<int64_t> order(n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (elem[i] < 0 || elem[i] >= ctx->n_elem || side[i] < 0 || side[i] > 3) return ctx->fail(MASTB200_ERR_ARG, "bad side load %lld", (long long)i);
+    order[i] = i;
+  }
+  // per element in ascending side id: the order in which the reference's element loop meets them
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return elem[a] != elem[b] ? elem[a] < elem[b] : side[a] < side[b];
+  });
+  std::vector<int32_t> ptr(ctx->n_elem + 1, 0), sd(n);
+  std::vector<double> val(n * 3);
+  for (int64_t i = 0; i < n; ++i) ptr[elem[i] + 1]++;
+  for (int64_t e = 0; e < ctx->n_elem; ++e) ptr[e + 1] += ptr[e];
+  for (int64_t k = 0; k < n; ++k) {
+    const int64_t i = order[k];
+    sd[k] = side[i];
+    val[k * 3] = heat_flux ? heat_flux[i] : 0.;
+    val[k * 3 + 1] = conv_coeff ? conv_coeff[i] : 0.;
+    val[k * 3 + 2] = T_amb ? T_amb[i] : 0.;
+  }
+  CU(ctx->d_hs_ptr.upload(ptr, ctx->stream));
+  CU(ctx->d_hs_side.upload(sd, ctx->stream));
+  CU(ctx->d_hs_val.upload(val, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_heat_sides = true;
   return MASTB200_OK;
 }
 

@@ -70,6 +70,10 @@ struct GatherParams {
   double* R = nullptr;
   double k0 = 0., k_beta = 0., thickness = 1., heat_source = 0.;
   int32_t k_of_T = 0;
+  // heat side loads per element (CSR over elements): side, HEAT_FLUX value, CONVECTION_HEAT_FLUX coefficient, T_ambient
+  const int32_t* sl_ptr = nullptr;       // [n_elem+1] or null (no side loads)
+  const int32_t* sl_side = nullptr;
+  const double* sl_val = nullptr;        // [n_entries][3]: flux, h_c, T_amb
 };
 cudaError_t launch_quad4_heat(const GatherParams& p, cudaStream_t stream);
 

@@ -112,6 +112,34 @@ __global__ void __launch_bounds__(TB) quad4_heat_kernel(const GatherParams p) {
       }
       jxw[q] = JxW; Na[q] = N[a];
     }
+    if (p.sl_ptr) {
+      // HeatConductionElementBase::surface_flux_residual / surface_convection_residual
+      // (/root/reference/src/heat_conduction/heat_conduction_elem_base.cpp:876-914, 1100-1155) on the loaded sides of
+      // this element that hold the row node: EDGE2 with the 2-point Gauss rule, f += JxW N_a th (flux + h_c (T - T_amb)),
+      // K_ab += JxW N_a N_b th h_c
+      for (int k = p.sl_ptr[e]; k < p.sl_ptr[e + 1]; ++k) {
+        const int sd = p.sl_side[k], n1 = sd, n2 = (sd + 1) & 3;
+        if (a != n1 && a != n2) continue;
+        const double flux = p.sl_val[k * 3], hc = p.sl_val[k * 3 + 1], Tamb = p.sl_val[k * 3 + 2];
+        const double ex = x[n2] - x[n1], ey = y[n2] - y[n1];
+        const double JxWs = 0.5 * sqrt(ex * ex + ey * ey);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const double xi = q ? GP : -GP;
+          const double N1 = 0.5 * (1. - xi), N2 = 0.5 * (1. + xi);
+          const double Nrow = a == n1 ? N1 : N2;
+          const double temp = N1 * T[n1] + N2 * T[n2];
+          if (p.R) {
+            f += JxWs * Nrow * flux * p.thickness;
+            if (hc != 0.) f += JxWs * Nrow * p.thickness * hc * (temp - Tamb);
+          }
+          if (p.J && hc != 0.) {
+            K[n1] += JxWs * (Nrow * N1) * p.thickness * hc;
+            K[n2] += JxWs * (Nrow * N2) * p.thickness * hc;
+          }
+        }
+      }
+    }
     if (p.R && p.heat_source != 0.) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) f -= jxw[q] * Na[q] * p.heat_source * p.thickness;

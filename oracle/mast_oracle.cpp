@@ -756,6 +756,29 @@ static void plate_internal_residual(const OracleProblem* p, const FE& fe, const 
   }
 }
 
+// HeatConductionElementBase::surface_flux_residual (heat_conduction_elem_base.cpp:876-914) and
+// ::surface_convection_residual (:1100-1155) on side `side` of a QUAD4 (an EDGE2 with the 2-point Gauss rule of
+// MAST::FEBase::init_for_side, fe_base.cpp:137-204): f += JxW N th flux ; f += JxW N th h_c (T - T_amb),
+// jac += JxW N N^T th h_c.  th = section thickness (solid_2d_section_element_property_card: "h").
+static void heat_side_residual(const OracleProblem* p, const double* X, const Vec& sol, int side, double flux, double hc,
+                               double Tamb, bool request_jacobian, Vec& f, Mat& jac) {
+  const int n1 = side, n2 = (side + 1) % 4;
+  const double dx = X[n2 * 3] - X[n1 * 3], dy = X[n2 * 3 + 1] - X[n1 * 3 + 1], dz = X[n2 * 3 + 2] - X[n1 * 3 + 2];
+  const double L = std::sqrt(dx * dx + dy * dy + dz * dz);
+  for (int q = 0; q < 2; ++q) {
+    const double xi = GP2[q], JxW = 0.5 * L * GW2[q];
+    const double N[2] = {0.5 * (1. - xi), 0.5 * (1. + xi)};
+    const int nd[2] = {n1, n2};
+    const double temp = N[0] * sol[n1] + N[1] * sol[n2];
+    for (int a = 0; a < 2; ++a) {
+      f[nd[a]] += JxW * N[a] * flux * p->thickness;
+      if (hc != 0.) f[nd[a]] += JxW * N[a] * p->thickness * hc * (temp - Tamb);
+      if (request_jacobian && hc != 0.)
+        for (int b = 0; b < 2; ++b) jac(nd[a], nd[b]) += JxW * (N[a] * N[b]) * p->thickness * hc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // HeatConductionElementBase::internal_residual (heat_conduction_elem_base.cpp:53-149), QUAD4 with
 // Solid2DSectionProperty::ThermalConductanceMatrix = k*h (solid_2d_section_element_property_card.cpp:940-953)
@@ -826,11 +849,12 @@ struct SideLoadIndex {  // (element -> its loaded sides), GeomElem::external_sid
   std::vector<int64_t> ptr;
   std::vector<int32_t> side;
   std::vector<double> press;
+  std::vector<int64_t> idx;  // original load index (heat side loads carry more than one value)
   void build(const OracleProblem* p) {
     ptr.assign(p->n_elem + 1, 0);
     for (int64_t l = 0; l < p->n_side_loads; ++l) ptr[p->side_elem[l] + 1]++;
     for (int64_t e = 0; e < p->n_elem; ++e) ptr[e + 1] += ptr[e];
-    side.resize(p->n_side_loads); press.resize(p->n_side_loads);
+    side.resize(p->n_side_loads); press.resize(p->n_side_loads); idx.resize(p->n_side_loads);
     std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
     // std::map<unsigned, ...> iteration is by ascending side id; stable within a side
     std::vector<int64_t> order(p->n_side_loads);
@@ -841,7 +865,7 @@ struct SideLoadIndex {  // (element -> its loaded sides), GeomElem::external_sid
     });
     for (int64_t l : order) {
       const int64_t k = pos[p->side_elem[l]]++;
-      side[k] = p->side_id[l]; press[k] = p->side_pressure[l];
+      side[k] = p->side_id[l]; press[k] = p->side_pressure[l]; idx[k] = l;
     }
   }
 };
@@ -871,8 +895,17 @@ static void elem_calculations(const OracleProblem* p, const SideLoadIndex& sl, i
   vec.assign(nd, 0.);
   mat.resize(nd, nd);
   if (p->elem_type == ORACLE_QUAD4) {
-    if (p->nv == 6) plate_internal_residual(p, fe, X.data(), sol, if_jac, vec, mat);  // StructuralElement2D
-    else heat_elem_calculations(p, fe, sol, if_jac, vec, mat);
+    if (p->nv == 6) {
+      plate_internal_residual(p, fe, X.data(), sol, if_jac, vec, mat);  // StructuralElement2D
+    } else {
+      heat_elem_calculations(p, fe, sol, if_jac, vec, mat);
+      // side_external_residual of heat conduction (heat_conduction_elem_base.cpp:428-483): HEAT_FLUX, CONVECTION_HEAT_FLUX
+      for (int64_t k = sl.ptr[e]; k < sl.ptr[e + 1]; ++k) {
+        const int64_t l = sl.idx[k];
+        heat_side_residual(p, X.data(), sol, sl.side[k], sl.press[k], p->side_conv_coeff ? p->side_conv_coeff[l] : 0.,
+                           p->side_T_amb ? p->side_T_amb[l] : 0., if_jac, vec, mat);
+      }
+    }
     return;
   }
   const int32_t* en = &p->conn[e * ei.nn];

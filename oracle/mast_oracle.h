@@ -59,6 +59,10 @@ typedef struct OracleProblem {
    * offset, shear correction factor kappa, plane_strain = 0 (plane stress) | 1 */
   double offset, kappa;
   int32_t plane_strain;
+  /* heat conduction side loads (QUAD4, nv=1) reuse side_elem / side_id; side_pressure holds the HEAT_FLUX value and
+   * these two the CONVECTION_HEAT_FLUX coefficient and ambient temperature per entry (NULL: none) */
+  const double* side_conv_coeff;
+  const double* side_T_amb;
 } OracleProblem;
 
 /* libMesh-style sparsity: every (row,col) pair of dofs that share an element; columns sorted.

@@ -19,6 +19,7 @@ class OracleProblem(C.Structure):
         ("temperature_const", C.c_double), ("ref_temperature", C.c_double), ("k0", C.c_double),
         ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32), ("heat_source", C.c_double),
         ("offset", C.c_double), ("kappa", C.c_double), ("plane_strain", C.c_int32),
+        ("side_conv_coeff", C.c_void_p), ("side_T_amb", C.c_void_p),
     ]
 
 
@@ -63,7 +64,7 @@ class Problem:
     def __init__(self, elem_type, xyz, conn, nv, constrained=None, E0=72e9, nu=0.33, alpha=0.0, rho=None,
                  rho_min=0.0, penalty=1.0, nonlinear_strain=0, side_elem=None, side_id=None, side_pressure=None,
                  thermal=0, temperature=None, temperature_const=0.0, ref_temperature=0.0, k0=0.0, k_beta=0.0,
-                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None, offset=0.0, kappa=5.0 / 6.0, plane_strain=0):
+                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None, offset=0.0, kappa=5.0 / 6.0, plane_strain=0, side_conv_coeff=None, side_T_amb=None):
         self.elem_type = elem_type
         self.xyz = np.ascontiguousarray(xyz, np.float64)
         self.conn = np.ascontiguousarray(conn, np.int32)
@@ -93,6 +94,9 @@ class Problem:
         s.ref_temperature = ref_temperature
         s.k0 = k0; s.k_beta = k_beta; s.thickness = thickness; s.k_of_T = k_of_T; s.heat_source = heat_source
         s.offset = offset; s.kappa = kappa; s.plane_strain = plane_strain
+        self.side_conv_coeff = None if side_conv_coeff is None else np.ascontiguousarray(side_conv_coeff, np.float64)
+        self.side_T_amb = None if side_T_amb is None else np.ascontiguousarray(side_T_amb, np.float64)
+        s.side_conv_coeff = _p(self.side_conv_coeff); s.side_T_amb = _p(self.side_T_amb)
         self.s = s
         self._pattern = None
 
@@ -181,7 +185,11 @@ class Problem:
         ctx.set_material(**self.mat)
         if device >= 0:
             if self.side_elem is not None:
-                ctx.set_side_pressure(self.side_elem, self.side_id, self.side_pressure)
+                if self.elem_type == QUAD4 and self.nv == 1:
+                    ctx.set_heat_side_loads(self.side_elem, self.side_id, self.side_pressure, self.side_conv_coeff,
+                                            self.side_T_amb)
+                else:
+                    ctx.set_side_pressure(self.side_elem, self.side_id, self.side_pressure)
             if self.thermal:
                 ctx.set_temperature(1, self.temperature, self.temperature_const, self.ref_temperature)
             if self.rho is not None:

@@ -514,3 +514,29 @@ def test_hex27_surface_pressure_and_compliance(built):
     dq = np.full(prob.n_dof, np.nan)
     ctx.compliance_derivative(X, dq)
     _close(dq, prob.compliance_derivative(X))
+
+
+def test_quad4_heat_flux_and_convection_side_loads(built):
+    # HEAT_FLUX on the bottom edge (boundary 0 of build_square), CONVECTION_HEAT_FLUX on the right edge (boundary 1)
+    nx, ny = 14, 9
+    xyz, conn = mesh.build_square(nx, ny, 1.4, 0.9)
+    rng = np.random.default_rng(2)
+    inner = (xyz[:, 0] > 0) & (xyz[:, 0] < 1.4) & (xyz[:, 1] > 0) & (xyz[:, 1] < 0.9)
+    xyz[inner, :2] += 0.02 * rng.uniform(-1, 1, (inner.sum(), 2))
+    con = np.isclose(xyz[:, 0], 0.0).astype(np.uint8)
+    bottom = np.arange(nx, dtype=np.int32)                       # elements j = 0, side 0
+    right = (np.arange(ny, dtype=np.int32) * nx + nx - 1)        # elements i = nx-1, side 1
+    se = np.concatenate([bottom, right, right[:3]])              # three elements carry both kinds on the same side
+    sid = np.concatenate([np.zeros(nx, np.int32), np.ones(ny, np.int32), np.ones(3, np.int32)])
+    flux = np.concatenate([np.full(nx, -2.5e3), np.zeros(ny), np.full(3, 4.0e2)])
+    hc = np.concatenate([np.zeros(nx), np.full(ny, 35.0), np.zeros(3)])
+    Tamb = np.concatenate([np.zeros(nx), np.full(ny, 290.0), np.zeros(3)])
+    for k_of_T in (0, 1):
+        prob = O.Problem(O.QUAD4, xyz, conn, 1, constrained=con, k0=237.0, k_beta=1e-3, k_of_T=k_of_T, thickness=0.06,
+                         heat_source=1.0e4, side_elem=se, side_id=sid, side_pressure=flux, side_conv_coeff=hc, side_T_amb=Tamb)
+        T = _temperature(prob.n_dof)
+        ctx, R, J = _check_RJ(prob, T)
+        plain = O.Problem(O.QUAD4, xyz, conn, 1, constrained=con, k0=237.0, k_beta=1e-3, k_of_T=k_of_T, thickness=0.06,
+                          heat_source=1.0e4)
+        R0, J0 = plain.residual_and_jacobian(T)
+        assert np.abs(R - R0).max() > 1e-3 * np.abs(R0).max() and np.abs(J - J0).max() > 0  # the loads are there
