@@ -58,7 +58,8 @@ constexpr int O_CM = O_CNT + NSB * 4;                   // [4 planes][NSB] uint8
 constexpr int O_TAB = O_CM + 4 * NSB;                   // [124] int32: array offsets within an IN / CR region
 constexpr int O_RHO = O_TAB + 124 * 4;                  // [3 planes][NS] nodal density (SIMP variant)
 constexpr int O_NODE = O_RHO + 3 * NS * 8;              // [64] int2: owned nodes of the unit (in-plane id, slot | boundary flags)
-constexpr int O_MISC = O_NODE + 64 * 8;
+constexpr int O_FPK = O_NODE + 64 * 8;                  // [4 passes][8 lanes] packed flush constants
+constexpr int O_MISC = O_FPK + 32 * 4;
 constexpr int SMEM_BYTES = O_MISC + 16;
 static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0, "alignment");
 static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
@@ -98,6 +99,7 @@ struct Sm {
   int32_t* tab;
   double* rho;
   int2* node;
+  int32_t* fpk;
   int* misc;
 };
 
@@ -261,53 +263,72 @@ __device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, uns
   if (checker) st_release_s32(cnt, rank + 1);
 }
 
-// ---- flush of node plane s: eight lanes per owned node ----------------------------------------------------------------
-__device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm, const StructUnit& u, int s, int warp, int lane) {
+// ---- flush of node plane s: eight lanes per owned node, four passes over its <= 27 neighbour directions ---------------
+// Consecutive lanes of a node write consecutive column blocks of its CSR rows (8 x 24 bytes per store instruction).
+// Everything that depends on (lane, pass) only is decoded once per kernel into one packed word per pass:
+//   bits 0-4 neighbour column shift + 10, 5-6 dk + 1, 7-12 boundary flags that remove the neighbour, 13 self,
+//   14 transposed (backward pair, stored at the neighbour), 15 direction exists (d < 27), 16-23 first entry of the
+//   direction's nine array offsets in the table, 24-28 d.
+__device__ __forceinline__ int flush_pack(int t, int l8) {
+  {
+    const int d0 = 8 * t + l8;
+    const int d = d0 < 27 ? d0 : 13;
+    const int dk = d / 9 - 1, dj = (d / 3) % 3 - 1, di = d % 3 - 1;
+    const bool self = d == 13, fwd = d > 13, tr = !(fwd || self);
+    const int sdi = tr ? -di : di, sdj = tr ? -dj : dj;
+    const int a0 = dk == 0 ? in_array(inplane_dir(sdi, sdj), 0) : cr_array(sdi, sdj, 0);
+    const int kill = (di < 0 ? 1 : 0) | (di > 0 ? 2 : 0) | (dj < 0 ? 4 : 0) | (dj > 0 ? 8 : 0) | (dk < 0 ? 16 : 0) | (dk > 0 ? 32 : 0);
+    return (dj * TCX + di + 10) | ((dk + 1) << 5) | (kill << 7) | (self ? 1 << 13 : 0) | (tr ? 1 << 14 : 0) |
+           (d0 < 27 ? 1 << 15 : 0) | (a0 << 16) | (d << 24);
+  }
+}
+
+__device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm, unsigned arena32, int s,
+                                            int n_own, int64_t plane_off, int warp, int lane) {
   const int g = warp * 4 + (lane >> 3), l8 = lane & 7;
-  const bool valid = g < u.nox * u.noy;
-  const int oyi = valid ? g / u.nox : 0, oxi = valid ? g - oyi * u.nox : 0;
-  const int ax = u.o0x + oxi, ay = u.o0y + oyi, az = s;
-  const int slotA = (ay - u.e0y) * TCX + (ax - u.e0x);
-  const int64_t npx = p.nx + 1, npy = p.ny + 1;
-  const int64_t gid = ax + ay * npx + (int64_t)az * npx * npy;
-  const int x0 = ax == 0, y0 = ay == 0, z0 = az == 0;
-  const int xcnt = 3 - x0 - (ax == p.nx), ycnt = 3 - y0 - (ay == p.ny), zcnt = 3 - z0 - (az == p.nz);
-  const int nnb = xcnt * ycnt * zcnt;
-  const int64_t nb0 = valid ? p.nbr_ptr[gid - (int64_t)p.oz0 * npx * npy] : 0;
-  const unsigned cmn = p.cmask ? sm.cm[(s & 3) * NSB + slotA] : 0u;
+  const bool valid = g < n_own;
+  const int2 ni = sm.node[valid ? g : 0];  // in-plane node id, slot | xy boundary flags << 8
+  const int64_t nb0 = valid ? p.nbr_ptr[plane_off + ni.x - (int64_t)p.oz0 * (p.nx + 1) * (p.ny + 1)] : 0;
+  const int slotA = ni.y & 0xff;
+  const int flags = (ni.y >> 8) | (s == 0 ? 16 : 0) | (s == p.nz ? 32 : 0);  // x0, xN, y0, yN, z0, zN
   const int par = s & 1;
-  const int inS = par ? p.in1_off : 0;                       // IN region of node plane s
-  const int crS = par ? p.cr1_off : p.cr0_off;               // cross s -> s+1
-  const int crD = par ? p.cr0_off : p.cr1_off;               // cross s-1 -> s
+  const unsigned cmn = p.cmask ? sm.cm[(s & 3) * NSB + slotA] : 0u;
+  // CSR numbering of the node's neighbours: interior nodes have all 27 (column block = direction)
+  int x0 = 0, y0 = 0, z0 = 0, xcnt = 3, ycnt = 3, rs = 81;
+  double nadj = 8.;
+  if (flags) {
+    x0 = flags & 1; y0 = (flags >> 2) & 1; z0 = (flags >> 4) & 1;
+    xcnt = 3 - x0 - ((flags >> 1) & 1); ycnt = 3 - y0 - ((flags >> 3) & 1);
+    const int zcnt = 3 - z0 - ((flags >> 5) & 1);
+    rs = 3 * xcnt * ycnt * zcnt;
+    nadj = double((xcnt - 1) * (ycnt - 1) * (zcnt - 1));
+  }
+  const unsigned regIn = arena32 + ((par ? p.in1_off : 0) + slotA) * 8;
+  const unsigned regUp = arena32 + ((par ? p.cr1_off : p.cr0_off) + slotA) * 8;
+  const unsigned regDn = arena32 + ((par ? p.cr0_off : p.cr1_off) + slotA) * 8;
+  double* Jrow = p.J + 9 * nb0;
   double r0 = 0., r1 = 0., r2 = 0.;
 #pragma unroll 1
-  for (int c0 = 0; c0 < 32; c0 += 8) {
-    const int d = c0 + l8;
-    const int dk = d / 9 - 1, dj = (d / 3) % 3 - 1, di = d % 3 - 1;
-    const int bx = ax + di, by = ay + dj, bz = az + dk;
-    const bool on = valid && d < 27 && bx >= 0 && bx <= p.nx && by >= 0 && by <= p.ny && bz >= 0 && bz <= p.nz;
+  for (int t = 0; t < 4; ++t) {
+    const int pk = sm.fpk[t * 8 + l8];
+    const bool on = valid && (pk & (1 << 15)) && !(flags & (pk >> 7) & 63);
     if (on) {
-      const int c = ((dk + 1 - z0) * ycnt + (dj + 1 - y0)) * xcnt + (di + 1 - x0);
-      const int slotB = slotA + dj * TCX + di;
-      const bool self = d == 13, fwd = d > 13;
-      // where the pair block lives: at the first node of the pair, oriented first -> second
-      int reg, slot, sdi, sdj;
-      if (fwd || self) { slot = slotA; sdi = di; sdj = dj; reg = dk == 0 ? inS : crS; }
-      else { slot = slotB; sdi = -di; sdj = -dj; reg = dk == 0 ? inS : crD; }
-      const double* blk = sm.arena + reg + slot;
+      const int nsh = (pk & 31) - 10, dk = ((pk >> 5) & 3) - 1;
+      const bool self = (pk >> 13) & 1, tr = (pk >> 14) & 1;
+      const unsigned blk = (dk == 0 ? regIn : (dk > 0 ? regUp : regDn)) + (tr ? nsh * 8 : 0);
+      const int32_t* tb = sm.tab + ((pk >> 16) & 255);
       double S[3][3];
       if (self) {
-        S[0][0] = blk[sm.tab[0]]; S[1][1] = blk[sm.tab[1]]; S[2][2] = blk[sm.tab[2]];
-        S[0][1] = S[1][0] = blk[sm.tab[3]]; S[0][2] = S[2][0] = blk[sm.tab[4]]; S[1][2] = S[2][1] = blk[sm.tab[5]];
+        S[0][0] = lds64(blk + tb[0] * 8); S[1][1] = lds64(blk + tb[1] * 8); S[2][2] = lds64(blk + tb[2] * 8);
+        S[0][1] = S[1][0] = lds64(blk + tb[3] * 8); S[0][2] = S[2][0] = lds64(blk + tb[4] * 8);
+        S[1][2] = S[2][1] = lds64(blk + tb[5] * 8);
       } else {
-        const int a0 = dk == 0 ? in_array(inplane_dir(sdi, sdj), 0) : cr_array(sdi, sdj, 0);
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) S[i][j] = blk[sm.tab[a0 + i * 3 + j]];
+          for (int j = 0; j < 3; ++j) S[i][j] = lds64(blk + tb[i * 3 + j] * 8);
       }
       // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
-      const bool tr = !(fwd || self);
       const double l1 = tr ? p.mu1 : p.lam1, l2 = tr ? p.lam1 : p.mu1;
       const double trm = p.mu1 * (S[0][0] + S[1][1] + S[2][2]);
       double K[3][3];
@@ -315,6 +336,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
       for (int i = 0; i < 3; ++i)
 #pragma unroll
         for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i][j] + l2 * S[j][i] + (i == j ? trm : 0.);
+      const int slotB = slotA + nsh;
       if (p.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
         const double* U = sm.u + ((s + dk) & 3) * 3 * NS + slotB;
         const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
@@ -325,7 +347,6 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
       if (p.J) {
         const unsigned cmm = p.cmask ? sm.cm[((s + dk) & 3) * NSB + slotB] : 0u;
         if (cmn | cmm) {  // libMesh constrain_element_matrix_and_vector: row/column zeroed, diagonal 1 per adjacent element
-          const double nadj = double((2 - x0 - (ax == p.nx)) * (2 - y0 - (ay == p.ny)) * (2 - z0 - (az == p.nz)));
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -336,8 +357,12 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
               K[i][j] = k;
             }
         }
-        double* dst = p.J + 9 * nb0 + 3 * c;
-        const int rs = 3 * nnb;
+        int c = (pk >> 24) & 31;
+        if (flags) {
+          const int d = c, ddk = d / 9, ddj = (d / 3) % 3, ddi = d % 3;
+          c = ((ddk - z0) * ycnt + (ddj - y0)) * xcnt + (ddi - x0);
+        }
+        double* dst = Jrow + 3 * c;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -355,7 +380,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
     y += __shfl_xor_sync(0xffffffffu, y, 1);
     if (valid && (l8 & 1) == 0 && l8 < 6) {
       const int i = l8 >> 1;
-      p.R[gid * 3 + i] = ((cmn >> i) & 1u) ? 0. : y;
+      p.R[(plane_off + ni.x) * 3 + i] = ((cmn >> i) & 1u) ? 0. : y;
     }
   }
 }
@@ -373,9 +398,11 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
   sm.tab = reinterpret_cast<int32_t*>(smem_raw + O_TAB);
   sm.rho = reinterpret_cast<double*>(smem_raw + O_RHO);
   sm.node = reinterpret_cast<int2*>(smem_raw + O_NODE);
+  sm.fpk = reinterpret_cast<int32_t*>(smem_raw + O_FPK);
   sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 123) sm.tab[tid] = p.arr_off[tid];
+  if (tid >= 128 && tid < 160) sm.fpk[tid - 128] = flush_pack((tid - 128) >> 3, (tid - 128) & 7);
   __syncthreads();
   LaneK lk;
   make_lane(p, sm.tab, lane, lk);
@@ -494,7 +521,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
       }
       __syncthreads();
       const bool do_flush = s >= u.z0;
-      if (do_flush) flush_plane(p, sm, u, s, warp, lane);
+      if (do_flush) flush_plane(p, sm, arena32, s, u.nox * u.noy, (int64_t)s * plane_nodes, warp, lane);
       if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
       cp_async_wait_all();
       __syncthreads();
