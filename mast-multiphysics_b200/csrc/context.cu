@@ -746,7 +746,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   int aux = (G || ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
   // build_cube-numbered meshes: the implicit-connectivity kernel serves the 3-dof R/J sweep (constant or SIMP modulus);
   // sensitivities requested together with R/J then come from the element-parallel kernels right after it
-  const bool struct_ok_cfg = ctx->nv == 3 && !ctx->thermal && (R || J);
+  const bool struct_ok_cfg = (ctx->nv == 3 || ctx->nv == 6) && !ctx->thermal && (R || J);
   if (struct_ok_cfg && (rc = ensure_struct_plan(ctx))) return rc;
   const bool use_struct = struct_ok_cfg && ctx->splan.ok;
   if (use_struct) aux = 0;
@@ -783,7 +783,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     const mastb200_context::StructPlan& S = ctx->splan;
     StructParams sp;
     sp.units = S.units.p; sp.n_units = S.n_units; sp.counter = ctx->d_tile_counter.p;
-    sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0;
+    sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0; sp.nv = ctx->nv;
     sp.nbr_ptr = S.nbr_ptr.p; sp.arr_off = S.arr_off.p;
     sp.in1_off = kStructIn1Off; sp.cr0_off = kStructCr0Off; sp.cr1_off = kStructCr1Off;
     sp.xyz = p.xyz; sp.X = dX; sp.cmask = p.cmask; sp.J = dJ; sp.R = dR;
@@ -1075,7 +1075,7 @@ int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz)
   ctx->have_plan = true;
   // the plan of the layout this problem will most likely sweep with is built now; the other one on first use
   const int aux = (ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
-  const bool struct_cfg = ctx->elem_type == MASTB200_HEX8 && ctx->nv == 3 && !ctx->thermal;
+  const bool struct_cfg = ctx->elem_type == MASTB200_HEX8 && (ctx->nv == 3 || ctx->nv == 6) && !ctx->thermal;
   if (struct_cfg) {
     if (int rc = ensure_struct_plan(ctx)) { ctx->have_plan = false; return rc; }
   }

@@ -37,6 +37,7 @@ struct StructParams {
   int32_t* counter = nullptr;            // dynamic unit scheduler (zeroed before every launch)
   int32_t nx = 0, ny = 0, nz = 0;        // elements per direction of the (local) box
   int32_t oz0 = 0;                       // first owned node plane: CSR rows start there
+  int32_t nv = 3;                        // 3 (compact) or 6 (MAST's structural system: rotational rows kept, see flush)
   const int64_t* nbr_ptr = nullptr;      // node-level CSR row pointer of the owned rows
   const int32_t* arr_off = nullptr;      // [123] offsets of the pair arrays within an IN (42) / CR (81) region
   int32_t in1_off = 0, cr0_off = 0, cr1_off = 0;

@@ -59,9 +59,10 @@ constexpr int O_TAB = O_CM + 4 * NSB;                   // [124] int32: array of
 constexpr int O_RHO = O_TAB + 124 * 4;                  // [3 planes][NS] nodal density (SIMP variant)
 constexpr int O_NODE = O_RHO + 3 * NS * 8;              // [64] int2: owned nodes of the unit (in-plane id, slot | boundary flags)
 constexpr int O_FPK = O_NODE + 64 * 8;                  // [4 passes][8 lanes] packed flush constants
-constexpr int O_MISC = O_FPK + 32 * 4;
+constexpr int O_ROT = O_FPK + 32 * 4;                   // [2 planes][NS] sum of 1e-20 * max(diag K_e) per node (nv = 6)
+constexpr int O_MISC = O_ROT + 2 * NS * 8;
 constexpr int SMEM_BYTES = O_MISC + 16;
-static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0, "alignment");
+static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0 && O_ROT % 8 == 0, "alignment");
 static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
@@ -100,6 +101,7 @@ struct Sm {
   double* rho;
   int2* node;
   int32_t* fpk;
+  double* rot;
   int* misc;
 };
 
@@ -211,9 +213,9 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
 }
 
 // ---- matrix + ordered accumulate: all 32 lanes on one element ------------------------------------------------------
-template <int PAR>
-__device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, unsigned arena32, int rankpack, const double* st,
-                                              int lex, int ley, int color, int lane) {
+template <int PAR, bool NV6>
+__device__ __forceinline__ void element_phase(const StructParams& p, const Sm& sm, const LaneK& lk, unsigned arena32, int rankpack,
+                                              const double* st, int lex, int ley, int color, int lane) {
   const int m = lane >> 2, q4 = lane & 3;
   double A[3][2], w[2];
 #pragma unroll
@@ -239,6 +241,19 @@ __device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, uns
     dmma8x8x4(C[4][0], C[4][1], A[0][h], B[2][h]);
     dmma8x8x4(C[5][0], C[5][1], A[1][h], B[2][h]);
   }
+  double mx = 0.;
+  if (NV6) {
+    // 1e-20*max(diag K_e) goes on the rotational diagonal of the 6-variable system (solid_element_3d.cpp:413-417);
+    // diag of K_e from S_aa: the lane with b == m holds it (the rotational diagonal itself is zero, so the max is >= 0)
+    const int bself = m - 2 * q4;
+    if (bself == 0 || bself == 1) {
+      const double s0 = C[0][bself & 1], s1 = C[1][bself & 1], s2 = C[2][bself & 1];
+      const double trm = p.mu1 * (s0 + s1 + s2);
+      mx = fmax(mx, fmax((p.lam1 + p.mu1) * s0 + trm, fmax((p.lam1 + p.mu1) * s1 + trm, (p.lam1 + p.mu1) * s2 + trm)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
   // ordered accumulation: the (up to) four elements around a node column add in colour order
   const int base = ley * TCX + lex;
   const bool checker = q4 == 0 && m < 4;
@@ -259,6 +274,11 @@ __device__ __forceinline__ void element_phase(const Sm& sm, const LaneK& lk, uns
 #pragma unroll
   for (int t = 0; t < 12; ++t)
     if ((lk.pred >> t) & 1u) sts64(ar + lk.off[PAR][t], old[t] + C[t % 6][t / 6]);
+  if (NV6 && checker) {  // both nodes of the column (node planes s and s+1)
+    const int col = base + (m >> 1) * TCX + (m & 1);
+    sm.rot[PAR * NS + col] += 1.0e-20 * mx;
+    sm.rot[(PAR ^ 1) * NS + col] += 1.0e-20 * mx;
+  }
   __syncwarp();
   if (checker) st_release_s32(cnt, rank + 1);
 }
@@ -283,6 +303,7 @@ __device__ __forceinline__ int flush_pack(int t, int l8) {
   }
 }
 
+template <bool NV6>
 __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm, unsigned arena32, int s,
                                             int n_own, int64_t plane_off, int warp, int lane) {
   const int g = warp * 4 + (lane >> 3), l8 = lane & 7;
@@ -306,7 +327,8 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
   const unsigned regIn = arena32 + ((par ? p.in1_off : 0) + slotA) * 8;
   const unsigned regUp = arena32 + ((par ? p.cr1_off : p.cr0_off) + slotA) * 8;
   const unsigned regDn = arena32 + ((par ? p.cr0_off : p.cr1_off) + slotA) * 8;
-  double* Jrow = p.J + 9 * nb0;
+  double* Jrow = p.J + (NV6 ? 36 : 9) * nb0;
+  const double rotA = NV6 ? sm.rot[par * NS + slotA] : 0.;
   double r0 = 0., r1 = 0., r2 = 0.;
 #pragma unroll 1
   for (int t = 0; t < 4; ++t) {
@@ -362,11 +384,25 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
           const int d = c, ddk = d / 9, ddj = (d / 3) % 3, ddi = d % 3;
           c = ((ddk - z0) * ycnt + (ddj - y0)) * xcnt + (ddi - x0);
         }
-        double* dst = Jrow + 3 * c;
+        if (!NV6) {
+          double* dst = Jrow + 3 * c;
 #pragma unroll
-        for (int i = 0; i < 3; ++i)
+          for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+            for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+        } else {  // 6-variable system: translational block, zero rotational rows/columns, tiny rotational diagonal
+          double* dst = Jrow + 6 * c;
+          const int rl = 2 * rs;
+#pragma unroll
+          for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+              double val = 0.;
+              if (i < 3 && j < 3) val = K[i][j];
+              else if (i == j && self) val = ((cmn >> i) & 1u) ? nadj : rotA;
+              dst[i * rl + j] = val;
+            }
+        }
       }
     }
   }
@@ -380,12 +416,13 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
     y += __shfl_xor_sync(0xffffffffu, y, 1);
     if (valid && (l8 & 1) == 0 && l8 < 6) {
       const int i = l8 >> 1;
-      p.R[(plane_off + ni.x) * 3 + i] = ((cmn >> i) & 1u) ? 0. : y;
+      p.R[(plane_off + ni.x) * (NV6 ? 6 : 3) + i] = ((cmn >> i) & 1u) ? 0. : y;
+      if (NV6) p.R[(plane_off + ni.x) * 6 + 3 + i] = 0.;  // rotational dofs: no residual
     }
   }
 }
 
-template <bool SIMP>
+template <bool SIMP, bool NV6>
 __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Sm sm;
@@ -399,6 +436,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
   sm.rho = reinterpret_cast<double*>(smem_raw + O_RHO);
   sm.node = reinterpret_cast<int2*>(smem_raw + O_NODE);
   sm.fpk = reinterpret_cast<int32_t*>(smem_raw + O_FPK);
+  sm.rot = reinterpret_cast<double*>(smem_raw + O_ROT);
   sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 123) sm.tab[tid] = p.arr_off[tid];
@@ -430,7 +468,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
       const int64_t gid0 = (u.e0x + lx) + (u.e0y + ly) * npx;
       ld_u = c >= 3;
       ld_dst = (ld_u ? c - 3 : c) * NS + ly * TCX + lx;
-      ld_src = gid0 * 3 + (ld_u ? c - 3 : c);
+      ld_src = gid0 * (ld_u && NV6 ? 6 : 3) + (ld_u ? c - 3 : c);
     }
     const bool cm_on = p.cmask != nullptr && tid < ncols;
     int cm_dst = 0;
@@ -446,7 +484,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
         cp_async8(sm.rho + (z % 3) * NS + ly * TCX + lx, p.rho + (int64_t)z * plane_nodes + (u.e0x + lx) + (u.e0y + ly) * npx);
       }
       if (ld_on) {
-        if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * 3 + ld_src);
+        if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * (NV6 ? 6 : 3) + ld_src);
         else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
       }
     };
@@ -481,6 +519,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
     // prologue: clear the accumulators, stage the first two node planes
     for (int i = tid; i < kStructArenaDoubles; i += ST) sm.arena[i] = 0.;
     if (tid < NS) sm.cnt[tid] = 0;
+    if (NV6 && tid < 2 * NS) sm.rot[tid] = 0.;
     load_plane(s_begin);
     if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
     if (cm_on) {
@@ -509,19 +548,19 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-            if (lex < u.nex && ley < u.ney) element_phase<1>(sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
+            if (lex < u.nex && ley < u.ney) element_phase<1, NV6>(p, sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
           }
         } else {
 #pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-            if (lex < u.nex && ley < u.ney) element_phase<0>(sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
+            if (lex < u.nex && ley < u.ney) element_phase<0, NV6>(p, sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
           }
         }
       }
       __syncthreads();
       const bool do_flush = s >= u.z0;
-      if (do_flush) flush_plane(p, sm, arena32, s, u.nox * u.noy, (int64_t)s * plane_nodes, warp, lane);
+      if (do_flush) flush_plane<NV6>(p, sm, arena32, s, u.nox * u.noy, (int64_t)s * plane_nodes, warp, lane);
       if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
       cp_async_wait_all();
       __syncthreads();
@@ -533,6 +572,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
         double* zc = sm.arena + (par ? p.cr0_off : p.cr1_off);
         for (int i = tid; i < 81 * NS; i += ST) zc[i] = 0.;
         if (tid < NS) sm.cnt[tid] = 0;
+        if (NV6 && tid < NS) sm.rot[par * NS + tid] = 0.;
       }
       __syncthreads();
     }
@@ -547,15 +587,15 @@ int hex8_struct_threads() { return ST; }
 cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  if (p.rho) {
-    e = cudaFuncSetAttribute(hex8_struct_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    hex8_struct_kernel<true><<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
-  } else {
-    e = cudaFuncSetAttribute(hex8_struct_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    hex8_struct_kernel<false><<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
-  }
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (er != cudaSuccess) return er;
+    kern<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+    return cudaSuccess;
+  };
+  if (p.nv == 6) e = p.rho ? go(hex8_struct_kernel<true, true>) : go(hex8_struct_kernel<false, true>);
+  else e = p.rho ? go(hex8_struct_kernel<true, false>) : go(hex8_struct_kernel<false, false>);
+  if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
 

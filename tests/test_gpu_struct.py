@@ -141,3 +141,27 @@ def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch):
     ctx2.sensitivity_sweep(X, lam, G2, R2, J2)
     assert ctx2.stats()["structured"] == 0
     _close(G2, G, 1e-11); _close(R2, R); _close(J2, J)
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (3, 2, 2), (9, 8, 7), (16, 9, 12)])
+def test_struct_nv6_reference_layout(built, shape, monkeypatch):
+    # MAST's own structural system has six variables per node: zero rotational rows/columns kept in the pattern,
+    # 1e-20*max(diag K_e) summed on the rotational diagonal (solid_element_3d.cpp:413-417); SIMP modulus too
+    nx, ny, nz = shape
+    for simp in (False, True):
+        prob = O.cantilever(nx, ny, nz, nv=6, jitter=0.2, simp=simp)
+        X = O.state(prob.n_dof, 1)
+        ctx = prob.make_context(0)
+        rp, ci = ctx.get_pattern()
+        orp, oci = prob.pattern()
+        assert np.array_equal(rp, orp) and np.array_equal(ci, oci)
+        R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
+        ctx.residual_and_jacobian(X, R, J)
+        assert ctx.stats()["structured"] == 1
+        Ro, Jo = prob.residual_and_jacobian(X)
+        _close(R, Ro); _close(J, Jo)
+        # the rotational diagonal is far below the tolerance of the whole-matrix comparison: check it on its own
+        rows = np.repeat(np.arange(prob.n_dof), np.diff(rp))
+        rot = (rows == ci) & (rows % 6 >= 3) & ~prob.constrained.astype(bool)[rows]
+        assert rot.sum() > 0 and np.all(Jo[rot] > 0)
+        assert np.abs(J[rot] - Jo[rot]).max() <= 1e-11 * np.abs(Jo[rot]).max()
