@@ -31,6 +31,9 @@ namespace mastb200 {
 namespace {
 
 constexpr int TB = 128;
+#ifndef MASTB200_H27_CTAS
+#define MASTB200_H27_CTAS 5
+#endif
 constexpr int QSTR = 36;              // q-stride of the gradient arrays (doubles): 36 = 4 mod 16 -> conflict-free fragments
 constexpr int GSZ = 28 * QSTR;        // one component array: 28 (27 + zero pad) quadrature points x 36 columns
 
@@ -41,9 +44,7 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 }
 
 struct Smem27 {
-  double tabN[27 * 27];       // N_b(q)            [q][b]
-  double tabD[27 * 27 * 3];   // dN_b/dxi_r(q)     [q][b][r]
-  double tabW[28];            // Gauss weights
+  double tabW[28];            // Gauss weights (the shape tables N_b(q), dN_b/dxi_r(q) stay in global memory / L1)
   double g[3][GSZ];           // physical gradients [i][q*36 + a]
   double wq[28];              // JxW * E at the point (0 for the pad point)
   double pth[28];             // thermal stress factor at the point
@@ -56,7 +57,7 @@ struct Smem27 {
   uint8_t pos[27 * 27 + 7];   // position of node b in the neighbour list of node a
 };
 
-__global__ void __launch_bounds__(TB, 4) hex27_sweep_kernel(const Hex27Params p) {
+__global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(const Hex27Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -64,8 +65,8 @@ __global__ void __launch_bounds__(TB, 4) hex27_sweep_kernel(const Hex27Params p)
   const bool wantJ = p.J != nullptr, wantR = p.R != nullptr;
 
   // tables and the zero padding of the operand arrays: once per CTA
-  for (int k = tid; k < 27 * 27; k += TB) s.tabN[k] = p.tab[k];
-  for (int k = tid; k < 27 * 27 * 3; k += TB) s.tabD[k] = p.tab[27 * 27 + k];
+  const double* __restrict__ tabN = p.tab;             // [q][b]
+  const double* __restrict__ tabD = p.tab + 27 * 27;   // [q][b][r]
   if (tid < 27) s.tabW[tid] = p.tab[27 * 27 * 4 + tid];
   for (int k = tid; k < 3 * GSZ; k += TB) (&s.g[0][0])[k] = 0.;
   if (tid < 28) { s.wq[tid] = 0.; s.pth[tid] = 0.; }
@@ -107,13 +108,13 @@ __global__ void __launch_bounds__(TB, 4) hex27_sweep_kernel(const Hex27Params p)
       double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
       double rq = 0., tq = 0.;
       for (int b = 0; b < 27; ++b) {
-        const double* d = s.tabD + (q * 27 + b) * 3;
+        const double* d = tabD + (q * 27 + b) * 3;
         const double x0 = s.xs[b * 3], x1 = s.xs[b * 3 + 1], x2 = s.xs[b * 3 + 2];
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
           Jm[r][0] = fma(d[r], x0, Jm[r][0]); Jm[r][1] = fma(d[r], x1, Jm[r][1]); Jm[r][2] = fma(d[r], x2, Jm[r][2]);
         }
-        const double N = s.tabN[q * 27 + b];
+        const double N = __ldg(tabN + q * 27 + b);
         rq = fma(N, s.rho[b], rq);
         tq = fma(N, s.T[b], tq);
       }
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(TB, 4) hex27_sweep_kernel(const Hex27Params p)
     // ---- phase 2: physical gradients g_i[q][a] ----
     for (int k = tid; k < 27 * 27; k += TB) {
       const int q = k / 27, a = k - q * 27;
-      const double* d = s.tabD + k * 3;
+      const double* d = tabD + k * 3;
       const double* inv = s.inv + q * 9;
 #pragma unroll
       for (int c = 0; c < 3; ++c) s.g[c][q * QSTR + a] = d[0] * inv[c * 3] + d[1] * inv[c * 3 + 1] + d[2] * inv[c * 3 + 2];
@@ -256,7 +257,7 @@ cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t 
   if (p.n_elems <= 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(hex27_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem27));
   if (e != cudaSuccess) return e;
-  const int grid = p.n_elems < 4 * sm_count ? p.n_elems : 4 * sm_count;
+  const int grid = p.n_elems < MASTB200_H27_CTAS * sm_count ? p.n_elems : MASTB200_H27_CTAS * sm_count;
   hex27_sweep_kernel<<<grid, TB, sizeof(Smem27), stream>>>(p);
   return cudaGetLastError();
 }
