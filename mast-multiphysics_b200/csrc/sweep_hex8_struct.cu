@@ -7,7 +7,8 @@
 // isotropic D of src/property_cards/isotropic_material_property_card.cpp:512-528 -- for the meshes libMesh's
 // MeshTools::Generation::build_cube produces (examples/structural/base/bracket_3d_model.h:172-177): node id
 // i + j(nx+1) + k(nx+1)(ny+1), element id i + j nx + k nx ny.  The host recognises that numbering (context.cu) and
-// uses this kernel for the plain 3-dof R/J sweep; any other mesh takes the plan-driven kernel of sweep_hex8.cu.
+// uses this kernel for the R/J sweep (nv = 3 or MAST's six-variable system, constant or SIMP modulus); any other mesh
+// and the thermoelastic load take the plan-driven kernel of sweep_hex8.cu.
 // Geometry is general (every element's Jacobian is evaluated at its 8 Gauss points); only the integer bookkeeping
 // is implicit, so no plan is streamed from HBM.
 //
@@ -22,11 +23,12 @@
 //             the pair -- addresses are lane constants plus the element's column index.  The four elements sharing a
 //             node column accumulate in colour order (x parity + 2 y parity), enforced by one counter per column
 //             (acquire/release): fixed summation order, no atomics, no CTA barrier inside the plane.
-//   flush   : node plane s is complete once element plane s is done.  Warp = owned node, lane = neighbour direction
-//             (its array offsets are lane constants): the pair block of each of the <= 27 neighbours (forward pairs
-//             stored at the node, backward pairs at the neighbour, transposed) becomes K_AB = lam S + mu S^T + mu tr(S) I
-//             with libMesh's per-element Dirichlet semantics and is stored -- every CSR value exactly once, consecutive
-//             lanes writing consecutive column blocks of a row; f_A = sum_B K_AB u_B by a fixed-order warp reduction.
+//   flush   : node plane s is complete once element plane s is done.  Eight lanes per owned node, four passes over its
+//             <= 27 neighbour directions (per-pass constants and the node table live in shared memory, nothing is held
+//             in registers across the element phase): the pair block of each neighbour (forward pairs stored at the
+//             node, backward pairs at the neighbour, transposed) becomes K_AB = lam S + mu S^T + mu tr(S) I with libMesh's
+//             per-element Dirichlet semantics and is stored -- every CSR value exactly once, consecutive lanes writing
+//             consecutive column blocks of a row; f_A = sum_B K_AB u_B by a fixed-order butterfly over the eight lanes.
 //             K_e is never formed.
 //   zero    : the accumulators of the flushed plane are cleared for reuse two planes later.
 // Nodal coordinates / displacements of plane s+2 are fetched with cp.async while plane s is processed.
