@@ -165,3 +165,48 @@ def test_struct_nv6_reference_layout(built, shape, monkeypatch):
         rot = (rows == ci) & (rows % 6 >= 3) & ~prob.constrained.astype(bool)[rows]
         assert rot.sum() > 0 and np.all(Jo[rot] > 0)
         assert np.abs(J[rot] - Jo[rot]).max() <= 1e-11 * np.abs(Jo[rot]).max()
+
+
+def test_struct_random_shapes_slabs_and_layouts(built):
+    # random box shapes around the tile sizes (7 owned nodes / 8 elements per tile edge, z-segments), random owned
+    # z-slabs, both dof layouts, SIMP or constant modulus: pattern bit-exact, values vs the oracle
+    import mast_b200
+    rng = np.random.default_rng(2026)
+    for trial in range(10):
+        nx, ny = int(rng.integers(1, 19)), int(rng.integers(1, 19))
+        nz = int(rng.integers(1, 40))
+        nv = int(rng.choice([3, 6]))
+        simp = bool(rng.integers(0, 2))
+        xyz, conn = mesh.build_cube(nx, ny, nz, 0.3 + 0.05 * nx, 0.2 + 0.05 * ny, 0.1 + 0.05 * nz, 8, jitter=0.2)
+        con = (rng.uniform(size=len(xyz) * nv) < 0.08).astype(np.uint8)
+        if nv == 6:
+            con.reshape(-1, 6)[:, 3:] = (rng.uniform(size=(len(xyz), 3)) < 0.03)
+        rho = 0.2 + 0.6 * rng.uniform(size=len(xyz)) if simp else None
+        prob = O.Problem(O.HEX8, xyz, conn, nv, constrained=con, rho=rho, rho_min=1e-8 if simp else 0.0,
+                         penalty=4.0 if simp else 1.0)
+        X = O.state(prob.n_dof, 1)
+        npxy = (nx + 1) * (ny + 1)
+        z0 = int(rng.integers(0, nz + 1)); z1 = int(rng.integers(z0 + 1, nz + 2))
+        owned = None
+        if trial % 2:
+            owned = np.zeros(prob.n_nodes, np.uint8); owned[z0 * npxy:z1 * npxy] = 1
+        ctx = mast_b200.Context(0)
+        ctx.set_mesh(8, prob.xyz, prob.conn)
+        ctx.set_dof_map(nv, prob.constrained, owned)
+        ctx.set_material(**prob.mat)
+        if simp:
+            ctx.set_density(prob.rho)
+        ctx.build_pattern()
+        R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
+        ctx.residual_and_jacobian(X, R, J)
+        assert ctx.stats()["structured"] == 1, (nx, ny, nz, nv)
+        Ro, Jo = prob.residual_and_jacobian(X)
+        rows = ctx.get_row_dofs()
+        orp, oci = prob.pattern()
+        rp, ci = ctx.get_pattern()
+        assert np.array_equal(np.diff(rp), np.diff(orp)[rows])
+        assert np.array_equal(ci, np.concatenate([oci[orp[r]:orp[r + 1]] for r in rows]))
+        Jo_rows = np.concatenate([Jo[orp[r]:orp[r + 1]] for r in rows])
+        _close(J, Jo_rows); _close(R[rows], Ro[rows])
+        ghost = np.ones(prob.n_dof, bool); ghost[rows] = False
+        assert np.all(R[ghost] == 0.0)
