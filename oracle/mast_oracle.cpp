@@ -756,6 +756,60 @@ static void plate_internal_residual(const OracleProblem* p, const FE& fe, const 
   }
 }
 
+// A QUAD4 plate anywhere in space: GeomElem builds a local element in the plane of the first three nodes when the
+// nodes do not share one z (geom_elem.cpp:358-374, ::_init_local_elem_2d :461-511), the element is evaluated there with
+// the solution rotated into the local frame (structural_element_base.cpp:1606-1640) and the residual / Jacobian are
+// rotated back: f = T_g f_l, K = T_g K_l T_g^T (:1565-1601, 1642-1674), T_g repeating the 3x3 T for the translations
+// and the rotations of every node.
+static void plate_elem_calculations(const OracleProblem* p, const double* X, const Vec& sol, bool request_jacobian,
+                                    Vec& f, Mat& jac) {
+  const int nn = 4, n2 = 24;
+  bool use_local = false;
+  for (int i = 1; i < nn; ++i)
+    if (std::fabs(X[2] - X[i * 3 + 2]) != 0.) use_local = true;
+  if (!use_local) {
+    FE fe;
+    fe_init(ORACLE_QUAD4, X, fe);
+    plate_internal_residual(p, fe, X, sol, request_jacobian, f, jac);
+    return;
+  }
+  auto sub = [&](int a, int b, double* o) { for (int c = 0; c < 3; ++c) o[c] = X[a * 3 + c] - X[b * 3 + c]; };
+  auto normalise = [](double* v) { const double n = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); for (int c = 0; c < 3; ++c) v[c] /= n; };
+  auto cross = [](const double* a, const double* b, double* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+  };
+  double v1[3], v2[3], v3[3];
+  sub(1, 0, v1); normalise(v1);
+  sub(2, 0, v2); normalise(v2);
+  cross(v1, v2, v3); normalise(v3);
+  cross(v3, v1, v2); normalise(v2);
+  double T[3][3];
+  for (int i = 0; i < 3; ++i) { T[i][0] = v1[i]; T[i][1] = v2[i]; T[i][2] = v3[i]; }
+  std::vector<double> Xl(nn * 3, 0.);
+  for (int i = 0; i < nn; ++i)
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) Xl[i * 3 + j] += T[k][j] * (X[i * 3 + k] - X[k]);
+  Mat Tg(n2, n2);
+  for (int i = 0; i < nn; ++i)
+    for (int j = 0; j < 3; ++j)
+      for (int k = 0; k < 3; ++k) { Tg(j * nn + i, k * nn + i) = T[j][k]; Tg((j + 3) * nn + i, (k + 3) * nn + i) = T[j][k]; }
+  const Vec sol_l = matvec_t(Tg, sol);
+  FE fe;
+  fe_init(ORACLE_QUAD4, Xl.data(), fe);  // planar FE in the local x-y coordinates
+  Vec fl(n2, 0.);
+  Mat Kl(n2, n2);
+  plate_internal_residual(p, fe, Xl.data(), sol_l, request_jacobian, fl, Kl);
+  const Vec fg = matvec(Tg, fl);
+  for (int i = 0; i < n2; ++i) f[i] += fg[i];
+  if (request_jacobian) {
+    Mat TK = matmul(Tg, Kl), Tt(n2, n2);
+    for (int i = 0; i < n2; ++i)
+      for (int j = 0; j < n2; ++j) Tt(i, j) = Tg(j, i);
+    const Mat Kg = matmul(TK, Tt);
+    add_scaled_top_left(jac, Kg, 1.);
+  }
+}
+
 // HeatConductionElementBase::surface_flux_residual (heat_conduction_elem_base.cpp:876-914) and
 // ::surface_convection_residual (:1100-1155) on side `side` of a QUAD4 (an EDGE2 with the 2-point Gauss rule of
 // MAST::FEBase::init_for_side, fe_base.cpp:137-204): f += JxW N th flux ; f += JxW N th h_c (T - T_amb),
@@ -896,7 +950,7 @@ static void elem_calculations(const OracleProblem* p, const SideLoadIndex& sl, i
   mat.resize(nd, nd);
   if (p->elem_type == ORACLE_QUAD4) {
     if (p->nv == 6) {
-      plate_internal_residual(p, fe, X.data(), sol, if_jac, vec, mat);  // StructuralElement2D
+      plate_elem_calculations(p, X.data(), sol, if_jac, vec, mat);  // StructuralElement2D
     } else {
       heat_elem_calculations(p, fe, sol, if_jac, vec, mat);
       // side_external_residual of heat conduction (heat_conduction_elem_base.cpp:428-483): HEAT_FLUX, CONVECTION_HEAT_FLUX
