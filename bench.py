@@ -315,7 +315,7 @@ def main():
             except Exception:
                 traffic = None
         st = ctx.stats()
-        kname = "hex8_struct_kernel" if st.get("structured") else "hex8_sweep_kernel"
+        kname = {1: "hex8_struct_kernel", 2: "hex8_march_kernel"}.get(st.get("structured"), "hex8_sweep_kernel")
         if os.path.exists(tpath):
             try:
                 traffic = json.load(open(tpath)).get(kname) if n == 200 and world == 1 else None

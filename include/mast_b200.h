@@ -170,7 +170,7 @@ typedef struct mastb200_stats {
   double last_main_kernel_ms;    /* ... of the dominant (tile sweep) kernel alone */
   int64_t plan_bytes;            /* device bytes of the static plan streamed per sweep */
   int32_t smem_bytes, threads_per_cta, ctas;
-  int32_t structured;            /* 1: the last HEX8 sweep used the implicit-connectivity kernel (build_cube numbering) */
+  int32_t structured;            /* the last HEX8 sweep used an implicit-connectivity kernel (build_cube numbering): 1 lock-step, 2 column march */
 } mastb200_stats;
 int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s);
 /* Streaming assembly plan of a planning-only context (device -1), for host-side verification of the integer

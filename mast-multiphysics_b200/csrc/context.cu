@@ -130,7 +130,13 @@ struct mastb200_context {
     DevBuf<StructUnit> units;
     DevBuf<int32_t> arr_off;
     DevBuf<int64_t> nbr_ptr;
-    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); }
+    // units of the register-accumulating march (sweep_hex8_march.cu; 3-dof system)
+    DevBuf<StructUnit> m_units;
+    int32_t m_n_units = 0, m_n_ctas = 0;
+    int64_t m_n_visits = 0;
+    bool march = false;       // the march kernel serves nv = 3
+    bool last_march = false;  // ... and ran the last sweep
+    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); m_units.release(); }
   } splan;
   int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
   DevBuf<int32_t> d_tile_counter, d_owned_nodes;
@@ -579,6 +585,51 @@ int ensure_struct_plan(mastb200_context* ctx) {
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
   std::vector<StructUnit> sorted(units.size());
   for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
+  // units of the register-accumulating march (3-dof system): columns of <= 16 x 4 owned nodes cut into z-segments.
+  // Opt-in with MASTB200_STRUCT_KERNEL=march: parity-green but slower than the lock-step kernel so far
+  // (profiles/r01h_hex8_march_ncu.md).
+  {
+    bool want = false;
+    if (const char* e = getenv("MASTB200_STRUCT_KERNEL"))
+      want = e[0] == 'm' && ctx->nv == 3 && (size_t)ctx->max_optin >= hex8_march_smem_bytes();
+    S.march = want;
+    if (want) {
+      std::vector<std::pair<int, int>> mx, my;
+      chunks(nx + 1, kMarchTileX, mx);
+      chunks(ny + 1, kMarchTileY, my);
+      const int64_t m_tiles = (int64_t)mx.size() * my.size();
+      int64_t mseg = (20 * (int64_t)ctx->sm_count + m_tiles - 1) / m_tiles;
+      mseg = std::max<int64_t>(1, std::min<int64_t>(mseg, std::max<int64_t>(1, planes / 24)));
+      std::vector<StructUnit> mu;
+      std::vector<int64_t> mc;
+      S.m_n_visits = 0;
+      for (size_t ty = 0; ty < my.size(); ++ty)
+        for (size_t tx = 0; tx < mx.size(); ++tx)
+          for (int64_t sg = 0; sg < mseg; ++sg) {
+            StructUnit u;
+            u.o0x = (int16_t)mx[tx].first; u.nox = (int16_t)mx[tx].second;
+            u.o0y = (int16_t)my[ty].first; u.noy = (int16_t)my[ty].second;
+            const int64_t e0x = std::max<int64_t>(u.o0x - 1, 0), e1x = std::min<int64_t>(u.o0x + u.nox, nx);
+            const int64_t e0y = std::max<int64_t>(u.o0y - 1, 0), e1y = std::min<int64_t>(u.o0y + u.noy, ny);
+            u.e0x = (int16_t)e0x; u.nex = (int16_t)(e1x - e0x);
+            u.e0y = (int16_t)e0y; u.ney = (int16_t)(e1y - e0y);
+            u.z0 = (int32_t)(oz0 + planes * sg / mseg); u.z1 = (int32_t)(oz0 + planes * (sg + 1) / mseg);
+            if (u.z1 <= u.z0) continue;
+            const int64_t e_begin = u.z0 > 0 ? u.z0 - 1 : 0, e_end = std::min<int64_t>(u.z1 - 1, nz - 1);
+            mu.push_back(u);
+            mc.push_back((int64_t)u.nex * u.ney * (e_end - e_begin + 1));
+            S.m_n_visits += (int64_t)u.nex * u.ney * std::max<int64_t>(e_end - e_begin + 1, 0);
+          }
+      std::vector<int32_t> mo(mu.size());
+      for (size_t i = 0; i < mo.size(); ++i) mo[i] = (int32_t)i;
+      std::stable_sort(mo.begin(), mo.end(), [&](int32_t a, int32_t b) { return mc[a] > mc[b]; });
+      std::vector<StructUnit> ms(mu.size());
+      for (size_t i = 0; i < mo.size(); ++i) ms[i] = mu[mo[i]];
+      CU(S.m_units.upload(ms, ctx->stream));
+      S.m_n_units = (int32_t)ms.size();
+      S.m_n_ctas = std::max(1, std::min(S.m_n_units, ctx->sm_count));
+    }
+  }
   std::vector<int32_t> arr_off(124, 0);
   for (int a = 0; a < 42; ++a) arr_off[a] = kStructPosIn[a] * kStructSlots;
   for (int a = 0; a < 81; ++a) arr_off[42 + a] = kStructPosCr[a] * kStructSlots;
@@ -789,7 +840,13 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     sp.xyz = p.xyz; sp.X = dX; sp.cmask = p.cmask; sp.J = dJ; sp.R = dR;
     sp.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
     sp.E0 = p.E0; sp.lam1 = p.lam1; sp.mu1 = p.mu1; sp.rho_min = p.rho_min; sp.penalty = p.penalty;
-    CU(launch_hex8_struct(sp, S.n_ctas, ctx->stream));
+    ctx->splan.last_march = S.march && ctx->nv == 3;
+    if (ctx->splan.last_march) {
+      sp.units = S.m_units.p; sp.n_units = S.m_n_units;
+      CU(launch_hex8_march(sp, S.m_n_ctas, ctx->stream));
+    } else {
+      CU(launch_hex8_struct(sp, S.n_ctas, ctx->stream));
+    }
   } else {
     CU(launch_hex8_sweep(p, ctx->dplan[aux].n_ctas, ctx->stream));
   }
@@ -1329,16 +1386,17 @@ int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   if (!ctx || !s) return MASTB200_ERR_ARG;
   std::memset(s, 0, sizeof *s);
   const mastb200_context::DevicePlan& D = ctx->dplan[ctx->last_plan];
-  s->n_tiles = ctx->last_struct ? ctx->splan.n_units : D.n_tiles;
-  s->n_visits = ctx->last_struct ? ctx->splan.n_visits : D.n_visits;
+  const bool lm = ctx->last_struct && ctx->splan.last_march;  // the march kernel ran the last structured sweep
+  s->n_tiles = ctx->last_struct ? (lm ? ctx->splan.m_n_units : ctx->splan.n_units) : D.n_tiles;
+  s->n_visits = ctx->last_struct ? (lm ? ctx->splan.m_n_visits : ctx->splan.n_visits) : D.n_visits;
   s->n_owned_nodes = ctx->pat.n_owned;
   s->n_elem = ctx->n_elem;
   s->kernel_launches = ctx->launches;
-  s->plan_bytes = ctx->last_struct ? (int64_t)ctx->splan.n_units * (int64_t)sizeof(StructUnit) : D.bytes;
-  s->smem_bytes = ctx->last_struct ? (int32_t)hex8_struct_smem_bytes() : (int32_t)D.smem;
-  s->threads_per_cta = ctx->last_struct ? hex8_struct_threads() : hex8_sweep_threads();
-  s->ctas = ctx->last_struct ? ctx->splan.n_ctas : D.n_ctas;
-  s->structured = ctx->last_struct ? 1 : 0;
+  s->plan_bytes = ctx->last_struct ? (int64_t)(lm ? ctx->splan.m_n_units : ctx->splan.n_units) * (int64_t)sizeof(StructUnit) : D.bytes;
+  s->smem_bytes = ctx->last_struct ? (int32_t)(lm ? hex8_march_smem_bytes() : hex8_struct_smem_bytes()) : (int32_t)D.smem;
+  s->threads_per_cta = ctx->last_struct ? (lm ? hex8_march_threads() : hex8_struct_threads()) : hex8_sweep_threads();
+  s->ctas = ctx->last_struct ? (lm ? ctx->splan.m_n_ctas : ctx->splan.n_ctas) : D.n_ctas;
+  s->structured = ctx->last_struct ? (lm ? 2 : 1) : 0;
   if (ctx->timed) {
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a + ctx->carry_ms;

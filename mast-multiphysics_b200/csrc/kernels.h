@@ -52,6 +52,11 @@ struct StructParams {
 size_t hex8_struct_smem_bytes();
 int hex8_struct_threads();
 cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream);
+// register-accumulating column march for the 3-dof system (sweep_hex8_march.cu): units of <= 16 x 4 owned node columns
+constexpr int kMarchTileX = 16, kMarchTileY = 4;
+size_t hex8_march_smem_bytes();
+int hex8_march_threads();
+cudaError_t launch_hex8_march(const StructParams& p, int n_ctas, cudaStream_t stream);
 
 // ---- row-owner gather kernels for small elements (sweep_quad4_heat.cu) ---------------------------------------------
 constexpr int kGatherMaxNbr = 24;      // neighbours per row the gather kernels keep in shared memory

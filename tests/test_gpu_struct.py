@@ -1,5 +1,6 @@
-"""Parity of the implicit-connectivity HEX8 sweep (sweep_hex8_struct.cu: build_cube numbering recognised by the host)
-against the CPU oracle, through the C-ABI, and agreement with the plan-driven sweep on the same inputs."""
+"""Parity of the implicit-connectivity HEX8 sweeps (sweep_hex8_struct.cu, and the opt-in column march of
+sweep_hex8_march.cu: build_cube numbering recognised by the host) against the CPU oracle, through the C-ABI, and
+agreement with the plan-driven sweep on the same inputs.  Every test runs once per kernel."""
 import numpy as np
 import pytest
 
@@ -8,6 +9,17 @@ from mast_b200 import mesh
 
 pytestmark = pytest.mark.gpu
 RTOL = 1e-12
+
+
+@pytest.fixture(autouse=True, params=["lockstep", "march"])
+def struct_kernel(request, monkeypatch):
+    monkeypatch.setenv("MASTB200_STRUCT_KERNEL", request.param)
+    return request.param
+
+
+def _is_struct(ctx, kernel, nv=3):
+    """stats()['structured']: 1 = lock-step kernel, 2 = column march (serves the 3-dof system when opted in)."""
+    return ctx.stats()["structured"] == (2 if kernel == "march" and nv == 3 else 1)
 
 
 def _close(a, b, rtol=RTOL):
@@ -28,7 +40,7 @@ def _problem(nx, ny, nz, jitter=0.2, constrained=True, seed=0):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (2, 3, 1), (3, 1, 2), (7, 8, 9), (8, 8, 8), (9, 15, 5), (14, 6, 30), (20, 10, 10)])
-def test_struct_residual_and_jacobian(built, shape):
+def test_struct_residual_and_jacobian(built, shape, struct_kernel):
     prob = _problem(*shape)
     X = O.state(prob.n_dof, 1)
     ctx = prob.make_context(0)
@@ -37,7 +49,7 @@ def test_struct_residual_and_jacobian(built, shape):
     assert np.array_equal(rp, orp) and np.array_equal(ci, oci)
     R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
     ctx.residual_and_jacobian(X, R, J)
-    assert ctx.stats()["structured"] == 1
+    assert _is_struct(ctx, struct_kernel)
     Ro, Jo = prob.residual_and_jacobian(X)
     _close(R, Ro); _close(J, Jo)
     con = prob.constrained.astype(bool)
@@ -49,13 +61,13 @@ def test_struct_residual_and_jacobian(built, shape):
     assert np.array_equal(R2, R) and np.array_equal(J2, J)
 
 
-def test_struct_matches_plan_driven_sweep(built, monkeypatch):
+def test_struct_matches_plan_driven_sweep(built, monkeypatch, struct_kernel):
     prob = _problem(13, 9, 11)
     X = O.state(prob.n_dof, 1)
     ctx = prob.make_context(0)
     R = np.empty(prob.n_dof); J = np.empty(ctx.nnz)
     ctx.residual_and_jacobian(X, R, J)
-    assert ctx.stats()["structured"] == 1
+    assert _is_struct(ctx, struct_kernel)
     monkeypatch.setenv("MASTB200_NO_STRUCT", "1")
     ctx2 = prob.make_context(0)
     R2 = np.empty(prob.n_dof); J2 = np.empty(ctx2.nnz)
@@ -72,7 +84,7 @@ def test_struct_matches_plan_driven_sweep(built, monkeypatch):
     assert ctx3.stats()["structured"] == 0
 
 
-def test_struct_owned_z_slab_with_ghost_planes(built):
+def test_struct_owned_z_slab_with_ghost_planes(built, struct_kernel):
     # a rank's local mesh in the z-slab partition: owned node planes [2, 6) of a 9-plane box, ghost planes around
     import mast_b200
     nx, ny, nz = 9, 8, 8
@@ -87,7 +99,7 @@ def test_struct_owned_z_slab_with_ghost_planes(built):
     ctx.build_pattern()
     R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
     ctx.residual_and_jacobian(X, R, J)
-    assert ctx.stats()["structured"] == 1
+    assert _is_struct(ctx, struct_kernel)
     Ro, Jo = prob.residual_and_jacobian(X)
     rows = ctx.get_row_dofs()
     orp, _ = prob.pattern()
@@ -101,7 +113,7 @@ def test_struct_owned_z_slab_with_ghost_planes(built):
     assert np.all(R[ghost] == 0.0)
 
 
-def test_struct_large_mesh_properties(built):
+def test_struct_large_mesh_properties(built, struct_kernel):
     # 96 x 70 x 50 jittered: symmetry of the assembled operator, rigid-body null space, K u == R (linear element)
     import scipy.sparse as sp
     nx, ny, nz = 96, 70, 50
@@ -112,7 +124,7 @@ def test_struct_large_mesh_properties(built):
     X = O.state(prob.n_dof, 1)
     R = np.empty(prob.n_dof); J = np.empty(ctx.nnz)
     ctx.residual_and_jacobian(X, R, J)
-    assert ctx.stats()["structured"] == 1
+    assert _is_struct(ctx, struct_kernel)
     A = sp.csr_matrix((J, ci, rp), shape=(prob.n_dof, prob.n_dof))
     assert abs(A - A.T).max() <= 1e-12 * np.abs(J).max()
     assert np.abs(A @ X - R).max() <= 1e-12 * np.abs(R).max()
@@ -120,7 +132,7 @@ def test_struct_large_mesh_properties(built):
     assert np.abs(A @ rb.ravel()).max() <= 1e-9 * np.abs(J).max()
 
 
-def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch):
+def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch, struct_kernel):
     # SIMP modulus in the implicit-connectivity sweep; G requested together with R/J comes from the element-parallel
     # kernels right after it; same numbers as the plan-driven fused sweep
     prob = O.cantilever(11, 9, 8, jitter=0.2, simp=True)
@@ -129,7 +141,7 @@ def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch):
     ctx = prob.make_context(0)
     G = np.full(n, np.nan); R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
     ctx.sensitivity_sweep(X, lam, G, R, J)
-    assert ctx.stats()["structured"] == 1
+    assert _is_struct(ctx, struct_kernel)
     Ro, Jo = prob.residual_and_jacobian(X)
     _close(R, Ro); _close(J, Jo)
     g_ref = prob.adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
@@ -144,7 +156,7 @@ def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch):
 
 
 @pytest.mark.parametrize("shape", [(1, 1, 1), (3, 2, 2), (9, 8, 7), (16, 9, 12)])
-def test_struct_nv6_reference_layout(built, shape, monkeypatch):
+def test_struct_nv6_reference_layout(built, shape, monkeypatch, struct_kernel):
     # MAST's own structural system has six variables per node: zero rotational rows/columns kept in the pattern,
     # 1e-20*max(diag K_e) summed on the rotational diagonal (solid_element_3d.cpp:413-417); SIMP modulus too
     nx, ny, nz = shape
@@ -157,7 +169,7 @@ def test_struct_nv6_reference_layout(built, shape, monkeypatch):
         assert np.array_equal(rp, orp) and np.array_equal(ci, oci)
         R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
         ctx.residual_and_jacobian(X, R, J)
-        assert ctx.stats()["structured"] == 1
+        assert _is_struct(ctx, struct_kernel, 6)
         Ro, Jo = prob.residual_and_jacobian(X)
         _close(R, Ro); _close(J, Jo)
         # the rotational diagonal is far below the tolerance of the whole-matrix comparison: check it on its own
@@ -167,7 +179,7 @@ def test_struct_nv6_reference_layout(built, shape, monkeypatch):
         assert np.abs(J[rot] - Jo[rot]).max() <= 1e-11 * np.abs(Jo[rot]).max()
 
 
-def test_struct_random_shapes_slabs_and_layouts(built):
+def test_struct_random_shapes_slabs_and_layouts(built, struct_kernel):
     # random box shapes around the tile sizes (7 owned nodes / 8 elements per tile edge, z-segments), random owned
     # z-slabs, both dof layouts, SIMP or constant modulus: pattern bit-exact, values vs the oracle
     import mast_b200
@@ -199,7 +211,7 @@ def test_struct_random_shapes_slabs_and_layouts(built):
         ctx.build_pattern()
         R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
         ctx.residual_and_jacobian(X, R, J)
-        assert ctx.stats()["structured"] == 1, (nx, ny, nz, nv)
+        assert _is_struct(ctx, struct_kernel, nv), (nx, ny, nz, nv)
         Ro, Jo = prob.residual_and_jacobian(X)
         rows = ctx.get_row_dofs()
         orp, oci = prob.pattern()
