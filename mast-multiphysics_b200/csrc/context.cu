@@ -375,14 +375,16 @@ int ensure_generic_plan(mastb200_context* ctx) {
   return MASTB200_OK;
 }
 
-// QUAD4 Mindlin plate in the xy-plane (row-block gather)
+// QUAD4 Mindlin plate (row-block gather; per-element local frames when an element is out of the xy-plane)
 int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
   int rc;
   if (ctx->mat.nonlinear_strain)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "von Karman strain of the plate element is not on the device path");
-  for (int64_t n = 1; n < ctx->n_nodes; ++n)
-    if (ctx->xyz[n * 3 + 2] != ctx->xyz[2])
-      return ctx->fail(MASTB200_ERR_UNSUPPORTED, "plate elements out of the xy-plane are not on the device path");
+  // GeomElem's rule (geom_elem.cpp:358-374): an element whose nodes do not share one z gets a local frame
+  int32_t local_frames = 0;
+  for (int64_t e = 0; e < ctx->n_elem && !local_frames; ++e)
+    for (int k = 1; k < 4; ++k)
+      if (ctx->xyz[(int64_t)ctx->conn[e * 4 + k] * 3 + 2] != ctx->xyz[(int64_t)ctx->conn[e * 4] * 3 + 2]) local_frames = 1;
   if ((rc = ensure_generic_plan(ctx))) return rc;
   mastb200_context::GenericPlan& G = ctx->gplan;
   const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
@@ -412,6 +414,7 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
   p.c33 = m.E0 / 2. / (1. + m.nu);
   p.shear_G = m.E0 / 2. / (1. + m.nu);
   p.thickness = m.thickness; p.offset = m.offset; p.kappa = m.kappa;
+  p.local_frames = local_frames;
   CU(launch_quad4_plate(p, ctx->stream));
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -1,4 +1,4 @@
-// sweep_quad4_plate.cu -- QUAD4 Mindlin plate residual + Jacobian, linear strain, elements in the xy-plane
+// sweep_quad4_plate.cu -- QUAD4 Mindlin plate residual + Jacobian, linear strain, elements anywhere in space
 // (sm_100a, fp64).
 //
 // Device counterpart of the element loop of MAST::NonlinearImplicitAssembly::residual_and_jacobian
@@ -9,7 +9,10 @@
 // the rule two orders lower -- one Gauss point for QUAD4 (:94-160, 314-361), the section matrices A = C h, B = C h off,
 // D = C (h^3/12 + h off^2), G kappa h (src/property_cards/solid_2d_section_element_property_card.cpp:395-510, 122-134;
 // C of isotropic_material_property_card.cpp:395-426) and the 1e-8 drilling diagonal (:1217-1221).
-// Elements out of the xy-plane (T K T^T of structural_element_base.cpp:1565-1601) are refused by the host.
+// Elements whose nodes do not share one z are evaluated in the local frame of their first three nodes (GeomElem,
+// src/mesh/geom_elem.cpp:358-374, 461-511): solution rotated in (structural_element_base.cpp:1606-1640), f = T f_l and
+// K = T K_l T^T rotated out (:1565-1601, 1642-1674), per element, before the block joins the row (LOCAL variant; the
+// host picks it when the mesh has such an element).
 //
 // Row-owner gather: one thread per (owned node, neighbour) pair, i.e. per 6x6 block of the node-level CSR.  The thread
 // walks the elements adjacent to the row node in ascending id (the order of the reference's element loop) and adds
@@ -54,6 +57,7 @@ __device__ __forceinline__ void q4_eval(const double* x, const double* y, double
   }
 }
 
+template <bool LOCAL>
 __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
   const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (t >= p.n_entries) return;
@@ -90,16 +94,57 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
     if (p.diag_elem && p.diag_elem[e]) { ++nadjd; continue; }
     ++nadj;
     int en[4], a = 0, b = -1;
-    double x[4], y[4];
+    double x[4], y[4], z[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       en[k] = p.conn[(int64_t)e * 4 + k];
       x[k] = p.xyz[(int64_t)en[k] * 3];
       y[k] = p.xyz[(int64_t)en[k] * 3 + 1];
+      if (LOCAL) z[k] = p.xyz[(int64_t)en[k] * 3 + 2];
       if (en[k] == n) a = k;
       if (en[k] == m) b = k;
     }
     if (b < 0) continue;
+    // local frame of an element out of the xy-plane: T columns = v1 (node 0 -> 1), v2 = v3 x v1, v3 = v1 x (node 0 -> 2)
+    bool use_local = false;
+    double T[3][3] = {{1., 0., 0.}, {0., 1., 0.}, {0., 0., 1.}};
+    if (LOCAL) {
+      use_local = z[1] != z[0] || z[2] != z[0] || z[3] != z[0];
+      if (use_local) {
+        double v1[3] = {x[1] - x[0], y[1] - y[0], z[1] - z[0]}, v2[3] = {x[2] - x[0], y[2] - y[0], z[2] - z[0]}, v3[3];
+        double nr = sqrt(v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2]);
+        v1[0] /= nr; v1[1] /= nr; v1[2] /= nr;
+        nr = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+        v2[0] /= nr; v2[1] /= nr; v2[2] /= nr;
+        v3[0] = v1[1] * v2[2] - v1[2] * v2[1]; v3[1] = v1[2] * v2[0] - v1[0] * v2[2]; v3[2] = v1[0] * v2[1] - v1[1] * v2[0];
+        nr = sqrt(v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2]);
+        v3[0] /= nr; v3[1] /= nr; v3[2] /= nr;
+        v2[0] = v3[1] * v1[2] - v3[2] * v1[1]; v2[1] = v3[2] * v1[0] - v3[0] * v1[2]; v2[2] = v3[0] * v1[1] - v3[1] * v1[0];
+        nr = sqrt(v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2]);
+        v2[0] /= nr; v2[1] /= nr; v2[2] /= nr;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { T[i][0] = v1[i]; T[i][1] = v2[i]; T[i][2] = v3[i]; }
+        const double x0 = x[0], y0 = y[0], z0 = z[0];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double dx = x[k] - x0, dy = y[k] - y0, dz = z[k] - z0;
+          x[k] = T[0][0] * dx + T[1][0] * dy + T[2][0] * dz;
+          y[k] = T[0][1] * dx + T[1][1] * dy + T[2][1] * dz;
+        }
+      }
+    }
+    // LOCAL: the element's block and force are formed in Ke / fe and rotated into K / f afterwards
+    double Ke[6][6], fe[6];
+    double (&KK)[6][6] = LOCAL ? Ke : K;
+    double (&ff)[6] = LOCAL ? fe : f;
+    if (LOCAL) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        fe[i] = 0.;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) Ke[i][j] = 0.;
+      }
+    }
     const bool want_f = self && p.R;
     double U[4][6];
     if (want_f)
@@ -107,6 +152,15 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int v = 0; v < 6; ++v) U[k][v] = p.X[(int64_t)en[k] * 6 + v];
+    if (LOCAL && want_f && use_local)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int h3 = 0; h3 < 6; h3 += 3) {
+          const double g0 = U[k][h3], g1 = U[k][h3 + 1], g2 = U[k][h3 + 2];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) U[k][h3 + j] = T[0][j] * g0 + T[1][j] * g1 + T[2][j] * g2;
+        }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       Q4 g;
@@ -117,10 +171,10 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
         const double M00 = gxa * c11 * gxb + gya * c33 * gyb, M01 = gxa * c12 * gyb + gya * c33 * gxb;
         const double M10 = gya * c12 * gxb + gxa * c33 * gyb, M11 = gya * c11 * gyb + gxa * c33 * gxb;
         const double wA = g.JxW * h, wB = g.JxW * hoff, wD = g.JxW * hD;
-        K[0][0] += wA * M00; K[0][1] += wA * M01; K[1][0] += wA * M10; K[1][1] += wA * M11;      // membrane
-        K[0][3] += wB * (-M01); K[0][4] += wB * M00; K[1][3] += wB * (-M11); K[1][4] += wB * M10;  // membrane - bending
-        K[3][0] += wB * (-M10); K[3][1] += wB * (-M11); K[4][0] += wB * M00; K[4][1] += wB * M01;  // bending - membrane
-        K[3][3] += wD * M11; K[3][4] += wD * (-M10); K[4][3] += wD * (-M01); K[4][4] += wD * M00;  // bending
+        KK[0][0] += wA * M00; KK[0][1] += wA * M01; KK[1][0] += wA * M10; KK[1][1] += wA * M11;      // membrane
+        KK[0][3] += wB * (-M01); KK[0][4] += wB * M00; KK[1][3] += wB * (-M11); KK[1][4] += wB * M10;  // membrane - bending
+        KK[3][0] += wB * (-M10); KK[3][1] += wB * (-M11); KK[4][0] += wB * M00; KK[4][1] += wB * M01;  // bending - membrane
+        KK[3][3] += wD * M11; KK[3][4] += wD * (-M10); KK[4][3] += wD * (-M01); KK[4][4] += wD * M00;  // bending
       }
       if (want_f) {
         double e0 = 0., e1 = 0., e2 = 0., k0 = 0., k1 = 0., k2 = 0.;
@@ -133,10 +187,10 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
         const double Ck0 = c11 * k0 + c12 * k1, Ck1 = c12 * k0 + c11 * k1, Ck2 = c33 * k2;
         const double N0 = h * Ce0 + hoff * Ck0, N1 = h * Ce1 + hoff * Ck1, N2 = h * Ce2 + hoff * Ck2;
         const double Q0 = hoff * Ce0 + hD * Ck0, Q1 = hoff * Ce1 + hD * Ck1, Q2 = hoff * Ce2 + hD * Ck2;
-        f[0] += g.JxW * (gxa * N0 + gya * N2);
-        f[1] += g.JxW * (gya * N1 + gxa * N2);
-        f[3] += g.JxW * (-(gya * Q1 + gxa * Q2));
-        f[4] += g.JxW * (gxa * Q0 + gya * Q2);
+        ff[0] += g.JxW * (gxa * N0 + gya * N2);
+        ff[1] += g.JxW * (gya * N1 + gxa * N2);
+        ff[3] += g.JxW * (-(gya * Q1 + gxa * Q2));
+        ff[4] += g.JxW * (gxa * Q0 + gya * Q2);
       }
     }
     {  // transverse shear at the single point of the reduced rule (weight 4)
@@ -145,9 +199,9 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
       const double w = g.JxW * Gs;
       const double gxa = g.gx[a], gya = g.gy[a], Na = g.N[a], gxb = g.gx[b], gyb = g.gy[b], Nb = g.N[b];
       if (p.J) {
-        K[2][2] += w * (gxa * gxb + gya * gyb); K[2][3] += w * (-(gya * Nb)); K[2][4] += w * (gxa * Nb);
-        K[3][2] += w * (-(Na * gyb)); K[3][3] += w * (Na * Nb);
-        K[4][2] += w * (Na * gxb); K[4][4] += w * (Na * Nb);
+        KK[2][2] += w * (gxa * gxb + gya * gyb); KK[2][3] += w * (-(gya * Nb)); KK[2][4] += w * (gxa * Nb);
+        KK[3][2] += w * (-(Na * gyb)); KK[3][3] += w * (Na * Nb);
+        KK[4][2] += w * (Na * gxb); KK[4][4] += w * (Na * Nb);
       }
       if (want_f) {
         double g0 = 0., g1 = 0.;
@@ -156,12 +210,42 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
           g0 += g.gx[k] * U[k][2] + g.N[k] * U[k][4];
           g1 += g.gy[k] * U[k][2] - g.N[k] * U[k][3];
         }
-        f[2] += w * (gxa * g0 + gya * g1);
-        f[3] += w * (-(Na * g1));
-        f[4] += w * (Na * g0);
+        ff[2] += w * (gxa * g0 + gya * g1);
+        ff[3] += w * (-(Na * g1));
+        ff[4] += w * (Na * g0);
       }
     }
-    if (self) K[5][5] += 1.0e-8;  // drilling dof (structural_element_2d.cpp:1217-1221)
+    if (self) KK[5][5] += 1.0e-8;  // drilling dof (structural_element_2d.cpp:1217-1221)
+    if (LOCAL) {
+      if (use_local) {  // K += T6 Ke T6^T, f += T6 fe with T6 = diag(T, T)
+#pragma unroll
+        for (int bi = 0; bi < 6; bi += 3)
+#pragma unroll
+          for (int bj = 0; bj < 6; bj += 3) {
+            double W[3][3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                W[i][j] = T[i][0] * Ke[bi][bj + j] + T[i][1] * Ke[bi + 1][bj + j] + T[i][2] * Ke[bi + 2][bj + j];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) K[bi + i][bj + j] += W[i][0] * T[j][0] + W[i][1] * T[j][1] + W[i][2] * T[j][2];
+          }
+#pragma unroll
+        for (int bi = 0; bi < 6; bi += 3)
+#pragma unroll
+          for (int i = 0; i < 3; ++i) f[bi + i] += T[i][0] * fe[bi] + T[i][1] * fe[bi + 1] + T[i][2] * fe[bi + 2];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          f[i] += fe[i];
+#pragma unroll
+          for (int j = 0; j < 6; ++j) K[i][j] += Ke[i][j];
+        }
+      }
+    }
   }
 
   if (p.J) {
@@ -190,7 +274,8 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
 
 cudaError_t launch_quad4_plate(const PlateParams& p, cudaStream_t stream) {
   const int blocks = (int)((p.n_entries + TB - 1) / TB);
-  quad4_plate_kernel<<<blocks, TB, 0, stream>>>(p);
+  if (p.local_frames) quad4_plate_kernel<true><<<blocks, TB, 0, stream>>>(p);
+  else quad4_plate_kernel<false><<<blocks, TB, 0, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -446,6 +446,26 @@ def test_quad4_mindlin_plate_diag_elems_unstructured_and_size(built):
     assert np.abs(R).max() <= 1e-9 * np.abs(J).max()
 
 
+def test_quad4_mindlin_plate_out_of_plane_and_folded(built):
+    # elements out of the xy-plane: local frame per element, T K T^T (structural_element_base.cpp:1565-1674)
+    prob = _plate_problem(8, 5, jitter=0.2)
+    A = np.random.default_rng(2).normal(size=(3, 3))
+    Q, _ = np.linalg.qr(A)
+    rot = O.Problem(O.QUAD4, prob.xyz @ Q.T + 0.4, prob.conn, 6, constrained=prob.constrained, E0=72e9, nu=0.33,
+                    thickness=0.06, offset=0.03, kappa=5.0 / 6.0)
+    X = O.state(rot.n_dof, 1)
+    _check_RJ(rot, X)
+    _check_RJ(rot, X, want_R=False)
+    _check_RJ(rot, X, want_J=False)
+    # a folded plate: the left half stays in the plane z = 0.1 (no local frame), the right half climbs; diag elements too
+    prob = _plate_problem(8, 5, jitter=0.2, diag=True)
+    xyz = prob.xyz.copy()
+    xyz[:, 2] = 0.1 + 0.6 * np.maximum(xyz[:, 0] - 0.75, 0.0)
+    fold = O.Problem(O.QUAD4, xyz, prob.conn, 6, constrained=prob.constrained, E0=72e9, nu=0.33, thickness=0.06,
+                     offset=0.0, kappa=5.0 / 6.0, diag_elem=prob.diag_elem)
+    _check_RJ(fold, O.state(fold.n_dof, 2))
+
+
 def test_density_sensitivities_alone_hex8_hex27_and_old_sweep(built, monkeypatch):
     # G without R/J: element-parallel kernels for HEX8 and HEX27; compliance case adj == X; the streaming sweep
     # (MASTB200_SENS_SWEEP=1) gives the same numbers

@@ -226,6 +226,32 @@ def test_plate_translation_rotation_stretch_invariance(built):
     assert np.abs(K3 - K3.T).max() <= 1e-12 * np.abs(K3).max()
 
 
+def test_plate_out_of_plane_matches_rotated_in_plane_element(built):
+    # an element whose nodes do not share one z is evaluated in the local frame of its first three nodes and rotated
+    # back (geom_elem.cpp:358-374, 461-511; structural_element_base.cpp:1565-1674): rigidly rotating the reference's
+    # fixture must rotate every nodal 6x6 block and the force with it, f' = Q6 f, K'_ab = Q6 K_ab Q6^T
+    rng = np.random.default_rng(7)
+    xy = np.array([[-1.0, -1.0, 0.0], [1.1, -0.9, 0.0], [0.9, 1.2, 0.0], [-1.2, 0.8, 0.0]])
+    p0 = _plate_single(xy)
+    X0 = O.state(p0.n_dof, 3)
+    f0, K0 = p0.elem_calculations(0, X0)
+    A = rng.normal(size=(3, 3))
+    Q, _ = np.linalg.qr(A)
+    if np.linalg.det(Q) < 0:
+        Q[:, 0] *= -1
+    p1 = _plate_single(xy @ Q.T + np.array([0.3, -0.2, 0.7]))
+    assert np.ptp(p1.xyz[:, 2]) > 0.1
+    X1 = (X0.reshape(4, 2, 3) @ Q.T).reshape(-1)          # node-major state: translations and rotations rotate alike
+    f1, K1 = p1.elem_calculations(0, X1)
+    Q6 = np.kron(np.eye(2), Q)
+    el = lambda a: np.array([v * 4 + a for v in range(6)])   # element (variable-major) dofs of node a
+    for a in range(4):
+        assert np.abs(f1[el(a)] - Q6 @ f0[el(a)]).max() <= 1e-10 * np.abs(f0).max()
+        for b in range(4):
+            Kab = K0[np.ix_(el(a), el(b))]
+            assert np.abs(K1[np.ix_(el(a), el(b))] - Q6 @ Kab @ Q6.T).max() <= 1e-10 * np.abs(K0).max()
+
+
 def test_plate_closed_forms(built):
     # uniform membrane stretch u = e x: N_x = A11 e, N_y = A12 e; pure twist-free bending theta_y = k x: M = D k (off = 0)
     xyz, conn = mesh.build_square(3, 2, 1.5, 1.0)
