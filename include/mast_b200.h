@@ -46,7 +46,7 @@ extern "C" {
 /* element types (libMesh node ordering) */
 #define MASTB200_HEX8 8
 #define MASTB200_HEX27 27
-#define MASTB200_QUAD4 4 /* in the xy-plane: nv = 1 heat conduction, nv = 6 Mindlin plate */
+#define MASTB200_QUAD4 4 /* nv = 1 heat conduction (xy-plane), nv = 6 Mindlin plate (anywhere in space) */
 
 typedef struct mastb200_context mastb200_context;
 
