@@ -93,6 +93,13 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
  *      src/heat_conduction/heat_conduction_elem_base.cpp:876-914, 1100-1155 (dispatch :428-483) */
 int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
                                  const double* heat_flux, const double* conv_coeff, const double* T_amb);
+/* The same with SURFACE_RADIATION_HEAT_FLUX: emissivity per entry (NULL: none), Stefan-Boltzmann constant and the
+ * reference-zero temperature of the boundary condition; the entry's T_amb is the radiation's ambient temperature.
+ * f += JxW N th sb eps ((T + T0)^4 - (T_amb + T0)^4), jac += JxW N N^T th sb eps 4 (T + T0)^3.
+ *   <- HeatConductionElementBase::surface_radiation_residual, heat_conduction_elem_base.cpp:1404-1458 */
+int mastb200_set_heat_side_loads_ex(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                                    const double* heat_flux, const double* conv_coeff, const double* T_amb,
+                                    const double* emissivity, double sb_const, double T_ref_zero);
 /* TEMPERATURE volume load: nodal field [h|d] (or NULL => constant), reference temperature. enable=0 clears. */
 int mastb200_set_temperature(mastb200_context* ctx, int32_t enable, const double* T_nodal, double T_const,
                              double T_ref);

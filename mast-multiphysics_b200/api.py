@@ -15,7 +15,7 @@ HEX8, HEX27, QUAD4 = 8, 27, 4
 
 EXPORTED_SYMBOLS = [
     "mastb200_create", "mastb200_destroy", "mastb200_last_error", "mastb200_version", "mastb200_set_mesh",
-    "mastb200_set_dof_map", "mastb200_set_material", "mastb200_set_side_pressure", "mastb200_set_heat_side_loads", "mastb200_set_temperature",
+    "mastb200_set_dof_map", "mastb200_set_material", "mastb200_set_side_pressure", "mastb200_set_heat_side_loads", "mastb200_set_heat_side_loads_ex", "mastb200_set_temperature",
     "mastb200_set_density", "mastb200_build_pattern", "mastb200_get_pattern", "mastb200_get_row_dofs",
     "mastb200_residual_and_jacobian", "mastb200_res_l2_norm", "mastb200_sensitivity_sweep",
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
@@ -79,6 +79,7 @@ def load_library():
     lib.mastb200_set_material.argtypes = [vp, C.POINTER(Material)]
     lib.mastb200_set_side_pressure.argtypes = [vp, i64, vp, vp, vp]
     lib.mastb200_set_heat_side_loads.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.mastb200_set_heat_side_loads_ex.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, dbl, dbl]
     lib.mastb200_set_temperature.argtypes = [vp, i32, vp, dbl, dbl]
     lib.mastb200_set_density.argtypes = [vp, vp]
     lib.mastb200_build_pattern.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
@@ -177,11 +178,14 @@ class Context:
         elem = _np(elem, np.int32); side = _np(side, np.int32); pressure = _np(pressure, np.float64)
         self._ck(self._lib.mastb200_set_side_pressure(self._h, len(elem), _ptr(elem), _ptr(side), _ptr(pressure)))
 
-    def set_heat_side_loads(self, elem, side, heat_flux=None, conv_coeff=None, T_amb=None):
+    def set_heat_side_loads(self, elem, side, heat_flux=None, conv_coeff=None, T_amb=None, emissivity=None,
+                            sb_const=0.0, T_ref_zero=0.0):
+        """HEAT_FLUX / CONVECTION_HEAT_FLUX / SURFACE_RADIATION_HEAT_FLUX on (element, side) entries of a QUAD4 mesh."""
         elem = _np(elem, np.int32); side = _np(side, np.int32)
-        self._ck(self._lib.mastb200_set_heat_side_loads(self._h, len(elem), _ptr(elem), _ptr(side),
-                                                        _ptr(_np(heat_flux, np.float64)), _ptr(_np(conv_coeff, np.float64)),
-                                                        _ptr(_np(T_amb, np.float64))))
+        self._ck(self._lib.mastb200_set_heat_side_loads_ex(
+            self._h, len(elem), _ptr(elem), _ptr(side), _ptr(_np(heat_flux, np.float64)),
+            _ptr(_np(conv_coeff, np.float64)), _ptr(_np(T_amb, np.float64)), _ptr(_np(emissivity, np.float64)),
+            float(sb_const), float(T_ref_zero)))
 
     def set_temperature(self, enable, T_nodal=None, T_const=0.0, T_ref=0.0):
         self._keep["T"] = T_nodal

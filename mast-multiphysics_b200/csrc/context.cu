@@ -160,6 +160,7 @@ struct mastb200_context {
   DevBuf<int32_t> d_hs_ptr, d_hs_side;
   DevBuf<double> d_hs_val;
   bool have_heat_sides = false;
+  double rad_sbc = 0., rad_T0 = 0.;  // SURFACE_RADIATION_HEAT_FLUX parameters of the heat side loads
   // dv map staging
   DevBuf<int64_t> d_dv_ptr;
   DevBuf<int32_t> d_dv_node;
@@ -457,7 +458,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
     p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
     p.k0 = m.k0; p.k_beta = m.k_beta; p.thickness = m.thickness; p.heat_source = m.heat_source; p.k_of_T = m.k_of_T;
-    if (ctx->have_heat_sides) { p.sl_ptr = ctx->d_hs_ptr.p; p.sl_side = ctx->d_hs_side.p; p.sl_val = ctx->d_hs_val.p; }
+    if (ctx->have_heat_sides) { p.sl_ptr = ctx->d_hs_ptr.p; p.sl_side = ctx->d_hs_side.p; p.sl_val = ctx->d_hs_val.p; p.rad_sbc = ctx->rad_sbc; p.rad_T0 = ctx->rad_T0; }
     CU(launch_quad4_heat(p, ctx->stream));
     ctx->launches++;
   } else {
@@ -1046,6 +1047,12 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
 
 int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
                                  const double* heat_flux, const double* conv_coeff, const double* T_amb) {
+  return mastb200_set_heat_side_loads_ex(ctx, n, elem, side, heat_flux, conv_coeff, T_amb, nullptr, 0., 0.);
+}
+
+int mastb200_set_heat_side_loads_ex(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                                    const double* heat_flux, const double* conv_coeff, const double* T_amb,
+                                    const double* emissivity, double sb_const, double T_ref_zero) {
   if (!ctx) return MASTB200_ERR_ARG;
   if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
   ctx->have_heat_sides = false;
@@ -1064,16 +1071,18 @@ int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t
     return elem[a] != elem[b] ? elem[a] < elem[b] : side[a] < side[b];
   });
   std::vector<int32_t> ptr(ctx->n_elem + 1, 0), sd(n);
-  std::vector<double> val(n * 3);
+  std::vector<double> val(n * 4);
   for (int64_t i = 0; i < n; ++i) ptr[elem[i] + 1]++;
   for (int64_t e = 0; e < ctx->n_elem; ++e) ptr[e + 1] += ptr[e];
   for (int64_t k = 0; k < n; ++k) {
     const int64_t i = order[k];
     sd[k] = side[i];
-    val[k * 3] = heat_flux ? heat_flux[i] : 0.;
-    val[k * 3 + 1] = conv_coeff ? conv_coeff[i] : 0.;
-    val[k * 3 + 2] = T_amb ? T_amb[i] : 0.;
+    val[k * 4] = heat_flux ? heat_flux[i] : 0.;
+    val[k * 4 + 1] = conv_coeff ? conv_coeff[i] : 0.;
+    val[k * 4 + 2] = T_amb ? T_amb[i] : 0.;
+    val[k * 4 + 3] = emissivity ? emissivity[i] : 0.;
   }
+  ctx->rad_sbc = sb_const; ctx->rad_T0 = T_ref_zero;
   CU(ctx->d_hs_ptr.upload(ptr, ctx->stream));
   CU(ctx->d_hs_side.upload(sd, ctx->stream));
   CU(ctx->d_hs_val.upload(val, ctx->stream));

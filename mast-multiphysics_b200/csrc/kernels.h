@@ -79,7 +79,8 @@ struct GatherParams {
   // heat side loads per element (CSR over elements): side, HEAT_FLUX value, CONVECTION_HEAT_FLUX coefficient, T_ambient
   const int32_t* sl_ptr = nullptr;       // [n_elem+1] or null (no side loads)
   const int32_t* sl_side = nullptr;
-  const double* sl_val = nullptr;        // [n_entries][3]: flux, h_c, T_amb
+  const double* sl_val = nullptr;        // [n_entries][4]: flux, h_c, T_amb, emissivity
+  double rad_sbc = 0., rad_T0 = 0.;      // Stefan-Boltzmann constant, reference-zero temperature (radiation)
 };
 cudaError_t launch_quad4_heat(const GatherParams& p, cudaStream_t stream);
 

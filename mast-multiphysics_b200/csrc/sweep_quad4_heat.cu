@@ -113,14 +113,14 @@ __global__ void __launch_bounds__(TB) quad4_heat_kernel(const GatherParams p) {
       jxw[q] = JxW; Na[q] = N[a];
     }
     if (p.sl_ptr) {
-      // HeatConductionElementBase::surface_flux_residual / surface_convection_residual
-      // (/root/reference/src/heat_conduction/heat_conduction_elem_base.cpp:876-914, 1100-1155) on the loaded sides of
+      // HeatConductionElementBase::surface_flux_residual / surface_convection_residual / surface_radiation_residual
+      // (/root/reference/src/heat_conduction/heat_conduction_elem_base.cpp:876-914, 1100-1155, 1404-1458) on the loaded sides of
       // this element that hold the row node: EDGE2 with the 2-point Gauss rule, f += JxW N_a th (flux + h_c (T - T_amb)),
       // K_ab += JxW N_a N_b th h_c
       for (int k = p.sl_ptr[e]; k < p.sl_ptr[e + 1]; ++k) {
         const int sd = p.sl_side[k], n1 = sd, n2 = (sd + 1) & 3;
         if (a != n1 && a != n2) continue;
-        const double flux = p.sl_val[k * 3], hc = p.sl_val[k * 3 + 1], Tamb = p.sl_val[k * 3 + 2];
+        const double flux = p.sl_val[k * 4], hc = p.sl_val[k * 4 + 1], Tamb = p.sl_val[k * 4 + 2], eps = p.sl_val[k * 4 + 3];
         const double ex = x[n2] - x[n1], ey = y[n2] - y[n1];
         const double JxWs = 0.5 * sqrt(ex * ex + ey * ey);
 #pragma unroll
@@ -136,6 +136,15 @@ __global__ void __launch_bounds__(TB) quad4_heat_kernel(const GatherParams p) {
           if (p.J && hc != 0.) {
             K[n1] += JxWs * (Nrow * N1) * p.thickness * hc;
             K[n2] += JxWs * (Nrow * N2) * p.thickness * hc;
+          }
+          if (eps != 0.) {  // ::surface_radiation_residual (:1404-1458)
+            const double tz = temp + p.rad_T0, az = Tamb + p.rad_T0;
+            if (p.R) f += JxWs * Nrow * p.rad_sbc * eps * p.thickness * (tz * tz * tz * tz - az * az * az * az);
+            if (p.J) {
+              const double d = p.rad_sbc * eps * p.thickness * 4. * (tz * tz * tz);
+              K[n1] += JxWs * (Nrow * N1) * d;
+              K[n2] += JxWs * (Nrow * N2) * d;
+            }
           }
         }
       }

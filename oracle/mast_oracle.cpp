@@ -815,7 +815,7 @@ static void plate_elem_calculations(const OracleProblem* p, const double* X, con
 // MAST::FEBase::init_for_side, fe_base.cpp:137-204): f += JxW N th flux ; f += JxW N th h_c (T - T_amb),
 // jac += JxW N N^T th h_c.  th = section thickness (solid_2d_section_element_property_card: "h").
 static void heat_side_residual(const OracleProblem* p, const double* X, const Vec& sol, int side, double flux, double hc,
-                               double Tamb, bool request_jacobian, Vec& f, Mat& jac) {
+                               double Tamb, double emiss, bool request_jacobian, Vec& f, Mat& jac) {
   const int n1 = side, n2 = (side + 1) % 4;
   const double dx = X[n2 * 3] - X[n1 * 3], dy = X[n2 * 3 + 1] - X[n1 * 3 + 1], dz = X[n2 * 3 + 2] - X[n1 * 3 + 2];
   const double L = std::sqrt(dx * dx + dy * dy + dz * dz);
@@ -829,6 +829,15 @@ static void heat_side_residual(const OracleProblem* p, const double* X, const Ve
       if (hc != 0.) f[nd[a]] += JxW * N[a] * p->thickness * hc * (temp - Tamb);
       if (request_jacobian && hc != 0.)
         for (int b = 0; b < 2; ++b) jac(nd[a], nd[b]) += JxW * (N[a] * N[b]) * p->thickness * hc;
+      if (emiss != 0.) {
+        // ::surface_radiation_residual (heat_conduction_elem_base.cpp:1404-1458):
+        // f += JxW phi sbc emiss th ((T + zero_ref)^4 - (T_amb + zero_ref)^4), jac += JxW phi phi^T sbc emiss th 4 (T + zero_ref)^3
+        f[nd[a]] += JxW * N[a] * p->rad_sb_const * emiss * p->thickness *
+                    (std::pow(temp + p->rad_T_ref_zero, 4.) - std::pow(Tamb + p->rad_T_ref_zero, 4.));
+        if (request_jacobian)
+          for (int b = 0; b < 2; ++b)
+            jac(nd[a], nd[b]) += JxW * (N[a] * N[b]) * p->rad_sb_const * emiss * p->thickness * 4. * std::pow(temp + p->rad_T_ref_zero, 3.);
+      }
     }
   }
 }
@@ -957,7 +966,7 @@ static void elem_calculations(const OracleProblem* p, const SideLoadIndex& sl, i
       for (int64_t k = sl.ptr[e]; k < sl.ptr[e + 1]; ++k) {
         const int64_t l = sl.idx[k];
         heat_side_residual(p, X.data(), sol, sl.side[k], sl.press[k], p->side_conv_coeff ? p->side_conv_coeff[l] : 0.,
-                           p->side_T_amb ? p->side_T_amb[l] : 0., if_jac, vec, mat);
+                           p->side_T_amb ? p->side_T_amb[l] : 0., p->side_emissivity ? p->side_emissivity[l] : 0., if_jac, vec, mat);
       }
     }
     return;

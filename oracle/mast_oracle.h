@@ -63,6 +63,10 @@ typedef struct OracleProblem {
    * these two the CONVECTION_HEAT_FLUX coefficient and ambient temperature per entry (NULL: none) */
   const double* side_conv_coeff;
   const double* side_T_amb;
+  /* SURFACE_RADIATION_HEAT_FLUX on the same entries: emissivity per entry (NULL: none; side_T_amb is its ambient
+   * temperature), Stefan-Boltzmann constant and reference-zero temperature of the boundary condition */
+  const double* side_emissivity;
+  double rad_sb_const, rad_T_ref_zero;
 } OracleProblem;
 
 /* libMesh-style sparsity: every (row,col) pair of dofs that share an element; columns sorted.

@@ -20,6 +20,7 @@ class OracleProblem(C.Structure):
         ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32), ("heat_source", C.c_double),
         ("offset", C.c_double), ("kappa", C.c_double), ("plane_strain", C.c_int32),
         ("side_conv_coeff", C.c_void_p), ("side_T_amb", C.c_void_p),
+        ("side_emissivity", C.c_void_p), ("rad_sb_const", C.c_double), ("rad_T_ref_zero", C.c_double),
     ]
 
 
@@ -64,7 +65,8 @@ class Problem:
     def __init__(self, elem_type, xyz, conn, nv, constrained=None, E0=72e9, nu=0.33, alpha=0.0, rho=None,
                  rho_min=0.0, penalty=1.0, nonlinear_strain=0, side_elem=None, side_id=None, side_pressure=None,
                  thermal=0, temperature=None, temperature_const=0.0, ref_temperature=0.0, k0=0.0, k_beta=0.0,
-                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None, offset=0.0, kappa=5.0 / 6.0, plane_strain=0, side_conv_coeff=None, side_T_amb=None):
+                 thickness=1.0, k_of_T=0, heat_source=0.0, diag_elem=None, offset=0.0, kappa=5.0 / 6.0, plane_strain=0, side_conv_coeff=None, side_T_amb=None,
+                 side_emissivity=None, rad_sb_const=0.0, rad_T_ref_zero=0.0):
         self.elem_type = elem_type
         self.xyz = np.ascontiguousarray(xyz, np.float64)
         self.conn = np.ascontiguousarray(conn, np.int32)
@@ -97,6 +99,9 @@ class Problem:
         self.side_conv_coeff = None if side_conv_coeff is None else np.ascontiguousarray(side_conv_coeff, np.float64)
         self.side_T_amb = None if side_T_amb is None else np.ascontiguousarray(side_T_amb, np.float64)
         s.side_conv_coeff = _p(self.side_conv_coeff); s.side_T_amb = _p(self.side_T_amb)
+        self.side_emissivity = None if side_emissivity is None else np.ascontiguousarray(side_emissivity, np.float64)
+        self.rad_sb_const, self.rad_T_ref_zero = rad_sb_const, rad_T_ref_zero
+        s.side_emissivity = _p(self.side_emissivity); s.rad_sb_const = rad_sb_const; s.rad_T_ref_zero = rad_T_ref_zero
         self.s = s
         self._pattern = None
 
@@ -187,7 +192,7 @@ class Problem:
             if self.side_elem is not None:
                 if self.elem_type == QUAD4 and self.nv == 1:
                     ctx.set_heat_side_loads(self.side_elem, self.side_id, self.side_pressure, self.side_conv_coeff,
-                                            self.side_T_amb)
+                                            self.side_T_amb, self.side_emissivity, self.rad_sb_const, self.rad_T_ref_zero)
                 else:
                     ctx.set_side_pressure(self.side_elem, self.side_id, self.side_pressure)
             if self.thermal:

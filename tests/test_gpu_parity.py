@@ -560,3 +560,31 @@ def test_quad4_heat_flux_and_convection_side_loads(built):
                           heat_source=1.0e4)
         R0, J0 = plain.residual_and_jacobian(T)
         assert np.abs(R - R0).max() > 1e-3 * np.abs(R0).max() and np.abs(J - J0).max() > 0  # the loads are there
+
+
+def test_quad4_heat_surface_radiation_side_loads(built):
+    # SURFACE_RADIATION_HEAT_FLUX (heat_conduction_elem_base.cpp:1404-1458) on the top edge (side 2), together with
+    # convection on the right edge and a flux entry that shares a side with a radiation entry
+    nx, ny = 12, 7
+    xyz, conn = mesh.build_square(nx, ny, 1.2, 0.7)
+    rng = np.random.default_rng(4)
+    inner = (xyz[:, 0] > 0) & (xyz[:, 0] < 1.2) & (xyz[:, 1] > 0) & (xyz[:, 1] < 0.7)
+    xyz[inner, :2] += 0.02 * rng.uniform(-1, 1, (inner.sum(), 2))
+    con = np.isclose(xyz[:, 0], 0.0).astype(np.uint8)
+    top = (np.arange(nx, dtype=np.int32) + (ny - 1) * nx)        # elements j = ny-1, side 2
+    right = (np.arange(ny, dtype=np.int32) * nx + nx - 1)        # elements i = nx-1, side 1
+    se = np.concatenate([top, right, top[:4]])
+    sid = np.concatenate([np.full(nx, 2, np.int32), np.ones(ny, np.int32), np.full(4, 2, np.int32)])
+    flux = np.concatenate([np.zeros(nx), np.zeros(ny), np.full(4, 3.0e2)])
+    hc = np.concatenate([np.zeros(nx), np.full(ny, 35.0), np.zeros(4)])
+    Tamb = np.concatenate([np.full(nx, 3.0), np.full(ny, 290.0), np.zeros(4)])
+    eps = np.concatenate([0.6 + 0.3 * rng.uniform(size=nx), np.zeros(ny), np.zeros(4)])
+    kw = dict(constrained=con, k0=237.0, k_beta=1e-3, k_of_T=1, thickness=0.06, heat_source=1.0e4)
+    prob = O.Problem(O.QUAD4, xyz, conn, 1, side_elem=se, side_id=sid, side_pressure=flux, side_conv_coeff=hc,
+                     side_T_amb=Tamb, side_emissivity=eps, rad_sb_const=5.670374419e-8, rad_T_ref_zero=273.15, **kw)
+    T = _temperature(prob.n_dof)
+    ctx, R, J = _check_RJ(prob, T)
+    norad = O.Problem(O.QUAD4, xyz, conn, 1, side_elem=se, side_id=sid, side_pressure=flux, side_conv_coeff=hc,
+                      side_T_amb=Tamb, **kw)
+    R0, J0 = norad.residual_and_jacobian(T)
+    assert np.abs(R - R0).max() > 1e-6 * np.abs(R0).max() and np.abs(J - J0).max() > 0  # the radiation is there

@@ -276,3 +276,31 @@ def test_plate_closed_forms(built):
     # cylindrical bending (kappa_y = 0): M_x = D11 k per unit width; w is quadratic so the one-point shear strain
     # gamma_xz = dw/dx + theta_y is not identically zero on distorted cells -- compare on the moment resultant only
     assert np.isclose(My, D11 * k * 1.0, rtol=5e-2)
+
+
+def test_heat_surface_radiation_jacobian_is_the_derivative_of_the_residual(built):
+    # HeatConductionElementBase::surface_radiation_residual (heat_conduction_elem_base.cpp:1404-1458): the Jacobian term
+    # 4 sb eps th (T + T0)^3 N N^T against central differences of the residual; zero flux at T == T_amb
+    xyz = np.array([[0.0, 0.0, 0.0], [1.3, 0.1, 0.0], [1.2, 0.9, 0.0], [-0.1, 1.0, 0.0]])
+    conn = np.array([[0, 1, 2, 3]], np.int32)
+    kw = dict(k0=0.0, thickness=0.06, side_elem=np.array([0], np.int32), side_id=np.array([2], np.int32),
+              side_pressure=np.zeros(1), side_T_amb=np.array([300.0]), side_emissivity=np.array([0.8]),
+              rad_sb_const=5.670374419e-8, rad_T_ref_zero=0.0)
+    p = O.Problem(O.QUAD4, xyz, conn, 1, **kw)
+    T = np.array([310.0, 350.0, 420.0, 390.0])
+    f0, K = p.elem_calculations(0, T)
+    assert np.all(K[[0, 1]] == 0.0) and np.all(f0[[0, 1]] == 0.0)      # only the nodes of side 2 (nodes 2, 3)
+    h = 1e-3
+    Kfd = np.zeros((4, 4))
+    for j in range(4):
+        Tp = T.copy(); Tp[j] += h
+        Tm = T.copy(); Tm[j] -= h
+        Kfd[:, j] = (p.elem_calculations(0, Tp, False)[0] - p.elem_calculations(0, Tm, False)[0]) / (2 * h)
+    assert np.abs(K - Kfd).max() <= 1e-7 * np.abs(K).max()
+    assert np.abs(K - K.T).max() <= 1e-14 * np.abs(K).max()
+    f_eq, _ = p.elem_calculations(0, np.full(4, 300.0))
+    assert np.abs(f_eq).max() <= 1e-9 * np.abs(f0).max()
+    # total radiated power of a uniform temperature: sb eps th L (T^4 - T_amb^4)
+    L = np.linalg.norm(xyz[3] - xyz[2])
+    f_u, _ = p.elem_calculations(0, np.full(4, 400.0))
+    assert np.isclose(f_u.sum(), 5.670374419e-8 * 0.8 * 0.06 * L * (400.0 ** 4 - 300.0 ** 4), rtol=1e-12)
