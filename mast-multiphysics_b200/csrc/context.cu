@@ -160,6 +160,10 @@ struct mastb200_context {
   DevBuf<int32_t> d_hs_ptr, d_hs_side;
   DevBuf<double> d_hs_val;
   bool have_heat_sides = false;
+  // build_square numbering of a QUAD4 heat mesh recognised (quad4_heat_struct_kernel)
+  bool q4s_tried = false, q4s_ok = false;
+  int32_t q4s_nx = 0, q4s_ny = 0;
+  bool last_q4s = false;
   double rad_sbc = 0., rad_T0 = 0.;  // SURFACE_RADIATION_HEAT_FLUX parameters of the heat side loads
   // dv map staging
   DevBuf<int64_t> d_dv_ptr;
@@ -376,6 +380,29 @@ int ensure_generic_plan(mastb200_context* ctx) {
   return MASTB200_OK;
 }
 
+// Recognises libMesh build_square numbering of a QUAD4 heat-conduction mesh (node id i + j(nx+1), element id i + j nx,
+// node order (i,j), (i+1,j), (i+1,j+1), (i,j+1)) with every node owned and no diagonal elements: the sweep then runs
+// with implicit connectivity (quad4_heat_struct_kernel).  MASTB200_NO_STRUCT=1 disables it.
+void detect_quad4_struct(mastb200_context* ctx) {
+  if (ctx->q4s_tried) return;
+  ctx->q4s_tried = true; ctx->q4s_ok = false;
+  if (ctx->elem_type != MASTB200_QUAD4 || ctx->nv != 1 || ctx->has_diag || !ctx->owned.empty() || ctx->planning_only) return;
+  if (const char* e = getenv("MASTB200_NO_STRUCT")) if (e[0] == '1') return;
+  const int32_t* c = ctx->conn.data();
+  const int64_t ne = ctx->n_elem, nn = ctx->n_nodes;
+  if (ne < 1 || c[0] != 0 || c[1] != 1) return;
+  const int64_t npx = c[3];
+  if (npx < 2 || nn % npx) return;
+  const int64_t nx = npx - 1, ny = nn / npx - 1;
+  if (ny < 1 || nx * ny != ne || nx > 2000000 || ny > 2000000) return;
+  for (int64_t e = 0; e < ne; ++e) {
+    const int64_t i = e % nx, j = e / nx, n0 = i + j * npx;
+    const int32_t* q = c + e * 4;
+    if (q[0] != n0 || q[1] != n0 + 1 || q[2] != n0 + npx + 1 || q[3] != n0 + npx) return;
+  }
+  ctx->q4s_nx = (int32_t)nx; ctx->q4s_ny = (int32_t)ny; ctx->q4s_ok = true;
+}
+
 // QUAD4 Mindlin plate (row-block gather; per-element local frames when an element is out of the xy-plane)
 int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
   int rc;
@@ -437,7 +464,10 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
   if (!heat && ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX27 elasticity needs nv = 3 or 6");
   if (!heat && ctx->mat.nonlinear_strain)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain: HEX8 only on the device path");
-  if ((rc = ensure_generic_plan(ctx))) return rc;
+  if (heat) detect_quad4_struct(ctx);
+  const bool q4s = heat && ctx->q4s_ok;
+  ctx->last_q4s = q4s;
+  if (!q4s && (rc = ensure_generic_plan(ctx))) return rc;
   mastb200_context::GenericPlan& G = ctx->gplan;
   const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
   const size_t nnz = (size_t)plan_nnz(ctx);
@@ -453,13 +483,16 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     GatherParams p;
     p.n_owned = ctx->pat.n_owned; p.owned_nodes = ctx->d_owned_nodes.p;
-    p.nbr_ptr = G.nbr_ptr.p; p.nbr = G.nbr.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p; p.conn = G.conn.p;
-    p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+    if (!q4s) {
+      p.nbr_ptr = G.nbr_ptr.p; p.nbr = G.nbr.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p; p.conn = G.conn.p;
+      p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
+    }
     p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
     p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;
     p.k0 = m.k0; p.k_beta = m.k_beta; p.thickness = m.thickness; p.heat_source = m.heat_source; p.k_of_T = m.k_of_T;
     if (ctx->have_heat_sides) { p.sl_ptr = ctx->d_hs_ptr.p; p.sl_side = ctx->d_hs_side.p; p.sl_val = ctx->d_hs_val.p; p.rad_sbc = ctx->rad_sbc; p.rad_T0 = ctx->rad_T0; }
-    CU(launch_quad4_heat(p, ctx->stream));
+    if (q4s) CU(launch_quad4_heat_struct(p, ctx->q4s_nx, ctx->q4s_ny, ctx->stream));
+    else CU(launch_quad4_heat(p, ctx->stream));
     ctx->launches++;
   } else {
     // the coloured scatter accumulates: R and J start from zero (nonlinear_implicit_assembly.cpp:81-82)
@@ -1137,6 +1170,7 @@ int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz)
   for (auto& D : ctx->dplan) D.reset();
   ctx->gplan.reset();
   ctx->splan.reset();
+  ctx->q4s_tried = false; ctx->q4s_ok = false;
   const std::string e = build_pattern(ctx->nn, ctx->n_nodes, ctx->n_elem, ctx->conn.data(),
                                       ctx->owned.empty() ? nullptr : ctx->owned.data(),
                                       ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(), ctx->pat);
@@ -1408,7 +1442,7 @@ int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   s->smem_bytes = ctx->last_struct ? (int32_t)(lm ? hex8_march_smem_bytes() : hex8_struct_smem_bytes()) : (int32_t)D.smem;
   s->threads_per_cta = ctx->last_struct ? (lm ? hex8_march_threads() : hex8_struct_threads()) : hex8_sweep_threads();
   s->ctas = ctx->last_struct ? (lm ? ctx->splan.m_n_ctas : ctx->splan.n_ctas) : D.n_ctas;
-  s->structured = ctx->last_struct ? (lm ? 2 : 1) : 0;
+  s->structured = ctx->last_struct ? (lm ? 2 : 1) : (ctx->elem_type == MASTB200_QUAD4 && ctx->last_q4s ? 1 : 0);
   if (ctx->timed) {
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a + ctx->carry_ms;

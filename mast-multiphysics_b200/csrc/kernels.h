@@ -83,6 +83,9 @@ struct GatherParams {
   double rad_sbc = 0., rad_T0 = 0.;      // Stefan-Boltzmann constant, reference-zero temperature (radiation)
 };
 cudaError_t launch_quad4_heat(const GatherParams& p, cudaStream_t stream);
+// the same sweep for build_square-numbered meshes (node i + j(nx+1), element i + j nx, every node owned, no
+// diagonal elements): implicit connectivity, every element evaluated once per CTA tile (quad4_heat_struct_kernel)
+cudaError_t launch_quad4_heat_struct(const GatherParams& p, int32_t nx, int32_t ny, cudaStream_t stream);
 
 // ---- HEX27 coloured DMMA sweep (sweep_hex27.cu) -----------------------------------------------------------------------
 struct Hex27Params {

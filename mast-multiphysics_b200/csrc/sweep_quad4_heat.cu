@@ -172,7 +172,185 @@ __global__ void __launch_bounds__(TB) quad4_heat_kernel(const GatherParams p) {
   if (p.R) p.R[n] = res;
 }
 
+// ---- build_square-numbered meshes: implicit connectivity, one evaluation per element and CTA tile -----------------------
+// CTA tile = 32 x 8 elements and the 31 x 7 nodes interior to them (plus the mesh-boundary nodes of edge tiles).
+// Element phase: thread = element -> the full element vector / matrix (4 + 16 values: conduction, k(T) tangent, heat
+// source, side loads -- the reference's elem_calculations) into shared memory, ke[value][element] (conflict-free).
+// Node phase: thread = owned node = CSR row; its <= 4 adjacent elements in ascending id (the order of the reference's
+// element loop) with libMesh's per-element Dirichlet semantics; the 9 column positions of a row are compile-time
+// constants, so the row lives in registers and is stored as one contiguous run.  Nothing but nodal state is read:
+// CSR row pointers have a closed form for a box.
+constexpr int SEX = 32, SEY = 8, SNX = SEX - 1, SNY = SEY - 1, STB = SEX * SEY;
+__device__ __forceinline__ double sel4(const double (&v)[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
+
+__global__ void __launch_bounds__(STB) quad4_heat_struct_kernel(const GatherParams p, const int nx, const int ny, const int tiles_x) {
+  __shared__ double ke[20 * STB];
+  const int tid = threadIdx.x;
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
+  const int o0x = tx * SNX, o0y = ty * SNY;  // first owned node; elements start one column / row before
+  const int npx = nx + 1;
+  {
+    const int lex = tid & (SEX - 1), ley = tid / SEX;
+    const int ex = o0x - 1 + lex, ey = o0y - 1 + ley;
+    if (ex >= 0 && ex < nx && ey >= 0 && ey < ny) {
+      const int e = ex + ey * nx;
+      const int m[4] = {ex + ey * npx, ex + 1 + ey * npx, ex + 1 + (ey + 1) * npx, ex + (ey + 1) * npx};
+      double x[4], y[4], T[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        x[b] = p.xyz[(int64_t)m[b] * 3];
+        y[b] = p.xyz[(int64_t)m[b] * 3 + 1];
+        T[b] = p.X[m[b]];
+      }
+      double f[4] = {0., 0., 0., 0.}, K[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) K[a][b] = 0.;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP;
+        const double sx[4] = {-1., 1., 1., -1.}, sy[4] = {-1., -1., 1., 1.};
+        double N[4], d0[4], d1[4];
+        double j00 = 0., j01 = 0., j10 = 0., j11 = 0.;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double fx = 0.5 * (1. + sx[b] * xi), fy = 0.5 * (1. + sy[b] * eta);
+          N[b] = fx * fy;
+          d0[b] = 0.5 * sx[b] * fy;
+          d1[b] = fx * 0.5 * sy[b];
+          j00 += d0[b] * x[b]; j01 += d0[b] * y[b];
+          j10 += d1[b] * x[b]; j11 += d1[b] * y[b];
+        }
+        const double det = j00 * j11 - j10 * j01;
+        const double inv = 1. / det;
+        const double JxW = det;
+        const double dxidx = j11 * inv, dxidy = -j10 * inv, detadx = -j01 * inv, detady = j00 * inv;
+        double gx[4], gy[4];
+        double Tq = 0., dTx = 0., dTy = 0.;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          gx[b] = d0[b] * dxidx + d1[b] * detadx;
+          gy[b] = d0[b] * dxidy + d1[b] * detady;
+          Tq += N[b] * T[b];
+          dTx += gx[b] * T[b];
+          dTy += gy[b] * T[b];
+        }
+        const double k = (p.k_of_T ? p.k0 * (1. + p.k_beta * Tq) : p.k0) * p.thickness;
+        const double dk = p.k_of_T ? p.k0 * p.k_beta * p.thickness : 0.;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          f[a] += JxW * (gx[a] * (dTx * k));
+          f[a] += JxW * (gy[a] * (dTy * k));
+          if (p.heat_source != 0.) f[a] -= JxW * N[a] * p.heat_source * p.thickness;
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            K[a][b] += JxW * k * (gx[a] * gx[b]);
+            K[a][b] += JxW * k * (gy[a] * gy[b]);
+            if (p.k_of_T) {
+              K[a][b] += JxW * dTx * dk * (gx[a] * N[b]);
+              K[a][b] += JxW * dTy * dk * (gy[a] * N[b]);
+            }
+          }
+        }
+      }
+      if (p.sl_ptr) {  // HEAT_FLUX / CONVECTION_HEAT_FLUX / SURFACE_RADIATION_HEAT_FLUX sides of this element (see above)
+        for (int k = p.sl_ptr[e]; k < p.sl_ptr[e + 1]; ++k) {
+          const int sd = p.sl_side[k], n1 = sd, n2 = (sd + 1) & 3;
+          const double flux = p.sl_val[k * 4], hc = p.sl_val[k * 4 + 1], Tamb = p.sl_val[k * 4 + 2], eps = p.sl_val[k * 4 + 3];
+          const double ex_ = sel4(x, n2) - sel4(x, n1), ey_ = sel4(y, n2) - sel4(y, n1), T1 = sel4(T, n1), T2 = sel4(T, n2);
+          const double JxWs = 0.5 * sqrt(ex_ * ex_ + ey_ * ey_);
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const double xi = q ? GP : -GP;
+            const double Ns[2] = {0.5 * (1. - xi), 0.5 * (1. + xi)};
+            const double temp = Ns[0] * T1 + Ns[1] * T2;
+            const double tz = temp + p.rad_T0, az = Tamb + p.rad_T0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              const int a = s ? n2 : n1;
+              double df = JxWs * Ns[s] * flux * p.thickness;
+              if (hc != 0.) df += JxWs * Ns[s] * p.thickness * hc * (temp - Tamb);
+              if (eps != 0.) df += JxWs * Ns[s] * p.rad_sbc * eps * p.thickness * (tz * tz * tz * tz - az * az * az * az);
+              double dK1 = 0., dK2 = 0.;
+              if (hc != 0.) { dK1 += JxWs * (Ns[s] * Ns[0]) * p.thickness * hc; dK2 += JxWs * (Ns[s] * Ns[1]) * p.thickness * hc; }
+              if (eps != 0.) {
+                const double d = p.rad_sbc * eps * p.thickness * 4. * (tz * tz * tz);
+                dK1 += JxWs * (Ns[s] * Ns[0]) * d; dK2 += JxWs * (Ns[s] * Ns[1]) * d;
+              }
+#pragma unroll
+              for (int aa = 0; aa < 4; ++aa)
+                if (aa == a) {
+                  f[aa] += df;
+#pragma unroll
+                  for (int bb = 0; bb < 4; ++bb) {
+                    if (bb == n1) K[aa][bb] += dK1;
+                    if (bb == n2) K[aa][bb] += dK2;
+                  }
+                }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        ke[a * STB + tid] = f[a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) ke[(4 + a * 4 + b) * STB + tid] = K[a][b];
+      }
+    }
+  }
+  __syncthreads();
+  const int li = tid & (SEX - 1), lj = tid / SEX;
+  const int i = o0x + li, j = o0y + lj;
+  if (li >= SNX || lj >= SNY || i > nx || j > ny) return;
+  const int n = i + j * npx;
+  const bool con_row = p.cmask && (p.cmask[n] & 1u);
+  double acc[9] = {0., 0., 0., 0., 0., 0., 0., 0., 0.};
+  double res = 0.;
+  // adjacent elements in ascending id: (i-1,j-1) holds the node as its local node 2, (i,j-1) as 3, (i-1,j) as 1, (i,j) as 0
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int dx = (c & 1) - 1, dy = (c >> 1) - 1;  // element (i + dx, j + dy)
+    const int a = c == 0 ? 2 : (c == 1 ? 3 : (c == 2 ? 1 : 0));
+    if (i + dx < 0 || i + dx >= nx || j + dy < 0 || j + dy >= ny) continue;
+    const double* k = ke + (lj + 1 + dy) * SEX + (li + 1 + dx);
+    if (p.R) res += con_row ? 0. : k[a * STB];
+    if (p.J) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int bx = dx + ((b == 1 || b == 2) ? 1 : 0), by = dy + (b >= 2 ? 1 : 0);  // neighbour offset of local node b
+        double v = k[(4 + a * 4 + b) * STB];
+        const bool con_col = p.cmask && (p.cmask[n + bx + by * npx] & 1u);
+        if (con_row || con_col) v = (b == a && con_row) ? 1. : 0.;
+        acc[(by + 1) * 3 + bx + 1] += v;
+      }
+    }
+  }
+  if (p.J) {
+    // node-level CSR row pointer of a box: rows in node order with xcnt*ycnt neighbours each
+    const int x0f = i == 0 ? 1 : 0, y0f = j == 0 ? 1 : 0;
+    const int xcnt = 3 - x0f - (i == nx ? 1 : 0), ycnt = 3 - y0f - (j == ny ? 1 : 0);
+    const int64_t SX = 3 * (int64_t)nx + 1, py = 3 * (int64_t)j - (j > 0 ? 1 : 0), px = 3 * (int64_t)i - (i > 0 ? 1 : 0);
+    double* dst = p.J + SX * py + ycnt * px;
+#pragma unroll
+    for (int by = 0; by < 3; ++by)
+#pragma unroll
+      for (int bx = 0; bx < 3; ++bx) {
+        const bool on = i + bx - 1 >= 0 && i + bx - 1 <= nx && j + by - 1 >= 0 && j + by - 1 <= ny;
+        if (on) *dst++ = acc[by * 3 + bx];
+      }
+  }
+  if (p.R) p.R[n] = res;
+}
+
 }  // namespace
+
+cudaError_t launch_quad4_heat_struct(const GatherParams& p, int32_t nx, int32_t ny, cudaStream_t stream) {
+  const int tiles_x = (nx + 1 + SNX - 1) / SNX, tiles_y = (ny + 1 + SNY - 1) / SNY;
+  quad4_heat_struct_kernel<<<tiles_x * tiles_y, STB, 0, stream>>>(p, nx, ny, tiles_x);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_quad4_heat(const GatherParams& p, cudaStream_t stream) {
   const int blocks = (int)((p.n_owned + TB - 1) / TB);

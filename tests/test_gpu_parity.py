@@ -241,9 +241,24 @@ def test_quad4_heat_residual_and_jacobian(built, k_of_T):
     _check_RJ(prob, T, want_J=False)
 
 
+@pytest.mark.parametrize("shape", [(1, 1), (2, 5), (30, 6), (31, 7), (32, 8), (63, 15), (70, 3)])
+def test_quad4_heat_implicit_connectivity_kernel(built, shape, monkeypatch):
+    # build_square numbering is recognised (every node owned, no diagonal elements) and takes quad4_heat_struct_kernel:
+    # parity with the oracle, and agreement with the gather kernel on the same inputs
+    prob = _heat_problem(*shape, k_of_T=1, jitter=0.2 if min(shape) > 1 else 0.0, source=2.0e3)
+    T = _temperature(prob.n_dof)
+    ctx, R, J = _check_RJ(prob, T)
+    assert ctx.stats()["structured"] == 1
+    monkeypatch.setenv("MASTB200_NO_STRUCT", "1")
+    ctx2, R2, J2 = _check_RJ(prob, T)
+    assert ctx2.stats()["structured"] == 0
+    _close(R, R2); _close(J, J2)
+
+
 def test_quad4_heat_diag_elems_and_unstructured_numbering(built):
     prob = _heat_problem(9, 7, diag=True)
-    _check_RJ(prob, _temperature(prob.n_dof))
+    ctx, _, _ = _check_RJ(prob, _temperature(prob.n_dof))
+    assert ctx.stats()["structured"] == 0
     rng = np.random.default_rng(0)
     xyz, conn = mesh.build_square(11, 8)
     perm = rng.permutation(len(xyz))
