@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TB) quad4_heat_kernel(const GatherParams p) {
 constexpr int SEX = 32, SEY = 8, SNX = SEX - 1, SNY = SEY - 1, STB = SEX * SEY;
 __device__ __forceinline__ double sel4(const double (&v)[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
 
-__global__ void __launch_bounds__(STB) quad4_heat_struct_kernel(const GatherParams p, const int nx, const int ny, const int tiles_x) {
+__global__ void __launch_bounds__(STB, 3) quad4_heat_struct_kernel(const GatherParams p, const int nx, const int ny, const int tiles_x) {
   __shared__ double ke[20 * STB];
   const int tid = threadIdx.x;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
@@ -202,11 +202,11 @@ __global__ void __launch_bounds__(STB) quad4_heat_struct_kernel(const GatherPara
         y[b] = p.xyz[(int64_t)m[b] * 3 + 1];
         T[b] = p.X[m[b]];
       }
-      double f[4] = {0., 0., 0., 0.}, K[4][4];
+      double f[4] = {0., 0., 0., 0.}, K[4][4], Kt[4][4];
 #pragma unroll
       for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) K[a][b] = 0.;
+        for (int b = 0; b < 4; ++b) { K[a][b] = 0.; Kt[a][b] = 0.; }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP;
@@ -238,22 +238,37 @@ __global__ void __launch_bounds__(STB) quad4_heat_struct_kernel(const GatherPara
         }
         const double k = (p.k_of_T ? p.k0 * (1. + p.k_beta * Tq) : p.k0) * p.thickness;
         const double dk = p.k_of_T ? p.k0 * p.k_beta * p.thickness : 0.;
+        // the element is fp64-pipe-bound: weights folded into the row gradients, so that a matrix entry costs two FMAs for
+        // the conduction part (upper triangle only, k grad N_a . grad N_b is symmetric) and one for the k(T) tangent
+        const double w = JxW * k, ws = JxW * p.heat_source * p.thickness;
+        const double wt = JxW * dk;
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
-          f[a] += JxW * (gx[a] * (dTx * k));
-          f[a] += JxW * (gy[a] * (dTy * k));
-          if (p.heat_source != 0.) f[a] -= JxW * N[a] * p.heat_source * p.thickness;
+          const double wgx = w * gx[a], wgy = w * gy[a];
+          f[a] = fma(wgx, dTx, f[a]);
+          f[a] = fma(wgy, dTy, f[a]);
+          if (p.heat_source != 0.) f[a] = fma(-ws, N[a], f[a]);
 #pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            K[a][b] += JxW * k * (gx[a] * gx[b]);
-            K[a][b] += JxW * k * (gy[a] * gy[b]);
-            if (p.k_of_T) {
-              K[a][b] += JxW * dTx * dk * (gx[a] * N[b]);
-              K[a][b] += JxW * dTy * dk * (gy[a] * N[b]);
-            }
+          for (int b = a; b < 4; ++b) K[a][b] = fma(wgy, gy[b], fma(wgx, gx[b], K[a][b]));
+          if (p.k_of_T) {
+            const double tg = wt * (dTx * gx[a] + dTy * gy[a]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) Kt[a][b] = fma(tg, N[b], Kt[a][b]);
           }
         }
       }
+      // full matrix: symmetric conduction part + tangent
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double sym = a <= b ? K[a][b] : K[b][a];
+          Kt[a][b] += sym;
+        }
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) K[a][b] = Kt[a][b];
       if (p.sl_ptr) {  // HEAT_FLUX / CONVECTION_HEAT_FLUX / SURFACE_RADIATION_HEAT_FLUX sides of this element (see above)
         for (int k = p.sl_ptr[e]; k < p.sl_ptr[e + 1]; ++k) {
           const int sd = p.sl_side[k], n1 = sd, n2 = (sd + 1) & 3;
