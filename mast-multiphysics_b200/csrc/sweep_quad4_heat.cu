@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TB) quad4_heat_kernel(const GatherParams p) {
 constexpr int SEX = 32, SEY = 8, SNX = SEX - 1, SNY = SEY - 1, STB = SEX * SEY;
 __device__ __forceinline__ double sel4(const double (&v)[4], int i) { return i == 0 ? v[0] : (i == 1 ? v[1] : (i == 2 ? v[2] : v[3])); }
 
-__global__ void __launch_bounds__(STB, 3) quad4_heat_struct_kernel(const GatherParams p, const int nx, const int ny, const int tiles_x) {
+__global__ void __launch_bounds__(STB) quad4_heat_struct_kernel(const GatherParams p, const int nx, const int ny, const int tiles_x) {
   __shared__ double ke[20 * STB];
   const int tid = threadIdx.x;
   const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x;
