@@ -7,24 +7,29 @@
 // isotropic D of src/property_cards/isotropic_material_property_card.cpp:512-528 -- with a different division of
 // labour: the pair blocks S_AB = sum_e sum_q JxW E grad N_A (x) grad N_B never pass through shared-memory accumulators.
 //
-// A work unit is a column of <= 16 x 4 owned nodes over a z-range; the CTA (8 warps) sweeps it element plane by element
+// A work unit is a column of <= 16 x 4 owned nodes over a z-range; the CTA (16 warps) sweeps it element plane by element
 // plane (e = node planes e and e+1).  Per plane:
 //   geometry : item = (element, qp) of the <= 17 x 5 elements touching the owned nodes: J^-1, JxW E (constant or SIMP
 //              modulus of the interpolated nodal density) and the eight physical gradients scaled by sqrt(JxW E) go to a
-//              shared-memory table tab[qp][node][component][element] (element innermost: lanes = consecutive nodes read
-//              consecutive elements, conflict-free).  Elements outside the mesh get zeros, so the march needs no tests.
-//   march    : thread = (owned node column A, type).  The 9 in-plane directions A -> B of a column are dealt to four
-//              thread types so that each has four (element column, direction) visits per plane: centre | x-edges |
-//              y-edges | corners.  A visit adds, for the eight qps, the four 3x3 blocks between {A_e, A_e+1} and
-//              {B_e, B_e+1} into 36 REGISTER accumulators (12 shared loads per 36 DFMA).  When the last element column of
-//              a direction is done the finished blocks -- row A_e: dz = 0, +1; row A_e+1: dz = -1 -- become
-//              K_AB = lam S + mu S^T + mu tr(S) I with libMesh's per-element Dirichlet semantics and are stored, every
-//              CSR value exactly once; the half-finished block (A_e+1, B_e+1) is carried to the next plane through shared
-//              memory.  Force partials f_A += K_AB u_B per (node, direction) are kept in shared memory and summed over the
-//              nine directions in fixed order by the centre threads after the plane.  K_e is never formed.
+//              shared-memory table tab[qp][xy-corner][component][element][z-corner] (element innermost: lanes =
+//              consecutive nodes read consecutive elements, conflict-free 16-byte loads of a (bottom, top) corner pair).
+//              Elements outside the mesh get zeros, so the march needs no tests.
+//   march    : thread = (owned node column A, type, half).  The 9 in-plane directions A -> B of a column are dealt to four
+//              warp-uniform thread types so that each has four (element column, direction) visits per plane: centre |
+//              the three directions towards column x-1 | towards x+1 | the two y-edges.  Half h pairs {A_e, A_e+1} with
+//              B_e+h; a visit adds, for the eight qps, two 3x3 blocks into 18 REGISTER accumulators (6 shared loads per
+//              18 DFMA).  When the last element column of a direction is done the finished blocks -- row A_e: dz = 0
+//              (half 0), +1 (half 1); row A_e+1: dz = -1 (half 0) -- become K_AB = lam S + mu S^T + mu tr(S) I with
+//              libMesh's per-element Dirichlet semantics and are stored, every CSR value exactly once; the half-finished
+//              block (A_e+1, B_e+1) of half 1 is carried to the next plane through shared memory.  Force partials
+//              f_A += K_AB u_B of the two halves are joined by one shuffle, kept per (node, direction) in shared memory and
+//              summed over the nine directions in fixed order by the centre threads after the next barrier.  K_e is never
+//              formed.  CSR row pointers of a box have a closed form, so nothing but nodal state is read.
 // Summation order of a CSR value: element planes ascending, element columns in the visit order of the direction
 // (y-major), qps ascending -- fixed, so runs are bitwise reproducible.  No atomics, no counters; two CTA barriers per plane.
 // Nodal coordinates / displacements / density of plane e+2 arrive by cp.async meanwhile.
+// Status: parity-green, slower than sweep_hex8_struct.cu (profiles/r01h_hex8_march_ncu.md); opt-in with
+// MASTB200_STRUCT_KERNEL=march.
 #include <cuda_runtime.h>
 
 #include "kernels.h"
