@@ -344,8 +344,7 @@ __global__ void __launch_bounds__(STB) quad4_heat_struct_kernel(const GatherPara
   }
   if (p.J) {
     // node-level CSR row pointer of a box: rows in node order with xcnt*ycnt neighbours each
-    const int x0f = i == 0 ? 1 : 0, y0f = j == 0 ? 1 : 0;
-    const int xcnt = 3 - x0f - (i == nx ? 1 : 0), ycnt = 3 - y0f - (j == ny ? 1 : 0);
+    const int ycnt = 3 - (j == 0 ? 1 : 0) - (j == ny ? 1 : 0);
     const int64_t SX = 3 * (int64_t)nx + 1, py = 3 * (int64_t)j - (j > 0 ? 1 : 0), px = 3 * (int64_t)i - (i > 0 ? 1 : 0);
     double* dst = p.J + SX * py + ycnt * px;
 #pragma unroll
