@@ -24,6 +24,18 @@ int hex8_sweep_threads();
 int hex8_sweep_workers();  // compute warps = rows of the plan's per-step visit grid
 cudaError_t launch_hex8_sweep(const SweepParams& p, int n_ctas, cudaStream_t stream);
 
+#ifdef __CUDACC__
+// rho^penalty of the SIMP law (examples/structural/example_6/example_6.cpp:100-137): the usual small integer penalties by
+// multiplication (a few ulp from pow, which costs ~150 instructions per quadrature point)
+__device__ __forceinline__ double simp_pow(double rho, double penalty) {
+  if (penalty == 3.) return rho * rho * rho;
+  if (penalty == 4.) { const double r2 = rho * rho; return r2 * r2; }
+  if (penalty == 2.) return rho * rho;
+  if (penalty == 1.) return rho;
+  return pow(rho, penalty);
+}
+#endif
+
 // ---- HEX8 sweep for ijk-numbered (build_cube) meshes with implicit connectivity (sweep_hex8_struct.cu) --------------
 struct StructUnit {          // a column of owned nodes over a z-range, with the elements that touch it
   int16_t e0x, nex;          // first visited element / number of visited elements in x (<= 8)

@@ -77,7 +77,7 @@ __device__ __forceinline__ void eval_qp(const StressParams& p, int64_t e, int q,
     if (p.rho) rho = fma(Nt[b], p.rho[en[b]], rho);
   }
   double E = p.E0;
-  if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(rho, p.penalty));
+  if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rho, p.penalty));
   g.E = E; g.rho = rho;
   if (p.nonlinear) {
     double Eg[3][3];

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
       inv[8] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
       const double JxW = det * s.tabW[q];
       double E = p.E0;
-      if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(rq, p.penalty));  // example_6.cpp:100-137
+      if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rq, p.penalty));  // example_6.cpp:100-137
       s.wq[q] = JxW * E;
       s.pth[q] = p.thermal ? -(JxW * E) * p.alpha_k * (tq - p.T_ref) : 0.;  // f -= JxW B^T (D alpha dT)
     }

@@ -198,7 +198,7 @@ __device__ __forceinline__ void geometry_phase(const SweepParams& p, const Smem&
       double r = 0.;
 #pragma unroll
       for (int b = 0; b < 8; ++b) r = fma(N[b], sm.rho[ln[b]], r);
-      E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(r, p.penalty));
+      E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(r, p.penalty));
       if (fl.G) dE = p.E0 * (1. - p.rho_min) * p.penalty * pow(r, p.penalty - 1.);
     }
     if (fl.thermal && fl.R) {  // thermal_residual: f -= JxW B^T (D alpha dT)

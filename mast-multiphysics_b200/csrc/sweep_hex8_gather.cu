@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(GW * 32) hex8_gather_kernel(const SolidGatherP
         if (b == a) { ga[0] = g[0]; ga[1] = g[1]; ga[2] = g[2]; }
       }
       double E = p.E0;
-      if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(rho, p.penalty));  // example_6.cpp:100-137
+      if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rho, p.penalty));  // example_6.cpp:100-137
       double eps[6];
       double F[3][3];
       if (nl) {  // E = 1/2 (H + H^T + H^T H), solid_element_3d.cpp:1404-1440

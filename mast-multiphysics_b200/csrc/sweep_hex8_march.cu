@@ -145,7 +145,7 @@ __device__ __forceinline__ void geometry_item(const StructParams& p, const Sm& s
       const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
       r = fma(0.125 * fx * fy * fz, sm.rho[(((m & 4) ? e + 1 : e) % 3) * NC + base + ((m >> 1) & 1) * NCX + (m & 1)], r);
     }
-    E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(r, p.penalty));
+    E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(r, p.penalty));
   }
   // sqrt(JxW E) / det folded into the inverse: the table holds h_m = sqrt(JxW E) grad N_m, so S_AB = sum_q h_A (x) h_B
   const double sc = sqrt(det * E) * __drcp_rn(det);  // Gauss weights are 1 for the 2x2x2 rule

@@ -209,7 +209,7 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
       const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
       r = fma(0.125 * fx * fy * fz, sm.rho[(((m & 4) ? s + 1 : s) % 3) * NS + base + ((m >> 1) & 1) * TCX + (m & 1)], r);
     }
-    E = p.E0 * (p.rho_min + (1. - p.rho_min) * pow(r, p.penalty));
+    E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(r, p.penalty));
   }
   o[4] = make_double2(inv[2][2], det * E);  // Gauss weights are 1 for the 2x2x2 rule
 }
