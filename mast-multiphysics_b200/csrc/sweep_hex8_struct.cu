@@ -393,17 +393,29 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
 #pragma unroll
             for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
         } else {  // 6-variable system: translational block, zero rotational rows/columns, tiny rotational diagonal
-          double* dst = Jrow + 6 * c;
-          const int rl = 2 * rs;
+          // a six-value row piece starts at a multiple of 48 bytes (36 nb0 + 6 c + i * 6 nnb doubles): 16-byte stores
+          double2* dst = reinterpret_cast<double2*>(Jrow + 6 * c);
+          const int rl2 = rs;  // row length 2 rs doubles = rs double2
 #pragma unroll
-          for (int i = 0; i < 6; ++i)
+          for (int i = 0; i < 6; ++i) {
+            double v[6];
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
               double val = 0.;
               if (i < 3 && j < 3) val = K[i][j];
               else if (i == j && self) val = ((cmn >> i) & 1u) ? nadj : rotA;
-              dst[i * rl + j] = val;
+              v[j] = val;
             }
+            if (p.j_aligned16) {
+              dst[i * rl2] = make_double2(v[0], v[1]);
+              dst[i * rl2 + 1] = make_double2(v[2], v[3]);
+              dst[i * rl2 + 2] = make_double2(v[4], v[5]);
+            } else {  // a caller's device pointer that is only 8-byte aligned
+              double* d1 = reinterpret_cast<double*>(dst + i * rl2);
+#pragma unroll
+              for (int j = 0; j < 6; ++j) d1[j] = v[j];
+            }
+          }
         }
       }
     }
