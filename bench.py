@@ -135,6 +135,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sens", action="store_true")
+    ap.add_argument("--no-nv6", action="store_true")
     ap.add_argument("--quick-ref", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -266,6 +267,34 @@ def main():
         ctx.set_density(None)
         ctx.set_material(E0=72e9, nu=0.33, alpha=1.5e-5)
 
+    # ---- the same sweep in MAST's own dof layout (six variables per node, rotational rows / columns kept) ----
+    nv6 = None
+    if not args.no_nv6 and world == 1:
+        try:
+            l6 = slab_problem(n, rank, world, args.jitter, 6)
+            ctx6 = make_context(l6[0], l6[1], l6[2], l6[3], l6[4], local_rank, 6)
+            X6 = torch.zeros(len(lxyz) * 6, dtype=torch.float64, device="cuda")
+            X6.view(-1, 6)[:, :3] = dX.view(-1, 3)
+            R6 = torch.empty(len(lxyz) * 6, dtype=torch.float64, device="cuda")
+            J6 = torch.empty(ctx6.nnz, dtype=torch.float64, device="cuda")
+            k6 = []
+            for i in range(args.warmup + args.steps):
+                ctx6.residual_and_jacobian(X6, R6, J6)
+                if i >= args.warmup:
+                    k6.append(ctx6.stats()["last_main_kernel_ms"])
+            torch.cuda.synchronize()
+            ms6 = float(np.mean(k6))
+            b6 = ctx6.nnz * 8 + len(lxyz) * (6 * 8 + 6 * 8 + 24) + len(lconn) * 32
+            nv6 = {"metric": "hex8_elasticity_residual_jacobian_elems_per_s (nv = 6, MAST's structural system)", "unit": UNIT,
+                   "value": len(lconn) / (ms6 * 1e-3), "kernel_ms": ms6, "nnz": int(ctx6.nnz),
+                   "algorithmic_bytes_per_launch": int(b6), "achieved_GBps": b6 / ms6 / 1e6,
+                   "config": f"same {n}^3 mesh, six variables per node ({(n + 1) ** 3 * 6} dof): translational block, zero "
+                             "rotational rows/columns stored, 1e-20 max(diag K_e) on the rotational diagonal"}
+            del ctx6, J6, R6, X6
+            torch.cuda.empty_cache()
+        except Exception as ex:  # noqa: BLE001
+            nv6 = {"error": str(ex)[:200]}
+
     # ---- end-to-end through the C-ABI with host buffers (pinned), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -323,6 +352,8 @@ def main():
                 traffic = None
         # fp64 work actually executed per launch (visits incl. ghost recompute): DMMA 18*512 + geometry/strain ~ 2.6k
         flops_exec = st["n_visits"] * (18 * 512 + 8 * 2 * 330)
+        if nv6 and "achieved_GBps" in nv6:
+            nv6["hbm_frac"] = nv6["achieved_GBps"] / peak
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -341,7 +372,7 @@ def main():
                          "bytes_per_element": alg_bytes / n_loc_elem,
                          "fp64": {"executed_tflops": flops_exec / (k_ms * 1e-3) / 1e12, "peak_tflops": 36.7,
                                   "peak_source": "profiles/r01_fp64_pipes.md (DFMA = DMMA = 36.7-37.1 TF, one shared pipe)"}},
-            "e2e": e2e, "adjoint_sensitivity": sens, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "adjoint_sensitivity": sens, "reference_layout_nv6": nv6, "gpu_launches": int(launches), "clocks": clocks,
             "kernel_share_of_step": float(np.sum(kern_ms) / total_ms),
         }
         if not args.no_cpu:

@@ -875,7 +875,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     sp.nbr_ptr = S.nbr_ptr.p; sp.arr_off = S.arr_off.p;
     sp.in1_off = kStructIn1Off; sp.cr0_off = kStructCr0Off; sp.cr1_off = kStructCr1Off;
     sp.xyz = p.xyz; sp.X = dX; sp.cmask = p.cmask; sp.J = dJ; sp.R = dR;
-    sp.j_aligned16 = (reinterpret_cast<uintptr_t>(dJ) & 15) == 0 ? 1 : 0;
+    sp.j_aligned32 = (reinterpret_cast<uintptr_t>(dJ) & 31) == 0 ? 1 : 0;
     sp.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
     sp.E0 = p.E0; sp.lam1 = p.lam1; sp.mu1 = p.mu1; sp.rho_min = p.rho_min; sp.penalty = p.penalty;
     ctx->splan.last_march = S.march && ctx->nv == 3;

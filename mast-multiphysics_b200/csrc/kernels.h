@@ -59,7 +59,7 @@ struct StructParams {
   const double* rho = nullptr;           // nodal density (SIMP modulus) or null
   double* J = nullptr;
   double* R = nullptr;
-  int32_t j_aligned16 = 0;               // J is 16-byte aligned: the nv = 6 flush stores double2
+  int32_t j_aligned32 = 0;               // J is 32-byte aligned: the nv = 6 flush uses 16- and 32-byte stores
   double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1.;
 };
 size_t hex8_struct_smem_bytes();

@@ -87,6 +87,12 @@ __device__ __forceinline__ double lds64(unsigned a) {
   return v;
 }
 __device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void stg256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void stg128(double* p, double a, double b) {
+  asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -392,32 +398,47 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
-        } else {  // 6-variable system: translational block, zero rotational rows/columns, tiny rotational diagonal
-          // a six-value row piece starts at a multiple of 48 bytes (36 nb0 + 6 c + i * 6 nnb doubles): 16-byte stores
-          double2* dst = reinterpret_cast<double2*>(Jrow + 6 * c);
-          const int rl2 = rs;  // row length 2 rs doubles = rs double2
+        } else {
+          // 6-variable system, translational rows of this column block: [K_i0 K_i1 K_i2 0 0 0].  A row piece starts at a
+          // multiple of 48 bytes (36 nb0 + 6 c + i * 6 nnb doubles), i.e. on a 32-byte boundary for every other piece:
+          // one 32-byte and one 16-byte store instead of six 8-byte ones.  The rotational rows follow after the passes.
+          double* dst = Jrow + 6 * c;
+          const int rl = 2 * rs;
 #pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            double v[6];
-#pragma unroll
-            for (int j = 0; j < 6; ++j) {
-              double val = 0.;
-              if (i < 3 && j < 3) val = K[i][j];
-              else if (i == j && self) val = ((cmn >> i) & 1u) ? nadj : rotA;
-              v[j] = val;
-            }
-            if (p.j_aligned16) {
-              dst[i * rl2] = make_double2(v[0], v[1]);
-              dst[i * rl2 + 1] = make_double2(v[2], v[3]);
-              dst[i * rl2 + 2] = make_double2(v[4], v[5]);
+          for (int i = 0; i < 3; ++i) {
+            double* d = dst + i * rl;
+            if (p.j_aligned32) {
+              if ((((c + i * (rs / 3)) & 1) == 0)) { stg256(d, K[i][0], K[i][1], K[i][2], 0.); stg128(d + 4, 0., 0.); }
+              else { stg128(d, K[i][0], K[i][1]); stg256(d + 2, K[i][2], 0., 0., 0.); }
             } else {  // a caller's device pointer that is only 8-byte aligned
-              double* d1 = reinterpret_cast<double*>(dst + i * rl2);
-#pragma unroll
-              for (int j = 0; j < 6; ++j) d1[j] = v[j];
+              d[0] = K[i][0]; d[1] = K[i][1]; d[2] = K[i][2]; d[3] = 0.; d[4] = 0.; d[5] = 0.;
             }
           }
         }
       }
+    }
+  }
+  if (NV6 && valid && p.J) {
+    // rotational rows 3-5 of the node: one contiguous run of 18 nnb doubles, zero but for the three diagonal entries
+    // (1e-20 sum of max diag K_e, or the adjacent-element count on a constrained dof): the eight lanes write it in
+    // 32-byte chunks
+    const int nnb = rs / 3, L = 18 * nnb;
+    const int cself = ((1 - z0) * ycnt + (1 - y0)) * xcnt + (1 - x0);
+    const int dpos0 = 6 * cself + 3, dpos1 = 6 * nnb + 6 * cself + 4, dpos2 = 12 * nnb + 6 * cself + 5;
+    const double dv0 = (cmn & 8u) ? nadj : rotA, dv1 = (cmn & 16u) ? nadj : rotA, dv2 = (cmn & 32u) ? nadj : rotA;
+    auto at = [&](int x) { return x == dpos0 ? dv0 : (x == dpos1 ? dv1 : (x == dpos2 ? dv2 : 0.)); };
+    double* base = Jrow + 18 * nnb;
+    if (p.j_aligned32) {
+      const int head = (nnb & 1) ? 2 : 0;  // 36 nb0 + 18 nnb doubles: on a 32-byte boundary iff nnb is even
+      const int nch = (L - head) >> 2, tail = (L - head) & 3;
+      if (head && l8 == 0) stg128(base, at(0), at(1));
+      for (int k = l8; k < nch; k += 8) {
+        const int x = head + 4 * k;
+        stg256(base + x, at(x), at(x + 1), at(x + 2), at(x + 3));
+      }
+      if (tail && l8 == 7) stg128(base + L - 2, at(L - 2), at(L - 1));
+    } else {
+      for (int x = l8; x < L; x += 8) base[x] = at(x);
     }
   }
   if (p.R) {
