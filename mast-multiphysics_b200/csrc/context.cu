@@ -595,8 +595,21 @@ int ensure_struct_plan(mastb200_context* ctx) {
   chunks(nx + 1, 7, cx);                  // 8 elements (9 node columns) per tile row
   chunks(ny + 1, kStructTileY - 1, cy);   // kStructTileY elements per tile column
   const int64_t n_tiles = (int64_t)cx.size() * cy.size(), planes = oz1 - oz0;
-  int64_t nseg = (20 * (int64_t)ctx->sm_count + n_tiles - 1) / n_tiles;
-  nseg = std::max<int64_t>(1, std::min<int64_t>(nseg, std::max<int64_t>(1, planes / 24)));
+  // z-segments per tile: large meshes get ~20 units per SM with at least 24 planes each (a segment costs one extra element
+  // plane); meshes too small for that take the split that minimises waves x (planes per segment + 1)
+  auto pick_segments = [&](int64_t tiles, int64_t ctas) {
+    int64_t ns = (20 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+    const int64_t cap = std::max<int64_t>(1, planes / 24);
+    ns = std::max<int64_t>(1, std::min<int64_t>(ns, cap));
+    if (tiles * cap >= 2 * ctas) return ns;
+    int64_t best = 1, best_cost = INT64_MAX;
+    for (int64_t c = 1; c <= std::max<int64_t>(1, planes / 2); ++c) {
+      const int64_t waves = (tiles * c + ctas - 1) / ctas, cost = waves * ((planes + c - 1) / c + 1);
+      if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    return best;
+  };
+  const int64_t nseg = pick_segments(n_tiles, ctx->sm_count);
   std::vector<StructUnit> units;
   std::vector<int64_t> cost;
   S.n_visits = 0;
@@ -635,8 +648,7 @@ int ensure_struct_plan(mastb200_context* ctx) {
       chunks(nx + 1, kMarchTileX, mx);
       chunks(ny + 1, kMarchTileY, my);
       const int64_t m_tiles = (int64_t)mx.size() * my.size();
-      int64_t mseg = (20 * (int64_t)ctx->sm_count + m_tiles - 1) / m_tiles;
-      mseg = std::max<int64_t>(1, std::min<int64_t>(mseg, std::max<int64_t>(1, planes / 24)));
+      const int64_t mseg = pick_segments(m_tiles, ctx->sm_count);
       std::vector<StructUnit> mu;
       std::vector<int64_t> mc;
       S.m_n_visits = 0;

@@ -426,13 +426,19 @@ int hex8_march_threads() { return NT; }
 cudaError_t launch_hex8_march(const StructParams& p, int n_ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  auto go = [&](auto kern) -> cudaError_t {
-    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (er != cudaSuccess) return er;
+  static bool attr_set[4][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  auto go = [&](auto kern, int variant) -> cudaError_t {
+    if (dev >= 64 || !attr_set[variant][dev]) {
+      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (er != cudaSuccess) return er;
+      if (dev < 64) attr_set[variant][dev] = true;
+    }
     kern<<<n_ctas, NT, SMEM_BYTES, stream>>>(p);
     return cudaSuccess;
   };
-  e = p.rho ? go(hex8_march_kernel<true>) : go(hex8_march_kernel<false>);
+  e = p.rho ? go(hex8_march_kernel<true>, 1) : go(hex8_march_kernel<false>, 0);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }

@@ -622,14 +622,20 @@ int hex8_struct_threads() { return ST; }
 cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  auto go = [&](auto kern) -> cudaError_t {
-    cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (er != cudaSuccess) return er;
+  static bool attr_set[4][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  auto go = [&](auto kern, int variant) -> cudaError_t {
+    if (dev >= 64 || !attr_set[variant][dev]) {
+      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (er != cudaSuccess) return er;
+      if (dev < 64) attr_set[variant][dev] = true;
+    }
     kern<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
     return cudaSuccess;
   };
-  if (p.nv == 6) e = p.rho ? go(hex8_struct_kernel<true, true>) : go(hex8_struct_kernel<false, true>);
-  else e = p.rho ? go(hex8_struct_kernel<true, false>) : go(hex8_struct_kernel<false, false>);
+  if (p.nv == 6) e = p.rho ? go(hex8_struct_kernel<true, true>, 3) : go(hex8_struct_kernel<false, true>, 2);
+  else e = p.rho ? go(hex8_struct_kernel<true, false>, 1) : go(hex8_struct_kernel<false, false>, 0);
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
