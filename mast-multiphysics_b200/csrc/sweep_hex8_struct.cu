@@ -338,7 +338,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
   double* Jrow = p.J + (NV6 ? 36 : 9) * nb0;
   const double rotA = NV6 ? sm.rot[par * NS + slotA] : 0.;
   double r0 = 0., r1 = 0., r2 = 0.;
-#pragma unroll 2
+#pragma unroll 1
   for (int t = 0; t < 4; ++t) {
     const int pk = sm.fpk[t * 8 + l8];
     const bool on = valid && (pk & (1 << 15)) && !(flags & (pk >> 7) & 63);
