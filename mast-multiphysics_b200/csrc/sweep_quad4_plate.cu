@@ -21,6 +21,8 @@
 // Algorithmic bytes per element on a structured mesh: 9 blocks x 36 values x 8 B = 2592 B of J + vectors: HBM-bound.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "kernels.h"
 
 namespace mastb200 {
@@ -252,8 +254,12 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
     const double nadj_all = double(nadj + nadjd);
     double* dst = p.J + 36 * nb0 + 6 * c;
     const int rl = 6 * nnb;
+    // a six-value row piece starts at a multiple of 48 bytes (36 nb0 + 6 c + i * 6 nnb doubles): 16-byte stores when the
+    // caller's J is 16-byte aligned
+    const bool al16 = (reinterpret_cast<uintptr_t>(p.J) & 15) == 0;
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
+    for (int i = 0; i < 6; ++i) {
+      double v[6];
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         double k = K[i][j];
@@ -262,8 +268,16 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
           if ((cmn >> i) & 1u) k = nadj_all;
           else k += 1.0e-24 * nadjd;
         }
-        dst[i * rl + j] = k;
+        v[j] = k;
       }
+      if (al16) {
+        double2* d2 = reinterpret_cast<double2*>(dst + i * rl);
+        d2[0] = make_double2(v[0], v[1]); d2[1] = make_double2(v[2], v[3]); d2[2] = make_double2(v[4], v[5]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) dst[i * rl + j] = v[j];
+      }
+    }
   }
   if (p.R && self)
 #pragma unroll
