@@ -111,14 +111,14 @@ struct mastb200_context {
   // device plan of the gather (QUAD4 heat) and coloured-scatter (HEX27) sweeps
   struct GenericPlan {
     bool built = false;
-    DevBuf<int32_t> conn, n2e, nbr, node_row, color_elems;
+    DevBuf<int32_t> conn, n2e, nbr, node_row, color_elems, ent_row;  // ent_row: owned row of every neighbour entry (plate)
     DevBuf<int64_t> n2e_ptr, nbr_ptr;
     DevBuf<uint8_t> diag, posmap;
     DevBuf<double> tab;
     std::vector<int32_t> color_ptr;
     void reset() {
       built = false; color_ptr.clear();
-      conn.release(); n2e.release(); nbr.release(); node_row.release(); color_elems.release();
+      conn.release(); n2e.release(); nbr.release(); node_row.release(); color_elems.release(); ent_row.release();
       n2e_ptr.release(); nbr_ptr.release(); diag.release(); posmap.release(); tab.release();
     }
   } gplan;
@@ -356,6 +356,12 @@ int ensure_generic_plan(mastb200_context* ctx) {
       if (P.nbr_ptr[r + 1] - P.nbr_ptr[r] > kGatherMaxNbr)
         return ctx->fail(MASTB200_ERR_PLAN, "plan: a node has more than %d neighbours", kGatherMaxNbr);
     CU(G.nbr.upload(P.nbr, ctx->stream));
+    if (ctx->nv == 6) {  // the plate kernel runs one thread per neighbour entry: its row, instead of a search per thread
+      std::vector<int32_t> er((size_t)P.nbr_ptr[P.n_owned]);
+      for (int64_t r = 0; r < P.n_owned; ++r)
+        for (int64_t k = P.nbr_ptr[r]; k < P.nbr_ptr[r + 1]; ++k) er[k] = (int32_t)r;
+      CU(G.ent_row.upload(er, ctx->stream));
+    }
   } else if (ctx->elem_type == MASTB200_HEX8) {  // gather sweep (Green-Lagrange strain) and stress output
     CU(G.nbr.upload(P.nbr, ctx->stream));
     std::vector<double> tab;
@@ -430,6 +436,7 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
   p.n_owned = ctx->pat.n_owned; p.n_entries = ctx->pat.nbr_ptr[ctx->pat.n_owned];
   p.owned_nodes = ctx->d_owned_nodes.p;
   p.nbr_ptr = G.nbr_ptr.p; p.nbr = G.nbr.p; p.n2e_ptr = G.n2e_ptr.p; p.n2e = G.n2e.p; p.conn = G.conn.p;
+  p.ent_row = G.ent_row.p;
   p.diag_elem = ctx->has_diag ? G.diag.p : nullptr;
   p.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
   p.xyz = ctx->d_xyz.p; p.X = dX; p.J = dJ; p.R = dR;

@@ -130,6 +130,7 @@ struct PlateParams {
   const int32_t* owned_nodes = nullptr;
   const int64_t* nbr_ptr = nullptr;
   const int32_t* nbr = nullptr;
+  const int32_t* ent_row = nullptr;      // [n_entries] owned row of every neighbour entry
   const int64_t* n2e_ptr = nullptr;
   const int32_t* n2e = nullptr;
   const int32_t* conn = nullptr;         // [n_elem][4]

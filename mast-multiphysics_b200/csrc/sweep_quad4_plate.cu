@@ -63,13 +63,7 @@ template <bool LOCAL>
 __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
   const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (t >= p.n_entries) return;
-  // row of this neighbour entry: last r with nbr_ptr[r] <= t
-  int64_t lo = 0, hi = p.n_owned;
-  while (hi - lo > 1) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (p.nbr_ptr[mid] <= t) lo = mid; else hi = mid;
-  }
-  const int64_t r = lo;
+  const int64_t r = p.ent_row[t];  // row of this neighbour entry (precomputed with the plan)
   const int n = p.owned_nodes[r];
   const int64_t nb0 = p.nbr_ptr[r];
   const int nnb = (int)(p.nbr_ptr[r + 1] - nb0);
