@@ -605,7 +605,7 @@ int ensure_struct_plan(mastb200_context* ctx) {
   // z-segments per tile: large meshes get ~20 units per SM with at least 24 planes each (a segment costs one extra element
   // plane); meshes too small for that take the split that minimises waves x (planes per segment + 1)
   auto pick_segments = [&](int64_t tiles, int64_t ctas) {
-    int64_t ns = (20 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+    int64_t ns = (20 * ctas + tiles - 1) / tiles;
     const int64_t cap = std::max<int64_t>(1, planes / 24);
     ns = std::max<int64_t>(1, std::min<int64_t>(ns, cap));
     if (tiles * cap >= 2 * ctas) return ns;
@@ -616,7 +616,7 @@ int ensure_struct_plan(mastb200_context* ctx) {
     }
     return best;
   };
-  const int64_t nseg = pick_segments(n_tiles, ctx->sm_count);
+  const int64_t nseg = pick_segments(n_tiles, (int64_t)ctx->sm_count * kStructCtasPerSm);
   std::vector<StructUnit> units;
   std::vector<int64_t> cost;
   S.n_visits = 0;
@@ -696,7 +696,7 @@ int ensure_struct_plan(mastb200_context* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   S.nx = (int32_t)nx; S.ny = (int32_t)ny; S.nz = (int32_t)nz; S.oz0 = (int32_t)oz0; S.oz1 = (int32_t)oz1;
   S.n_units = (int32_t)sorted.size();
-  S.n_ctas = std::max(1, std::min(S.n_units, ctx->sm_count));
+  S.n_ctas = std::max(1, std::min(S.n_units, ctx->sm_count * kStructCtasPerSm));
   S.ok = true;
   return MASTB200_OK;
 }

@@ -47,6 +47,8 @@ constexpr int NS = TCX * TCY;          // node-column slots
 constexpr int NSB = (NS + 3) & ~3;     // padded byte-array row
 static_assert(NS == kStructSlots, "layout header out of date");
 constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
+constexpr int GEO_ROUNDS = kStructGeoRounds;  // geometry of a warp's 2x2 block in one round of four elements or two rounds of two
+constexpr int STAGE_EL = 4 / GEO_ROUNDS;        // elements staged per warp at a time
 constexpr double GP = 0.57735026918962576451;
 
 // shared-memory carve-up (bytes)
@@ -54,8 +56,8 @@ constexpr int O_ARENA = 0;
 constexpr int ARENA_BYTES = kStructArenaDoubles * 8;
 constexpr int O_XYZ = O_ARENA + ARENA_BYTES;            // [3 planes][3][NS]
 constexpr int O_U = O_XYZ + 3 * 3 * NS * 8;             // [4 planes][3][NS]
-constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;  // [SW][4 el][8 qp][QS]
-constexpr int O_CNT = O_STAGE + SW * 4 * 8 * QS * 8;    // [NS] int32 (+pad)
+constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;  // [SW][STAGE_EL el][8 qp][QS]
+constexpr int O_CNT = O_STAGE + SW * STAGE_EL * 8 * QS * 8;    // [NS] int32 (+pad)
 constexpr int O_CM = O_CNT + NSB * 4;                   // [4 planes][NSB] uint8
 constexpr int O_TAB = O_CM + 4 * NSB;                   // [124] int32: array offsets within an IN / CR region
 constexpr int O_RHO = O_TAB + 124 * 4;                  // [3 planes][NS] nodal density (SIMP variant)
@@ -65,7 +67,7 @@ constexpr int O_ROT = O_FPK + 32 * 4;                   // [2 planes][NS] sum of
 constexpr int O_MISC = O_ROT + 2 * NS * 8;
 constexpr int SMEM_BYTES = O_MISC + 16;
 static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0 && O_ROT % 8 == 0, "alignment");
-static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
+static_assert(SMEM_BYTES <= (kStructCtasPerSm == 1 ? 232448 : 115712), "shared-memory layout exceeds the per-CTA budget");
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -458,7 +460,7 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
 }
 
 template <bool SIMP, bool NV6>
-__global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p) {
+__global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const StructParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Sm sm;
   sm.arena = reinterpret_cast<double*>(smem_raw + O_ARENA);
@@ -480,7 +482,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
   LaneK lk;
   make_lane(p, sm.tab, lane, lk);
   const unsigned arena32 = (unsigned)__cvta_generic_to_shared(sm.arena);
-  double* my_stage = sm.stage + warp * (4 * 8 * QS);
+  double* my_stage = sm.stage + warp * (STAGE_EL * 8 * QS);
   const int bx2 = (warp & 3) * 2, by2 = (warp >> 2) * 2;  // origin of the warp's 2x2 element block
 
   for (;;) {
@@ -521,6 +523,16 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
       if (ld_on) {
         if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * (NV6 ? 6 : 3) + ld_src);
         else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
+      }
+      if (NS * 6 > ST && tid + ST < ncols * 6) {  // small CTAs: the few items beyond one per thread
+        const int t = tid + ST, col = t / 6, c = t - col * 6;
+        const int ly = col / ncx, lx = col - ly * ncx;
+        const int64_t gid0 = (u.e0x + lx) + (u.e0y + ly) * npx;
+        const bool isu = c >= 3;
+        const int dst = (isu ? c - 3 : c) * NS + ly * TCX + lx;
+        const int64_t src = gid0 * (isu && NV6 ? 6 : 3) + (isu ? c - 3 : c);
+        if (isu) cp_async8(sm.u + (z & 3) * 3 * NS + dst, p.X + (int64_t)z * plane_nodes * (NV6 ? 6 : 3) + src);
+        else cp_async8(sm.xyz + (z % 3) * 3 * NS + dst, p.xyz + (int64_t)z * plane_nodes * 3 + src);
       }
     };
     // accumulation ranks of this lane's node column for the four elements of the warp's block (2 bits per colour)
@@ -573,23 +585,29 @@ __global__ void __launch_bounds__(ST, 1) hex8_struct_kernel(const StructParams p
       }
       if (s < p.nz) {
         // ---- compute: the warp's 2x2 block of elements of plane s ----
-        {
-          const int el = lane >> 3, q = lane & 7;
-          const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
-          if (lex < u.nex && ley < u.ney) geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
-        }
-        __syncwarp();
-        if (s & 1) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-            if (lex < u.nex && ley < u.ney) element_phase<1, NV6>(p, sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
+        for (int round = 0; round < GEO_ROUNDS; ++round) {
+          const int c_lo = round * STAGE_EL;
+          if (GEO_ROUNDS > 1) __syncwarp();  // the staged geometry of the previous round has been consumed
+          {
+            const int el = c_lo + (lane >> 3), q = lane & 7;
+            const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
+            if ((lane >> 3) < STAGE_EL && lex < u.nex && ley < u.ney)
+              geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
           }
-        } else {
+          __syncwarp();
+          if (s & 1) {
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
-            const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-            if (lex < u.nex && ley < u.ney) element_phase<0, NV6>(p, sm, lk, arena32, rankpack, my_stage + c * 8 * QS, lex, ley, c, lane);
+            for (int c = c_lo; c < c_lo + STAGE_EL; ++c) {
+              const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+              if (lex < u.nex && ley < u.ney) element_phase<1, NV6>(p, sm, lk, arena32, rankpack, my_stage + (c - c_lo) * 8 * QS, lex, ley, c, lane);
+            }
+          } else {
+#pragma unroll 1
+            for (int c = c_lo; c < c_lo + STAGE_EL; ++c) {
+              const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+              if (lex < u.nex && ley < u.ney) element_phase<0, NV6>(p, sm, lk, arena32, rankpack, my_stage + (c - c_lo) * 8 * QS, lex, ley, c, lane);
+            }
           }
         }
       }
@@ -629,6 +647,7 @@ cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t s
     if (dev >= 64 || !attr_set[variant][dev]) {
       cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
       if (er != cudaSuccess) return er;
+      if ((er = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return er;
       if (dev < 64) attr_set[variant][dev] = true;
     }
     kern<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
