@@ -100,6 +100,10 @@ int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t
 int mastb200_set_heat_side_loads_ex(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
                                     const double* heat_flux, const double* conv_coeff, const double* T_amb,
                                     const double* emissivity, double sb_const, double T_ref_zero);
+/* Point loads (discipline.point_loads()): load[n][nv] on node[n]; R[dofs of the node] -= load on the unconstrained dofs
+ * of the nodes this rank owns (loads of one node are summed in the order given); n = 0 clears.  Call after set_dof_map.
+ *   <- NonlinearImplicitAssembly::residual_and_jacobian, src/base/nonlinear_implicit_assembly.cpp:190-247 */
+int mastb200_set_point_loads(mastb200_context* ctx, int64_t n, const int32_t* node, const double* load);
 /* TEMPERATURE volume load: nodal field [h|d] (or NULL => constant), reference temperature. enable=0 clears. */
 int mastb200_set_temperature(mastb200_context* ctx, int32_t enable, const double* T_nodal, double T_const,
                              double T_ref);
@@ -111,6 +115,11 @@ int mastb200_set_density(mastb200_context* ctx, const double* rho_nodal);
 int mastb200_build_pattern(mastb200_context* ctx, int64_t* n_rows, int64_t* nnz);
 /* Copies the CSR pattern of the owned rows out (host pointers): row_ptr[n_rows+1], col_idx[nnz]. */
 int mastb200_get_pattern(const mastb200_context* ctx, int64_t* row_ptr, int32_t* col_idx);
+/* The same for a sample of rows (the full col_idx of a 200^3 mesh is 7.8 GB): rows[n] are CSR row numbers;
+ * row_begin[n] = position of the row's first value in J_vals, row_len[n] = its number of values,
+ * col_idx (may be NULL) = the rows' column indices concatenated in the order of rows[]. */
+int mastb200_get_pattern_rows(const mastb200_context* ctx, int64_t n, const int64_t* rows, int64_t* row_begin,
+                              int32_t* row_len, int32_t* col_idx);
 /* dof id of each CSR row: row_dof[n_rows] (owned nodes ascending, nv rows per node). */
 int mastb200_get_row_dofs(const mastb200_context* ctx, int64_t* row_dof);
 
@@ -131,8 +140,32 @@ int mastb200_sensitivity_sweep(mastb200_context* ctx, const double* X, const dou
 int mastb200_apply_dv_map_transpose(mastb200_context* ctx, const double* G, int64_t n_dv, const int64_t* dv_ptr,
                                     const int32_t* dv_node, const double* dv_weight, double* sens);
 
-/* ComplianceOutput: q = -sum f_ext . u  (owned part; caller sums over ranks unless skip_comm_sum) */
+/* dR/dp of ONE parameter as a vector, dRdp[n_nodes*nv] [h|d] (rows of owned nodes, constrained dofs zeroed per element):
+ *   MASTB200_PARAM_DENSITY_DV  nodal-density design variable under the SIMP law; dv_node[n_k], dv_weight[n_k] (host) =
+ *                              the nodes and weights of its filter column (d rho_n / dp)
+ *   MASTB200_PARAM_E           Young's modulus E0 of the isotropic card (dv arguments ignored)
+ *   MASTB200_PARAM_NU          Poisson's ratio
+ * 3D solids, linear strain; matrix-free (two launches), K_e is never formed.
+ *   <- NonlinearImplicitAssembly::sensitivity_assemble, src/base/nonlinear_implicit_assembly.cpp:515-686, with
+ *      StructuralElement3D::internal_residual_sensitivity (src/elasticity/solid_element_3d.cpp:566-788, D <- dD/dp at :640)
+ *      and IsotropicMaterialProperty::StiffnessMatrix3D::derivative (isotropic_material_property_card.cpp:530-567) */
+#define MASTB200_PARAM_DENSITY_DV 0
+#define MASTB200_PARAM_E 1
+#define MASTB200_PARAM_NU 2
+int mastb200_sensitivity_assemble(mastb200_context* ctx, const double* X, int32_t param, int64_t n_k, const int32_t* dv_node,
+                                  const double* dv_weight, double* dRdp);
+/* out[n_nodes*nv] [h|d] = J(X) dX without forming J (constrained dofs zeroed per element), 3D solids, linear strain
+ *   <- NonlinearImplicitAssembly::linearized_jacobian_solution_product, src/base/nonlinear_implicit_assembly.cpp:270-383
+ *      (declared at nonlinear_implicit_assembly.h:115), elem_linearized_jacobian_solution_product */
+int mastb200_linearized_jacobian_solution_product(mastb200_context* ctx, const double* X, const double* dX, double* out);
+
+/* ComplianceOutput: q = -sum f_ext . u  (owned part; caller sums over ranks unless skip_comm_sum); f_ext = SURFACE_PRESSURE
+ * sides and the TEMPERATURE volume load (3D solids) */
 int mastb200_compliance(mastb200_context* ctx, const double* X, double* q);
+/* ComplianceOutput::evaluate_sensitivity through AssemblyBase::calculate_output_direct_sensitivity for parameters that do
+ * not enter the loads: dq = -f_ext . dX/dp (dXdp [h|d] may be NULL => 0)
+ *   <- src/base/assembly_base.cpp:434-550, src/elasticity/compliance_output.cpp:106-150 */
+int mastb200_compliance_direct_sensitivity(mastb200_context* ctx, const double* X, const double* dXdp, double* dq);
 /* dq_dX[n_nodes*nv] [h|d] = -f_ext with constrained rows zeroed */
 int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, double* dq_dX);
 

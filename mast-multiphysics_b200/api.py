@@ -16,7 +16,8 @@ HEX8, HEX27, QUAD4 = 8, 27, 4
 EXPORTED_SYMBOLS = [
     "mastb200_create", "mastb200_destroy", "mastb200_last_error", "mastb200_version", "mastb200_set_mesh",
     "mastb200_set_dof_map", "mastb200_set_material", "mastb200_set_side_pressure", "mastb200_set_heat_side_loads", "mastb200_set_heat_side_loads_ex", "mastb200_set_temperature",
-    "mastb200_set_density", "mastb200_build_pattern", "mastb200_get_pattern", "mastb200_get_row_dofs",
+    "mastb200_set_point_loads", "mastb200_sensitivity_assemble", "mastb200_linearized_jacobian_solution_product",
+    "mastb200_compliance_direct_sensitivity", "mastb200_set_density", "mastb200_build_pattern", "mastb200_get_pattern", "mastb200_get_pattern_rows", "mastb200_get_row_dofs",
     "mastb200_residual_and_jacobian", "mastb200_res_l2_norm", "mastb200_sensitivity_sweep",
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
     "mastb200_stress", "mastb200_stress_functional", "mastb200_stress_functional_derivative",
@@ -82,9 +83,14 @@ def load_library():
     lib.mastb200_set_heat_side_loads_ex.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, dbl, dbl]
     lib.mastb200_set_temperature.argtypes = [vp, i32, vp, dbl, dbl]
     lib.mastb200_set_density.argtypes = [vp, vp]
+    lib.mastb200_set_point_loads.argtypes = [vp, i64, vp, vp]
+    lib.mastb200_sensitivity_assemble.argtypes = [vp, vp, i32, i64, vp, vp, vp]
+    lib.mastb200_linearized_jacobian_solution_product.argtypes = [vp, vp, vp, vp]
+    lib.mastb200_compliance_direct_sensitivity.argtypes = [vp, vp, vp, C.POINTER(dbl)]
     lib.mastb200_build_pattern.argtypes = [vp, C.POINTER(i64), C.POINTER(i64)]
     lib.mastb200_get_pattern.argtypes = [vp, vp, vp]
     lib.mastb200_get_row_dofs.argtypes = [vp, vp]
+    lib.mastb200_get_pattern_rows.argtypes = [vp, i64, vp, vp, vp, vp]
     lib.mastb200_residual_and_jacobian.argtypes = [vp, vp, vp, vp]
     lib.mastb200_res_l2_norm.argtypes = [vp, C.POINTER(dbl)]
     lib.mastb200_sensitivity_sweep.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -191,6 +197,10 @@ class Context:
         self._keep["T"] = T_nodal
         self._ck(self._lib.mastb200_set_temperature(self._h, int(enable), _ptr(T_nodal), T_const, T_ref))
 
+    def set_point_loads(self, node, load):
+        node = _np(node, np.int32); load = _np(load, np.float64)
+        self._ck(self._lib.mastb200_set_point_loads(self._h, len(node), _ptr(node), _ptr(load)))
+
     def set_density(self, rho):
         self._keep["rho"] = rho  # a device tensor is used in place: keep it alive
         self._ck(self._lib.mastb200_set_density(self._h, _ptr(rho)))
@@ -206,6 +216,15 @@ class Context:
         col_idx = np.empty(self.nnz, np.int32) if with_cols else None
         self._ck(self._lib.mastb200_get_pattern(self._h, _ptr(row_ptr), _ptr(col_idx)))
         return row_ptr, col_idx
+
+    def get_pattern_rows(self, rows):
+        """(row_begin, row_len, col_idx) of a sample of CSR rows: positions of the rows' values in J and their columns."""
+        rows = _np(rows, np.int64)
+        begin = np.empty(len(rows), np.int64); length = np.empty(len(rows), np.int32)
+        self._ck(self._lib.mastb200_get_pattern_rows(self._h, len(rows), _ptr(rows), _ptr(begin), _ptr(length), None))
+        cols = np.empty(int(length.sum()), np.int32)
+        self._ck(self._lib.mastb200_get_pattern_rows(self._h, len(rows), _ptr(rows), _ptr(begin), _ptr(length), _ptr(cols)))
+        return begin, length, cols
 
     def get_row_dofs(self):
         out = np.empty(self.n_rows, np.int64)
@@ -230,6 +249,20 @@ class Context:
         self._ck(self._lib.mastb200_apply_dv_map_transpose(self._h, _ptr(G), len(dv_ptr) - 1, _ptr(dv_ptr),
                                                            _ptr(dv_node), _ptr(dv_weight), _ptr(sens)))
         return sens
+
+    def sensitivity_assemble(self, X, dRdp, param=0, dv_node=None, dv_weight=None):
+        """dR/dp of one parameter: param 0 = nodal-density DV (dv_node, dv_weight), 1 = E0, 2 = nu."""
+        dv_node = _np(dv_node, np.int32); dv_weight = _np(dv_weight, np.float64)
+        n_k = 0 if dv_node is None else len(dv_node)
+        self._ck(self._lib.mastb200_sensitivity_assemble(self._h, _ptr(X), int(param), n_k, _ptr(dv_node), _ptr(dv_weight), _ptr(dRdp)))
+
+    def linearized_jacobian_solution_product(self, X, dX, out):
+        self._ck(self._lib.mastb200_linearized_jacobian_solution_product(self._h, _ptr(X), _ptr(dX), _ptr(out)))
+
+    def compliance_direct_sensitivity(self, X, dXdp):
+        v = C.c_double()
+        self._ck(self._lib.mastb200_compliance_direct_sensitivity(self._h, _ptr(X), _ptr(dXdp), C.byref(v)))
+        return v.value
 
     def compliance(self, X):
         v = C.c_double()

@@ -149,13 +149,22 @@ struct mastb200_context {
   const double* T_ext = nullptr;
   double T_const = 0., T_ref = 0.;
   const double* last_R = nullptr;   // device pointer of the last residual
-  // face loads
+  // face loads: raw (element, side, pressure) entries and the per-owned-node gather lists built from them
+  std::vector<int32_t> sp_elem, sp_side;
+  std::vector<double> sp_p;
   std::vector<int32_t> fl_node, fl_ptr, fl_face_nodes;
   std::vector<uint8_t> fl_k;
   std::vector<double> fl_p;
   DevBuf<int32_t> d_fl_node, d_fl_ptr, d_fl_face_nodes;
   DevBuf<uint8_t> d_fl_k;
   DevBuf<double> d_fl_p;
+  // point loads: loads of the OWNED nodes, summed per node in the order given (nonlinear_implicit_assembly.cpp:190-247)
+  std::vector<int32_t> pl_node;
+  std::vector<double> pl_load;
+  DevBuf<int32_t> d_pl_node, d_dvn;
+  DevBuf<double> d_pl_load, d_dfield, d_dvw, d_vec2;
+  std::vector<int32_t> pl_raw_node;
+  std::vector<double> pl_raw_load;
   // heat side loads (CSR over elements)
   DevBuf<int32_t> d_hs_ptr, d_hs_side;
   DevBuf<double> d_hs_val;
@@ -287,6 +296,20 @@ FaceLoadPlan face_plan(const mastb200_context* ctx) {
   return fp;
 }
 
+// external loads of the residual: SURFACE_PRESSURE sides (side_external_residual) and point loads
+int apply_external_loads(mastb200_context* ctx, double* dR, const uint8_t* cmask) {
+  if (!dR) return MASTB200_OK;
+  if (!ctx->fl_node.empty()) {
+    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, cmask, ctx->nv, dR, nullptr, nullptr, nullptr, ctx->stream));
+    ctx->launches++;
+  }
+  if (!ctx->pl_node.empty()) {
+    CU(launch_point_loads((int)ctx->pl_node.size(), ctx->d_pl_node.p, ctx->d_pl_load.p, cmask, ctx->nv, dR, ctx->stream));
+    ctx->launches++;
+  }
+  return MASTB200_OK;
+}
+
 int check_ready(mastb200_context* ctx) {
   if (!ctx) return MASTB200_ERR_ARG;
   if (ctx->planning_only)
@@ -414,6 +437,10 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
   int rc;
   if (ctx->mat.nonlinear_strain)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "von Karman strain of the plate element is not on the device path");
+  if (ctx->thermal)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "TEMPERATURE load on the plate element is not on the device path");
+  if (ctx->rho_set)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "SIMP density field on the plate element is not on the device path");
   // GeomElem's rule (geom_elem.cpp:358-374): an element whose nodes do not share one z gets a local frame
   int32_t local_frames = 0;
   for (int64_t e = 0; e < ctx->n_elem && !local_frames; ++e)
@@ -453,6 +480,10 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
   CU(launch_quad4_plate(p, ctx->stream));
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  if (dR && !ctx->pl_node.empty()) {
+    CU(launch_point_loads((int)ctx->pl_node.size(), ctx->d_pl_node.p, ctx->d_pl_load.p, p.cmask, ctx->nv, dR, ctx->stream));
+    ctx->launches++;
+  }
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;
@@ -529,11 +560,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     }
   }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (!heat && dR && !ctx->fl_node.empty()) {  // side_external_residual: SURFACE_PRESSURE on HEX27 faces
-    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, ctx->has_constraints ? ctx->d_cmask.p : nullptr, ctx->nv, dR,
-                         nullptr, nullptr, nullptr, ctx->stream));
-    ctx->launches++;
-  }
+  if (!heat && (rc = apply_external_loads(ctx, dR, ctx->has_constraints ? ctx->d_cmask.p : nullptr))) return rc;  // SURFACE_PRESSURE on HEX27 faces, point loads
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;
@@ -739,10 +766,7 @@ int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J
   CU(launch_hex8_gather(p, ctx->stream));
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (dR && !ctx->fl_node.empty()) {
-    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, p.cmask, ctx->nv, dR, nullptr, nullptr, nullptr, ctx->stream));
-    ctx->launches++;
-  }
+  if ((rc = apply_external_loads(ctx, dR, p.cmask))) return rc;
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;
@@ -817,6 +841,33 @@ int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, 
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   if ((rc = finish_out(ctx, G, (size_t)ctx->n_nodes, dG))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+// matrix-free element force of a 3D solid mesh (linear strain) into `out` [n_nodes*nv]: see launch_internal_force
+int run_internal_force(mastb200_context* ctx, const double* V, int mode, const double* dfield, double lam1, double mu1,
+                       double* out, bool constrain_rows = true) {
+  int rc;
+  StressParams p;
+  if ((rc = fill_stress_params(ctx, V, p))) return rc;
+  if (!constrain_rows) p.cmask = nullptr;  // ComplianceOutput::evaluate dots the unconstrained element vectors with the state
+  if (ctx->mat.nonlinear_strain)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "matrix-free products with Green-Lagrange strain are not on the device path");
+  p.lam1 = lam1; p.mu1 = mu1;
+  p.alpha_k = ctx->mat.alpha * (3. * p.lam1 + 2. * p.mu1);
+  p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
+  p.temperature = (ctx->thermal && ctx->T_nodal) ? (ctx->T_ext ? ctx->T_ext : ctx->d_T.p) : nullptr;
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  double* d = nullptr;
+  if ((rc = resolve_out(ctx, out, n_dof, ctx->d_dq, &d))) return rc;
+  CU(ctx->d_scratch.ensure(size_t(ctx->n_elem) * p.nq * 9));
+  p.scratch = ctx->d_scratch.p;
+  p.dq_dX = d;
+  if (ctx->has_ghosts) CU(cudaMemsetAsync(d, 0, n_dof * sizeof(double), ctx->stream));
+  CU(launch_internal_force(p, mode, dfield, ctx->stream));
+  ctx->launches += 2;
+  if ((rc = finish_out(ctx, out, n_dof, d))) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   return MASTB200_OK;
 }
@@ -909,10 +960,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   }
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if (dR && !ctx->fl_node.empty()) {
-    CU(launch_face_loads(face_plan(ctx), ctx->d_xyz.p, nullptr, p.cmask, ctx->nv, dR, nullptr, nullptr, nullptr, ctx->stream));
-    ctx->launches++;
-  }
+  if ((rc = apply_external_loads(ctx, dR, p.cmask))) return rc;
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;
@@ -926,6 +974,8 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
 }  // namespace
 
 extern "C" {
+
+static int rebuild_face_loads(mastb200_context* ctx);
 
 const char* mastb200_version(void) { return "mast_b200 0.1 (sm_100a)"; }
 
@@ -1006,7 +1056,12 @@ int mastb200_set_mesh(mastb200_context* ctx, int32_t elem_type, int64_t n_elem, 
   }
   if (!ctx->planning_only) CU(ctx->d_xyz.upload(ctx->xyz, ctx->stream));
   ctx->have_mesh = true; ctx->have_plan = false;
-  ctx->fl_node.clear();
+  // everything sized for the previous mesh goes: the caller sets the dof map, density, temperature and loads again
+  ctx->have_dofs = false; ctx->owned.clear(); ctx->cmask.clear(); ctx->has_constraints = false; ctx->has_ghosts = false;
+  ctx->rho_set = false; ctx->rho_ext = nullptr; ctx->thermal = false; ctx->T_nodal = false; ctx->T_ext = nullptr;
+  ctx->last_R = nullptr;
+  ctx->sp_elem.clear(); ctx->sp_side.clear(); ctx->sp_p.clear();
+  ctx->fl_node.clear(); ctx->fl_ptr.clear(); ctx->fl_face_nodes.clear(); ctx->fl_k.clear(); ctx->fl_p.clear();
   ctx->have_heat_sides = false;
   return MASTB200_OK;
 }
@@ -1036,6 +1091,7 @@ int mastb200_set_dof_map(mastb200_context* ctx, int32_t nv, const uint8_t* const
   }
   if (!ctx->planning_only) CU(ctx->d_cmask.upload(ctx->cmask, ctx->stream));
   ctx->have_dofs = true; ctx->have_plan = false;
+  if (!ctx->planning_only && !ctx->sp_elem.empty()) return rebuild_face_loads(ctx);  // the owned flags select the loaded nodes
   return MASTB200_OK;
 }
 
@@ -1046,23 +1102,19 @@ int mastb200_set_material(mastb200_context* ctx, const mastb200_material* mat) {
   return MASTB200_OK;
 }
 
-int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
-                               const double* pressure) {
-  if (!ctx) return MASTB200_ERR_ARG;
-  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+// Builds the per-node gather lists of the SURFACE_PRESSURE loads from the raw (element, side, pressure) entries.  Only
+// OWNED nodes get a list: ghost rows of R stay zero and the compliance sum of a rank covers its own nodes, so the
+// caller's sum over ranks counts every loaded node once (ghost elements carry the load of nodes on a partition cut).
+static int rebuild_face_loads(mastb200_context* ctx) {
   ctx->fl_node.clear(); ctx->fl_ptr.clear(); ctx->fl_face_nodes.clear(); ctx->fl_k.clear(); ctx->fl_p.clear();
+  const int64_t n = (int64_t)ctx->sp_elem.size();
   if (n == 0) return MASTB200_OK;
-  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "side pressure: 3D solids (HEX8, HEX27) only");
   const int nfn = ctx->elem_type == MASTB200_HEX8 ? 4 : 9, nne = ctx->nn;
-  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
-  CU(cudaSetDevice(ctx->device));
+  const int32_t* elem = ctx->sp_elem.data();
+  const int32_t* side = ctx->sp_side.data();
   // entries ordered by (element, side): the order in which the reference's element loop meets the loads
   std::vector<int64_t> order(n);
-  for (int64_t i = 0; i < n; ++i) {
-    if (elem[i] < 0 || elem[i] >= ctx->n_elem || side[i] < 0 || side[i] > 5) return ctx->fail(MASTB200_ERR_ARG, "bad side load %lld", (long long)i);
-    order[i] = i;
-  }
+  for (int64_t i = 0; i < n; ++i) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
     return elem[a] != elem[b] ? elem[a] < elem[b] : side[a] < side[b];
   });
@@ -1075,8 +1127,11 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
     for (int k = 0; k < 9; ++k) e.fn[k] = 0;
     for (int k = 0; k < nfn; ++k)
       e.fn[k] = ctx->conn[(int64_t)elem[i] * nne + (nfn == 4 ? H8_SIDE[side[i]][k] : H27_SIDE[side[i]][k])];
-    e.p = pressure[i];
-    for (int k = 0; k < nfn; ++k) { e.node = e.fn[k]; e.k = (uint8_t)k; e.seq = s; ents.push_back(e); }
+    e.p = ctx->sp_p[i];
+    for (int k = 0; k < nfn; ++k) {
+      e.node = e.fn[k]; e.k = (uint8_t)k; e.seq = s;
+      if (ctx->owned.empty() || ctx->owned[e.node]) ents.push_back(e);
+    }
   }
   std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.node < b.node; });
   for (size_t i = 0; i < ents.size(); ++i) {
@@ -1089,6 +1144,7 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
     ctx->fl_p.push_back(ents[i].p);
   }
   ctx->fl_ptr.push_back((int32_t)ents.size());
+  if (ents.empty()) { ctx->fl_ptr.clear(); return MASTB200_OK; }
   CU(ctx->d_fl_node.upload(ctx->fl_node, ctx->stream));
   CU(ctx->d_fl_ptr.upload(ctx->fl_ptr, ctx->stream));
   CU(ctx->d_fl_face_nodes.upload(ctx->fl_face_nodes, ctx->stream));
@@ -1096,6 +1152,23 @@ int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* 
   CU(ctx->d_fl_p.upload(ctx->fl_p, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return MASTB200_OK;
+}
+
+int mastb200_set_side_pressure(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
+                               const double* pressure) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh) return ctx->fail(MASTB200_ERR_ARG, "set_mesh first");
+  ctx->sp_elem.clear(); ctx->sp_side.clear(); ctx->sp_p.clear();
+  ctx->fl_node.clear(); ctx->fl_ptr.clear(); ctx->fl_face_nodes.clear(); ctx->fl_k.clear(); ctx->fl_p.clear();
+  if (n == 0) return MASTB200_OK;
+  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "side pressure: 3D solids (HEX8, HEX27) only");
+  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
+  CU(cudaSetDevice(ctx->device));
+  for (int64_t i = 0; i < n; ++i)
+    if (elem[i] < 0 || elem[i] >= ctx->n_elem || side[i] < 0 || side[i] > 5) return ctx->fail(MASTB200_ERR_ARG, "bad side load %lld", (long long)i);
+  ctx->sp_elem.assign(elem, elem + n); ctx->sp_side.assign(side, side + n); ctx->sp_p.assign(pressure, pressure + n);
+  return rebuild_face_loads(ctx);
 }
 
 int mastb200_set_heat_side_loads(mastb200_context* ctx, int64_t n, const int32_t* elem, const int32_t* side,
@@ -1235,6 +1308,26 @@ int mastb200_get_pattern(const mastb200_context* ctx, int64_t* row_ptr, int32_t*
   return MASTB200_OK;
 }
 
+int mastb200_get_pattern_rows(const mastb200_context* ctx, int64_t n, const int64_t* rows, int64_t* row_begin,
+                              int32_t* row_len, int32_t* col_idx) {
+  if (!ctx || !ctx->have_plan || n < 0 || (n > 0 && (!rows || !row_begin || !row_len))) return MASTB200_ERR_ARG;
+  const Pattern& P = ctx->pat;
+  const int nv = ctx->nv;
+  int64_t k = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    const int64_t r = rows[i];
+    if (r < 0 || r >= P.n_owned * nv) return MASTB200_ERR_ARG;
+    const int64_t node = r / nv, v = r - node * nv;
+    const int64_t b = P.nbr_ptr[node], e = P.nbr_ptr[node + 1];
+    row_begin[i] = b * nv * nv + v * (e - b) * nv;  // the nv rows of a node are contiguous, (e - b) * nv values each
+    row_len[i] = (int32_t)((e - b) * nv);
+    if (col_idx)
+      for (int64_t j = b; j < e; ++j)
+        for (int w = 0; w < nv; ++w) col_idx[k++] = P.nbr[j] * nv + w;
+  }
+  return MASTB200_OK;
+}
+
 int mastb200_get_row_dofs(const mastb200_context* ctx, int64_t* row_dof) {
   if (!ctx || !ctx->have_plan || !row_dof) return MASTB200_ERR_ARG;
   for (int64_t r = 0; r < ctx->pat.n_owned; ++r)
@@ -1302,13 +1395,127 @@ int mastb200_apply_dv_map_transpose(mastb200_context* ctx, const double* G, int6
   return MASTB200_OK;
 }
 
+int mastb200_set_point_loads(mastb200_context* ctx, int64_t n, const int32_t* node, const double* load) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  if (!ctx->have_mesh || !ctx->have_dofs) return ctx->fail(MASTB200_ERR_ARG, "set_mesh and set_dof_map first");
+  if (ctx->planning_only) return ctx->fail(MASTB200_ERR_CUDA, "planning-only context");
+  ctx->pl_node.clear(); ctx->pl_load.clear();
+  if (n == 0) return MASTB200_OK;
+  if (!node || !load) return MASTB200_ERR_ARG;
+  CU(cudaSetDevice(ctx->device));
+  const int nv = ctx->nv;
+  std::vector<int64_t> order(n);
+  for (int64_t i = 0; i < n; ++i) {
+    if (node[i] < 0 || node[i] >= ctx->n_nodes) return ctx->fail(MASTB200_ERR_ARG, "bad point load %lld", (long long)i);
+    order[i] = i;
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return node[a] < node[b]; });
+  for (int64_t s = 0; s < n; ++s) {
+    const int64_t i = order[s];
+    if (!ctx->owned.empty() && !ctx->owned[node[i]]) continue;  // the reference zeroes components of other ranks' dofs
+    if (ctx->pl_node.empty() || ctx->pl_node.back() != node[i]) {
+      ctx->pl_node.push_back(node[i]);
+      ctx->pl_load.insert(ctx->pl_load.end(), nv, 0.);
+    }
+    for (int v = 0; v < nv; ++v) ctx->pl_load[ctx->pl_load.size() - nv + v] += load[i * nv + v];
+  }
+  if (ctx->pl_node.empty()) return MASTB200_OK;
+  CU(ctx->d_pl_node.upload(ctx->pl_node, ctx->stream));
+  CU(ctx->d_pl_load.upload(ctx->pl_load, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
+int mastb200_sensitivity_assemble(mastb200_context* ctx, const double* X, int32_t param, int64_t n_k, const int32_t* dv_node,
+                                  const double* dv_weight, double* dRdp) {
+  if (!ctx || !X || !dRdp) return MASTB200_ERR_ARG;
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "sensitivity_assemble: 3D solids (HEX8, HEX27) only");
+  if (ctx->thermal)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
+  CU(cudaSetDevice(ctx->device));
+  const double nu = ctx->mat.nu;
+  const double lam1 = nu / (1. - nu - 2. * nu * nu), mu1 = 1. / 2. / (1. + nu);
+  if (param == MASTB200_PARAM_DENSITY_DV) {
+    if (!ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "a density design variable needs a nodal density field");
+    if (n_k < 0 || (n_k > 0 && (!dv_node || !dv_weight))) return MASTB200_ERR_ARG;
+    for (int64_t k = 0; k < n_k; ++k)
+      if (dv_node[k] < 0 || dv_node[k] >= ctx->n_nodes) return ctx->fail(MASTB200_ERR_ARG, "bad design-variable node");
+    // nodal derivative field d(rho_n)/dp: the filter column of the design variable, zero outside its support
+    CU(ctx->d_dfield.ensure(ctx->n_nodes));
+    CU(cudaMemsetAsync(ctx->d_dfield.p, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
+    if (n_k > 0) {
+      CU(ctx->d_dvn.ensure(n_k)); CU(ctx->d_dvw.ensure(n_k));
+      CU(cudaMemcpyAsync(ctx->d_dvn.p, dv_node, n_k * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_dvw.p, dv_weight, n_k * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      CU(launch_scatter_field(n_k, ctx->d_dvn.p, ctx->d_dvw.p, ctx->d_dfield.p, ctx->stream));
+      ctx->launches++;
+    }
+    return run_internal_force(ctx, X, 1, ctx->d_dfield.p, lam1, mu1, dRdp);
+  }
+  if (param == MASTB200_PARAM_E) return run_internal_force(ctx, X, 2, nullptr, lam1, mu1, dRdp);
+  if (param == MASTB200_PARAM_NU) {
+    // d/dnu of the unit-modulus Lame constants of isotropic_material_property_card.cpp:512-528 (derivative :530-567)
+    const double den = 1. - nu - 2. * nu * nu;
+    const double dlam = (den + nu * (1. + 4. * nu)) / (den * den), dmu = -1. / 2. / ((1. + nu) * (1. + nu));
+    return run_internal_force(ctx, X, 3, nullptr, dlam, dmu, dRdp);
+  }
+  return ctx->fail(MASTB200_ERR_ARG, "unknown parameter kind %d", (int)param);
+}
+
+int mastb200_linearized_jacobian_solution_product(mastb200_context* ctx, const double* X, const double* dX, double* out) {
+  if (!ctx || !dX || !out) return MASTB200_ERR_ARG;
+  (void)X;  // linear strain: the tangent does not depend on the state
+  int rc = check_ready(ctx);
+  if (rc) return rc;
+  if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "linearized_jacobian_solution_product: 3D solids (HEX8, HEX27) only");
+  CU(cudaSetDevice(ctx->device));
+  const double nu = ctx->mat.nu;
+  return run_internal_force(ctx, dX, 0, nullptr, nu / (1. - nu - 2. * nu * nu), 1. / 2. / (1. + nu), out);
+}
+
+// -f_th . V over the owned nodes, f_th = the TEMPERATURE volume load as an element force vector (mode 4)
+static int thermal_load_dot(mastb200_context* ctx, const double* V, double* val, double* vec_out) {
+  // value: the unconstrained load vector (compliance_output.cpp:71-102); derivative: constrained rows zeroed (:265-296)
+  int rc;
+  const double nu = ctx->mat.nu;
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  CU(ctx->d_vec2.ensure(n_dof));
+  const double* dV = nullptr;
+  if (V && (rc = resolve_in(ctx, V, n_dof, ctx->d_X, &dV))) return rc;
+  if ((rc = run_internal_force(ctx, dV ? dV : ctx->d_vec2.p, 4, nullptr, nu / (1. - nu - 2. * nu * nu), 1. / 2. / (1. + nu),
+                               ctx->d_vec2.p, val == nullptr)))
+    return rc;
+  if (vec_out) CU(cudaMemcpyAsync(vec_out, ctx->d_vec2.p, n_dof * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  if (val) {
+    const int nb = 1024;
+    CU(ctx->d_partial.ensure(4096));
+    CU(ctx->d_scalar.ensure(8));
+    CU(launch_dot_owned(ctx->d_vec2.p, dV, ctx->d_owned_nodes.p, ctx->pat.n_owned, ctx->nv, ctx->d_partial.p, nb, ctx->stream));
+    CU(launch_reduce_partials(ctx->d_partial.p, nb, ctx->d_scalar.p + 1, ctx->stream));
+    ctx->launches += 2;
+    CU(cudaMemcpyAsync(val, ctx->d_scalar.p + 1, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return MASTB200_OK;
+}
+
 int mastb200_compliance(mastb200_context* ctx, const double* X, double* q) {
   if (!ctx || !q || !X) return MASTB200_ERR_ARG;
   int rc = check_ready(ctx);
   if (rc) return rc;
-  if (ctx->thermal) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance with a thermoelastic load is not on the device path yet");
   CU(cudaSetDevice(ctx->device));
   *q = 0.;
+  double q_th = 0.;
+  if (ctx->thermal) {  // volume_external_residual: vec = -f_th (thermal_residual), compliance -= vec . u
+    if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+      return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance with a thermoelastic load: 3D solids only");
+    if ((rc = thermal_load_dot(ctx, X, &q_th, nullptr))) return rc;
+    *q = q_th;
+  }
   if (ctx->fl_node.empty()) return MASTB200_OK;
   const double* dX = nullptr;
   if ((rc = resolve_in(ctx, X, size_t(ctx->n_nodes) * ctx->nv, ctx->d_X, &dX))) return rc;
@@ -1320,7 +1527,19 @@ int mastb200_compliance(mastb200_context* ctx, const double* X, double* q) {
   ctx->launches += 2;
   CU(cudaMemcpyAsync(q, ctx->d_scalar.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  *q += q_th;
   return MASTB200_OK;
+}
+
+int mastb200_compliance_direct_sensitivity(mastb200_context* ctx, const double* X, const double* dXdp, double* dq) {
+  // ComplianceOutput::evaluate_sensitivity (compliance_output.cpp:106-150): -d(f_ext)/dp . u - f_ext . du/dp; the loads on
+  // the device path (non-follower pressure, thermal load at fixed modulus) do not depend on the parameter, and the
+  // output is linear in the state
+  (void)X;
+  if (!ctx || !dq) return MASTB200_ERR_ARG;
+  *dq = 0.;
+  if (!dXdp) return MASTB200_OK;
+  return mastb200_compliance(ctx, dXdp, dq);
 }
 
 int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, double* dq_dX) {
@@ -1328,10 +1547,20 @@ int mastb200_compliance_derivative(mastb200_context* ctx, const double* X, doubl
   (void)X;  // linear in X: -f_ext does not depend on the state for non-follower pressure loads
   int rc = check_ready(ctx);
   if (rc) return rc;
-  if (ctx->thermal) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance with a thermoelastic load is not on the device path yet");
   CU(cudaSetDevice(ctx->device));
   const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
   double* d = nullptr;
+  if (ctx->thermal) {  // dq/dX = -vec = +f_th on the unconstrained dofs; the pressure part is set on its own (loaded) dofs
+    if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
+      return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance with a thermoelastic load: 3D solids only");
+    if (!ctx->fl_node.empty())
+      return ctx->fail(MASTB200_ERR_UNSUPPORTED, "compliance derivative with both a pressure and a thermoelastic load is not on the device path");
+    if ((rc = thermal_load_dot(ctx, nullptr, nullptr, nullptr))) return rc;
+    if (is_device_ptr(dq_dX)) CU(cudaMemcpyAsync(dq_dX, ctx->d_vec2.p, n_dof * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    else CU(cudaMemcpyAsync(dq_dX, ctx->d_vec2.p, n_dof * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return MASTB200_OK;
+  }
   if ((rc = resolve_out(ctx, dq_dX, n_dof, ctx->d_dq, &d))) return rc;
   CU(cudaMemsetAsync(d, 0, n_dof * sizeof(double), ctx->stream));
   if (!ctx->fl_node.empty()) {

@@ -178,6 +178,8 @@ struct StressParams {
   const double* xyz = nullptr;
   const double* X = nullptr;
   const double* rho = nullptr;
+  const double* temperature = nullptr;   // nodal temperature or null (T_const): thermal stress of the matrix-free force, mode 4
+  double alpha_k = 0., T_const = 0., T_ref = 0.;
   const uint8_t* elem_mask = nullptr;    // participating elements or null (all)
   const uint8_t* diag_elem = nullptr;
   const uint8_t* cmask = nullptr;
@@ -198,6 +200,10 @@ int stress_blocks(int64_t n_elem, int nq);
 cudaError_t launch_stress_qp(const StressParams& p, cudaStream_t stream);
 cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaStream_t stream);
 cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream);  // two launches
+// matrix-free internal force with a per-point modulus into p.dq_dX (two launches); scratch: [n_elem*nq][9] doubles.
+// mode 0 E(rho), 1 density design variable (dfield = nodal filter column), 2 d/dE0, 3 lam1 / mu1 are d/dnu,
+// 4 thermal stress E(rho) alpha_k (T - T_ref) I instead of D eps (the TEMPERATURE volume load as a force vector)
+cudaError_t launch_internal_force(const StressParams& p, int mode, const double* dfield, cudaStream_t stream);
 // density sensitivities alone (no R/J): G[n] = adj . dR/d(rho_n); scratch: [n_elem*nq] doubles (two launches)
 cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream);
 // dq/d(rho_n) of the stress aggregate at fixed state (two launches); scratch: [n_elem*nq] doubles
@@ -223,6 +229,13 @@ int face_loads_blocks(int n_loaded_nodes);
 cudaError_t launch_reduce_partials(const double* partial, int n, double* out, cudaStream_t stream);
 cudaError_t launch_sumsq_owned(const double* R, const int32_t* owned_nodes, int64_t n_owned, int nv, double* partial,
                                int n_blocks, cudaStream_t stream);
+
+// point loads: R[nv*node[t]+i] -= load[t*nv+i] on unconstrained dofs; field[node[t]] = w[t]; sum over owned nodes of a.b
+cudaError_t launch_point_loads(int n, const int32_t* node, const double* load, const uint8_t* cmask, int nv, double* R,
+                              cudaStream_t stream);
+cudaError_t launch_scatter_field(int64_t n, const int32_t* node, const double* w, double* field, cudaStream_t stream);
+cudaError_t launch_dot_owned(const double* a, const double* b, const int32_t* owned_nodes, int64_t n_owned, int nv,
+                             double* partial, int n_blocks, cudaStream_t stream);
 
 // G^T W : sens[i] = sum_k w[k] * G[node[k]]
 cudaError_t launch_dv_map_transpose(const double* G, int64_t n_dv, const int64_t* dv_ptr, const int32_t* dv_node,

@@ -139,6 +139,44 @@ __global__ void __launch_bounds__(256) sumsq_owned_kernel(const double* __restri
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
+// point loads (nonlinear_implicit_assembly.cpp:190-247): R[dofs of node] -= load, constrained dofs untouched; the host has
+// summed the loads of a node in the order they were given and dropped the nodes this rank does not own
+__global__ void __launch_bounds__(128) point_load_kernel(int n, const int32_t* __restrict__ node, const double* __restrict__ load,
+                                                         const uint8_t* __restrict__ cmask, int nv, double* R) {
+  const int t = blockIdx.x * 128 + threadIdx.x;
+  if (t >= n) return;
+  const int nd = node[t];
+  const unsigned cm = cmask ? cmask[nd] : 0u;
+  for (int i = 0; i < nv; ++i)
+    if (!((cm >> i) & 1u)) R[(int64_t)nd * nv + i] -= load[(int64_t)t * nv + i];
+}
+
+__global__ void __launch_bounds__(128) scatter_field_kernel(int64_t n, const int32_t* __restrict__ node,
+                                                            const double* __restrict__ w, double* field) {
+  const int64_t t = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (t < n) field[node[t]] = w[t];
+}
+
+// sum over the owned nodes of a . b (fixed grid: deterministic two-stage reduction)
+__global__ void __launch_bounds__(256) dot_owned_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                                        const int32_t* __restrict__ owned, int64_t n_owned, int nv, double* partial) {
+  __shared__ double red[256];
+  double s = 0.;
+  const int64_t total = n_owned * nv;
+  for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < total; k += (int64_t)gridDim.x * 256) {
+    const int64_t r = k / nv;
+    const int64_t i = (int64_t)owned[r] * nv + (k - r * nv);
+    s += a[i] * b[i];
+  }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) {
+    if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
 __global__ void __launch_bounds__(128) dv_map_transpose_kernel(const double* __restrict__ G, int64_t n_dv,
                                                                const int64_t* __restrict__ dv_ptr,
                                                                const int32_t* __restrict__ dv_node,
@@ -171,6 +209,25 @@ cudaError_t launch_reduce_partials(const double* partial, int n, double* out, cu
 cudaError_t launch_sumsq_owned(const double* R, const int32_t* owned_nodes, int64_t n_owned, int nv, double* partial,
                                int n_blocks, cudaStream_t stream) {
   sumsq_owned_kernel<<<n_blocks, 256, 0, stream>>>(R, owned_nodes, n_owned, nv, partial);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_point_loads(int n, const int32_t* node, const double* load, const uint8_t* cmask, int nv, double* R,
+                              cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  point_load_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, node, load, cmask, nv, R);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_field(int64_t n, const int32_t* node, const double* w, double* field, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  scatter_field_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, node, w, field);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_dot_owned(const double* a, const double* b, const int32_t* owned_nodes, int64_t n_owned, int nv,
+                             double* partial, int n_blocks, cudaStream_t stream) {
+  dot_owned_kernel<<<n_blocks, 256, 0, stream>>>(a, b, owned_nodes, n_owned, nv, partial);
   return cudaGetLastError();
 }
 

@@ -97,6 +97,15 @@ __device__ __forceinline__ void eval_qp(const StressParams& p, int64_t e, int q,
   g.sig[3] = mu * g.eps[3]; g.sig[4] = mu * g.eps[4]; g.sig[5] = mu * g.eps[5];
 }
 
+// rho^(penalty-1) of E'(rho): the usual small integer SIMP penalties by multiplication
+__device__ __forceinline__ double pow_pm1(double rho, double pm1) {
+  if (pm1 == 3.) return rho * rho * rho;
+  if (pm1 == 2.) return rho * rho;
+  if (pm1 == 1.) return rho;
+  if (pm1 == 0.) return 1.;
+  return pow(rho, pm1);
+}
+
 __device__ __forceinline__ double vm_pp(const double* s) {
   const double a = s[0] - s[1], b = s[1] - s[2], c = s[2] - s[0];
   return 0.5 * (a * a + b * b + c * c) + 3.0 * (s[3] * s[3] + s[4] * s[4] + s[5] * s[5]);
@@ -139,7 +148,8 @@ __global__ void __launch_bounds__(TB) stress_qp_kernel(const StressParams p) {
       for (int i = 0; i < 6; ++i) p.out_strain[t * 6 + i] = g.eps[i];
     if (p.out_vm) p.out_vm[t] = vm;
     if (p.out_jxw) p.out_jxw[t] = JxW;
-    if (p.partial && (!p.elem_mask || p.elem_mask[e])) {
+    // diagonal_elem_subdomain_id elements take no part in outputs (assembly_base.cpp:299), as in the derivative kernels
+    if (p.partial && (!p.elem_mask || p.elem_mask[e]) && !(p.diag_elem && p.diag_elem[e])) {
       const double sp = (vm - p.sigma0) / p.sigma0;  // p_norm_weight = 1 (stress_output_base.cpp:278-281)
       const double ex = (p.rho_exp * sp > 1.e2) ? exp(1.e2) : exp(p.rho_exp * sp);
       num = pow(vm / p.sigma0, p.p_norm) * ex * JxW;
@@ -221,6 +231,64 @@ __global__ void __launch_bounds__(TB) stress_dq_qp_kernel(const StressParams p) 
       T[k * 3 + r] = kappa * (M[k][0] * g.inv[0][r] + M[k][1] * g.inv[1][r] + M[k][2] * g.inv[2][r]);
 }
 
+
+// ---- matrix-free internal force with a per-point modulus (linear strain) -------------------------------------------------
+// f_a = sum_q JxW B_a^T sigma_q with sigma_q = Ehat_q D_1 eps(u): the element vector of StructuralElement3D::
+// internal_residual (solid_element_3d.cpp:135-423) when Ehat = E(rho_q), of ::internal_residual_sensitivity (:566-788, D <-
+// dD/dp at :640) when Ehat / D_1 carry the parameter derivative, and of elem_linearized_jacobian_solution_product
+// (structural_nonlinear_assembly.cpp:142-166) when u is the perturbation dX.  Same three passes as the aggregate
+// derivative: T_q = JxW sigma_q J^-T per point, then the row-owner gather f_a = sum_e sum_q T_q dN_a/dxi(q) in ascending
+// element id with constrained dofs zeroed per element (constrain_element_vector).
+//   mode 0: Ehat = E(rho_q)                                   (f_int of the state, J dX of a perturbation)
+//   mode 1: Ehat = E'(rho_q) sum_b N_b(q) dfield[b]           (nodal-density design variable with filter column dfield)
+//   mode 2: Ehat = E(rho_q) / E0                              (parameter E0 of the property card)
+//   mode 3: Ehat = E(rho_q), D_1 <- dD_1/dnu (lam1, mu1 of the params are the derivatives)
+//   mode 4: sigma_q = E(rho_q) alpha_k (T_q - T_ref) I: the TEMPERATURE volume load B^T D alpha dT of thermal_residual
+//           (solid_element_3d.cpp:950-1089, linear strain) as a force vector
+__global__ void __launch_bounds__(TB) force_qp_kernel(const StressParams p, int mode, const double* __restrict__ dfield) {
+  const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
+  const int64_t nqp = p.n_elem * p.nq;
+  if (t >= nqp) return;
+  const int64_t e = t / p.nq;
+  const int q = (int)(t - e * p.nq);
+  double* T = p.scratch + t * 9;
+  if (p.diag_elem && p.diag_elem[e]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) T[i] = 0.;
+    return;
+  }
+  QpGeom g;
+  eval_qp(p, e, q, g);  // sig = E(rho_q) D_1 eps with the lam1 / mu1 of the params
+  double f = g.det * g.wq;
+  if (mode == 1) {
+    const double* Nt = p.tab + (size_t)q * p.nn;
+    const int32_t* en = p.conn + e * p.nn;
+    double dr = 0.;
+    for (int b = 0; b < p.nn; ++b) dr = fma(Nt[b], dfield[en[b]], dr);
+    const double dE = p.E0 * (1. - p.rho_min) * p.penalty * pow_pm1(g.rho, p.penalty - 1.);
+    f *= dE * dr / g.E;
+  } else if (mode == 2) {
+    f /= p.E0;
+  }
+  if (mode == 4) {
+    double Tq = p.T_const;
+    if (p.temperature) {
+      const double* Nt = p.tab + (size_t)q * p.nn;
+      const int32_t* en = p.conn + e * p.nn;
+      Tq = 0.;
+      for (int b = 0; b < p.nn; ++b) Tq = fma(Nt[b], p.temperature[en[b]], Tq);
+    }
+    const double st = g.E * p.alpha_k * (Tq - p.T_ref);
+    g.sig[0] = g.sig[1] = g.sig[2] = st;
+    g.sig[3] = g.sig[4] = g.sig[5] = 0.;
+  }
+  const double S[3][3] = {{g.sig[0], g.sig[3], g.sig[5]}, {g.sig[3], g.sig[1], g.sig[4]}, {g.sig[5], g.sig[4], g.sig[2]}};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) T[k * 3 + r] = f * (S[k][0] * g.inv[0][r] + S[k][1] * g.inv[1][r] + S[k][2] * g.inv[2][r]);
+}
+
 // pass 3: dq_dX rows of the owned nodes
 __global__ void __launch_bounds__(TB) stress_dq_gather_kernel(const StressParams p) {
   const int64_t r = (int64_t)blockIdx.x * TB + threadIdx.x;
@@ -271,6 +339,13 @@ cudaError_t launch_stress_qp(const StressParams& p, cudaStream_t stream) {
 }
 cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaStream_t stream) {
   reduce_pairs_kernel<<<1, 32, 0, stream>>>(partial, n, out);
+  return cudaGetLastError();
+}
+cudaError_t launch_internal_force(const StressParams& p, int mode, const double* dfield, cudaStream_t stream) {
+  force_qp_kernel<<<stress_blocks(p.n_elem, p.nq), TB, 0, stream>>>(p, mode, dfield);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  stress_dq_gather_kernel<<<(int)((p.n_owned + TB - 1) / TB), TB, 0, stream>>>(p);
   return cudaGetLastError();
 }
 cudaError_t launch_stress_derivative(const StressParams& p, cudaStream_t stream) {

@@ -500,7 +500,8 @@ static void add_scaled_top_left(Mat& jac, const Mat& m, double s) {  // jac.topL
 // f has nd entries, jac nd x nd (nd = nv*nn); only the leading 3nn block is touched, plus the
 // rotational diagonal when nv == 6 (:413-417).
 static void solid3d_internal_residual(const OracleProblem* p, const FE& fe, const int32_t* en, const Vec& sol,
-                                      bool request_jacobian, Vec& f, Mat& jac, const double* drho_nodal /*sens*/) {
+                                      bool request_jacobian, Vec& f, Mat& jac, const double* drho_nodal /*sens*/,
+                                      int param_kind = 0 /* 1: d/dE0, 2: d/dnu of the property card (internal_residual_sensitivity) */) {
   const int nn = fe.nn, n2 = 3 * nn;
   const bool nl = p->nonlinear_strain != 0;
   Vec disp(sol.begin(), sol.begin() + n2), stress, vec2, vec3;
@@ -509,7 +510,9 @@ static void solid3d_internal_residual(const OracleProblem* p, const FE& fe, cons
   strain_ops_reinit(s, nn);
   Modulus mod{p};
   for (int qp = 0; qp < fe.nq; ++qp) {
-    if (!drho_nodal) stiffness_3d(mod.E(fe, en, qp), p->nu, D);                                  // :272
+    if (param_kind == 1) stiffness_3d_derivative(mod.E(fe, en, qp), p->nu, mod.E(fe, en, qp) / p->E0, 0., D);  // :640, dE(x)/dE0
+    else if (param_kind == 2) stiffness_3d_derivative(mod.E(fe, en, qp), p->nu, 0., 1., D);              // :640, dnu/dnu = 1
+    else if (!drho_nodal) stiffness_3d(mod.E(fe, en, qp), p->nu, D);                                  // :272
     else stiffness_3d_derivative(mod.E(fe, en, qp), p->nu, mod.dE(fe, en, qp, drho_nodal), 0., D);  // :640
     init_strain_operator(fe, qp, nl, disp, s);
     stress = matvec(D, s.eps);  // :289 (Gmat*alpha == 0: incompatible modes are inert)
@@ -1162,6 +1165,81 @@ int oracle_sensitivity_assemble(const OracleProblem* p, const double* X, int64_t
     constrain(p, di, nullptr, &vec);                          // :613
     for (int i = 0; i < nd; ++i) dres_dp[di[i]] += vec[i];  // :616
   }
+  return 0;
+}
+
+// NonlinearImplicitAssembly::sensitivity_assemble (nonlinear_implicit_assembly.cpp:515-686) for a Parameter of the
+// isotropic property card: kind 1 = E0, 2 = nu; every element depends on it (no ElemParameterDependence skip)
+int oracle_sensitivity_assemble_param(const OracleProblem* p, const double* X, int kind, double* dres_dp) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  if (p->elem_type == ORACLE_QUAD4) return 3;
+  if (p->thermal) return 4;  // 3D thermal_residual_sensitivity is libmesh_error() (solid_element_3d.cpp:1093-1104)
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::fill(dres_dp, dres_dp + n_dof, 0.);
+  std::vector<int64_t> di;
+  std::vector<double> Xe;
+  Vec sol, vec;
+  Mat dummy;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size());
+    sol.resize(nd);
+    for (int i = 0; i < nd; ++i) sol[i] = X[di[i]];
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    vec.assign(nd, 0.);
+    dummy.resize(nd, nd);
+    solid3d_internal_residual(p, fe, &p->conn[e * ei.nn], sol, false, vec, dummy, nullptr, kind);
+    constrain(p, di, nullptr, &vec);
+    for (int i = 0; i < nd; ++i) dres_dp[di[i]] += vec[i];
+  }
+  return 0;
+}
+
+// NonlinearImplicitAssembly::linearized_jacobian_solution_product (nonlinear_implicit_assembly.cpp:270-383) with
+// StructuralNonlinearAssemblyElemOperations::elem_linearized_jacobian_solution_product
+// (structural_nonlinear_assembly.cpp:142-166): vec = K_e(sol) dsol (StructuralElementBase::linearized_internal_residual,
+// structural_element_base.cpp:224-252; the non-follower pressure and the linear-strain thermal load have no tangent),
+// constrain_element_vector, add
+int oracle_linearized_jacobian_solution_product(const OracleProblem* p, const double* X, const double* dX, double* out) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  if (p->elem_type == ORACLE_QUAD4) return 3;
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::fill(out, out + n_dof, 0.);
+  std::vector<int64_t> di;
+  std::vector<double> Xe;
+  Vec sol, dsol, v, vec;
+  Mat m;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size());
+    sol.resize(nd); dsol.resize(nd);
+    for (int i = 0; i < nd; ++i) { sol[i] = X[di[i]]; dsol[i] = dX[di[i]]; }
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    v.assign(nd, 0.);
+    m.resize(nd, nd);
+    solid3d_internal_residual(p, fe, &p->conn[e * ei.nn], sol, true, v, m, nullptr);
+    vec = matvec(m, dsol);
+    constrain(p, di, nullptr, &vec);
+    for (int i = 0; i < nd; ++i) out[di[i]] += vec[i];
+  }
+  return 0;
+}
+
+// the point loads of NonlinearImplicitAssembly::residual_and_jacobian (nonlinear_implicit_assembly.cpp:190-247): for every
+// (node, load[nv]) entry vec = -load, constrain_element_vector (constrained dofs zeroed), R.add_vector
+int oracle_add_point_loads(const OracleProblem* p, int64_t n, const int32_t* node, const double* load, double* R) {
+  for (int64_t i = 0; i < n; ++i)
+    for (int v = 0; v < p->nv; ++v) {
+      const int64_t d = int64_t(node[i]) * p->nv + v;
+      if (p->constrained && p->constrained[d]) continue;
+      R[d] += -load[i * p->nv + v];
+    }
   return 0;
 }
 

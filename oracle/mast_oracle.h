@@ -87,6 +87,13 @@ int oracle_elem_calculations(const OracleProblem* p, int64_t e, const double* X,
 int oracle_sensitivity_assemble(const OracleProblem* p, const double* X, int64_t dv_begin, int64_t dv_end,
                                 const int32_t* dv_node, const double* dv_weight, double* dres_dp);
 
+/* sensitivity_assemble for a Parameter of the isotropic card: kind 1 = E0, 2 = nu -> dres_dp[n_dof] */
+int oracle_sensitivity_assemble_param(const OracleProblem* p, const double* X, int kind, double* dres_dp);
+/* NonlinearImplicitAssembly::linearized_jacobian_solution_product: out[n_dof] = sum_e constrain(K_e(X) dX_e) */
+int oracle_linearized_jacobian_solution_product(const OracleProblem* p, const double* X, const double* dX, double* out);
+/* point loads of residual_and_jacobian: R[dofs of node[i]] -= load[i][nv] on unconstrained dofs */
+int oracle_add_point_loads(const OracleProblem* p, int64_t n, const int32_t* node, const double* load, double* R);
+
 /* AssemblyBase::calculate_output_adjoint_sensitivity_multiple_parameters_no_direct: sens[i] = adj . dR/dp_i */
 int oracle_adjoint_sensitivity(const OracleProblem* p, const double* X, const double* adj, int64_t n_dv,
                                const int64_t* dv_ptr, const int32_t* dv_node, const double* dv_weight,

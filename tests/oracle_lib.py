@@ -39,6 +39,9 @@ def lib():
         L.oracle_elem_calculations.argtypes = [P, i64, vp, C.c_int, vp, vp]
         L.oracle_sensitivity_assemble.argtypes = [P, vp, i64, i64, vp, vp, vp]
         L.oracle_adjoint_sensitivity.argtypes = [P, vp, vp, i64, vp, vp, vp, vp]
+        L.oracle_sensitivity_assemble_param.argtypes = [P, vp, C.c_int, vp]
+        L.oracle_linearized_jacobian_solution_product.argtypes = [P, vp, vp, vp]
+        L.oracle_add_point_loads.argtypes = [P, i64, vp, vp, vp]
         L.oracle_compliance.argtypes = [P, vp]; L.oracle_compliance.restype = dbl
         L.oracle_compliance_derivative.argtypes = [P, vp, vp]
         L.oracle_stress.argtypes = [P, vp, vp, vp, vp, vp]
@@ -145,6 +148,24 @@ class Problem:
         rc = lib().oracle_sensitivity_assemble(C.byref(self.s), _p(X), 0, len(dv_node), _p(dv_node), _p(dv_weight), _p(out))
         assert rc == 0, rc
         return out
+
+    def sensitivity_assemble_param(self, X, kind):
+        """dR/dp for a Parameter of the isotropic card: kind 1 = E0, 2 = nu."""
+        out = np.empty(self.n_dof)
+        rc = lib().oracle_sensitivity_assemble_param(C.byref(self.s), _p(X), int(kind), _p(out))
+        assert rc == 0, rc
+        return out
+
+    def linearized_jacobian_solution_product(self, X, dX):
+        out = np.empty(self.n_dof)
+        rc = lib().oracle_linearized_jacobian_solution_product(C.byref(self.s), _p(X), _p(dX), _p(out))
+        assert rc == 0, rc
+        return out
+
+    def add_point_loads(self, R, node, load):
+        node = np.ascontiguousarray(node, np.int32); load = np.ascontiguousarray(load, np.float64)
+        assert lib().oracle_add_point_loads(C.byref(self.s), len(node), _p(node), _p(load), _p(R)) == 0
+        return R
 
     def compliance(self, X):
         return lib().oracle_compliance(C.byref(self.s), _p(X))
