@@ -202,6 +202,47 @@ int mastb200_stress_functional_density_derivative(mastb200_context* ctx, const d
                                                   double sigma0, const uint8_t* elem_mask, const double* sums,
                                                   double* dq_drho);
 
+/* ---- communicator: ghost exchange and sums over the ranks of one box (NCCL over NVLink) ------------------------- */
+/* One process per GPU.  Rank 0 calls mastb200_comm_unique_id (id: at least 128 bytes), the host broadcasts the bytes by
+ * whatever it has (MPI_Bcast in a MAST run, torch.distributed in bench.py), every rank calls mastb200_comm_init; or an
+ * existing ncclComm_t is attached (not destroyed with the context).  libnccl.so.2 is loaded on first use (dlopen). */
+int mastb200_comm_unique_id(void* id, int32_t bytes);
+int mastb200_comm_init(mastb200_context* ctx, int32_t rank, int32_t world, const void* id);
+int mastb200_comm_attach(mastb200_context* ctx, void* nccl_comm, int32_t rank, int32_t world);
+/* Ghost lists in the context's local node numbering, per neighbouring rank k (CSR over the neighbours):
+ * send_nodes[send_ptr[k] .. send_ptr[k+1]) = my owned nodes rank nbr_rank[k] keeps as ghosts, recv_nodes[...] = my ghosts it
+ * owns; both sides list the shared nodes in the same order.  Contiguous ranges travel without packing.
+ * auto_localize = 1: every sweep refreshes the ghost values of its X (adjoint, ...) itself before the kernels, on the
+ * context stream -- X must then be a device vector and is updated in place; n_nbr = 0 clears.
+ *   <- AssemblyBase::build_localized_vector, src/base/assembly_base.cpp:209-228 (send_list of the libMesh dof map) */
+int mastb200_set_ghost_exchange(mastb200_context* ctx, int32_t n_nbr, const int32_t* nbr_rank, const int64_t* send_ptr,
+                                const int32_t* send_nodes, const int64_t* recv_ptr, const int32_t* recv_nodes,
+                                int32_t auto_localize);
+/* V [h|d]: [n_nodes*width] with valid owned values; the ghost values are fetched from their owners, in place. */
+int mastb200_build_localized_vector(mastb200_context* ctx, double* V, int32_t width);
+/* vals[n] (host, n <= 64) summed over the ranks in place (res_l2_norm^2, compliance, aggregate sums); no-op for one rank */
+int mastb200_all_reduce_sum(mastb200_context* ctx, double* vals, int32_t n);
+
+/* ---- the linear solve after assembly, on the device CSR ----------------------------------------------------------- */
+typedef struct mastb200_solve_info {
+  int32_t iterations, converged;
+  double rel_residual;  /* |rhs - J x| / |rhs| of the recurrence */
+  double solve_ms;      /* CUDA-event time of the solve on the context stream */
+} mastb200_solve_info;
+/* x [h|d]: [n_nodes*nv] solution of J x = rhs over the owned rows by conjugate gradients with the 3x3 node blocks of J as
+ * the preconditioner, initial guess zero, stop at |r| <= rtol |rhs| or max_it iterations.  J_vals [h|d] in the order of
+ * mastb200_get_pattern (normally the device array the last sweep filled: J never leaves HBM); rhs [h|d].
+ * 3-dof structural system (nv = 3; HEX8, HEX27); with a communicator the ranks solve the distributed system together
+ * (ghost refresh of the search direction per iteration, scalars summed over the ranks).
+ *   <- NonlinearSystem::solve / sensitivity_solve / adjoint_solve: linear_solver->solve(*matrix, pc, dsol, rhs, tol, max_it),
+ *      src/base/nonlinear_system.cpp:777-782, 834-839 (PETSc KSP: -ksp_type cg -pc_type bjacobi) */
+int mastb200_solve(mastb200_context* ctx, const double* J_vals, const double* rhs, double* x, double rtol, int32_t max_it,
+                   mastb200_solve_info* info);
+/* modes[6][n_nodes*nv] [h|d]: the rigid-body modes a multigrid preconditioner takes as its near null space: three
+ * translations, three rotations by 1e-5 about the origin
+ *   <- StructuralNearNullVectorSpace / StructuralModes, src/elasticity/structural_near_null_vector_space.cpp:32-150 */
+int mastb200_near_null_space(mastb200_context* ctx, double* modes);
+
 /* ---- introspection for bench / tests -------------------------------------------------------- */
 typedef struct mastb200_stats {
   int64_t n_tiles, n_visits, n_owned_nodes, n_elem;

@@ -22,6 +22,8 @@ EXPORTED_SYMBOLS = [
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
     "mastb200_stress", "mastb200_stress_functional", "mastb200_stress_functional_derivative",
     "mastb200_stress_functional_density_derivative",
+    "mastb200_comm_unique_id", "mastb200_comm_init", "mastb200_comm_attach", "mastb200_set_ghost_exchange",
+    "mastb200_build_localized_vector", "mastb200_all_reduce_sum", "mastb200_solve", "mastb200_near_null_space",
     "mastb200_get_stats", "mastb200_stream", "mastb200_debug_plan_sizes", "mastb200_debug_plan_copy",
 ]
 
@@ -38,6 +40,10 @@ class Material(C.Structure):
                 ("k_beta", C.c_double), ("thickness", C.c_double), ("k_of_T", C.c_int32),
                 ("heat_source", C.c_double), ("offset", C.c_double), ("kappa", C.c_double),
                 ("plane_strain", C.c_int32)]
+
+
+class SolveInfo(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("converged", C.c_int32), ("rel_residual", C.c_double), ("solve_ms", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -101,6 +107,14 @@ def load_library():
     lib.mastb200_stress_functional.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, C.POINTER(dbl)]
     lib.mastb200_stress_functional_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
     lib.mastb200_stress_functional_density_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
+    lib.mastb200_comm_unique_id.argtypes = [vp, i32]
+    lib.mastb200_comm_init.argtypes = [vp, i32, i32, vp]
+    lib.mastb200_comm_attach.argtypes = [vp, vp, i32, i32]
+    lib.mastb200_set_ghost_exchange.argtypes = [vp, i32, vp, vp, vp, vp, vp, i32]
+    lib.mastb200_build_localized_vector.argtypes = [vp, vp, i32]
+    lib.mastb200_all_reduce_sum.argtypes = [vp, vp, i32]
+    lib.mastb200_solve.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(SolveInfo)]
+    lib.mastb200_near_null_space.argtypes = [vp, vp]
     lib.mastb200_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.mastb200_debug_plan_sizes.argtypes = [vp, i32, vp]
     lib.mastb200_debug_plan_copy.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
@@ -293,6 +307,47 @@ class Context:
         self._ck(self._lib.mastb200_stress_functional_density_derivative(self._h, _ptr(X), p_norm, rho_exp, sigma0,
                                                                          _ptr(_np(elem_mask, np.uint8)), _ptr(sums),
                                                                          _ptr(dq_drho)))
+
+    # ---- communicator, linear solve ----
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes rank 0 hands to every rank (any broadcast will do) for ``comm_init``."""
+        buf = np.zeros(128, np.uint8)
+        rc = load_library().mastb200_comm_unique_id(_ptr(buf), 128)
+        if rc:
+            raise MastB200Error(rc, load_library().mastb200_last_error(None).decode())
+        return buf
+
+    def comm_init(self, rank, world, unique_id):
+        unique_id = _np(unique_id, np.uint8)
+        self._ck(self._lib.mastb200_comm_init(self._h, int(rank), int(world), _ptr(unique_id)))
+
+    def set_ghost_exchange(self, nbr_rank, send_lists, recv_lists, auto_localize=True):
+        """send_lists[k] / recv_lists[k]: local node ids exchanged with rank nbr_rank[k] (same order on both sides)."""
+        nbr_rank = _np(nbr_rank, np.int32)
+        sp = np.concatenate([[0], np.cumsum([len(a) for a in send_lists])]).astype(np.int64)
+        rp = np.concatenate([[0], np.cumsum([len(a) for a in recv_lists])]).astype(np.int64)
+        sn = _np(np.concatenate(send_lists) if len(send_lists) else np.zeros(0), np.int32)
+        rn = _np(np.concatenate(recv_lists) if len(recv_lists) else np.zeros(0), np.int32)
+        self._ck(self._lib.mastb200_set_ghost_exchange(self._h, len(nbr_rank), _ptr(nbr_rank), _ptr(sp), _ptr(sn), _ptr(rp),
+                                                       _ptr(rn), int(bool(auto_localize))))
+
+    def build_localized_vector(self, V, width):
+        self._ck(self._lib.mastb200_build_localized_vector(self._h, _ptr(V), int(width)))
+
+    def all_reduce_sum(self, vals):
+        vals = np.ascontiguousarray(vals, np.float64)
+        self._ck(self._lib.mastb200_all_reduce_sum(self._h, _ptr(vals), len(vals)))
+        return vals
+
+    def solve(self, J, rhs, x, rtol=1e-8, max_it=10000):
+        """Block-Jacobi PCG on the device CSR; returns dict(iterations, converged, rel_residual, solve_ms)."""
+        info = SolveInfo()
+        self._ck(self._lib.mastb200_solve(self._h, _ptr(J), _ptr(rhs), _ptr(x), float(rtol), int(max_it), C.byref(info)))
+        return {k: getattr(info, k) for k, _ in SolveInfo._fields_}
+
+    def near_null_space(self, modes):
+        self._ck(self._lib.mastb200_near_null_space(self._h, _ptr(modes)))
 
     def stats(self):
         s = Stats()

@@ -3,205 +3,9 @@
 // Owns the device copies of mesh, dof map, plan and state; resolves host-or-device pointers; orders all
 // work on one CUDA stream.  There is no CPU compute path: without a usable CUDA device every sweep
 // entry point fails with MASTB200_ERR_CUDA.
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/mast_b200.h"
-#include "device_types.h"
-#include "kernels.h"
-#include "plan.h"
-
-using namespace mastb200;
-
-namespace {
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr;
-  size_t n = 0;
-  ~DevBuf() { release(); }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr; n = 0;
-  }
-  cudaError_t ensure(size_t count) {
-    if (count <= n && p) return cudaSuccess;
-    release();
-    if (count == 0) return cudaSuccess;
-    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-    if (e == cudaSuccess) n = count;
-    return e;
-  }
-  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
-    cudaError_t e = ensure(v.size());
-    if (e != cudaSuccess || v.empty()) return e;
-    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
-  }
-};
-
-bool is_device_ptr(const void* ptr) {
-  if (!ptr) return false;
-  cudaPointerAttributes at;
-  if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
-  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
-}
-
-const int H8_SIDE[6][4] = {{0, 3, 2, 1}, {0, 1, 5, 4}, {1, 2, 6, 5}, {2, 3, 7, 6}, {3, 0, 4, 7}, {4, 5, 6, 7}};
-const int H27_SIDE[6][9] = {{0, 3, 2, 1, 11, 10, 9, 8, 20},  {0, 1, 5, 4, 8, 13, 16, 12, 21}, {1, 2, 6, 5, 9, 14, 17, 13, 22},
-                            {2, 3, 7, 6, 10, 15, 18, 14, 23}, {3, 0, 4, 7, 11, 12, 19, 15, 24}, {4, 5, 6, 7, 16, 17, 18, 19, 25}};
+#include "context.h"
 
 std::string g_create_error;
-
-}  // namespace
-
-struct mastb200_context {
-  int device = 0;
-  bool planning_only = false;  // device == -1: pattern/plan construction on the host only, no sweeps
-  cudaStream_t stream = nullptr;
-  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  bool timed = false;
-  std::string err;
-  int sm_count = 0;
-
-  // mesh / dof map (host)
-  int32_t elem_type = 0, nn = 0, nv = 0;
-  int64_t n_elem = 0, n_nodes = 0;
-  std::vector<double> xyz;
-  std::vector<int32_t> conn;
-  std::vector<uint8_t> diag_elem, owned, cmask;
-  bool has_constraints = false, has_ghosts = false, has_diag = false;
-  mastb200_material mat{};
-  bool have_mesh = false, have_dofs = false, have_mat = false, have_plan = false;
-
-  Pattern pat;
-  // streaming plans: [0] plain layout (R/J of the 3-dof system), [1] aux layout (adjoint, density, temperature, nv=6)
-  struct DevicePlan {
-    bool built = false;
-    PlanLimits lim{};
-    size_t smem = 0;
-    int n_ctas = 0;
-    int64_t n_tiles = 0, n_visits = 0, bytes = 0;
-    int32_t max_live_blocks = 0, max_live_slots = 0;
-    StreamPlan host;  // kept only by planning-only contexts (tests inspect it)
-    DevBuf<TileDesc> tiles;
-    DevBuf<StepDesc> steps;
-    DevBuf<VisitRec8> visits;
-    DevBuf<FlushRow> frows;
-    DevBuf<uint32_t> fent;
-    DevBuf<LoadRec> loads;
-    void reset() {
-      built = false; host = StreamPlan();
-      tiles.release(); steps.release(); visits.release(); frows.release(); fent.release(); loads.release();
-    }
-  } dplan[2];
-  int last_plan = 0;
-  bool last_struct = false;
-  double carry_ms = 0.;  // time of the first part of a two-part sweep (R/J, then sensitivities), added to the stats
-  // device plan of the gather (QUAD4 heat) and coloured-scatter (HEX27) sweeps
-  struct GenericPlan {
-    bool built = false;
-    DevBuf<int32_t> conn, n2e, nbr, node_row, color_elems, ent_row;  // ent_row: owned row of every neighbour entry (plate)
-    DevBuf<int64_t> n2e_ptr, nbr_ptr;
-    DevBuf<uint8_t> diag, posmap;
-    DevBuf<double> tab;
-    std::vector<int32_t> color_ptr;
-    void reset() {
-      built = false; color_ptr.clear();
-      conn.release(); n2e.release(); nbr.release(); node_row.release(); color_elems.release(); ent_row.release();
-      n2e_ptr.release(); nbr_ptr.release(); diag.release(); posmap.release(); tab.release();
-    }
-  } gplan;
-  // implicit-connectivity sweep of ijk-numbered (build_cube) HEX8 meshes (sweep_hex8_struct.cu)
-  struct StructPlan {
-    bool tried = false, ok = false;
-    int32_t nx = 0, ny = 0, nz = 0, oz0 = 0, oz1 = 0, n_units = 0, n_ctas = 0;
-    int64_t n_visits = 0;
-    DevBuf<StructUnit> units;
-    DevBuf<int32_t> arr_off;
-    DevBuf<int64_t> nbr_ptr;
-    // units of the register-accumulating march (sweep_hex8_march.cu; 3-dof system)
-    DevBuf<StructUnit> m_units;
-    int32_t m_n_units = 0, m_n_ctas = 0;
-    int64_t m_n_visits = 0;
-    bool march = false;       // the march kernel serves nv = 3
-    bool last_march = false;  // ... and ran the last sweep
-    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); m_units.release(); }
-  } splan;
-  int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
-  DevBuf<int32_t> d_tile_counter, d_owned_nodes;
-  DevBuf<uint8_t> d_cmask;
-  // device: mesh + state + staging for host pointers
-  DevBuf<double> d_xyz, d_X, d_adj, d_rho, d_T, d_R, d_J, d_G, d_dq, d_partial, d_scalar, d_scratch, d_st[4];
-  DevBuf<uint8_t> d_elem_mask;
-  bool rho_set = false, T_nodal = false, thermal = false;
-  const double* rho_ext = nullptr;  // caller-owned device density
-  const double* T_ext = nullptr;
-  double T_const = 0., T_ref = 0.;
-  const double* last_R = nullptr;   // device pointer of the last residual
-  // face loads: raw (element, side, pressure) entries and the per-owned-node gather lists built from them
-  std::vector<int32_t> sp_elem, sp_side;
-  std::vector<double> sp_p;
-  std::vector<int32_t> fl_node, fl_ptr, fl_face_nodes;
-  std::vector<uint8_t> fl_k;
-  std::vector<double> fl_p;
-  DevBuf<int32_t> d_fl_node, d_fl_ptr, d_fl_face_nodes;
-  DevBuf<uint8_t> d_fl_k;
-  DevBuf<double> d_fl_p;
-  // point loads: loads of the OWNED nodes, summed per node in the order given (nonlinear_implicit_assembly.cpp:190-247)
-  std::vector<int32_t> pl_node;
-  std::vector<double> pl_load;
-  DevBuf<int32_t> d_pl_node, d_dvn;
-  DevBuf<double> d_pl_load, d_dfield, d_dvw, d_vec2;
-  std::vector<int32_t> pl_raw_node;
-  std::vector<double> pl_raw_load;
-  // heat side loads (CSR over elements)
-  DevBuf<int32_t> d_hs_ptr, d_hs_side;
-  DevBuf<double> d_hs_val;
-  bool have_heat_sides = false;
-  // build_square numbering of a QUAD4 heat mesh recognised (quad4_heat_struct_kernel)
-  bool q4s_tried = false, q4s_ok = false;
-  int32_t q4s_nx = 0, q4s_ny = 0;
-  bool last_q4s = false;
-  double rad_sbc = 0., rad_T0 = 0.;  // SURFACE_RADIATION_HEAT_FLUX parameters of the heat side loads
-  // dv map staging
-  DevBuf<int64_t> d_dv_ptr;
-  DevBuf<int32_t> d_dv_node;
-  DevBuf<double> d_dv_w, d_sens;
-
-  int64_t launches = 0;
-
-  int fail(int code, const char* fmt, ...) {
-    char buf[512];
-    va_list ap;
-    va_start(ap, fmt);
-    vsnprintf(buf, sizeof buf, fmt, ap);
-    va_end(ap);
-    err = buf;
-    return code;
-  }
-  int cuda_fail(cudaError_t e, const char* what) {
-    return fail(MASTB200_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
-  }
-};
-
-#define CU(call)                                                   \
-  do {                                                             \
-    cudaError_t e_ = (call);                                       \
-    if (e_ != cudaSuccess) return ctx->cuda_fail(e_, #call);       \
-  } while (0)
-
-namespace {
 
 // device view of an input array: device pointers pass through, host pointers are copied into `stage`
 int resolve_in(mastb200_context* ctx, const double* ptr, size_t n, DevBuf<double>& stage, const double** out) {
@@ -308,6 +112,13 @@ int apply_external_loads(mastb200_context* ctx, double* dR, const uint8_t* cmask
     ctx->launches++;
   }
   return MASTB200_OK;
+}
+
+// sweeps of a context with auto_localize refresh the ghost values of their input vector themselves (in place, on the
+// context stream): AssemblyBase::build_localized_vector inside residual_and_jacobian (nonlinear_implicit_assembly.cpp:93-95)
+int localize_if_needed(mastb200_context* ctx, const double* dV, int width) {
+  if (!ctx->auto_localize || ctx->neighbours.empty() || !dV) return MASTB200_OK;
+  return comm_exchange(ctx, const_cast<double*>(dV), width);
 }
 
 int check_ready(mastb200_context* ctx) {
@@ -453,6 +264,7 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
   const double* dX = nullptr;
   double *dR = nullptr, *dJ = nullptr;
   if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
   if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
   if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
   const mastb200_material& m = ctx->mat;
@@ -512,6 +324,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
   const double* dX = nullptr;
   double *dR = nullptr, *dJ = nullptr;
   if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
   if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
   if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
   const mastb200_material& m = ctx->mat;
@@ -742,6 +555,7 @@ int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J
   const double* dX = nullptr;
   double *dR = nullptr, *dJ = nullptr;
   if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
   if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
   if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
   const mastb200_material& m = ctx->mat;
@@ -788,6 +602,7 @@ int fill_stress_params(mastb200_context* ctx, const double* X, StressParams& p) 
   mastb200_context::GenericPlan& G = ctx->gplan;
   const double* dX = nullptr;
   if ((rc = resolve_in(ctx, X, size_t(ctx->n_nodes) * ctx->nv, ctx->d_X, &dX))) return rc;
+  if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
   p = StressParams();
   p.n_elem = ctx->n_elem; p.n_owned = ctx->pat.n_owned;
   p.nn = ctx->nn; p.nq = ctx->nn; p.nv = ctx->nv; p.nonlinear = ctx->mat.nonlinear_strain ? 1 : 0;
@@ -828,7 +643,10 @@ int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, 
   const double* dadj = nullptr;
   double* dG = nullptr;
   if (adj == X) dadj = p.X;  // compliance: the adjoint is the state
-  else if ((rc = resolve_in(ctx, adj, n_dof, ctx->d_adj, &dadj))) return rc;
+  else {
+    if ((rc = resolve_in(ctx, adj, n_dof, ctx->d_adj, &dadj))) return rc;
+    if ((rc = localize_if_needed(ctx, dadj, ctx->nv))) return rc;
+  }
   if ((rc = resolve_out(ctx, G, (size_t)ctx->n_nodes, ctx->d_G, &dG))) return rc;
   CU(ctx->d_scratch.ensure(size_t(ctx->n_elem) * p.nq));
   p.scratch = ctx->d_scratch.p;
@@ -926,7 +744,9 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   const double *dX = nullptr, *dadj = nullptr;
   double *dR = nullptr, *dJ = nullptr, *dG = nullptr;
   if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
   if (G && (rc = resolve_in(ctx, adj, n_dof, ctx->d_adj, &dadj))) return rc;
+  if (G && adj != X && (rc = localize_if_needed(ctx, dadj, ctx->nv))) return rc;
   if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
   if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
   if ((rc = resolve_out(ctx, G, (size_t)ctx->n_nodes, ctx->d_G, &dG))) return rc;
@@ -971,7 +791,6 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   return MASTB200_OK;
 }
 
-}  // namespace
 
 extern "C" {
 
@@ -1024,6 +843,7 @@ int mastb200_destroy(mastb200_context* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  comm_release(ctx);
   delete ctx;
   return MASTB200_OK;
 }

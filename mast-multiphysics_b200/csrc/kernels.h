@@ -237,6 +237,22 @@ cudaError_t launch_scatter_field(int64_t n, const int32_t* node, const double* w
 cudaError_t launch_dot_owned(const double* a, const double* b, const int32_t* owned_nodes, int64_t n_owned, int nv,
                              double* partial, int n_blocks, cudaStream_t stream);
 
+// ---- device linear solve (solve.cu): block-Jacobi preconditioned CG on the node-block CSR of the 3-dof system ---------
+int pcg_reduction_blocks();
+cudaError_t launch_bj_setup(int64_t n_owned, const int32_t* owned, const int64_t* nbr_ptr, const int32_t* nbr, const double* J,
+                            double* minv, cudaStream_t s);
+cudaError_t launch_spmv_node(int64_t n_owned, const int32_t* owned, const int64_t* nbr_ptr, const int32_t* nbr, const double* J,
+                             const double* x, double* y, double* partial, int sm_count, cudaStream_t s);
+cudaError_t launch_reduce_multi(const double* partial, int n, int n_out, int stride, double* out, cudaStream_t s);
+cudaError_t launch_pcg_alpha(double* scal, cudaStream_t s);
+cudaError_t launch_pcg_beta(double* scal, cudaStream_t s);
+cudaError_t launch_pcg_init(int64_t n_owned, const int32_t* owned, const double* rhs, const double* minv, double* x, double* r,
+                            double* z, double* p, double* partial, cudaStream_t s);
+cudaError_t launch_pcg_update(int64_t n_owned, const int32_t* owned, const double* scal, const double* minv, const double* p,
+                              const double* Ap, double* x, double* r, double* z, double* partial, cudaStream_t s);
+cudaError_t launch_pcg_direction(int64_t n_owned, const int32_t* owned, const double* scal, const double* z, double* p, cudaStream_t s);
+cudaError_t launch_near_null(int64_t n_nodes, int nv, const double* xyz, double* modes, cudaStream_t s);
+
 // G^T W : sens[i] = sum_k w[k] * G[node[k]]
 cudaError_t launch_dv_map_transpose(const double* G, int64_t n_dv, const int64_t* dv_ptr, const int32_t* dv_node,
                                     const double* dv_weight, double* sens, cudaStream_t stream);

@@ -62,3 +62,16 @@ def exchange_halo(dist, X, info, rank, world, width):
         return
     for r in dist.batch_isend_irecv(halo_ops(dist, X, info, rank, world, width)):
         r.wait()
+
+
+def slab_exchange_lists(info, rank, world):
+    """Ghost exchange of the slab partition in the library's terms (``Context.set_ghost_exchange``): per neighbouring rank
+    the local node ids of the owned plane it keeps as ghosts (send) and of the ghost plane it owns (recv)."""
+    npl, p0, p1, q0 = info["npl"], info["p0"], info["p1"], info["q0"]
+    plane = lambda z: np.arange((z - q0) * npl, (z - q0 + 1) * npl, dtype=np.int32)  # noqa: E731
+    ranks, send, recv = [], [], []
+    if rank > 0:
+        ranks.append(rank - 1); send.append(plane(p0)); recv.append(plane(p0 - 1))
+    if rank < world - 1:
+        ranks.append(rank + 1); send.append(plane(p1 - 1)); recv.append(plane(p1))
+    return ranks, send, recv

@@ -1534,19 +1534,38 @@ int oracle_fe_tables(int32_t elem_type, const double* coords, double* phi, doubl
 // interfaces, workers run the element loop on disjoint element ranges into the SAME arrays in two passes
 // (even blocks, then odd blocks) so that no two concurrent workers touch the same row.  The arithmetic and the
 // per-row binary search are exactly those of the serial path.
-double oracle_time_residual_and_jacobian(const OracleProblem* p, const double* X, double* R, double* J_vals,
-                                         const int64_t* row_ptr, const int32_t* col_idx, int threads) {
+// threads_used (may be NULL): the number of threads the sweep really ran with -- the block scheme below needs blocks of
+// equal parity to touch disjoint node ranges and halves the thread count until they do
+double oracle_time_residual_and_jacobian_ex(const OracleProblem* p, const double* X, double* R, double* J_vals,
+                                            const int64_t* row_ptr, const int32_t* col_idx, int threads, int* threads_used) {
   const int64_t n_dof = p->n_nodes * p->nv;
+  const ElemInfo ei = elem_info(p->elem_type);
   SideLoadIndex sl;
   sl.build(p);
+  // 2*threads contiguous element blocks, even blocks first, then odd ones: one std::thread per block of a parity, like
+  // MPI ranks owning contiguous element ranges.  Two blocks of equal parity must not share a node (they ADD into the same
+  // rows otherwise): checked on the actual node ranges, not assumed.
+  auto disjoint = [&](int nb) {
+    std::vector<int64_t> lo(nb), hi(nb);
+    for (int b = 0; b < nb; ++b) {
+      const int64_t e0 = p->n_elem * b / nb, e1 = p->n_elem * (b + 1) / nb;
+      int64_t mn = INT64_MAX, mx = -1;
+      for (int64_t k = e0 * ei.nn; k < e1 * ei.nn; ++k) { mn = std::min<int64_t>(mn, p->conn[k]); mx = std::max<int64_t>(mx, p->conn[k]); }
+      lo[b] = mn; hi[b] = mx;
+    }
+    for (int b = 0; b + 2 < nb; ++b)
+      for (int c = b + 2; c < nb; c += 2)
+        if (hi[b] >= lo[c] && hi[c] >= lo[b]) return false;
+    return true;
+  };
+  while (threads > 1 && !disjoint(2 * threads)) threads /= 2;
+  if (threads_used) *threads_used = std::max(threads, 1);
   const auto t0 = std::chrono::steady_clock::now();
   if (R) std::fill(R, R + n_dof, 0.);
   if (J_vals) std::fill(J_vals, J_vals + row_ptr[n_dof], 0.);
   if (threads <= 1) {
     assemble_range(p, sl, X, R, J_vals, row_ptr, col_idx, 0, p->n_elem);
   } else {
-    // 2*threads contiguous blocks; blocks of equal parity are separated by a whole block, which for the structured
-    // meshes used in the bench (block >> one element layer) guarantees disjoint rows.
     const int nb = 2 * threads;
     for (int parity = 0; parity < 2; ++parity) {
       std::vector<std::thread> pool;
@@ -1558,6 +1577,11 @@ double oracle_time_residual_and_jacobian(const OracleProblem* p, const double* X
     }
   }
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+double oracle_time_residual_and_jacobian(const OracleProblem* p, const double* X, double* R, double* J_vals,
+                                         const int64_t* row_ptr, const int32_t* col_idx, int threads) {
+  return oracle_time_residual_and_jacobian_ex(p, X, R, J_vals, row_ptr, col_idx, threads, nullptr);
 }
 
 }  // extern "C"

@@ -135,6 +135,9 @@ int oracle_fe_tables(int32_t elem_type, const double* coords /* [nn][3] */, doub
  * reduced afterwards, like the PETSc stash). Returns seconds. */
 double oracle_time_residual_and_jacobian(const OracleProblem* p, const double* X, double* R, double* J_vals,
                                          const int64_t* row_ptr, const int32_t* col_idx, int threads);
+/* the same; *threads_used = the thread count the sweep ran with (halved until blocks of equal parity share no node) */
+double oracle_time_residual_and_jacobian_ex(const OracleProblem* p, const double* X, double* R, double* J_vals,
+                                            const int64_t* row_ptr, const int32_t* col_idx, int threads, int* threads_used);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ def lib():
         L.oracle_fe_tables.argtypes = [C.c_int32, vp, vp, vp, vp, vp]
         L.oracle_time_residual_and_jacobian.argtypes = [P, vp, vp, vp, vp, vp, C.c_int]
         L.oracle_time_residual_and_jacobian.restype = dbl
+        L.oracle_time_residual_and_jacobian_ex.argtypes = [P, vp, vp, vp, vp, vp, C.c_int, C.POINTER(C.c_int)]
+        L.oracle_time_residual_and_jacobian_ex.restype = dbl
         _lib = L
     return _lib
 
@@ -196,11 +198,21 @@ class Problem:
         assert rc == 0, rc
         return sens
 
-    def time_residual_and_jacobian(self, X, threads, want_R=True, want_J=True):
+    def time_residual_and_jacobian(self, X, threads, want_R=True, want_J=True, out=None):
+        """Seconds of one sweep with up to ``threads`` threads; ``out`` (a dict) receives the thread count really used
+        and the result arrays (reused between calls when passed back in)."""
         row_ptr, col = self.pattern()
-        R = np.empty(self.n_dof) if want_R else None
-        J = np.empty(len(col)) if want_J else None
-        return lib().oracle_time_residual_and_jacobian(C.byref(self.s), _p(X), _p(R), _p(J), _p(row_ptr), _p(col), threads)
+        out = {} if out is None else out
+        if want_R and "R" not in out:
+            out["R"] = np.empty(self.n_dof)
+        if want_J and "J" not in out:
+            out["J"] = np.empty(len(col))
+        used = C.c_int(0)
+        t = lib().oracle_time_residual_and_jacobian_ex(C.byref(self.s), _p(X), _p(out.get("R") if want_R else None),
+                                                       _p(out.get("J") if want_J else None), _p(row_ptr), _p(col), threads,
+                                                       C.byref(used))
+        out["threads_used"] = used.value
+        return t
 
     # ---- the same problem on the device library ----
     def make_context(self, device=0):
