@@ -726,7 +726,11 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   if (struct_ok_cfg && (rc = ensure_struct_plan(ctx))) return rc;
   const bool use_struct = struct_ok_cfg && ctx->splan.ok;
   if (use_struct) aux = 0;
-  if (use_struct && G) {  // R/J by the implicit-connectivity sweep, then the sensitivities of the same state
+  // ... or, for the 3-dof system, from the same launch: the structured kernel's sensitivity variant
+  const bool fused_G = use_struct && G && ctx->nv == 3 && hex8_struct_sens_smem_bytes() != 0 &&
+                       (size_t)ctx->max_optin >= hex8_struct_sens_smem_bytes() && !(ctx->splan.march) &&
+                       !(getenv("MASTB200_NO_FUSED_SENS") && getenv("MASTB200_NO_FUSED_SENS")[0] == '1');
+  if (use_struct && G && !fused_G) {  // R/J by the implicit-connectivity sweep, then the sensitivities of the same state
     if ((rc = run_sweep(ctx, X, nullptr, nullptr, R, J))) return rc;
     float a = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) != cudaSuccess) a = 0.f;
@@ -767,6 +771,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     sp.xyz = p.xyz; sp.X = dX; sp.cmask = p.cmask; sp.J = dJ; sp.R = dR;
     sp.j_aligned32 = (reinterpret_cast<uintptr_t>(dJ) & 31) == 0 ? 1 : 0;
     sp.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+    if (fused_G) { sp.adj = adj == X ? dX : dadj; sp.G = dG; }
     sp.E0 = p.E0; sp.lam1 = p.lam1; sp.mu1 = p.mu1; sp.rho_min = p.rho_min; sp.penalty = p.penalty;
     ctx->splan.last_march = S.march && ctx->nv == 3;
     if (ctx->splan.last_march) {

@@ -57,12 +57,15 @@ struct StructParams {
   const double* X = nullptr;
   const uint8_t* cmask = nullptr;
   const double* rho = nullptr;           // nodal density (SIMP modulus) or null
+  const double* adj = nullptr;           // adjoint [n_nodes*3] (== X for the compliance) when G is requested
+  double* G = nullptr;                   // [n_nodes] density sensitivities fused into the sweep, or null
   double* J = nullptr;
   double* R = nullptr;
   int32_t j_aligned32 = 0;               // J is 32-byte aligned: the nv = 6 flush uses 16- and 32-byte stores
   double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1.;
 };
 size_t hex8_struct_smem_bytes();
+size_t hex8_struct_sens_smem_bytes();   // of the variant with fused density sensitivities (0: not built for this CTA shape)
 int hex8_struct_threads();
 cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream);
 // register-accumulating column march for the 3-dof system (sweep_hex8_march.cu): units of <= 16 x 4 owned node columns

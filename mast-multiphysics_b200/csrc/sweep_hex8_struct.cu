@@ -65,9 +65,14 @@ constexpr int O_NODE = O_RHO + 3 * NS * 8;              // [64] int2: owned node
 constexpr int O_FPK = O_NODE + 64 * 8;                  // [4 passes][8 lanes] packed flush constants
 constexpr int O_ROT = O_FPK + 32 * 4;                   // [2 planes][NS] sum of 1e-20 * max(diag K_e) per node (nv = 6)
 constexpr int O_MISC = O_ROT + 2 * NS * 8;
-constexpr int SMEM_BYTES = O_MISC + 16;
+constexpr int SMEM_BYTES = O_MISC + 16;                 // variants without sensitivities end here
+constexpr int O_ADJ = SMEM_BYTES;                       // [3 planes][3][NS] adjoint (fused density sensitivities)
+constexpr int O_GACC = O_ADJ + 3 * 3 * NS * 8;          // [2 planes][NS] G_n = adj . dR/d(rho_n) accumulators
+constexpr int O_GQ = O_GACC + 2 * NS * 8;               // [SW][4 el][8 nodes] nodal sums of the point values s_q
+constexpr int SMEM_BYTES_SENS = O_GQ + SW * 4 * 8 * 8;
 static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0 && O_ROT % 8 == 0, "alignment");
 static_assert(SMEM_BYTES <= (kStructCtasPerSm == 1 ? 232448 : 115712), "shared-memory layout exceeds the per-CTA budget");
+static_assert(kStructCtasPerSm > 1 || SMEM_BYTES_SENS <= 232448, "shared-memory layout of the sensitivity variant exceeds 227 KB");
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -112,6 +117,9 @@ struct Sm {
   int2* node;
   int32_t* fpk;
   double* rot;
+  double* adj;
+  double* gacc;
+  double* gq;
   int* misc;
 };
 
@@ -175,8 +183,14 @@ __device__ __forceinline__ void make_lane(const StructParams& p, const int32_t* 
 }
 
 // ---- geometry: lane = (element el of the warp's 2x2 block, quadrature point q) ------------------------------------
-template <bool SIMP>
-__device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& sm, int s, int base, int q, double* out) {
+// SENS: the lane also evaluates s_q = JxW E'(rho_q) eps(adj)^T D_1 eps(u) (adj zeroed on constrained dofs, the reference's
+// constrain_element_vector) and the eight lanes of an element turn the point values into the element's nodal sums
+// g_a = sum_q N_a(q) s_q (q ascending), left in gq[a] for the ordered accumulation of the element phase: the density
+// sensitivities G_n = adj . dR/d(rho_n) of all design variables come out of the same sweep as R and J
+// (assembly_base.cpp:594-639, solid_element_3d.cpp:566-788 with dD/dp of the SIMP law).
+template <bool SIMP, bool SENS>
+__device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& sm, int s, int base, int q, double* out,
+                                               double* gq, bool live) {
   const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP, zeta = (q & 4) ? GP : -GP;
   const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
   double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
@@ -205,11 +219,13 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
   inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
   inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
   double2* o = reinterpret_cast<double2*>(out);
-  o[0] = make_double2(inv[0][0], inv[0][1]);
-  o[1] = make_double2(inv[0][2], inv[1][0]);
-  o[2] = make_double2(inv[1][1], inv[1][2]);
-  o[3] = make_double2(inv[2][0], inv[2][1]);
-  double E = p.E0;
+  if (live) {
+    o[0] = make_double2(inv[0][0], inv[0][1]);
+    o[1] = make_double2(inv[0][2], inv[1][0]);
+    o[2] = make_double2(inv[1][1], inv[1][2]);
+    o[3] = make_double2(inv[2][0], inv[2][1]);
+  }
+  double E = p.E0, rho_q = 0.;
   if (SIMP) {  // modulus of the interpolated nodal density (examples/structural/example_6/example_6.cpp:100-137)
     double r = 0.;
 #pragma unroll
@@ -218,14 +234,82 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
       r = fma(0.125 * fx * fy * fz, sm.rho[(((m & 4) ? s + 1 : s) % 3) * NS + base + ((m >> 1) & 1) * TCX + (m & 1)], r);
     }
     E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(r, p.penalty));
+    rho_q = r;
   }
-  o[4] = make_double2(inv[2][2], det * E);  // Gauss weights are 1 for the 2x2x2 rule
+  if (live) o[4] = make_double2(inv[2][2], det * E);  // Gauss weights are 1 for the 2x2x2 rule
+  if (SENS) {
+    double sq = 0.;
+    if (live) {
+      // displacement gradients through the reference gradients: Href[i][r] = sum_m u_m,i dN_m/dxi_r (72 fma), then
+      // H[i][j] = sum_r Href[i][r] dxi_r/dx_j (27 fma) instead of physical gradients of all eight nodes; the adjoint's
+      // gradient equals the state's when the adjoint IS the state (compliance) and no dof of the element is constrained
+      const bool same = p.adj == p.X;
+      const double* adjp = same ? sm.u : sm.adj;
+      double Hr[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}}, Ar[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+      unsigned cmany = 0u;
+      if (p.cmask) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+          cmany |= sm.cm[((((m & 4) ? s + 1 : s)) & 3) * NSB + base + ((m >> 1) & 1) * TCX + (m & 1)];
+      }
+      const bool need_adj = !same || cmany != 0u;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
+        const double d0 = ((m & 1) ? 0.125 : -0.125) * fy * fz, d1 = ((m & 2) ? 0.125 : -0.125) * fx * fz,
+                     d2 = ((m & 4) ? 0.125 : -0.125) * fx * fy;
+        const int z = (m & 4) ? s + 1 : s, col = base + ((m >> 1) & 1) * TCX + (m & 1);
+        const double* U = sm.u + (z & 3) * 3 * NS + col;
+        const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
+        Hr[0][0] = fma(u0, d0, Hr[0][0]); Hr[0][1] = fma(u0, d1, Hr[0][1]); Hr[0][2] = fma(u0, d2, Hr[0][2]);
+        Hr[1][0] = fma(u1, d0, Hr[1][0]); Hr[1][1] = fma(u1, d1, Hr[1][1]); Hr[1][2] = fma(u1, d2, Hr[1][2]);
+        Hr[2][0] = fma(u2, d0, Hr[2][0]); Hr[2][1] = fma(u2, d1, Hr[2][1]); Hr[2][2] = fma(u2, d2, Hr[2][2]);
+        if (need_adj) {
+          const double* L = adjp + (same ? (z & 3) : (z % 3)) * 3 * NS + col;
+          const unsigned cm = p.cmask ? sm.cm[(z & 3) * NSB + col] : 0u;
+          const double l0 = (cm & 1u) ? 0. : L[0], l1 = (cm & 2u) ? 0. : L[NS], l2 = (cm & 4u) ? 0. : L[2 * NS];
+          Ar[0][0] = fma(l0, d0, Ar[0][0]); Ar[0][1] = fma(l0, d1, Ar[0][1]); Ar[0][2] = fma(l0, d2, Ar[0][2]);
+          Ar[1][0] = fma(l1, d0, Ar[1][0]); Ar[1][1] = fma(l1, d1, Ar[1][1]); Ar[1][2] = fma(l1, d2, Ar[1][2]);
+          Ar[2][0] = fma(l2, d0, Ar[2][0]); Ar[2][1] = fma(l2, d1, Ar[2][1]); Ar[2][2] = fma(l2, d2, Ar[2][2]);
+        }
+      }
+      double H[3][3], A[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          H[i][j] = Hr[i][0] * inv[j][0] + Hr[i][1] * inv[j][1] + Hr[i][2] * inv[j][2];
+          A[i][j] = need_adj ? Ar[i][0] * inv[j][0] + Ar[i][1] * inv[j][1] + Ar[i][2] * inv[j][2] : H[i][j];
+        }
+      const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
+      const double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
+      const double a0 = A[0][0], a1 = A[1][1], a2 = A[2][2];
+      const double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
+      const double dens = p.lam1 * (a0 + a1 + a2) * (e0 + e1 + e2) +
+                          p.mu1 * (2. * (a0 * e0 + a1 * e1 + a2 * e2) + a3 * e3 + a4 * e4 + a5 * e5);
+      const double pm1 = p.penalty - 1.;
+      const double rpow = pm1 == 3. ? rho_q * rho_q * rho_q : (pm1 == 2. ? rho_q * rho_q : (pm1 == 1. ? rho_q : (pm1 == 0. ? 1. : pow(rho_q, pm1))));
+      sq = det * p.E0 * (1. - p.rho_min) * p.penalty * rpow * dens;
+    }
+    // lane a of the element's eight lanes ends with sum_q N_a(q) s_q; a in ijk order (dx = a & 1, dy = (a >> 1) & 1, dz = a >> 2)
+    const int a = q, lane = threadIdx.x & 31;
+    double acc = 0.;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+      const double sv = __shfl_sync(0xffffffffu, sq, (lane & ~7) | qq);
+      const double fx = ((qq & 1) != 0) == ((a & 1) != 0) ? 1. + GP : 1. - GP;
+      const double fy = ((qq & 2) != 0) == ((a & 2) != 0) ? 1. + GP : 1. - GP;
+      const double fz = ((qq & 4) != 0) == ((a & 4) != 0) ? 1. + GP : 1. - GP;
+      acc = fma(0.125 * fx * fy * fz, sv, acc);
+    }
+    if (live) gq[a] = acc;
+  }
 }
 
 // ---- matrix + ordered accumulate: all 32 lanes on one element ------------------------------------------------------
-template <int PAR, bool NV6>
+template <int PAR, bool NV6, bool SENS>
 __device__ __forceinline__ void element_phase(const StructParams& p, const Sm& sm, const LaneK& lk, unsigned arena32, int rankpack,
-                                              const double* st, int lex, int ley, int color, int lane) {
+                                              const double* st, int lex, int ley, int color, int lane, const double* gq) {
   const int m = lane >> 2, q4 = lane & 3;
   double A[3][2], w[2];
 #pragma unroll
@@ -284,6 +368,10 @@ __device__ __forceinline__ void element_phase(const StructParams& p, const Sm& s
 #pragma unroll
   for (int t = 0; t < 12; ++t)
     if ((lk.pred >> t) & 1u) sts64(ar + lk.off[PAR][t], old[t] + C[t % 6][t / 6]);
+  if (SENS && q4 == 0) {  // node m of the element: its nodal sensitivity sum joins the node's accumulator (plane s or s+1)
+    double* ga = sm.gacc + (PAR ^ (m >> 2)) * NS + base + ((m >> 1) & 1) * TCX + (m & 1);
+    *ga += gq[m];
+  }
   if (NV6 && checker) {  // both nodes of the column (node planes s and s+1)
     const int col = base + (m >> 1) * TCX + (m & 1);
     sm.rot[PAR * NS + col] += 1.0e-20 * mx;
@@ -457,9 +545,10 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
       if (NV6) p.R[(plane_off + ni.x) * 6 + 3 + i] = 0.;  // rotational dofs: no residual
     }
   }
+  if (!NV6 && p.G && valid && l8 == 7) p.G[plane_off + ni.x] = sm.gacc[par * NS + slotA];  // fused density sensitivities
 }
 
-template <bool SIMP, bool NV6>
+template <bool SIMP, bool NV6, bool SENS>
 __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const StructParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Sm sm;
@@ -475,6 +564,9 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
   sm.fpk = reinterpret_cast<int32_t*>(smem_raw + O_FPK);
   sm.rot = reinterpret_cast<double*>(smem_raw + O_ROT);
   sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
+  sm.adj = reinterpret_cast<double*>(smem_raw + O_ADJ);
+  sm.gacc = reinterpret_cast<double*>(smem_raw + O_GACC);
+  sm.gq = reinterpret_cast<double*>(smem_raw + O_GQ);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid < 123) sm.tab[tid] = p.arr_off[tid];
   if (tid >= 128 && tid < 160) sm.fpk[tid - 128] = flush_pack((tid - 128) >> 3, (tid - 128) & 7);
@@ -524,6 +616,13 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
         if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * (NV6 ? 6 : 3) + ld_src);
         else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
       }
+      if (SENS && p.adj != p.X)  // adjoint planes of the fused sensitivities (three buffers, like the coordinates)
+        for (int t = tid; t < ncols * 3; t += ST) {
+          const int col = t / 3, c = t - col * 3;
+          const int ly = col / ncx, lx = col - ly * ncx;
+          cp_async8(sm.adj + (z % 3) * 3 * NS + c * NS + ly * TCX + lx,
+                    p.adj + ((int64_t)z * plane_nodes + (u.e0x + lx) + (u.e0y + ly) * npx) * 3 + c);
+        }
       if (NS * 6 > ST && tid + ST < ncols * 6) {  // small CTAs: the few items beyond one per thread
         const int t = tid + ST, col = t / 6, c = t - col * 6;
         const int ly = col / ncx, lx = col - ly * ncx;
@@ -567,6 +666,7 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
     for (int i = tid; i < kStructArenaDoubles; i += ST) sm.arena[i] = 0.;
     if (tid < NS) sm.cnt[tid] = 0;
     if (NV6 && tid < 2 * NS) sm.rot[tid] = 0.;
+    if (SENS && tid < 2 * NS) sm.gacc[tid] = 0.;
     load_plane(s_begin);
     if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
     if (cm_on) {
@@ -592,21 +692,22 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
           {
             const int el = c_lo + (lane >> 3), q = lane & 7;
             const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
-            if ((lane >> 3) < STAGE_EL && lex < u.nex && ley < u.ney)
-              geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
+            const bool live = (lane >> 3) < STAGE_EL && lex < u.nex && ley < u.ney;
+            if (SENS || live)  // with sensitivities all lanes go in: the point values are joined by shuffles
+              geometry_phase<SIMP, SENS>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS, sm.gq + warp * 32 + (el & 3) * 8, live);
           }
           __syncwarp();
           if (s & 1) {
 #pragma unroll 1
             for (int c = c_lo; c < c_lo + STAGE_EL; ++c) {
               const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-              if (lex < u.nex && ley < u.ney) element_phase<1, NV6>(p, sm, lk, arena32, rankpack, my_stage + (c - c_lo) * 8 * QS, lex, ley, c, lane);
+              if (lex < u.nex && ley < u.ney) element_phase<1, NV6, SENS>(p, sm, lk, arena32, rankpack, my_stage + (c - c_lo) * 8 * QS, lex, ley, c, lane, sm.gq + warp * 32 + c * 8);
             }
           } else {
 #pragma unroll 1
             for (int c = c_lo; c < c_lo + STAGE_EL; ++c) {
               const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-              if (lex < u.nex && ley < u.ney) element_phase<0, NV6>(p, sm, lk, arena32, rankpack, my_stage + (c - c_lo) * 8 * QS, lex, ley, c, lane);
+              if (lex < u.nex && ley < u.ney) element_phase<0, NV6, SENS>(p, sm, lk, arena32, rankpack, my_stage + (c - c_lo) * 8 * QS, lex, ley, c, lane, sm.gq + warp * 32 + c * 8);
             }
           }
         }
@@ -626,6 +727,7 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
         for (int i = tid; i < 81 * NS; i += ST) zc[i] = 0.;
         if (tid < NS) sm.cnt[tid] = 0;
         if (NV6 && tid < NS) sm.rot[par * NS + tid] = 0.;
+        if (SENS && tid < NS) sm.gacc[par * NS + tid] = 0.;
       }
       __syncthreads();
     }
@@ -635,26 +737,33 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
 }  // namespace
 
 size_t hex8_struct_smem_bytes() { return SMEM_BYTES; }
+size_t hex8_struct_sens_smem_bytes() { return kStructCtasPerSm == 1 ? SMEM_BYTES_SENS : 0; }  // 0: variant not built
 int hex8_struct_threads() { return ST; }
 
 cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  static bool attr_set[4][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
+  static bool attr_set[5][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-  auto go = [&](auto kern, int variant) -> cudaError_t {
+  auto go = [&](auto kern, int variant, int smem) -> cudaError_t {
     if (dev >= 64 || !attr_set[variant][dev]) {
-      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (er != cudaSuccess) return er;
       if ((er = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return er;
       if (dev < 64) attr_set[variant][dev] = true;
     }
-    kern<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+    kern<<<n_ctas, ST, smem, stream>>>(p);
     return cudaSuccess;
   };
-  if (p.nv == 6) e = p.rho ? go(hex8_struct_kernel<true, true>, 3) : go(hex8_struct_kernel<false, true>, 2);
-  else e = p.rho ? go(hex8_struct_kernel<true, false>, 1) : go(hex8_struct_kernel<false, false>, 0);
+  if (p.G) {  // R / J with the density sensitivities of the same state in one launch (3-dof system, SIMP modulus)
+    if (p.nv != 3 || !p.rho || !p.adj || kStructCtasPerSm != 1) return cudaErrorInvalidValue;
+    e = go(hex8_struct_kernel<true, false, true>, 4, SMEM_BYTES_SENS);
+  } else if (p.nv == 6) {
+    e = p.rho ? go(hex8_struct_kernel<true, true, false>, 3, SMEM_BYTES) : go(hex8_struct_kernel<false, true, false>, 2, SMEM_BYTES);
+  } else {
+    e = p.rho ? go(hex8_struct_kernel<true, false, false>, 1, SMEM_BYTES) : go(hex8_struct_kernel<false, false, false>, 0, SMEM_BYTES);
+  }
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }
