@@ -203,11 +203,30 @@ int ensure_generic_plan(mastb200_context* ctx) {
     CU(G.tab.upload(tab, ctx->stream));
   } else {  // HEX27
     std::vector<int32_t> color_elems;
-    std::string e = build_coloring(P, ctx->conn.data(), G.color_ptr, color_elems);
-    if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
     std::vector<uint8_t> posmap;
-    e = build_posmap(P, ctx->conn.data(), posmap);
-    if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+    std::string e;
+    const char* env = getenv("MASTB200_H27_ORDERED");  // 1: the single-launch ordered sweep (experiment, slower on B200)
+    if (!(env && env[0] == '1')) {
+      e = build_coloring(P, ctx->conn.data(), G.color_ptr, color_elems);
+      if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+      e = build_posmap(P, ctx->conn.data(), posmap);
+      if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+    } else {
+      std::vector<int32_t> order, pred_ptr, pred;
+      bool fw = false;
+      int brick = 1024;
+      if (const char* b = getenv("MASTB200_H27_BRICK")) brick = std::max(8, atoi(b));
+      e = build_ordered_scatter(P, ctx->xyz.data(), ctx->conn.data(), ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(),
+                                brick, order, pred_ptr, pred, posmap, fw);
+      if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+      G.ordered = true; G.first_writer = fw; G.n_order = (int32_t)order.size(); G.epoch = 0;
+      CU(G.order.upload(order, ctx->stream));
+      CU(G.pred_ptr.upload(pred_ptr, ctx->stream));
+      if (pred.empty()) pred.push_back(0);
+      CU(G.pred.upload(pred, ctx->stream));
+      CU(G.done.ensure((size_t)ctx->n_elem));
+      CU(cudaMemsetAsync(G.done.p, 0, size_t(ctx->n_elem) * sizeof(int32_t), ctx->stream));
+    }
     std::vector<double> tab;
     hex27_tables(tab);
     CU(G.color_elems.upload(color_elems, ctx->stream));
@@ -346,9 +365,11 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     else CU(launch_quad4_heat(p, ctx->stream));
     ctx->launches++;
   } else {
-    // the coloured scatter accumulates: R and J start from zero (nonlinear_implicit_assembly.cpp:81-82)
+    // the scatter accumulates: R and J start from zero (nonlinear_implicit_assembly.cpp:81-82) -- except that the ordered
+    // sweep of the 3-dof system stores the first contribution to every CSR block, so J needs no memset there
+    const bool fw = G.ordered && G.first_writer && ctx->nv == 3;
     if (dR) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
-    if (dJ) CU(cudaMemsetAsync(dJ, 0, nnz * sizeof(double), ctx->stream));
+    if (dJ && !fw) CU(cudaMemsetAsync(dJ, 0, nnz * sizeof(double), ctx->stream));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     Hex27Params p;
     p.conn = G.conn.p; p.posmap = G.posmap.p; p.node_row = G.node_row.p; p.nbr_ptr = G.nbr_ptr.p; p.tab = G.tab.p;
@@ -364,12 +385,25 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
     p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
     p.nv = ctx->nv; p.thermal = ctx->thermal ? 1 : 0;
-    const int nc = (int)G.color_ptr.size() - 1;
-    for (int c = 0; c < nc; ++c) {
-      p.elems = G.color_elems.p + G.color_ptr[c];
-      p.n_elems = G.color_ptr[c + 1] - G.color_ptr[c];
+    if (G.ordered) {  // one launch: the plan's order with done flags
+      if (++G.epoch == INT32_MAX) {
+        G.epoch = 1;
+        CU(cudaMemsetAsync(G.done.p, 0, size_t(ctx->n_elem) * sizeof(int32_t), ctx->stream));
+      }
+      p.elems = G.order.p; p.n_elems = G.n_order;
+      p.pred_ptr = G.pred_ptr.p; p.pred = G.pred.p; p.done = G.done.p; p.epoch = G.epoch;
+      p.first_writer = fw ? 1 : 0;
+      p.pos_flagged = G.first_writer ? 1 : 0;
       CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
       ctx->launches++;
+    } else {
+      const int nc = (int)G.color_ptr.size() - 1;
+      for (int c = 0; c < nc; ++c) {
+        p.elems = G.color_elems.p + G.color_ptr[c];
+        p.n_elems = G.color_ptr[c + 1] - G.color_ptr[c];
+        CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
+        ctx->launches++;
+      }
     }
   }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));

@@ -107,12 +107,17 @@ struct mastb200_context {
   struct GenericPlan {
     bool built = false;
     DevBuf<int32_t> conn, n2e, nbr, node_row, color_elems, ent_row;  // ent_row: owned row of every neighbour entry (plate)
+    // ordered single-launch HEX27 scatter: processing order, predecessor lists, done flags (value = sweep counter)
+    DevBuf<int32_t> order, pred_ptr, pred, done;
+    int32_t n_order = 0, epoch = 0;
+    bool ordered = false, first_writer = false;
     DevBuf<int64_t> n2e_ptr, nbr_ptr;
     DevBuf<uint8_t> diag, posmap;
     DevBuf<double> tab;
     std::vector<int32_t> color_ptr;
     void reset() {
-      built = false; color_ptr.clear();
+      built = false; color_ptr.clear(); ordered = false; first_writer = false; n_order = 0; epoch = 0;
+      order.release(); pred_ptr.release(); pred.release(); done.release();
       conn.release(); n2e.release(); nbr.release(); node_row.release(); color_elems.release(); ent_row.release();
       n2e_ptr.release(); nbr_ptr.release(); diag.release(); posmap.release(); tab.release();
     }

@@ -105,8 +105,15 @@ cudaError_t launch_quad4_heat_struct(const GatherParams& p, int32_t nx, int32_t 
 
 // ---- HEX27 coloured DMMA sweep (sweep_hex27.cu) -----------------------------------------------------------------------
 struct Hex27Params {
-  const int32_t* elems = nullptr;        // element ids of the colour being swept
+  const int32_t* elems = nullptr;        // element ids in processing order (of one colour, or the whole ordered sweep)
   int32_t n_elems = 0;
+  // ordered single-launch sweep: predecessor lists per position, done flags per element, the value that marks 'done'
+  const int32_t* pred_ptr = nullptr;
+  const int32_t* pred = nullptr;
+  int32_t* done = nullptr;
+  int32_t epoch = 0;
+  int32_t pos_flagged = 0;               // posmap entries carry the first-writer flag in bit 7 (positions are 7 bits)
+  int32_t first_writer = 0;              // use the flag: the first element to touch a block stores (no memset of J)
   const int32_t* conn = nullptr;         // [n_elem][27]
   const uint8_t* posmap = nullptr;       // [n_elem][27][27] position of node b in the neighbour list of node a
   const int32_t* node_row = nullptr;     // [n_nodes] owned-row index or -1

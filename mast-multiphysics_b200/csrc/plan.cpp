@@ -754,4 +754,118 @@ std::string build_posmap(const Pattern& pat, const int32_t* conn, std::vector<ui
   return "";
 }
 
+// Processing order of the single-launch HEX27 scatter (sweep_hex27.cu): elements grouped into spatial bricks (so that the
+// CSR rows a brick adds into stay in L2 while its elements run), colour-major inside a brick (elements of one colour share
+// no node).  An element may start when every element that shares a node with it and comes EARLIER in the order has
+// finished: pred lists those.  The order fixes the summation order of every CSR value and residual entry (independent of
+// scheduling) and is deadlock-free for CTAs that take the list round-robin, each in increasing position.
+// first_flag[(e, a, b)]: this element is the first in the order to touch block (a, b) of its row -> it stores, the later
+// ones add, and J needs no memset.
+std::string build_ordered_scatter(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
+                                  int brick_elems, std::vector<int32_t>& order, std::vector<int32_t>& pred_ptr,
+                                  std::vector<int32_t>& pred, std::vector<uint8_t>& posmap, bool& first_writer) {
+  const int nn = pat.nn;
+  const int64_t ne = pat.n_elem;
+  // colours (greedy, as build_coloring) of the elements that touch an owned node
+  std::vector<int32_t> cptr, celems;
+  std::string err = build_coloring(pat, conn, cptr, celems);
+  if (!err.empty()) return err;
+  std::vector<int8_t> color(ne, -1);
+  for (int c = 0; c + 1 < (int)cptr.size(); ++c)
+    for (int32_t k = cptr[c]; k < cptr[c + 1]; ++k) color[celems[k]] = (int8_t)c;
+  // bricks: cubes of side h in the bounding box of the element centroids, about brick_elems elements each
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  std::vector<double> cen((size_t)ne * 3);
+  for (int64_t e = 0; e < ne; ++e)
+    for (int d = 0; d < 3; ++d) {
+      double c = 0.;
+      for (int a = 0; a < nn; ++a) c += xyz[(int64_t)conn[e * nn + a] * 3 + d];
+      c /= nn;
+      cen[e * 3 + d] = c; lo[d] = std::min(lo[d], c); hi[d] = std::max(hi[d], c);
+    }
+  const int64_t active = (int64_t)celems.size();
+  double vol = 1.;
+  int ext_dims = 0;
+  for (int d = 0; d < 3; ++d)
+    if (hi[d] > lo[d]) { vol *= hi[d] - lo[d]; ++ext_dims; }
+  const double nbricks = std::max(1.0, double(active) / brick_elems);
+  const double h = ext_dims ? std::pow(vol / nbricks, 1.0 / ext_dims) : 1.;
+  int64_t nb[3];
+  for (int d = 0; d < 3; ++d) nb[d] = std::max<int64_t>(1, (int64_t)std::ceil((hi[d] - lo[d]) / h + 1e-9));
+  std::vector<std::pair<int64_t, int32_t>> keyed;  // (brick * 64 + colour, element)
+  keyed.reserve(active);
+  for (int64_t e = 0; e < ne; ++e) {
+    if (color[e] < 0) continue;
+    int64_t b[3];
+    for (int d = 0; d < 3; ++d) b[d] = std::min<int64_t>(nb[d] - 1, (int64_t)((cen[e * 3 + d] - lo[d]) / h));
+    const int64_t brick = (b[2] * nb[1] + b[1]) * nb[0] + b[0];
+    keyed.emplace_back(brick * 64 + color[e], (int32_t)e);
+  }
+  std::sort(keyed.begin(), keyed.end());
+  order.resize(keyed.size());
+  std::vector<int32_t> posn(ne, -1);
+  for (size_t k = 0; k < keyed.size(); ++k) { order[k] = keyed[k].second; posn[keyed[k].second] = (int32_t)k; }
+  // predecessors: node-sharing elements earlier in the order (two passes: count, then fill)
+  pred_ptr.assign(order.size() + 1, 0);
+  auto collect = [&](size_t k, std::vector<int32_t>& scratch) {
+    const int64_t e = order[k];
+    scratch.clear();
+    for (int a = 0; a < nn; ++a) {
+      const int32_t n = conn[e * nn + a];
+      for (int64_t q = pat.n2e_ptr[n]; q < pat.n2e_ptr[n + 1]; ++q) {
+        const int32_t o = pat.n2e[q];
+        if (o != e && posn[o] >= 0 && posn[o] < (int32_t)k) scratch.push_back(o);
+      }
+    }
+    std::sort(scratch.begin(), scratch.end());
+    scratch.erase(std::unique(scratch.begin(), scratch.end()), scratch.end());
+  };
+  std::atomic<int> too_many{0};
+  parallel_for((int64_t)order.size(), [&](int64_t b0, int64_t e0, int) {
+    std::vector<int32_t> scratch;
+    for (int64_t k = b0; k < e0; ++k) {
+      collect((size_t)k, scratch);
+      if (scratch.size() > 64) too_many = 1;
+      pred_ptr[k + 1] = (int32_t)scratch.size();
+    }
+  });
+  if (too_many) return "an element has more than 64 node-sharing predecessors";
+  for (size_t k = 0; k < order.size(); ++k) pred_ptr[k + 1] += pred_ptr[k];
+  pred.resize((size_t)pred_ptr[order.size()]);
+  parallel_for((int64_t)order.size(), [&](int64_t b0, int64_t e0, int) {
+    std::vector<int32_t> scratch;
+    for (int64_t k = b0; k < e0; ++k) {
+      collect((size_t)k, scratch);
+      std::copy(scratch.begin(), scratch.end(), pred.begin() + pred_ptr[k]);
+    }
+  });
+  // position map, with the first-writer flag in bit 7 when every row has < 128 neighbours and there are no diagonal elements
+  err = build_posmap(pat, conn, posmap);
+  if (!err.empty()) return err;
+  first_writer = true;
+  for (int64_t r = 0; r < pat.n_owned && first_writer; ++r)
+    if (pat.nbr_ptr[r + 1] - pat.nbr_ptr[r] > 127) first_writer = false;
+  if (diag_elem)
+    for (int64_t e = 0; e < ne && first_writer; ++e)
+      if (diag_elem[e]) first_writer = false;
+  if (first_writer) {
+    std::vector<uint64_t> seen(((size_t)pat.nbr_ptr[pat.n_owned] + 63) / 64, 0);
+    for (size_t k = 0; k < order.size(); ++k) {
+      const int64_t e = order[k];
+      const int32_t* c = conn + e * nn;
+      for (int a = 0; a < nn; ++a) {
+        const int32_t r = pat.node_row[c[a]];
+        if (r < 0) continue;
+        for (int b = 0; b < nn; ++b) {
+          uint8_t& pm = posmap[((size_t)e * nn + a) * nn + b];
+          const size_t blk = (size_t)pat.nbr_ptr[r] + pm;
+          if (!((seen[blk >> 6] >> (blk & 63)) & 1u)) { seen[blk >> 6] |= uint64_t(1) << (blk & 63); pm |= 0x80; }
+        }
+      }
+    }
+    // every block of an owned row is touched by some element (the pattern comes from the elements), so no value stays unset
+  }
+  return "";
+}
+
 }  // namespace mastb200

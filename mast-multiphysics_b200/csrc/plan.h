@@ -140,5 +140,9 @@ std::string build_coloring(const Pattern& pat, const int32_t* conn, std::vector<
 // element -> nnz map: posmap[e][a][b] = position of node conn[e][b] in the neighbour list of the owned node conn[e][a]
 // (0 for unowned a).  One byte per node pair; fails if a row has more than 255 neighbours.
 std::string build_posmap(const Pattern& pat, const int32_t* conn, std::vector<uint8_t>& posmap);
+// processing order, predecessor lists and position map (bit 7: first writer of the block) of the single-launch scatter
+std::string build_ordered_scatter(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
+                                  int brick_elems, std::vector<int32_t>& order, std::vector<int32_t>& pred_ptr,
+                                  std::vector<int32_t>& pred, std::vector<uint8_t>& posmap, bool& first_writer);
 
 }  // namespace mastb200

@@ -11,11 +11,16 @@
 // i.e. nine 27x27x27 products (padded to 32x32x28) instead of B^T D B with K = 162: 1008 mma.sync.m8n8k4.f64 per
 // element (516 kflop) against 2.1 Mflop for the dense form.
 //
-// One CTA (4 warps) per element, four CTAs per SM; elements are processed colour by colour (no two elements of a colour
+// One CTA (4 warps) per element, five CTAs per SM; elements are processed colour by colour (no two elements of a colour
 // share a node), so the adds into the CSR values and the residual are plain read-modify-writes without atomics and the
 // summation order into every entry is the colour order -- fixed by the plan, independent of scheduling.  K_e is never
 // stored: the accumulator fragments go from registers straight to their CSR slots through the per-element position map
 // (a precomputed element -> nnz map, one byte per node pair).
+// Opt-in (MASTB200_H27_ORDERED=1): ONE launch in the plan's order (spatial bricks, colour-major inside a brick:
+// plan.cpp build_ordered_scatter) where an element starts when all node-sharing elements before it have finished (done
+// flags, acquire / release at gpu scope), the first element to touch a CSR block stores and the later ones add (position
+// map, bit 7: no memset of J).  Parity-green and bitwise reproducible, but slower on B200: with 740 elements in flight the
+// L2 holds only ~4 element-times of CSR rows while an 8-colour dependency chain needs 8 (profiles/r02c_hex27_ordered.md).
 //   phase 1  one thread per quadrature point: J, J^-1, w_q (SIMP modulus of the interpolated nodal density), thermal
 //            stress factor
 //   phase 2  gradients g_i[q][a] = J^-T dN_a, staged in shared memory in three arrays with a q-stride of 36 doubles so
@@ -57,12 +62,17 @@ struct Smem27 {
   uint8_t pos[27 * 27 + 7];   // position of node b in the neighbour list of node a
 };
 
+// read of a value another CTA of the SAME launch may have added to: past L1 in the ordered sweep
+__device__ __forceinline__ double ld_acc(const double* a, bool ordered) { return ordered ? __ldcg(a) : *a; }
+
 __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(const Hex27Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nv = p.nv;
   const bool wantJ = p.J != nullptr, wantR = p.R != nullptr;
+  const bool ordered = p.pred_ptr != nullptr;
+  const unsigned pos_mask = p.pos_flagged ? 0x7fu : 0xffu;  // bit 7 of a position-map entry: first writer of the block
 
   // tables and the zero padding of the operand arrays: once per CTA
   const double* __restrict__ tabN = p.tab;             // [q][b]
@@ -74,6 +84,18 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
   for (int idx = blockIdx.x; idx < p.n_elems; idx += gridDim.x) {
     const int e = p.elems[idx];
     __syncthreads();  // previous element done with the staging arrays
+    if (p.pred_ptr) {  // ordered sweep: wait for the node-sharing elements before this one in the order
+      const int pb = p.pred_ptr[idx], pn = p.pred_ptr[idx + 1] - pb;
+      if (tid < pn) {
+        const int32_t* flag = p.done + p.pred[pb + tid];
+        int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+          if (v != p.epoch) __nanosleep(64);
+        } while (v != p.epoch);
+      }
+      __syncthreads();
+    }
     if (tid < 27) {
       const int n = p.conn[(int64_t)e * 27 + tid];
       s.gid[tid] = n;
@@ -96,8 +118,13 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
     if (p.diag_elem && p.diag_elem[e]) {  // diagonal_elem_subdomain_id (nonlinear_implicit_assembly.cpp:117-130)
       if (wantJ && tid < 27 && s.row[tid] >= 0) {
         const int64_t rl = (int64_t)s.nnb[tid] * nv;
-        double* blk = p.J + s.base[tid] * nv * nv + (int64_t)s.pos[tid * 27 + tid] * nv;
-        for (int i = 0; i < nv; ++i) blk[i * rl + i] += ((s.cm[tid] >> i) & 1u) ? 1. : 1.0e-24;
+        double* blk = p.J + s.base[tid] * nv * nv + (int64_t)(s.pos[tid * 27 + tid] & pos_mask) * nv;
+        for (int i = 0; i < nv; ++i) blk[i * rl + i] = ld_acc(blk + i * rl + i, ordered) + (((s.cm[tid] >> i) & 1u) ? 1. : 1.0e-24);
+      }
+      if (p.pred_ptr) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + e), "r"(p.epoch) : "memory");
       }
       continue;
     }
@@ -210,14 +237,16 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
           if (a == b) mx = fmax(mx, fmax(K[0][0], fmax(K[1][1], K[2][2])));
           if (rowJ) {
             const unsigned cmb = s.cm[b];
-            double* dst = rowJ + (int64_t)s.pos[a * 27 + b] * nv;
+            const unsigned pm = s.pos[a * 27 + b];
+            const bool first = p.first_writer && (pm & 0x80u);  // no element before this one has touched the block
+            double* dst = rowJ + (int64_t)(pm & pos_mask) * nv;
 #pragma unroll
             for (int i = 0; i < 3; ++i)
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
                 double k = K[i][j];
                 if (((cma >> i) | (cmb >> j)) & 1u) k = (a == b && i == j && ((cma >> i) & 1u)) ? 1. : 0.;
-                dst[i * rl + j] += k;
+                dst[i * rl + j] = first ? k : ld_acc(dst + i * rl + j, ordered) + k;
               }
           }
         }
@@ -235,16 +264,21 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
       if (kq == 0 && rowa >= 0) {
         if (p.thermal) { f0 += s.fth[a * 3]; f1 += s.fth[a * 3 + 1]; f2 += s.fth[a * 3 + 2]; }
         double* r = p.R + (int64_t)s.gid[a] * nv;
-        if (!(cma & 1u)) r[0] += f0;
-        if (!(cma & 2u)) r[1] += f1;
-        if (!(cma & 4u)) r[2] += f2;
+        if (!(cma & 1u)) r[0] = ld_acc(r, ordered) + f0;
+        if (!(cma & 2u)) r[1] = ld_acc(r + 1, ordered) + f1;
+        if (!(cma & 4u)) r[2] = ld_acc(r + 2, ordered) + f2;
       }
     }
     if (nv == 6 && wantJ && tid < 27 && s.row[tid] >= 0) {
       const double m = fmax(fmax(s.red[0], s.red[1]), fmax(s.red[2], s.red[3]));
       const int64_t rl6 = (int64_t)s.nnb[tid] * 6;
-      double* blk = p.J + s.base[tid] * 36 + (int64_t)s.pos[tid * 27 + tid] * 6;
-      for (int i = 3; i < 6; ++i) blk[i * rl6 + i] += ((s.cm[tid] >> i) & 1u) ? 1. : 1.0e-20 * m;
+      double* blk = p.J + s.base[tid] * 36 + (int64_t)(s.pos[tid * 27 + tid] & pos_mask) * 6;
+      for (int i = 3; i < 6; ++i) blk[i * rl6 + i] = ld_acc(blk + i * rl6 + i, ordered) + (((s.cm[tid] >> i) & 1u) ? 1. : 1.0e-20 * m);
+    }
+    if (p.pred_ptr) {  // this element's adds are visible before its flag
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.done + e), "r"(p.epoch) : "memory");
     }
   }
 }
@@ -257,7 +291,14 @@ cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t 
   if (p.n_elems <= 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(hex27_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem27));
   if (e != cudaSuccess) return e;
-  const int grid = p.n_elems < MASTB200_H27_CTAS * sm_count ? p.n_elems : MASTB200_H27_CTAS * sm_count;
+  // the ordered sweep waits on other CTAs: every CTA of the grid must be resident at once
+  int per_sm = MASTB200_H27_CTAS;
+  if (p.pred_ptr) {
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hex27_sweep_kernel, TB, sizeof(Smem27))) != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    per_sm = per_sm < MASTB200_H27_CTAS ? per_sm : MASTB200_H27_CTAS;
+  }
+  const int grid = p.n_elems < per_sm * sm_count ? p.n_elems : per_sm * sm_count;
   hex27_sweep_kernel<<<grid, TB, sizeof(Smem27), stream>>>(p);
   return cudaGetLastError();
 }
