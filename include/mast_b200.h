@@ -202,6 +202,24 @@ int mastb200_stress_functional_density_derivative(mastb200_context* ctx, const d
                                                   double sigma0, const uint8_t* elem_mask, const double* sums,
                                                   double* dq_drho);
 
+/* ---- density filter and material volume of the SIMP loop ------------------------------------------------------------ */
+/* Geometric filter over the nodes of the mesh: W[n,k] = (radius - |x_n - x_k|) / sum_k' (radius - |x_n - x_k'|) for the
+ * nodes k within `radius` of n, neighbours in ascending node id.  dv_node[n_nodes] (host) or NULL = every node is a
+ * design variable; rows of the other nodes are the identity.  The radius search runs on the device at this call.
+ * Every node within the radius must be local (one rank, or a radius inside the ghost layer).
+ *   <- MAST::FilterBase::_init / _init2, src/level_set/filter_base.cpp:275-372, 378-447 */
+int mastb200_filter_init(mastb200_context* ctx, double radius, const uint8_t* dv_node, int64_t* nnz);
+/* the filter as CSR (host arrays; col / weight may be NULL): row_ptr[n_nodes+1], col[nnz], weight[nnz] */
+int mastb200_filter_get(mastb200_context* ctx, int64_t* row_ptr, int32_t* col, double* weight);
+/* rho[n_nodes] = W d   <- FilterBase::compute_filtered_values, filter_base.cpp:59-97.  [h|d], rho != d */
+int mastb200_filter_apply(mastb200_context* ctx, const double* d, double* rho);
+/* grad[n_nodes] = W^T G: nodal sensitivities G_n (mastb200_sensitivity_sweep, ..._density_derivative) to design-variable
+ * sensitivities, the per-DV loop of examples/structural/example_6/example_6.cpp:877-939 as one product.  [h|d] */
+int mastb200_filter_apply_transpose(mastb200_context* ctx, const double* G, double* grad);
+/* material volume V = sum_e vol(e) mean_{a in e} rho_a over this rank's owned nodes' share, and dV/d(rho_n) [n_nodes]
+ * (either may be NULL; the gradient does not depend on rho)   <- example_6.cpp:714-791 */
+int mastb200_volume(mastb200_context* ctx, const double* rho, double* volume, double* dV_drho);
+
 /* ---- communicator: ghost exchange and sums over the ranks of one box (NCCL over NVLink) ------------------------- */
 /* One process per GPU.  Rank 0 calls mastb200_comm_unique_id (id: at least 128 bytes), the host broadcasts the bytes by
  * whatever it has (MPI_Bcast in a MAST run, torch.distributed in bench.py), every rank calls mastb200_comm_init; or an

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
     "mastb200_stress", "mastb200_stress_functional", "mastb200_stress_functional_derivative",
     "mastb200_stress_functional_density_derivative",
+    "mastb200_filter_init", "mastb200_filter_get", "mastb200_filter_apply", "mastb200_filter_apply_transpose", "mastb200_volume",
     "mastb200_comm_unique_id", "mastb200_comm_init", "mastb200_comm_attach", "mastb200_set_ghost_exchange",
     "mastb200_build_localized_vector", "mastb200_all_reduce_sum", "mastb200_solve", "mastb200_near_null_space",
     "mastb200_get_stats", "mastb200_stream", "mastb200_debug_plan_sizes", "mastb200_debug_plan_copy",
@@ -107,6 +108,11 @@ def load_library():
     lib.mastb200_stress_functional.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, C.POINTER(dbl)]
     lib.mastb200_stress_functional_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
     lib.mastb200_stress_functional_density_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
+    lib.mastb200_filter_init.argtypes = [vp, dbl, vp, C.POINTER(i64)]
+    lib.mastb200_filter_get.argtypes = [vp, vp, vp, vp]
+    lib.mastb200_filter_apply.argtypes = [vp, vp, vp]
+    lib.mastb200_filter_apply_transpose.argtypes = [vp, vp, vp]
+    lib.mastb200_volume.argtypes = [vp, vp, C.POINTER(dbl), vp]
     lib.mastb200_comm_unique_id.argtypes = [vp, i32]
     lib.mastb200_comm_init.argtypes = [vp, i32, i32, vp]
     lib.mastb200_comm_attach.argtypes = [vp, vp, i32, i32]
@@ -307,6 +313,29 @@ class Context:
         self._ck(self._lib.mastb200_stress_functional_density_derivative(self._h, _ptr(X), p_norm, rho_exp, sigma0,
                                                                          _ptr(_np(elem_mask, np.uint8)), _ptr(sums),
                                                                          _ptr(dq_drho)))
+
+    # ---- density filter, volume ----
+    def filter_init(self, radius, dv_node=None):
+        nnz = C.c_int64()
+        self._ck(self._lib.mastb200_filter_init(self._h, float(radius), _ptr(_np(dv_node, np.uint8)), C.byref(nnz)))
+        self._filter_nnz = nnz.value
+        return nnz.value
+
+    def filter_get(self):
+        rp = np.empty(self.n_nodes + 1, np.int64); col = np.empty(self._filter_nnz, np.int32); w = np.empty(self._filter_nnz)
+        self._ck(self._lib.mastb200_filter_get(self._h, _ptr(rp), _ptr(col), _ptr(w)))
+        return rp, col, w
+
+    def filter_apply(self, d, rho):
+        self._ck(self._lib.mastb200_filter_apply(self._h, _ptr(d), _ptr(rho)))
+
+    def filter_apply_transpose(self, G, grad):
+        self._ck(self._lib.mastb200_filter_apply_transpose(self._h, _ptr(G), _ptr(grad)))
+
+    def volume(self, rho, dV_drho=None):
+        v = C.c_double()
+        self._ck(self._lib.mastb200_volume(self._h, _ptr(rho), C.byref(v), _ptr(dV_drho)))
+        return v.value
 
     # ---- communicator, linear solve ----
     @staticmethod

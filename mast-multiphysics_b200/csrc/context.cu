@@ -919,6 +919,7 @@ int mastb200_set_mesh(mastb200_context* ctx, int32_t elem_type, int64_t n_elem, 
   ctx->have_dofs = false; ctx->owned.clear(); ctx->cmask.clear(); ctx->has_constraints = false; ctx->has_ghosts = false;
   ctx->rho_set = false; ctx->rho_ext = nullptr; ctx->thermal = false; ctx->T_nodal = false; ctx->T_ext = nullptr;
   ctx->last_R = nullptr;
+  ctx->have_filter = false; ctx->have_nodal_vol = false;
   ctx->sp_elem.clear(); ctx->sp_side.clear(); ctx->sp_p.clear();
   ctx->fl_node.clear(); ctx->fl_ptr.clear(); ctx->fl_face_nodes.clear(); ctx->fl_k.clear(); ctx->fl_p.clear();
   ctx->have_heat_sides = false;

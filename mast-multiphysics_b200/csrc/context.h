@@ -192,6 +192,14 @@ struct mastb200_context {
   };
   std::vector<Neighbour*> neighbours;
   bool auto_localize = false;      // sweeps refresh the ghost values of X themselves (device X, in place)
+  // density filter and material volume (filter.cu)
+  DevBuf<int64_t> f_ptr;
+  DevBuf<int32_t> f_col;
+  DevBuf<double> f_raw, f_sum, nodal_vol;
+  DevBuf<uint8_t> f_dv;
+  bool have_filter = false, f_has_dv = false, have_nodal_vol = false;
+  int64_t f_nnz = 0;
+  double f_radius = 0.;
   // linear solve (solver.cu)
   DevBuf<double> d_minv, d_pr, d_pz, d_pp, d_pAp, d_px, d_ppart, d_pscal;
 

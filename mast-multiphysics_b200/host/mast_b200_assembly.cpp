@@ -308,6 +308,7 @@ mastb200_context* AssemblyBase::_device_problem(const libMesh::SparseMatrix<Real
       libmesh_error_msg("device path: one property card (subdomain 0) plus diagonal_elem_subdomain_id subdomains");
   const MaterialPropertyCardBase& mat = card.get_material();
 
+  const bool fresh = _ctx == nullptr;
   if (!_ctx) {
     if (mastb200_create(_device_id, &_ctx) != MASTB200_OK) {
       _ctx = nullptr;
@@ -322,18 +323,54 @@ mastb200_context* AssemblyBase::_device_problem(const libMesh::SparseMatrix<Real
     _check(mastb200_set_mesh(_ctx, et, mesh.n_elem(), mesh.n_nodes(), mesh.xyz.data(), mesh.conn.data(),
                              diag.empty() ? nullptr : diag.data()), "set_mesh");
     _check(mastb200_set_dof_map(_ctx, (int32_t)nv, sys.constrained_dofs.data(), nullptr), "set_dof_map");
-    // side loads: SURFACE_PRESSURE on every side carrying the boundary id (structural_element_base.cpp:628-701)
-    std::vector<int32_t> se, ss;
-    std::vector<double> sp;
-    for (const auto& kv : _discipline->side_loads()) {
-      if (kv.second->type() != SURFACE_PRESSURE) libmesh_error_msg("side load type has no device path (SURFACE_PRESSURE only)");
-      const Real p = constant_of(*kv.second, "pressure", true);
-      for (const auto& s : mesh.get_boundary_info().sides())
-        if (s.id == kv.first) { se.push_back((int32_t)s.elem); ss.push_back(s.side); sp.push_back(p); }
-    }
-    if (!se.empty()) _check(mastb200_set_side_pressure(_ctx, (int64_t)se.size(), se.data(), ss.data(), sp.data()), "set_side_pressure");
     int64_t n_rows = 0, nnz = 0;
     _check(mastb200_build_pattern(_ctx, &n_rows, &nnz), "build_pattern");
+  }
+
+  // loads: SURFACE_PRESSURE sides (structural_element_base.cpp:628-701), heat-conduction side loads
+  // (heat_conduction_elem_base.cpp:428-483) and point loads (nonlinear_implicit_assembly.cpp:190-247).  Their values are
+  // Parameters the caller may change between sweeps (load stepping): gathered every time, re-sent when they differ
+  {
+    std::vector<int32_t> se, ss, pn;
+    std::vector<double> sp, hc, ta, em, pl, sig;
+    bool any_heat = false, any_rad = false;
+    double sbc = 0., T0 = 0.;
+    for (const auto& kv : _discipline->side_loads()) {
+      const BoundaryConditionType t = kv.second->type();
+      double v = 0., c = 0., a = 0., e = 0.;
+      if (t == SURFACE_PRESSURE) v = constant_of(*kv.second, "pressure", true);
+      else if (t == HEAT_FLUX) { v = constant_of(*kv.second, "heat_flux", true); any_heat = true; }
+      else if (t == CONVECTION_HEAT_FLUX) {
+        c = constant_of(*kv.second, "convection_coeff", true); a = constant_of(*kv.second, "ambient_temperature", true); any_heat = true;
+      } else if (t == SURFACE_RADIATION_HEAT_FLUX) {
+        e = constant_of(*kv.second, "emissivity", true); a = constant_of(*kv.second, "ambient_temperature", true);
+        sbc = constant_of(*kv.second, "stefan_bolzmann_constant", true); T0 = constant_of(*kv.second, "reference_zero_temperature", true);
+        any_heat = any_rad = true;
+      } else libmesh_error_msg("side load type has no device path");
+      for (const auto& sd : mesh.get_boundary_info().sides())
+        if (sd.id == kv.first) {
+          se.push_back((int32_t)sd.elem); ss.push_back(sd.side); sp.push_back(v); hc.push_back(c); ta.push_back(a); em.push_back(e);
+        }
+    }
+    for (const PointLoadCondition* pc : _discipline->point_loads()) {
+      const ConstantVectorFieldFunction* f = pc->get_if<ConstantVectorFieldFunction>("load");
+      if (!f || f->values.size() != nv) libmesh_error_msg("point load: a ConstantVectorFieldFunction \"load\" with one value per variable");
+      for (libMesh::dof_id_type n : pc->get_nodes()) { pn.push_back((int32_t)n); pl.insert(pl.end(), f->values.begin(), f->values.end()); }
+    }
+    sig = sp; sig.insert(sig.end(), hc.begin(), hc.end()); sig.insert(sig.end(), ta.begin(), ta.end());
+    sig.insert(sig.end(), em.begin(), em.end()); sig.insert(sig.end(), pl.begin(), pl.end());
+    sig.push_back(double(se.size())); sig.push_back(double(pn.size())); sig.push_back(sbc); sig.push_back(T0);
+    if (fresh || sig != _side_values) {
+      if (any_heat) {
+        if (structural) libmesh_error_msg("heat side loads on a structural system");
+        _check(mastb200_set_heat_side_loads_ex(_ctx, (int64_t)se.size(), se.data(), ss.data(), sp.data(), hc.data(), ta.data(),
+                                               any_rad ? em.data() : nullptr, sbc, T0), "set_heat_side_loads");
+      } else if (!se.empty() || !fresh) {
+        _check(mastb200_set_side_pressure(_ctx, (int64_t)se.size(), se.data(), ss.data(), sp.data()), "set_side_pressure");
+      }
+      if (!pn.empty() || !fresh) _check(mastb200_set_point_loads(_ctx, (int64_t)pn.size(), pn.data(), pl.data()), "set_point_loads");
+      _side_values = sig;
+    }
   }
 
   // values that may change between sweeps (parameters, density field): refreshed every time, cheap
@@ -403,9 +440,7 @@ void StressStrainOutputBase::init(const GeomElem&) { _host_element_path("StressS
 void StressStrainOutputBase::evaluate() { _host_element_path("StressStrainOutputBase::evaluate"); }
 void StressStrainOutputBase::evaluate_sensitivity(const FunctionBase&) { _host_element_path("StressStrainOutputBase::evaluate_sensitivity"); }
 void StressStrainOutputBase::output_derivative_for_elem(RealVectorX&) { _host_element_path("StressStrainOutputBase::output_derivative_for_elem"); }
-Real StressStrainOutputBase::output_sensitivity_total(const FunctionBase&) {
-  libmesh_error_msg("StressStrainOutputBase::output_sensitivity_total: use the adjoint path (calculate_output_derivative)");
-}
+Real StressStrainOutputBase::output_sensitivity_total(const FunctionBase&) { return _dq_dp; }
 // StressStrainOutputBase::functional_for_all_elems (stress_output_base.cpp:851-909); with skip_comm_sum the caller sums
 // the two integrals over the ranks first (here: one rank per context, the sums are this rank's)
 Real StressStrainOutputBase::output_total() {
@@ -467,17 +502,90 @@ void AssemblyBase::calculate_output_derivative(const libMesh::NumericVector<Real
   dq_dX.close();
 }
 
+int AssemblyBase::_card_parameter(const FunctionBase& f) const {
+  if (!_discipline) return -1;
+  const MaterialPropertyCardBase& mat = _discipline->get_property_card(0).get_material();
+  if (const ConstantFieldFunction* c = mat.get_if<ConstantFieldFunction>("E"))
+    if (&c->parameter() == &f) return MASTB200_PARAM_E;
+  if (const ConstantFieldFunction* c = mat.get_if<ConstantFieldFunction>("nu"))
+    if (&c->parameter() == &f) return MASTB200_PARAM_NU;
+  return -1;
+}
+
+// AssemblyBase::calculate_output_direct_sensitivity (assembly_base.cpp:434-550): output.evaluate_sensitivity(p) over the
+// elements = the partial derivative at fixed state plus (dq/dX) . dXdp
+void AssemblyBase::calculate_output_direct_sensitivity(const libMesh::NumericVector<Real>& X, bool,
+                                                       const libMesh::NumericVector<Real>* dXdp, bool, const FunctionBase& p,
+                                                       OutputAssemblyElemOperations& output) {
+  AssemblyElemOperations* saved = _elem_ops;
+  if (!_elem_ops) _elem_ops = &output;
+  mastb200_context* ctx = _device_problem(nullptr);
+  _elem_ops = saved;
+  output.zero_for_sensitivity();
+  if (ComplianceOutput* c = dynamic_cast<ComplianceOutput*>(&output)) {
+    // compliance_output.cpp:106-150: -d(f_ext)/dp . u - f_ext . du/dp; the device loads do not depend on a density DV or a
+    // card parameter, a load's own Parameter is not on the device path
+    if (!dynamic_cast<const DensityDesignVariable*>(&p) && _card_parameter(p) < 0)
+      libmesh_error_msg("calculate_output_direct_sensitivity: parameter " + p.name() + " has no device path");
+    double dq = 0.;
+    _check(mastb200_compliance_direct_sensitivity(ctx, X.get_array_read(), dXdp ? dXdp->get_array_read() : nullptr, &dq),
+           "compliance_direct_sensitivity");
+    c->_dcompliance_dp = dq;
+    return;
+  }
+  if (StressStrainOutputBase* so = dynamic_cast<StressStrainOutputBase*>(&output)) {
+    if (!so->_primal_data_initialized) libmesh_error_msg("calculate_output_direct_sensitivity: call calculate_output first");
+    const DensityDesignVariable* dv = dynamic_cast<const DensityDesignVariable*>(&p);
+    if (!dv) libmesh_error_msg("stress output sensitivity: density design variables only");
+    const double sums[2] = {so->_sigma_vm_int, so->_JxW_val};
+    const size_t nn = system().get_mesh().n_nodes();
+    double dq = 0.;
+    if (_rho_field) {  // partial derivative at fixed state: W^T (dq / d rho_n)   (stress_output_base.cpp:911-1043)
+      std::vector<double> G(nn);
+      _check(mastb200_stress_functional_density_derivative(ctx, X.get_array_read(), so->_p_norm_stress, so->_rho, so->_sigma0, nullptr,
+                                                           sums, G.data()), "stress_functional_density_derivative");
+      const int64_t ptr[2] = {0, (int64_t)dv->nodes.size()};
+      _check(mastb200_apply_dv_map_transpose(ctx, G.data(), 1, ptr, dv->nodes.data(), dv->weights.data(), &dq), "apply_dv_map_transpose");
+    }
+    if (dXdp) {
+      std::vector<double> g(system().n_dofs());
+      _check(mastb200_stress_functional_derivative(ctx, X.get_array_read(), so->_p_norm_stress, so->_rho, so->_sigma0, nullptr, sums,
+                                                   g.data()), "stress_functional_derivative");
+      const double* d = dXdp->get_array_read();
+      for (size_t i = 0; i < g.size(); ++i) dq += g[i] * d[i];
+    }
+    so->_dq_dp = dq;
+    return;
+  }
+  libmesh_error_msg("calculate_output_direct_sensitivity: only ComplianceOutput and StressStrainOutputBase are on the device path");
+}
+
 Real AssemblyBase::calculate_output_adjoint_sensitivity(const libMesh::NumericVector<Real>& X, bool if_localize_sol,
                                                         const libMesh::NumericVector<Real>& adj_sol, const FunctionBase& p,
                                                         AssemblyElemOperations& elem_ops, OutputAssemblyElemOperations& output,
                                                         const bool include_partial_sens) {
   // dq/dp = adj . dR/dp [+ partial q / partial p]   (assembly_base.cpp:555-590)
-  std::vector<const FunctionBase*> pv(1, &p);
-  std::vector<Real> sens;
-  calculate_output_adjoint_sensitivity_multiple_parameters_no_direct(X, if_localize_sol, adj_sol, pv, elem_ops, output, sens);
-  // density DVs do not enter the non-follower pressure load, so the partial derivative of the compliance is zero
-  (void)include_partial_sens;
-  return sens[0];
+  Real dq_dp = 0.;
+  if (dynamic_cast<const DensityDesignVariable*>(&p)) {
+    std::vector<const FunctionBase*> pv(1, &p);
+    std::vector<Real> sens;
+    calculate_output_adjoint_sensitivity_multiple_parameters_no_direct(X, if_localize_sol, adj_sol, pv, elem_ops, output, sens);
+    dq_dp = sens[0];
+  } else {  // a Parameter of the card: the reference's own recipe, sensitivity_assemble + dot
+    libMesh::NumericVector<Real> dres(system().n_dofs());
+    AssemblyElemOperations* saved = _elem_ops;
+    _elem_ops = &elem_ops;
+    const bool ok = this->sensitivity_assemble(X, if_localize_sol, p, dres);
+    _elem_ops = saved;
+    if (!ok) libmesh_error_msg("parameter " + p.name() + ": no device sensitivity path");
+    const double *a = adj_sol.get_array_read(), *d = dres.get_array_read();
+    for (size_t i = 0; i < dres.size(); ++i) dq_dp += a[i] * d[i];
+  }
+  if (include_partial_sens) {  // :578-586: the partial sensitivity of the output, with zero solution sensitivity
+    calculate_output_direct_sensitivity(X, if_localize_sol, nullptr, false, p, output);
+    dq_dp += output.output_sensitivity_total(p);
+  }
+  return dq_dp;
 }
 
 void AssemblyBase::calculate_output_adjoint_sensitivity_multiple_parameters_no_direct(
@@ -528,14 +636,46 @@ void NonlinearImplicitAssembly::residual_and_jacobian(const libMesh::NumericVect
   if (J && close_matrix) J->close();
 }
 
-bool NonlinearImplicitAssembly::sensitivity_assemble(const libMesh::NumericVector<Real>&, bool, const FunctionBase& f,
-                                                     libMesh::NumericVector<Real>&, bool) {
-  // The reference assembles one global dR/dp vector per parameter (:515-686).  The device path never forms that vector
-  // for density DVs (it contracts with the adjoint inside the sweep: calculate_output_adjoint_sensitivity*); returning
-  // false is the documented "not implemented for this parameter, caller may finite-difference" answer
-  // (assembly_base.h:241-244).
-  (void)f;
-  return false;
+// NonlinearImplicitAssembly::sensitivity_assemble (nonlinear_implicit_assembly.cpp:515-686): the global dR/dp vector of one
+// parameter.  Device paths: a density design variable (SIMP) and the card's E / nu Parameters (3D solids, linear strain);
+// for anything else the reference's answer "false => the caller may finite-difference" (assembly_base.h:241-244).
+bool NonlinearImplicitAssembly::sensitivity_assemble(const libMesh::NumericVector<Real>& X, bool, const FunctionBase& f,
+                                                     libMesh::NumericVector<Real>& sensitivity_rhs, bool close_vector) {
+  mastb200_context* ctx = _device_problem(nullptr);
+  int rc;
+  if (const DensityDesignVariable* dv = dynamic_cast<const DensityDesignVariable*>(&f)) {
+    rc = mastb200_sensitivity_assemble(ctx, X.get_array_read(), MASTB200_PARAM_DENSITY_DV, (int64_t)dv->nodes.size(), dv->nodes.data(),
+                                       dv->weights.data(), sensitivity_rhs.get_array());
+  } else {
+    const int kind = _card_parameter(f);
+    if (kind < 0) return false;
+    rc = mastb200_sensitivity_assemble(ctx, X.get_array_read(), kind, 0, nullptr, nullptr, sensitivity_rhs.get_array());
+  }
+  if (rc == MASTB200_ERR_UNSUPPORTED) return false;
+  _check(rc, "sensitivity_assemble");
+  if (close_vector) sensitivity_rhs.close();
+  return true;
+}
+
+void NonlinearImplicitAssembly::linearized_jacobian_solution_product(const libMesh::NumericVector<Real>& X,
+                                                                     const libMesh::NumericVector<Real>& dX,
+                                                                     libMesh::NumericVector<Real>& JdX, libMesh::NonlinearImplicitSystem&) {
+  mastb200_context* ctx = _device_problem(nullptr);
+  _check(mastb200_linearized_jacobian_solution_product(ctx, X.get_array_read(), dX.get_array_read(), JdX.get_array()),
+         "linearized_jacobian_solution_product");
+  JdX.close();
+}
+
+void NonlinearImplicitAssembly::second_derivative_dot_solution_assembly(const libMesh::NumericVector<Real>&,
+                                                                        const libMesh::NumericVector<Real>&,
+                                                                        libMesh::SparseMatrix<Real>& d_JdX_dX,
+                                                                        libMesh::NonlinearImplicitSystem&) {
+  // d(J dX)/dX: with LINEAR_STRAIN the tangent does not depend on the state, the matrix is identically zero; the
+  // Green-Lagrange case needs the third derivative of the strain energy and has no device path
+  if (_discipline && _discipline->get_property_card(0).strain_type() == NONLINEAR_STRAIN)
+    libmesh_error_msg("second_derivative_dot_solution_assembly with NONLINEAR_STRAIN has no device path");
+  std::memset(d_JdX_dX.values(), 0, sizeof(Real) * d_JdX_dX.n_nonzeros());
+  if (close_matrix) d_JdX_dX.close();
 }
 
 }  // namespace MAST

@@ -63,8 +63,15 @@ class ConstantFieldFunction : public FieldFunction<Real> {
  public:
   ConstantFieldFunction(const std::string& nm, const Parameter& p) : FieldFunction<Real>(nm), _p(p) {}
   Real value() const { return _p(); }
+  const Parameter& parameter() const { return _p; }  // the Parameter sensitivity_assemble is asked about
  private:
   const Parameter& _p;
+};
+// constant vector field (a point load's "load": one value per system variable)
+class ConstantVectorFieldFunction : public FieldFunction<RealVectorX> {
+ public:
+  ConstantVectorFieldFunction(const std::string& nm, RealVectorX v) : FieldFunction<RealVectorX>(nm), values(std::move(v)) {}
+  RealVectorX values;
 };
 // nodal scalar field (the role of MAST::MeshFieldFunction over the density system, src/base/mesh_field_function.cpp:72-100)
 class NodalFieldFunction : public FieldFunction<Real> {
@@ -110,7 +117,9 @@ class FunctionSetBase {  // src/base/function_set_base.h
   std::map<std::string, FunctionBase*> _map;
 };
 
-enum BoundaryConditionType { SURFACE_PRESSURE, TEMPERATURE, HEAT_SOURCE, DIRICHLET };  // src/base/boundary_condition_base.h
+enum BoundaryConditionType {  // src/base/boundary_condition_base.h
+  SURFACE_PRESSURE, TEMPERATURE, HEAT_SOURCE, DIRICHLET, POINT_LOAD, HEAT_FLUX, CONVECTION_HEAT_FLUX, SURFACE_RADIATION_HEAT_FLUX
+};
 class BoundaryConditionBase : public FunctionSetBase {
  public:
   explicit BoundaryConditionBase(BoundaryConditionType t) : _type(t) {}
@@ -127,6 +136,16 @@ class DirichletBoundaryCondition : public BoundaryConditionBase {  // src/bounda
  private:
   libMesh::boundary_id_type _bid = 0;
   std::vector<unsigned int> _vars;
+};
+
+// a load on a set of nodes (src/boundary_condition/point_load_condition.h): "load" = ConstantVectorFieldFunction
+class PointLoadCondition : public BoundaryConditionBase {
+ public:
+  explicit PointLoadCondition(BoundaryConditionType t = POINT_LOAD) : BoundaryConditionBase(t) {}
+  void add_node(libMesh::dof_id_type n) { _nodes.insert(n); }
+  const std::set<libMesh::dof_id_type>& get_nodes() const { return _nodes; }
+ private:
+  std::set<libMesh::dof_id_type> _nodes;
 };
 
 class MaterialPropertyCardBase : public FunctionSetBase {};
@@ -185,6 +204,8 @@ class PhysicsDisciplineBase {  // src/base/physics_discipline_base.h
   void add_side_load(libMesh::boundary_id_type bid, BoundaryConditionBase& load);
   void add_dirichlet_bc(libMesh::boundary_id_type bid, DirichletBoundaryCondition& load);
   void add_volume_load(libMesh::subdomain_id_type sid, BoundaryConditionBase& load);
+  void add_point_load(PointLoadCondition& load) { _point_loads.insert(&load); }
+  const std::set<PointLoadCondition*>& point_loads() const { return _point_loads; }
   void set_property_for_subdomain(libMesh::subdomain_id_type sid, const ElementPropertyCardBase& prop);
   const ElementPropertyCardBase& get_property_card(unsigned int sid) const;
   void init_system_dirichlet_bc(NonlinearSystem& sys) const;
@@ -197,6 +218,7 @@ class PhysicsDisciplineBase {  // src/base/physics_discipline_base.h
   std::multimap<libMesh::boundary_id_type, BoundaryConditionBase*> _side_bc;
   std::multimap<libMesh::subdomain_id_type, BoundaryConditionBase*> _vol_bc;
   std::map<libMesh::boundary_id_type, DirichletBoundaryCondition*> _dirichlet;
+  std::set<PointLoadCondition*> _point_loads;
   std::map<libMesh::subdomain_id_type, const ElementPropertyCardBase*> _prop;
 };
 
@@ -294,7 +316,7 @@ class StressStrainOutputBase : public OutputAssemblyElemOperations {
   void zero_for_analysis() override { _sigma_vm_int = 0.; _JxW_val = 0.; _primal_data_initialized = false; }
   void zero_for_sensitivity() override {}
   Real output_total() override;   // functional_for_all_elems
-  Real output_sensitivity_total(const FunctionBase&) override;
+  Real output_sensitivity_total(const FunctionBase&) override;  // set by calculate_output_direct_sensitivity
   void evaluate() override;
   void evaluate_sensitivity(const FunctionBase& f) override;
   void output_derivative_for_elem(RealVectorX& dq_dX) override;
@@ -302,6 +324,7 @@ class StressStrainOutputBase : public OutputAssemblyElemOperations {
   friend class AssemblyBase;
   Real _p_norm_stress = 2., _p_norm_weight = 1., _rho = 1., _sigma0 = 1.;
   Real _sigma_vm_int = 0., _JxW_val = 0.;   // the two sums of functional_for_all_elems (this rank's part)
+  Real _dq_dp = 0.;                         // last direct sensitivity
   bool _primal_data_initialized = false;
 };
 
@@ -348,6 +371,10 @@ class AssemblyBase : public libMesh::NonlinearImplicitSystem::ComputeResidualand
                                 OutputAssemblyElemOperations& output);
   virtual void calculate_output_derivative(const libMesh::NumericVector<Real>& X, bool if_localize_sol,
                                            OutputAssemblyElemOperations& output, libMesh::NumericVector<Real>& dq_dX);
+  // assembly_base.h:282-288: partial (fixed-state) sensitivity of the output plus dq/dX . dXdp when dXdp is given
+  virtual void calculate_output_direct_sensitivity(const libMesh::NumericVector<Real>& X, bool if_localize_sol,
+                                                   const libMesh::NumericVector<Real>* dXdp, bool if_localize_sol_sens,
+                                                   const FunctionBase& p, OutputAssemblyElemOperations& output);
   virtual Real calculate_output_adjoint_sensitivity(const libMesh::NumericVector<Real>& X, bool if_localize_sol,
                                                     const libMesh::NumericVector<Real>& adj_sol, const FunctionBase& p,
                                                     AssemblyElemOperations& elem_ops, OutputAssemblyElemOperations& output,
@@ -378,6 +405,9 @@ class AssemblyBase : public libMesh::NonlinearImplicitSystem::ComputeResidualand
   int _device_id;
   bool _pattern_checked;
   const NodalFieldFunction* _rho_field;
+  std::vector<double> _side_values;   // side / point load values of the last sweep: loads are re-sent when they change
+  // which Parameter of the property card a FunctionBase is: MASTB200_PARAM_E / _NU, or -1
+  int _card_parameter(const FunctionBase& f) const;
 };
 
 class NonlinearImplicitAssembly : public AssemblyBase {
@@ -396,6 +426,12 @@ class NonlinearImplicitAssembly : public AssemblyBase {
                              libMesh::SparseMatrix<Real>* J, libMesh::NonlinearImplicitSystem& S) override;
   bool sensitivity_assemble(const libMesh::NumericVector<Real>& X, bool if_localize_sol, const FunctionBase& f,
                             libMesh::NumericVector<Real>& sensitivity_rhs, bool close_vector = true) override;
+  // nonlinear_implicit_assembly.h:115: JdX = J(X) dX without the matrix (matrix-free on the device)
+  virtual void linearized_jacobian_solution_product(const libMesh::NumericVector<Real>& X, const libMesh::NumericVector<Real>& dX,
+                                                    libMesh::NumericVector<Real>& JdX, libMesh::NonlinearImplicitSystem& S);
+  // nonlinear_implicit_assembly.h:125: d(J dX)/dX for the second-order adjoint; identically zero for linear strain
+  virtual void second_derivative_dot_solution_assembly(const libMesh::NumericVector<Real>& X, const libMesh::NumericVector<Real>& dX,
+                                                       libMesh::SparseMatrix<Real>& d_JdX_dX, libMesh::NonlinearImplicitSystem& S);
  protected:
   PostAssemblyOperation* _post_assembly;
   Real _res_l2_norm;

@@ -1490,6 +1490,69 @@ int oracle_stress_functional_density_sensitivity(const OracleProblem* p, const d
   return 0;
 }
 
+// MAST::FilterBase::_init (src/level_set/filter_base.cpp:378-447, the linear search; _init2 :275-372 finds the same set
+// with a KD-tree): for every node 1 all nodes 2 with |x_1 - x_2| <= radius, weight (radius - d_12) / sum, node 2 ascending.
+// row_ptr[n_nodes+1]; call with col == NULL to size.  Returns nnz.
+int64_t oracle_filter_weights(int64_t n_nodes, const double* xyz, double radius, int64_t* row_ptr, int32_t* col, double* weight) {
+  int64_t k = 0;
+  row_ptr[0] = 0;
+  for (int64_t a = 0; a < n_nodes; ++a) {
+    double sum = 0.;
+    const int64_t k0 = k;
+    for (int64_t b = 0; b < n_nodes; ++b) {
+      const double dx = xyz[a * 3] - xyz[b * 3], dy = xyz[a * 3 + 1] - xyz[b * 3 + 1], dz = xyz[a * 3 + 2] - xyz[b * 3 + 2];
+      const double d12 = std::sqrt(dx * dx + dy * dy + dz * dz);
+      if (d12 <= radius) {                                                  // :419
+        sum += radius - d12;                                                // :421
+        if (col) { col[k] = (int32_t)b; weight[k] = radius - d12; }        // :424
+        ++k;
+      }
+    }
+    if (col)
+      for (int64_t i = k0; i < k; ++i) weight[i] /= sum;                   // :434-438
+    row_ptr[a + 1] = k;
+  }
+  return k;
+}
+
+// FilterBase::compute_filtered_values (filter_base.cpp:59-97): filtered value for the design-variable nodes (dv == NULL:
+// all), the input itself for the others
+void oracle_filtered_values(int64_t n_nodes, const int64_t* row_ptr, const int32_t* col, const double* weight,
+                            const uint8_t* dv, const double* input, double* output) {
+  for (int64_t n = 0; n < n_nodes; ++n) {
+    output[n] = 0.;
+    for (int64_t k = row_ptr[n]; k < row_ptr[n + 1]; ++k) {
+      if (!dv || dv[n]) output[n] += input[col[k]] * weight[k];              // :86
+      else output[n] = input[n];                                           // :88
+    }
+  }
+}
+
+// material volume of examples/structural/example_6/example_6.cpp:714-745: sum over the elements of
+// volume(e) * mean nodal density; dV_drho (may be NULL): derivative w.r.t. every nodal density (:748-788 for one DV)
+double oracle_volume(const OracleProblem* p, const double* rho, double* dV_drho) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  if (dV_drho) std::fill(dV_drho, dV_drho + p->n_nodes, 0.);
+  std::vector<double> Xe;
+  double V = 0.;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    double vol = 0.;
+    for (int q = 0; q < fe.nq; ++q) vol += fe.JxW[q];
+    double r = 0.;
+    for (int a = 0; a < ei.nn; ++a) r += rho[p->conn[e * ei.nn + a]];
+    r /= (1. * ei.nn);
+    V += vol * r;
+    if (dV_drho)
+      for (int a = 0; a < ei.nn; ++a) dV_drho[p->conn[e * ei.nn + a]] += vol / (1. * ei.nn);
+  }
+  return V;
+}
+
+
 void oracle_plate_section_matrices(double E, double nu, double h, double off, double kappa, int plane_strain,
                                    double* A9, double* B9, double* D9, double* S4) {
   Mat C;

@@ -116,6 +116,13 @@ int oracle_stress_functional_density_sensitivity(const OracleProblem* p, const d
                                                  double sigma0, int64_t n_dv, const int64_t* dv_ptr, const int32_t* dv_node,
                                                  const double* dv_weight, double* sens);
 
+/* MAST::FilterBase: geometric density filter (linear radius search), filtered values, and the material volume of
+ * example_6 with its derivative w.r.t. the nodal densities */
+int64_t oracle_filter_weights(int64_t n_nodes, const double* xyz, double radius, int64_t* row_ptr, int32_t* col, double* weight);
+void oracle_filtered_values(int64_t n_nodes, const int64_t* row_ptr, const int32_t* col, const double* weight,
+                            const uint8_t* dv, const double* input, double* output);
+double oracle_volume(const OracleProblem* p, const double* rho, double* dV_drho);
+
 /* material matrices for the golden-vector tests */
 void oracle_stiffness_3d(double E, double nu, double* D36);
 void oracle_stiffness_3d_derivative(double E, double nu, double dE, double dnu, double* D36);

@@ -98,6 +98,10 @@ int main(int argc, char** argv) {
       }
     }
 
+    // a point load the c1 case adds for its second sweep (the discipline keeps the pointer: lives as long as it)
+    MAST::PointLoadCondition point_load;
+    MAST::ConstantVectorFieldFunction load_f("load", {1.0e5, -2.0e5, 3.0e5, 0., 0., 0.});
+
     MAST::NonlinearImplicitAssembly assembly;
     MAST::StructuralNonlinearAssemblyElemOperations structural_ops;
     MAST::HeatConductionNonlinearAssemblyElemOperations thermal_ops;
@@ -147,6 +151,54 @@ int main(int argc, char** argv) {
         sc << "sens1_single " << assembly.calculate_output_adjoint_sensitivity(*system.solution, false, adj, dv1, structural_ops, compliance) << "\n";
       }
       compliance.clear_discipline_and_system();
+    }
+    if (which == "c1") {
+      // sensitivity_assemble for the card's Parameters, the matrix-free J dX, point loads, load stepping of the pressure
+      libMesh::NumericVector<Real> dres(system.n_dofs());
+      const bool okE = assembly.sensitivity_assemble(*system.solution, false, E, dres);
+      write_bin(dir + "/dRdE.bin", dres.get_array_read(), dres.size());
+      const bool okN = assembly.sensitivity_assemble(*system.solution, false, nu, dres);
+      write_bin(dir + "/dRdnu.bin", dres.get_array_read(), dres.size());
+      const bool okH = assembly.sensitivity_assemble(*system.solution, false, h, dres);  // not a parameter of this problem
+      sc << "sens_E_ok " << okE << "\nsens_nu_ok " << okN << "\nsens_other_ok " << okH << "\n";
+      const std::vector<double> dXv = read_bin(dir + "/dX.bin");
+      libMesh::NumericVector<Real> dX(system.n_dofs()), JdX(system.n_dofs());
+      for (libMesh::dof_id_type i = 0; i < system.n_dofs(); ++i) dX.set(i, dXv[i]);
+      dX.close();
+      assembly.linearized_jacobian_solution_product(*system.solution, dX, JdX, system);
+      write_bin(dir + "/JdX.bin", JdX.get_array_read(), JdX.size());
+      {
+        MAST::ComplianceOutput compliance;
+        compliance.set_discipline_and_system(discipline, *sys_init);
+        assembly.calculate_output_direct_sensitivity(*system.solution, false, &dX, false, E, compliance);
+        sc << "compliance_direct " << compliance.output_sensitivity_total(E) << "\n";
+        compliance.clear_discipline_and_system();
+      }
+      point_load.add(load_f);
+      point_load.add_node(2540); point_load.add_node(1300); point_load.add_node(0);
+      discipline.add_point_load(point_load);
+      press = 2.5e7;  // load stepping: the assembly must pick the new value up
+      assembly.residual_and_jacobian(*system.solution, system.rhs, nullptr, system);
+      write_bin(dir + "/R_step.bin", system.rhs->get_array_read(), system.n_dofs());
+    }
+    if (which == "simp") {  // the global dR/dp vector of one filtered density design variable
+      libMesh::NumericVector<Real> dres(system.n_dofs());
+      MAST::DensityDesignVariable dv1("dv1", {1200, 1201}, {0.7, 0.3});
+      const bool ok = assembly.sensitivity_assemble(*system.solution, false, dv1, dres);
+      sc << "sens_dv_ok " << ok << "\n";
+      write_bin(dir + "/dRdp1.bin", dres.get_array_read(), dres.size());
+      // stress aggregate: adjoint sensitivity with the partial term (include_partial_sens = true)
+      const std::vector<double> adjv = read_bin(dir + "/adj.bin");
+      libMesh::NumericVector<Real> adj(system.n_dofs());
+      for (libMesh::dof_id_type i = 0; i < system.n_dofs(); ++i) adj.set(i, adjv[i]);
+      adj.close();
+      MAST::StressStrainOutputBase stress;
+      stress.set_discipline_and_system(discipline, *sys_init);
+      stress.set_aggregation_coefficients(6., 1., 1.5, 2.0e8);
+      assembly.calculate_output(*system.solution, false, stress);
+      sc << "stress_total_sens " << assembly.calculate_output_adjoint_sensitivity(*system.solution, false, adj, dv1, structural_ops, stress, true) << "\n";
+      sc << "stress_adjoint_only " << assembly.calculate_output_adjoint_sensitivity(*system.solution, false, adj, dv1, structural_ops, stress, false) << "\n";
+      stress.clear_discipline_and_system();
     }
     if (which == "c1") {  // StressStrainOutputBase: von Mises p-norm aggregate and its state derivative (adjoint rhs)
       MAST::StressStrainOutputBase stress;

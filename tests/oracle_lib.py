@@ -47,6 +47,9 @@ def lib():
         L.oracle_stress.argtypes = [P, vp, vp, vp, vp, vp]
         L.oracle_stress_functional.argtypes = [P, vp, dbl, dbl, dbl, vp]; L.oracle_stress_functional.restype = dbl
         L.oracle_stress_functional_density_sensitivity.argtypes = [P, vp, dbl, dbl, dbl, i64, vp, vp, vp, vp]
+        L.oracle_filter_weights.argtypes = [i64, vp, dbl, vp, vp, vp]; L.oracle_filter_weights.restype = i64
+        L.oracle_filtered_values.argtypes = [i64, vp, vp, vp, vp, vp, vp]
+        L.oracle_volume.argtypes = [P, vp, vp]; L.oracle_volume.restype = dbl
         L.oracle_stiffness_3d.argtypes = [dbl, dbl, vp]
         L.oracle_stiffness_3d_derivative.argtypes = [dbl, dbl, dbl, dbl, vp]
         L.oracle_thermal_expansion_A_3d.argtypes = [dbl, dbl, dbl, vp]
@@ -168,6 +171,25 @@ class Problem:
         node = np.ascontiguousarray(node, np.int32); load = np.ascontiguousarray(load, np.float64)
         assert lib().oracle_add_point_loads(C.byref(self.s), len(node), _p(node), _p(load), _p(R)) == 0
         return R
+
+    def filter_weights(self, radius):
+        rp = np.zeros(self.n_nodes + 1, np.int64)
+        nnz = lib().oracle_filter_weights(self.n_nodes, _p(self.xyz), radius, _p(rp), None, None)
+        col = np.empty(nnz, np.int32); w = np.empty(nnz)
+        lib().oracle_filter_weights(self.n_nodes, _p(self.xyz), radius, _p(rp), _p(col), _p(w))
+        return rp, col, w
+
+    def filtered_values(self, filt, d, dv=None):
+        rp, col, w = filt
+        out = np.empty(self.n_nodes)
+        dv = None if dv is None else np.ascontiguousarray(dv, np.uint8)
+        lib().oracle_filtered_values(self.n_nodes, _p(rp), _p(col), _p(w), _p(dv), _p(np.ascontiguousarray(d, np.float64)), _p(out))
+        return out
+
+    def volume(self, rho, want_gradient=False):
+        g = np.empty(self.n_nodes) if want_gradient else None
+        v = lib().oracle_volume(C.byref(self.s), _p(np.ascontiguousarray(rho, np.float64)), _p(g))
+        return (v, g) if want_gradient else v
 
     def compliance(self, X):
         return lib().oracle_compliance(C.byref(self.s), _p(X))

@@ -56,13 +56,26 @@ def _compare_common(prob, d, X):
 @pytest.mark.gpu
 def test_mirror_c1_cantilever_reference_layout(built, tmp_path):
     prob = O.cantilever(20, 10, 10, nv=6)
-    X = O.state(prob.n_dof, 1)
-    X.tofile(tmp_path / "X.bin")
+    X = O.state(prob.n_dof, 1); dX = O.state(prob.n_dof, 7)
+    X.tofile(tmp_path / "X.bin"); dX.tofile(tmp_path / "dX.bin")
     r = _run("c1", tmp_path)
     assert r.returncode == 0, r.stderr
     s = _compare_common(prob, tmp_path, X)
     assert np.isclose(s["compliance"], prob.compliance(X), rtol=1e-12)
     _close(np.fromfile(tmp_path / "dq_dX.bin"), prob.compliance_derivative(X))
+    # sensitivity_assemble for the card's Parameters (true) and a foreign one (false => caller may finite-difference)
+    assert s["sens_E_ok"] == 1 and s["sens_nu_ok"] == 1 and s["sens_other_ok"] == 0
+    _close(np.fromfile(tmp_path / "dRdE.bin"), prob.sensitivity_assemble_param(X, 1), 1e-11)
+    _close(np.fromfile(tmp_path / "dRdnu.bin"), prob.sensitivity_assemble_param(X, 2), 1e-11)
+    _close(np.fromfile(tmp_path / "JdX.bin"), prob.linearized_jacobian_solution_product(X, dX), 1e-11)
+    assert np.isclose(s["compliance_direct"], prob.compliance(dX), rtol=1e-12)
+    # second sweep: halved pressure (load stepping) and point loads
+    p2 = O.cantilever(20, 10, 10, nv=6)
+    p2.side_pressure[:] = 2.5e7
+    R2, _ = p2.residual_and_jacobian(X, want_J=False)
+    nodes = np.array([0, 1300, 2540], np.int32)
+    p2.add_point_loads(R2, nodes, np.tile([1.0e5, -2.0e5, 3.0e5, 0., 0., 0.], (3, 1)))
+    _close(np.fromfile(tmp_path / "R_step.bin"), R2)
     # StressStrainOutputBase through calculate_output / calculate_output_derivative
     q, dq = prob.stress_functional(X, 6.0, 1.5, 2.0e8, want_derivative=True)
     assert np.isclose(s["stress_functional"], q, rtol=1e-12)
@@ -81,6 +94,12 @@ def test_mirror_simp_adjoint_sensitivities(built, tmp_path):
     got = np.array([s["sens0"], s["sens1"], s["sens2"]])
     assert np.abs(got - ref).max() <= 1e-11 * np.abs(ref).max()
     assert np.isclose(s["sens1_single"], ref[1], rtol=1e-10)
+    # the dR/dp vector itself, and the stress aggregate's total sensitivity = adjoint part + partial part
+    assert s["sens_dv_ok"] == 1
+    _close(np.fromfile(tmp_path / "dRdp1.bin"), prob.sensitivity_assemble(X, [1200, 1201], [0.7, 0.3]), 1e-11)
+    part = prob.stress_functional_density_sensitivity(X, 6.0, 1.5, 2.0e8, [0, 2], [1200, 1201], [0.7, 0.3])[0]
+    assert np.isclose(s["stress_adjoint_only"], ref[1], rtol=1e-10)
+    assert np.isclose(s["stress_total_sens"], ref[1] + part, rtol=1e-10)
 
 
 @pytest.mark.gpu
