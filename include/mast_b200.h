@@ -202,6 +202,26 @@ int mastb200_stress_functional_density_derivative(mastb200_context* ctx, const d
                                                   double sigma0, const uint8_t* elem_mask, const double* sums,
                                                   double* dq_drho);
 
+/* ---- transient and modal variants of the assembly ------------------------------------------------------------------ */
+/* M_vals[nnz] [h|d]: the mass matrix (3D solids: rho_m = density, on the three translations) or the capacitance matrix
+ * (QUAD4 heat conduction: rho_m = rho cp, times the section thickness) in the pattern of mastb200_get_pattern, per-element
+ * constraint semantics of constrain_element_matrix.  lumped = 1: if_diagonal_mass_matrix (vol / n_shape for the solids,
+ * row sums for heat conduction).
+ *   <- StructuralElement3D::inertial_residual, src/elasticity/solid_element_3d.cpp:48-130;
+ *      HeatConductionElementBase::velocity_residual, src/heat_conduction/heat_conduction_elem_base.cpp:155-243 */
+int mastb200_mass_matrix(mastb200_context* ctx, double rho_m, int32_t lumped, double* M_vals);
+/* R = f_x(X) + M rate, J = df_x/dX + jac_coeff M, constrained per element as one matrix / vector.  rate [h|d]: the
+ * acceleration (second-order structural system, jac_coeff = 1 / beta / dt^2) or the temperature rate (first-order heat
+ * conduction, jac_coeff = 1 / beta / dt) the transient solver derives from X; R / J_vals [h|d], either may be NULL.
+ *   <- TransientAssembly::residual_and_jacobian, src/base/transient_assembly.cpp:63-180, with
+ *      SecondOrderNewmarkTransientSolver::elem_calculations, src/solver/second_order_newmark_transient_solver.cpp:277-380 */
+int mastb200_transient_residual_and_jacobian(mastb200_context* ctx, const double* X, const double* rate, double rho_m,
+                                             int32_t lumped, double jac_coeff, double* R, double* J_vals);
+/* A_vals = tangent stiffness at X, B_vals = mass matrix (both [nnz], [h|d])
+ *   <- EigenproblemAssembly::eigenproblem_assemble, src/base/eigenproblem_assembly.cpp:90-180 */
+int mastb200_eigenproblem_assemble(mastb200_context* ctx, const double* X, double rho_m, int32_t lumped, double* A_vals,
+                                   double* B_vals);
+
 /* ---- density filter and material volume of the SIMP loop ------------------------------------------------------------ */
 /* Geometric filter over the nodes of the mesh: W[n,k] = (radius - |x_n - x_k|) / sum_k' (radius - |x_n - x_k'|) for the
  * nodes k within `radius` of n, neighbours in ascending node id.  dv_node[n_nodes] (host) or NULL = every node is a

@@ -22,6 +22,7 @@ EXPORTED_SYMBOLS = [
     "mastb200_apply_dv_map_transpose", "mastb200_compliance", "mastb200_compliance_derivative",
     "mastb200_stress", "mastb200_stress_functional", "mastb200_stress_functional_derivative",
     "mastb200_stress_functional_density_derivative",
+    "mastb200_mass_matrix", "mastb200_transient_residual_and_jacobian", "mastb200_eigenproblem_assemble",
     "mastb200_filter_init", "mastb200_filter_get", "mastb200_filter_apply", "mastb200_filter_apply_transpose", "mastb200_volume",
     "mastb200_comm_unique_id", "mastb200_comm_init", "mastb200_comm_attach", "mastb200_set_ghost_exchange",
     "mastb200_build_localized_vector", "mastb200_all_reduce_sum", "mastb200_solve", "mastb200_near_null_space",
@@ -108,6 +109,9 @@ def load_library():
     lib.mastb200_stress_functional.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, C.POINTER(dbl)]
     lib.mastb200_stress_functional_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
     lib.mastb200_stress_functional_density_derivative.argtypes = [vp, vp, dbl, dbl, dbl, vp, vp, vp]
+    lib.mastb200_mass_matrix.argtypes = [vp, dbl, i32, vp]
+    lib.mastb200_transient_residual_and_jacobian.argtypes = [vp, vp, vp, dbl, i32, dbl, vp, vp]
+    lib.mastb200_eigenproblem_assemble.argtypes = [vp, vp, dbl, i32, vp, vp]
     lib.mastb200_filter_init.argtypes = [vp, dbl, vp, C.POINTER(i64)]
     lib.mastb200_filter_get.argtypes = [vp, vp, vp, vp]
     lib.mastb200_filter_apply.argtypes = [vp, vp, vp]
@@ -313,6 +317,17 @@ class Context:
         self._ck(self._lib.mastb200_stress_functional_density_derivative(self._h, _ptr(X), p_norm, rho_exp, sigma0,
                                                                          _ptr(_np(elem_mask, np.uint8)), _ptr(sums),
                                                                          _ptr(dq_drho)))
+
+    # ---- transient / modal ----
+    def mass_matrix(self, rho_m, M, lumped=False):
+        self._ck(self._lib.mastb200_mass_matrix(self._h, float(rho_m), int(bool(lumped)), _ptr(M)))
+
+    def transient_residual_and_jacobian(self, X, rate, rho_m, jac_coeff, R=None, J=None, lumped=False):
+        self._ck(self._lib.mastb200_transient_residual_and_jacobian(self._h, _ptr(X), _ptr(rate), float(rho_m), int(bool(lumped)),
+                                                                    float(jac_coeff), _ptr(R), _ptr(J)))
+
+    def eigenproblem_assemble(self, X, rho_m, A, B, lumped=False):
+        self._ck(self._lib.mastb200_eigenproblem_assemble(self._h, _ptr(X), float(rho_m), int(bool(lumped)), _ptr(A), _ptr(B)))
 
     # ---- density filter, volume ----
     def filter_init(self, radius, dv_node=None):

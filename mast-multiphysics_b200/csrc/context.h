@@ -233,6 +233,7 @@ int finish_out(mastb200_context* ctx, double* ptr, size_t n, const double* dev);
 int check_ready(mastb200_context* ctx);
 int ensure_generic_plan(mastb200_context* ctx);
 int64_t plan_nnz(const mastb200_context* ctx);
+int localize_if_needed(mastb200_context* ctx, const double* dV, int width);
 // ghost refresh of a device vector on the context stream (no-op without a configured exchange); solver.cu
 int comm_exchange(mastb200_context* ctx, double* dV, int width);
 int comm_all_reduce(mastb200_context* ctx, double* d_vals, int n);

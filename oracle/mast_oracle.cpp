@@ -1021,6 +1021,48 @@ static inline int64_t csr_find(const int64_t* row_ptr, const int32_t* col_idx, i
   return (it != e && *it == col) ? (it - col_idx) : -1;
 }
 
+// inertial / capacitance element matrix (jac_xddot resp. jac_xdot) and vector f_m = M rate:
+//   3D solids: StructuralElement3D::inertial_residual (solid_element_3d.cpp:48-130): consistent sum_q JxW N^T rho N on the
+//     three translations, or with if_diagonal_mass_matrix vol / n_shape rho on the diagonal;
+//   heat conduction: HeatConductionElementBase::velocity_residual (heat_conduction_elem_base.cpp:155-243): sum_q JxW
+//     (rho cp) N^T N (times the section thickness for the 2D card), row-sum lumped with if_diagonal_mass_matrix.
+static void elem_mass(const OracleProblem* p, const FE& fe, double rho_m, bool lumped, const Vec& rate, Vec& f, Mat& m) {
+  const int nn = fe.nn, nd = p->nv * nn;
+  m.resize(nd, nd);
+  f.assign(nd, 0.);
+  if (p->elem_type == ORACLE_QUAD4 && p->nv == 1) {
+    const double c = rho_m * p->thickness;
+    for (int q = 0; q < fe.nq; ++q)
+      for (int a = 0; a < nn; ++a)
+        for (int b = 0; b < nn; ++b) m(a, b) += fe.JxW[q] * c * fe.N(a, q) * fe.N(b, q);   // :213
+    if (lumped)
+      for (int a = 0; a < nn; ++a) {                                                        // :232-236
+        double s = 0.;
+        for (int b = 0; b < nn; ++b) { s += m(a, b); m(a, b) = 0.; }
+        m(a, a) = s;
+      }
+  } else {
+    const int ndim = 3;
+    if (lumped) {                                                                            // :84-99
+      double vol = 0.;
+      for (int q = 0; q < fe.nq; ++q) vol += fe.JxW[q];
+      vol /= (1. * nn);
+      for (int v = 0; v < ndim; ++v)
+        for (int a = 0; a < nn; ++a) m(v * nn + a, v * nn + a) = vol * rho_m;
+    } else {                                                                                 // :101-126
+      for (int q = 0; q < fe.nq; ++q)
+        for (int v = 0; v < ndim; ++v)
+          for (int a = 0; a < nn; ++a)
+            for (int b = 0; b < nn; ++b) m(v * nn + a, v * nn + b) += fe.JxW[q] * rho_m * fe.N(a, q) * fe.N(b, q);
+    }
+  }
+  for (int i = 0; i < nd; ++i) {
+    double s = 0.;
+    for (int j = 0; j < nd; ++j) s += m(i, j) * rate[j];
+    f[i] = s;
+  }
+}
+
 // the element loop of NonlinearImplicitAssembly::residual_and_jacobian (nonlinear_implicit_assembly.cpp:111-186)
 // restricted to elements [e0,e1) and rows [r0,r1) (r0=0,r1=n_dof for the whole system)
 static int assemble_range(const OracleProblem* p, const SideLoadIndex& sl, const double* Xg, double* R, double* Jv,
@@ -1240,6 +1282,84 @@ int oracle_add_point_loads(const OracleProblem* p, int64_t n, const int32_t* nod
       if (p->constrained && p->constrained[d]) continue;
       R[d] += -load[i * p->nv + v];
     }
+  return 0;
+}
+
+// Mass (capacitance) matrix in the system's pattern: the B matrix of EigenproblemAssembly::eigenproblem_assemble
+// (src/base/eigenproblem_assembly.cpp:90-180: constrain_element_matrix on A and B separately, :167-168)
+int oracle_mass_matrix(const OracleProblem* p, double rho_m, int lumped, const int64_t* row_ptr, const int32_t* col_idx,
+                       double* M_vals) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  const int64_t n_dof = p->n_nodes * p->nv;
+  std::fill(M_vals, M_vals + row_ptr[n_dof], 0.);
+  std::vector<int64_t> di;
+  std::vector<double> Xe;
+  Vec rate, f;
+  Mat m;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    if (p->diag_elem && p->diag_elem[e]) continue;
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size());
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    rate.assign(nd, 0.);
+    elem_mass(p, fe, rho_m, lumped != 0, rate, f, m);
+    constrain(p, di, &m, nullptr);
+    for (int i = 0; i < nd; ++i)
+      for (int j = 0; j < nd; ++j) {
+        const int64_t k = csr_find(row_ptr, col_idx, di[i], di[j]);
+        if (k < 0) return 2;
+        M_vals[k] += m(i, j);
+      }
+  }
+  return 0;
+}
+
+// TransientAssembly::residual_and_jacobian (src/base/transient_assembly.cpp:63-180) with the element combination of the
+// transient solvers: vec = f_m + f_x, mat = jac_coeff * df_m/d(rate) + df_x/dx -- SecondOrderNewmarkTransientSolver::
+// elem_calculations (src/solver/second_order_newmark_transient_solver.cpp:277-380: jac_coeff = 1 / beta / dt^2, rate = the
+// acceleration it derives from x) and FirstOrderNewmarkTransientSolver (jac_coeff = 1 / beta / dt, rate = the velocity);
+// the combined element matrix and vector are constrained together (:150-156)
+int oracle_transient_residual_and_jacobian(const OracleProblem* p, const double* X, const double* rate, double rho_m, int lumped,
+                                           double jac_coeff, double* R, double* J_vals, const int64_t* row_ptr,
+                                           const int32_t* col_idx) {
+  const ElemInfo ei = elem_info(p->elem_type);
+  const int64_t n_dof = p->n_nodes * p->nv;
+  if (R) std::fill(R, R + n_dof, 0.);
+  if (J_vals) std::fill(J_vals, J_vals + row_ptr[n_dof], 0.);
+  SideLoadIndex sl;
+  sl.build(p);
+  std::vector<int64_t> di;
+  std::vector<double> Xe;
+  Vec sol, rt, vec, fm;
+  Mat mat, mm;
+  for (int64_t e = 0; e < p->n_elem; ++e) {
+    dof_indices(p, e, ei.nn, di);
+    const int nd = int(di.size());
+    sol.resize(nd); rt.resize(nd);
+    for (int i = 0; i < nd; ++i) { sol[i] = X[di[i]]; rt[i] = rate[di[i]]; }
+    elem_calculations(p, sl, e, sol, J_vals != nullptr, vec, mat);
+    gather_coords(p, e, ei.nn, Xe);
+    FE fe;
+    fe_init(p->elem_type, Xe.data(), fe);
+    elem_mass(p, fe, rho_m, lumped != 0, rt, fm, mm);
+    for (int i = 0; i < nd; ++i) {
+      vec[i] += fm[i];
+      if (J_vals)
+        for (int j = 0; j < nd; ++j) mat(i, j) += jac_coeff * mm(i, j);
+    }
+    constrain(p, di, J_vals ? &mat : nullptr, R ? &vec : nullptr);
+    if (R)
+      for (int i = 0; i < nd; ++i) R[di[i]] += vec[i];
+    if (J_vals)
+      for (int i = 0; i < nd; ++i)
+        for (int j = 0; j < nd; ++j) {
+          const int64_t k = csr_find(row_ptr, col_idx, di[i], di[j]);
+          if (k < 0) return 2;
+          J_vals[k] += mat(i, j);
+        }
+  }
   return 0;
 }
 

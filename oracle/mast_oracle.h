@@ -94,6 +94,15 @@ int oracle_linearized_jacobian_solution_product(const OracleProblem* p, const do
 /* point loads of residual_and_jacobian: R[dofs of node[i]] -= load[i][nv] on unconstrained dofs */
 int oracle_add_point_loads(const OracleProblem* p, int64_t n, const int32_t* node, const double* load, double* R);
 
+/* mass / capacitance matrix in the pattern (EigenproblemAssembly's B; constrain_element_matrix per element) */
+int oracle_mass_matrix(const OracleProblem* p, double rho_m, int lumped, const int64_t* row_ptr, const int32_t* col_idx,
+                       double* M_vals);
+/* TransientAssembly::residual_and_jacobian with the element combination of the Newmark solvers:
+ * R = f_x(X) + M rate, J = df_x/dX + jac_coeff M, constrained per element */
+int oracle_transient_residual_and_jacobian(const OracleProblem* p, const double* X, const double* rate, double rho_m, int lumped,
+                                           double jac_coeff, double* R, double* J_vals, const int64_t* row_ptr,
+                                           const int32_t* col_idx);
+
 /* AssemblyBase::calculate_output_adjoint_sensitivity_multiple_parameters_no_direct: sens[i] = adj . dR/dp_i */
 int oracle_adjoint_sensitivity(const OracleProblem* p, const double* X, const double* adj, int64_t n_dv,
                                const int64_t* dv_ptr, const int32_t* dv_node, const double* dv_weight,

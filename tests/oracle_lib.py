@@ -39,6 +39,8 @@ def lib():
         L.oracle_elem_calculations.argtypes = [P, i64, vp, C.c_int, vp, vp]
         L.oracle_sensitivity_assemble.argtypes = [P, vp, i64, i64, vp, vp, vp]
         L.oracle_adjoint_sensitivity.argtypes = [P, vp, vp, i64, vp, vp, vp, vp]
+        L.oracle_mass_matrix.argtypes = [P, dbl, C.c_int, vp, vp, vp]
+        L.oracle_transient_residual_and_jacobian.argtypes = [P, vp, vp, dbl, C.c_int, dbl, vp, vp, vp, vp]
         L.oracle_sensitivity_assemble_param.argtypes = [P, vp, C.c_int, vp]
         L.oracle_linearized_jacobian_solution_product.argtypes = [P, vp, vp, vp]
         L.oracle_add_point_loads.argtypes = [P, i64, vp, vp, vp]
@@ -190,6 +192,20 @@ class Problem:
         g = np.empty(self.n_nodes) if want_gradient else None
         v = lib().oracle_volume(C.byref(self.s), _p(np.ascontiguousarray(rho, np.float64)), _p(g))
         return (v, g) if want_gradient else v
+
+    def mass_matrix(self, rho_m, lumped=False):
+        row_ptr, col = self.pattern()
+        M = np.empty(len(col))
+        assert lib().oracle_mass_matrix(C.byref(self.s), rho_m, int(lumped), _p(row_ptr), _p(col), _p(M)) == 0
+        return M
+
+    def transient_residual_and_jacobian(self, X, rate, rho_m, jac_coeff, lumped=False):
+        row_ptr, col = self.pattern()
+        R = np.empty(self.n_dof); J = np.empty(len(col))
+        rc = lib().oracle_transient_residual_and_jacobian(C.byref(self.s), _p(X), _p(rate), rho_m, int(lumped), jac_coeff,
+                                                          _p(R), _p(J), _p(row_ptr), _p(col))
+        assert rc == 0, rc
+        return R, J
 
     def compliance(self, X):
         return lib().oracle_compliance(C.byref(self.s), _p(X))
