@@ -524,6 +524,11 @@ int ensure_struct_plan(mastb200_context* ctx) {
     if (const char* e = getenv("MASTB200_STRUCT_KERNEL"))
       want = e[0] == 'm' && ctx->nv == 3 && (size_t)ctx->max_optin >= hex8_march_smem_bytes();
     S.march = want;
+    // MASTB200_STRUCT_KERNEL=slots: element results in shared-memory slots, gather straight to the CSR (sweep_hex8_slots.cu);
+    // same units as the lock-step kernel
+    S.slots = false;
+    if (const char* e = getenv("MASTB200_STRUCT_KERNEL"))
+      S.slots = e[0] == 's' && ctx->nv == 3 && (size_t)ctx->max_optin >= hex8_slots_smem_bytes();
     if (want) {
       std::vector<std::pair<int, int>> mx, my;
       chunks(nx + 1, kMarchTileX, mx);
@@ -808,9 +813,12 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     if (fused_G) { sp.adj = adj == X ? dX : dadj; sp.G = dG; }
     sp.E0 = p.E0; sp.lam1 = p.lam1; sp.mu1 = p.mu1; sp.rho_min = p.rho_min; sp.penalty = p.penalty;
     ctx->splan.last_march = S.march && ctx->nv == 3;
+    ctx->splan.last_slots = S.slots && ctx->nv == 3 && !fused_G && kStructWarps == 16;
     if (ctx->splan.last_march) {
       sp.units = S.m_units.p; sp.n_units = S.m_n_units;
       CU(launch_hex8_march(sp, S.m_n_ctas, ctx->stream));
+    } else if (ctx->splan.last_slots) {
+      CU(launch_hex8_slots(sp, std::max(1, std::min(S.n_units, ctx->sm_count)), ctx->stream));
     } else {
       CU(launch_hex8_struct(sp, S.n_ctas, ctx->stream));
     }
@@ -1551,7 +1559,7 @@ int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   s->smem_bytes = ctx->last_struct ? (int32_t)(lm ? hex8_march_smem_bytes() : hex8_struct_smem_bytes()) : (int32_t)D.smem;
   s->threads_per_cta = ctx->last_struct ? (lm ? hex8_march_threads() : hex8_struct_threads()) : hex8_sweep_threads();
   s->ctas = ctx->last_struct ? (lm ? ctx->splan.m_n_ctas : ctx->splan.n_ctas) : D.n_ctas;
-  s->structured = ctx->last_struct ? (lm ? 2 : 1) : (ctx->elem_type == MASTB200_QUAD4 && ctx->last_q4s ? 1 : 0);
+  s->structured = ctx->last_struct ? (lm ? 2 : (ctx->splan.last_slots ? 3 : 1)) : (ctx->elem_type == MASTB200_QUAD4 && ctx->last_q4s ? 1 : 0);
   if (ctx->timed) {
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a + ctx->carry_ms;

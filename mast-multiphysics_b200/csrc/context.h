@@ -136,6 +136,8 @@ struct mastb200_context {
     int64_t m_n_visits = 0;
     bool march = false;       // the march kernel serves nv = 3
     bool last_march = false;  // ... and ran the last sweep
+    bool slots = false;       // the slot kernel (sweep_hex8_slots.cu) serves nv = 3 without fused sensitivities
+    bool last_slots = false;
     void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); m_units.release(); }
   } splan;
   int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA

@@ -73,6 +73,11 @@ constexpr int kMarchTileX = 16, kMarchTileY = 4;
 size_t hex8_march_smem_bytes();
 int hex8_march_threads();
 cudaError_t launch_hex8_march(const StructParams& p, int n_ctas, cudaStream_t stream);
+// element results in shared-memory slots, row-owner gather straight to the CSR (sweep_hex8_slots.cu; 3-dof system, same units
+// as the lock-step kernel)
+size_t hex8_slots_smem_bytes();
+int hex8_slots_threads();
+cudaError_t launch_hex8_slots(const StructParams& p, int n_ctas, cudaStream_t stream);
 
 // ---- row-owner gather kernels for small elements (sweep_quad4_heat.cu) ---------------------------------------------
 constexpr int kGatherMaxNbr = 24;      // neighbours per row the gather kernels keep in shared memory

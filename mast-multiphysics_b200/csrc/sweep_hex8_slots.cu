@@ -1,0 +1,502 @@
+// sweep_hex8_slots.cu -- HEX8 linear-elastic residual + Jacobian sweep for ijk-numbered (build_cube) meshes, 3-dof
+// system: element results in shared-memory SLOTS, row-owner gather straight to the CSR (sm_100a, fp64).
+//
+// Same device counterpart as sweep_hex8_struct.cu -- the element loop of MAST::NonlinearImplicitAssembly::
+// residual_and_jacobian (/root/reference/src/base/nonlinear_implicit_assembly.cpp:111-186) with
+// StructuralElement3D::internal_residual (src/elasticity/solid_element_3d.cpp:135-423, linear strain) and the
+// isotropic D of src/property_cards/isotropic_material_property_card.cpp:512-528 -- with a different division of
+// labour between the two phases of an element plane.  The lock-step kernel of sweep_hex8_struct.cu scatter-ADDS every
+// element's pair blocks into per-node-pair accumulators (a read-modify-write per value, four elements per node column
+// ordered by counters, accumulators cleared after every plane) and its flush decodes (node, direction) per lane.  Here
+//   element phase : warp w owns a 2x2 block of elements (same geometry lanes and the same 12 mma.sync.m8n8k4.f64 as
+//                   the lock-step kernel: S_ij[a][b] = sum_q w g_a[i] g_b[j]); the pair blocks of an element are STORED
+//                   once into the element's own slot, arrays [value id][element column] -- cross pairs (bottom node,
+//                   top node; 144 values) plainly, in-plane pairs (78 unique values) added onto what the element below
+//                   stored for the same node plane (the only read-modify-write; same warp, so no ordering protocol).
+//                   No counters, no spinning, no clearing pass.
+//   gather phase  : item = (owned node, neighbour direction); three consecutive lanes take the x-neighbours -1, 0, +1 of one
+//                   (node, dy, dz), ten such triples per warp.  An item sums the <= 4 element columns that hold its pair
+//                   (fixed order: y then x ascending), K_AB = lam S + mu S^T + mu tr(S) I with libMesh's per-element
+//                   Dirichlet semantics goes straight to the CSR (three lanes = 72 contiguous bytes per row), and
+//                   f_A += K_AB u_B is joined over the triple by shuffles and over the nine (dy, dz) by a fixed-order sum.
+//                   At time s the items are: plane s with dz = 0, +1 and plane s+1 with dz = -1 (all of them read the
+//                   element plane s that has just been computed), so a slot lives for one plane only.
+// Two CTA barriers per plane.  Summation order of a CSR value: quadrature points inside the DMMA, then the element below
+// before the element above (in-plane pairs), then element columns y-major -- fixed, so runs are bitwise reproducible.
+// Serves nv = 3 without fused sensitivities; the six-variable layout and the fused density sensitivities stay with
+// sweep_hex8_struct.cu.
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace mastb200 {
+namespace {
+
+constexpr int SW = 16;                 // warps per CTA: 4 x 4 blocks of 2x2 elements
+constexpr int ST = SW * 32;
+constexpr int TCX = 9, TCY = 9;        // node columns of a tile (8 x 8 elements)
+constexpr int NS = TCX * TCY;
+constexpr int NSB = (NS + 3) & ~3;
+constexpr int NEP = 65;                // doubles per slot array: 64 element columns + 1 (bank = value id + column)
+constexpr int N_CR = 144, N_IN = 78;   // value arrays: cross pairs 9 x 16; in-plane 3 x 16 (i < j) + 3 x 10 (i == j, unordered)
+constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
+constexpr int MAXOWN = 49;
+constexpr double GP = 0.57735026918962576451;
+
+// shared-memory carve-up (bytes).  The in-plane regions start 8 doubles (mod 16) after the cross region so that the two
+// kinds of lanes of one store instruction fall into different banks.
+constexpr int O_CR = 0;
+constexpr int CR_BYTES = N_CR * NEP * 8;
+constexpr int IN_BYTES = N_IN * NEP * 8;
+constexpr int O_IN0 = O_CR + CR_BYTES + 64;
+constexpr int O_IN1 = O_IN0 + IN_BYTES + 16;
+constexpr int O_XYZ = O_IN1 + IN_BYTES;                  // [3 planes][3][NS]
+constexpr int O_U = O_XYZ + 3 * 3 * NS * 8;              // [4 planes][3][NS]
+constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;   // [SW][4 el][8 qp][QS]
+constexpr int O_CM = O_STAGE + SW * 4 * 8 * QS * 8;      // [4 planes][NSB] uint8
+constexpr int O_RHO = (O_CM + 4 * NSB + 7) & ~7;         // [3 planes][NS]
+constexpr int O_NODE = O_RHO + 3 * NS * 8;               // [64] int2: in-plane node id, lx | ly << 4 | xy boundary flags << 8
+constexpr int O_FP = O_NODE + 64 * 8;                    // [9 (dy, dz)][MAXOWN][3] force partials of a plane's items
+constexpr int O_CARRY = O_FP + 9 * MAXOWN * 3 * 8;       // [MAXOWN][3] dz = -1 partials of the plane above, from the step before
+constexpr int O_MISC = O_CARRY + MAXOWN * 3 * 8;
+constexpr int SMEM_BYTES = O_MISC + 16;
+static_assert((O_CR / 8) % 16 == 0 && (O_IN0 / 8) % 16 == 8 && (O_IN1 / 8) % 16 == 8, "bank phases of the slot regions");
+static_assert(O_XYZ % 8 == 0 && O_STAGE % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0 && O_FP % 8 == 0, "alignment");
+static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ double lds64(unsigned a) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct Sm {
+  double* xyz;
+  double* u;
+  double* stage;
+  uint8_t* cm;
+  double* rho;
+  int2* node;
+  double* fp;
+  double* carry;
+  int* misc;
+};
+
+// position of the pair (first node a, second node b; xy-local indices 0..3) within a 16-array group: the x bit of b moves
+// by 8, so that the three lanes of a gather triple and the eight lanes of a store quadrant hit distinct banks
+__device__ __forceinline__ int pm(int a, int b) { return (b & 1) * 8 + a * 2 + (b >> 1); }
+// unordered pair a <= b of 0..3 -> 0..9
+__device__ __forceinline__ int up(int a, int b) { return a * 4 - ((a * (a - 1)) >> 1) + (b - a); }
+
+struct LaneK {
+  double d0[2], d1[2], d2;   // reference gradients of N_m at qps q4 (h = 0) and q4 + 4 (h = 1)
+  int off[12];               // BYTE offset of value t = bb * 6 + k within its region (array start; the column is added)
+  unsigned pred;             // bit t: this lane stores C[k][bb]
+  int kind;                  // 0 cross pairs, 1 in-plane pairs of the bottom nodes (added), 2 of the top nodes (stored)
+};
+
+// Row / column index m of the DMMA tile is the element node (dx = m&1, dy = (m>>1)&1, dz = m>>2); lane = (m, q4) holds
+// C[k][bb] = S_(m,b)[KI[k]][KJ[k]] for b = 2 q4 + bb.
+__device__ __forceinline__ void make_lane(int lane, LaneK& lk) {
+  const int m = lane >> 2, q4 = lane & 3;
+  const double sx = (m & 1) ? 1. : -1., sy = (m & 2) ? 1. : -1., sz = (m & 4) ? 1. : -1.;
+  const double fx = 1. + sx * ((q4 & 1) ? GP : -GP), fy = 1. + sy * ((q4 & 2) ? GP : -GP);
+  const double fz0 = 1. - sz * GP, fz1 = 1. + sz * GP;
+  lk.d0[0] = 0.125 * sx * fy * fz0; lk.d0[1] = 0.125 * sx * fy * fz1;
+  lk.d1[0] = 0.125 * sy * fx * fz0; lk.d1[1] = 0.125 * sy * fx * fz1;
+  lk.d2 = 0.125 * sz * fx * fy;
+  lk.pred = 0u;
+  const int KI[6] = {0, 1, 2, 0, 0, 1}, KJ[6] = {0, 1, 2, 1, 2, 2};
+  const int mz = m >> 2, bz = q4 >> 1, m4 = m & 3;
+  lk.kind = mz == bz ? (mz == 0 ? 1 : 2) : 0;
+#pragma unroll
+  for (int bb = 0; bb < 2; ++bb) {
+    const int b4 = (2 * q4 + bb) & 3;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      int idx;
+      bool on = true;
+      if (mz == bz) {
+        if (k >= 3) idx = (k - 3) * 16 + pm(m4, b4);
+        else { on = m4 <= b4; idx = 48 + k * 10 + up(on ? m4 : b4, on ? b4 : m4); }
+      } else if (mz == 0) {  // bottom m, top b: S_(m,b)[KI][KJ]
+        idx = (KI[k] * 3 + KJ[k]) * 16 + pm(m4, b4);
+      } else {               // top m, bottom b: C = S_(m,b)[KI][KJ] = S_(b,m)[KJ][KI]; the diagonal components are the other lane's
+        on = k >= 3;
+        idx = (KJ[k] * 3 + KI[k]) * 16 + pm(b4, m4);
+      }
+      lk.off[bb * 6 + k] = idx * NEP * 8;
+      if (on) lk.pred |= 1u << (bb * 6 + k);
+    }
+  }
+}
+
+// ---- geometry: lane = (element el of the warp's 2x2 block, quadrature point q): J^-1 and w = JxW E to the stage -----
+template <bool SIMP>
+__device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& sm, int s, int base, int q, double* out) {
+  const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP, zeta = (q & 4) ? GP : -GP;
+  const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
+    const double d0 = ((m & 1) ? 0.125 : -0.125) * fy * fz, d1 = ((m & 2) ? 0.125 : -0.125) * fx * fz,
+                 d2 = ((m & 4) ? 0.125 : -0.125) * fx * fy;
+    const double* X = sm.xyz + (((m & 4) ? s + 1 : s) % 3) * 3 * NS + base + ((m >> 1) & 1) * TCX + (m & 1);
+    const double x0 = X[0], x1 = X[NS], x2 = X[2 * NS];
+    Jm[0][0] = fma(d0, x0, Jm[0][0]); Jm[0][1] = fma(d0, x1, Jm[0][1]); Jm[0][2] = fma(d0, x2, Jm[0][2]);
+    Jm[1][0] = fma(d1, x0, Jm[1][0]); Jm[1][1] = fma(d1, x1, Jm[1][1]); Jm[1][2] = fma(d1, x2, Jm[1][2]);
+    Jm[2][0] = fma(d2, x0, Jm[2][0]); Jm[2][1] = fma(d2, x1, Jm[2][1]); Jm[2][2] = fma(d2, x2, Jm[2][2]);
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = __drcp_rn(det);
+  double2* o = reinterpret_cast<double2*>(out);
+  o[0] = make_double2(c00 * idet, (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet);
+  o[1] = make_double2((Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet, c01 * idet);
+  o[2] = make_double2((Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet, (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet);
+  o[3] = make_double2(c02 * idet, (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet);
+  double E = p.E0;
+  if (SIMP) {  // modulus of the interpolated nodal density (examples/structural/example_6/example_6.cpp:100-137)
+    double r = 0.;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
+      r = fma(0.125 * fx * fy * fz, sm.rho[(((m & 4) ? s + 1 : s) % 3) * NS + base + ((m >> 1) & 1) * TCX + (m & 1)], r);
+    }
+    E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(r, p.penalty));
+  }
+  o[4] = make_double2((Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet, det * E);  // Gauss weights are 1 for the 2x2x2 rule
+}
+
+// ---- matrix + slot stores: all 32 lanes on one element -------------------------------------------------------------
+__device__ __forceinline__ void element_phase(const LaneK& lk, unsigned smem32, const double* st, int ecol, int par, int lane) {
+  const int q4 = lane & 3;
+  double A[3][2], w[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const double2* s2 = reinterpret_cast<const double2*>(st + (q4 + 4 * h) * QS);
+    const double2 v0 = s2[0], v1 = s2[1], v2 = s2[2], v3 = s2[3], v4 = s2[4];
+    A[0][h] = v0.x * lk.d0[h] + v0.y * lk.d1[h] + v1.x * lk.d2;
+    A[1][h] = v1.y * lk.d0[h] + v2.x * lk.d1[h] + v2.y * lk.d2;
+    A[2][h] = v3.x * lk.d0[h] + v3.y * lk.d1[h] + v4.x * lk.d2;
+    w[h] = v4.y;
+  }
+  double B[3][2], C[6][2];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { B[j][0] = A[j][0] * w[0]; B[j][1] = A[j][1] * w[1]; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { C[k][0] = 0.; C[k][1] = 0.; }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    dmma8x8x4(C[0][0], C[0][1], A[0][h], B[0][h]);
+    dmma8x8x4(C[1][0], C[1][1], A[1][h], B[1][h]);
+    dmma8x8x4(C[2][0], C[2][1], A[2][h], B[2][h]);
+    dmma8x8x4(C[3][0], C[3][1], A[0][h], B[1][h]);
+    dmma8x8x4(C[4][0], C[4][1], A[0][h], B[2][h]);
+    dmma8x8x4(C[5][0], C[5][1], A[1][h], B[2][h]);
+  }
+  // bottom in-plane pairs join what the element below left for node plane s (region IN[par]); top in-plane pairs open
+  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone
+  const unsigned rb = lk.kind == 0 ? O_CR : (((lk.kind == 1) == (par == 0)) ? O_IN0 : O_IN1);
+  const unsigned ar = smem32 + rb + ecol * 8;
+  double old[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) {
+    old[t] = 0.;
+    if (lk.kind == 1 && ((lk.pred >> t) & 1u)) old[t] = lds64(ar + lk.off[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < 12; ++t)
+    if ((lk.pred >> t) & 1u) sts64(ar + lk.off[t], old[t] + C[t % 6][t / 6]);
+}
+
+// ---- gather: item = (owned node column, dy, dz) x three lanes dx = -1, 0, +1 ------------------------------------------
+// At time s (element plane s just computed): node plane s with dz = 0 (in-plane slots, complete) and dz = +1, node plane
+// s + 1 with dz = -1 (cross slots of element plane s).
+__device__ __forceinline__ void gather_phase(const StructParams& p, const Sm& sm, unsigned smem32, const StructUnit& u, int s,
+                                             int n_own, unsigned inv_own, int64_t plane_nodes, int warp, int lane) {
+  const int l3 = (lane * 11) >> 5;  // lane / 3
+  const int di = lane - 3 * l3 - 1;
+  const int ntr = 9 * n_own;
+  const int par = s & 1;
+  const bool low_on = s >= u.z0;                       // node plane s is flushed by this unit
+  const bool up_on = s + 1 < u.z1 && s < p.nz;         // node plane s + 1 gets its dz = -1 blocks now
+#pragma unroll 1
+  for (int r = 0; r < 3; ++r) {
+    const int tr0 = (r * SW + warp) * 10;
+    if (tr0 >= ntr) break;
+    const int tr = tr0 + l3;
+    const bool tv = lane < 30 && tr < ntr;
+    const int combo = tv ? (int)(((unsigned)tr * inv_own) >> 16) : 0;
+    const int col = tv ? tr - combo * n_own : 0;
+    // (dy, dz) of the combo: the three dy = 0 combos come first (they have twice the element columns)
+    const int dj = combo < 3 ? 0 : (combo < 6 ? -1 : 1);
+    const int dk = (combo < 3 ? combo : (combo < 6 ? combo - 3 : combo - 6)) - 1;
+    const int2 ni = sm.node[col];
+    const int lx = ni.y & 15, ly = (ni.y >> 4) & 15;
+    const int pl = dk < 0 ? s + 1 : s;  // node plane of the item's row
+    const int flags = (ni.y >> 8) | (pl == 0 ? 16 : 0) | (pl == p.nz ? 32 : 0);  // x0, xN, y0, yN, z0, zN
+    const int kill = (di < 0 ? 1 : 0) | (di > 0 ? 2 : 0) | (dj < 0 ? 4 : 0) | (dj > 0 ? 8 : 0) | (dk < 0 ? 16 : 0) | (dk > 0 ? 32 : 0);
+    const bool on = tv && (dk < 0 ? up_on : low_on) && !(flags & kill);
+    double r0 = 0., r1 = 0., r2 = 0.;
+    if (on) {
+      double S[9];
+#pragma unroll
+      for (int c = 0; c < 9; ++c) S[c] = 0.;
+      const unsigned inb = smem32 + (par ? O_IN1 : O_IN0);
+#pragma unroll
+      for (int cy = 0; cy < 2; ++cy) {
+        const int my = 1 - cy, by = my + dj, ley = ly - 1 + cy;
+        if ((unsigned)by > 1u || (unsigned)ley >= (unsigned)u.ney) continue;
+#pragma unroll
+        for (int cx = 0; cx < 2; ++cx) {
+          const int mx = 1 - cx, bx = mx + di, lex = lx - 1 + cx;
+          if ((unsigned)bx > 1u || (unsigned)lex >= (unsigned)u.nex) continue;
+          const int m4 = mx + 2 * my, b4 = bx + 2 * by, e = ley * 8 + lex;
+          if (dk == 0) {
+            const unsigned a = inb + e * 8;
+            const unsigned pu = a + pm(m4, b4) * (NEP * 8), pl2 = a + pm(b4, m4) * (NEP * 8);
+            const unsigned pd = a + (48 + up(min(m4, b4), max(m4, b4))) * (NEP * 8);
+            S[1] += lds64(pu); S[2] += lds64(pu + 16 * NEP * 8); S[5] += lds64(pu + 32 * NEP * 8);
+            S[3] += lds64(pl2); S[6] += lds64(pl2 + 16 * NEP * 8); S[7] += lds64(pl2 + 32 * NEP * 8);
+            S[0] += lds64(pd); S[4] += lds64(pd + 10 * NEP * 8); S[8] += lds64(pd + 20 * NEP * 8);
+          } else {
+            // dz = +1: S_(A,B) with A the bottom node; dz = -1: the slot holds S_(B,A) (B bottom), i.e. the transpose
+            const unsigned a = smem32 + O_CR + ((dk > 0 ? pm(m4, b4) : pm(b4, m4)) * NEP + e) * 8;
+#pragma unroll
+            for (int c = 0; c < 9; ++c) S[c] += lds64(a + c * (16 * NEP * 8));
+          }
+        }
+      }
+      // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
+      const bool tr_ = dk < 0;
+      const double l1 = tr_ ? p.mu1 : p.lam1, l2 = tr_ ? p.lam1 : p.mu1;
+      const double trm = p.mu1 * (S[0] + S[4] + S[8]);
+      double K[3][3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i * 3 + j] + l2 * S[j * 3 + i] + (i == j ? trm : 0.);
+      const int slotA = ly * TCX + lx, slotB = slotA + dj * TCX + di;
+      if (p.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
+        const double* U = sm.u + ((pl + dk) & 3) * 3 * NS + slotB;
+        const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
+        r0 = K[0][0] * u0 + K[0][1] * u1 + K[0][2] * u2;
+        r1 = K[1][0] * u0 + K[1][1] * u1 + K[1][2] * u2;
+        r2 = K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
+      }
+      if (p.J) {
+        // CSR numbering of the node's neighbours: interior nodes have all 27 (column block = direction)
+        int x0 = 0, y0 = 0, z0 = 0, xcnt = 3, ycnt = 3, rs = 81;
+        double nadj = 8.;
+        if (flags) {
+          x0 = flags & 1; y0 = (flags >> 2) & 1; z0 = (flags >> 4) & 1;
+          xcnt = 3 - x0 - ((flags >> 1) & 1); ycnt = 3 - y0 - ((flags >> 3) & 1);
+          const int zcnt = 3 - z0 - ((flags >> 5) & 1);
+          rs = 3 * xcnt * ycnt * zcnt;
+          nadj = double((xcnt - 1) * (ycnt - 1) * (zcnt - 1));
+        }
+        const int c = ((dk + 1 - z0) * ycnt + (dj + 1 - y0)) * xcnt + (di + 1 - x0);
+        if (p.cmask) {
+          const unsigned cmn = sm.cm[(pl & 3) * NSB + slotA], cmm = sm.cm[((pl + dk) & 3) * NSB + slotB];
+          if (cmn | cmm) {  // libMesh constrain_element_matrix_and_vector: row/column zeroed, diagonal 1 per adjacent element
+            const bool self = (di | dj | dk) == 0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                double k = K[i][j];
+                if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
+                if (self && i == j && ((cmn >> i) & 1u)) k = nadj;
+                K[i][j] = k;
+              }
+          }
+        }
+        const int64_t nb0 = p.nbr_ptr[(int64_t)(pl - p.oz0) * plane_nodes + ni.x];
+        double* dst = p.J + 9 * nb0 + 3 * c;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+      }
+    }
+    if (p.R) {
+      // fixed order over the triple: (dx = -1) + (dx = 0), then + (dx = +1); the lead lane keeps the (dy, dz) partial
+      const double a0 = __shfl_down_sync(0xffffffffu, r0, 1), a1 = __shfl_down_sync(0xffffffffu, r1, 1), a2 = __shfl_down_sync(0xffffffffu, r2, 1);
+      const double b0 = __shfl_down_sync(0xffffffffu, r0, 2), b1 = __shfl_down_sync(0xffffffffu, r1, 2), b2 = __shfl_down_sync(0xffffffffu, r2, 2);
+      if (tv && di == -1) {
+        double* fp = sm.fp + (combo * MAXOWN + col) * 3;
+        fp[0] = (r0 + a0) + b0; fp[1] = (r1 + a1) + b1; fp[2] = (r2 + a2) + b2;
+      }
+    }
+  }
+}
+
+template <bool SIMP>
+__global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Sm sm;
+  sm.xyz = reinterpret_cast<double*>(smem_raw + O_XYZ);
+  sm.u = reinterpret_cast<double*>(smem_raw + O_U);
+  sm.stage = reinterpret_cast<double*>(smem_raw + O_STAGE);
+  sm.cm = smem_raw + O_CM;
+  sm.rho = reinterpret_cast<double*>(smem_raw + O_RHO);
+  sm.node = reinterpret_cast<int2*>(smem_raw + O_NODE);
+  sm.fp = reinterpret_cast<double*>(smem_raw + O_FP);
+  sm.carry = reinterpret_cast<double*>(smem_raw + O_CARRY);
+  sm.misc = reinterpret_cast<int*>(smem_raw + O_MISC);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  LaneK lk;
+  make_lane(lane, lk);
+  const unsigned smem32 = (unsigned)__cvta_generic_to_shared(smem_raw);
+  double* my_stage = sm.stage + warp * (4 * 8 * QS);
+  const int bx2 = (warp & 3) * 2, by2 = (warp >> 2) * 2;  // origin of the warp's 2x2 element block
+
+  for (;;) {
+    if (tid == 0) sm.misc[0] = atomicAdd(p.counter, 1);
+    __syncthreads();
+    const int unit = sm.misc[0];
+    if (unit >= p.n_units) break;
+    const StructUnit u = p.units[unit];
+    const int s_begin = u.z0 > 0 ? u.z0 - 1 : 0;
+    const int64_t npx = p.nx + 1, plane_nodes = npx * (p.ny + 1);
+    const int ncx = u.nex + 1, ncols = ncx * (u.ney + 1);
+    const int n_own = u.nox * u.noy;
+    const unsigned inv_own = (65536u + n_own - 1) / n_own;  // tr / n_own == (tr * inv_own) >> 16 for tr < 9 * 49
+    // per-thread constants of the unit: the state item this thread stages every plane
+    const bool ld_on = tid < ncols * 6;
+    int ld_dst = 0;
+    int64_t ld_src = 0;
+    bool ld_u = false;
+    {
+      const int col = tid / 6, c = tid - col * 6;
+      const int ly = col / ncx, lx = col - ly * ncx;
+      const int64_t gid0 = (u.e0x + lx) + (u.e0y + ly) * npx;
+      ld_u = c >= 3;
+      ld_dst = (ld_u ? c - 3 : c) * NS + ly * TCX + lx;
+      ld_src = gid0 * 3 + (ld_u ? c - 3 : c);
+    }
+    const bool cm_on = p.cmask != nullptr && tid < ncols;
+    int cm_dst = 0;
+    int64_t cm_src = 0;
+    {
+      const int ly = tid / ncx, lx = tid - ly * ncx;
+      cm_dst = ly * TCX + lx;
+      cm_src = (u.e0x + lx) + (u.e0y + ly) * npx;
+    }
+    auto load_plane = [&](int z) {  // coordinates, displacements (and density) of node plane z, asynchronously
+      if (SIMP && tid < ncols) {
+        const int ly = tid / ncx, lx = tid - ly * ncx;
+        cp_async8(sm.rho + (z % 3) * NS + ly * TCX + lx, p.rho + (int64_t)z * plane_nodes + (u.e0x + lx) + (u.e0y + ly) * npx);
+      }
+      if (ld_on) {
+        if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * 3 + ld_src);
+        else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
+      }
+    };
+    if (tid < n_own) {
+      const int oyi = tid / u.nox, oxi = tid - oyi * u.nox;
+      const int ax = u.o0x + oxi, ay = u.o0y + oyi;
+      const int flags = (ax == 0 ? 1 : 0) | (ax == p.nx ? 2 : 0) | (ay == 0 ? 4 : 0) | (ay == p.ny ? 8 : 0);
+      sm.node[tid] = make_int2((int)(ax + ay * npx), (ax - u.e0x) | ((ay - u.e0y) << 4) | (flags << 8));
+    }
+    // prologue: node plane s_begin starts from zero (its element plane below is not visited), no force carried in
+    {
+      double* zi = reinterpret_cast<double*>(smem_raw + ((s_begin & 1) ? O_IN1 : O_IN0));
+      for (int i = tid; i < N_IN * NEP; i += ST) zi[i] = 0.;
+      if (tid < MAXOWN * 3) sm.carry[tid] = 0.;
+    }
+    load_plane(s_begin);
+    if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
+    if (cm_on) {
+      sm.cm[(s_begin & 3) * NSB + cm_dst] = p.cmask[(int64_t)s_begin * plane_nodes + cm_src];
+      if (s_begin + 1 <= p.nz) sm.cm[((s_begin + 1) & 3) * NSB + cm_dst] = p.cmask[(int64_t)(s_begin + 1) * plane_nodes + cm_src];
+    }
+    cp_async_wait_all();
+    __syncthreads();
+
+    for (int s = s_begin; s < u.z1; ++s) {
+      unsigned cmv = 0u;
+      if (s + 2 <= p.nz) {  // fetched while this plane is processed
+        load_plane(s + 2);
+        if (cm_on) cmv = p.cmask[(int64_t)(s + 2) * plane_nodes + cm_src];
+      }
+      if (s < p.nz) {
+        // ---- element phase: the warp's 2x2 block of elements of plane s ----
+        {
+          const int el = lane >> 3, q = lane & 7;
+          const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
+          if (lex < u.nex && ley < u.ney) geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+          if (lex < u.nex && ley < u.ney) element_phase(lk, smem32, my_stage + c * 8 * QS, ley * 8 + lex, s & 1, lane);
+        }
+      }
+      __syncthreads();
+      gather_phase(p, sm, smem32, u, s, n_own, inv_own, plane_nodes, warp, lane);
+      if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
+      cp_async_wait_all();
+      __syncthreads();
+      // residual of node plane s: the dz = -1 partials carried from the step before, then (dy, dz) in fixed order
+      if (p.R && tid < 3 * n_own) {
+        const int col = (tid * 21846) >> 16, i = tid - 3 * col;
+        const double* fp = sm.fp + col * 3 + i;
+        constexpr int CS = MAXOWN * 3;
+        double v = sm.carry[tid];
+        v += fp[1 * CS]; v += fp[2 * CS]; v += fp[4 * CS]; v += fp[5 * CS]; v += fp[7 * CS]; v += fp[8 * CS];
+        sm.carry[tid] = (fp[0] + fp[3 * CS]) + fp[6 * CS];
+        if (s >= u.z0) {
+          const int2 ni = sm.node[col];
+          const int slot = ((ni.y >> 4) & 15) * TCX + (ni.y & 15);
+          const unsigned cmn = p.cmask ? sm.cm[(s & 3) * NSB + slot] : 0u;
+          p.R[((int64_t)s * plane_nodes + ni.x) * 3 + i] = ((cmn >> i) & 1u) ? 0. : v;
+        }
+      }
+    }
+  }
+}
+
+}  // namespace
+
+size_t hex8_slots_smem_bytes() { return SMEM_BYTES; }
+int hex8_slots_threads() { return ST; }
+
+cudaError_t launch_hex8_slots(const StructParams& p, int n_ctas, cudaStream_t stream) {
+  if (p.nv != 3 || p.G) return cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
+  if (e != cudaSuccess) return e;
+  static bool attr_set[2][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  auto go = [&](auto kern, int variant) -> cudaError_t {
+    if (dev >= 64 || !attr_set[variant][dev]) {
+      cudaError_t er = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+      if (er != cudaSuccess) return er;
+      if ((er = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return er;
+      if (dev < 64) attr_set[variant][dev] = true;
+    }
+    kern<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
+    return cudaSuccess;
+  };
+  e = p.rho ? go(hex8_slots_kernel<true>, 1) : go(hex8_slots_kernel<false>, 0);
+  if (e != cudaSuccess) return e;
+  return cudaGetLastError();
+}
+
+}  // namespace mastb200

@@ -12,15 +12,21 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-12
 
 
-@pytest.fixture(autouse=True, params=["lockstep", "march"])
+@pytest.fixture(autouse=True, params=["lockstep", "march", "slots"])
 def struct_kernel(request, monkeypatch):
     monkeypatch.setenv("MASTB200_STRUCT_KERNEL", request.param)
     return request.param
 
 
-def _is_struct(ctx, kernel, nv=3):
-    """stats()['structured']: 1 = lock-step kernel, 2 = column march (serves the 3-dof system when opted in)."""
-    return ctx.stats()["structured"] == (2 if kernel == "march" and nv == 3 else 1)
+def _is_struct(ctx, kernel, nv=3, fused=False):
+    """stats()['structured']: 1 = lock-step kernel, 2 = column march, 3 = slot kernel (the last two serve the 3-dof system
+    when opted in; sensitivities fused into the launch stay with the lock-step kernel)."""
+    want = 1
+    if nv == 3 and kernel == "march":
+        want = 2
+    if nv == 3 and kernel == "slots" and not fused:
+        want = 3
+    return ctx.stats()["structured"] == want
 
 
 def _close(a, b, rtol=RTOL):
@@ -142,7 +148,7 @@ def test_struct_simp_modulus_and_fused_sensitivities(built, monkeypatch, struct_
     ctx = prob.make_context(0)
     G = np.full(n, np.nan); R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
     ctx.sensitivity_sweep(X, lam, G, R, J)
-    assert _is_struct(ctx, struct_kernel)
+    assert _is_struct(ctx, struct_kernel, fused=True)
     Ro, Jo = prob.residual_and_jacobian(X)
     _close(R, Ro); _close(J, Jo)
     g_ref = prob.adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
