@@ -39,6 +39,7 @@ constexpr int NS = TCX * TCY;
 constexpr int NSB = (NS + 3) & ~3;
 constexpr int NEP = 65;                // doubles per slot array: 64 element columns + 1 (bank = value id + column)
 constexpr int N_CR = 144, N_IN = 78;   // value arrays: cross pairs 9 x 16; in-plane 3 x 16 (i < j) + 3 x 10 (i == j, unordered)
+constexpr int TRASH_CR = N_CR, TRASH_IN = N_IN;  // one more array per region takes the values a lane holds in duplicate
 constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
 constexpr int MAXOWN = 49;
 constexpr double GP = 0.57735026918962576451;
@@ -46,18 +47,18 @@ constexpr double GP = 0.57735026918962576451;
 // shared-memory carve-up (bytes).  The in-plane regions start 8 doubles (mod 16) after the cross region so that the two
 // kinds of lanes of one store instruction fall into different banks.
 constexpr int O_CR = 0;
-constexpr int CR_BYTES = N_CR * NEP * 8;
-constexpr int IN_BYTES = N_IN * NEP * 8;
-constexpr int O_IN0 = O_CR + CR_BYTES + 64;
-constexpr int O_IN1 = O_IN0 + IN_BYTES + 16;
+constexpr int CR_BYTES = (N_CR + 1) * NEP * 8;
+constexpr int IN_BYTES = (N_IN + 1) * NEP * 8;
+constexpr int O_IN0 = ((O_CR + CR_BYTES + 127) & ~127) + 64;
+constexpr int O_IN1 = ((O_IN0 + IN_BYTES + 127) & ~127) + 64;
 constexpr int O_XYZ = O_IN1 + IN_BYTES;                  // [3 planes][3][NS]
 constexpr int O_U = O_XYZ + 3 * 3 * NS * 8;              // [4 planes][3][NS]
 constexpr int O_STAGE = (O_U + 4 * 3 * NS * 8 + 15) & ~15;   // [SW][4 el][8 qp][QS]
 constexpr int O_CM = O_STAGE + SW * 4 * 8 * QS * 8;      // [4 planes][NSB] uint8
 constexpr int O_RHO = (O_CM + 4 * NSB + 7) & ~7;         // [3 planes][NS]
 constexpr int O_NODE = O_RHO + 3 * NS * 8;               // [64] int2: in-plane node id, lx | ly << 4 | xy boundary flags << 8
-constexpr int O_FP = O_NODE + 64 * 8;                    // [9 (dy, dz)][MAXOWN][3] force partials of a plane's items
-constexpr int O_CARRY = O_FP + 9 * MAXOWN * 3 * 8;       // [MAXOWN][3] dz = -1 partials of the plane above, from the step before
+constexpr int O_FP = O_NODE + 64 * 8;                    // [3 dz][MAXOWN][3] force partials of a plane's items
+constexpr int O_CARRY = O_FP + 3 * MAXOWN * 3 * 8;       // [MAXOWN][3] dz = -1 partials of the plane above, from the step before
 constexpr int O_MISC = O_CARRY + MAXOWN * 3 * 8;
 constexpr int SMEM_BYTES = O_MISC + 16;
 static_assert((O_CR / 8) % 16 == 0 && (O_IN0 / 8) % 16 == 8 && (O_IN1 / 8) % 16 == 8, "bank phases of the slot regions");
@@ -95,13 +96,14 @@ struct Sm {
 // position of the pair (first node a, second node b; xy-local indices 0..3) within a 16-array group: the x bit of b moves
 // by 8, so that the three lanes of a gather triple and the eight lanes of a store quadrant hit distinct banks
 __device__ __forceinline__ int pm(int a, int b) { return (b & 1) * 8 + a * 2 + (b >> 1); }
-// unordered pair a <= b of 0..3 -> 0..9
-__device__ __forceinline__ int up(int a, int b) { return a * 4 - ((a * (a - 1)) >> 1) + (b - a); }
+// unordered pair a <= b of 0..3 -> 0..9, by diagonals: linear in a for a fixed difference (the gather's corners)
+__device__ __forceinline__ int updiag(int d) { return d == 0 ? 0 : (d == 1 ? 4 : (d == 2 ? 7 : 9)); }
+__device__ __forceinline__ int up(int a, int b) { return a + updiag(b - a); }
 
 struct LaneK {
   double d0[2], d1[2], d2;   // reference gradients of N_m at qps q4 (h = 0) and q4 + 4 (h = 1)
-  int off[12];               // BYTE offset of value t = bb * 6 + k within its region (array start; the column is added)
-  unsigned pred;             // bit t: this lane stores C[k][bb]
+  int off[12];               // BYTE offset of value t = bb * 6 + k within its region (array start; the column is added);
+                             // values the lane holds in duplicate go to the region's trash array
   int kind;                  // 0 cross pairs, 1 in-plane pairs of the bottom nodes (added), 2 of the top nodes (stored)
 };
 
@@ -115,7 +117,6 @@ __device__ __forceinline__ void make_lane(int lane, LaneK& lk) {
   lk.d0[0] = 0.125 * sx * fy * fz0; lk.d0[1] = 0.125 * sx * fy * fz1;
   lk.d1[0] = 0.125 * sy * fx * fz0; lk.d1[1] = 0.125 * sy * fx * fz1;
   lk.d2 = 0.125 * sz * fx * fy;
-  lk.pred = 0u;
   const int KI[6] = {0, 1, 2, 0, 0, 1}, KJ[6] = {0, 1, 2, 1, 2, 2};
   const int mz = m >> 2, bz = q4 >> 1, m4 = m & 3;
   lk.kind = mz == bz ? (mz == 0 ? 1 : 2) : 0;
@@ -125,18 +126,15 @@ __device__ __forceinline__ void make_lane(int lane, LaneK& lk) {
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       int idx;
-      bool on = true;
       if (mz == bz) {
         if (k >= 3) idx = (k - 3) * 16 + pm(m4, b4);
-        else { on = m4 <= b4; idx = 48 + k * 10 + up(on ? m4 : b4, on ? b4 : m4); }
+        else idx = m4 <= b4 ? 48 + k * 10 + up(m4, b4) : TRASH_IN;  // S_ii of an unordered pair: the lane (b, m) holds it too
       } else if (mz == 0) {  // bottom m, top b: S_(m,b)[KI][KJ]
         idx = (KI[k] * 3 + KJ[k]) * 16 + pm(m4, b4);
       } else {               // top m, bottom b: C = S_(m,b)[KI][KJ] = S_(b,m)[KJ][KI]; the diagonal components are the other lane's
-        on = k >= 3;
-        idx = (KJ[k] * 3 + KI[k]) * 16 + pm(b4, m4);
+        idx = k >= 3 ? (KJ[k] * 3 + KI[k]) * 16 + pm(b4, m4) : TRASH_CR;
       }
       lk.off[bb * 6 + k] = idx * NEP * 8;
-      if (on) lk.pred |= 1u << (bb * 6 + k);
     }
   }
 }
@@ -209,138 +207,178 @@ __device__ __forceinline__ void element_phase(const LaneK& lk, unsigned smem32, 
     dmma8x8x4(C[5][0], C[5][1], A[1][h], B[2][h]);
   }
   // bottom in-plane pairs join what the element below left for node plane s (region IN[par]); top in-plane pairs open
-  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone
+  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone.  No per-value predicates: duplicates go to
+  // the trash array, the twelve loads of the adding lanes share one predicate.
   const unsigned rb = lk.kind == 0 ? O_CR : (((lk.kind == 1) == (par == 0)) ? O_IN0 : O_IN1);
   const unsigned ar = smem32 + rb + ecol * 8;
   double old[12];
 #pragma unroll
-  for (int t = 0; t < 12; ++t) {
-    old[t] = 0.;
-    if (lk.kind == 1 && ((lk.pred >> t) & 1u)) old[t] = lds64(ar + lk.off[t]);
-  }
+  for (int t = 0; t < 12; ++t) old[t] = 0.;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.eq.s32 q, %12, 1;\n"
+      "@q ld.shared.f64 %0, [%13];\n @q ld.shared.f64 %1, [%14];\n @q ld.shared.f64 %2, [%15];\n @q ld.shared.f64 %3, [%16];\n"
+      "@q ld.shared.f64 %4, [%17];\n @q ld.shared.f64 %5, [%18];\n @q ld.shared.f64 %6, [%19];\n @q ld.shared.f64 %7, [%20];\n"
+      "@q ld.shared.f64 %8, [%21];\n @q ld.shared.f64 %9, [%22];\n @q ld.shared.f64 %10, [%23];\n @q ld.shared.f64 %11, [%24];\n}"
+      : "+d"(old[0]), "+d"(old[1]), "+d"(old[2]), "+d"(old[3]), "+d"(old[4]), "+d"(old[5]), "+d"(old[6]), "+d"(old[7]),
+        "+d"(old[8]), "+d"(old[9]), "+d"(old[10]), "+d"(old[11])
+      : "r"(lk.kind), "r"(ar + lk.off[0]), "r"(ar + lk.off[1]), "r"(ar + lk.off[2]), "r"(ar + lk.off[3]), "r"(ar + lk.off[4]),
+        "r"(ar + lk.off[5]), "r"(ar + lk.off[6]), "r"(ar + lk.off[7]), "r"(ar + lk.off[8]), "r"(ar + lk.off[9]),
+        "r"(ar + lk.off[10]), "r"(ar + lk.off[11])
+      : "memory");
 #pragma unroll
-  for (int t = 0; t < 12; ++t)
-    if ((lk.pred >> t) & 1u) sts64(ar + lk.off[t], old[t] + C[t % 6][t / 6]);
+  for (int t = 0; t < 12; ++t) sts64(ar + lk.off[t], old[t] + C[t % 6][t / 6]);
 }
 
-// ---- gather: item = (owned node column, dy, dz) x three lanes dx = -1, 0, +1 ------------------------------------------
+// ---- gather: warp = (group of ten owned node columns, dz), lane = (node column, dx); the three dy in turn -------------
 // At time s (element plane s just computed): node plane s with dz = 0 (in-plane slots, complete) and dz = +1, node plane
-// s + 1 with dz = -1 (cross slots of element plane s).
-__device__ __forceinline__ void gather_phase(const StructParams& p, const Sm& sm, unsigned smem32, const StructUnit& u, int s,
-                                             int n_own, unsigned inv_own, int64_t plane_nodes, int warp, int lane) {
-  const int l3 = (lane * 11) >> 5;  // lane / 3
-  const int di = lane - 3 * l3 - 1;
-  const int ntr = 9 * n_own;
-  const int par = s & 1;
-  const bool low_on = s >= u.z0;                       // node plane s is flushed by this unit
-  const bool up_on = s + 1 < u.z1 && s < p.nz;         // node plane s + 1 gets its dz = -1 blocks now
-#pragma unroll 1
-  for (int r = 0; r < 3; ++r) {
-    const int tr0 = (r * SW + warp) * 10;
-    if (tr0 >= ntr) break;
-    const int tr = tr0 + l3;
-    const bool tv = lane < 30 && tr < ntr;
-    const int combo = tv ? (int)(((unsigned)tr * inv_own) >> 16) : 0;
-    const int col = tv ? tr - combo * n_own : 0;
-    // (dy, dz) of the combo: the three dy = 0 combos come first (they have twice the element columns)
-    const int dj = combo < 3 ? 0 : (combo < 6 ? -1 : 1);
-    const int dk = (combo < 3 ? combo : (combo < 6 ? combo - 3 : combo - 6)) - 1;
-    const int2 ni = sm.node[col];
-    const int lx = ni.y & 15, ly = (ni.y >> 4) & 15;
-    const int pl = dk < 0 ? s + 1 : s;  // node plane of the item's row
-    const int flags = (ni.y >> 8) | (pl == 0 ? 16 : 0) | (pl == p.nz ? 32 : 0);  // x0, xN, y0, yN, z0, zN
-    const int kill = (di < 0 ? 1 : 0) | (di > 0 ? 2 : 0) | (dj < 0 ? 4 : 0) | (dj > 0 ? 8 : 0) | (dk < 0 ? 16 : 0) | (dk > 0 ? 32 : 0);
-    const bool on = tv && (dk < 0 ? up_on : low_on) && !(flags & kill);
-    double r0 = 0., r1 = 0., r2 = 0.;
-    if (on) {
-      double S[9];
+// s + 1 with dz = -1 (cross slots of element plane s).  (dy, dz) are compile-time, dx is the lane's.  The slot address of
+// a pair is linear in the corner (cx, cy) of the element column relative to the node: one base register per item, the
+// four corners and the components are immediates.
+constexpr int DXC = (-10 * NEP + 1) * 8, DYC = (-5 * NEP + 8) * 8;   // pm-indexed arrays (cross, in-plane i != j)
+constexpr int DXD = (-1 * NEP + 1) * 8, DYD = (-2 * NEP + 8) * 8;    // in-plane i == j (unordered pairs by diagonals)
+constexpr int CST = 16 * NEP * 8, DST = 10 * NEP * 8;                // component strides
+
+struct Item {        // what the three (dy) items of a lane share
+  int lx, ly, xyflags, node, di, killx;
+  bool tv, vx0, vx1;
+  int e00;
+};
+
+template <int DJ, int DK>
+__device__ __forceinline__ void gather_item(const StructParams& p, const Sm& sm, unsigned smem32, const StructUnit& u, int s,
+                                            const Item& it, int64_t plane_nodes, double& f0, double& f1, double& f2) {
+  const int pl = DK < 0 ? s + 1 : s;  // node plane of the item's row
+  const int flags = it.xyflags | (pl == 0 ? 16 : 0) | (pl == p.nz ? 32 : 0);  // x0, xN, y0, yN, z0, zN
+  const int kill = it.killx | (DJ < 0 ? 4 : 0) | (DJ > 0 ? 8 : 0) | (DK < 0 ? 16 : 0) | (DK > 0 ? 32 : 0);
+  if (!it.tv || (flags & kill)) return;
+  const int di = it.di;
+  // element columns (corner cx, cy) that hold the pair: x by the lane's dx, y by dy, both inside the tile
+  const bool vy0 = DJ <= 0 && it.ly >= 1 && it.ly - 1 < u.ney, vy1 = DJ >= 0 && it.ly < u.ney;
+  double S[9];
 #pragma unroll
-      for (int c = 0; c < 9; ++c) S[c] = 0.;
-      const unsigned inb = smem32 + (par ? O_IN1 : O_IN0);
+  for (int c = 0; c < 9; ++c) S[c] = 0.;
+  if (DK == 0) {
+    const unsigned inb = smem32 + ((s & 1) ? O_IN1 : O_IN0) + it.e00 * 8;
+    // corner (0, 0): m4 = 3, b4 = 3 + dx + 2 dy
+    const unsigned pu = inb + ((1 + di) * 8 + 6 + (1 + DJ)) * (NEP * 8);            // S_(A,B)[i][j], i < j
+    const unsigned pl2 = inb + (8 + 2 * (1 + di) + 4 * (1 + DJ) + 1) * (NEP * 8);   // S_(B,A)[i][j], i < j
+    const int dlt = di + 2 * DJ;                                                    // b4 - m4
+    const unsigned pd = inb + (48 + min(3, 3 + dlt) + updiag(dlt < 0 ? -dlt : dlt)) * (NEP * 8);
+#define MASTB200_IN_CORNER(CX, CY)                                                                  \
+    {                                                                                               \
+      const unsigned o = (unsigned)((CX) * DXC + (CY) * DYC), od = (unsigned)((CX) * DXD + (CY) * DYD); \
+      S[1] += lds64(pu + o); S[2] += lds64(pu + o + CST); S[5] += lds64(pu + o + 2 * CST);          \
+      S[3] += lds64(pl2 + o); S[6] += lds64(pl2 + o + CST); S[7] += lds64(pl2 + o + 2 * CST);       \
+      S[0] += lds64(pd + od); S[4] += lds64(pd + od + DST); S[8] += lds64(pd + od + 2 * DST);       \
+    }
+    if (vy0) {
+      if (it.vx0) MASTB200_IN_CORNER(0, 0)
+      if (it.vx1) MASTB200_IN_CORNER(1, 0)
+    }
+    if (vy1) {
+      if (it.vx0) MASTB200_IN_CORNER(0, 1)
+      if (it.vx1) MASTB200_IN_CORNER(1, 1)
+    }
+#undef MASTB200_IN_CORNER
+  } else {
+    // dz = +1: S_(A,B) with A the bottom node; dz = -1: the slot holds S_(B,A) (B bottom), i.e. the transpose
+    const int idx00 = DK > 0 ? (1 + di) * 8 + 6 + (1 + DJ) : 8 + 2 * (1 + di) + 4 * (1 + DJ) + 1;
+    const unsigned a = smem32 + O_CR + (idx00 * NEP + it.e00) * 8;
+#define MASTB200_CR_CORNER(CX, CY)                                                  \
+    {                                                                               \
+      const unsigned o = (unsigned)((CX) * DXC + (CY) * DYC);                       \
+      _Pragma("unroll") for (int c = 0; c < 9; ++c) S[c] += lds64(a + o + c * CST); \
+    }
+    if (vy0) {
+      if (it.vx0) MASTB200_CR_CORNER(0, 0)
+      if (it.vx1) MASTB200_CR_CORNER(1, 0)
+    }
+    if (vy1) {
+      if (it.vx0) MASTB200_CR_CORNER(0, 1)
+      if (it.vx1) MASTB200_CR_CORNER(1, 1)
+    }
+#undef MASTB200_CR_CORNER
+  }
+  // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
+  const double l1 = DK < 0 ? p.mu1 : p.lam1, l2 = DK < 0 ? p.lam1 : p.mu1;
+  const double trm = p.mu1 * (S[0] + S[4] + S[8]);
+  double K[3][3];
 #pragma unroll
-      for (int cy = 0; cy < 2; ++cy) {
-        const int my = 1 - cy, by = my + dj, ley = ly - 1 + cy;
-        if ((unsigned)by > 1u || (unsigned)ley >= (unsigned)u.ney) continue;
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
-        for (int cx = 0; cx < 2; ++cx) {
-          const int mx = 1 - cx, bx = mx + di, lex = lx - 1 + cx;
-          if ((unsigned)bx > 1u || (unsigned)lex >= (unsigned)u.nex) continue;
-          const int m4 = mx + 2 * my, b4 = bx + 2 * by, e = ley * 8 + lex;
-          if (dk == 0) {
-            const unsigned a = inb + e * 8;
-            const unsigned pu = a + pm(m4, b4) * (NEP * 8), pl2 = a + pm(b4, m4) * (NEP * 8);
-            const unsigned pd = a + (48 + up(min(m4, b4), max(m4, b4))) * (NEP * 8);
-            S[1] += lds64(pu); S[2] += lds64(pu + 16 * NEP * 8); S[5] += lds64(pu + 32 * NEP * 8);
-            S[3] += lds64(pl2); S[6] += lds64(pl2 + 16 * NEP * 8); S[7] += lds64(pl2 + 32 * NEP * 8);
-            S[0] += lds64(pd); S[4] += lds64(pd + 10 * NEP * 8); S[8] += lds64(pd + 20 * NEP * 8);
-          } else {
-            // dz = +1: S_(A,B) with A the bottom node; dz = -1: the slot holds S_(B,A) (B bottom), i.e. the transpose
-            const unsigned a = smem32 + O_CR + ((dk > 0 ? pm(m4, b4) : pm(b4, m4)) * NEP + e) * 8;
-#pragma unroll
-            for (int c = 0; c < 9; ++c) S[c] += lds64(a + c * (16 * NEP * 8));
-          }
-        }
-      }
-      // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
-      const bool tr_ = dk < 0;
-      const double l1 = tr_ ? p.mu1 : p.lam1, l2 = tr_ ? p.lam1 : p.mu1;
-      const double trm = p.mu1 * (S[0] + S[4] + S[8]);
-      double K[3][3];
-#pragma unroll
-      for (int i = 0; i < 3; ++i)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i * 3 + j] + l2 * S[j * 3 + i] + (i == j ? trm : 0.);
-      const int slotA = ly * TCX + lx, slotB = slotA + dj * TCX + di;
-      if (p.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
-        const double* U = sm.u + ((pl + dk) & 3) * 3 * NS + slotB;
-        const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
-        r0 = K[0][0] * u0 + K[0][1] * u1 + K[0][2] * u2;
-        r1 = K[1][0] * u0 + K[1][1] * u1 + K[1][2] * u2;
-        r2 = K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
-      }
-      if (p.J) {
-        // CSR numbering of the node's neighbours: interior nodes have all 27 (column block = direction)
-        int x0 = 0, y0 = 0, z0 = 0, xcnt = 3, ycnt = 3, rs = 81;
-        double nadj = 8.;
-        if (flags) {
-          x0 = flags & 1; y0 = (flags >> 2) & 1; z0 = (flags >> 4) & 1;
-          xcnt = 3 - x0 - ((flags >> 1) & 1); ycnt = 3 - y0 - ((flags >> 3) & 1);
-          const int zcnt = 3 - z0 - ((flags >> 5) & 1);
-          rs = 3 * xcnt * ycnt * zcnt;
-          nadj = double((xcnt - 1) * (ycnt - 1) * (zcnt - 1));
-        }
-        const int c = ((dk + 1 - z0) * ycnt + (dj + 1 - y0)) * xcnt + (di + 1 - x0);
-        if (p.cmask) {
-          const unsigned cmn = sm.cm[(pl & 3) * NSB + slotA], cmm = sm.cm[((pl + dk) & 3) * NSB + slotB];
-          if (cmn | cmm) {  // libMesh constrain_element_matrix_and_vector: row/column zeroed, diagonal 1 per adjacent element
-            const bool self = (di | dj | dk) == 0;
-#pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-              for (int j = 0; j < 3; ++j) {
-                double k = K[i][j];
-                if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
-                if (self && i == j && ((cmn >> i) & 1u)) k = nadj;
-                K[i][j] = k;
-              }
-          }
-        }
-        const int64_t nb0 = p.nbr_ptr[(int64_t)(pl - p.oz0) * plane_nodes + ni.x];
-        double* dst = p.J + 9 * nb0 + 3 * c;
+    for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i * 3 + j] + l2 * S[j * 3 + i] + (i == j ? trm : 0.);
+  const int slotA = it.ly * TCX + it.lx, slotB = slotA + DJ * TCX + di;
+  if (p.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
+    const double* U = sm.u + ((pl + DK) & 3) * 3 * NS + slotB;
+    const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
+    f0 += K[0][0] * u0 + K[0][1] * u1 + K[0][2] * u2;
+    f1 += K[1][0] * u0 + K[1][1] * u1 + K[1][2] * u2;
+    f2 += K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
+  }
+  if (p.J) {
+    // CSR numbering of the node's neighbours: interior nodes have all 27 (column block = direction)
+    int c = (DK + 1) * 9 + (DJ + 1) * 3 + di + 1, rs = 81;
+    double nadj = 8.;
+    if (flags) {
+      const int x0 = flags & 1, y0 = (flags >> 2) & 1, z0 = (flags >> 4) & 1;
+      const int xcnt = 3 - x0 - ((flags >> 1) & 1), ycnt = 3 - y0 - ((flags >> 3) & 1);
+      const int zcnt = 3 - z0 - ((flags >> 5) & 1);
+      rs = 3 * xcnt * ycnt * zcnt;
+      nadj = double((xcnt - 1) * (ycnt - 1) * (zcnt - 1));
+      c = ((DK + 1 - z0) * ycnt + (DJ + 1 - y0)) * xcnt + (di + 1 - x0);
+    }
+    if (p.cmask) {
+      const unsigned cmn = sm.cm[(pl & 3) * NSB + slotA], cmm = sm.cm[((pl + DK) & 3) * NSB + slotB];
+      if (cmn | cmm) {  // libMesh constrain_element_matrix_and_vector: row/column zeroed, diagonal 1 per adjacent element
+        const bool self = DJ == 0 && DK == 0 && di == 0;
 #pragma unroll
         for (int i = 0; i < 3; ++i)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+          for (int j = 0; j < 3; ++j) {
+            double k = K[i][j];
+            if (((cmn >> i) | (cmm >> j)) & 1u) k = 0.;
+            if (self && i == j && ((cmn >> i) & 1u)) k = nadj;
+            K[i][j] = k;
+          }
       }
     }
-    if (p.R) {
-      // fixed order over the triple: (dx = -1) + (dx = 0), then + (dx = +1); the lead lane keeps the (dy, dz) partial
-      const double a0 = __shfl_down_sync(0xffffffffu, r0, 1), a1 = __shfl_down_sync(0xffffffffu, r1, 1), a2 = __shfl_down_sync(0xffffffffu, r2, 1);
-      const double b0 = __shfl_down_sync(0xffffffffu, r0, 2), b1 = __shfl_down_sync(0xffffffffu, r1, 2), b2 = __shfl_down_sync(0xffffffffu, r2, 2);
-      if (tv && di == -1) {
-        double* fp = sm.fp + (combo * MAXOWN + col) * 3;
-        fp[0] = (r0 + a0) + b0; fp[1] = (r1 + a1) + b1; fp[2] = (r2 + a2) + b2;
-      }
+    const int64_t nb0 = p.nbr_ptr[(int64_t)(pl - p.oz0) * plane_nodes + it.node];
+    double* dst = p.J + 9 * nb0 + 3 * c;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+  }
+}
+
+template <int DK>
+__device__ __forceinline__ void gather_dz(const StructParams& p, const Sm& sm, unsigned smem32, const StructUnit& u, int s,
+                                          int n_own, int group, int64_t plane_nodes, int lane) {
+  const int l3 = (lane * 11) >> 5;  // lane / 3
+  Item it;
+  it.di = lane - 3 * l3 - 1;
+  it.killx = it.di < 0 ? 1 : (it.di > 0 ? 2 : 0);
+  const int col = group * 10 + l3;
+  // node plane s is flushed by this unit from z0 on; node plane s + 1 gets its dz = -1 blocks if the unit owns it
+  const bool plane_on = DK < 0 ? (s + 1 < u.z1 && s < p.nz) : s >= u.z0;
+  it.tv = lane < 30 && col < n_own && plane_on;
+  const int2 ni = sm.node[col < n_own ? col : 0];
+  it.node = ni.x;
+  it.lx = ni.y & 15; it.ly = (ni.y >> 4) & 15; it.xyflags = ni.y >> 8;
+  it.vx0 = it.di <= 0 && it.lx >= 1 && it.lx - 1 < u.nex;
+  it.vx1 = it.di >= 0 && it.lx < u.nex;
+  it.e00 = (it.ly - 1) * 8 + it.lx - 1;
+  double f0 = 0., f1 = 0., f2 = 0.;
+  gather_item<0, DK>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
+  gather_item<-1, DK>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
+  gather_item<1, DK>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
+  if (p.R) {
+    // fixed order over the triple: (dx = -1) + (dx = 0), then + (dx = +1); the lead lane keeps the dz partial of the node
+    const double a0 = __shfl_down_sync(0xffffffffu, f0, 1), a1 = __shfl_down_sync(0xffffffffu, f1, 1), a2 = __shfl_down_sync(0xffffffffu, f2, 1);
+    const double b0 = __shfl_down_sync(0xffffffffu, f0, 2), b1 = __shfl_down_sync(0xffffffffu, f1, 2), b2 = __shfl_down_sync(0xffffffffu, f2, 2);
+    if (lane < 30 && col < n_own && it.di == -1) {
+      double* fp = sm.fp + ((DK + 1) * MAXOWN + col) * 3;
+      fp[0] = (f0 + a0) + b0; fp[1] = (f1 + a1) + b1; fp[2] = (f2 + a2) + b2;
     }
   }
 }
@@ -373,35 +411,33 @@ __global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p)
     const StructUnit u = p.units[unit];
     const int s_begin = u.z0 > 0 ? u.z0 - 1 : 0;
     const int64_t npx = p.nx + 1, plane_nodes = npx * (p.ny + 1);
-    const int ncx = u.nex + 1, ncols = ncx * (u.ney + 1);
+    const int ncx = u.nex + 1;
     const int n_own = u.nox * u.noy;
-    const unsigned inv_own = (65536u + n_own - 1) / n_own;  // tr / n_own == (tr * inv_own) >> 16 for tr < 9 * 49
-    // per-thread constants of the unit: the state item this thread stages every plane
-    const bool ld_on = tid < ncols * 6;
-    int ld_dst = 0;
-    int64_t ld_src = 0;
-    bool ld_u = false;
+    // per-thread constants of the unit: the state item this thread stages every plane.  The thread -> (node column,
+    // component) map is the tile's fixed 9 x 9 shape (constant divisors), so recomputing it per plane costs nothing.
+    bool ld_on, ld_u;
+    int ld_dst;
+    int64_t ld_src;
     {
       const int col = tid / 6, c = tid - col * 6;
-      const int ly = col / ncx, lx = col - ly * ncx;
+      const int ly = col / TCX, lx = col - ly * TCX;
+      ld_on = col < NS && lx < ncx && ly <= u.ney;
       const int64_t gid0 = (u.e0x + lx) + (u.e0y + ly) * npx;
       ld_u = c >= 3;
-      ld_dst = (ld_u ? c - 3 : c) * NS + ly * TCX + lx;
+      ld_dst = (ld_u ? c - 3 : c) * NS + col;
       ld_src = gid0 * 3 + (ld_u ? c - 3 : c);
     }
-    const bool cm_on = p.cmask != nullptr && tid < ncols;
-    int cm_dst = 0;
-    int64_t cm_src = 0;
+    bool cm_on;
+    int64_t cm_src;
+    const int cm_dst = tid;
     {
-      const int ly = tid / ncx, lx = tid - ly * ncx;
-      cm_dst = ly * TCX + lx;
+      const int ly = tid / TCX, lx = tid - ly * TCX;
+      cm_on = tid < NS && lx < ncx && ly <= u.ney;
       cm_src = (u.e0x + lx) + (u.e0y + ly) * npx;
     }
+    const bool cmk_on = cm_on && p.cmask != nullptr;
     auto load_plane = [&](int z) {  // coordinates, displacements (and density) of node plane z, asynchronously
-      if (SIMP && tid < ncols) {
-        const int ly = tid / ncx, lx = tid - ly * ncx;
-        cp_async8(sm.rho + (z % 3) * NS + ly * TCX + lx, p.rho + (int64_t)z * plane_nodes + (u.e0x + lx) + (u.e0y + ly) * npx);
-      }
+      if (SIMP && cm_on) cp_async8(sm.rho + (z % 3) * NS + cm_dst, p.rho + (int64_t)z * plane_nodes + cm_src);
       if (ld_on) {
         if (ld_u) cp_async8(sm.u + (z & 3) * 3 * NS + ld_dst, p.X + (int64_t)z * plane_nodes * 3 + ld_src);
         else cp_async8(sm.xyz + (z % 3) * 3 * NS + ld_dst, p.xyz + (int64_t)z * plane_nodes * 3 + ld_src);
@@ -421,7 +457,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p)
     }
     load_plane(s_begin);
     if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
-    if (cm_on) {
+    if (cmk_on) {
       sm.cm[(s_begin & 3) * NSB + cm_dst] = p.cmask[(int64_t)s_begin * plane_nodes + cm_src];
       if (s_begin + 1 <= p.nz) sm.cm[((s_begin + 1) & 3) * NSB + cm_dst] = p.cmask[(int64_t)(s_begin + 1) * plane_nodes + cm_src];
     }
@@ -432,7 +468,7 @@ __global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p)
       unsigned cmv = 0u;
       if (s + 2 <= p.nz) {  // fetched while this plane is processed
         load_plane(s + 2);
-        if (cm_on) cmv = p.cmask[(int64_t)(s + 2) * plane_nodes + cm_src];
+        if (cmk_on) cmv = p.cmask[(int64_t)(s + 2) * plane_nodes + cm_src];
       }
       if (s < p.nz) {
         // ---- element phase: the warp's 2x2 block of elements of plane s ----
@@ -449,18 +485,25 @@ __global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p)
         }
       }
       __syncthreads();
-      gather_phase(p, sm, smem32, u, s, n_own, inv_own, plane_nodes, warp, lane);
-      if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
+      if (warp < 15) {  // warp = (group of ten owned node columns, dz)
+        const int group = warp % 5, dzi = warp / 5;
+        if (group * 10 < n_own) {
+          if (dzi == 0) gather_dz<-1>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
+          else if (dzi == 1) gather_dz<0>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
+          else gather_dz<1>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
+        }
+      }
+      if (cmk_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
       cp_async_wait_all();
       __syncthreads();
-      // residual of node plane s: the dz = -1 partials carried from the step before, then (dy, dz) in fixed order
+      // residual of node plane s: the dz = -1 partial carried from the step before, then dz = 0, +1
       if (p.R && tid < 3 * n_own) {
         const int col = (tid * 21846) >> 16, i = tid - 3 * col;
         const double* fp = sm.fp + col * 3 + i;
         constexpr int CS = MAXOWN * 3;
         double v = sm.carry[tid];
-        v += fp[1 * CS]; v += fp[2 * CS]; v += fp[4 * CS]; v += fp[5 * CS]; v += fp[7 * CS]; v += fp[8 * CS];
-        sm.carry[tid] = (fp[0] + fp[3 * CS]) + fp[6 * CS];
+        v += fp[1 * CS]; v += fp[2 * CS];
+        sm.carry[tid] = fp[0];
         if (s >= u.z0) {
           const int2 ni = sm.node[col];
           const int slot = ((ni.y >> 4) & 15) * TCX + (ni.y & 15);
