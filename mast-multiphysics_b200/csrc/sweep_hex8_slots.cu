@@ -239,7 +239,8 @@ constexpr int DXD = (-1 * NEP + 1) * 8, DYD = (-2 * NEP + 8) * 8;    // in-plane
 constexpr int CST = 16 * NEP * 8, DST = 10 * NEP * 8;                // component strides
 
 struct Item {        // what the three (dy) items of a lane share
-  int lx, ly, xyflags, node, di, killx;
+  int lx, ly, xyflags, di, killx;
+  int64_t nb0;        // CSR row pointer (in node blocks) of the item's node, fetched before the first item needs it
   bool tv, vx0, vx1;
   int e00;
 };
@@ -342,8 +343,7 @@ __device__ __forceinline__ void gather_item(const StructParams& p, const Sm& sm,
           }
       }
     }
-    const int64_t nb0 = p.nbr_ptr[(int64_t)(pl - p.oz0) * plane_nodes + it.node];
-    double* dst = p.J + 9 * nb0 + 3 * c;
+    double* dst = p.J + 9 * it.nb0 + 3 * c;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
@@ -363,7 +363,7 @@ __device__ __forceinline__ void gather_dz(const StructParams& p, const Sm& sm, u
   const bool plane_on = DK < 0 ? (s + 1 < u.z1 && s < p.nz) : s >= u.z0;
   it.tv = lane < 30 && col < n_own && plane_on;
   const int2 ni = sm.node[col < n_own ? col : 0];
-  it.node = ni.x;
+  it.nb0 = it.tv && p.J ? p.nbr_ptr[(int64_t)((DK < 0 ? s + 1 : s) - p.oz0) * plane_nodes + ni.x] : 0;
   it.lx = ni.y & 15; it.ly = (ni.y >> 4) & 15; it.xyflags = ni.y >> 8;
   it.vx0 = it.di <= 0 && it.lx >= 1 && it.lx - 1 < u.nex;
   it.vx1 = it.di >= 0 && it.lx < u.nex;
