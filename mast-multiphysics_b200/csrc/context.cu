@@ -211,6 +211,14 @@ int ensure_generic_plan(mastb200_context* ctx) {
       if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
       e = build_posmap(P, ctx->conn.data(), posmap);
       if (!e.empty()) return ctx->fail(MASTB200_ERR_PLAN, "plan: %s", e.c_str());
+      // MASTB200_H27_FIRST_WRITER=1 (experiment): the colour launches run in colour order, so the first colour to touch a CSR
+      // block can store and the later ones add -- no memset of J, no read of 70 % of its values.  Measured neutral on B200
+      // (C5: 197.0 ms against 188.9 + 10.1 ms of memset): a 24-byte store into a 32-byte sector costs the L2 the same fill as
+      // the read-modify-write did (profiles/r02e_hex27_first_writer.md), so it stays off by default.
+      const char* fwe = getenv("MASTB200_H27_FIRST_WRITER");
+      G.first_writer = (fwe && fwe[0] == '1') &&
+                       flag_first_writers(P, ctx->conn.data(), ctx->diag_elem.empty() ? nullptr : ctx->diag_elem.data(),
+                                          G.color_ptr, color_elems, true, posmap);
     } else {
       std::vector<int32_t> order, pred_ptr, pred;
       bool fw = false;
@@ -367,7 +375,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
   } else {
     // the scatter accumulates: R and J start from zero (nonlinear_implicit_assembly.cpp:81-82) -- except that the ordered
     // sweep of the 3-dof system stores the first contribution to every CSR block, so J needs no memset there
-    const bool fw = G.ordered && G.first_writer && ctx->nv == 3;
+    const bool fw = G.first_writer && ctx->nv == 3;
     if (dR) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
     if (dJ && !fw) CU(cudaMemsetAsync(dJ, 0, nnz * sizeof(double), ctx->stream));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
@@ -398,6 +406,8 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
       ctx->launches++;
     } else {
       const int nc = (int)G.color_ptr.size() - 1;
+      p.first_writer = fw ? 1 : 0;
+      p.pos_flagged = G.first_writer ? 1 : 0;
       for (int c = 0; c < nc; ++c) {
         p.elems = G.color_elems.p + G.color_ptr[c];
         p.n_elems = G.color_ptr[c + 1] - G.color_ptr[c];

@@ -761,6 +761,48 @@ std::string build_posmap(const Pattern& pat, const int32_t* conn, std::vector<ui
 // scheduling) and is deadlock-free for CTAs that take the list round-robin, each in increasing position.
 // first_flag[(e, a, b)]: this element is the first in the order to touch block (a, b) of its row -> it stores, the later
 // ones add, and J needs no memset.
+// Sets bit 7 of the position-map entry of the FIRST element (in the order given: group by group, elements of a group in
+// any order) that touches each CSR block, so that a scatter in that order can store the first contribution instead of adding
+// to a cleared value.  Needs < 128 neighbours per row and no diagonal elements; returns false (map untouched) otherwise.
+// With parallel_groups the elements of a group are known not to share nodes (colours): they are flagged concurrently.
+bool flag_first_writers(const Pattern& pat, const int32_t* conn, const uint8_t* diag_elem, const std::vector<int32_t>& group_ptr,
+                        const std::vector<int32_t>& elems, bool parallel_groups, std::vector<uint8_t>& posmap) {
+  const int nn = pat.nn;
+  for (int64_t r = 0; r < pat.n_owned; ++r)
+    if (pat.nbr_ptr[r + 1] - pat.nbr_ptr[r] > 127) return false;
+  if (diag_elem)
+    for (int64_t e = 0; e < pat.n_elem; ++e)
+      if (diag_elem[e]) return false;
+  std::vector<uint64_t> seen(((size_t)pat.nbr_ptr[pat.n_owned] + 63) / 64, 0);
+  auto flag = [&](int64_t e) {
+    const int32_t* c = conn + e * nn;
+    for (int a = 0; a < nn; ++a) {
+      const int32_t r = pat.node_row[c[a]];
+      if (r < 0) continue;
+      for (int b = 0; b < nn; ++b) {
+        uint8_t& pm = posmap[((size_t)e * nn + a) * nn + b];
+        const size_t blk = (size_t)pat.nbr_ptr[r] + pm;
+        const uint64_t bit = uint64_t(1) << (blk & 63);
+        // elements of one group touch disjoint blocks, but their blocks may share a word of the bitmap
+        const uint64_t old = __atomic_fetch_or(&seen[blk >> 6], bit, __ATOMIC_RELAXED);
+        if (!(old & bit)) pm |= 0x80;
+      }
+    }
+  };
+  for (size_t g = 0; g + 1 < group_ptr.size(); ++g) {
+    const int64_t g0 = group_ptr[g], g1 = group_ptr[g + 1];
+    if (parallel_groups) {
+      parallel_for(g1 - g0, [&](int64_t b0, int64_t e0, int) {
+        for (int64_t k = b0; k < e0; ++k) flag(elems[g0 + k]);
+      });
+    } else {
+      for (int64_t k = g0; k < g1; ++k) flag(elems[k]);
+    }
+  }
+  // every block of an owned row is touched by some element (the pattern comes from the elements), so no value stays unset
+  return true;
+}
+
 std::string build_ordered_scatter(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
                                   int brick_elems, std::vector<int32_t>& order, std::vector<int32_t>& pred_ptr,
                                   std::vector<int32_t>& pred, std::vector<uint8_t>& posmap, bool& first_writer) {
@@ -842,29 +884,8 @@ std::string build_ordered_scatter(const Pattern& pat, const double* xyz, const i
   // position map, with the first-writer flag in bit 7 when every row has < 128 neighbours and there are no diagonal elements
   err = build_posmap(pat, conn, posmap);
   if (!err.empty()) return err;
-  first_writer = true;
-  for (int64_t r = 0; r < pat.n_owned && first_writer; ++r)
-    if (pat.nbr_ptr[r + 1] - pat.nbr_ptr[r] > 127) first_writer = false;
-  if (diag_elem)
-    for (int64_t e = 0; e < ne && first_writer; ++e)
-      if (diag_elem[e]) first_writer = false;
-  if (first_writer) {
-    std::vector<uint64_t> seen(((size_t)pat.nbr_ptr[pat.n_owned] + 63) / 64, 0);
-    for (size_t k = 0; k < order.size(); ++k) {
-      const int64_t e = order[k];
-      const int32_t* c = conn + e * nn;
-      for (int a = 0; a < nn; ++a) {
-        const int32_t r = pat.node_row[c[a]];
-        if (r < 0) continue;
-        for (int b = 0; b < nn; ++b) {
-          uint8_t& pm = posmap[((size_t)e * nn + a) * nn + b];
-          const size_t blk = (size_t)pat.nbr_ptr[r] + pm;
-          if (!((seen[blk >> 6] >> (blk & 63)) & 1u)) { seen[blk >> 6] |= uint64_t(1) << (blk & 63); pm |= 0x80; }
-        }
-      }
-    }
-    // every block of an owned row is touched by some element (the pattern comes from the elements), so no value stays unset
-  }
+  std::vector<int32_t> one_group = {0, (int32_t)order.size()};
+  first_writer = flag_first_writers(pat, conn, diag_elem, one_group, order, /*parallel_groups=*/false, posmap);
   return "";
 }
 

@@ -141,6 +141,9 @@ std::string build_coloring(const Pattern& pat, const int32_t* conn, std::vector<
 // (0 for unowned a).  One byte per node pair; fails if a row has more than 255 neighbours.
 std::string build_posmap(const Pattern& pat, const int32_t* conn, std::vector<uint8_t>& posmap);
 // processing order, predecessor lists and position map (bit 7: first writer of the block) of the single-launch scatter
+// first-writer flags (bit 7 of the position map) for a scatter that runs group by group in the given order
+bool flag_first_writers(const Pattern& pat, const int32_t* conn, const uint8_t* diag_elem, const std::vector<int32_t>& group_ptr,
+                        const std::vector<int32_t>& elems, bool parallel_groups, std::vector<uint8_t>& posmap);
 std::string build_ordered_scatter(const Pattern& pat, const double* xyz, const int32_t* conn, const uint8_t* diag_elem,
                                   int brick_elems, std::vector<int32_t>& order, std::vector<int32_t>& pred_ptr,
                                   std::vector<int32_t>& pred, std::vector<uint8_t>& posmap, bool& first_writer);
