@@ -333,14 +333,14 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
 }
 
 // QUAD4 heat conduction (row gather) and HEX27 elasticity (coloured DMMA scatter)
+int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J);
 int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
   int rc;
   const bool heat = ctx->elem_type == MASTB200_QUAD4;
   if (heat && ctx->nv == 6) return run_plate_sweep(ctx, X, R, J);
   if (heat && ctx->nv != 1) return ctx->fail(MASTB200_ERR_ARG, "QUAD4: nv = 1 (heat conduction) or 6 (Mindlin plate)");
   if (!heat && ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX27 elasticity needs nv = 3 or 6");
-  if (!heat && ctx->mat.nonlinear_strain)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "Green-Lagrange strain: HEX8 only on the device path");
+  if (!heat && ctx->mat.nonlinear_strain) return run_hex8_gather(ctx, X, R, J);  // HEX27, Green-Lagrange: row-owner gather
   if (heat) detect_quad4_struct(ctx);
   const bool q4s = heat && ctx->q4s_ok;
   ctx->last_q4s = q4s;
@@ -596,9 +596,15 @@ int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J
   if ((rc = ensure_generic_plan(ctx))) return rc;
   mastb200_context::GenericPlan& G = ctx->gplan;
   const Pattern& P = ctx->pat;
+  const bool h27 = ctx->elem_type == MASTB200_HEX27;
+  const int max_nbr = h27 ? 128 : 32;  // one 3x3 block per lane (HEX8), four per lane (HEX27: a vertex node has 125)
   for (int64_t r = 0; r < P.n_owned; ++r)
-    if (P.nbr_ptr[r + 1] - P.nbr_ptr[r] > 32)
-      return ctx->fail(MASTB200_ERR_PLAN, "plan: a node has more than 32 neighbours (gather sweep)");
+    if (P.nbr_ptr[r + 1] - P.nbr_ptr[r] > max_nbr)
+      return ctx->fail(MASTB200_ERR_PLAN, "plan: a node has more than %d neighbours (gather sweep)", max_nbr);
+  if (h27 && !G.nbr.p) {  // the HEX27 plan keeps the column list on the host until the gather sweep asks for it
+    CU(G.nbr.upload(P.nbr, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
   const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
   const size_t nnz = (size_t)plan_nnz(ctx);
   const double* dX = nullptr;
@@ -626,7 +632,9 @@ int run_hex8_gather(mastb200_context* ctx, const double* X, double* R, double* J
   p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
   p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
   p.nv = ctx->nv; p.thermal = ctx->thermal ? 1 : 0; p.nonlinear = m.nonlinear_strain ? 1 : 0;
-  CU(launch_hex8_gather(p, ctx->stream));
+  p.tab = G.tab.p;
+  if (h27) CU(launch_hex27_gather(p, ctx->stream));
+  else CU(launch_hex8_gather(p, ctx->stream));
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   if ((rc = apply_external_loads(ctx, dR, p.cmask))) return rc;

@@ -169,7 +169,8 @@ struct SolidGatherParams {
   const int32_t* nbr = nullptr;
   const int64_t* n2e_ptr = nullptr;
   const int32_t* n2e = nullptr;
-  const int32_t* conn = nullptr;         // [n_elem][8]
+  const int32_t* conn = nullptr;         // [n_elem][8] (HEX27: [n_elem][27])
+  const double* tab = nullptr;           // HEX27: N[27][27], dN[27][27][3], w[27]
   const uint8_t* diag_elem = nullptr;
   const uint8_t* cmask = nullptr;
   const double* xyz = nullptr;
@@ -182,6 +183,7 @@ struct SolidGatherParams {
   int32_t nv = 3, thermal = 0, nonlinear = 0;
 };
 cudaError_t launch_hex8_gather(const SolidGatherParams& p, cudaStream_t stream);
+cudaError_t launch_hex27_gather(const SolidGatherParams& p, cudaStream_t stream);  // sweep_hex27_gather.cu (<= 128 neighbours per row)
 
 // ---- stress output: per-qp stress/strain/von Mises, p-norm aggregate and its state derivative (stress_output.cu) ----
 struct StressParams {

@@ -371,6 +371,32 @@ def test_hex8_green_lagrange_thermal_simp_diag_unstructured(built):
     _check_RJ(prob2, O.state(prob2.n_dof, 1, scale=2e-3))
 
 
+# ---- Green-Lagrange strain on HEX27 (row-owner gather, sweep_hex27_gather.cu) ---------------------------------------------
+@pytest.mark.parametrize("nv", [3, 6])
+def test_hex27_green_lagrange_residual_and_jacobian(built, nv):
+    # StructuralElement3D::internal_residual with NONLINEAR_STRAIN on the tri-quadratic element (solid_element_3d.cpp:299-409)
+    prob = _hex27_problem(4, 3, 2, nv=nv, jitter=0.1, nonlinear_strain=1)
+    X = O.state(prob.n_dof, 1, scale=2e-3)
+    ctx, R, J = _check_RJ(prob, X)
+    lin = _hex27_problem(4, 3, 2, nv=nv, jitter=0.1)
+    _, Jl = lin.residual_and_jacobian(X, want_R=False)
+    assert np.abs(J - Jl).max() > 1e-3 * np.abs(Jl).max()  # the nonlinear terms matter at this state
+    _check_RJ(prob, X, want_R=False)
+    _check_RJ(prob, X, want_J=False)
+
+
+def test_hex27_green_lagrange_thermal_simp_diag(built):
+    # thermoelastic load with its geometric term (solid_element_3d.cpp:1039-1084), SIMP modulus, diagonal elements
+    nx, ny, nz = 3, 3, 2
+    n_nodes = (2 * nx + 1) * (2 * ny + 1) * (2 * nz + 1)
+    rng = np.random.default_rng(5)
+    diag = np.zeros(nx * ny * nz, np.uint8); diag[[2, 7]] = 1
+    prob = _hex27_problem(nx, ny, nz, jitter=0.1, nonlinear_strain=1, alpha=1.5e-5, thermal=1,
+                          temperature=_temperature(n_nodes), ref_temperature=300.0,
+                          rho=0.2 + 0.6 * rng.uniform(size=n_nodes), rho_min=1e-8, penalty=4.0, diag_elem=diag)
+    _check_RJ(prob, O.state(prob.n_dof, 1, scale=2e-3))
+
+
 # ---- stress output (StressStrainOutputBase) ------------------------------------------------------------------------
 def _stress_case(prob, X, p_norm=2.0, rho_exp=0.0, sigma0=None):
     ctx = prob.make_context(0)
