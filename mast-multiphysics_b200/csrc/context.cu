@@ -689,8 +689,6 @@ int upload_elem_mask(mastb200_context* ctx, const uint8_t* elem_mask, const uint
 int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, double* G) {
   int rc;
   if (!ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
-  if (ctx->mat.nonlinear_strain)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities with Green-Lagrange strain are not on the device path");
   if (ctx->thermal)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED,
                      "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
@@ -760,9 +758,14 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     return MASTB200_OK;
   }
   if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX8 elasticity needs nv = 3 or 6");
-  if (ctx->mat.nonlinear_strain) {
-    if (G) return ctx->fail(MASTB200_ERR_UNSUPPORTED, "density sensitivities with Green-Lagrange strain are not on the device path");
-    return run_hex8_gather(ctx, X, R, J);
+  if (ctx->mat.nonlinear_strain) {  // Green-Lagrange strain: R / J by the row-owner gather, G by the element-parallel kernels
+    if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
+    if ((R || J) && (rc = run_hex8_gather(ctx, X, R, J))) return rc;
+    if (!G) return MASTB200_OK;
+    const double* last_R = ctx->last_R;
+    rc = run_density_sens(ctx, X, adj, G);
+    if (R || J) ctx->last_R = last_R;
+    return rc;
   }
   if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
   {  // sensitivities alone: element-parallel kernels instead of the streaming sweep (MASTB200_SENS_SWEEP=1: old path)

@@ -422,10 +422,26 @@ __global__ void __launch_bounds__(128) sens_qp_kernel(const StressParams p, cons
     }
     rho = fma(Nt[b], p.rho[n], rho);
   }
-  const double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
-  const double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
-  const double a0 = A[0][0], a1 = A[1][1], a2 = A[2][2];
-  const double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
+  double e0 = H[0][0], e1 = H[1][1], e2 = H[2][2];
+  double e3 = H[0][1] + H[1][0], e4 = H[1][2] + H[2][1], e5 = H[0][2] + H[2][0];
+  double a0 = A[0][0], a1 = A[1][1], a2 = A[2][2];
+  double a3 = A[0][1] + A[1][0], a4 = A[1][2] + A[2][1], a5 = A[0][2] + A[2][0];
+  if (p.nonlinear) {
+    // Green-Lagrange strain E = 1/2 (H + H^T + H^T H) of the state and its variation along the adjoint,
+    // sum_a B_a(F) adj_a = sym(F^T grad adj) with F = I + H (solid_element_3d.cpp:566-788 with the operators of :1308-1463)
+    double Eg[3][3], Dm[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        Eg[i][j] = 0.5 * (H[i][j] + H[j][i] + (H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j]));
+        Dm[i][j] = A[i][j] + (H[0][i] * A[0][j] + H[1][i] * A[1][j] + H[2][i] * A[2][j]);  // (F^T grad adj)_ij
+      }
+    e0 = Eg[0][0]; e1 = Eg[1][1]; e2 = Eg[2][2];
+    e3 = Eg[0][1] + Eg[1][0]; e4 = Eg[1][2] + Eg[2][1]; e5 = Eg[0][2] + Eg[2][0];
+    a0 = Dm[0][0]; a1 = Dm[1][1]; a2 = Dm[2][2];
+    a3 = Dm[0][1] + Dm[1][0]; a4 = Dm[1][2] + Dm[2][1]; a5 = Dm[0][2] + Dm[2][0];
+  }
   const double dens = p.lam1 * (a0 + a1 + a2) * (e0 + e1 + e2) +
                       p.mu1 * (2. * (a0 * e0 + a1 * e1 + a2 * e2) + a3 * e3 + a4 * e4 + a5 * e5);
   const double dE = p.E0 * (1. - p.rho_min) * p.penalty * pow(rho, p.penalty - 1.);
@@ -556,8 +572,9 @@ __global__ void __launch_bounds__(128) sens_gather_kernel(const StressParams p, 
 
 cudaError_t launch_density_sensitivities(const StressParams& p, const double* adj, double* G, cudaStream_t stream) {
   StressParams q = p;
-  q.scratch_nodal = p.nn == 8 ? 1 : 0;
-  if (p.nn == 8) sens_qp_hex8_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(q, adj);
+  const bool fast8 = p.nn == 8 && !p.nonlinear;  // the HEX8 specialisation is the linear-strain kernel
+  q.scratch_nodal = fast8 ? 1 : 0;
+  if (fast8) sens_qp_hex8_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(q, adj);
   else sens_qp_kernel<<<stress_blocks(p.n_elem, p.nq), 128, 0, stream>>>(q, adj);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;

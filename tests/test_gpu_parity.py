@@ -397,6 +397,39 @@ def test_hex27_green_lagrange_thermal_simp_diag(built):
     _check_RJ(prob, O.state(prob.n_dof, 1, scale=2e-3))
 
 
+def test_green_lagrange_density_sensitivities_hex8_hex27(built):
+    # internal_residual_sensitivity with NONLINEAR_STRAIN (solid_element_3d.cpp:566-788): adj . dR/d(rho_n) with the
+    # Green-Lagrange strain of the state and its variation along the adjoint, alone and together with R / J
+    rng = np.random.default_rng(9)
+    for nv in (3, 6):
+        prob = O.cantilever(6, 4, 3, nv=nv, jitter=0.2, simp=True, nonlinear_strain=1)
+        X = O.state(prob.n_dof, 1, scale=2e-3); lam = O.state(prob.n_dof, 2, scale=2e-3)
+        n = prob.n_nodes
+        ctx = prob.make_context(0)
+        g_ref = prob.adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
+        g_lin = O.cantilever(6, 4, 3, nv=nv, jitter=0.2, simp=True).adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
+        assert np.abs(g_ref - g_lin).max() > 1e-3 * np.abs(g_lin).max()  # the nonlinear terms matter at this state
+        G = np.full(n, np.nan); R = np.empty(prob.n_dof); J = np.empty(ctx.nnz)
+        ctx.sensitivity_sweep(X, lam, G, R, J)
+        _close(G, g_ref, 1e-11)
+        Ro, Jo = prob.residual_and_jacobian(X)
+        _close(R, Ro); _close(J, Jo)
+        G2 = np.full(n, np.nan)
+        ctx.sensitivity_sweep(X, lam, G2)
+        assert np.array_equal(G, G2)
+    p27 = _hex27_problem(3, 2, 2, jitter=0.1, nonlinear_strain=1, rho=0.2 + 0.6 * rng.uniform(size=7 * 5 * 5), rho_min=1e-8,
+                         penalty=4.0)
+    X = O.state(p27.n_dof, 1, scale=2e-3); lam = O.state(p27.n_dof, 2, scale=2e-3)
+    n = p27.n_nodes
+    c27 = p27.make_context(0)
+    g_ref = p27.adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
+    G = np.full(n, np.nan); R = np.empty(p27.n_dof); J = np.empty(c27.nnz)
+    c27.sensitivity_sweep(X, lam, G, R, J)
+    _close(G, g_ref, 1e-11)
+    Ro, Jo = p27.residual_and_jacobian(X)
+    _close(R, Ro); _close(J, Jo)
+
+
 # ---- stress output (StressStrainOutputBase) ------------------------------------------------------------------------
 def _stress_case(prob, X, p_norm=2.0, rho_exp=0.0, sigma0=None):
     ctx = prob.make_context(0)
