@@ -725,8 +725,10 @@ int run_internal_force(mastb200_context* ctx, const double* V, int mode, const d
   StressParams p;
   if ((rc = fill_stress_params(ctx, V, p))) return rc;
   if (!constrain_rows) p.cmask = nullptr;  // ComplianceOutput::evaluate dots the unconstrained element vectors with the state
-  if (ctx->mat.nonlinear_strain)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "matrix-free products with Green-Lagrange strain are not on the device path");
+  // Green-Lagrange strain: the parameter sensitivities of the internal force (modes 1-3) carry F = I + grad u of the state;
+  // the tangent product J dX (mode 0 with a perturbation) and the thermoelastic force vector need more than that
+  if (ctx->mat.nonlinear_strain && (mode == 0 || mode == 4))
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "tangent products with Green-Lagrange strain are not on the device path");
   p.lam1 = lam1; p.mu1 = mu1;
   p.alpha_k = ctx->mat.alpha * (3. * p.lam1 + 2. * p.mu1);
   p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;

@@ -30,6 +30,7 @@ struct QpGeom {
   double det, wq;
   double eps[6], sig[6];
   double E, rho;
+  double H[3][3];    // displacement gradient d u_i / d x_j (F = I + H for the Green-Lagrange strain)
 };
 
 // geometry + linear/Green-Lagrange strain + stress at (e, q); tab: N[q][b], dN[q][b][3], w[q]
@@ -79,6 +80,10 @@ __device__ __forceinline__ void eval_qp(const StressParams& p, int64_t e, int q,
   double E = p.E0;
   if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rho, p.penalty));
   g.E = E; g.rho = rho;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) g.H[i][j] = H[i][j];
   if (p.nonlinear) {
     double Eg[3][3];
 #pragma unroll
@@ -282,7 +287,18 @@ __global__ void __launch_bounds__(TB) force_qp_kernel(const StressParams p, int 
     g.sig[0] = g.sig[1] = g.sig[2] = st;
     g.sig[3] = g.sig[4] = g.sig[5] = 0.;
   }
-  const double S[3][3] = {{g.sig[0], g.sig[3], g.sig[5]}, {g.sig[3], g.sig[1], g.sig[4]}, {g.sig[5], g.sig[4], g.sig[2]}};
+  double S[3][3] = {{g.sig[0], g.sig[3], g.sig[5]}, {g.sig[3], g.sig[1], g.sig[4]}, {g.sig[5], g.sig[4], g.sig[2]}};
+  if (p.nonlinear) {  // Green-Lagrange: f_a = JxW B_a(F)^T S = JxW (F S) grad N_a with F = I + H (modes 1-3: S <- dD/dp E_GL)
+    double FS[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) FS[k][c] = S[k][c] + (g.H[k][0] * S[0][c] + g.H[k][1] * S[1][c] + g.H[k][2] * S[2][c]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) S[k][c] = FS[k][c];
+  }
 #pragma unroll
   for (int k = 0; k < 3; ++k)
 #pragma unroll

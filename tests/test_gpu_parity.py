@@ -708,6 +708,26 @@ def test_sensitivity_assemble_vector(built, elem_type):
 
 
 @pytest.mark.parametrize("elem_type", [8, 27])
+def test_sensitivity_assemble_vector_green_lagrange(built, elem_type):
+    """The same three parameters with NONLINEAR_STRAIN: dR/dp = sum_q JxW B_a(F)^T (dD/dp E_GL), F = I + grad u."""
+    prob = _solid(elem_type, nonlinear_strain=1)
+    X = O.state(prob.n_dof, 1, scale=2e-3)
+    ctx = prob.make_context(0)
+    rng = np.random.default_rng(11)
+    dv_node = rng.choice(prob.n_nodes, 9, replace=False).astype(np.int32)
+    dv_w = rng.uniform(0.1, 1.0, 9)
+    out = np.full(prob.n_dof, np.nan)
+    ctx.sensitivity_assemble(X, out, 0, dv_node, dv_w)
+    ref = prob.sensitivity_assemble(X, dv_node, dv_w)
+    _close(out, ref, 1e-11)
+    lin = _solid(elem_type).sensitivity_assemble(X, dv_node, dv_w)
+    assert np.abs(ref - lin).max() > 1e-3 * np.abs(lin).max()
+    for kind in (1, 2):
+        ctx.sensitivity_assemble(X, out, kind)
+        _close(out, prob.sensitivity_assemble_param(X, kind), 1e-11)
+
+
+@pytest.mark.parametrize("elem_type", [8, 27])
 def test_linearized_jacobian_solution_product(built, elem_type):
     prob = _solid(elem_type, loads=False)
     X = O.state(prob.n_dof, 1); dX = O.state(prob.n_dof, 7)
