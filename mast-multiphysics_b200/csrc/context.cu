@@ -273,8 +273,6 @@ void detect_quad4_struct(mastb200_context* ctx) {
 // QUAD4 Mindlin plate (row-block gather; per-element local frames when an element is out of the xy-plane)
 int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J) {
   int rc;
-  if (ctx->mat.nonlinear_strain)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "von Karman strain of the plate element is not on the device path");
   if (ctx->thermal)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "TEMPERATURE load on the plate element is not on the device path");
   if (ctx->rho_set)
@@ -316,6 +314,7 @@ int run_plate_sweep(mastb200_context* ctx, const double* X, double* R, double* J
   p.shear_G = m.E0 / 2. / (1. + m.nu);
   p.thickness = m.thickness; p.offset = m.offset; p.kappa = m.kappa;
   p.local_frames = local_frames;
+  p.nonlinear = ctx->mat.nonlinear_strain ? 1 : 0;
   CU(launch_quad4_plate(p, ctx->stream));
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));

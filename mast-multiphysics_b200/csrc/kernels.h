@@ -158,6 +158,7 @@ struct PlateParams {
   double c11 = 0., c12 = 0., c33 = 0.;   // plane-stress / plane-strain material matrix C
   double shear_G = 0., thickness = 1., offset = 0., kappa = 5. / 6.;
   int32_t local_frames = 0;              // 1: some element's nodes do not share one z -> per-element local frames (T K T^T)
+  int32_t nonlinear = 0;                 // 1: NONLINEAR_STRAIN -- Green-Lagrange membrane strain + von Karman strain
 };
 cudaError_t launch_quad4_plate(const PlateParams& p, cudaStream_t stream);
 

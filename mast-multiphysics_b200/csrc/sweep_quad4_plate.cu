@@ -1,4 +1,4 @@
-// sweep_quad4_plate.cu -- QUAD4 Mindlin plate residual + Jacobian, linear strain, elements anywhere in space
+// sweep_quad4_plate.cu -- QUAD4 Mindlin plate residual + Jacobian, linear or von Karman strain, elements anywhere in space
 // (sm_100a, fp64).
 //
 // Device counterpart of the element loop of MAST::NonlinearImplicitAssembly::residual_and_jacobian
@@ -13,6 +13,12 @@
 // src/mesh/geom_elem.cpp:358-374, 461-511): solution rotated in (structural_element_base.cpp:1606-1640), f = T f_l and
 // K = T K_l T^T rotated out (:1565-1601, 1642-1674), per element, before the block joins the row (LOCAL variant; the
 // host picks it when the mesh has such an element).
+// NONLINEAR_STRAIN (NL variant): Green-Lagrange membrane strain (::initialize_green_lagrange_strain_operator, :141-250:
+// B_m = B_lin + mat_x B_x + mat_y B_y, i.e. the columns [(1+u,x) N,x; u,y N,y; (1+u,x) N,y + u,y N,x] and
+// [v,x N,x; (1+v,y) N,y; v,x N,y + (1+v,y) N,x]) plus the von Karman strain 1/2 w,x^2, 1/2 w,y^2, w,x w,y
+// (::initialize_von_karman_strain_operator, :57-100), with the tangent terms exactly as the reference has them
+// (:1886-1998): B_m^T A B_m and the initial-stress stiffness of u, v and w from N = A eps + B kappa, but B_lin -- not
+// B_m -- in the membrane / von Karman / bending couplings.
 //
 // Row-owner gather: one thread per (owned node, neighbour) pair, i.e. per 6x6 block of the node-level CSR.  The thread
 // walks the elements adjacent to the row node in ascending id (the order of the reference's element loop) and adds
@@ -59,7 +65,7 @@ __device__ __forceinline__ void q4_eval(const double* x, const double* y, double
   }
 }
 
-template <bool LOCAL>
+template <bool LOCAL, bool NL>
 __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
   const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (t >= p.n_entries) return;
@@ -142,13 +148,14 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
       }
     }
     const bool want_f = self && p.R;
+    const bool want_u = want_f || NL;  // the nonlinear tangent depends on the state
     double U[4][6];
-    if (want_f)
+    if (want_u)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int v = 0; v < 6; ++v) U[k][v] = p.X[(int64_t)en[k] * 6 + v];
-    if (LOCAL && want_f && use_local)
+    if (LOCAL && want_u && use_local)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
 #pragma unroll
@@ -162,17 +169,64 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
       Q4 g;
       q4_eval(x, y, (q & 1) ? GP : -GP, (q & 2) ? GP : -GP, 1., g);
       const double gxa = g.gx[a], gya = g.gy[a], gxb = g.gx[b], gyb = g.gy[b];
+      // NL: displacement gradients, total membrane strain (Green-Lagrange + von Karman), curvatures, stress resultants
+      double ux = 0., uy = 0., vx = 0., vy = 0., wx = 0., wy = 0., N0 = 0., N1 = 0., N2 = 0., Q0 = 0., Q1 = 0., Q2 = 0.;
+      if (NL) {
+        double k0 = 0., k1 = 0., k2 = 0.;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          ux += g.gx[k] * U[k][0]; uy += g.gy[k] * U[k][0];
+          vx += g.gx[k] * U[k][1]; vy += g.gy[k] * U[k][1];
+          wx += g.gx[k] * U[k][2]; wy += g.gy[k] * U[k][2];
+          k0 += g.gx[k] * U[k][4]; k1 += -g.gy[k] * U[k][3]; k2 += -g.gx[k] * U[k][3] + g.gy[k] * U[k][4];
+        }
+        const double e0 = ux + 0.5 * (ux * ux + vx * vx) + 0.5 * wx * wx, e1 = vy + 0.5 * (uy * uy + vy * vy) + 0.5 * wy * wy;
+        const double e2 = (uy + vx) + (ux * uy + vx * vy) + wx * wy;
+        const double Ce0 = c11 * e0 + c12 * e1, Ce1 = c12 * e0 + c11 * e1, Ce2 = c33 * e2;
+        const double Ck0 = c11 * k0 + c12 * k1, Ck1 = c12 * k0 + c11 * k1, Ck2 = c33 * k2;
+        N0 = h * Ce0 + hoff * Ck0; N1 = h * Ce1 + hoff * Ck1; N2 = h * Ce2 + hoff * Ck2;
+        Q0 = hoff * Ce0 + hD * Ck0; Q1 = hoff * Ce1 + hD * Ck1; Q2 = hoff * Ce2 + hD * Ck2;
+      }
+      auto cdot = [&](double x0, double x1, double x2, double y0, double y1, double y2) {
+        return x0 * (c11 * y0 + c12 * y1) + x1 * (c12 * y0 + c11 * y1) + x2 * (c33 * y2);
+      };
       if (p.J) {
         // M[p][q] = s_p(a)^T C s_q(b),  s_1 = [gx, 0, gy], s_2 = [0, gy, gx]
         const double M00 = gxa * c11 * gxb + gya * c33 * gyb, M01 = gxa * c12 * gyb + gya * c33 * gxb;
         const double M10 = gya * c12 * gxb + gxa * c33 * gyb, M11 = gya * c11 * gyb + gxa * c33 * gxb;
         const double wA = g.JxW * h, wB = g.JxW * hoff, wD = g.JxW * hD;
-        KK[0][0] += wA * M00; KK[0][1] += wA * M01; KK[1][0] += wA * M10; KK[1][1] += wA * M11;      // membrane
+        if (!NL) {
+          KK[0][0] += wA * M00; KK[0][1] += wA * M01; KK[1][0] += wA * M10; KK[1][1] += wA * M11;      // membrane
+        } else {
+          // columns of B_m for u and v at the two nodes, the von Karman column of w
+          const double au0 = (1. + ux) * gxa, au1 = uy * gya, au2 = (1. + ux) * gya + uy * gxa;
+          const double av0 = vx * gxa, av1 = (1. + vy) * gya, av2 = vx * gya + (1. + vy) * gxa;
+          const double bu0 = (1. + ux) * gxb, bu1 = uy * gyb, bu2 = (1. + ux) * gyb + uy * gxb;
+          const double bv0 = vx * gxb, bv1 = (1. + vy) * gyb, bv2 = vx * gyb + (1. + vy) * gxb;
+          const double aw0 = wx * gxa, aw1 = wy * gya, aw2 = wy * gxa + wx * gya;
+          const double bw0 = wx * gxb, bw1 = wy * gyb, bw2 = wy * gxb + wx * gyb;
+          const double geo = g.JxW * (gxa * (N0 * gxb + N2 * gyb) + gya * (N2 * gxb + N1 * gyb));  // initial-stress stiffness
+          KK[0][0] += wA * cdot(au0, au1, au2, bu0, bu1, bu2) + geo; KK[0][1] += wA * cdot(au0, au1, au2, bv0, bv1, bv2);
+          KK[1][0] += wA * cdot(av0, av1, av2, bu0, bu1, bu2); KK[1][1] += wA * cdot(av0, av1, av2, bv0, bv1, bv2) + geo;
+          // membrane - vk and vk - membrane with B_lin (s_1, s_2), vk - vk, bending - vk and vk - bending
+          KK[0][2] += wA * cdot(gxa, 0., gya, bw0, bw1, bw2); KK[1][2] += wA * cdot(0., gya, gxa, bw0, bw1, bw2);
+          KK[2][0] += wA * cdot(aw0, aw1, aw2, gxb, 0., gyb); KK[2][1] += wA * cdot(aw0, aw1, aw2, 0., gyb, gxb);
+          KK[2][2] += geo + wA * cdot(aw0, aw1, aw2, bw0, bw1, bw2);
+          KK[3][2] += wB * cdot(0., -gya, -gxa, bw0, bw1, bw2); KK[4][2] += wB * cdot(gxa, 0., gya, bw0, bw1, bw2);
+          KK[2][3] += wB * cdot(aw0, aw1, aw2, 0., -gyb, -gxb); KK[2][4] += wB * cdot(aw0, aw1, aw2, gxb, 0., gyb);
+        }
         KK[0][3] += wB * (-M01); KK[0][4] += wB * M00; KK[1][3] += wB * (-M11); KK[1][4] += wB * M10;  // membrane - bending
         KK[3][0] += wB * (-M10); KK[3][1] += wB * (-M11); KK[4][0] += wB * M00; KK[4][1] += wB * M01;  // bending - membrane
         KK[3][3] += wD * M11; KK[3][4] += wD * (-M10); KK[4][3] += wD * (-M01); KK[4][4] += wD * M00;  // bending
       }
-      if (want_f) {
+      if (want_f && NL) {  // B_m^T N, the von Karman column of w, B_bend^T (B^T eps + D kappa) with the total membrane strain
+        ff[0] += g.JxW * ((1. + ux) * gxa * N0 + uy * gya * N1 + ((1. + ux) * gya + uy * gxa) * N2);
+        ff[1] += g.JxW * (vx * gxa * N0 + (1. + vy) * gya * N1 + (vx * gya + (1. + vy) * gxa) * N2);
+        ff[2] += g.JxW * (wx * gxa * N0 + wy * gya * N1 + (wy * gxa + wx * gya) * N2);
+        ff[3] += g.JxW * (-(gya * Q1 + gxa * Q2));
+        ff[4] += g.JxW * (gxa * Q0 + gya * Q2);
+      }
+      if (want_f && !NL) {
         double e0 = 0., e1 = 0., e2 = 0., k0 = 0., k1 = 0., k2 = 0.;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -282,8 +336,13 @@ __global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
 
 cudaError_t launch_quad4_plate(const PlateParams& p, cudaStream_t stream) {
   const int blocks = (int)((p.n_entries + TB - 1) / TB);
-  if (p.local_frames) quad4_plate_kernel<true><<<blocks, TB, 0, stream>>>(p);
-  else quad4_plate_kernel<false><<<blocks, TB, 0, stream>>>(p);
+  if (p.nonlinear) {
+    if (p.local_frames) quad4_plate_kernel<true, true><<<blocks, TB, 0, stream>>>(p);
+    else quad4_plate_kernel<false, true><<<blocks, TB, 0, stream>>>(p);
+  } else {
+    if (p.local_frames) quad4_plate_kernel<true, false><<<blocks, TB, 0, stream>>>(p);
+    else quad4_plate_kernel<false, false><<<blocks, TB, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 

@@ -624,7 +624,9 @@ static void solid3d_thermal_residual(const OracleProblem* p, const FE& fe, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// StructuralElement2D::internal_residual for a QUAD4 Mindlin plate in the xy-plane, linear strain
+// StructuralElement2D::internal_residual for a QUAD4 Mindlin plate in the xy-plane; linear strain or, with
+// nonlinear_strain = 1, the Green-Lagrange membrane strain of ::initialize_green_lagrange_strain_operator (:141-250) plus the
+// von Karman strain of ::initialize_von_karman_strain_operator (:57-100) with every tangent term of :1886-1998
 // (structural_element_2d.cpp:1075-1227, ::_internal_residual_operation :1765-2019,
 //  ::initialize_green_lagrange_strain_operator :141-250, MindlinBendingOperator
 //  mindlin_bending_operator.cpp:47-80 (bending strain), :94-160 + :314-361 (transverse shear with the
@@ -691,28 +693,74 @@ static void plate_internal_residual(const OracleProblem* p, const FE& fe, const 
   A = scaled(C, h);                                    // ExtensionStiffnessMatrix
   B = scaled(C, h * off);                              // ExtensionBendingStiffnessMatrix
   D = scaled(C, std::pow(h, 3) / 12. + h * std::pow(off, 2));  // BendingStiffnessMatrix
-  OperatorMatrix Bl, Bb;
+  OperatorMatrix Bl, Bb, Bnx, Bny, Bnu, Bnv, Bvk;
   Bl.reinit(3, 6, nn); Bb.reinit(3, 6, nn);
-  Vec phi(nn), strain, vec1, vec2, vec3, local_f(n2, 0.);
-  Mat local_jac(n2, n2);
+  const bool nl = p->nonlinear_strain != 0;  // strain_type() == NONLINEAR_STRAIN: if_vk (:1133)
+  if (nl) { Bnx.reinit(2, 6, nn); Bny.reinit(2, 6, nn); Bnu.reinit(2, 6, nn); Bnv.reinit(2, 6, nn); Bvk.reinit(2, 6, nn); }
+  Vec phi(nn), strain, vec1, vec2, vec3, vec4, vec6, local_f(n2, 0.);
+  Mat local_jac(n2, n2), mat_x(3, 2), mat_y(3, 2), vk_dwdxi(3, 2), stress(2, 2), mat5;
   for (int qp = 0; qp < fe.nq; ++qp) {
     const double JxW = fe.JxW[qp];
     for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 0);
     Bl.set_shape_function(0, 0, phi); Bl.set_shape_function(2, 1, phi);     // :184-186
+    if (nl) {                                                               // :188-197
+      Bnx.set_shape_function(0, 0, phi); Bnx.set_shape_function(1, 1, phi);
+      Bnu.set_shape_function(0, 0, phi); Bnv.set_shape_function(0, 1, phi);
+      Bvk.set_shape_function(0, 2, phi);                                    // :84
+    }
     Bb.set_shape_function(0, 4, phi);                                       // mindlin :69
     for (int a = 0; a < nn; ++a) phi[a] = -fe.dN(a, qp, 0);
     Bb.set_shape_function(2, 3, phi);                                       // :71
     for (int a = 0; a < nn; ++a) phi[a] = fe.dN(a, qp, 1);
     Bl.set_shape_function(1, 1, phi); Bl.set_shape_function(2, 0, phi);     // :203-204
+    if (nl) {                                                               // :206-215
+      Bny.set_shape_function(0, 0, phi); Bny.set_shape_function(1, 1, phi);
+      Bnu.set_shape_function(1, 0, phi); Bnv.set_shape_function(1, 1, phi);
+      Bvk.set_shape_function(1, 2, phi);                                    // :95
+    }
     Bb.set_shape_function(2, 4, phi);                                       // :78
     for (int a = 0; a < nn; ++a) phi[a] = -fe.dN(a, qp, 1);
     Bb.set_shape_function(1, 3, phi);                                       // :81
-    Bl.vector_mult(strain, sol);
+    if (nl) {  // :217-246: E = 1/2 (F + F^T + F^T F) with F = [d disp/dx, d disp/dy]
+      Vec ddx, ddy;
+      Bnx.vector_mult(ddx, sol); Bny.vector_mult(ddy, sol);
+      Mat F(2, 2), E(2, 2);
+      F(0, 0) = ddx[0]; F(1, 0) = ddx[1]; F(0, 1) = ddy[0]; F(1, 1) = ddy[1];
+      for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) E(i, j) = 0.5 * (F(i, j) + F(j, i) + (F(0, i) * F(0, j) + F(1, i) * F(1, j)));
+      strain.assign(3, 0.);
+      strain[0] = E(0, 0); strain[1] = E(1, 1); strain[2] = E(0, 1) + E(1, 0);
+      mat_x.zero(); mat_y.zero();
+      mat_x(0, 0) = ddx[0]; mat_x(0, 1) = ddx[1]; mat_x(2, 0) = ddy[0]; mat_x(2, 1) = ddy[1];
+      mat_y(1, 0) = ddy[0]; mat_y(1, 1) = ddy[1]; mat_y(2, 0) = ddx[0]; mat_y(2, 1) = ddx[1];
+    } else {
+      Bl.vector_mult(strain, sol);
+    }
     vec2 = matvec(A, strain);                       // membrane stress  :1815
     Bb.vector_mult(vec1, sol);
     { const Vec t = matvec(B, vec1); for (int i = 0; i < 3; ++i) vec2[i] += t[i]; }  // :1822
+    if (nl) {  // von Karman strain (:57-100) joins the membrane strain and stress (:1824-1833)
+      Vec dwv;
+      Bvk.vector_mult(dwv, sol);
+      const double dwx = dwv[0], dwy = dwv[1];
+      vk_dwdxi.zero();
+      vk_dwdxi(0, 0) = dwx; vk_dwdxi(2, 1) = dwx; vk_dwdxi(1, 1) = dwy; vk_dwdxi(2, 0) = dwy;
+      const Vec evk = {0.5 * dwx * dwx, 0.5 * dwy * dwy, dwx * dwy};
+      for (int i = 0; i < 3; ++i) strain[i] += evk[i];
+      const Vec t = matvec(A, evk);
+      for (int i = 0; i < 3; ++i) vec2[i] += t[i];
+    }
+    stress(0, 0) = vec2[0]; stress(0, 1) = vec2[2]; stress(1, 0) = vec2[2]; stress(1, 1) = vec2[1];  // :1838-1841
     Bl.vector_mult_transpose(vec3, vec2);
     for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];               // :1846-1847
+    if (nl) {
+      vec4 = matvec_t(mat_x, vec2); Bnx.vector_mult_transpose(vec6, vec4);  // :1853-1855
+      for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec6[i];
+      vec4 = matvec_t(mat_y, vec2); Bny.vector_mult_transpose(vec6, vec4);  // :1858-1860
+      for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec6[i];
+      vec4 = matvec_t(vk_dwdxi, vec2); Bvk.vector_mult_transpose(vec3, vec4);  // :1867-1869
+      for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];
+    }
     vec1 = matvec_t(B, strain);                                             // :1875
     Bb.vector_mult_transpose(vec3, vec1);
     for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];
@@ -722,6 +770,27 @@ static void plate_internal_residual(const OracleProblem* p, const FE& fe, const 
     for (int i = 0; i < n2; ++i) local_f[i] += JxW * vec3[i];
     if (request_jacobian) {
       Bl.left_multiply(mat1, A); Bl.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);  // :1888-1890
+      if (nl) {
+        // the eight products of the Green-Lagrange membrane operator (:1895-1949) ...
+        Bnx.left_multiply(mat1, mat_x); mat1 = matmul(A, mat1); Bl.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);
+        Bny.left_multiply(mat1, mat_y); mat1 = matmul(A, mat1); Bl.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);
+        Bl.left_multiply(mat1, A); mat5 = matmul_tn(mat_x, mat1); Bnx.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        Bnx.left_multiply(mat1, mat_x); mat1 = matmul(A, mat1); mat5 = matmul_tn(mat_x, mat1); Bnx.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        Bny.left_multiply(mat1, mat_y); mat1 = matmul(A, mat1); mat5 = matmul_tn(mat_x, mat1); Bnx.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        Bl.left_multiply(mat1, A); mat5 = matmul_tn(mat_y, mat1); Bny.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        Bnx.left_multiply(mat1, mat_x); mat1 = matmul(A, mat1); mat5 = matmul_tn(mat_y, mat1); Bny.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        Bny.left_multiply(mat1, mat_y); mat1 = matmul(A, mat1); mat5 = matmul_tn(mat_y, mat1); Bny.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        // ... and the initial-stress stiffness of u and v (:1954-1963)
+        Bnu.left_multiply(mat5, stress); Bnu.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        Bnv.left_multiply(mat5, stress); Bnv.right_multiply_transpose(mat2, mat5); add_scaled_top_left(local_jac, mat2, JxW);
+        // von Karman terms (:1967-1998): membrane - vk, vk - membrane (with B_lin only, as the reference has them), vk - vk, bending - vk
+        Bvk.left_multiply(mat3, vk_dwdxi); mat3 = matmul(A, mat3); Bl.right_multiply_transpose(mat2, mat3); add_scaled_top_left(local_jac, mat2, JxW);
+        Bl.left_multiply(mat1, A); mat3 = matmul_tn(vk_dwdxi, mat1); Bvk.right_multiply_transpose(mat2, mat3); add_scaled_top_left(local_jac, mat2, JxW);
+        Bvk.left_multiply(mat3, stress); Bvk.right_multiply_transpose(mat2, mat3); add_scaled_top_left(local_jac, mat2, JxW);
+        Bvk.left_multiply(mat3, vk_dwdxi); mat3 = matmul_tn(vk_dwdxi, matmul(A, mat3)); Bvk.right_multiply_transpose(mat2, mat3); add_scaled_top_left(local_jac, mat2, JxW);
+        Bvk.left_multiply(mat3, vk_dwdxi); mat3 = matmul_tn(B, mat3); Bb.right_multiply_transpose(mat2, mat3); add_scaled_top_left(local_jac, mat2, JxW);
+        Bb.left_multiply(mat1, B); mat3 = matmul_tn(vk_dwdxi, mat1); Bvk.right_multiply_transpose(mat2, mat3); add_scaled_top_left(local_jac, mat2, JxW);
+      }
       mat3 = transposed(B);
       Bl.left_multiply(mat1, mat3); Bb.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);  // :2001-2004
       Bb.left_multiply(mat1, B); Bl.right_multiply_transpose(mat2, mat1); add_scaled_top_left(local_jac, mat2, JxW);     // :2007-2009

@@ -471,7 +471,7 @@ def test_hex27_stress_output_and_aggregate(built):
 
 
 # ---- QUAD4 Mindlin plate (StructuralElement2D) -----------------------------------------------------------------------
-def _plate_problem(nx, ny, jitter=0.0, offset=0.03, plane_strain=0, diag=False, scramble=False):
+def _plate_problem(nx, ny, jitter=0.0, offset=0.03, plane_strain=0, diag=False, scramble=False, **kw):
     xyz, conn = mesh.build_square(nx, ny, 1.5, 1.0)
     rng = np.random.default_rng(11)
     if jitter:
@@ -490,7 +490,7 @@ def _plate_problem(nx, ny, jitter=0.0, offset=0.03, plane_strain=0, diag=False, 
         xyz, con = xyz2, c6.ravel()
         conn = perm[conn].astype(np.int32)[rng.permutation(len(conn))]
     return O.Problem(O.QUAD4, xyz, conn, 6, constrained=con, E0=72e9, nu=0.33, thickness=0.06, offset=offset,
-                     kappa=5.0 / 6.0, plane_strain=plane_strain, diag_elem=d)
+                     kappa=5.0 / 6.0, plane_strain=plane_strain, diag_elem=d, **kw)
 
 
 @pytest.mark.parametrize("offset,plane_strain", [(0.0, 0), (0.03, 0), (0.03, 1)])
@@ -538,6 +538,40 @@ def test_quad4_mindlin_plate_out_of_plane_and_folded(built):
     fold = O.Problem(O.QUAD4, xyz, prob.conn, 6, constrained=prob.constrained, E0=72e9, nu=0.33, thickness=0.06,
                      offset=0.0, kappa=5.0 / 6.0, diag_elem=prob.diag_elem)
     _check_RJ(fold, O.state(fold.n_dof, 2))
+
+
+def _plate_state(prob, seed, amp_uv, amp_w, amp_th):
+    rng = np.random.default_rng(seed)
+    U = np.zeros((prob.n_nodes, 6))
+    U[:, :2] = amp_uv * rng.uniform(-1, 1, (prob.n_nodes, 2))
+    U[:, 2] = amp_w * rng.uniform(-1, 1, prob.n_nodes)
+    U[:, 3:5] = amp_th * rng.uniform(-1, 1, (prob.n_nodes, 2))
+    return U.ravel()
+
+
+@pytest.mark.parametrize("offset", [0.0, 0.03])
+def test_quad4_plate_von_karman_residual_and_jacobian(built, offset):
+    # NONLINEAR_STRAIN on the plate: Green-Lagrange membrane strain + von Karman strain (structural_element_2d.cpp:57-100,
+    # 141-250) with the tangent terms of :1886-1998, at a state where they matter (deflections of a few thicknesses)
+    prob = _plate_problem(8, 5, jitter=0.2, offset=offset, nonlinear_strain=1)
+    X = _plate_state(prob, 4, 0.01, 0.08, 0.05)
+    ctx, R, J = _check_RJ(prob, X)
+    lin = _plate_problem(8, 5, jitter=0.2, offset=offset)
+    Rl, Jl = lin.residual_and_jacobian(X)
+    assert np.abs(J - Jl).max() > 1e-2 * np.abs(Jl).max() and np.abs(R - Rl).max() > 1e-2 * np.abs(Rl).max()
+    _check_RJ(prob, X, want_R=False)
+    _check_RJ(prob, X, want_J=False)
+
+
+def test_quad4_plate_von_karman_local_frames_diag_scrambled(built):
+    # out of the xy-plane (local frames rotate the state in and the block out), diagonal elements, scrambled numbering
+    prob = _plate_problem(7, 5, jitter=0.2, diag=True, scramble=True, nonlinear_strain=1)
+    _check_RJ(prob, _plate_state(prob, 5, 0.01, 0.08, 0.05))
+    flat = _plate_problem(6, 4, jitter=0.2, nonlinear_strain=1)
+    Q, _ = np.linalg.qr(np.random.default_rng(2).normal(size=(3, 3)))
+    rot = O.Problem(O.QUAD4, flat.xyz @ Q.T + 0.4, flat.conn, 6, constrained=flat.constrained, E0=72e9, nu=0.33,
+                    thickness=0.06, offset=0.03, kappa=5.0 / 6.0, nonlinear_strain=1)
+    _check_RJ(rot, _plate_state(rot, 6, 0.01, 0.05, 0.05))
 
 
 def test_density_sensitivities_alone_hex8_hex27_and_old_sweep(built, monkeypatch):

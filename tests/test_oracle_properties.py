@@ -304,3 +304,38 @@ def test_heat_surface_radiation_jacobian_is_the_derivative_of_the_residual(built
     L = np.linalg.norm(xyz[3] - xyz[2])
     f_u, _ = p.elem_calculations(0, np.full(4, 400.0))
     assert np.isclose(f_u.sum(), 5.670374419e-8 * 0.8 * 0.06 * L * (400.0 ** 4 - 300.0 ** 4), rtol=1e-12)
+
+
+def test_plate_von_karman_tangent_is_exact_where_the_reference_is_consistent():
+    """StructuralElement2D with NONLINEAR_STRAIN (structural_element_2d.cpp:1765-2019): the tangent equals the derivative of
+    the residual for a pure bending state (von Karman terms alone) and, without section offset, for a pure membrane state
+    (Green-Lagrange terms alone).  With both active the reference keeps B_lin in the membrane / von Karman couplings
+    (:1967-1977), so its tangent is not the exact linearisation -- the oracle restates that too."""
+    import scipy.sparse as sp
+    from mast_b200 import mesh
+    xyz, conn = mesh.build_square(3, 2, 1.5, 1.0)
+    rng = np.random.default_rng(1)
+    inner = (xyz[:, 0] > 0) & (xyz[:, 0] < 1.5) & (xyz[:, 1] > 0) & (xyz[:, 1] < 1.0)
+    xyz[inner, :2] += 0.1 * rng.uniform(-1, 1, (inner.sum(), 2))
+    n = len(xyz)
+
+    def fd_error(prob, X):
+        _, J = prob.residual_and_jacobian(X)
+        rp, ci = prob.pattern()
+        A = sp.csr_matrix((J, ci, rp), shape=(prob.n_dof, prob.n_dof)).toarray()
+        Afd = np.zeros_like(A)
+        h = 1e-7
+        for j in range(prob.n_dof):
+            Xp = X.copy(); Xp[j] += h
+            Xm = X.copy(); Xm[j] -= h
+            Afd[:, j] = (prob.residual_and_jacobian(Xp, want_J=False)[0] - prob.residual_and_jacobian(Xm, want_J=False)[0]) / (2 * h)
+        assert np.abs(A - A.T).max() <= 1e-13 * np.abs(A).max()
+        return np.abs(A - Afd).max() / np.abs(A).max()
+
+    bend = np.zeros((n, 6)); bend[:, 2] = 0.05 * rng.uniform(-1, 1, n); bend[:, 3:5] = 0.02 * rng.uniform(-1, 1, (n, 2))
+    memb = np.zeros((n, 6)); memb[:, :2] = 0.02 * rng.uniform(-1, 1, (n, 2))
+    p_off = O.Problem(O.QUAD4, xyz, conn, 6, thickness=0.06, offset=0.03, kappa=5 / 6, nonlinear_strain=1)
+    p_mid = O.Problem(O.QUAD4, xyz, conn, 6, thickness=0.06, offset=0.0, kappa=5 / 6, nonlinear_strain=1)
+    assert fd_error(p_off, bend.ravel()) < 1e-9
+    assert fd_error(p_mid, memb.ravel()) < 1e-9
+    assert fd_error(p_mid, (bend + memb).ravel()) > 1e-4   # the reference's inconsistent cross terms
