@@ -303,6 +303,13 @@ int mastb200_debug_plan_copy(mastb200_context* ctx, int32_t aux, void* tiles, vo
 /* the CUDA stream all work of this context is ordered on (cudaStream_t as void*) */
 void* mastb200_stream(const mastb200_context* ctx);
 
+/* Stream-ordered mode ("one context per rank/GPU, stream-ordered").  Off (default): every call returns after its
+ * work has finished, as MAST's assembly does (R and J closed on return, nonlinear_implicit_assembly.cpp:258-265).  On: a
+ * residual_and_jacobian / sensitivity_sweep call whose X, R, J, G (and adjoint) are all DEVICE pointers only enqueues its
+ * work on mastb200_stream() and returns; the caller orders later work on that stream (the device solve, the next sweep) or
+ * synchronises it.  Calls with host buffers still synchronise.  mastb200_get_stats synchronises the stream. */
+int mastb200_set_async(mastb200_context* ctx, int32_t on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "mastb200_filter_init", "mastb200_filter_get", "mastb200_filter_apply", "mastb200_filter_apply_transpose", "mastb200_volume",
     "mastb200_comm_unique_id", "mastb200_comm_init", "mastb200_comm_attach", "mastb200_set_ghost_exchange",
     "mastb200_build_localized_vector", "mastb200_all_reduce_sum", "mastb200_solve", "mastb200_near_null_space",
-    "mastb200_get_stats", "mastb200_stream", "mastb200_debug_plan_sizes", "mastb200_debug_plan_copy",
+    "mastb200_get_stats", "mastb200_stream", "mastb200_set_async", "mastb200_debug_plan_sizes", "mastb200_debug_plan_copy",
 ]
 
 
@@ -130,6 +130,7 @@ def load_library():
     lib.mastb200_debug_plan_copy.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp]
     lib.mastb200_stream.argtypes = [vp]
     lib.mastb200_stream.restype = vp
+    lib.mastb200_set_async.argtypes = [vp, i32]
     _LIB = lib
     return lib
 
@@ -420,3 +421,7 @@ class Context:
     @property
     def stream(self):
         return self._lib.mastb200_stream(self._h)
+
+    def set_async(self, on=True):
+        """Stream-ordered mode: sweeps whose buffers all live on the device return without synchronising the stream."""
+        self._ck(self._lib.mastb200_set_async(self._h, 1 if on else 0))

@@ -856,7 +856,10 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
   if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
   if ((rc = finish_out(ctx, G, (size_t)ctx->n_nodes, dG))) return rc;
-  CU(cudaStreamSynchronize(ctx->stream));
+  // stream-ordered mode: nothing left the device, so the caller's next call (or its own stream work) may queue behind this
+  // sweep; errors of the launch itself were collected above, asynchronous ones surface at the next synchronising call
+  const bool all_device = dX == X && (!R || dR == R) && (!J || dJ == J) && (!G || (dG == G && (adj == X || dadj == adj)));
+  if (!(ctx->async_device && all_device)) CU(cudaStreamSynchronize(ctx->stream));
   return MASTB200_OK;
 }
 
@@ -920,6 +923,12 @@ int mastb200_destroy(mastb200_context* ctx) {
 const char* mastb200_last_error(const mastb200_context* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 void* mastb200_stream(const mastb200_context* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int mastb200_set_async(mastb200_context* ctx, int32_t on) {
+  if (!ctx) return MASTB200_ERR_ARG;
+  ctx->async_device = on != 0;
+  return MASTB200_OK;
+}
 
 int mastb200_set_mesh(mastb200_context* ctx, int32_t elem_type, int64_t n_elem, int64_t n_nodes, const double* xyz,
                       const int32_t* conn, const uint8_t* diag_elem) {
@@ -1583,6 +1592,7 @@ int mastb200_get_stats(const mastb200_context* ctx, mastb200_stats* s) {
   s->ctas = ctx->last_struct ? (lm ? ctx->splan.m_n_ctas : ctx->splan.n_ctas) : D.n_ctas;
   s->structured = ctx->last_struct ? (lm ? 2 : (ctx->splan.last_slots ? 3 : 1)) : (ctx->elem_type == MASTB200_QUAD4 && ctx->last_q4s ? 1 : 0);
   if (ctx->timed) {
+    if (ctx->async_device) cudaStreamSynchronize(ctx->stream);  // the events of the last sweep may still be in flight
     float a = 0.f, b = 0.f;
     if (cudaEventElapsedTime(&a, ctx->ev[0], ctx->ev[3]) == cudaSuccess) s->last_sweep_ms = a + ctx->carry_ms;
     if (cudaEventElapsedTime(&b, ctx->ev[1], ctx->ev[2]) == cudaSuccess) s->last_main_kernel_ms = b + ctx->carry_ms;

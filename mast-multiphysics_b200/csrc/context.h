@@ -140,6 +140,7 @@ struct mastb200_context {
     bool last_slots = false;
     void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); m_units.release(); }
   } splan;
+  bool async_device = false;  // mastb200_set_async: sweeps whose buffers all live on the device return without a stream sync
   int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
   DevBuf<int32_t> d_tile_counter, d_owned_nodes;
   DevBuf<uint8_t> d_cmask;

@@ -113,6 +113,31 @@ def test_device_pointers_and_determinism(built):
     assert np.array_equal(R2, R1) and np.array_equal(J2, J1)
 
 
+def test_stream_ordered_mode_gives_the_same_bits(built):
+    # mastb200_set_async: with device buffers the call only enqueues on the context stream; same values, and host buffers
+    # still come back complete
+    import torch
+    prob = O.cantilever(10, 7, 6, jitter=0.2)
+    X = O.state(prob.n_dof, 1)
+    ctx = prob.make_context(0)
+    R0 = np.empty(prob.n_dof); J0 = np.empty(ctx.nnz)
+    ctx.residual_and_jacobian(X, R0, J0)
+    ctx.set_async(True)
+    dX = torch.from_numpy(X).cuda()
+    dR = torch.zeros(prob.n_dof, dtype=torch.float64, device="cuda")
+    dJ = torch.zeros(ctx.nnz, dtype=torch.float64, device="cuda")
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    for _ in range(3):
+        ctx.residual_and_jacobian(dX, dR, dJ)
+    stream.synchronize()
+    assert np.array_equal(dR.cpu().numpy(), R0) and np.array_equal(dJ.cpu().numpy(), J0)
+    assert ctx.stats()["last_main_kernel_ms"] > 0
+    R1 = np.full(prob.n_dof, np.nan); J1 = np.full(ctx.nnz, np.nan)
+    ctx.residual_and_jacobian(X, R1, J1)   # host buffers: synchronous as before
+    assert np.array_equal(R1, R0) and np.array_equal(J1, J0)
+    ctx.set_async(False)
+
+
 def test_density_sensitivities(built):
     # one fused sweep == n_dv sensitivity_assemble sweeps + dots of the reference
     prob = O.cantilever(6, 4, 4, jitter=0.2, simp=True)
