@@ -372,11 +372,47 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     else CU(launch_quad4_heat(p, ctx->stream));
     ctx->launches++;
   } else {
+    // Two-pass assembly of the 3-dof Jacobian (default when J is requested): chunks of consecutive element ids; pass 1 stores
+    // K_e and f_e element-major (one launch per chunk, no colours, no read-modify-write), pass 2 sums them per owned row and
+    // writes the CSR rows as whole runs.  The coloured scatter touches every CSR value 1.42 times in 24-byte pieces
+    // (partial-sector fills: 160 KB of DRAM traffic per element); here everything streams (profiles/r02g_hex27_two_pass.md).
+    // MASTB200_H27_TWO_PASS=0 keeps the coloured scatter; MASTB200_H27_CHUNK sets the elements per chunk.
+    bool two_pass = ctx->nv == 3 && !ctx->has_diag && !G.ordered && dJ != nullptr;
+    if (const char* e2 = getenv("MASTB200_H27_TWO_PASS")) if (e2[0] == '0') two_pass = false;
+    if (two_pass && !G.tp_built) {
+      int64_t chunk = 131072;
+      if (const char* ce = getenv("MASTB200_H27_CHUNK")) chunk = std::max<int64_t>(1, atoll(ce));
+      chunk = std::min<int64_t>(chunk, ctx->n_elem);
+      const Pattern& P = ctx->pat;
+      std::vector<int32_t> rows;
+      std::vector<int32_t> stamp((size_t)ctx->n_nodes, -1);
+      G.tp_row_ptr.assign(1, 0);
+      for (int64_t c0 = 0, c = 0; c0 < ctx->n_elem; c0 += chunk, ++c) {
+        const int64_t c1 = std::min<int64_t>(c0 + chunk, ctx->n_elem);
+        const size_t first = rows.size();
+        for (int64_t e = c0; e < c1; ++e)
+          for (int a = 0; a < 27; ++a) {
+            const int32_t nd = ctx->conn[e * 27 + a];
+            if (stamp[nd] == (int32_t)c) continue;
+            stamp[nd] = (int32_t)c;
+            if (P.node_row[nd] >= 0) rows.push_back(P.node_row[nd]);
+          }
+        std::sort(rows.begin() + first, rows.end());
+        G.tp_row_ptr.push_back((int64_t)rows.size());
+      }
+      if (rows.empty()) rows.push_back(0);
+      CU(G.tp_rows.upload(rows, ctx->stream));
+      CU(G.tp_K.ensure((size_t)chunk * 27 * 27 * 9));
+      CU(G.tp_f.ensure((size_t)chunk * 27 * 3));
+      if (!ctx->d_owned_nodes.p) return ctx->fail(MASTB200_ERR_PLAN, "two-pass HEX27 assembly: owned-node list missing");
+      G.tp_chunk = (int32_t)chunk;
+      G.tp_built = true;
+    }
     // the scatter accumulates: R and J start from zero (nonlinear_implicit_assembly.cpp:81-82) -- except that the ordered
     // sweep of the 3-dof system stores the first contribution to every CSR block, so J needs no memset there
     const bool fw = G.first_writer && ctx->nv == 3;
     if (dR) CU(cudaMemsetAsync(dR, 0, n_dof * sizeof(double), ctx->stream));
-    if (dJ && !fw) CU(cudaMemsetAsync(dJ, 0, nnz * sizeof(double), ctx->stream));
+    if (dJ && !fw && !two_pass) CU(cudaMemsetAsync(dJ, 0, nnz * sizeof(double), ctx->stream));
     CU(cudaEventRecord(ctx->ev[1], ctx->stream));
     Hex27Params p;
     p.conn = G.conn.p; p.posmap = G.posmap.p; p.node_row = G.node_row.p; p.nbr_ptr = G.nbr_ptr.p; p.tab = G.tab.p;
@@ -392,7 +428,25 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
     p.alpha_k = m.alpha * (3. * p.lam1 + 2. * p.mu1);
     p.T_const = ctx->T_const; p.T_ref = ctx->T_ref;
     p.nv = ctx->nv; p.thermal = ctx->thermal ? 1 : 0;
-    if (G.ordered) {  // one launch: the plan's order with done flags
+    if (two_pass) {
+      Hex27GatherParams g;
+      g.owned_nodes = ctx->d_owned_nodes.p; g.nbr_ptr = G.nbr_ptr.p; g.n2e_ptr = G.n2e_ptr.p; g.n2e = G.n2e.p;
+      g.conn = G.conn.p; g.posmap = G.posmap.p; g.pos_flagged = G.first_writer ? 1 : 0;
+      g.tmp_K = G.tp_K.p; g.tmp_f = dR ? G.tp_f.p : nullptr; g.J = dJ; g.R = dR;
+      p.J = nullptr; p.R = nullptr;
+      p.tmp_K = G.tp_K.p; p.tmp_f = dR ? G.tp_f.p : nullptr;
+      p.pos_flagged = G.first_writer ? 1 : 0;
+      const int64_t n_chunks = (int64_t)G.tp_row_ptr.size() - 1;
+      for (int64_t c = 0; c < n_chunks; ++c) {
+        p.elems = nullptr; p.elem_first = (int32_t)(c * G.tp_chunk);
+        p.n_elems = (int32_t)std::min<int64_t>(G.tp_chunk, ctx->n_elem - (int64_t)c * G.tp_chunk);
+        CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
+        g.elem_first = p.elem_first; g.n_elems = p.n_elems;
+        g.rows = G.tp_rows.p + G.tp_row_ptr[c]; g.n_rows = G.tp_row_ptr[c + 1] - G.tp_row_ptr[c];
+        CU(launch_hex27_row_gather(g, ctx->stream));
+        ctx->launches += 2;
+      }
+    } else if (G.ordered) {  // one launch: the plan's order with done flags
       if (++G.epoch == INT32_MAX) {
         G.epoch = 1;
         CU(cudaMemsetAsync(G.done.p, 0, size_t(ctx->n_elem) * sizeof(int32_t), ctx->stream));

@@ -134,9 +134,34 @@ struct Hex27Params {
   double* R = nullptr;
   double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1., alpha_k = 0., T_const = 0., T_ref = 0.;
   int32_t nv = 3, thermal = 0;
+  // two-pass assembly (3-dof system): pass 1 = this kernel over a chunk of consecutive element ids [elem_first, elem_first +
+  // n_elems) with elems == nullptr, K_e blocks and f_e STORED element-major (no colours, no read-modify-write); pass 2 = the
+  // row gather below
+  int32_t elem_first = 0;
+  double* tmp_K = nullptr;               // [n_elems][27][27][9] block (a, b) of the chunk's element, constrained as the element is
+  double* tmp_f = nullptr;               // [n_elems][27][3]
 };
 size_t hex27_sweep_smem_bytes();
 cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t stream);
+// pass 2: one warp per owned row touched by the chunk sums the blocks of the row's elements inside the chunk (ascending id)
+// in shared memory and writes the node's three CSR rows as whole runs; rows that earlier chunks have written are added to
+struct Hex27GatherParams {
+  int64_t n_rows = 0;                    // rows of this chunk
+  const int32_t* rows = nullptr;         // owned-row indices
+  const int32_t* owned_nodes = nullptr;
+  const int64_t* nbr_ptr = nullptr;
+  const int64_t* n2e_ptr = nullptr;
+  const int32_t* n2e = nullptr;
+  const int32_t* conn = nullptr;
+  const uint8_t* posmap = nullptr;
+  int32_t pos_flagged = 0;
+  int32_t elem_first = 0, n_elems = 0;
+  const double* tmp_K = nullptr;
+  const double* tmp_f = nullptr;
+  double* J = nullptr;
+  double* R = nullptr;
+};
+cudaError_t launch_hex27_row_gather(const Hex27GatherParams& p, cudaStream_t stream);
 
 
 // ---- QUAD4 Mindlin plate in the xy-plane (sweep_quad4_plate.cu): one thread per (owned node, neighbour) block ------

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
   Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nv = p.nv;
-  const bool wantJ = p.J != nullptr, wantR = p.R != nullptr;
+  const bool wantJ = p.J != nullptr || p.tmp_K != nullptr, wantR = p.R != nullptr || p.tmp_f != nullptr;
   const bool ordered = p.pred_ptr != nullptr;
   const unsigned pos_mask = p.pos_flagged ? 0x7fu : 0xffu;  // bit 7 of a position-map entry: first writer of the block
 
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
   if (tid < 28) { s.wq[tid] = 0.; s.pth[tid] = 0.; }
 
   for (int idx = blockIdx.x; idx < p.n_elems; idx += gridDim.x) {
-    const int e = p.elems[idx];
+    const int e = p.elems ? p.elems[idx] : p.elem_first + idx;
     __syncthreads();  // previous element done with the staging arrays
     if (p.pred_ptr) {  // ordered sweep: wait for the node-sharing elements before this one in the order
       const int pb = p.pred_ptr[idx], pn = p.pred_ptr[idx + 1] - pb;
@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
     const unsigned cma = a_ok ? s.cm[a] : 0u;
     const int64_t rl = a_ok ? (int64_t)s.nnb[a] * nv : 0;
     double* rowJ = (wantJ && rowa >= 0) ? p.J + s.base[a] * nv * nv : nullptr;
+    double* tmpK = (p.tmp_K && rowa >= 0) ? p.tmp_K + ((int64_t)idx * 27 + a) * (27 * 9) : nullptr;  // two-pass: element-major
     double f0 = 0., f1 = 0., f2 = 0., mx = 0.;
     for (int pass = 0; pass < 2; ++pass) {
       double C[9][2][2];
@@ -235,7 +236,18 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
             f2 += K[2][0] * u0 + K[2][1] * u1 + K[2][2] * u2;
           }
           if (a == b) mx = fmax(mx, fmax(K[0][0], fmax(K[1][1], K[2][2])));
-          if (rowJ) {
+          if (tmpK) {  // two-pass assembly: the block is stored, the row gather sums it (same per-element Dirichlet semantics)
+            const unsigned cmb = s.cm[b];
+            double* dst = tmpK + b * 9;
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                double k = K[i][j];
+                if (((cma >> i) | (cmb >> j)) & 1u) k = (a == b && i == j && ((cma >> i) & 1u)) ? 1. : 0.;
+                dst[i * 3 + j] = k;
+              }
+          } else if (rowJ) {
             const unsigned cmb = s.cm[b];
             const unsigned pm = s.pos[a * 27 + b];
             const bool first = p.first_writer && (pm & 0x80u);  // no element before this one has touched the block
@@ -263,10 +275,15 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
       f2 += __shfl_xor_sync(0xffffffffu, f2, 1); f2 += __shfl_xor_sync(0xffffffffu, f2, 2);
       if (kq == 0 && rowa >= 0) {
         if (p.thermal) { f0 += s.fth[a * 3]; f1 += s.fth[a * 3 + 1]; f2 += s.fth[a * 3 + 2]; }
-        double* r = p.R + (int64_t)s.gid[a] * nv;
-        if (!(cma & 1u)) r[0] = ld_acc(r, ordered) + f0;
-        if (!(cma & 2u)) r[1] = ld_acc(r + 1, ordered) + f1;
-        if (!(cma & 4u)) r[2] = ld_acc(r + 2, ordered) + f2;
+        if (p.tmp_f) {
+          double* r = p.tmp_f + ((int64_t)idx * 27 + a) * 3;
+          r[0] = (cma & 1u) ? 0. : f0; r[1] = (cma & 2u) ? 0. : f1; r[2] = (cma & 4u) ? 0. : f2;
+        } else {
+          double* r = p.R + (int64_t)s.gid[a] * nv;
+          if (!(cma & 1u)) r[0] = ld_acc(r, ordered) + f0;
+          if (!(cma & 2u)) r[1] = ld_acc(r + 1, ordered) + f1;
+          if (!(cma & 4u)) r[2] = ld_acc(r + 2, ordered) + f2;
+        }
       }
     }
     if (nv == 6 && wantJ && tid < 27 && s.row[tid] >= 0) {
@@ -283,7 +300,83 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
   }
 }
 
+// ---- pass 2 of the two-pass assembly: row gather -------------------------------------------------------------------
+// One warp per owned row of the chunk.  The node's blocks are summed in shared memory (<= 125 neighbours x 9 values) over
+// its elements inside the chunk in ascending element id -- the order of the reference's element loop -- from the
+// element-major buffer of pass 1 (243 contiguous doubles per (element, node): coalesced reads), then the three CSR rows
+// leave as whole runs (coalesced 8-byte stores, every CSR value written once per chunk that touches the row).
+constexpr int GW2 = 4;         // warps per CTA
+constexpr int GMAXNB = 128;    // neighbours per row (position map: 7 bits)
+
+__global__ void __launch_bounds__(GW2 * 32) hex27_row_gather_kernel(const Hex27GatherParams p) {
+  __shared__ double acc_all[GW2][GMAXNB * 9];
+  __shared__ uint8_t pos_all[GW2][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ir = (int64_t)blockIdx.x * GW2 + warp;
+  if (ir >= p.n_rows) return;
+  double* acc = acc_all[warp];
+  uint8_t* pos = pos_all[warp];
+  const int r = p.rows[ir];
+  const int n = p.owned_nodes[r];
+  const int64_t nb0 = p.nbr_ptr[r];
+  const int nnb = (int)(p.nbr_ptr[r + 1] - nb0);
+  const unsigned pmask = p.pos_flagged ? 0x7fu : 0xffu;
+  for (int t = lane; t < nnb * 9; t += 32) acc[t] = 0.;
+  double f = 0.;  // lanes 0-2: the node's force components
+  bool first_chunk = true;  // no element of the row lies before the chunk: the row is stored, otherwise added to
+  const int e_end = p.elem_first + p.n_elems;
+  for (int64_t ke = p.n2e_ptr[n]; ke < p.n2e_ptr[n + 1]; ++ke) {
+    const int e = p.n2e[ke];
+    if (e < p.elem_first) { first_chunk = false; continue; }
+    if (e >= e_end) break;
+    __syncwarp();
+    const int nd = lane < 27 ? p.conn[(int64_t)e * 27 + lane] : -1;
+    const int a = __ffs(__ballot_sync(0xffffffffu, nd == n)) - 1;
+    if (lane < 27) pos[lane] = (uint8_t)(p.posmap[((int64_t)e * 27 + a) * 27 + lane] & pmask);
+    __syncwarp();
+    const double* src = p.tmp_K + ((int64_t)(e - p.elem_first) * 27 + a) * (27 * 9);
+    double v[8];  // the eight loads of a lane are issued before the first shared-memory add
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = lane + 32 * u;
+      v[u] = t < 27 * 9 ? __ldcs(src + t) : 0.;  // streamed once
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int t = lane + 32 * u;
+      if (t < 27 * 9) {
+        const int b = (t * 7282) >> 16;  // t / 9 for t < 243
+        acc[pos[b] * 9 + (t - b * 9)] += v[u];
+      }
+    }
+    if (p.R && lane < 3) f += p.tmp_f[((int64_t)(e - p.elem_first) * 27 + a) * 3 + lane];
+  }
+  __syncwarp();
+  if (p.J) {
+    double* row = p.J + 9 * nb0;
+    const int rl = 3 * nnb, total = 9 * nnb;
+    int i = 0, rem = lane;  // output index o = i * rl + rem
+    for (int o = lane; o < total; o += 32) {
+      while (rem >= rl) { rem -= rl; ++i; }
+      const int c = (rem * 43691) >> 17;  // rem / 3 for rem < 384
+      const double v = acc[c * 9 + i * 3 + (rem - 3 * c)];
+      row[o] = first_chunk ? v : row[o] + v;
+      rem += 32;
+    }
+  }
+  if (p.R && lane < 3) {
+    double* d = p.R + (int64_t)n * 3 + lane;
+    *d = first_chunk ? f : *d + f;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_hex27_row_gather(const Hex27GatherParams& p, cudaStream_t stream) {
+  if (p.n_rows <= 0) return cudaSuccess;
+  hex27_row_gather_kernel<<<(unsigned)((p.n_rows + GW2 - 1) / GW2), GW2 * 32, 0, stream>>>(p);
+  return cudaGetLastError();
+}
 
 size_t hex27_sweep_smem_bytes() { return sizeof(Smem27); }
 
