@@ -773,14 +773,14 @@ int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, 
 
 // matrix-free element force of a 3D solid mesh (linear strain) into `out` [n_nodes*nv]: see launch_internal_force
 int run_internal_force(mastb200_context* ctx, const double* V, int mode, const double* dfield, double lam1, double mu1,
-                       double* out, bool constrain_rows = true) {
+                       double* out, bool constrain_rows = true, bool v_is_state = false) {
   int rc;
   StressParams p;
   if ((rc = fill_stress_params(ctx, V, p))) return rc;
   if (!constrain_rows) p.cmask = nullptr;  // ComplianceOutput::evaluate dots the unconstrained element vectors with the state
   // Green-Lagrange strain: the parameter sensitivities of the internal force (modes 1-3) carry F = I + grad u of the state;
   // the tangent product J dX (mode 0 with a perturbation) and the thermoelastic force vector need more than that
-  if (ctx->mat.nonlinear_strain && (mode == 0 || mode == 4))
+  if (ctx->mat.nonlinear_strain && ((mode == 0 && !v_is_state) || mode == 4))
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "tangent products with Green-Lagrange strain are not on the device path");
   p.lam1 = lam1; p.mu1 = mu1;
   p.alpha_k = ctx->mat.alpha * (3. * p.lam1 + 2. * p.mu1);
@@ -800,6 +800,60 @@ int run_internal_force(mastb200_context* ctx, const double* V, int mode, const d
   return MASTB200_OK;
 }
 
+// HEX8 with Green-Lagrange strain on an ijk-numbered (build_cube) mesh, 3-dof system, no thermal load: the tangent comes from
+// the slot kernel's Green-Lagrange variant (sweep_hex8_slots.cu: 54 DMMA per element visit, the slots hold K itself), the
+// residual f_a = sum_q JxW (F S) grad N_a from the matrix-free force kernels of the state (stress_output.cu, mode 0) plus the
+// external loads.  MASTB200_GL_STRUCT=0 keeps the row-owner gather of sweep_hex8_gather.cu (any mesh, thermal, nv = 6).
+bool gl_struct_ok(mastb200_context* ctx) {
+  if (ctx->nv != 3 || ctx->thermal || kStructWarps != 16) return false;
+  if (const char* e = getenv("MASTB200_GL_STRUCT")) if (e[0] == '0') return false;
+  if (ensure_struct_plan(ctx) != MASTB200_OK || !ctx->splan.ok) return false;
+  return (size_t)ctx->max_optin >= hex8_slots_smem_bytes();
+}
+
+int run_gl_struct(mastb200_context* ctx, const double* X, double* R, double* J) {
+  int rc;
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const size_t nnz = (size_t)plan_nnz(ctx);
+  const double* dX = nullptr;
+  double *dR = nullptr, *dJ = nullptr;
+  if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
+  if ((rc = resolve_out(ctx, R, n_dof, ctx->d_R, &dR))) return rc;
+  if ((rc = resolve_out(ctx, J, nnz, ctx->d_J, &dJ))) return rc;
+  const mastb200_material& m = ctx->mat;
+  const double lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu), mu1 = 1. / 2. / (1. + m.nu);
+  const uint8_t* cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+  if (dJ) {
+    const mastb200_context::StructPlan& S = ctx->splan;
+    StructParams sp;
+    sp.units = S.units.p; sp.n_units = S.n_units; sp.counter = ctx->d_tile_counter.p;
+    sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0; sp.nv = 3;
+    sp.nbr_ptr = S.nbr_ptr.p;
+    sp.xyz = ctx->d_xyz.p; sp.X = dX; sp.cmask = cmask; sp.J = dJ; sp.R = nullptr;
+    sp.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;
+    sp.E0 = m.E0; sp.lam1 = lam1; sp.mu1 = mu1; sp.rho_min = m.rho_min; sp.penalty = m.penalty;
+    sp.gl = 1;
+    CU(launch_hex8_slots(sp, std::max(1, std::min(S.n_units, ctx->sm_count)), ctx->stream));
+    ctx->launches++;
+  }
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  ctx->last_struct = true; ctx->splan.last_march = false; ctx->splan.last_slots = true;
+  if (dR) {
+    if ((rc = run_internal_force(ctx, dX, 0, nullptr, lam1, mu1, dR, true, true))) return rc;
+    if ((rc = apply_external_loads(ctx, dR, cmask))) return rc;
+  }
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->timed = true;
+  ctx->last_R = dR;
+  if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
+  if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return MASTB200_OK;
+}
+
 // the common sweep: any of R, J, G may be null
 int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double* G, double* R, double* J) {
   int rc = check_ready(ctx);
@@ -815,7 +869,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   if (ctx->nv == 1) return ctx->fail(MASTB200_ERR_ARG, "HEX8 elasticity needs nv = 3 or 6");
   if (ctx->mat.nonlinear_strain) {  // Green-Lagrange strain: R / J by the row-owner gather, G by the element-parallel kernels
     if (G && !ctx->rho_set) return ctx->fail(MASTB200_ERR_ARG, "density sensitivities need a nodal density field");
-    if ((R || J) && (rc = run_hex8_gather(ctx, X, R, J))) return rc;
+    if ((R || J) && (rc = gl_struct_ok(ctx) ? run_gl_struct(ctx, X, R, J) : run_hex8_gather(ctx, X, R, J))) return rc;
     if (!G) return MASTB200_OK;
     const double* last_R = ctx->last_R;
     rc = run_density_sens(ctx, X, adj, G);

@@ -62,6 +62,7 @@ struct StructParams {
   double* J = nullptr;
   double* R = nullptr;
   int32_t j_aligned32 = 0;               // J is 32-byte aligned: the nv = 6 flush uses 16- and 32-byte stores
+  int32_t gl = 0;                        // slot kernel: Green-Lagrange strain, tangent only (R must be null)
   double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1.;
 };
 size_t hex8_struct_smem_bytes();

@@ -64,6 +64,7 @@ constexpr int SMEM_BYTES = O_MISC + 16;
 static_assert((O_CR / 8) % 16 == 0 && (O_IN0 / 8) % 16 == 8 && (O_IN1 / 8) % 16 == 8, "bank phases of the slot regions");
 static_assert(O_XYZ % 8 == 0 && O_STAGE % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0 && O_FP % 8 == 0, "alignment");
 static_assert(SMEM_BYTES <= 232448, "shared-memory layout exceeds 227 KB");
+static_assert(2 * 8 * 20 <= 4 * 8 * QS, "the Green-Lagrange variant stages two elements in the same per-warp buffer");
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -179,6 +180,31 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
   o[4] = make_double2((Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet, det * E);  // Gauss weights are 1 for the 2x2x2 rule
 }
 
+// ---- slot stores of one element's tiles (lane = (m, q4) holds C[k][bb] for b = 2 q4 + bb) -----------------------------
+__device__ __forceinline__ void store_slots(const LaneK& lk, unsigned smem32, int ecol, int par, const double (&C)[6][2]) {
+  // bottom in-plane pairs join what the element below left for node plane s (region IN[par]); top in-plane pairs open
+  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone.  No per-value predicates: duplicates go to
+  // the trash array, the twelve loads of the adding lanes share one predicate.
+  const unsigned rb = lk.kind == 0 ? O_CR : (((lk.kind == 1) == (par == 0)) ? O_IN0 : O_IN1);
+  const unsigned ar = smem32 + rb + ecol * 8;
+  double old[12];
+#pragma unroll
+  for (int t = 0; t < 12; ++t) old[t] = 0.;
+  asm volatile(
+      "{\n .reg .pred q;\n setp.eq.s32 q, %12, 1;\n"
+      "@q ld.shared.f64 %0, [%13];\n @q ld.shared.f64 %1, [%14];\n @q ld.shared.f64 %2, [%15];\n @q ld.shared.f64 %3, [%16];\n"
+      "@q ld.shared.f64 %4, [%17];\n @q ld.shared.f64 %5, [%18];\n @q ld.shared.f64 %6, [%19];\n @q ld.shared.f64 %7, [%20];\n"
+      "@q ld.shared.f64 %8, [%21];\n @q ld.shared.f64 %9, [%22];\n @q ld.shared.f64 %10, [%23];\n @q ld.shared.f64 %11, [%24];\n}"
+      : "+d"(old[0]), "+d"(old[1]), "+d"(old[2]), "+d"(old[3]), "+d"(old[4]), "+d"(old[5]), "+d"(old[6]), "+d"(old[7]),
+        "+d"(old[8]), "+d"(old[9]), "+d"(old[10]), "+d"(old[11])
+      : "r"(lk.kind), "r"(ar + lk.off[0]), "r"(ar + lk.off[1]), "r"(ar + lk.off[2]), "r"(ar + lk.off[3]), "r"(ar + lk.off[4]),
+        "r"(ar + lk.off[5]), "r"(ar + lk.off[6]), "r"(ar + lk.off[7]), "r"(ar + lk.off[8]), "r"(ar + lk.off[9]),
+        "r"(ar + lk.off[10]), "r"(ar + lk.off[11])
+      : "memory");
+#pragma unroll
+  for (int t = 0; t < 12; ++t) sts64(ar + lk.off[t], old[t] + C[t % 6][t / 6]);
+}
+
 // ---- matrix + slot stores: all 32 lanes on one element -------------------------------------------------------------
 __device__ __forceinline__ void element_phase(const LaneK& lk, unsigned smem32, const double* st, int ecol, int par, int lane) {
   const int q4 = lane & 3;
@@ -206,27 +232,126 @@ __device__ __forceinline__ void element_phase(const LaneK& lk, unsigned smem32, 
     dmma8x8x4(C[4][0], C[4][1], A[0][h], B[2][h]);
     dmma8x8x4(C[5][0], C[5][1], A[1][h], B[2][h]);
   }
-  // bottom in-plane pairs join what the element below left for node plane s (region IN[par]); top in-plane pairs open
-  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone.  No per-value predicates: duplicates go to
-  // the trash array, the twelve loads of the adding lanes share one predicate.
-  const unsigned rb = lk.kind == 0 ? O_CR : (((lk.kind == 1) == (par == 0)) ? O_IN0 : O_IN1);
-  const unsigned ar = smem32 + rb + ecol * 8;
-  double old[12];
+  store_slots(lk, smem32, ecol, par, C);
+}
+
+// ---- Green-Lagrange strain (GL variant): StructuralElement3D::internal_residual with NONLINEAR_STRAIN ------------------
+// (solid_element_3d.cpp:299-409).  With F = I + grad u, g = grad N and the isotropic D the tangent block of a node pair is
+//   K_ab = sum_q JxW E [ lam1 (F g_a)(F g_b)^T + mu1 (F g_b)(F g_a)^T + mu1 (g_a . g_b) F F^T + (g_a . S_1 g_b) I ],
+// S_1 = lam1 tr(E_GL) I + 2 mu1 E_GL (B_a^T D B_b of the reference's sixteen operator products, plus the initial-stress
+// stiffness), i.e. K_ij[a][b] is again a sum of rank-one DMMA products over the quadrature points: 27 products = 54
+// mma.sync.m8n8k4.f64 per element for the six tiles i <= j (K_ji[a][b] = K_ij[b][a]), and the slots then hold K itself.
+constexpr int QSG = 20;  // doubles staged per (element, qp): inv[3][3], w, H[3][3] = grad u, pad
+
+template <bool SIMP>
+__device__ __forceinline__ void geometry_phase_gl(const StructParams& p, const Sm& sm, int s, int base, int q, double* out) {
+  const double xi = (q & 1) ? GP : -GP, eta = (q & 2) ? GP : -GP, zeta = (q & 4) ? GP : -GP;
+  const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
+  double Hr[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Hr[i][r] = sum_m u_m,i dN_m/dxi_r
+  double r = 0.;
 #pragma unroll
-  for (int t = 0; t < 12; ++t) old[t] = 0.;
-  asm volatile(
-      "{\n .reg .pred q;\n setp.eq.s32 q, %12, 1;\n"
-      "@q ld.shared.f64 %0, [%13];\n @q ld.shared.f64 %1, [%14];\n @q ld.shared.f64 %2, [%15];\n @q ld.shared.f64 %3, [%16];\n"
-      "@q ld.shared.f64 %4, [%17];\n @q ld.shared.f64 %5, [%18];\n @q ld.shared.f64 %6, [%19];\n @q ld.shared.f64 %7, [%20];\n"
-      "@q ld.shared.f64 %8, [%21];\n @q ld.shared.f64 %9, [%22];\n @q ld.shared.f64 %10, [%23];\n @q ld.shared.f64 %11, [%24];\n}"
-      : "+d"(old[0]), "+d"(old[1]), "+d"(old[2]), "+d"(old[3]), "+d"(old[4]), "+d"(old[5]), "+d"(old[6]), "+d"(old[7]),
-        "+d"(old[8]), "+d"(old[9]), "+d"(old[10]), "+d"(old[11])
-      : "r"(lk.kind), "r"(ar + lk.off[0]), "r"(ar + lk.off[1]), "r"(ar + lk.off[2]), "r"(ar + lk.off[3]), "r"(ar + lk.off[4]),
-        "r"(ar + lk.off[5]), "r"(ar + lk.off[6]), "r"(ar + lk.off[7]), "r"(ar + lk.off[8]), "r"(ar + lk.off[9]),
-        "r"(ar + lk.off[10]), "r"(ar + lk.off[11])
-      : "memory");
+  for (int m = 0; m < 8; ++m) {
+    const double fx = (m & 1) ? xp : xm, fy = (m & 2) ? yp : ym, fz = (m & 4) ? zp : zm;
+    const double d0 = ((m & 1) ? 0.125 : -0.125) * fy * fz, d1 = ((m & 2) ? 0.125 : -0.125) * fx * fz,
+                 d2 = ((m & 4) ? 0.125 : -0.125) * fx * fy;
+    const int z = (m & 4) ? s + 1 : s, col = base + ((m >> 1) & 1) * TCX + (m & 1);
+    const double* X = sm.xyz + (z % 3) * 3 * NS + col;
+    const double x0 = X[0], x1 = X[NS], x2 = X[2 * NS];
+    Jm[0][0] = fma(d0, x0, Jm[0][0]); Jm[0][1] = fma(d0, x1, Jm[0][1]); Jm[0][2] = fma(d0, x2, Jm[0][2]);
+    Jm[1][0] = fma(d1, x0, Jm[1][0]); Jm[1][1] = fma(d1, x1, Jm[1][1]); Jm[1][2] = fma(d1, x2, Jm[1][2]);
+    Jm[2][0] = fma(d2, x0, Jm[2][0]); Jm[2][1] = fma(d2, x1, Jm[2][1]); Jm[2][2] = fma(d2, x2, Jm[2][2]);
+    const double* U = sm.u + (z & 3) * 3 * NS + col;
+    const double u0 = U[0], u1 = U[NS], u2 = U[2 * NS];
+    Hr[0][0] = fma(u0, d0, Hr[0][0]); Hr[0][1] = fma(u0, d1, Hr[0][1]); Hr[0][2] = fma(u0, d2, Hr[0][2]);
+    Hr[1][0] = fma(u1, d0, Hr[1][0]); Hr[1][1] = fma(u1, d1, Hr[1][1]); Hr[1][2] = fma(u1, d2, Hr[1][2]);
+    Hr[2][0] = fma(u2, d0, Hr[2][0]); Hr[2][1] = fma(u2, d1, Hr[2][1]); Hr[2][2] = fma(u2, d2, Hr[2][2]);
+    if (SIMP) r = fma(0.125 * fx * fy * fz, sm.rho[(z % 3) * NS + col], r);
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = __drcp_rn(det);
+  double inv[3][3];  // inv[c][r] = d xi_r / d x_c
+  inv[0][0] = c00 * idet; inv[1][0] = c01 * idet; inv[2][0] = c02 * idet;
+  inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+  inv[1][1] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+  inv[2][1] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+  inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+  inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+  inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+  double E = p.E0;
+  if (SIMP) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(r, p.penalty));
 #pragma unroll
-  for (int t = 0; t < 12; ++t) sts64(ar + lk.off[t], old[t] + C[t % 6][t / 6]);
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int rr = 0; rr < 3; ++rr) out[c * 3 + rr] = inv[c][rr];
+  out[9] = det * E;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) out[10 + i * 3 + j] = Hr[i][0] * inv[j][0] + Hr[i][1] * inv[j][1] + Hr[i][2] * inv[j][2];
+  out[19] = 0.;
+}
+
+__device__ __forceinline__ void element_phase_gl(const StructParams& p, const LaneK& lk, unsigned smem32, const double* st, int ecol,
+                                                 int par, int lane) {
+  const int q4 = lane & 3;
+  double C[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { C[k][0] = 0.; C[k][1] = 0.; }
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const double2* s2 = reinterpret_cast<const double2*>(st + (q4 + 4 * h) * QSG);
+    double v[20];
+#pragma unroll
+    for (int t = 0; t < 10; ++t) { const double2 x = s2[t]; v[2 * t] = x.x; v[2 * t + 1] = x.y; }
+    const double w = v[9];
+    const double* H = v + 10;  // H[i * 3 + j] = d u_i / d x_j
+    double g[3], gh[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = v[c * 3] * lk.d0[h] + v[c * 3 + 1] * lk.d1[h] + v[c * 3 + 2] * lk.d2;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) gh[i] = g[i] + (H[i * 3] * g[0] + H[i * 3 + 1] * g[1] + H[i * 3 + 2] * g[2]);  // F g
+    // F F^T and the Green-Lagrange strain E = 1/2 (H + H^T + H^T H), symmetric: index (i, j) -> KK
+    double Bm[6], Eg[6];
+    {
+      const int KI[6] = {0, 1, 2, 0, 0, 1}, KJ[6] = {0, 1, 2, 1, 2, 2};
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int i = KI[k], j = KJ[k];
+        Bm[k] = (i == j ? 1. : 0.) + H[i * 3 + j] + H[j * 3 + i] + (H[i * 3] * H[j * 3] + H[i * 3 + 1] * H[j * 3 + 1] + H[i * 3 + 2] * H[j * 3 + 2]);
+        Eg[k] = 0.5 * (H[i * 3 + j] + H[j * 3 + i] + (H[i] * H[j] + H[3 + i] * H[3 + j] + H[6 + i] * H[6 + j]));
+      }
+    }
+    const double tr = p.lam1 * (Eg[0] + Eg[1] + Eg[2]), m2 = 2. * p.mu1;
+    const double S00 = tr + m2 * Eg[0], S11 = tr + m2 * Eg[1], S22 = tr + m2 * Eg[2], S01 = m2 * Eg[3], S02 = m2 * Eg[4], S12 = m2 * Eg[5];
+    const double Sg[3] = {S00 * g[0] + S01 * g[1] + S02 * g[2], S01 * g[0] + S11 * g[1] + S12 * g[2],
+                          S02 * g[0] + S12 * g[1] + S22 * g[2]};
+    const double wl = w * p.lam1, wm = w * p.mu1, wlm = w * (p.lam1 + p.mu1);
+    // diagonal tiles (i, i): (lam1 + mu1) (F g_a)_i (F g_b)_i + sum_J g_a[J] (mu1 (F F^T)_ii g_b[J] + (S_1 g_b)[J])
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      dmma8x8x4(C[i][0], C[i][1], gh[i], wlm * gh[i]);
+#pragma unroll
+      for (int J = 0; J < 3; ++J) dmma8x8x4(C[i][0], C[i][1], g[J], wm * Bm[i] * g[J] + w * Sg[J]);
+    }
+    // off-diagonal tiles (i < j): lam1 (F g_a)_i (F g_b)_j + mu1 (F g_a)_j (F g_b)_i + mu1 (F F^T)_ij sum_J g_a[J] g_b[J]
+    {
+      const int KI[3] = {0, 0, 1}, KJ[3] = {1, 2, 2};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int i = KI[k], j = KJ[k];
+        dmma8x8x4(C[3 + k][0], C[3 + k][1], gh[i], wl * gh[j]);
+        dmma8x8x4(C[3 + k][0], C[3 + k][1], gh[j], wm * gh[i]);
+        const double wb = wm * Bm[3 + k];
+#pragma unroll
+        for (int J = 0; J < 3; ++J) dmma8x8x4(C[3 + k][0], C[3 + k][1], g[J], wb * g[J]);
+      }
+    }
+  }
+  store_slots(lk, smem32, ecol, par, C);
 }
 
 // ---- gather: warp = (group of ten owned node columns, dz), lane = (node column, dx); the three dy in turn -------------
@@ -245,7 +370,7 @@ struct Item {        // what the three (dy) items of a lane share
   int e00;
 };
 
-template <int DJ, int DK>
+template <int DJ, int DK, bool KMODE>
 __device__ __forceinline__ void gather_item(const StructParams& p, const Sm& sm, unsigned smem32, const StructUnit& u, int s,
                                             const Item& it, int64_t plane_nodes, double& f0, double& f1, double& f2) {
   const int pl = DK < 0 ? s + 1 : s;  // node plane of the item's row
@@ -300,14 +425,16 @@ __device__ __forceinline__ void gather_item(const StructParams& p, const Sm& sm,
     }
 #undef MASTB200_CR_CORNER
   }
-  // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped
+  // the block holds S_(row,nbr) or its transpose: K = lam*S + mu*S^T + mu*tr(S)*I either way, with lam/mu swapped;
+  // KMODE (Green-Lagrange variant): the slots hold the tangent blocks themselves
   const double l1 = DK < 0 ? p.mu1 : p.lam1, l2 = DK < 0 ? p.lam1 : p.mu1;
   const double trm = p.mu1 * (S[0] + S[4] + S[8]);
   double K[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) K[i][j] = l1 * S[i * 3 + j] + l2 * S[j * 3 + i] + (i == j ? trm : 0.);
+    for (int j = 0; j < 3; ++j)
+      K[i][j] = KMODE ? (DK < 0 ? S[j * 3 + i] : S[i * 3 + j]) : l1 * S[i * 3 + j] + l2 * S[j * 3 + i] + (i == j ? trm : 0.);
   const int slotA = it.ly * TCX + it.lx, slotB = slotA + DJ * TCX + di;
   if (p.R) {  // internal force of linear elasticity: f_a += K_ab u_b (unconstrained element matrices)
     const double* U = sm.u + ((pl + DK) & 3) * 3 * NS + slotB;
@@ -351,7 +478,7 @@ __device__ __forceinline__ void gather_item(const StructParams& p, const Sm& sm,
   }
 }
 
-template <int DK>
+template <int DK, bool KMODE>
 __device__ __forceinline__ void gather_dz(const StructParams& p, const Sm& sm, unsigned smem32, const StructUnit& u, int s,
                                           int n_own, int group, int64_t plane_nodes, int lane) {
   const int l3 = (lane * 11) >> 5;  // lane / 3
@@ -369,9 +496,9 @@ __device__ __forceinline__ void gather_dz(const StructParams& p, const Sm& sm, u
   it.vx1 = it.di >= 0 && it.lx < u.nex;
   it.e00 = (it.ly - 1) * 8 + it.lx - 1;
   double f0 = 0., f1 = 0., f2 = 0.;
-  gather_item<0, DK>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
-  gather_item<-1, DK>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
-  gather_item<1, DK>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
+  gather_item<0, DK, KMODE>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
+  gather_item<-1, DK, KMODE>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
+  gather_item<1, DK, KMODE>(p, sm, smem32, u, s, it, plane_nodes, f0, f1, f2);
   if (p.R) {
     // fixed order over the triple: (dx = -1) + (dx = 0), then + (dx = +1); the lead lane keeps the dz partial of the node
     const double a0 = __shfl_down_sync(0xffffffffu, f0, 1), a1 = __shfl_down_sync(0xffffffffu, f1, 1), a2 = __shfl_down_sync(0xffffffffu, f2, 1);
@@ -383,7 +510,7 @@ __device__ __forceinline__ void gather_dz(const StructParams& p, const Sm& sm, u
   }
 }
 
-template <bool SIMP>
+template <bool SIMP, bool GL>
 __global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Sm sm;
@@ -472,25 +599,44 @@ __global__ void __launch_bounds__(ST, 1) hex8_slots_kernel(const StructParams p)
       }
       if (s < p.nz) {
         // ---- element phase: the warp's 2x2 block of elements of plane s ----
-        {
-          const int el = lane >> 3, q = lane & 7;
-          const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
-          if (lex < u.nex && ley < u.ney) geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
-        }
-        __syncwarp();
+        if (!GL) {
+          {
+            const int el = lane >> 3, q = lane & 7;
+            const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
+            if (lex < u.nex && ley < u.ney) geometry_phase<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS);
+          }
+          __syncwarp();
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
-          if (lex < u.nex && ley < u.ney) element_phase(lk, smem32, my_stage + c * 8 * QS, ley * 8 + lex, s & 1, lane);
+          for (int c = 0; c < 4; ++c) {
+            const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+            if (lex < u.nex && ley < u.ney) element_phase(lk, smem32, my_stage + c * 8 * QS, ley * 8 + lex, s & 1, lane);
+          }
+        } else {
+          // Green-Lagrange: twice as much staged per quadrature point, so two elements at a time (lanes 0-15 stage them)
+#pragma unroll 1
+          for (int round = 0; round < 2; ++round) {
+            if (lane < 16) {
+              const int el = 2 * round + (lane >> 3), q = lane & 7;
+              const int lex = bx2 + (el & 1), ley = by2 + (el >> 1);
+              if (lex < u.nex && ley < u.ney) geometry_phase_gl<SIMP>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QSG);
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int c = 2 * round; c < 2 * round + 2; ++c) {
+              const int lex = bx2 + (c & 1), ley = by2 + (c >> 1);
+              if (lex < u.nex && ley < u.ney) element_phase_gl(p, lk, smem32, my_stage + (c & 1) * 8 * QSG, ley * 8 + lex, s & 1, lane);
+            }
+            __syncwarp();
+          }
         }
       }
       __syncthreads();
       if (warp < 15) {  // warp = (group of ten owned node columns, dz)
         const int group = warp % 5, dzi = warp / 5;
         if (group * 10 < n_own) {
-          if (dzi == 0) gather_dz<-1>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
-          else if (dzi == 1) gather_dz<0>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
-          else gather_dz<1>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
+          if (dzi == 0) gather_dz<-1, GL>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
+          else if (dzi == 1) gather_dz<0, GL>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
+          else gather_dz<1, GL>(p, sm, smem32, u, s, n_own, group, plane_nodes, lane);
         }
       }
       if (cmk_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
@@ -524,7 +670,7 @@ cudaError_t launch_hex8_slots(const StructParams& p, int n_ctas, cudaStream_t st
   if (p.nv != 3 || p.G) return cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(p.counter, 0, sizeof(int32_t), stream);
   if (e != cudaSuccess) return e;
-  static bool attr_set[2][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
+  static bool attr_set[4][64] = {};  // per kernel variant and device: the attribute is set once, not per launch
   int dev = 0;
   if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
   auto go = [&](auto kern, int variant) -> cudaError_t {
@@ -537,7 +683,12 @@ cudaError_t launch_hex8_slots(const StructParams& p, int n_ctas, cudaStream_t st
     kern<<<n_ctas, ST, SMEM_BYTES, stream>>>(p);
     return cudaSuccess;
   };
-  e = p.rho ? go(hex8_slots_kernel<true>, 1) : go(hex8_slots_kernel<false>, 0);
+  if (p.gl) {  // Green-Lagrange strain: tangent only (the residual comes from the matrix-free force kernels)
+    if (p.R) return cudaErrorInvalidValue;
+    e = p.rho ? go(hex8_slots_kernel<true, true>, 3) : go(hex8_slots_kernel<false, true>, 2);
+  } else {
+    e = p.rho ? go(hex8_slots_kernel<true, false>, 1) : go(hex8_slots_kernel<false, false>, 0);
+  }
   if (e != cudaSuccess) return e;
   return cudaGetLastError();
 }

@@ -229,3 +229,60 @@ def test_struct_random_shapes_slabs_and_layouts(built, struct_kernel):
         _close(J, Jo_rows); _close(R[rows], Ro[rows])
         ghost = np.ones(prob.n_dof, bool); ghost[rows] = False
         assert np.all(R[ghost] == 0.0)
+
+
+def test_struct_green_lagrange_tangent_in_the_slot_kernel(built, monkeypatch, struct_kernel):
+    # NONLINEAR_STRAIN on build_cube meshes (3-dof system): tangent from the slot kernel's Green-Lagrange variant, residual
+    # from the matrix-free force kernels; random shapes, owned z-slabs, SIMP, scattered Dirichlet dofs; against the oracle and
+    # against the row-owner gather (MASTB200_GL_STRUCT=0)
+    if struct_kernel != "slots":
+        pytest.skip("one run is enough: the Green-Lagrange path does not depend on the linear kernel's choice")
+    import mast_b200
+    rng = np.random.default_rng(77)
+    for trial, shape in enumerate([(1, 1, 1), (2, 3, 1), (8, 8, 8), (9, 15, 5), (13, 6, 17), (7, 9, 30)]):
+        nx, ny, nz = shape
+        simp = bool(trial % 2)
+        xyz, conn = mesh.build_cube(nx, ny, nz, 0.3 + 0.05 * nx, 0.2 + 0.05 * ny, 0.1 + 0.05 * nz, 8, jitter=0.2)
+        con = (rng.uniform(size=len(xyz) * 3) < 0.08).astype(np.uint8)
+        rho = 0.2 + 0.6 * rng.uniform(size=len(xyz)) if simp else None
+        se, sid = mesh.boundary_sides(nx, ny, nz, 3)
+        prob = O.Problem(O.HEX8, xyz, conn, 3, constrained=con, rho=rho, rho_min=1e-8 if simp else 0.0,
+                         penalty=4.0 if simp else 1.0, nonlinear_strain=1, side_elem=se, side_id=sid,
+                         side_pressure=np.full(len(se), 5e7))
+        X = O.state(prob.n_dof, 1, scale=4e-3)
+        npxy = (nx + 1) * (ny + 1)
+        owned = None
+        if trial >= 3:
+            z0 = int(rng.integers(0, nz + 1)); z1 = int(rng.integers(z0 + 1, nz + 2))
+            owned = np.zeros(prob.n_nodes, np.uint8); owned[z0 * npxy:z1 * npxy] = 1
+        def run():
+            ctx = mast_b200.Context(0)
+            ctx.set_mesh(8, prob.xyz, prob.conn)
+            ctx.set_dof_map(3, prob.constrained, owned)
+            ctx.set_material(**prob.mat)
+            if simp:
+                ctx.set_density(prob.rho)
+            if owned is None:
+                ctx.set_side_pressure(prob.side_elem, prob.side_id, prob.side_pressure)
+            ctx.build_pattern()
+            R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
+            ctx.residual_and_jacobian(X, R, J)
+            return ctx, R, J
+        ctx, R, J = run()
+        assert ctx.stats()["structured"] == 3, shape
+        Ro, Jo = prob.residual_and_jacobian(X)
+        if owned is not None:  # the context above has no pressure load: compare the internal part
+            Ro, _ = O.Problem(O.HEX8, xyz, conn, 3, constrained=con, rho=rho, rho_min=1e-8 if simp else 0.0,
+                              penalty=4.0 if simp else 1.0, nonlinear_strain=1).residual_and_jacobian(X, want_J=False)
+        rows = ctx.get_row_dofs()
+        orp, _ = prob.pattern()
+        Jo_rows = np.concatenate([Jo[orp[r]:orp[r + 1]] for r in rows])
+        _close(J, Jo_rows); _close(R[rows], Ro[rows])
+        J2 = np.full(ctx.nnz, np.nan)
+        ctx.residual_and_jacobian(X, None, J2)
+        assert np.array_equal(J2, J)  # bitwise reproducible, tangent alone
+        monkeypatch.setenv("MASTB200_GL_STRUCT", "0")
+        ctx_g, Rg, Jg = run()
+        monkeypatch.delenv("MASTB200_GL_STRUCT")
+        assert ctx_g.stats()["structured"] == 0
+        _close(J, Jg); _close(R[rows], Rg[rows])
