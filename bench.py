@@ -390,7 +390,8 @@ def main():
                "h2d_bytes_per_step": int(nX.nbytes), "d2h_bytes_per_step": int(nR.nbytes),
                "steps": e_steps, "pinned": pinned,
                "note": "host X in (pinned), host residual out, Jacobian left in HBM for the device linear solve "
-                       "(mastb200_solve); copies inside the timed region; per-rank bytes"}
+                       "(mastb200_solve); copies inside the timed region (the library sweeps z-segment by z-segment and "
+                       "overlaps the planes of X coming in and the rows of R going out with the kernels); per-rank bytes"}
         assert np.isfinite(nR).all() and float(np.abs(nR).max()) > 0
         # the solve that consumes the device Jacobian: a bounded number of PCG iterations of the Newton step J dx = -R
         try:

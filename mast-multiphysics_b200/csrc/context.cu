@@ -579,6 +579,18 @@ int ensure_struct_plan(mastb200_context* ctx) {
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
   std::vector<StructUnit> sorted(units.size());
   for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
+  {  // the same units by z-segment (ascending), cost-sorted inside a segment: the segmented sweep of host-buffer calls
+    std::vector<StructUnit> grouped;
+    S.g_ptr.assign(1, 0); S.g_z0.clear(); S.g_z1.clear();
+    for (int64_t sg = 0; sg < nseg; ++sg) {
+      const int32_t z0 = (int32_t)(oz0 + planes * sg / nseg), z1 = (int32_t)(oz0 + planes * (sg + 1) / nseg);
+      if (z1 <= z0) continue;
+      for (const StructUnit& u : sorted)
+        if (u.z0 == z0 && u.z1 == z1) grouped.push_back(u);
+      S.g_ptr.push_back((int32_t)grouped.size()); S.g_z0.push_back(z0); S.g_z1.push_back(z1);
+    }
+    CU(S.g_units.upload(grouped, ctx->stream));
+  }
   // units of the register-accumulating march (3-dof system): columns of <= 16 x 4 owned nodes cut into z-segments.
   // Opt-in with MASTB200_STRUCT_KERNEL=march: parity-green but slower than the lock-step kernel so far
   // (profiles/r01h_hex8_march_ncu.md).
@@ -634,7 +646,7 @@ int ensure_struct_plan(mastb200_context* ctx) {
   CU(S.units.upload(sorted, ctx->stream));
   CU(S.arr_off.upload(arr_off, ctx->stream));
   CU(S.nbr_ptr.upload(ctx->pat.nbr_ptr, ctx->stream));
-  CU(ctx->d_tile_counter.ensure(4));
+  CU(ctx->d_tile_counter.ensure(40));
   CU(cudaStreamSynchronize(ctx->stream));
   S.nx = (int32_t)nx; S.ny = (int32_t)ny; S.nz = (int32_t)nz; S.oz0 = (int32_t)oz0; S.oz1 = (int32_t)oz1;
   S.n_units = (int32_t)sorted.size();
@@ -916,7 +928,17 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   fill_params(ctx, aux, p);
   const double *dX = nullptr, *dadj = nullptr;
   double *dR = nullptr, *dJ = nullptr, *dG = nullptr;
-  if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
+  // Host X in and / or host R out on the implicit-connectivity path of one rank: the sweep runs z-segment by z-segment, the
+  // planes of X a segment needs arrive on a second stream while the segment before is swept, and a segment's rows of R leave
+  // while the next one is swept (MASTB200_SEG_COPY=0: one copy in, one launch, one copy out).
+  const bool x_host = !is_device_ptr(X), r_host = R && !is_device_ptr(R);
+  bool seg = use_struct && !G && (x_host || r_host) && ctx->neighbours.empty() && !ctx->has_ghosts &&
+             ctx->splan.g_ptr.size() > 2 && ctx->splan.g_ptr.size() <= 33 && !(ctx->splan.march && ctx->nv == 3);
+  if (const char* e = getenv("MASTB200_SEG_COPY")) if (e[0] == '0') seg = false;
+  if (seg && x_host) {
+    CU(ctx->d_X.ensure(n_dof));
+    dX = ctx->d_X.p;
+  } else if ((rc = resolve_in(ctx, X, n_dof, ctx->d_X, &dX))) return rc;
   if ((rc = localize_if_needed(ctx, dX, ctx->nv))) return rc;
   if (G && (rc = resolve_in(ctx, adj, n_dof, ctx->d_adj, &dadj))) return rc;
   if (G && adj != X && (rc = localize_if_needed(ctx, dadj, ctx->nv))) return rc;
@@ -944,7 +966,60 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     sp.E0 = p.E0; sp.lam1 = p.lam1; sp.mu1 = p.mu1; sp.rho_min = p.rho_min; sp.penalty = p.penalty;
     ctx->splan.last_march = S.march && ctx->nv == 3;
     ctx->splan.last_slots = S.slots && ctx->nv == 3 && !fused_G && kStructWarps == 16;
-    if (ctx->splan.last_march) {
+    if (seg) {
+      if (!ctx->seg_ready) {
+        CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : ctx->seg_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->seg_ready = true;
+      }
+      const int ng = (int)S.g_ptr.size() - 1;
+      const int64_t pn = (int64_t)(S.nx + 1) * (S.ny + 1) * ctx->nv;  // doubles per node plane
+      CU(cudaEventRecord(ctx->seg_ev[64], ctx->stream));                // the copy stream starts behind what is queued so far
+      CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->seg_ev[64], 0));
+      if (x_host) {
+        int64_t up = 0;  // node planes of X on the device so far
+        for (int g = 0; g < ng; ++g) {
+          const int64_t hi = std::min<int64_t>((int64_t)S.g_z1[g] + 2, (int64_t)S.nz + 1);  // the segment reads planes < z1 + 2
+          if (hi > up)
+            CU(cudaMemcpyAsync(ctx->d_X.p + up * pn, X + up * pn, size_t(hi - up) * pn * sizeof(double), cudaMemcpyHostToDevice,
+                               ctx->copy_stream));
+          up = std::max(up, hi);
+          CU(cudaEventRecord(ctx->seg_ev[g], ctx->copy_stream));
+        }
+      }
+      for (int g = 0; g < ng; ++g) {
+        if (x_host) CU(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[g], 0));
+        sp.units = S.g_units.p + S.g_ptr[g]; sp.n_units = S.g_ptr[g + 1] - S.g_ptr[g];
+        sp.counter = ctx->d_tile_counter.p + 1 + g;
+        const int ctas = std::max(1, std::min(sp.n_units, ctx->sm_count * (ctx->splan.last_slots ? 1 : kStructCtasPerSm)));
+        if (ctx->splan.last_slots) CU(launch_hex8_slots(sp, ctas, ctx->stream));
+        else CU(launch_hex8_struct(sp, ctas, ctx->stream));
+        ctx->launches++;
+        if (dR) {  // external loads of the segment's nodes, then its rows of R may leave
+          const int64_t pnn = (int64_t)(S.nx + 1) * (S.ny + 1);
+          const int lo = (int)(S.g_z0[g] * pnn), hi = (int)(S.g_z1[g] * pnn);
+          if (!ctx->fl_node.empty()) {
+            FaceLoadPlan fp = face_plan(ctx);
+            fp.node_lo = lo; fp.node_hi = hi;
+            CU(launch_face_loads(fp, ctx->d_xyz.p, nullptr, p.cmask, ctx->nv, dR, nullptr, nullptr, nullptr, ctx->stream));
+            ctx->launches++;
+          }
+          if (!ctx->pl_node.empty()) {
+            CU(launch_point_loads((int)ctx->pl_node.size(), ctx->d_pl_node.p, ctx->d_pl_load.p, p.cmask, ctx->nv, dR, ctx->stream, lo, hi));
+            ctx->launches++;
+          }
+          if (r_host) {
+            CU(cudaEventRecord(ctx->seg_ev[32 + g], ctx->stream));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->seg_ev[32 + g], 0));
+            CU(cudaMemcpyAsync(R + S.g_z0[g] * pn, dR + S.g_z0[g] * pn, size_t(S.g_z1[g] - S.g_z0[g]) * pn * sizeof(double),
+                               cudaMemcpyDeviceToHost, ctx->copy_stream));
+          }
+        }
+      }
+      CU(cudaEventRecord(ctx->seg_ev[65], ctx->copy_stream));  // the context stream is complete when the copies are
+      CU(cudaStreamWaitEvent(ctx->stream, ctx->seg_ev[65], 0));
+      ctx->launches--;  // the common code below counts one launch
+    } else if (ctx->splan.last_march) {
       sp.units = S.m_units.p; sp.n_units = S.m_n_units;
       CU(launch_hex8_march(sp, S.m_n_ctas, ctx->stream));
     } else if (ctx->splan.last_slots) {
@@ -957,11 +1032,11 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   }
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  if ((rc = apply_external_loads(ctx, dR, p.cmask))) return rc;
+  if (!seg && (rc = apply_external_loads(ctx, dR, p.cmask))) return rc;
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;
-  if ((rc = finish_out(ctx, R, n_dof, dR))) return rc;
+  if (!(seg && r_host) && (rc = finish_out(ctx, R, n_dof, dR))) return rc;
   if ((rc = finish_out(ctx, J, nnz, dJ))) return rc;
   if ((rc = finish_out(ctx, G, (size_t)ctx->n_nodes, dG))) return rc;
   // stream-ordered mode: nothing left the device, so the caller's next call (or its own stream work) may queue behind this
@@ -1023,6 +1098,8 @@ int mastb200_destroy(mastb200_context* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->seg_ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   comm_release(ctx);
   delete ctx;
   return MASTB200_OK;

@@ -144,9 +144,16 @@ struct mastb200_context {
     bool march = false;       // the march kernel serves nv = 3
     bool last_march = false;  // ... and ran the last sweep
     bool slots = false;       // the slot kernel (sweep_hex8_slots.cu) serves nv = 3 without fused sensitivities
+    // the same units grouped by z-segment (ascending z, cost-sorted inside a group): a sweep with host buffers runs group by
+    // group so that the copies of X (in) and R (out) overlap the kernels
+    DevBuf<StructUnit> g_units;
+    std::vector<int32_t> g_ptr, g_z0, g_z1;
     bool last_slots = false;
-    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); m_units.release(); }
+    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); m_units.release(); g_units.release(); g_ptr.clear(); g_z0.clear(); g_z1.clear(); }
   } splan;
+  cudaStream_t copy_stream = nullptr;  // second stream + events of the segmented host-buffer sweep (created on first use)
+  cudaEvent_t seg_ev[66] = {};  // [g] planes of X for segment g are in, [32 + g] segment g is swept, [64], [65] fork / join
+  bool seg_ready = false;
   bool async_device = false;  // mastb200_set_async: sweeps whose buffers all live on the device return without a stream sync
   int max_optin = 232448;  // sm_100: 227 KB opt-in shared memory per CTA
   DevBuf<int32_t> d_tile_counter, d_owned_nodes;

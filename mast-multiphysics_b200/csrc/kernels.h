@@ -262,6 +262,7 @@ struct FaceLoadPlan {
   const int32_t* face_nodes = nullptr;  // [n_entries][nfn] nodes of the loaded face (libMesh side ordering)
   const uint8_t* face_k = nullptr;    // [n_entries] which face node this entry's node is
   const double* pressure = nullptr;   // [n_entries]
+  int32_t node_lo = 0, node_hi = 0x7fffffff;  // only loaded nodes in [node_lo, node_hi) are applied (segmented sweeps)
 };
 // R[nv*n+i] -= F_i (unconstrained dofs) if R; dq[nv*n+i] = F_i (unconstrained) if dq;
 // partial[block] = sum_n F_n . u_n if partial (then reduce_partials).
@@ -276,7 +277,7 @@ cudaError_t launch_sumsq_owned(const double* R, const int32_t* owned_nodes, int6
 
 // point loads: R[nv*node[t]+i] -= load[t*nv+i] on unconstrained dofs; field[node[t]] = w[t]; sum over owned nodes of a.b
 cudaError_t launch_point_loads(int n, const int32_t* node, const double* load, const uint8_t* cmask, int nv, double* R,
-                              cudaStream_t stream);
+                               cudaStream_t stream, int node_lo = 0, int node_hi = 0x7fffffff);
 cudaError_t launch_scatter_field(int64_t n, const int32_t* node, const double* w, double* field, cudaStream_t stream);
 cudaError_t launch_dot_owned(const double* a, const double* b, const int32_t* owned_nodes, int64_t n_owned, int nv,
                              double* partial, int n_blocks, cudaStream_t stream);

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(LB) face_load_kernel(FaceLoadPlan fp, const do
   __shared__ double red[LB];
   const int t = blockIdx.x * LB + threadIdx.x;
   double dot = 0.;
-  if (t < fp.n_loaded_nodes) {
+  if (t < fp.n_loaded_nodes && fp.node[t] >= fp.node_lo && fp.node[t] < fp.node_hi) {
     const int n = fp.node[t];
     double F[3] = {0., 0., 0.};
     for (int e = fp.ptr[t]; e < fp.ptr[t + 1]; ++e) {
@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(256) sumsq_owned_kernel(const double* __restri
 // point loads (nonlinear_implicit_assembly.cpp:190-247): R[dofs of node] -= load, constrained dofs untouched; the host has
 // summed the loads of a node in the order they were given and dropped the nodes this rank does not own
 __global__ void __launch_bounds__(128) point_load_kernel(int n, const int32_t* __restrict__ node, const double* __restrict__ load,
-                                                         const uint8_t* __restrict__ cmask, int nv, double* R) {
+                                                         const uint8_t* __restrict__ cmask, int nv, double* R, int node_lo, int node_hi) {
   const int t = blockIdx.x * 128 + threadIdx.x;
   if (t >= n) return;
   const int nd = node[t];
+  if (nd < node_lo || nd >= node_hi) return;
   const unsigned cm = cmask ? cmask[nd] : 0u;
   for (int i = 0; i < nv; ++i)
     if (!((cm >> i) & 1u)) R[(int64_t)nd * nv + i] -= load[(int64_t)t * nv + i];
@@ -213,9 +214,9 @@ cudaError_t launch_sumsq_owned(const double* R, const int32_t* owned_nodes, int6
 }
 
 cudaError_t launch_point_loads(int n, const int32_t* node, const double* load, const uint8_t* cmask, int nv, double* R,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, int node_lo, int node_hi) {
   if (n == 0) return cudaSuccess;
-  point_load_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, node, load, cmask, nv, R);
+  point_load_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, node, load, cmask, nv, R, node_lo, node_hi);
   return cudaGetLastError();
 }
 
