@@ -357,7 +357,158 @@ cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaS
   reduce_pairs_kernel<<<1, 32, 0, stream>>>(partial, n, out);
   return cudaGetLastError();
 }
+// ---- HEX8 specialisation of the element force (modes 0-3): closed-form reference gradients, one (element, qp) per thread,
+// the eight points of an element in adjacent lanes; the point tensors T_q = f (F) sigma J^-T meet in shared memory and lane a
+// leaves the element's nodal force f_a = sum_q T_q dN_a/dxi(q) (q ascending): 24 doubles per element instead of 72 per
+// element going through HBM, and the gather reads three values per (node, element).
+__global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressParams p, int mode, const double* __restrict__ dfield) {
+  __shared__ double Ts[256 * 9];
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool live = t < p.n_elem * 8;
+  const int64_t e = live ? (t >> 3) : 0;
+  const int q = (int)(t & 7);
+  const bool skip = !live || (p.diag_elem && p.diag_elem[e]);
+  const double GPq = 0.57735026918962576451;
+  const double xi = (q & 1) ? GPq : -GPq, eta = (q & 2) ? GPq : -GPq, zeta = (q & 4) ? GPq : -GPq;
+  const double xm = 1. - xi, xp = 1. + xi, ym = 1. - eta, yp = 1. + eta, zm = 1. - zeta, zp = 1. + zeta;
+  int en[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) en[b] = p.conn[e * 8 + b];
+  double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool px = b == 1 || b == 2 || b == 5 || b == 6, py = b == 2 || b == 3 || b == 6 || b == 7, pz = b >= 4;
+    const double fx = px ? xp : xm, fy = py ? yp : ym, fz = pz ? zp : zm;
+    const double d0 = (px ? 0.125 : -0.125) * fy * fz, d1 = (py ? 0.125 : -0.125) * fx * fz, d2 = (pz ? 0.125 : -0.125) * fx * fy;
+    const double* X = p.xyz + (int64_t)en[b] * 3;
+    const double x0 = X[0], x1 = X[1], x2 = X[2];
+    Jm[0][0] = fma(d0, x0, Jm[0][0]); Jm[0][1] = fma(d0, x1, Jm[0][1]); Jm[0][2] = fma(d0, x2, Jm[0][2]);
+    Jm[1][0] = fma(d1, x0, Jm[1][0]); Jm[1][1] = fma(d1, x1, Jm[1][1]); Jm[1][2] = fma(d1, x2, Jm[1][2]);
+    Jm[2][0] = fma(d2, x0, Jm[2][0]); Jm[2][1] = fma(d2, x1, Jm[2][1]); Jm[2][2] = fma(d2, x2, Jm[2][2]);
+  }
+  const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+  const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+  const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+  const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+  const double idet = 1. / det;
+  double inv[3][3];
+  inv[0][0] = c00 * idet; inv[1][0] = c01 * idet; inv[2][0] = c02 * idet;
+  inv[0][1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+  inv[1][1] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+  inv[2][1] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+  inv[0][2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+  inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+  inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+  double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
+  double rho = 0., dr = 0.;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const bool px = b == 1 || b == 2 || b == 5 || b == 6, py = b == 2 || b == 3 || b == 6 || b == 7, pz = b >= 4;
+    const double fx = px ? xp : xm, fy = py ? yp : ym, fz = pz ? zp : zm;
+    const double d0 = (px ? 0.125 : -0.125) * fy * fz, d1 = (py ? 0.125 : -0.125) * fx * fz, d2 = (pz ? 0.125 : -0.125) * fx * fy;
+    const double Nb = 0.125 * fx * fy * fz;
+    double g[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) g[c] = d0 * inv[c][0] + d1 * inv[c][1] + d2 * inv[c][2];
+    const int64_t n = en[b];
+    const double* U = p.X + n * p.nv;
+    const double u0 = U[0], u1 = U[1], u2 = U[2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      H[0][j] = fma(u0, g[j], H[0][j]); H[1][j] = fma(u1, g[j], H[1][j]); H[2][j] = fma(u2, g[j], H[2][j]);
+    }
+    if (p.rho) rho = fma(Nb, p.rho[n], rho);
+    if (mode == 1) dr = fma(Nb, dfield[n], dr);
+  }
+  double E = p.E0;
+  if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rho, p.penalty));
+  double eps[6];
+  if (p.nonlinear) {
+    double Eg[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Eg[i][j] = 0.5 * (H[i][j] + H[j][i] + (H[0][i] * H[0][j] + H[1][i] * H[1][j] + H[2][i] * H[2][j]));
+    eps[0] = Eg[0][0]; eps[1] = Eg[1][1]; eps[2] = Eg[2][2];
+    eps[3] = Eg[0][1] + Eg[1][0]; eps[4] = Eg[1][2] + Eg[2][1]; eps[5] = Eg[0][2] + Eg[2][0];
+  } else {
+    eps[0] = H[0][0]; eps[1] = H[1][1]; eps[2] = H[2][2];
+    eps[3] = H[0][1] + H[1][0]; eps[4] = H[1][2] + H[2][1]; eps[5] = H[0][2] + H[2][0];
+  }
+  const double lam = E * p.lam1, mu = E * p.mu1, tr = eps[0] + eps[1] + eps[2];
+  const double s0 = lam * tr + 2. * mu * eps[0], s1 = lam * tr + 2. * mu * eps[1], s2 = lam * tr + 2. * mu * eps[2];
+  const double s3 = mu * eps[3], s4 = mu * eps[4], s5 = mu * eps[5];
+  double f = det;  // Gauss weights are 1 for the 2x2x2 rule
+  if (mode == 1) f *= p.E0 * (1. - p.rho_min) * p.penalty * pow_pm1(rho, p.penalty - 1.) * dr / E;
+  else if (mode == 2) f /= p.E0;
+  if (skip) f = 0.;
+  double S[3][3] = {{s0, s3, s5}, {s3, s1, s4}, {s5, s4, s2}};
+  if (p.nonlinear) {
+    double FS[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) FS[k][c] = S[k][c] + (H[k][0] * S[0][c] + H[k][1] * S[1][c] + H[k][2] * S[2][c]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) S[k][c] = FS[k][c];
+  }
+  double* T = Ts + threadIdx.x * 9;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) T[k * 3 + r] = f * (S[k][0] * inv[0][r] + S[k][1] * inv[1][r] + S[k][2] * inv[2][r]);
+  __syncthreads();
+  // lane a of the element's eight: f_a[k] = sum_q sum_r T_q[k][r] dN_a/dxi_r(q)
+  const int a = q;
+  const bool ax = a == 1 || a == 2 || a == 5 || a == 6, ay = a == 2 || a == 3 || a == 6 || a == 7, az = a >= 4;
+  double o[3] = {0., 0., 0.};
+#pragma unroll
+  for (int qq = 0; qq < 8; ++qq) {
+    const double* Tq = Ts + ((threadIdx.x & ~7) | qq) * 9;
+    const double fx = ((qq & 1) != 0) == ax ? 1. + GPq : 1. - GPq;
+    const double fy = ((qq & 2) != 0) == ay ? 1. + GPq : 1. - GPq;
+    const double fz = ((qq & 4) != 0) == az ? 1. + GPq : 1. - GPq;
+    const double d0 = (ax ? 0.125 : -0.125) * fy * fz, d1 = (ay ? 0.125 : -0.125) * fx * fz, d2 = (az ? 0.125 : -0.125) * fx * fy;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) o[k] += Tq[k * 3] * d0 + Tq[k * 3 + 1] * d1 + Tq[k * 3 + 2] * d2;
+  }
+  if (live) {
+    double* dst = p.scratch + e * 24 + a * 3;
+    dst[0] = o[0]; dst[1] = o[1]; dst[2] = o[2];
+  }
+}
+
+// row-owner gather of the nodal element forces: adjacent elements in ascending id, constrained dofs zeroed
+__global__ void __launch_bounds__(TB) force_hex8_gather_kernel(const StressParams p) {
+  const int64_t r = (int64_t)blockIdx.x * TB + threadIdx.x;
+  if (r >= p.n_owned) return;
+  const int n = p.owned_nodes[r];
+  const unsigned cm = p.cmask ? p.cmask[n] : 0u;
+  double acc[3] = {0., 0., 0.};
+  for (int64_t ke = p.n2e_ptr[n]; ke < p.n2e_ptr[n + 1]; ++ke) {
+    const int64_t e = p.n2e[ke];
+    const int32_t* en = p.conn + e * 8;
+    int a = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+      if (en[b] == n) a = b;
+    const double* o = p.scratch + e * 24 + a * 3;
+    acc[0] += o[0]; acc[1] += o[1]; acc[2] += o[2];
+  }
+  for (int k = 0; k < p.nv; ++k) p.dq_dX[(int64_t)n * p.nv + k] = (k < 3 && !((cm >> k) & 1u)) ? acc[k] : 0.;
+}
+
 cudaError_t launch_internal_force(const StressParams& p, int mode, const double* dfield, cudaStream_t stream) {
+  if (p.nn == 8 && mode != 4) {  // HEX8: nodal element forces (24 doubles per element) instead of point tensors
+    force_hex8_nodal_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(p, mode, dfield);
+    cudaError_t e8 = cudaGetLastError();
+    if (e8 != cudaSuccess) return e8;
+    force_hex8_gather_kernel<<<(int)((p.n_owned + TB - 1) / TB), TB, 0, stream>>>(p);
+    return cudaGetLastError();
+  }
   force_qp_kernel<<<stress_blocks(p.n_elem, p.nq), TB, 0, stream>>>(p, mode, dfield);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
