@@ -903,7 +903,9 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   int aux = (G || ctx->rho_set || ctx->thermal || ctx->nv == 6) ? 1 : 0;
   // build_cube-numbered meshes: the implicit-connectivity kernel serves the 3-dof R/J sweep (constant or SIMP modulus);
   // sensitivities requested together with R/J then come from the element-parallel kernels right after it
-  const bool struct_ok_cfg = (ctx->nv == 3 || ctx->nv == 6) && !ctx->thermal && (R || J);
+  // (the TEMPERATURE load of linear strain changes the residual only: the structured kernel still serves R / J and the load's
+  // force vector, B^T D alpha dT from the matrix-free force kernels, is subtracted afterwards)
+  const bool struct_ok_cfg = (ctx->nv == 3 || ctx->nv == 6) && !(ctx->thermal && G) && (R || J);
   if (struct_ok_cfg && (rc = ensure_struct_plan(ctx))) return rc;
   const bool use_struct = struct_ok_cfg && ctx->splan.ok;
   if (use_struct) aux = 0;
@@ -933,7 +935,8 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   // while the next one is swept (MASTB200_SEG_COPY=0: one copy in, one launch, one copy out).
   const bool x_host = !is_device_ptr(X), r_host = R && !is_device_ptr(R);
   bool seg = use_struct && !G && (x_host || r_host) && ctx->neighbours.empty() && !ctx->has_ghosts &&
-             ctx->splan.g_ptr.size() > 2 && ctx->splan.g_ptr.size() <= 33 && !(ctx->splan.march && ctx->nv == 3);
+             ctx->splan.g_ptr.size() > 2 && ctx->splan.g_ptr.size() <= 33 && !(ctx->splan.march && ctx->nv == 3) &&
+             !(ctx->thermal && R);
   if (const char* e = getenv("MASTB200_SEG_COPY")) if (e[0] == '0') seg = false;
   if (seg && x_host) {
     CU(ctx->d_X.ensure(n_dof));
@@ -1033,6 +1036,12 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
   ctx->launches++;
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   if (!seg && (rc = apply_external_loads(ctx, dR, p.cmask))) return rc;
+  if (use_struct && ctx->thermal && dR) {  // f -= JxW B^T (D alpha dT) (solid_element_3d.cpp:950-1089, linear strain)
+    CU(ctx->d_vec2.ensure(n_dof));
+    if ((rc = run_internal_force(ctx, dX, 4, nullptr, p.lam1, p.mu1, ctx->d_vec2.p))) return rc;
+    CU(launch_sub_vector((int64_t)n_dof, dR, ctx->d_vec2.p, ctx->stream));
+    ctx->launches++;
+  }
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;
   ctx->last_R = dR;

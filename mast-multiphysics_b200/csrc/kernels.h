@@ -276,6 +276,7 @@ cudaError_t launch_sumsq_owned(const double* R, const int32_t* owned_nodes, int6
                                int n_blocks, cudaStream_t stream);
 
 // point loads: R[nv*node[t]+i] -= load[t*nv+i] on unconstrained dofs; field[node[t]] = w[t]; sum over owned nodes of a.b
+cudaError_t launch_sub_vector(int64_t n, double* a, const double* b, cudaStream_t stream);  // a -= b
 cudaError_t launch_point_loads(int n, const int32_t* node, const double* load, const uint8_t* cmask, int nv, double* R,
                                cudaStream_t stream, int node_lo = 0, int node_hi = 0x7fffffff);
 cudaError_t launch_scatter_field(int64_t n, const int32_t* node, const double* w, double* field, cudaStream_t stream);

@@ -220,6 +220,16 @@ cudaError_t launch_point_loads(int n, const int32_t* node, const double* load, c
   return cudaGetLastError();
 }
 
+__global__ void __launch_bounds__(256) sub_vector_kernel(int64_t n, double* __restrict__ a, const double* __restrict__ b) {
+  const int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (t < n) a[t] -= b[t];
+}
+cudaError_t launch_sub_vector(int64_t n, double* a, const double* b, cudaStream_t stream) {
+  if (n == 0) return cudaSuccess;
+  sub_vector_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, a, b);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_scatter_field(int64_t n, const int32_t* node, const double* w, double* field, cudaStream_t stream) {
   if (n == 0) return cudaSuccess;
   scatter_field_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(n, node, w, field);

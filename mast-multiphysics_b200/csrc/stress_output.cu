@@ -357,7 +357,7 @@ cudaError_t launch_reduce_pairs(const double* partial, int n, double* out, cudaS
   reduce_pairs_kernel<<<1, 32, 0, stream>>>(partial, n, out);
   return cudaGetLastError();
 }
-// ---- HEX8 specialisation of the element force (modes 0-3): closed-form reference gradients, one (element, qp) per thread,
+// ---- HEX8 specialisation of the element force (modes 0-4): closed-form reference gradients, one (element, qp) per thread,
 // the eight points of an element in adjacent lanes; the point tensors T_q = f (F) sigma J^-T meet in shared memory and lane a
 // leaves the element's nodal force f_a = sum_q T_q dN_a/dxi(q) (q ascending): 24 doubles per element instead of 72 per
 // element going through HBM, and the gather reads three values per (node, element).
@@ -400,7 +400,7 @@ __global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressPa
   inv[1][2] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
   inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
   double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
-  double rho = 0., dr = 0.;
+  double rho = 0., dr = 0., tq = 0.;
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     const bool px = b == 1 || b == 2 || b == 5 || b == 6, py = b == 2 || b == 3 || b == 6 || b == 7, pz = b >= 4;
@@ -419,6 +419,7 @@ __global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressPa
     }
     if (p.rho) rho = fma(Nb, p.rho[n], rho);
     if (mode == 1) dr = fma(Nb, dfield[n], dr);
+    if (mode == 4 && p.temperature) tq = fma(Nb, p.temperature[n], tq);
   }
   double E = p.E0;
   if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rho, p.penalty));
@@ -444,7 +445,13 @@ __global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressPa
   else if (mode == 2) f /= p.E0;
   if (skip) f = 0.;
   double S[3][3] = {{s0, s3, s5}, {s3, s1, s4}, {s5, s4, s2}};
-  if (p.nonlinear) {
+  if (mode == 4) {  // the TEMPERATURE volume load as a force vector: sigma = E alpha_k (T - T_ref) I (linear strain)
+    const double st = E * p.alpha_k * ((p.temperature ? tq : p.T_const) - p.T_ref);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) S[k][c] = k == c ? st : 0.;
+  } else if (p.nonlinear) {
     double FS[3][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(TB) force_hex8_gather_kernel(const StressParam
 }
 
 cudaError_t launch_internal_force(const StressParams& p, int mode, const double* dfield, cudaStream_t stream) {
-  if (p.nn == 8 && mode != 4) {  // HEX8: nodal element forces (24 doubles per element) instead of point tensors
+  if (p.nn == 8) {  // HEX8: nodal element forces (24 doubles per element) instead of point tensors
     force_hex8_nodal_kernel<<<(int)((p.n_elem * 8 + 255) / 256), 256, 0, stream>>>(p, mode, dfield);
     cudaError_t e8 = cudaGetLastError();
     if (e8 != cudaSuccess) return e8;

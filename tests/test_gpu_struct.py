@@ -286,3 +286,26 @@ def test_struct_green_lagrange_tangent_in_the_slot_kernel(built, monkeypatch, st
         monkeypatch.delenv("MASTB200_GL_STRUCT")
         assert ctx_g.stats()["structured"] == 0
         _close(J, Jg); _close(R[rows], Rg[rows])
+
+
+def test_struct_thermoelastic_load(built, monkeypatch, struct_kernel):
+    # TEMPERATURE volume load with linear strain (solid_element_3d.cpp:950-1089): the structured kernel serves R / J, the load's
+    # force vector comes from the matrix-free force kernels; nodal and constant temperature, SIMP, nv = 3 / 6
+    rng = np.random.default_rng(4)
+    for nv, simp, const_T in ((3, True, False), (6, False, True), (3, False, False)):
+        kw = dict(alpha=1.5e-5, thermal=1, ref_temperature=300.0)
+        if const_T:
+            kw["temperature_const"] = 345.0
+        else:
+            kw["temperature"] = 300 + 50 * rng.uniform(0, 1, 12 * 8 * 10)
+        prob = O.cantilever(11, 7, 9, nv=nv, jitter=0.2, simp=simp, **kw)
+        X = O.state(prob.n_dof, 1)
+        ctx = prob.make_context(0)
+        R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
+        ctx.residual_and_jacobian(X, R, J)
+        assert _is_struct(ctx, struct_kernel, nv)
+        Ro, Jo = prob.residual_and_jacobian(X)
+        _close(R, Ro); _close(J, Jo)
+        R2 = np.full(prob.n_dof, np.nan)
+        ctx.residual_and_jacobian(X, R2, None)
+        assert np.array_equal(R2, R)
