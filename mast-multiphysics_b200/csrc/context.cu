@@ -436,11 +436,14 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
       p.J = nullptr; p.R = nullptr;
       p.tmp_K = G.tp_K.p; p.tmp_f = dR ? G.tp_f.p : nullptr;
       p.pos_flagged = G.first_writer ? 1 : 0;
+      bool h27_sym = true;  // MASTB200_H27_SYM=0: pass 1 contracts all sixteen tile pairs (the colour kernel's tiling)
+      if (const char* es = getenv("MASTB200_H27_SYM")) if (es[0] == '0') h27_sym = false;
       const int64_t n_chunks = (int64_t)G.tp_row_ptr.size() - 1;
       for (int64_t c = 0; c < n_chunks; ++c) {
         p.elems = nullptr; p.elem_first = (int32_t)(c * G.tp_chunk);
         p.n_elems = (int32_t)std::min<int64_t>(G.tp_chunk, ctx->n_elem - (int64_t)c * G.tp_chunk);
-        CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
+        if (h27_sym) CU(launch_hex27_sym_pass1(p, ctx->sm_count, ctx->stream));
+        else CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
         g.elem_first = p.elem_first; g.n_elems = p.n_elems;
         g.rows = G.tp_rows.p + G.tp_row_ptr[c]; g.n_rows = G.tp_row_ptr[c + 1] - G.tp_row_ptr[c];
         CU(launch_hex27_row_gather(g, ctx->stream));

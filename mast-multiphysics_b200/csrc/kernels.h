@@ -163,6 +163,8 @@ struct Hex27GatherParams {
   double* R = nullptr;
 };
 cudaError_t launch_hex27_row_gather(const Hex27GatherParams& p, cudaStream_t stream);
+// pass 1 with the symmetric half of the tile pairs (630 instead of 1008 DMMA per element; 3-dof system, no diagonal elements)
+cudaError_t launch_hex27_sym_pass1(const Hex27Params& p, int sm_count, cudaStream_t stream);
 
 
 // ---- QUAD4 Mindlin plate in the xy-plane (sweep_quad4_plate.cu): one thread per (owned node, neighbour) block ------

@@ -300,6 +300,188 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
   }
 }
 
+// ---- pass 1 of the two-pass assembly with the symmetric half of the contraction ---------------------------------------
+// K_ba = K_ab^T element-wise, so only the ten tile pairs (row tile <= column tile) of the 4 x 4 tile grid are contracted: 630
+// DMMA per element instead of 1008, five warps with two tile pairs each; a lane stores its block (a, b) and, off the tile
+// diagonal, the mirrored block (b, a).  The element force is not K u any more but what the reference computes,
+// f_a = sum_q JxW B_a^T sigma_q (solid_element_3d.cpp:289-297): stress per point, then one thread per (node, component).
+// 3-dof system, no diagonal elements (the host keeps the other kernel for those).
+constexpr int TB5 = 160;
+
+__global__ void __launch_bounds__(TB5, 4) hex27_sym_pass1_kernel(const Hex27Params p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool wantR = p.tmp_f != nullptr;
+  const double* __restrict__ tabN = p.tab;             // [q][b]
+  const double* __restrict__ tabD = p.tab + 27 * 27;   // [q][b][r]
+  if (tid < 27) s.tabW[tid] = p.tab[27 * 27 * 4 + tid];
+  for (int k = tid; k < 3 * GSZ; k += TB5) (&s.g[0][0])[k] = 0.;
+  if (tid < 28) { s.wq[tid] = 0.; s.pth[tid] = 0.; }
+
+  for (int idx = blockIdx.x; idx < p.n_elems; idx += gridDim.x) {
+    const int e = p.elem_first + idx;
+    __syncthreads();  // previous element done with the staging arrays
+    if (tid < 27) {
+      const int n = p.conn[(int64_t)e * 27 + tid];
+      s.gid[tid] = n;
+      s.row[tid] = p.node_row[n];
+      s.cm[tid] = p.cmask ? p.cmask[n] : 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        s.xs[tid * 3 + c] = p.xyz[(int64_t)n * 3 + c];
+        s.us[tid * 3 + c] = p.X[(int64_t)n * 3 + c];
+      }
+      s.rho[tid] = p.rho ? p.rho[n] : 1.;
+      s.T[tid] = p.temperature ? p.temperature[n] : p.T_const;
+    }
+    __syncthreads();
+    // ---- phase 1: geometry at the quadrature points ----
+    if (tid < 27) {
+      const int q = tid;
+      double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
+      double rq = 0., tq = 0.;
+      for (int b = 0; b < 27; ++b) {
+        const double* d = tabD + (q * 27 + b) * 3;
+        const double x0 = s.xs[b * 3], x1 = s.xs[b * 3 + 1], x2 = s.xs[b * 3 + 2];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          Jm[r][0] = fma(d[r], x0, Jm[r][0]); Jm[r][1] = fma(d[r], x1, Jm[r][1]); Jm[r][2] = fma(d[r], x2, Jm[r][2]);
+        }
+        const double N = __ldg(tabN + q * 27 + b);
+        rq = fma(N, s.rho[b], rq);
+        tq = fma(N, s.T[b], tq);
+      }
+      const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
+      const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
+      const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
+      const double det = Jm[0][0] * c00 + Jm[0][1] * c01 + Jm[0][2] * c02;
+      const double idet = 1. / det;
+      double* inv = s.inv + q * 9;
+      inv[0] = c00 * idet; inv[3] = c01 * idet; inv[6] = c02 * idet;
+      inv[1] = (Jm[0][2] * Jm[2][1] - Jm[0][1] * Jm[2][2]) * idet;
+      inv[4] = (Jm[0][0] * Jm[2][2] - Jm[0][2] * Jm[2][0]) * idet;
+      inv[7] = (Jm[0][1] * Jm[2][0] - Jm[0][0] * Jm[2][1]) * idet;
+      inv[2] = (Jm[0][1] * Jm[1][2] - Jm[0][2] * Jm[1][1]) * idet;
+      inv[5] = (Jm[0][2] * Jm[1][0] - Jm[0][0] * Jm[1][2]) * idet;
+      inv[8] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
+      const double JxW = det * s.tabW[q];
+      double E = p.E0;
+      if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rq, p.penalty));  // example_6.cpp:100-137
+      s.wq[q] = JxW * E;
+      s.pth[q] = p.thermal ? -(JxW * E) * p.alpha_k * (tq - p.T_ref) : 0.;  // f -= JxW B^T (D alpha dT)
+    }
+    __syncthreads();
+    // ---- phase 2: physical gradients g_i[q][a] ----
+    for (int k = tid; k < 27 * 27; k += TB5) {
+      const int q = k / 27, a = k - q * 27;
+      const double* d = tabD + k * 3;
+      const double* inv = s.inv + q * 9;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) s.g[c][q * QSTR + a] = d[0] * inv[c * 3] + d[1] * inv[c * 3 + 1] + d[2] * inv[c * 3 + 2];
+    }
+    __syncthreads();
+    // ---- phase 2b: stress per point (w_q E-scaled; the thermal part rides on the diagonal), into the J^-1 storage ----
+    if (wantR && tid < 27) {
+      const int q = tid;
+      double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // H[i][j] = d u_i / d x_j
+      for (int b = 0; b < 27; ++b) {
+        const double u0 = s.us[b * 3], u1 = s.us[b * 3 + 1], u2 = s.us[b * 3 + 2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const double gj = s.g[j][q * QSTR + b];
+          H[0][j] = fma(u0, gj, H[0][j]); H[1][j] = fma(u1, gj, H[1][j]); H[2][j] = fma(u2, gj, H[2][j]);
+        }
+      }
+      const double w = s.wq[q], tr = p.lam1 * (H[0][0] + H[1][1] + H[2][2]), m2 = 2. * p.mu1;
+      double* sg = s.inv + q * 9;  // xx, yy, zz, xy, yz, zx
+      sg[0] = w * (tr + m2 * H[0][0]) + s.pth[q]; sg[1] = w * (tr + m2 * H[1][1]) + s.pth[q]; sg[2] = w * (tr + m2 * H[2][2]) + s.pth[q];
+      sg[3] = w * p.mu1 * (H[0][1] + H[1][0]); sg[4] = w * p.mu1 * (H[1][2] + H[2][1]); sg[5] = w * p.mu1 * (H[0][2] + H[2][0]);
+    }
+    __syncthreads();
+    if (wantR && tid < 81) {  // f_a[i] = sum_q sum_j sigma_q[i][j] g_j[q][a]
+      const int a = tid / 3, i = tid - a * 3;
+      double f = 0.;
+      for (int q = 0; q < 27; ++q) {
+        const double* sg = s.inv + q * 9;
+        const double g0 = s.g[0][q * QSTR + a], g1 = s.g[1][q * QSTR + a], g2 = s.g[2][q * QSTR + a];
+        const double r0 = i == 0 ? sg[0] : (i == 1 ? sg[3] : sg[5]);
+        const double r1 = i == 0 ? sg[3] : (i == 1 ? sg[1] : sg[4]);
+        const double r2 = i == 0 ? sg[5] : (i == 1 ? sg[4] : sg[2]);
+        f += r0 * g0 + r1 * g1 + r2 * g2;
+      }
+      if (s.row[a] >= 0) p.tmp_f[((int64_t)idx * 27 + a) * 3 + i] = ((s.cm[a] >> i) & 1u) ? 0. : f;
+    }
+    if (!p.tmp_K) continue;
+
+    // ---- phases 3 + 4: two tile pairs per warp ----
+    const int al = lane >> 2, kq = lane & 3;
+#pragma unroll 1
+    for (int pi = 0; pi < 2; ++pi) {
+      // pairs in the order (0,0) (0,1) (0,2) (0,3) (1,1) (1,2) (1,3) (2,2) (2,3) (3,3)
+      const int pr = 2 * warp + pi;
+      const int rt = pr < 4 ? 0 : (pr < 7 ? 1 : (pr < 9 ? 2 : 3));
+      const int ct = pr < 4 ? pr : (pr < 7 ? pr - 3 : (pr < 9 ? pr - 5 : 3));
+      const int a = 8 * rt + al, bc = 8 * ct + al;
+      double C[9][2];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) { C[k][0] = 0.; C[k][1] = 0.; }
+#pragma unroll 1
+      for (int ks = 0; ks < 7; ++ks) {
+        const int q = 4 * ks + kq;
+        const double w = s.wq[q];
+        const double A0 = s.g[0][q * QSTR + a], A1 = s.g[1][q * QSTR + a], A2 = s.g[2][q * QSTR + a];
+        const double B0 = w * s.g[0][q * QSTR + bc], B1 = w * s.g[1][q * QSTR + bc], B2 = w * s.g[2][q * QSTR + bc];
+        dmma8x8x4(C[0][0], C[0][1], A0, B0);
+        dmma8x8x4(C[1][0], C[1][1], A0, B1);
+        dmma8x8x4(C[2][0], C[2][1], A0, B2);
+        dmma8x8x4(C[3][0], C[3][1], A1, B0);
+        dmma8x8x4(C[4][0], C[4][1], A1, B1);
+        dmma8x8x4(C[5][0], C[5][1], A1, B2);
+        dmma8x8x4(C[6][0], C[6][1], A2, B0);
+        dmma8x8x4(C[7][0], C[7][1], A2, B1);
+        dmma8x8x4(C[8][0], C[8][1], A2, B2);
+      }
+      if (a >= 27) continue;
+      const unsigned cma = s.cm[a];
+      const bool own_a = s.row[a] >= 0;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb) {
+        const int b = 8 * ct + 2 * kq + bb;
+        if (b >= 27) continue;
+        double K[3][3];
+        const double trm = p.mu1 * (C[0][bb] + C[4][bb] + C[8][bb]);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) K[i][j] = p.lam1 * C[i * 3 + j][bb] + p.mu1 * C[j * 3 + i][bb] + (i == j ? trm : 0.);
+        const unsigned cmb = s.cm[b];
+        if (cma | cmb) {  // per-element Dirichlet semantics (symmetric: the mirrored block sees the same zeros)
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+              if (((cma >> i) | (cmb >> j)) & 1u) K[i][j] = (a == b && i == j && ((cma >> i) & 1u)) ? 1. : 0.;
+        }
+        if (own_a) {
+          double* dst = p.tmp_K + (((int64_t)idx * 27 + a) * 27 + b) * 9;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dst[i * 3 + j] = K[i][j];
+        }
+        if (rt != ct && s.row[b] >= 0) {  // the mirrored block K_ba = K_ab^T
+          double* dst = p.tmp_K + (((int64_t)idx * 27 + b) * 27 + a) * 9;
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dst[i * 3 + j] = K[j][i];
+        }
+      }
+    }
+  }
+}
+
 // ---- pass 2 of the two-pass assembly: row gather -------------------------------------------------------------------
 // One warp per owned row of the chunk.  The node's blocks are summed in shared memory (<= 125 neighbours x 9 values) over
 // its elements inside the chunk in ascending element id -- the order of the reference's element loop -- from the
@@ -371,6 +553,16 @@ __global__ void __launch_bounds__(GW2 * 32) hex27_row_gather_kernel(const Hex27G
 }
 
 }  // namespace
+
+cudaError_t launch_hex27_sym_pass1(const Hex27Params& p, int sm_count, cudaStream_t stream) {
+  if (p.n_elems <= 0) return cudaSuccess;
+  if (p.nv != 3 || p.diag_elem || p.elems) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(hex27_sym_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem27));
+  if (e != cudaSuccess) return e;
+  const int grid = p.n_elems < 4 * sm_count ? p.n_elems : 4 * sm_count;
+  hex27_sym_pass1_kernel<<<grid, TB5, sizeof(Smem27), stream>>>(p);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_hex27_row_gather(const Hex27GatherParams& p, cudaStream_t stream) {
   if (p.n_rows <= 0) return cudaSuccess;
