@@ -384,7 +384,9 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
       if (const char* ce = getenv("MASTB200_H27_CHUNK")) chunk = std::max<int64_t>(1, atoll(ce));
       chunk = std::min<int64_t>(chunk, ctx->n_elem);
       const Pattern& P = ctx->pat;
-      std::vector<int32_t> rows;
+      std::vector<int32_t> rows, ea;
+      std::vector<int64_t> ea_ptr;
+      std::vector<uint8_t> row_first;
       std::vector<int32_t> stamp((size_t)ctx->n_nodes, -1);
       G.tp_row_ptr.assign(1, 0);
       for (int64_t c0 = 0, c = 0; c0 < ctx->n_elem; c0 += chunk, ++c) {
@@ -399,9 +401,32 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
           }
         std::sort(rows.begin() + first, rows.end());
         G.tp_row_ptr.push_back((int64_t)rows.size());
+        // per row of the chunk: its elements inside the chunk (ascending id) with the node's local index, so that the gather
+        // starts its loads without walking n2e / conn
+        ea_ptr.push_back((int64_t)ea.size());
+        for (size_t k = first; k < rows.size(); ++k) {
+          const int32_t nd = P.owned_nodes[rows[k]];
+          const int64_t q0 = P.n2e_ptr[nd], q1 = P.n2e_ptr[nd + 1];
+          row_first.push_back((q0 == q1 || P.n2e[q0] >= c0) ? 1 : 0);
+          for (int64_t q = q0; q < q1; ++q) {
+            const int64_t e = P.n2e[q];
+            if (e < c0) continue;
+            if (e >= c1) break;
+            int a = 0;
+            for (int b = 0; b < 27; ++b)
+              if (ctx->conn[e * 27 + b] == nd) a = b;
+            ea.push_back((int32_t)((e - c0) * 27 + a));
+          }
+          ea_ptr.push_back((int64_t)ea.size());
+        }
       }
       if (rows.empty()) rows.push_back(0);
+      if (ea.empty()) ea.push_back(0);
+      if (row_first.empty()) row_first.push_back(0);
       CU(G.tp_rows.upload(rows, ctx->stream));
+      CU(G.tp_ea.upload(ea, ctx->stream));
+      CU(G.tp_ea_ptr.upload(ea_ptr, ctx->stream));
+      CU(G.tp_first.upload(row_first, ctx->stream));
       CU(G.tp_K.ensure((size_t)chunk * 27 * 27 * 9));
       CU(G.tp_f.ensure((size_t)chunk * 27 * 3));
       if (!ctx->d_owned_nodes.p) return ctx->fail(MASTB200_ERR_PLAN, "two-pass HEX27 assembly: owned-node list missing");
@@ -446,6 +471,7 @@ int run_generic_sweep(mastb200_context* ctx, const double* X, double* R, double*
         else CU(launch_hex27_sweep(p, ctx->sm_count, ctx->stream));
         g.elem_first = p.elem_first; g.n_elems = p.n_elems;
         g.rows = G.tp_rows.p + G.tp_row_ptr[c]; g.n_rows = G.tp_row_ptr[c + 1] - G.tp_row_ptr[c];
+        g.ea_ptr = G.tp_ea_ptr.p + G.tp_row_ptr[c] + c; g.ea = G.tp_ea.p; g.row_first = G.tp_first.p + G.tp_row_ptr[c];
         CU(launch_hex27_row_gather(g, ctx->stream));
         ctx->launches += 2;
       }

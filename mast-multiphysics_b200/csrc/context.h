@@ -119,14 +119,16 @@ struct mastb200_context {
     bool tp_built = false;
     int32_t tp_chunk = 0;
     std::vector<int64_t> tp_row_ptr;     // per chunk: range in tp_rows
-    DevBuf<int32_t> tp_rows;
+    DevBuf<int32_t> tp_rows, tp_ea;      // rows per chunk; per row the (element - chunk start) * 27 + local node codes
+    DevBuf<int64_t> tp_ea_ptr;           // [rows + chunks]: per chunk, rows + 1 offsets into tp_ea
+    DevBuf<uint8_t> tp_first;
     DevBuf<double> tp_K, tp_f;
     void reset() {
       built = false; color_ptr.clear(); ordered = false; first_writer = false; n_order = 0; epoch = 0;
       order.release(); pred_ptr.release(); pred.release(); done.release();
       conn.release(); n2e.release(); nbr.release(); node_row.release(); color_elems.release(); ent_row.release();
       n2e_ptr.release(); nbr_ptr.release(); diag.release(); posmap.release(); tab.release();
-      tp_built = false; tp_chunk = 0; tp_row_ptr.clear(); tp_rows.release(); tp_K.release(); tp_f.release();
+      tp_built = false; tp_chunk = 0; tp_row_ptr.clear(); tp_rows.release(); tp_ea.release(); tp_ea_ptr.release(); tp_first.release(); tp_K.release(); tp_f.release();
     }
   } gplan;
   // implicit-connectivity sweep of ijk-numbered (build_cube) HEX8 meshes (sweep_hex8_struct.cu)

@@ -149,6 +149,9 @@ cudaError_t launch_hex27_sweep(const Hex27Params& p, int sm_count, cudaStream_t 
 struct Hex27GatherParams {
   int64_t n_rows = 0;                    // rows of this chunk
   const int32_t* rows = nullptr;         // owned-row indices
+  const int64_t* ea_ptr = nullptr;       // [n_rows + 1] range of the row's (element, local node) list
+  const int32_t* ea = nullptr;           // (element - elem_first) * 27 + local node, ascending element id
+  const uint8_t* row_first = nullptr;    // [n_rows] 1: no element of the row lies before the chunk (store), 0: add
   const int32_t* owned_nodes = nullptr;
   const int64_t* nbr_ptr = nullptr;
   const int64_t* n2e_ptr = nullptr;

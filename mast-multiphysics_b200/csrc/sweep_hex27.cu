@@ -30,6 +30,8 @@
 //   phase 4  epilogue per pass: K from S, f_a += K_ab u_b, libMesh's per-element Dirichlet semantics, scatter.
 #include <cuda_runtime.h>
 
+#include <cstdint>
+
 #include "kernels.h"
 
 namespace mastb200 {
@@ -308,6 +310,20 @@ __global__ void __launch_bounds__(TB, MASTB200_H27_CTAS) hex27_sweep_kernel(cons
 // 3-dof system, no diagonal elements (the host keeps the other kernel for those).
 constexpr int TB5 = 160;
 
+// a 3x3 block = 72 contiguous bytes at an 8-byte aligned address: four 16-byte stores and one 8-byte store (three sectors per
+// lane instead of nine partial-sector writes)
+__device__ __forceinline__ void store_block72(double* dst, const double (&v)[9]) {
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    double2* d2 = reinterpret_cast<double2*>(dst);
+    d2[0] = make_double2(v[0], v[1]); d2[1] = make_double2(v[2], v[3]); d2[2] = make_double2(v[4], v[5]); d2[3] = make_double2(v[6], v[7]);
+    dst[8] = v[8];
+  } else {
+    dst[0] = v[0];
+    double2* d2 = reinterpret_cast<double2*>(dst + 1);
+    d2[0] = make_double2(v[1], v[2]); d2[1] = make_double2(v[3], v[4]); d2[2] = make_double2(v[5], v[6]); d2[3] = make_double2(v[7], v[8]);
+  }
+}
+
 __global__ void __launch_bounds__(TB5, 4) hex27_sym_pass1_kernel(const Hex27Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
@@ -336,22 +352,35 @@ __global__ void __launch_bounds__(TB5, 4) hex27_sym_pass1_kernel(const Hex27Para
       s.T[tid] = p.temperature ? p.temperature[n] : p.T_const;
     }
     __syncthreads();
-    // ---- phase 1: geometry at the quadrature points ----
-    if (tid < 27) {
-      const int q = tid;
-      double Jm[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // Jm[r][c] = d x_c / d xi_r
+    // ---- phase 1: geometry at the quadrature points; 81 threads form the rows of J, 27 more interpolate rho and T ----
+    if (tid < 81) {
+      const int q = tid / 3, r = tid - q * 3;
+      double j0 = 0., j1 = 0., j2 = 0.;  // row r of Jm[r][c] = d x_c / d xi_r
+      for (int b = 0; b < 27; ++b) {
+        const double d = tabD[(q * 27 + b) * 3 + r];
+        j0 = fma(d, s.xs[b * 3], j0); j1 = fma(d, s.xs[b * 3 + 1], j1); j2 = fma(d, s.xs[b * 3 + 2], j2);
+      }
+      double* Jr = s.inv + q * 9 + r * 3;
+      Jr[0] = j0; Jr[1] = j1; Jr[2] = j2;
+    } else if (tid < 108) {
+      const int q = tid - 81;
       double rq = 0., tq = 0.;
       for (int b = 0; b < 27; ++b) {
-        const double* d = tabD + (q * 27 + b) * 3;
-        const double x0 = s.xs[b * 3], x1 = s.xs[b * 3 + 1], x2 = s.xs[b * 3 + 2];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-          Jm[r][0] = fma(d[r], x0, Jm[r][0]); Jm[r][1] = fma(d[r], x1, Jm[r][1]); Jm[r][2] = fma(d[r], x2, Jm[r][2]);
-        }
         const double N = __ldg(tabN + q * 27 + b);
         rq = fma(N, s.rho[b], rq);
         tq = fma(N, s.T[b], tq);
       }
+      s.fth[q] = rq; s.fth[27 + q] = tq;
+    }
+    __syncthreads();
+    if (tid < 27) {
+      const int q = tid;
+      double Jm[3][3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) Jm[r][c] = s.inv[q * 9 + r * 3 + c];
+      const double rq = s.fth[q], tq = s.fth[27 + q];
       const double c00 = Jm[1][1] * Jm[2][2] - Jm[1][2] * Jm[2][1];
       const double c01 = Jm[1][2] * Jm[2][0] - Jm[1][0] * Jm[2][2];
       const double c02 = Jm[1][0] * Jm[2][1] - Jm[1][1] * Jm[2][0];
@@ -381,18 +410,26 @@ __global__ void __launch_bounds__(TB5, 4) hex27_sym_pass1_kernel(const Hex27Para
       for (int c = 0; c < 3; ++c) s.g[c][q * QSTR + a] = d[0] * inv[c * 3] + d[1] * inv[c * 3 + 1] + d[2] * inv[c * 3 + 2];
     }
     __syncthreads();
-    // ---- phase 2b: stress per point (w_q E-scaled; the thermal part rides on the diagonal), into the J^-1 storage ----
+    // ---- phase 2b: stress per point (w_q E-scaled; the thermal part rides on the diagonal), into the J^-1 storage:
+    //      81 threads form the rows of H = grad u, 27 turn them into the stress ----
+    if (wantR && tid < 81) {
+      const int q = tid / 3, i = tid - q * 3;
+      double h0 = 0., h1 = 0., h2 = 0.;  // H[i][j] = d u_i / d x_j
+      for (int b = 0; b < 27; ++b) {
+        const double u = s.us[b * 3 + i];
+        h0 = fma(u, s.g[0][q * QSTR + b], h0); h1 = fma(u, s.g[1][q * QSTR + b], h1); h2 = fma(u, s.g[2][q * QSTR + b], h2);
+      }
+      double* Hr = s.inv + q * 9 + i * 3;
+      Hr[0] = h0; Hr[1] = h1; Hr[2] = h2;
+    }
+    __syncthreads();
     if (wantR && tid < 27) {
       const int q = tid;
-      double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // H[i][j] = d u_i / d x_j
-      for (int b = 0; b < 27; ++b) {
-        const double u0 = s.us[b * 3], u1 = s.us[b * 3 + 1], u2 = s.us[b * 3 + 2];
+      double H[3][3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          const double gj = s.g[j][q * QSTR + b];
-          H[0][j] = fma(u0, gj, H[0][j]); H[1][j] = fma(u1, gj, H[1][j]); H[2][j] = fma(u2, gj, H[2][j]);
-        }
-      }
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) H[i][j] = s.inv[q * 9 + i * 3 + j];
       const double w = s.wq[q], tr = p.lam1 * (H[0][0] + H[1][1] + H[2][2]), m2 = 2. * p.mu1;
       double* sg = s.inv + q * 9;  // xx, yy, zz, xy, yz, zx
       sg[0] = w * (tr + m2 * H[0][0]) + s.pth[q]; sg[1] = w * (tr + m2 * H[1][1]) + s.pth[q]; sg[2] = w * (tr + m2 * H[2][2]) + s.pth[q];
@@ -464,18 +501,12 @@ __global__ void __launch_bounds__(TB5, 4) hex27_sym_pass1_kernel(const Hex27Para
               if (((cma >> i) | (cmb >> j)) & 1u) K[i][j] = (a == b && i == j && ((cma >> i) & 1u)) ? 1. : 0.;
         }
         if (own_a) {
-          double* dst = p.tmp_K + (((int64_t)idx * 27 + a) * 27 + b) * 9;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) dst[i * 3 + j] = K[i][j];
+          const double v[9] = {K[0][0], K[0][1], K[0][2], K[1][0], K[1][1], K[1][2], K[2][0], K[2][1], K[2][2]};
+          store_block72(p.tmp_K + (((int64_t)idx * 27 + a) * 27 + b) * 9, v);
         }
         if (rt != ct && s.row[b] >= 0) {  // the mirrored block K_ba = K_ab^T
-          double* dst = p.tmp_K + (((int64_t)idx * 27 + b) * 27 + a) * 9;
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) dst[i * 3 + j] = K[j][i];
+          const double v[9] = {K[0][0], K[1][0], K[2][0], K[0][1], K[1][1], K[2][1], K[0][2], K[1][2], K[2][2]};
+          store_block72(p.tmp_K + (((int64_t)idx * 27 + b) * 27 + a) * 9, v);
         }
       }
     }
@@ -492,46 +523,53 @@ constexpr int GMAXNB = 128;    // neighbours per row (position map: 7 bits)
 
 __global__ void __launch_bounds__(GW2 * 32) hex27_row_gather_kernel(const Hex27GatherParams p) {
   __shared__ double acc_all[GW2][GMAXNB * 9];
-  __shared__ uint8_t pos_all[GW2][32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ir = (int64_t)blockIdx.x * GW2 + warp;
   if (ir >= p.n_rows) return;
   double* acc = acc_all[warp];
-  uint8_t* pos = pos_all[warp];
   const int r = p.rows[ir];
   const int n = p.owned_nodes[r];
   const int64_t nb0 = p.nbr_ptr[r];
   const int nnb = (int)(p.nbr_ptr[r + 1] - nb0);
   const unsigned pmask = p.pos_flagged ? 0x7fu : 0xffu;
+  const int64_t k0 = p.ea_ptr[ir], k1 = p.ea_ptr[ir + 1];
+  const bool first_chunk = p.row_first[ir] != 0;  // no element of the row lies before the chunk: stored, otherwise added to
   for (int t = lane; t < nnb * 9; t += 32) acc[t] = 0.;
   double f = 0.;  // lanes 0-2: the node's force components
-  bool first_chunk = true;  // no element of the row lies before the chunk: the row is stored, otherwise added to
-  const int e_end = p.elem_first + p.n_elems;
-  for (int64_t ke = p.n2e_ptr[n]; ke < p.n2e_ptr[n + 1]; ++ke) {
-    const int e = p.n2e[ke];
-    if (e < p.elem_first) { first_chunk = false; continue; }
-    if (e >= e_end) break;
-    __syncwarp();
-    const int nd = lane < 27 ? p.conn[(int64_t)e * 27 + lane] : -1;
-    const int a = __ffs(__ballot_sync(0xffffffffu, nd == n)) - 1;
-    if (lane < 27) pos[lane] = (uint8_t)(p.posmap[((int64_t)e * 27 + a) * 27 + lane] & pmask);
-    __syncwarp();
-    const double* src = p.tmp_K + ((int64_t)(e - p.elem_first) * 27 + a) * (27 * 9);
-    double v[8];  // the eight loads of a lane are issued before the first shared-memory add
+  // the row's (element, local node) codes come from the plan; the loads of element k + 1 (eight doubles per lane and the
+  // positions of its 27 blocks) are in flight while element k is added
+  auto fetch = [&](int code, double (&v)[8], unsigned& pb) {
+    const double* src = p.tmp_K + (int64_t)code * (27 * 9);
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int t = lane + 32 * u;
       v[u] = t < 27 * 9 ? __ldcs(src + t) : 0.;  // streamed once
     }
+    const int el = (int)__umulhi((unsigned)code, 159072863u);  // code / 27 (exact below 8e8)
+    pb = lane < 27 ? (unsigned)(p.posmap[((int64_t)(p.elem_first + el) * 27 + (code - el * 27)) * 27 + lane] & pmask) : 0u;
+  };
+  for (int64_t kb = k0; kb < k1; kb += 32) {
+    const int cnt = (int)(k1 - kb < 32 ? k1 - kb : 32);
+    const int mine = lane < cnt ? p.ea[kb + lane] : 0;
+    double va[8], vb[8];
+    unsigned pa = 0u, pbn = 0u;
+    fetch(__shfl_sync(0xffffffffu, mine, 0), va, pa);
+    for (int el = 0; el < cnt; ++el) {
+      const int code = __shfl_sync(0xffffffffu, mine, el);
+      if (el + 1 < cnt) fetch(__shfl_sync(0xffffffffu, mine, el + 1), vb, pbn);
+      __syncwarp();
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int t = lane + 32 * u;
-      if (t < 27 * 9) {
-        const int b = (t * 7282) >> 16;  // t / 9 for t < 243
-        acc[pos[b] * 9 + (t - b * 9)] += v[u];
+      for (int u = 0; u < 8; ++u) {
+        const int t = lane + 32 * u;
+        const int b = (t * 7282) >> 16;  // t / 9 for t < 243 (and 27.. for the padding lanes: masked below)
+        const unsigned pos = __shfl_sync(0xffffffffu, pa, b < 27 ? b : 0);
+        if (t < 27 * 9) acc[pos * 9 + (t - b * 9)] += va[u];
       }
+      if (p.R && lane < 3) f += p.tmp_f[(int64_t)code * 3 + lane];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) va[u] = vb[u];
+      pa = pbn;
     }
-    if (p.R && lane < 3) f += p.tmp_f[((int64_t)(e - p.elem_first) * 27 + a) * 3 + lane];
   }
   __syncwarp();
   if (p.J) {
