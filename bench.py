@@ -326,8 +326,8 @@ def main():
                 "value": n_elem_global * args.steps / (float(sms.item()) * 1e-3),
                 "fused_with_residual_jacobian": n_elem_global * args.steps / (float(fms.item()) * 1e-3),
                 "config": f"same {n}^3 mesh, SIMP (rho_min 1e-8, p 4) of a nodal density field, compliance adjoint = state; "
-                          "value: G alone (two element-parallel kernels); fused: R + J + G of one state in ONE launch of the structured kernel",
-                "gpu_launches_per_step": 2}
+                          "value: G alone (structured sensitivity sweep, sweep_hex8_sens_struct.cu: one launch, node planes staged in shared memory); fused: R + J + G of one state in ONE launch of the structured kernel",
+                "gpu_launches_per_step": 1}
         # the sensitivity-only sweep is fp64-bound (5.1 kflop and 121 B per element); roof = the measured DFMA /
         # DMMA rate of profiles/r01_fp64_pipes.md per GPU
         sens["roofline"] = {"bound": "fp64", "unit": "TFLOP/s", "flops_per_element": 5100,

@@ -802,8 +802,28 @@ int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, 
   CU(cudaEventRecord(ctx->ev[0], ctx->stream));
   if (ctx->has_ghosts) CU(cudaMemsetAsync(dG, 0, size_t(ctx->n_nodes) * sizeof(double), ctx->stream));
   CU(cudaEventRecord(ctx->ev[1], ctx->stream));
-  CU(launch_density_sensitivities(p, dadj, dG, ctx->stream));
-  ctx->launches += 2;
+  // build_cube-numbered HEX8 meshes, 3-dof system, linear strain: the structured sensitivity sweep (node planes staged in
+  // shared memory, nothing but G leaves the SM) instead of the two element-parallel kernels (MASTB200_SENS_STRUCT=0)
+  bool sens_struct = ctx->elem_type == MASTB200_HEX8 && ctx->nv == 3 && !ctx->mat.nonlinear_strain;
+  if (const char* e = getenv("MASTB200_SENS_STRUCT")) if (e[0] == '0') sens_struct = false;
+  if (sens_struct) sens_struct = ensure_struct_plan(ctx) == MASTB200_OK && ctx->splan.ok;
+  if (sens_struct) {
+    const mastb200_context::StructPlan& S = ctx->splan;
+    const mastb200_material& m = ctx->mat;
+    StructParams sp;
+    sp.units = S.units.p; sp.n_units = S.n_units; sp.counter = ctx->d_tile_counter.p;
+    sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0; sp.nv = 3;
+    sp.xyz = ctx->d_xyz.p; sp.X = p.X; sp.adj = dadj; sp.G = dG;
+    sp.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;
+    sp.rho = ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p;
+    sp.E0 = m.E0; sp.lam1 = m.nu / (1. - m.nu - 2. * m.nu * m.nu); sp.mu1 = 1. / 2. / (1. + m.nu);
+    sp.rho_min = m.rho_min; sp.penalty = m.penalty;
+    CU(launch_hex8_sens_struct(sp, ctx->sm_count, ctx->stream));
+    ctx->launches += 1;
+  } else {
+    CU(launch_density_sensitivities(p, dadj, dG, ctx->stream));
+    ctx->launches += 2;
+  }
   CU(cudaEventRecord(ctx->ev[2], ctx->stream));
   CU(cudaEventRecord(ctx->ev[3], ctx->stream));
   ctx->timed = true;

@@ -309,3 +309,49 @@ def test_struct_thermoelastic_load(built, monkeypatch, struct_kernel):
         R2 = np.full(prob.n_dof, np.nan)
         ctx.residual_and_jacobian(X, R2, None)
         assert np.array_equal(R2, R)
+
+
+def test_struct_density_sensitivities_alone(built, monkeypatch, struct_kernel):
+    # G without R / J on build_cube meshes: the structured sensitivity sweep (sweep_hex8_sens_struct.cu) against the oracle's
+    # adjoint sensitivities and against the element-parallel kernels; compliance (adj == X) and a separate adjoint, scattered
+    # Dirichlet dofs, owned z-slabs, shapes around the tile sizes
+    if struct_kernel != "lockstep":
+        pytest.skip("one run is enough: the sensitivity sweep does not depend on the R / J kernel's choice")
+    import mast_b200
+    rng = np.random.default_rng(31)
+    for trial, shape in enumerate([(1, 1, 1), (3, 2, 2), (8, 8, 8), (9, 15, 5), (14, 7, 19), (7, 8, 30)]):
+        nx, ny, nz = shape
+        xyz, conn = mesh.build_cube(nx, ny, nz, 0.3 + 0.05 * nx, 0.2 + 0.05 * ny, 0.1 + 0.05 * nz, 8, jitter=0.2)
+        con = (rng.uniform(size=len(xyz) * 3) < 0.08).astype(np.uint8)
+        rho = 0.2 + 0.6 * rng.uniform(size=len(xyz))
+        prob = O.Problem(O.HEX8, xyz, conn, 3, constrained=con, rho=rho, rho_min=1e-8, penalty=3.0 + (trial % 2))
+        X = O.state(prob.n_dof, 1); lam = X if trial % 3 == 0 else O.state(prob.n_dof, 2)
+        n = prob.n_nodes
+        npxy = (nx + 1) * (ny + 1)
+        owned = None
+        if trial >= 3:
+            z0 = int(rng.integers(0, nz + 1)); z1 = int(rng.integers(z0 + 1, nz + 2))
+            owned = np.zeros(n, np.uint8); owned[z0 * npxy:z1 * npxy] = 1
+        def run():
+            ctx = mast_b200.Context(0)
+            ctx.set_mesh(8, prob.xyz, prob.conn)
+            ctx.set_dof_map(3, prob.constrained, owned)
+            ctx.set_material(**prob.mat)
+            ctx.set_density(prob.rho)
+            ctx.build_pattern()
+            G = np.full(n, np.nan)
+            ctx.sensitivity_sweep(X, lam, G)
+            return ctx, G
+        ctx, G = run()
+        assert ctx.stats()["kernel_launches"] == 1, shape  # one launch: the structured sweep
+        g_ref = prob.adjoint_sensitivity(X, lam, np.arange(n + 1), np.arange(n), np.ones(n))
+        own = np.ones(n, bool) if owned is None else owned.astype(bool)
+        _close(G[own], g_ref[own], 1e-11)
+        assert np.all(G[~own] == 0.0)
+        _, G2 = run()
+        assert np.array_equal(G, G2)  # bitwise reproducible
+        monkeypatch.setenv("MASTB200_SENS_STRUCT", "0")
+        ctx_e, Ge = run()
+        monkeypatch.delenv("MASTB200_SENS_STRUCT")
+        assert ctx_e.stats()["kernel_launches"] == 2
+        _close(G[own], Ge[own], 1e-11)
