@@ -65,8 +65,11 @@ __device__ __forceinline__ void q4_eval(const double* x, const double* y, double
   }
 }
 
+#ifndef MASTB200_PLATE_CTAS
+#define MASTB200_PLATE_CTAS 3  // 168 registers: 12 warps per SM (2: 191 registers, 320 M elem/s; 3: 380 M; 4: spills, 309 M at 1024^2)
+#endif
 template <bool LOCAL, bool NL>
-__global__ void __launch_bounds__(TB) quad4_plate_kernel(const PlateParams p) {
+__global__ void __launch_bounds__(TB, MASTB200_PLATE_CTAS) quad4_plate_kernel(const PlateParams p) {
   const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
   if (t >= p.n_entries) return;
   const int64_t r = p.ent_row[t];  // row of this neighbour entry (precomputed with the plan)
