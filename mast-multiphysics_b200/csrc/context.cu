@@ -1609,14 +1609,24 @@ int mastb200_sensitivity_assemble(mastb200_context* ctx, const double* X, int32_
 
 int mastb200_linearized_jacobian_solution_product(mastb200_context* ctx, const double* X, const double* dX, double* out) {
   if (!ctx || !dX || !out) return MASTB200_ERR_ARG;
-  (void)X;  // linear strain: the tangent does not depend on the state
   int rc = check_ready(ctx);
   if (rc) return rc;
   if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "linearized_jacobian_solution_product: 3D solids (HEX8, HEX27) only");
   CU(cudaSetDevice(ctx->device));
   const double nu = ctx->mat.nu;
-  return run_internal_force(ctx, dX, 0, nullptr, nu / (1. - nu - 2. * nu * nu), 1. / 2. / (1. + nu), out);
+  const double lam1 = nu / (1. - nu - 2. * nu * nu), mu1 = 1. / 2. / (1. + nu);
+  if (!ctx->mat.nonlinear_strain)  // linear strain: the tangent does not depend on the state
+    return run_internal_force(ctx, dX, 0, nullptr, lam1, mu1, out);
+  // Green-Lagrange strain: K_T(X) dX matrix-free (material tangent + initial-stress stiffness, mode 5 of the force kernels)
+  if (!X) return MASTB200_ERR_ARG;
+  if (ctx->thermal)
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "tangent product with Green-Lagrange strain and a thermal load is not on the device path");
+  const size_t n_dof = size_t(ctx->n_nodes) * ctx->nv;
+  const double* ddX = nullptr;
+  if ((rc = resolve_in(ctx, dX, n_dof, ctx->d_adj, &ddX))) return rc;
+  if ((rc = localize_if_needed(ctx, ddX, ctx->nv))) return rc;
+  return run_internal_force(ctx, X, 5, ddX, lam1, mu1, out, true, true);
 }
 
 // -f_th . V over the owned nodes, f_th = the TEMPERATURE volume load as an element force vector (mode 4)

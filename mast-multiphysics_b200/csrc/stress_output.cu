@@ -250,6 +250,41 @@ __global__ void __launch_bounds__(TB) stress_dq_qp_kernel(const StressParams p) 
 //   mode 3: Ehat = E(rho_q), D_1 <- dD_1/dnu (lam1, mu1 of the params are the derivatives)
 //   mode 4: sigma_q = E(rho_q) alpha_k (T_q - T_ref) I: the TEMPERATURE volume load B^T D alpha dT of thermal_residual
 //           (solid_element_3d.cpp:950-1089, linear strain) as a force vector
+//   mode 5: the tangent product K_T(u) du with Green-Lagrange strain (dfield = du as a dof vector): the first Piola-Kirchhoff
+//           increment dP = grad(du) S + F dS, dS = E D_1 sym(F^T grad du) -- material tangent + initial-stress stiffness of
+//           solid_element_3d.cpp:327-409 applied to a vector; with linear strain it reduces to mode 0 of du
+// dP = grad(du) S + F dS with dS = E D_1 sym(F^T grad du) (F = I + H with Green-Lagrange strain; F = I and no initial-stress
+// term with linear strain): the increment of the first Piola-Kirchhoff stress along du, written over S
+__device__ __forceinline__ void tangent_increment(const StressParams& p, double E, const double (&H)[3][3], const double (&dH)[3][3],
+                                                  double (&S)[3][3]) {
+  double Dm[3][3];  // F^T grad(du)
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      Dm[i][j] = dH[i][j] + (p.nonlinear ? H[0][i] * dH[0][j] + H[1][i] * dH[1][j] + H[2][i] * dH[2][j] : 0.);
+  const double lam = E * p.lam1, mu = E * p.mu1, tr = lam * (Dm[0][0] + Dm[1][1] + Dm[2][2]);
+  double dS[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dS[i][j] = mu * (Dm[i][j] + Dm[j][i]) + (i == j ? tr : 0.);
+  double P[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      double v = dS[k][c];
+      if (p.nonlinear)
+        v += H[k][0] * dS[0][c] + H[k][1] * dS[1][c] + H[k][2] * dS[2][c] + dH[k][0] * S[0][c] + dH[k][1] * S[1][c] + dH[k][2] * S[2][c];
+      P[k][c] = v;
+    }
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) S[k][c] = P[k][c];
+}
+
 __global__ void __launch_bounds__(TB) force_qp_kernel(const StressParams p, int mode, const double* __restrict__ dfield) {
   const int64_t t = (int64_t)blockIdx.x * TB + threadIdx.x;
   const int64_t nqp = p.n_elem * p.nq;
@@ -288,7 +323,24 @@ __global__ void __launch_bounds__(TB) force_qp_kernel(const StressParams p, int 
     g.sig[3] = g.sig[4] = g.sig[5] = 0.;
   }
   double S[3][3] = {{g.sig[0], g.sig[3], g.sig[5]}, {g.sig[3], g.sig[1], g.sig[4]}, {g.sig[5], g.sig[4], g.sig[2]}};
-  if (p.nonlinear) {  // Green-Lagrange: f_a = JxW B_a(F)^T S = JxW (F S) grad N_a with F = I + H (modes 1-3: S <- dD/dp E_GL)
+  if (mode == 5) {
+    double dH[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // grad(du)
+    const double* dNt = p.tab + (size_t)p.nq * p.nn + (size_t)q * p.nn * 3;
+    const int32_t* en = p.conn + e * p.nn;
+    for (int b = 0; b < p.nn; ++b) {
+      const double d0 = dNt[b * 3], d1 = dNt[b * 3 + 1], d2 = dNt[b * 3 + 2];
+      double gr[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) gr[c] = d0 * g.inv[c][0] + d1 * g.inv[c][1] + d2 * g.inv[c][2];
+      const double* D = dfield + (int64_t)en[b] * p.nv;
+      const double v0 = D[0], v1 = D[1], v2 = D[2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        dH[0][j] = fma(v0, gr[j], dH[0][j]); dH[1][j] = fma(v1, gr[j], dH[1][j]); dH[2][j] = fma(v2, gr[j], dH[2][j]);
+      }
+    }
+    tangent_increment(p, g.E, g.H, dH, S);  // S <- dP
+  } else if (p.nonlinear) {  // Green-Lagrange: f_a = JxW B_a(F)^T S = JxW (F S) grad N_a with F = I + H (modes 1-3: S <- dD/dp E_GL)
     double FS[3][3];
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -401,6 +453,7 @@ __global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressPa
   inv[2][2] = (Jm[0][0] * Jm[1][1] - Jm[0][1] * Jm[1][0]) * idet;
   double H[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};
   double rho = 0., dr = 0., tq = 0.;
+  double dH[3][3] = {{0., 0., 0.}, {0., 0., 0.}, {0., 0., 0.}};  // grad(du), mode 5
 #pragma unroll
   for (int b = 0; b < 8; ++b) {
     const bool px = b == 1 || b == 2 || b == 5 || b == 6, py = b == 2 || b == 3 || b == 6 || b == 7, pz = b >= 4;
@@ -420,6 +473,14 @@ __global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressPa
     if (p.rho) rho = fma(Nb, p.rho[n], rho);
     if (mode == 1) dr = fma(Nb, dfield[n], dr);
     if (mode == 4 && p.temperature) tq = fma(Nb, p.temperature[n], tq);
+    if (mode == 5) {
+      const double* D = dfield + n * p.nv;
+      const double v0 = D[0], v1 = D[1], v2 = D[2];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        dH[0][j] = fma(v0, g[j], dH[0][j]); dH[1][j] = fma(v1, g[j], dH[1][j]); dH[2][j] = fma(v2, g[j], dH[2][j]);
+      }
+    }
   }
   double E = p.E0;
   if (p.rho) E = p.E0 * (p.rho_min + (1. - p.rho_min) * simp_pow(rho, p.penalty));
@@ -451,6 +512,8 @@ __global__ void __launch_bounds__(256, 2) force_hex8_nodal_kernel(const StressPa
     for (int k = 0; k < 3; ++k)
 #pragma unroll
       for (int c = 0; c < 3; ++c) S[k][c] = k == c ? st : 0.;
+  } else if (mode == 5) {
+    tangent_increment(p, E, H, dH, S);
   } else if (p.nonlinear) {
     double FS[3][3];
 #pragma unroll

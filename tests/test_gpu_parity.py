@@ -796,6 +796,31 @@ def test_linearized_jacobian_solution_product(built, elem_type):
     _close(out, prob.linearized_jacobian_solution_product(X, dX), 1e-11)
 
 
+@pytest.mark.parametrize("elem_type", [8, 27])
+def test_linearized_jacobian_solution_product_green_lagrange(built, elem_type):
+    # K_T(X) dX with NONLINEAR_STRAIN: material tangent + initial-stress stiffness applied to a vector, matrix-free
+    prob = _solid(elem_type, loads=False, nonlinear_strain=1)
+    X = O.state(prob.n_dof, 1, scale=2e-3); dX = O.state(prob.n_dof, 7)
+    ctx = prob.make_context(0)
+    out = np.full(prob.n_dof, np.nan)
+    ctx.linearized_jacobian_solution_product(X, dX, out)
+    ref = prob.linearized_jacobian_solution_product(X, dX)
+    _close(out, ref, 1e-11)
+    lin = _solid(elem_type, loads=False).linearized_jacobian_solution_product(X, dX)
+    assert np.abs(ref - lin).max() > 1e-3 * np.abs(lin).max()
+    # and it is the assembled tangent times dX
+    import scipy.sparse as sp
+    J = np.empty(ctx.nnz)
+    ctx.residual_and_jacobian(X, None, J)
+    rp, ci = ctx.get_pattern()
+    A = sp.csr_matrix((J, ci, rp), shape=(prob.n_dof, prob.n_dof))
+    free = ~prob.constrained.astype(bool)
+    dXc = np.where(free, dX, 0.0)   # the element matrices are constrained: columns of constrained dofs are zero
+    outc = np.full(prob.n_dof, np.nan)
+    ctx.linearized_jacobian_solution_product(X, dXc, outc)
+    assert np.abs((A @ dXc)[free] - outc[free]).max() <= 1e-10 * np.abs(outc).max()
+
+
 def test_point_loads(built):
     prob = _solid(8, simp=False)
     X = O.state(prob.n_dof, 1)
