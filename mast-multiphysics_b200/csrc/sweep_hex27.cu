@@ -324,7 +324,10 @@ __device__ __forceinline__ void store_block72(double* dst, const double (&v)[9])
   }
 }
 
-__global__ void __launch_bounds__(TB5, 4) hex27_sym_pass1_kernel(const Hex27Params p) {
+#ifndef MASTB200_H27_SYM_CTAS
+#define MASTB200_H27_SYM_CTAS 4
+#endif
+__global__ void __launch_bounds__(TB5, MASTB200_H27_SYM_CTAS) hex27_sym_pass1_kernel(const Hex27Params p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem27& s = *reinterpret_cast<Smem27*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -597,7 +600,7 @@ cudaError_t launch_hex27_sym_pass1(const Hex27Params& p, int sm_count, cudaStrea
   if (p.nv != 3 || p.diag_elem || p.elems) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(hex27_sym_pass1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem27));
   if (e != cudaSuccess) return e;
-  const int grid = p.n_elems < 4 * sm_count ? p.n_elems : 4 * sm_count;
+  const int grid = p.n_elems < MASTB200_H27_SYM_CTAS * sm_count ? p.n_elems : MASTB200_H27_SYM_CTAS * sm_count;
   hex27_sym_pass1_kernel<<<grid, TB5, sizeof(Smem27), stream>>>(p);
   return cudaGetLastError();
 }
