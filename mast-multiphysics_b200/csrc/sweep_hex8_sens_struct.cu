@@ -14,7 +14,8 @@
 // node planes (coordinates, state, adjoint, density) are staged once per plane with cp.async, lane = (element, qp) forms
 // s_q, the eight lanes of an element turn the point values into nodal sums by shuffles (q ascending) and leave them in a
 // per-element slot; one thread per owned node then adds its <= 8 corner values in ascending element id (the reference's
-// ADD order) and writes G.  Nothing but G leaves the SM; bitwise reproducible; ~30 KB of shared memory, two CTAs per SM.
+// ADD order) and writes G -- while the other warps already compute the next element plane (three slot buffers, one CTA
+// barrier per plane).  Nothing but G leaves the SM; bitwise reproducible; ~33 KB of shared memory, two CTAs per SM.
 #include <cuda_runtime.h>
 
 #include "kernels.h"
@@ -34,7 +35,7 @@ struct SmemS {
   double u[3][3][NS];
   double adj[3][3][NS];
   double rho[3][NS];
-  double slot[2][64][8];   // [element plane parity][element column][node in ijk order]: sum_q N_a(q) s_q
+  double slot[3][64][8];   // [element plane % 3][element column][node in ijk order]: sum_q N_a(q) s_q
   uint8_t cm[3][NSB];
   int2 node[64];           // owned nodes of the unit: in-plane node id, lx | ly << 4
   int misc[4];
@@ -184,11 +185,13 @@ __global__ void __launch_bounds__(ST, 2) hex8_sens_struct_kernel(const StructPar
           const int lex = el & 7, ley = el >> 3;
           const bool live = lex < u.nex && ley < u.ney;
           const double g = element_point(p, sm, s, ley * TCX + lex, q, live, same, lane);
-          if (live) sm.slot[s & 1][el][q] = g;
+          if (live) sm.slot[s % 3][el][q] = g;
         }
       }
+      cp_async_wait_all();
       __syncthreads();
-      // node plane s is complete: corner elements of plane s - 1 (the node is one of their top nodes) and of plane s
+      // node plane s is complete: corner elements of plane s - 1 (the node is one of their top nodes) and of plane s.  ONE
+      // barrier per plane: three slot buffers, so the next element plane is computed while these few threads add corners
       if (s >= u.z0 && tid < n_own) {
         const int2 ni = sm.node[tid];
         const int lx = ni.y & 15, ly = (ni.y >> 4) & 15;
@@ -205,14 +208,12 @@ __global__ void __launch_bounds__(ST, 2) hex8_sens_struct_kernel(const StructPar
             for (int cx = 0; cx < 2; ++cx) {
               const int lex = lx - 1 + cx;
               if ((unsigned)lex >= (unsigned)u.nex) continue;
-              acc += sm.slot[layer & 1][ley * 8 + lex][(1 - cx) + 2 * (1 - cy) + 4 * (1 - cz)];
+              acc += sm.slot[layer % 3][ley * 8 + lex][(1 - cx) + 2 * (1 - cy) + 4 * (1 - cz)];
             }
           }
         }
         p.G[(int64_t)s * plane_nodes + ni.x] = acc;
       }
-      cp_async_wait_all();
-      __syncthreads();
     }
   }
 }

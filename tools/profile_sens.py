@@ -1,9 +1,11 @@
-import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""Driver for ncu: density sensitivities alone (structured sensitivity sweep) on an n^3 mesh."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 import numpy as np, torch
 import mast_b200
 from mast_b200 import mesh
-n = 128
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 xyz, conn = mesh.build_cube(n, n, n, 1.0, 1.0, 1.0, 8, jitter=0.2)
 ctx = mast_b200.Context(0)
 ctx.set_mesh(mast_b200.HEX8, xyz, conn)
@@ -11,7 +13,6 @@ ctx.set_dof_map(3, mesh.dirichlet_flags(len(xyz), 3, mesh.boundary_nodes(n, n, n
 ctx.set_material(E0=72e9, nu=0.33, rho_min=1e-8, penalty=4.0)
 rng = np.random.default_rng(3)
 ctx.set_density(0.2 + 0.6 * rng.uniform(size=len(xyz)))
-os.environ["MASTB200_NO_STRUCT"] = "1"
 ctx.build_pattern()
 X = torch.from_numpy(1e-3 * rng.uniform(-1, 1, len(xyz) * 3)).cuda()
 G = torch.empty(len(xyz), dtype=torch.float64, device="cuda")
