@@ -39,7 +39,6 @@ constexpr int NS = TCX * TCY;
 constexpr int NSB = (NS + 3) & ~3;
 constexpr int NEP = 65;                // doubles per slot array: 64 element columns + 1 (bank = value id + column)
 constexpr int N_CR = 144, N_IN = 78;   // value arrays: cross pairs 9 x 16; in-plane 3 x 16 (i < j) + 3 x 10 (i == j, unordered)
-constexpr int TRASH_CR = N_CR, TRASH_IN = N_IN;  // one more array per region takes the values a lane holds in duplicate
 constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
 constexpr int MAXOWN = 49;
 constexpr double GP = 0.57735026918962576451;
@@ -47,8 +46,8 @@ constexpr double GP = 0.57735026918962576451;
 // shared-memory carve-up (bytes).  The in-plane regions start 8 doubles (mod 16) after the cross region so that the two
 // kinds of lanes of one store instruction fall into different banks.
 constexpr int O_CR = 0;
-constexpr int CR_BYTES = (N_CR + 1) * NEP * 8;
-constexpr int IN_BYTES = (N_IN + 1) * NEP * 8;
+constexpr int CR_BYTES = N_CR * NEP * 8;
+constexpr int IN_BYTES = N_IN * NEP * 8;
 constexpr int O_IN0 = ((O_CR + CR_BYTES + 127) & ~127) + 64;
 constexpr int O_IN1 = ((O_IN0 + IN_BYTES + 127) & ~127) + 64;
 constexpr int O_XYZ = O_IN1 + IN_BYTES;                  // [3 planes][3][NS]
@@ -103,8 +102,8 @@ __device__ __forceinline__ int up(int a, int b) { return a + updiag(b - a); }
 
 struct LaneK {
   double d0[2], d1[2], d2;   // reference gradients of N_m at qps q4 (h = 0) and q4 + 4 (h = 1)
-  int off[12];               // BYTE offset of value t = bb * 6 + k within its region (array start; the column is added);
-                             // values the lane holds in duplicate go to the region's trash array
+  int off[12];               // BYTE offset of value t = bb * 6 + k within its region (array start; the column is added)
+  unsigned pred;             // bit t: the lane stores value t (values it holds in duplicate with another lane are skipped)
   int kind;                  // 0 cross pairs, 1 in-plane pairs of the bottom nodes (added), 2 of the top nodes (stored)
 };
 
@@ -121,21 +120,26 @@ __device__ __forceinline__ void make_lane(int lane, LaneK& lk) {
   const int KI[6] = {0, 1, 2, 0, 0, 1}, KJ[6] = {0, 1, 2, 1, 2, 2};
   const int mz = m >> 2, bz = q4 >> 1, m4 = m & 3;
   lk.kind = mz == bz ? (mz == 0 ? 1 : 2) : 0;
+  lk.pred = 0u;
 #pragma unroll
   for (int bb = 0; bb < 2; ++bb) {
     const int b4 = (2 * q4 + bb) & 3;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      int idx;
+      int idx = 0;
+      bool on = true;
       if (mz == bz) {
         if (k >= 3) idx = (k - 3) * 16 + pm(m4, b4);
-        else idx = m4 <= b4 ? 48 + k * 10 + up(m4, b4) : TRASH_IN;  // S_ii of an unordered pair: the lane (b, m) holds it too
+        else if (m4 <= b4) idx = 48 + k * 10 + up(m4, b4);
+        else on = false;  // S_ii of an unordered pair: the lane (b, m) holds it too
       } else if (mz == 0) {  // bottom m, top b: S_(m,b)[KI][KJ]
         idx = (KI[k] * 3 + KJ[k]) * 16 + pm(m4, b4);
       } else {               // top m, bottom b: C = S_(m,b)[KI][KJ] = S_(b,m)[KJ][KI]; the diagonal components are the other lane's
-        idx = k >= 3 ? (KJ[k] * 3 + KI[k]) * 16 + pm(b4, m4) : TRASH_CR;
+        if (k >= 3) idx = (KJ[k] * 3 + KI[k]) * 16 + pm(b4, m4);
+        else on = false;
       }
       lk.off[bb * 6 + k] = idx * NEP * 8;
+      if (on) lk.pred |= 1u << (bb * 6 + k);
     }
   }
 }
@@ -181,28 +185,27 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
 }
 
 // ---- slot stores of one element's tiles (lane = (m, q4) holds C[k][bb] for b = 2 q4 + bb) -----------------------------
+__device__ __forceinline__ void sts64_if(unsigned a, double v, unsigned cond) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q st.shared.f64 [%0], %1;\n}" ::"r"(a), "d"(v), "r"(cond) : "memory");
+}
+__device__ __forceinline__ void lds64_if(double& v, unsigned a, unsigned cond) {
+  asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n @q ld.shared.f64 %0, [%1];\n}" : "+d"(v) : "r"(a), "r"(cond) : "memory");
+}
 __device__ __forceinline__ void store_slots(const LaneK& lk, unsigned smem32, int ecol, int par, const double (&C)[6][2]) {
   // bottom in-plane pairs join what the element below left for node plane s (region IN[par]); top in-plane pairs open
-  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone.  No per-value predicates: duplicates go to
-  // the trash array, the twelve loads of the adding lanes share one predicate.
+  // node plane s+1 (region IN[par ^ 1]); cross pairs are this element's alone.  Values a lane holds in duplicate are not
+  // stored (predicated instructions, no branches).
   const unsigned rb = lk.kind == 0 ? O_CR : (((lk.kind == 1) == (par == 0)) ? O_IN0 : O_IN1);
   const unsigned ar = smem32 + rb + ecol * 8;
+  const unsigned ldm = lk.kind == 1 ? lk.pred : 0u;  // the adding lanes read first
   double old[12];
 #pragma unroll
-  for (int t = 0; t < 12; ++t) old[t] = 0.;
-  asm volatile(
-      "{\n .reg .pred q;\n setp.eq.s32 q, %12, 1;\n"
-      "@q ld.shared.f64 %0, [%13];\n @q ld.shared.f64 %1, [%14];\n @q ld.shared.f64 %2, [%15];\n @q ld.shared.f64 %3, [%16];\n"
-      "@q ld.shared.f64 %4, [%17];\n @q ld.shared.f64 %5, [%18];\n @q ld.shared.f64 %6, [%19];\n @q ld.shared.f64 %7, [%20];\n"
-      "@q ld.shared.f64 %8, [%21];\n @q ld.shared.f64 %9, [%22];\n @q ld.shared.f64 %10, [%23];\n @q ld.shared.f64 %11, [%24];\n}"
-      : "+d"(old[0]), "+d"(old[1]), "+d"(old[2]), "+d"(old[3]), "+d"(old[4]), "+d"(old[5]), "+d"(old[6]), "+d"(old[7]),
-        "+d"(old[8]), "+d"(old[9]), "+d"(old[10]), "+d"(old[11])
-      : "r"(lk.kind), "r"(ar + lk.off[0]), "r"(ar + lk.off[1]), "r"(ar + lk.off[2]), "r"(ar + lk.off[3]), "r"(ar + lk.off[4]),
-        "r"(ar + lk.off[5]), "r"(ar + lk.off[6]), "r"(ar + lk.off[7]), "r"(ar + lk.off[8]), "r"(ar + lk.off[9]),
-        "r"(ar + lk.off[10]), "r"(ar + lk.off[11])
-      : "memory");
+  for (int t = 0; t < 12; ++t) {
+    old[t] = 0.;
+    lds64_if(old[t], ar + lk.off[t], (ldm >> t) & 1u);
+  }
 #pragma unroll
-  for (int t = 0; t < 12; ++t) sts64(ar + lk.off[t], old[t] + C[t % 6][t / 6]);
+  for (int t = 0; t < 12; ++t) sts64_if(ar + lk.off[t], old[t] + C[t % 6][t / 6], (lk.pred >> t) & 1u);
 }
 
 // ---- matrix + slot stores: all 32 lanes on one element -------------------------------------------------------------
