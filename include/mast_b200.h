@@ -145,13 +145,19 @@ int mastb200_apply_dv_map_transpose(mastb200_context* ctx, const double* G, int6
  *                              the nodes and weights of its filter column (d rho_n / dp)
  *   MASTB200_PARAM_E           Young's modulus E0 of the isotropic card (dv arguments ignored)
  *   MASTB200_PARAM_NU          Poisson's ratio
- * 3D solids, linear strain; matrix-free (two launches), K_e is never formed.
+ *   MASTB200_PARAM_K0          (QUAD4 heat conduction) conductivity k0 of the material card, k(T) = k0 (1 + k_beta T)
+ *   MASTB200_PARAM_THICKNESS   (QUAD4 heat conduction) section thickness: conductance, volume source and side loads
+ * 3D solids: matrix-free (two launches), K_e is never formed.  Heat conduction: one residual launch with the card swapped
+ * (every term is linear in k0 or h)  <- HeatConductionElementBase::internal_residual_sensitivity and the load
+ * sensitivities, src/heat_conduction/heat_conduction_elem_base.cpp:552-617, 957-1002, 1217-1275, 1524-1583, 1750-1794.
  *   <- NonlinearImplicitAssembly::sensitivity_assemble, src/base/nonlinear_implicit_assembly.cpp:515-686, with
  *      StructuralElement3D::internal_residual_sensitivity (src/elasticity/solid_element_3d.cpp:566-788, D <- dD/dp at :640)
  *      and IsotropicMaterialProperty::StiffnessMatrix3D::derivative (isotropic_material_property_card.cpp:530-567) */
 #define MASTB200_PARAM_DENSITY_DV 0
 #define MASTB200_PARAM_E 1
 #define MASTB200_PARAM_NU 2
+#define MASTB200_PARAM_K0 3
+#define MASTB200_PARAM_THICKNESS 4
 int mastb200_sensitivity_assemble(mastb200_context* ctx, const double* X, int32_t param, int64_t n_k, const int32_t* dv_node,
                                   const double* dv_weight, double* dRdp);
 /* out[n_nodes*nv] [h|d] = J(X) dX without forming J (constrained dofs zeroed per element), 3D solids, linear strain

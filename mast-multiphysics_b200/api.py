@@ -276,7 +276,8 @@ class Context:
         return sens
 
     def sensitivity_assemble(self, X, dRdp, param=0, dv_node=None, dv_weight=None):
-        """dR/dp of one parameter: param 0 = nodal-density DV (dv_node, dv_weight), 1 = E0, 2 = nu."""
+        """dR/dp of one parameter: param 0 = nodal-density DV (dv_node, dv_weight), 1 = E0, 2 = nu (3D solids);
+        3 = conductivity k0, 4 = section thickness (QUAD4 heat conduction)."""
         dv_node = _np(dv_node, np.int32); dv_weight = _np(dv_weight, np.float64)
         n_k = 0 if dv_node is None else len(dv_node)
         self._ck(self._lib.mastb200_sensitivity_assemble(self._h, _ptr(X), int(param), n_k, _ptr(dv_node), _ptr(dv_weight), _ptr(dRdp)))

@@ -1573,8 +1573,25 @@ int mastb200_sensitivity_assemble(mastb200_context* ctx, const double* X, int32_
   if (!ctx || !X || !dRdp) return MASTB200_ERR_ARG;
   int rc = check_ready(ctx);
   if (rc) return rc;
+  if (ctx->elem_type == MASTB200_QUAD4 && ctx->nv == 1) {
+    // Heat conduction (HeatConductionNonlinearAssemblyElemOperations::elem_sensitivity_calculations,
+    // heat_conduction_nonlinear_assembly.cpp:100-116).  Every term of the element residual is linear in the conductivity k0
+    // or in the section thickness h (d(k h) = dk h + k dh, solid_2d_section_element_property_card.cpp:955-975; sources and
+    // side loads are value*dth + dvalue*th with dvalue = 0), so dR/dp is the residual sweep itself with the card swapped:
+    //   dR/dk0 = internal residual at k0 = 1 (no source, no side loads),   dR/dh = full residual at h = 1.
+    if (param != MASTB200_PARAM_K0 && param != MASTB200_PARAM_THICKNESS)
+      return ctx->fail(MASTB200_ERR_ARG, "heat conduction: parameter kinds MASTB200_PARAM_K0 / MASTB200_PARAM_THICKNESS");
+    const mastb200_material saved = ctx->mat;
+    const bool saved_sides = ctx->have_heat_sides;
+    if (param == MASTB200_PARAM_K0) { ctx->mat.k0 = 1.; ctx->mat.heat_source = 0.; ctx->have_heat_sides = false; }
+    else ctx->mat.thickness = 1.;
+    rc = run_generic_sweep(ctx, X, dRdp, nullptr);
+    ctx->mat = saved;
+    ctx->have_heat_sides = saved_sides;
+    return rc;
+  }
   if (ctx->elem_type != MASTB200_HEX8 && ctx->elem_type != MASTB200_HEX27)
-    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "sensitivity_assemble: 3D solids (HEX8, HEX27) only");
+    return ctx->fail(MASTB200_ERR_UNSUPPORTED, "sensitivity_assemble: 3D solids (HEX8, HEX27) and QUAD4 heat conduction only");
   if (ctx->thermal)
     return ctx->fail(MASTB200_ERR_UNSUPPORTED, "thermal_residual_sensitivity is libmesh_error() for 3D elements in the reference");
   CU(cudaSetDevice(ctx->device));

@@ -509,6 +509,11 @@ int AssemblyBase::_card_parameter(const FunctionBase& f) const {
     if (&c->parameter() == &f) return MASTB200_PARAM_E;
   if (const ConstantFieldFunction* c = mat.get_if<ConstantFieldFunction>("nu"))
     if (&c->parameter() == &f) return MASTB200_PARAM_NU;
+  // heat conduction: the constant conductivity of the material card and the thickness of the 2D section card
+  if (const ConstantFieldFunction* c = mat.get_if<ConstantFieldFunction>("k_th"))
+    if (&c->parameter() == &f) return MASTB200_PARAM_K0;
+  if (const ConstantFieldFunction* c = _discipline->get_property_card(0).get_if<ConstantFieldFunction>("h"))
+    if (&c->parameter() == &f) return MASTB200_PARAM_THICKNESS;
   return -1;
 }
 
@@ -637,7 +642,8 @@ void NonlinearImplicitAssembly::residual_and_jacobian(const libMesh::NumericVect
 }
 
 // NonlinearImplicitAssembly::sensitivity_assemble (nonlinear_implicit_assembly.cpp:515-686): the global dR/dp vector of one
-// parameter.  Device paths: a density design variable (SIMP) and the card's E / nu Parameters (3D solids, linear strain);
+// parameter.  Device paths: a density design variable (SIMP), the card's E / nu Parameters (3D solids) and the conductivity /
+// section thickness Parameters of a QUAD4 heat-conduction system;
 // for anything else the reference's answer "false => the caller may finite-difference" (assembly_base.h:241-244).
 bool NonlinearImplicitAssembly::sensitivity_assemble(const libMesh::NumericVector<Real>& X, bool, const FunctionBase& f,
                                                      libMesh::NumericVector<Real>& sensitivity_rhs, bool close_vector) {

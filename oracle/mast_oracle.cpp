@@ -977,6 +977,51 @@ static void heat_elem_calculations(const OracleProblem* p, const FE& fe, const V
   }
 }
 
+// HeatConductionNonlinearAssemblyElemOperations::elem_sensitivity_calculations (heat_conduction_nonlinear_assembly.cpp:
+// 100-116) for a parameter of the property cards: kind 1 = the conductivity k0 of the material card, kind 2 = the section
+// thickness h.  ::internal_residual_sensitivity (heat_conduction_elem_base.cpp:552-617) with the derivative of the
+// conductance matrix k(T) h (solid_2d_section_element_property_card.cpp:955-975: dk h + k dh),
+// ::volume_heat_source_residual_sensitivity (:1750-1794: f -= JxW N (dq th + q dth)) and the side-load sensitivities
+// (:957-1002 flux, :1217-1275 convection, :1524-1583 radiation: every term is (value dth + dvalue th) with dvalue = 0 here).
+static void heat_elem_sensitivity(const OracleProblem* p, const FE& fe, const Vec& sol, int kind, Vec& f) {
+  const int nn = fe.nn, dim = fe.dim;
+  const double dth = kind == 2 ? 1. : 0.;
+  for (int qp = 0; qp < fe.nq; ++qp) {
+    double Tqp = 0.;
+    for (int a = 0; a < nn; ++a) Tqp += fe.N(a, qp) * sol[a];
+    const double kT = p->k_of_T ? p->k0 * (1. + p->k_beta * Tqp) : p->k0;
+    const double dkT = kind == 1 ? (p->k_of_T ? (1. + p->k_beta * Tqp) : 1.) : 0.;
+    const double dcond = dkT * p->thickness + kT * dth;  // d(k h)/dp
+    for (int i = 0; i < dim; ++i) {
+      double dTi = 0.;
+      for (int a = 0; a < nn; ++a) dTi += fe.dN(a, qp, i) * sol[a];
+      for (int a = 0; a < nn; ++a) f[a] += fe.JxW[qp] * fe.dN(a, qp, i) * (dcond * dTi);
+    }
+    if (p->heat_source != 0.)
+      for (int a = 0; a < nn; ++a) f[a] -= fe.JxW[qp] * fe.N(a, qp) * (p->heat_source * dth);
+  }
+}
+static void heat_side_sensitivity(const OracleProblem* p, const double* X, const Vec& sol, int side, double flux, double hc,
+                                  double Tamb, double emiss, int kind, Vec& f) {
+  const double dth = kind == 2 ? 1. : 0.;
+  const int n1 = side, n2 = (side + 1) % 4;
+  const double dx = X[n2 * 3] - X[n1 * 3], dy = X[n2 * 3 + 1] - X[n1 * 3 + 1], dz = X[n2 * 3 + 2] - X[n1 * 3 + 2];
+  const double L = std::sqrt(dx * dx + dy * dy + dz * dz);
+  for (int q = 0; q < 2; ++q) {
+    const double xi = GP2[q], JxW = 0.5 * L * GW2[q];
+    const double N[2] = {0.5 * (1. - xi), 0.5 * (1. + xi)};
+    const int nd[2] = {n1, n2};
+    const double temp = N[0] * sol[n1] + N[1] * sol[n2];
+    for (int a = 0; a < 2; ++a) {
+      f[nd[a]] += JxW * N[a] * (flux * dth);
+      if (hc != 0.) f[nd[a]] += JxW * N[a] * (dth * hc * (temp - Tamb));
+      if (emiss != 0.)
+        f[nd[a]] += JxW * N[a] * p->rad_sb_const * (emiss * dth) *
+                    (std::pow(temp + p->rad_T_ref_zero, 4.) - std::pow(Tamb + p->rad_T_ref_zero, 4.));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // elem-ops layer
 // ---------------------------------------------------------------------------------------------
@@ -1283,7 +1328,36 @@ int oracle_sensitivity_assemble(const OracleProblem* p, const double* X, int64_t
 // isotropic property card: kind 1 = E0, 2 = nu; every element depends on it (no ElemParameterDependence skip)
 int oracle_sensitivity_assemble_param(const OracleProblem* p, const double* X, int kind, double* dres_dp) {
   const ElemInfo ei = elem_info(p->elem_type);
-  if (p->elem_type == ORACLE_QUAD4) return 3;
+  if (p->elem_type == ORACLE_QUAD4) {  // heat conduction: kind 1 = k0, kind 2 = section thickness
+    if (p->nv != 1) return 3;
+    const int64_t n_dof = p->n_nodes;
+    std::fill(dres_dp, dres_dp + n_dof, 0.);
+    SideLoadIndex sl;
+    sl.build(p);
+    std::vector<int64_t> di;
+    std::vector<double> Xe;
+    Vec sol, vec;
+    for (int64_t e = 0; e < p->n_elem; ++e) {
+      if (p->diag_elem && p->diag_elem[e]) continue;
+      dof_indices(p, e, ei.nn, di);
+      const int nd = int(di.size());
+      sol.resize(nd);
+      for (int i = 0; i < nd; ++i) sol[i] = X[di[i]];
+      gather_coords(p, e, ei.nn, Xe);
+      FE fe;
+      fe_init(p->elem_type, Xe.data(), fe);
+      vec.assign(nd, 0.);
+      heat_elem_sensitivity(p, fe, sol, kind, vec);
+      for (int64_t k = sl.ptr[e]; k < sl.ptr[e + 1]; ++k) {
+        const int64_t l = sl.idx[k];
+        heat_side_sensitivity(p, Xe.data(), sol, sl.side[k], sl.press[k], p->side_conv_coeff ? p->side_conv_coeff[l] : 0.,
+                              p->side_T_amb ? p->side_T_amb[l] : 0., p->side_emissivity ? p->side_emissivity[l] : 0., kind, vec);
+      }
+      constrain(p, di, nullptr, &vec);
+      for (int i = 0; i < nd; ++i) dres_dp[di[i]] += vec[i];
+    }
+    return 0;
+  }
   if (p->thermal) return 4;  // 3D thermal_residual_sensitivity is libmesh_error() (solid_element_3d.cpp:1093-1104)
   const int64_t n_dof = p->n_nodes * p->nv;
   std::fill(dres_dp, dres_dp + n_dof, 0.);

@@ -157,7 +157,7 @@ class Problem:
         return out
 
     def sensitivity_assemble_param(self, X, kind):
-        """dR/dp for a Parameter of the isotropic card: kind 1 = E0, 2 = nu."""
+        """dR/dp for a Parameter of the cards: 3D solids kind 1 = E0, 2 = nu; QUAD4 heat conduction kind 1 = k0, 2 = thickness."""
         out = np.empty(self.n_dof)
         rc = lib().oracle_sensitivity_assemble_param(C.byref(self.s), _p(X), int(kind), _p(out))
         assert rc == 0, rc

@@ -723,6 +723,44 @@ def test_quad4_heat_surface_radiation_side_loads(built):
     assert np.abs(R - R0).max() > 1e-6 * np.abs(R0).max() and np.abs(J - J0).max() > 0  # the radiation is there
 
 
+@pytest.mark.parametrize("k_of_T", [0, 1])
+@pytest.mark.parametrize("struct", [True, False])
+def test_quad4_heat_sensitivity_assemble_conductivity_and_thickness(built, k_of_T, struct, monkeypatch):
+    # sensitivity_assemble of the heat-conduction system for the conductivity k0 and the section thickness
+    # (heat_conduction_elem_base.cpp:552-617 + the load sensitivities), with a source and flux / convection / radiation sides
+    if not struct:
+        monkeypatch.setenv("MASTB200_NO_STRUCT", "1")
+    nx, ny = 33, 17
+    xyz, conn = mesh.build_square(nx, ny, 1.2, 0.7)
+    rng = np.random.default_rng(4)
+    inner = (xyz[:, 0] > 0) & (xyz[:, 0] < 1.2) & (xyz[:, 1] > 0) & (xyz[:, 1] < 0.7)
+    xyz[inner, :2] += 0.01 * rng.uniform(-1, 1, (inner.sum(), 2))
+    con = np.isclose(xyz[:, 0], 0.0).astype(np.uint8)
+    top = (np.arange(nx, dtype=np.int32) + (ny - 1) * nx)
+    right = (np.arange(ny, dtype=np.int32) * nx + nx - 1)
+    se = np.concatenate([top, right, top[:4]])
+    sid = np.concatenate([np.full(nx, 2, np.int32), np.ones(ny, np.int32), np.full(4, 2, np.int32)])
+    flux = np.concatenate([np.zeros(nx), np.zeros(ny), np.full(4, 3.0e2)])
+    hc = np.concatenate([np.zeros(nx), np.full(ny, 35.0), np.zeros(4)])
+    Tamb = np.concatenate([np.full(nx, 3.0), np.full(ny, 290.0), np.zeros(4)])
+    eps = np.concatenate([0.6 + 0.3 * rng.uniform(size=nx), np.zeros(ny), np.zeros(4)])
+    prob = O.Problem(O.QUAD4, xyz, conn, 1, constrained=con, k0=237.0, k_beta=1e-3, k_of_T=k_of_T, thickness=0.06,
+                     heat_source=1.0e4, side_elem=se, side_id=sid, side_pressure=flux, side_conv_coeff=hc, side_T_amb=Tamb,
+                     side_emissivity=eps, rad_sb_const=5.670374419e-8, rad_T_ref_zero=273.15)
+    T = _temperature(prob.n_dof)
+    ctx = prob.make_context(0)
+    for param, kind in ((3, 1), (4, 2)):   # MASTB200_PARAM_K0, MASTB200_PARAM_THICKNESS
+        out = np.full(prob.n_dof, np.nan)
+        ctx.sensitivity_assemble(T, out, param=param)
+        _close(out, prob.sensitivity_assemble_param(T, kind))
+    # the card is back in place afterwards
+    R = np.full(prob.n_dof, np.nan)
+    ctx.residual_and_jacobian(T, R, None)
+    _close(R, prob.residual_and_jacobian(T)[0])
+    with pytest.raises(Exception):
+        ctx.sensitivity_assemble(T, out, param=1)
+
+
 # ---- round 2: sensitivity_assemble as a vector, linearized product, point loads, thermoelastic compliance -----------
 def _solid(elem_type, simp=True, jitter=0.2, loads=True, **kw):
     nx, ny, nz = (5, 4, 3) if elem_type == 8 else (3, 2, 2)

@@ -306,6 +306,43 @@ def test_heat_surface_radiation_jacobian_is_the_derivative_of_the_residual(built
     assert np.isclose(f_u.sum(), 5.670374419e-8 * 0.8 * 0.06 * L * (400.0 ** 4 - 300.0 ** 4), rtol=1e-12)
 
 
+def test_heat_parameter_sensitivities_are_the_derivative_of_the_residual(built):
+    # elem_sensitivity_calculations of the heat-conduction system (heat_conduction_nonlinear_assembly.cpp:100-116) for the
+    # conductivity k0 (kind 1) and the section thickness (kind 2): central differences of the assembled residual in the
+    # parameter, with a volume source, flux + convection + radiation sides and a Dirichlet edge
+    nx, ny = 6, 4
+    xyz, conn = mesh.build_square(nx, ny, 1.2, 0.7)
+    rng = np.random.default_rng(11)
+    inner = (xyz[:, 0] > 0) & (xyz[:, 0] < 1.2) & (xyz[:, 1] > 0) & (xyz[:, 1] < 0.7)
+    xyz[inner, :2] += 0.03 * rng.uniform(-1, 1, (inner.sum(), 2))
+    con = np.isclose(xyz[:, 0], 0.0).astype(np.uint8)
+    top = (np.arange(nx, dtype=np.int32) + (ny - 1) * nx)
+    right = (np.arange(ny, dtype=np.int32) * nx + nx - 1)
+    se = np.concatenate([top, right]); sid = np.concatenate([np.full(nx, 2, np.int32), np.ones(ny, np.int32)])
+    flux = np.concatenate([np.full(nx, 3.0e2), np.zeros(ny)])
+    hc = np.concatenate([np.zeros(nx), np.full(ny, 35.0)])
+    Tamb = np.concatenate([np.full(nx, 280.0), np.full(ny, 290.0)])
+    eps = np.concatenate([np.full(nx, 0.7), np.zeros(ny)])
+    T = 300 + 50 * rng.uniform(size=len(xyz))
+
+    def prob(k0, th, k_of_T):
+        return O.Problem(O.QUAD4, xyz, conn, 1, constrained=con, k0=k0, k_beta=1e-3, k_of_T=k_of_T, thickness=th,
+                         heat_source=1.0e4, side_elem=se, side_id=sid, side_pressure=flux, side_conv_coeff=hc,
+                         side_T_amb=Tamb, side_emissivity=eps, rad_sb_const=5.670374419e-8, rad_T_ref_zero=273.15)
+
+    for k_of_T in (0, 1):
+        p0 = prob(237.0, 0.06, k_of_T)
+        dk = p0.sensitivity_assemble_param(T, 1)
+        dh = p0.sensitivity_assemble_param(T, 2)
+        fd_k = (prob(238.0, 0.06, k_of_T).residual_and_jacobian(T)[0] - prob(236.0, 0.06, k_of_T).residual_and_jacobian(T)[0]) / 2.0
+        fd_h = (prob(237.0, 0.07, k_of_T).residual_and_jacobian(T)[0] - prob(237.0, 0.05, k_of_T).residual_and_jacobian(T)[0]) / 0.02
+        # the residual is linear in either parameter: central differences are exact up to rounding
+        assert np.abs(dk - fd_k).max() <= 1e-10 * np.abs(fd_k).max()
+        assert np.abs(dh - fd_h).max() <= 1e-10 * np.abs(fd_h).max()
+        assert np.all(dk[con.astype(bool)] == 0.0) and np.all(dh[con.astype(bool)] == 0.0)
+        assert np.abs(dh).max() > 0 and np.abs(dk).max() > 0
+
+
 def test_plate_von_karman_tangent_is_exact_where_the_reference_is_consistent():
     """StructuralElement2D with NONLINEAR_STRAIN (structural_element_2d.cpp:1765-2019): the tangent equals the derivative of
     the residual for a pure bending state (von Karman terms alone) and, without section offset, for a pure membrane state
