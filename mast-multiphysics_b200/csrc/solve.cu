@@ -18,6 +18,8 @@
 // refresh the ghost values of p before every product and add the scalars over the ranks (context.cu, NCCL).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace mastb200 {
@@ -56,7 +58,14 @@ __global__ void __launch_bounds__(128) bj_setup_kernel(int64_t n_owned, const in
   m[8] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
 }
 
-// y_A = sum_c K_Ac x_c for the owned nodes; partial[block] = sum over the block's nodes of x_A . y_A (if partial)
+// y_A = sum_c K_Ac x_c for the owned nodes; partial[block] = sum over the block's nodes of x_A . y_A (if partial).
+// Lane = position p = 3 c + j of a scalar row (three positions per lane and chunk of 96): the x value of a position is
+// loaded once and serves the node's three rows.  The product is latency-bound unless the dependent round trips
+// row pointer -> neighbour ids -> x are taken out of the node's own iteration: the row pointers arrive two iterations
+// ahead and the neighbour ids of the first chunk one iteration ahead, so the nine streaming 256-byte runs of J, the x
+// values and the next node's ids are all issued before the first dependent instruction (the one-value-per-iteration loop
+// this replaces ran at 1.95 TB/s).  J is read once per product: evict-first (ld.global.cs), so that the stream does not
+// push x out of L2.  The grid is one resident wave (launch_spmv_node).
 __global__ void __launch_bounds__(256) spmv_node_kernel(int64_t n_owned, const int32_t* __restrict__ owned,
                                                         const int64_t* __restrict__ nbr_ptr, const int32_t* __restrict__ nbr,
                                                         const double* __restrict__ J, const double* __restrict__ x,
@@ -64,16 +73,62 @@ __global__ void __launch_bounds__(256) spmv_node_kernel(int64_t n_owned, const i
   __shared__ double red[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double blocksum = 0.;
-  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < n_owned; r += (int64_t)gridDim.x * 8) {
-    const int64_t b = nbr_ptr[r];
-    const int nnb = (int)(nbr_ptr[r + 1] - b), rl = 3 * nnb;
+  const int64_t stride = (int64_t)gridDim.x * 8;
+  int64_t r = (int64_t)blockIdx.x * 8 + warp;
+  int jj[3], cc[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { cc[k] = (32 * k + lane) / 3; jj[k] = 32 * k + lane - 3 * cc[k]; }
+  // pipeline: (b, e) of this node, (b1, e1) of the next one, ids nb[] of this node's first chunk
+  int64_t b = 0, e = 0, b1 = 0, e1 = 0;
+  int32_t nb[3] = {-1, -1, -1};
+  if (r < n_owned) { b = nbr_ptr[r]; e = nbr_ptr[r + 1]; }
+  if (r + stride < n_owned) { b1 = nbr_ptr[r + stride]; e1 = nbr_ptr[r + stride + 1]; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) nb[k] = 32 * k + lane < 3 * (int)(e - b) ? __ldg(nbr + b + cc[k]) : -1;
+  for (; r < n_owned; r += stride) {
+    const int rl = 3 * (int)(e - b);
     const double* v = J + 9 * b;
+    double j0[3], j1[3], j2[3], xv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int p = 32 * k + lane;
+      const bool ok = p < rl;
+      j0[k] = ok ? __ldcs(v + p) : 0.;
+      j1[k] = ok ? __ldcs(v + rl + p) : 0.;
+      j2[k] = ok ? __ldcs(v + 2 * rl + p) : 0.;
+      xv[k] = nb[k] >= 0 ? x[(int64_t)nb[k] * 3 + jj[k]] : 0.;
+    }
+    // next node: ids of its first chunk, row pointers of the one after
+    const int64_t bc = b;
+    b = b1; e = e1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nb[k] = 32 * k + lane < 3 * (int)(e - b) ? __ldg(nbr + b + cc[k]) : -1;
+    if (r + 2 * stride < n_owned) { b1 = nbr_ptr[r + 2 * stride]; e1 = nbr_ptr[r + 2 * stride + 1]; } else { b1 = e1 = 0; }
     double a0 = 0., a1 = 0., a2 = 0.;
-    for (int t = lane; t < 3 * rl; t += 32) {
-      const int i = t / rl, rem = t - i * rl;
-      const int c = rem / 3, j = rem - 3 * c;
-      const double prod = v[t] * x[(int64_t)nbr[b + c] * 3 + j];
-      if (i == 0) a0 += prod; else if (i == 1) a1 += prod; else a2 += prod;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      a0 += j0[k] * xv[k];
+      a1 += j1[k] * xv[k];
+      a2 += j2[k] * xv[k];
+    }
+    for (int p0 = 96; p0 < rl; p0 += 96) {  // rows with more than 32 neighbours (HEX27): the remaining chunks
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int p = p0 + 32 * k + lane;
+        const bool ok = p < rl;
+        const int c = p / 3;
+        const int32_t id = ok ? __ldg(nbr + bc + c) : -1;
+        j0[k] = ok ? __ldcs(v + p) : 0.;
+        j1[k] = ok ? __ldcs(v + rl + p) : 0.;
+        j2[k] = ok ? __ldcs(v + 2 * rl + p) : 0.;
+        xv[k] = ok ? x[(int64_t)id * 3 + (p - 3 * c)] : 0.;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        a0 += j0[k] * xv[k];
+        a1 += j1[k] * xv[k];
+        a2 += j2[k] * xv[k];
+      }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -223,8 +278,13 @@ cudaError_t launch_spmv_node(int64_t n_owned, const int32_t* owned, const int64_
                              const double* x, double* y, double* partial, int sm_count, cudaStream_t s) {
   // partial (if any) has RB entries: the grid is RB blocks or fewer (unused entries are zeroed by the caller once)
   const int64_t want = (n_owned + 7) / 8;
-  const int grid = (int)(want < RB ? want : RB);
-  (void)sm_count;
+  static int per_sm = 0;
+  if (!per_sm) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spmv_node_kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+  }
+  int64_t wave = (int64_t)(sm_count > 0 ? sm_count : 148) * per_sm;  // one resident wave: no second, partly filled one
+  if (wave > RB) wave = RB;
+  const int grid = (int)(want < wave ? want : wave);
   spmv_node_kernel<<<grid, 256, 0, s>>>(n_owned, owned, nbr_ptr, nbr, J, x, y, partial);
   return cudaGetLastError();
 }
