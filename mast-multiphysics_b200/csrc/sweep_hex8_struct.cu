@@ -66,6 +66,9 @@ constexpr int O_FPK = O_NODE + 64 * 8;                  // [4 passes][8 lanes] p
 constexpr int O_ROT = O_FPK + 32 * 4;                   // [2 planes][NS] sum of 1e-20 * max(diag K_e) per node (nv = 6)
 constexpr int O_MISC = O_ROT + 2 * NS * 8;
 constexpr int SMEM_BYTES = O_MISC + 16;                 // variants without sensitivities end here
+constexpr int O_ZERO = (SMEM_BYTES + 15) & ~15;         // nv = 6: zeros, the source of the bulk stores of the rotational rows
+constexpr int ZERO_BYTES = 18 * 27 * 8;                 //   (three rows of 6 x 27 values: the longest run of one node)
+constexpr int SMEM_BYTES_NV6 = O_ZERO + ZERO_BYTES;     // (the same bytes hold the adjoint planes of the sensitivity variant)
 constexpr int O_ADJ = SMEM_BYTES;                       // [3 planes][3][NS] adjoint (fused density sensitivities)
 constexpr int O_GACC = O_ADJ + 3 * 3 * NS * 8;          // [2 planes][NS] G_n = adj . dR/d(rho_n) accumulators
 constexpr int O_GQ = O_GACC + 2 * NS * 8;               // [SW][4 el][8 nodes] nodal sums of the point values s_q
@@ -73,6 +76,7 @@ constexpr int SMEM_BYTES_SENS = O_GQ + SW * 4 * 8 * 8;
 static_assert(O_STAGE % 16 == 0 && O_XYZ % 16 == 0 && O_RHO % 8 == 0 && O_NODE % 8 == 0 && O_ROT % 8 == 0, "alignment");
 static_assert(SMEM_BYTES <= (kStructCtasPerSm == 1 ? 232448 : 115712), "shared-memory layout exceeds the per-CTA budget");
 static_assert(kStructCtasPerSm > 1 || SMEM_BYTES_SENS <= 232448, "shared-memory layout of the sensitivity variant exceeds 227 KB");
+static_assert(SMEM_BYTES_NV6 <= (kStructCtasPerSm == 1 ? 232448 : 115712), "shared-memory layout of the nv = 6 variant exceeds the per-CTA budget");
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -104,6 +108,13 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) 
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// TMA bulk store shared -> global (async proxy; both addresses and the size multiples of 16 bytes), one bulk group per call
+__device__ __forceinline__ void bulk_store(void* gmem_dst, unsigned smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
+               ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct Sm {
   double* arena;
@@ -121,6 +132,7 @@ struct Sm {
   double* gacc;
   double* gq;
   int* misc;
+  unsigned zero32;  // nv = 6: shared-space address of the zero block
 };
 
 // in-plane pair direction (A -> B, B after A in ijk order): 0 self, 1 (+1,0), 2 (-1,+1), 3 (0,+1), 4 (+1,+1)
@@ -519,14 +531,18 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
     auto at = [&](int x) { return x == dpos0 ? dv0 : (x == dpos1 ? dv1 : (x == dpos2 ? dv2 : 0.)); };
     double* base = Jrow + 18 * nnb;
     if (p.j_aligned32) {
-      const int head = (nnb & 1) ? 2 : 0;  // 36 nb0 + 18 nnb doubles: on a 32-byte boundary iff nnb is even
-      const int nch = (L - head) >> 2, tail = (L - head) & 3;
-      if (head && l8 == 0) stg128(base, at(0), at(1));
-      for (int k = l8; k < nch; k += 8) {
-        const int x = head + 4 * k;
-        stg256(base + x, at(x), at(x + 1), at(x + 2), at(x + 3));
-      }
-      if (tail && l8 == 7) stg128(base + L - 2, at(L - 2), at(L - 1));
+      // The run starts on a 16-byte boundary (36 nb0 + 18 nnb doubles) and is zero but for three values: the three aligned
+      // pairs that hold a diagonal entry go out as 16-byte stores, the four zero stretches between them as TMA bulk stores
+      // from the zero block (cp.async.bulk shared -> global: half of the matrix bytes of the six-variable layout never
+      // pass the LSU).  The bulk stores and the pair stores touch disjoint bytes: no ordering between the proxies needed.
+      const int P0 = dpos0 - 1, P1 = dpos1, P2 = dpos2 - 1;  // even positions of the three pairs
+      if (l8 < 4) {
+        const int lo = l8 == 0 ? 0 : (l8 == 1 ? P0 + 2 : (l8 == 2 ? P1 + 2 : P2 + 2));
+        const int hi = l8 == 0 ? P0 : (l8 == 1 ? P1 : (l8 == 2 ? P2 : L));
+        if (hi > lo) bulk_store(base + lo, sm.zero32, (unsigned)(hi - lo) * 8u);
+      } else if (l8 == 4) stg128(base + P0, 0., dv0);
+      else if (l8 == 5) stg128(base + P1, dv1, 0.);
+      else if (l8 == 6) stg128(base + P2, 0., dv2);
     } else {
       for (int x = l8; x < L; x += 8) base[x] = at(x);
     }
@@ -567,7 +583,12 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
   sm.adj = reinterpret_cast<double*>(smem_raw + O_ADJ);
   sm.gacc = reinterpret_cast<double*>(smem_raw + O_GACC);
   sm.gq = reinterpret_cast<double*>(smem_raw + O_GQ);
+  sm.zero32 = (unsigned)__cvta_generic_to_shared(smem_raw + O_ZERO);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (NV6) {  // written once (generic proxy), read by the bulk stores (async proxy) from the first flush on
+    for (int i = tid; i < ZERO_BYTES / 8; i += ST) reinterpret_cast<double*>(smem_raw + O_ZERO)[i] = 0.;
+    fence_proxy_async_smem();
+  }
   if (tid < 123) sm.tab[tid] = p.arr_off[tid];
   if (tid >= 128 && tid < 160) sm.fpk[tid - 128] = flush_pack((tid - 128) >> 3, (tid - 128) & 7);
   __syncthreads();
@@ -732,11 +753,12 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
       __syncthreads();
     }
   }
+  if (NV6) bulk_store_wait_all();  // the zero block must outlive the reads of the last bulk stores
 }
 
 }  // namespace
 
-size_t hex8_struct_smem_bytes() { return SMEM_BYTES; }
+size_t hex8_struct_smem_bytes() { return SMEM_BYTES_NV6 > SMEM_BYTES ? SMEM_BYTES_NV6 : SMEM_BYTES; }
 size_t hex8_struct_sens_smem_bytes() { return kStructCtasPerSm == 1 ? SMEM_BYTES_SENS : 0; }  // 0: variant not built
 int hex8_struct_threads() { return ST; }
 
@@ -760,7 +782,7 @@ cudaError_t launch_hex8_struct(const StructParams& p, int n_ctas, cudaStream_t s
     if (p.nv != 3 || !p.rho || !p.adj || kStructCtasPerSm != 1) return cudaErrorInvalidValue;
     e = go(hex8_struct_kernel<true, false, true>, 4, SMEM_BYTES_SENS);
   } else if (p.nv == 6) {
-    e = p.rho ? go(hex8_struct_kernel<true, true, false>, 3, SMEM_BYTES) : go(hex8_struct_kernel<false, true, false>, 2, SMEM_BYTES);
+    e = p.rho ? go(hex8_struct_kernel<true, true, false>, 3, SMEM_BYTES_NV6) : go(hex8_struct_kernel<false, true, false>, 2, SMEM_BYTES_NV6);
   } else {
     e = p.rho ? go(hex8_struct_kernel<true, false, false>, 1, SMEM_BYTES) : go(hex8_struct_kernel<false, false, false>, 0, SMEM_BYTES);
   }

@@ -4,7 +4,7 @@ import numpy as np, torch
 import mast_b200
 from mast_b200 import mesh
 for nv in (3, 6):
-    n = 100
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     xyz, conn = mesh.build_cube(n, n, n, 1.0, 1.0, 1.0, 8, jitter=0.2)
     ctx = mast_b200.Context(0)
     ctx.set_mesh(mast_b200.HEX8, xyz, conn)
