@@ -674,6 +674,8 @@ int ensure_struct_plan(mastb200_context* ctx) {
   for (int a = 0; a < 81; ++a) arr_off[42 + a] = kStructPosCr[a] * kStructSlots;
   CU(S.units.upload(sorted, ctx->stream));
   CU(S.arr_off.upload(arr_off, ctx->stream));
+  CU(S.zeros.ensure(kStructZeroDoubles));
+  CU(cudaMemsetAsync(S.zeros.p, 0, kStructZeroDoubles * sizeof(double), ctx->stream));
   CU(S.nbr_ptr.upload(ctx->pat.nbr_ptr, ctx->stream));
   CU(ctx->d_tile_counter.ensure(40));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1011,6 +1013,7 @@ int run_sweep(mastb200_context* ctx, const double* X, const double* adj, double*
     sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0; sp.nv = ctx->nv;
     sp.nbr_ptr = S.nbr_ptr.p; sp.arr_off = S.arr_off.p;
     sp.in1_off = kStructIn1Off; sp.cr0_off = kStructCr0Off; sp.cr1_off = kStructCr1Off;
+    sp.zeros = getenv("MASTB200_STRUCT_NO_TMA_CLEAR") ? nullptr : S.zeros.p;
     sp.xyz = p.xyz; sp.X = dX; sp.cmask = p.cmask; sp.J = dJ; sp.R = dR;
     sp.j_aligned32 = (reinterpret_cast<uintptr_t>(dJ) & 31) == 0 ? 1 : 0;
     sp.rho = ctx->rho_set ? (ctx->rho_ext ? ctx->rho_ext : ctx->d_rho.p) : nullptr;

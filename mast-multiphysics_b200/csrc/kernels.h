@@ -53,6 +53,7 @@ struct StructParams {
   const int64_t* nbr_ptr = nullptr;      // node-level CSR row pointer of the owned rows
   const int32_t* arr_off = nullptr;      // [123] offsets of the pair arrays within an IN (42) / CR (81) region
   int32_t in1_off = 0, cr0_off = 0, cr1_off = 0;
+  const double* zeros = nullptr;         // >= kStructZeroDoubles zeros, 16-byte aligned (lock-step kernel: bulk-copy clear), or null
   const double* xyz = nullptr;
   const double* X = nullptr;
   const uint8_t* cmask = nullptr;
@@ -65,6 +66,7 @@ struct StructParams {
   int32_t gl = 0;                        // slot kernel: Green-Lagrange strain, tangent only (R must be null)
   double E0 = 0., lam1 = 0., mu1 = 0., rho_min = 0., penalty = 1.;
 };
+constexpr int kStructZeroDoubles = 81 * 81 + 8;
 size_t hex8_struct_smem_bytes();
 size_t hex8_struct_sens_smem_bytes();   // of the variant with fused density sensitivities (0: not built for this CTA shape)
 int hex8_struct_threads();

@@ -78,6 +78,18 @@ static_assert(SMEM_BYTES <= (kStructCtasPerSm == 1 ? 232448 : 115712), "shared-m
 static_assert(kStructCtasPerSm > 1 || SMEM_BYTES_SENS <= 232448, "shared-memory layout of the sensitivity variant exceeds 227 KB");
 static_assert(SMEM_BYTES_NV6 <= (kStructCtasPerSm == 1 ? 232448 : 115712), "shared-memory layout of the nv = 6 variant exceeds the per-CTA budget");
 
+// Accumulator regions as 16-byte aligned ranges [lo, hi) of the arena (doubles): the bulk-copy clear may touch the padding
+// between regions but nothing that is live.  kTmaClear is false for a layout without that padding.
+constexpr int even_dn(int x) { return x & ~1; }
+constexpr int even_up(int x) { return (x + 1) & ~1; }
+constexpr int IN0_LO = 0, IN0_HI = even_up(42 * NS);
+constexpr int IN1_LO = even_dn(kStructIn1Off), IN1_HI = even_up(kStructIn1Off + 42 * NS);
+constexpr int CR0_LO = even_dn(kStructCr0Off), CR0_HI = even_up(kStructCr0Off + 81 * NS);
+constexpr int CR1_LO = even_dn(kStructCr1Off), CR1_HI = even_up(kStructCr1Off + 81 * NS);
+constexpr bool kTmaClear = IN0_HI <= kStructIn1Off && IN1_LO >= 42 * NS && IN1_HI <= kStructCr0Off &&
+                           CR0_LO >= kStructIn1Off + 42 * NS && CR0_HI <= kStructCr1Off && CR1_LO >= kStructCr0Off + 81 * NS &&
+                           CR1_HI <= kStructArenaDoubles && CR0_HI - CR0_LO <= kStructZeroDoubles && O_ARENA % 16 == 0;
+
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -112,6 +124,24 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 __device__ __forceinline__ void bulk_store(void* gmem_dst, unsigned smem_src, unsigned bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n\tcp.async.bulk.commit_group;"
                ::"l"(gmem_dst), "r"(smem_src), "r"(bytes) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; mbarrier helpers (one arriving thread)
+__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void* gmem_src, unsigned bytes, unsigned mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(gmem_src), "r"(bytes), "r"(mbar) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  unsigned ok = 0;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+  } while (!ok);
 }
 __device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -589,6 +619,12 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
     for (int i = tid; i < ZERO_BYTES / 8; i += ST) reinterpret_cast<double*>(smem_raw + O_ZERO)[i] = 0.;
     fence_proxy_async_smem();
   }
+  // bulk-copy clear of the accumulators: the mbarrier lives in the second half of the misc words
+  const unsigned clear_bar = (unsigned)__cvta_generic_to_shared(smem_raw + O_MISC + 8);
+  const bool tma_clear = kTmaClear && p.zeros != nullptr;
+  unsigned clear_phase = 0u;
+  bool clear_pending = false;
+  if (tma_clear && tid == 0) mbar_init(clear_bar, 1u);
   if (tid < 123) sm.tab[tid] = p.arr_off[tid];
   if (tid >= 128 && tid < 160) sm.fpk[tid - 128] = flush_pack((tid - 128) >> 3, (tid - 128) & 7);
   __syncthreads();
@@ -718,6 +754,11 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
               geometry_phase<SIMP, SENS>(p, sm, s, ley * TCX + lex, q, my_stage + lane * QS, sm.gq + warp * 32 + (el & 3) * 8, live);
           }
           __syncwarp();
+          if (clear_pending) {  // the zeros of the recycled accumulators have landed (issued after the previous flush)
+            mbar_wait(clear_bar, clear_phase);
+            clear_phase ^= 1u;
+            clear_pending = false;
+          }
           if (s & 1) {
 #pragma unroll 1
             for (int c = c_lo; c < c_lo + STAGE_EL; ++c) {
@@ -735,6 +776,11 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
       }
       __syncthreads();
       const bool do_flush = s >= u.z0;
+      if (clear_pending) {  // top node plane: no element phase has waited for the clear
+        mbar_wait(clear_bar, clear_phase);
+        clear_phase ^= 1u;
+        clear_pending = false;
+      }
       if (do_flush) flush_plane<NV6>(p, sm, arena32, s, u.nox * u.noy, (int64_t)s * plane_nodes, warp, lane);
       if (cm_on && s + 2 <= p.nz) sm.cm[((s + 2) & 3) * NSB + cm_dst] = (uint8_t)cmv;
       cp_async_wait_all();
@@ -742,10 +788,28 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
       // the accumulators of node plane s (-> plane s+2) and of the cross pairs s-1 -> s (-> s+1 -> s+2) start from zero
       {
         const int par = s & 1;
-        double* zi = sm.arena + (par ? p.in1_off : 0);
-        for (int i = tid; i < 42 * NS; i += ST) zi[i] = 0.;
-        double* zc = sm.arena + (par ? p.cr0_off : p.cr1_off);
-        for (int i = tid; i < 81 * NS; i += ST) zc[i] = 0.;
+        if (tma_clear) {
+          // two TMA bulk copies from a block of zeros in global memory (L2-resident) instead of 20 shared-memory stores
+          // per thread: issued by one thread, they land while the CTA runs the geometry of the next element plane; every
+          // thread waits on the mbarrier before its first accumulate.  The last plane of a unit needs none (the next
+          // unit's prologue clears the whole arena).
+          if (s + 1 < u.z1) {
+            if (tid == 0) {
+              fence_proxy_async_smem();  // the flush's reads (generic proxy, ordered by the barrier above) before the async writes
+              const int ilo = par ? IN1_LO : IN0_LO, ihi = par ? IN1_HI : IN0_HI;
+              const int clo = par ? CR0_LO : CR1_LO, chi = par ? CR0_HI : CR1_HI;
+              mbar_arrive_expect_tx(clear_bar, (unsigned)(ihi - ilo + chi - clo) * 8u);
+              bulk_load(arena32 + ilo * 8, p.zeros, (unsigned)(ihi - ilo) * 8u, clear_bar);
+              bulk_load(arena32 + clo * 8, p.zeros, (unsigned)(chi - clo) * 8u, clear_bar);
+            }
+            clear_pending = true;
+          }
+        } else {
+          double* zi = sm.arena + (par ? p.in1_off : 0);
+          for (int i = tid; i < 42 * NS; i += ST) zi[i] = 0.;
+          double* zc = sm.arena + (par ? p.cr0_off : p.cr1_off);
+          for (int i = tid; i < 81 * NS; i += ST) zc[i] = 0.;
+        }
         if (tid < NS) sm.cnt[tid] = 0;
         if (NV6 && tid < NS) sm.rot[par * NS + tid] = 0.;
         if (SENS && tid < NS) sm.gacc[par * NS + tid] = 0.;

@@ -1,0 +1,131 @@
+// Joint simulated annealing of the pair-array placement of the structured HEX8 sweep (struct_layout.h) against BOTH
+// shared-memory access patterns: the accumulate of the element phase (12 read-modify-writes per element visit, lane =
+// (tile row, column pair)) and the loads of the flush (lane = (node, direction), nine components per direction).
+// bank_search.py models the accumulate only; ncu shows as many conflict wavefronts in the flush.  Banks are 8 bytes wide,
+// 16 per wavefront; NS = 81 = 1 (mod 16), so the residue of array a is its position modulo 16.
+//   g++ -O2 -o /tmp/bank_search2 tools/design/bank_search2.cpp && /tmp/bank_search2 SEED ITERS  -> JSON on stdout
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+static const int TCX = 9, NS = 81;
+static const int KI[6] = {0, 1, 2, 0, 0, 1}, KJ[6] = {0, 1, 2, 1, 2, 2};
+static int inplane_dir(int di, int dj) { return dj == 0 ? (di == 0 ? 0 : 1) : 3 + di; }
+static int in_array(int dir, int comp) { return dir == 0 ? comp : 6 + (dir - 1) * 9 + comp; }
+static int cr_array(int di, int dj, int comp) { return 42 + ((dj + 1) * 3 + (di + 1)) * 9 + comp; }
+struct Acc { int buf, arr, so; };  // buf: 0 IN0, 1 IN1, 2 CR0, 3 CR1; arr: tab index 0..122
+std::vector<std::vector<Acc>> groups_acc, groups_flush;
+static void build() {
+  // accumulate (make_lane of sweep_hex8_struct.cu, PAR = 0): lane (m = lane >> 2, q4 = lane & 3), bb, k
+  for (int bb = 0; bb < 2; ++bb)
+    for (int k = 0; k < 6; ++k)
+      for (int half = 0; half < 2; ++half) {
+        std::vector<Acc> g;
+        for (int lane = half * 16; lane < half * 16 + 16; ++lane) {
+          const int m = lane >> 2, q4 = lane & 3, b = 2 * q4 + bb;
+          int lo = m, hi = b, ci = KI[k], cj = KJ[k], comp;
+          if (m == b) comp = k;
+          else {
+            if (m > b) { lo = b; hi = m; ci = KJ[k]; cj = KI[k]; if (KI[k] == KJ[k]) continue; }
+            comp = ci * 3 + cj;
+          }
+          const int lx = lo & 1, ly = (lo >> 1) & 1, lz = lo >> 2;
+          const int ox = (hi & 1) - lx, oy = ((hi >> 1) & 1) - ly, oz = (hi >> 2) - lz;
+          const int so = ly * TCX + lx;
+          if (oz == 0) g.push_back({lz ? 1 : 0, in_array(inplane_dir(ox, oy), comp), so});
+          else g.push_back({2, cr_array(ox, oy, comp), so});
+        }
+        groups_acc.push_back(g);
+      }
+  // flush (flush_plane, par = 0): half-warp = two nodes (slots differ by delta) x eight directions of pass t; comp c
+  for (int delta : {1, 1, 1, 1, 1, 1, 1, 3})  // one node pair in eight straddles a tile row (7 owned nodes per row)
+    for (int t = 0; t < 4; ++t)
+      for (int c = 0; c < 9; ++c) {
+        std::vector<Acc> g;
+        for (int n = 0; n < 2; ++n)
+          for (int l8 = 0; l8 < 8; ++l8) {
+            const int d = 8 * t + l8;
+            if (d >= 27 || d == 13) continue;  // self: its own six loads, one lane per node
+            const int dk = d / 9 - 1, dj = (d / 3) % 3 - 1, di = d % 3 - 1;
+            const bool tr = d < 13;
+            const int sdi = tr ? -di : di, sdj = tr ? -dj : dj;
+            const int a0 = dk == 0 ? in_array(inplane_dir(sdi, sdj), 0) : cr_array(sdi, sdj, 0);
+            const int nsh = dj * TCX + di;
+            const int buf = dk == 0 ? 0 : (dk > 0 ? 2 : 3);
+            g.push_back({buf, a0 + c, 40 + n * delta + (tr ? nsh : 0)});
+          }
+        groups_flush.push_back(g);
+      }
+}
+int pin[42], pcr[81], base1, base2;
+static inline int residue(const Acc& a) {
+  const int pos = a.arr < 42 ? pin[a.arr] : pcr[a.arr - 42];
+  const int bs = a.buf == 0 ? 0 : (a.buf == 1 ? base1 : (a.buf == 2 ? base2 : base2 + base1));
+  return (pos * NS + bs + a.so) & 15;
+}
+static int group_cost(const std::vector<Acc>& g) {
+  int cnt[16] = {0}, mx = 0;
+  for (const Acc& a : g) mx = std::max(mx, ++cnt[residue(a)]);
+  return mx;
+}
+static void costs(int& ca, int& cf) {
+  ca = cf = 0;
+  for (auto& g : groups_acc) ca += group_cost(g);
+  for (auto& g : groups_flush) cf += group_cost(g);
+}
+int main(int argc, char** argv) {
+  const int seed = argc > 1 ? atoi(argv[1]) : 0;
+  const long iters = argc > 2 ? atol(argv[2]) : 2000000;
+  build();
+  std::mt19937 rng(seed);
+  for (int i = 0; i < 42; ++i) pin[i] = i;
+  for (int i = 0; i < 81; ++i) pcr[i] = i;
+  std::shuffle(pin, pin + 42, rng); std::shuffle(pcr, pcr + 81, rng);
+  base1 = (rng() & 1) * 8; base2 = rng() & 15;
+  // objective in shared-memory wavefronts per element: accumulate = load + store at 1.34 visits per element;
+  // flush groups: 8 node-pair samples, two nodes each
+  auto obj = [](int ca, int cf) { return 2.68 * ca + cf / 16.0; };
+  int ca, cf;
+  if (argc > 3) {  // evaluate a layout: 42 + 81 positions, base1, base2 as whitespace-separated integers
+    FILE* f = fopen(argv[3], "r");
+    for (int i = 0; i < 42; ++i) if (fscanf(f, "%d", &pin[i]) != 1) return 1;
+    for (int i = 0; i < 81; ++i) if (fscanf(f, "%d", &pcr[i]) != 1) return 1;
+    if (fscanf(f, "%d %d", &base1, &base2) != 2) return 1;
+    fclose(f);
+    costs(ca, cf);
+    printf("accumulate %d (ideal 24), flush %d (ideal %d), objective %.2f\n", ca, cf, (int)groups_flush.size(), obj(ca, cf));
+    return 0;
+  }
+  costs(ca, cf);
+  double cur = obj(ca, cf), best = cur;
+  int bpin[42], bpcr[81], bb1 = base1, bb2 = base2, bca = ca, bcf = cf;
+  std::copy(pin, pin + 42, bpin); std::copy(pcr, pcr + 81, bpcr);
+  std::uniform_real_distribution<double> U(0., 1.);
+  for (long it = 0; it < iters; ++it) {
+    const double T = std::max(0.05, 3.0 * (1. - double(it) / iters));
+    const int w = rng() % 10;
+    int i = 0, j = 0, old = 0;
+    if (w < 4) { i = rng() % 42; j = rng() % 42; std::swap(pin[i], pin[j]); }
+    else if (w < 9) { i = rng() % 81; j = rng() % 81; std::swap(pcr[i], pcr[j]); }
+    else if (rng() & 1) { old = base1; base1 = (rng() & 1) * 8; }
+    else { old = base2; base2 = rng() & 15; i = 1; }
+    costs(ca, cf);
+    const double c = obj(ca, cf);
+    if (c <= cur || U(rng) < std::exp((cur - c) / T)) {
+      cur = c;
+      if (c < best) { best = c; std::copy(pin, pin + 42, bpin); std::copy(pcr, pcr + 81, bpcr); bb1 = base1; bb2 = base2; bca = ca; bcf = cf; }
+    } else {
+      if (w < 4) std::swap(pin[i], pin[j]);
+      else if (w < 9) std::swap(pcr[i], pcr[j]);
+      else if (i == 0) base1 = old; else base2 = old;
+    }
+  }
+  printf("{\"cost\": %d, \"ideal\": 24, \"flush_cost\": %d, \"flush_ideal\": %d, \"objective\": %.2f, \"pin\": [", bca, bcf, (int)groups_flush.size(), best);
+  for (int i = 0; i < 42; ++i) printf("%d%s", bpin[i], i < 41 ? ", " : "");
+  printf("], \"pcr\": [");
+  for (int i = 0; i < 81; ++i) printf("%d%s", bpcr[i], i < 80 ? ", " : "");
+  printf("], \"base\": [0, %d, %d]}\n", bb1, bb2);
+  return 0;
+}
