@@ -526,10 +526,24 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
         }
         if (!NV6) {
           double* dst = Jrow + 3 * c;
+          if (p.j_aligned32) {
+            // a row piece of three values starts at an even or an odd double (9 nb0 + i rs + 3 c): one 16-byte store of the
+            // aligned pair and one 8-byte store of the third value, chosen without a branch -- two store instructions
+            // per row piece instead of three, and every 32-byte sector is touched by two instructions instead of three
+            const int par0 = ((int)nb0 + c) & 1;
 #pragma unroll
-          for (int i = 0; i < 3; ++i)
+            for (int i = 0; i < 3; ++i) {
+              double* d = dst + i * rs;
+              const bool odd = ((par0 + i * rs) & 1) != 0;
+              stg128(odd ? d + 1 : d, odd ? K[i][1] : K[i][0], odd ? K[i][2] : K[i][1]);
+              *(odd ? d : d + 2) = odd ? K[i][0] : K[i][2];
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+              for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+          }
         } else {
           // 6-variable system, translational rows of this column block: [K_i0 K_i1 K_i2 0 0 0].  A row piece starts at a
           // multiple of 48 bytes (36 nb0 + 6 c + i * 6 nnb doubles), i.e. on a 32-byte boundary for every other piece:
