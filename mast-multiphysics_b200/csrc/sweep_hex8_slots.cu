@@ -474,10 +474,25 @@ __device__ __forceinline__ void gather_item(const StructParams& p, const Sm& sm,
       }
     }
     double* dst = p.J + 9 * it.nb0 + 3 * c;
+    if (p.j_aligned32) {
+      // a row piece starts at an even or an odd double (9 nb0 + i rs + 3 c): one 16-byte store of the aligned pair and one
+      // 8-byte store of the third value, chosen without a branch (as in the lock-step kernel's flush)
+      const int par0 = ((int)it.nb0 + c) & 1;
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+      for (int i = 0; i < 3; ++i) {
+        double* d = dst + i * rs;
+        const bool odd = ((par0 + i * rs) & 1) != 0;
+        double* d2 = odd ? d + 1 : d;
+        const double a = odd ? K[i][1] : K[i][0], b = odd ? K[i][2] : K[i][1];
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(d2), "d"(a), "d"(b) : "memory");
+        *(odd ? d : d + 2) = odd ? K[i][0] : K[i][2];
+      }
+    } else {
 #pragma unroll
-      for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dst[i * rs + j] = K[i][j];
+    }
   }
 }
 

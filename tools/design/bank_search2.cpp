@@ -75,6 +75,27 @@ static void costs(int& ca, int& cf) {
   for (auto& g : groups_acc) ca += group_cost(g);
   for (auto& g : groups_flush) cf += group_cost(g);
 }
+// incremental evaluation: the groups an array takes part in, and the cached cost of every group
+std::vector<int> arr_groups[123];  // group ids: < n_acc accumulate, >= n_acc flush
+std::vector<int> gcost;
+static const std::vector<Acc>& group(int id) { return id < (int)groups_acc.size() ? groups_acc[id] : groups_flush[id - groups_acc.size()]; }
+static void index_groups() {
+  const int n = (int)(groups_acc.size() + groups_flush.size());
+  gcost.assign(n, 0);
+  for (int id = 0; id < n; ++id)
+    for (const Acc& a : group(id))
+      if (std::find(arr_groups[a.arr].begin(), arr_groups[a.arr].end(), id) == arr_groups[a.arr].end()) arr_groups[a.arr].push_back(id);
+}
+static void recost_all(int& ca, int& cf) {
+  ca = cf = 0;
+  for (int id = 0; id < (int)gcost.size(); ++id) { gcost[id] = group_cost(group(id)); (id < (int)groups_acc.size() ? ca : cf) += gcost[id]; }
+}
+static void recost_arrays(int a1, int a2, int& ca, int& cf) {  // after the positions of arrays a1, a2 (tab indices) changed
+  static std::vector<int> touched; touched.clear();
+  for (int id : arr_groups[a1]) touched.push_back(id);
+  for (int id : arr_groups[a2]) if (std::find(touched.begin(), touched.end(), id) == touched.end()) touched.push_back(id);
+  for (int id : touched) { const int c = group_cost(group(id)); (id < (int)groups_acc.size() ? ca : cf) += c - gcost[id]; gcost[id] = c; }
+}
 int main(int argc, char** argv) {
   const int seed = argc > 1 ? atoi(argv[1]) : 0;
   const long iters = argc > 2 ? atol(argv[2]) : 2000000;
@@ -98,28 +119,31 @@ int main(int argc, char** argv) {
     printf("accumulate %d (ideal 24), flush %d (ideal %d), objective %.2f\n", ca, cf, (int)groups_flush.size(), obj(ca, cf));
     return 0;
   }
-  costs(ca, cf);
+  index_groups();
+  recost_all(ca, cf);
   double cur = obj(ca, cf), best = cur;
   int bpin[42], bpcr[81], bb1 = base1, bb2 = base2, bca = ca, bcf = cf;
   std::copy(pin, pin + 42, bpin); std::copy(pcr, pcr + 81, bpcr);
   std::uniform_real_distribution<double> U(0., 1.);
+  const double T0 = getenv("SA_T0") ? atof(getenv("SA_T0")) : 3.0;
   for (long it = 0; it < iters; ++it) {
-    const double T = std::max(0.05, 3.0 * (1. - double(it) / iters));
-    const int w = rng() % 10;
+    const double T = std::max(0.03, T0 * (1. - double(it) / iters));
+    const int w = rng() % 40;
     int i = 0, j = 0, old = 0;
-    if (w < 4) { i = rng() % 42; j = rng() % 42; std::swap(pin[i], pin[j]); }
-    else if (w < 9) { i = rng() % 81; j = rng() % 81; std::swap(pcr[i], pcr[j]); }
-    else if (rng() & 1) { old = base1; base1 = (rng() & 1) * 8; }
-    else { old = base2; base2 = rng() & 15; i = 1; }
-    costs(ca, cf);
+    const int ca0 = ca, cf0 = cf;
+    if (w < 16) { i = rng() % 42; j = rng() % 42; std::swap(pin[i], pin[j]); recost_arrays(i, j, ca, cf); }
+    else if (w < 39) { i = rng() % 81; j = rng() % 81; std::swap(pcr[i], pcr[j]); recost_arrays(42 + i, 42 + j, ca, cf); }
+    else if (rng() & 1) { old = base1; base1 = (rng() & 1) * 8; recost_all(ca, cf); }
+    else { old = base2; base2 = rng() & 15; i = 1; recost_all(ca, cf); }
     const double c = obj(ca, cf);
     if (c <= cur || U(rng) < std::exp((cur - c) / T)) {
       cur = c;
       if (c < best) { best = c; std::copy(pin, pin + 42, bpin); std::copy(pcr, pcr + 81, bpcr); bb1 = base1; bb2 = base2; bca = ca; bcf = cf; }
     } else {
-      if (w < 4) std::swap(pin[i], pin[j]);
-      else if (w < 9) std::swap(pcr[i], pcr[j]);
-      else if (i == 0) base1 = old; else base2 = old;
+      if (w < 16) { std::swap(pin[i], pin[j]); recost_arrays(i, j, ca, cf); }
+      else if (w < 39) { std::swap(pcr[i], pcr[j]); recost_arrays(42 + i, 42 + j, ca, cf); }
+      else { if (i == 0) base1 = old; else base2 = old; recost_all(ca, cf); }
+      (void)ca0; (void)cf0;
     }
   }
   printf("{\"cost\": %d, \"ideal\": 24, \"flush_cost\": %d, \"flush_ideal\": %d, \"objective\": %.2f, \"pin\": [", bca, bcf, (int)groups_flush.size(), best);
