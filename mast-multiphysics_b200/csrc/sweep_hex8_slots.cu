@@ -37,7 +37,8 @@ constexpr int ST = SW * 32;
 constexpr int TCX = 9, TCY = 9;        // node columns of a tile (8 x 8 elements)
 constexpr int NS = TCX * TCY;
 constexpr int NSB = (NS + 3) & ~3;
-constexpr int NEP = 65;                // doubles per slot array: 64 element columns + 1 (bank = value id + column)
+constexpr int NEP = 69;                 // doubles per slot array: 64 element columns + 5: bank = 5 x value id + column (tools/design/slots_bank_model.py:
+                                       // the gather costs 47 wavefronts per node at this stride, 68 at 65, 44 without conflicts)
 constexpr int N_CR = 144, N_IN = 78;   // value arrays: cross pairs 9 x 16; in-plane 3 x 16 (i < j) + 3 x 10 (i == j, unordered)
 constexpr int QS = 10;                 // doubles staged per (element, qp): inv[3][3], w
 constexpr int MAXOWN = 49;
