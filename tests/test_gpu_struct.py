@@ -355,3 +355,34 @@ def test_struct_density_sensitivities_alone(built, monkeypatch, struct_kernel):
         monkeypatch.delenv("MASTB200_SENS_STRUCT")
         assert ctx_e.stats()["kernel_launches"] == 2
         _close(G[own], Ge[own], 1e-11)
+
+
+@pytest.mark.parametrize("nv", [3, 6])
+def test_struct_store_paths_give_the_same_bits(built, monkeypatch, struct_kernel, nv):
+    # The CSR stores of the structured kernels take a wide path when the caller's J is 32-byte aligned (16-byte + 8-byte
+    # stores of a row piece; TMA bulk stores of the rotational rows at nv = 6) and plain 8-byte stores otherwise; the
+    # lock-step kernel clears its accumulators by TMA bulk copies unless MASTB200_STRUCT_NO_TMA_CLEAR is set.  Every
+    # combination must give the same bits as the library-owned (aligned) buffer.
+    import torch
+    xyz, conn = mesh.build_cube(9, 8, 6, 0.3, 0.2, 0.25, 8, jitter=0.2)
+    con = mesh.dirichlet_flags(len(xyz), nv, mesh.boundary_nodes(9, 8, 6, 4))
+    prob = O.Problem(O.HEX8, xyz, conn, nv, constrained=con)
+    X = O.state(prob.n_dof, 3)
+    ctx = prob.make_context(0)
+    R0 = np.empty(prob.n_dof); J0 = np.empty(ctx.nnz)
+    ctx.residual_and_jacobian(X, R0, J0)
+    assert _is_struct(ctx, struct_kernel, nv)
+    dX = torch.from_numpy(X).cuda()
+    for off in (0, 1, 2):  # doubles: 32-byte aligned, 8-byte aligned, 16-byte aligned
+        buf = torch.full((ctx.nnz + 4,), float("nan"), dtype=torch.float64, device="cuda")
+        dJ = buf[off:off + ctx.nnz]
+        dR = torch.empty(prob.n_dof, dtype=torch.float64, device="cuda")
+        ctx.residual_and_jacobian(dX, dR, dJ)
+        torch.cuda.synchronize()
+        assert np.array_equal(dJ.cpu().numpy(), J0) and np.array_equal(dR.cpu().numpy(), R0), off
+        assert torch.isnan(buf[:off]).all() and torch.isnan(buf[off + ctx.nnz:]).all()  # nothing written outside J
+    monkeypatch.setenv("MASTB200_STRUCT_NO_TMA_CLEAR", "1")
+    ctx2 = prob.make_context(0)
+    R1 = np.empty(prob.n_dof); J1 = np.empty(ctx2.nnz)
+    ctx2.residual_and_jacobian(X, R1, J1)
+    assert np.array_equal(J1, J0) and np.array_equal(R1, R0)
