@@ -308,6 +308,7 @@ __global__ void __launch_bounds__(TB, MASTB200_PLATE_CTAS) quad4_plate_kernel(co
     // a six-value row piece starts at a multiple of 48 bytes (36 nb0 + 6 c + i * 6 nnb doubles): 16-byte stores when the
     // caller's J is 16-byte aligned
     const bool al16 = (reinterpret_cast<uintptr_t>(p.J) & 15) == 0;
+    const bool al32 = (reinterpret_cast<uintptr_t>(p.J) & 31) == 0;  // every other piece starts on a 32-byte boundary
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       double v[6];
@@ -321,7 +322,15 @@ __global__ void __launch_bounds__(TB, MASTB200_PLATE_CTAS) quad4_plate_kernel(co
         }
         v[j] = k;
       }
-      if (al16) {
+      if (al32) {  // one 32-byte and one 16-byte store, chosen without a branch
+        double* d = dst + i * rl;
+        const bool odd = ((c + i * nnb) & 1) != 0;
+        double* p16 = odd ? d : d + 4;
+        double* p32 = odd ? d + 2 : d;
+        asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p16), "d"(odd ? v[0] : v[4]), "d"(odd ? v[1] : v[5]) : "memory");
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p32), "d"(odd ? v[2] : v[0]), "d"(odd ? v[3] : v[1]),
+                     "d"(odd ? v[4] : v[2]), "d"(odd ? v[5] : v[3]) : "memory");
+      } else if (al16) {
         double2* d2 = reinterpret_cast<double2*>(dst + i * rl);
         d2[0] = make_double2(v[0], v[1]); d2[1] = make_double2(v[2], v[3]); d2[2] = make_double2(v[4], v[5]);
       } else {
