@@ -553,9 +553,10 @@ __device__ __forceinline__ void flush_plane(const StructParams& p, const Sm& sm,
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             double* d = dst + i * rl;
-            if (p.j_aligned32) {
-              if ((((c + i * (rs / 3)) & 1) == 0)) { stg256(d, K[i][0], K[i][1], K[i][2], 0.); stg128(d + 4, 0., 0.); }
-              else { stg128(d, K[i][0], K[i][1]); stg256(d + 2, K[i][2], 0., 0., 0.); }
+            if (p.j_aligned32) {  // chosen without a branch: neighbouring lanes alternate between the two cases
+              const bool odd = ((c + i * (rs / 3)) & 1) != 0;
+              stg128(odd ? d : d + 4, odd ? K[i][0] : 0., odd ? K[i][1] : 0.);
+              stg256(odd ? d + 2 : d, odd ? K[i][2] : K[i][0], odd ? 0. : K[i][1], odd ? 0. : K[i][2], 0.);
             } else {  // a caller's device pointer that is only 8-byte aligned
               d[0] = K[i][0]; d[1] = K[i][1]; d[2] = K[i][2]; d[3] = 0.; d[4] = 0.; d[5] = 0.;
             }
