@@ -620,6 +620,38 @@ int ensure_struct_plan(mastb200_context* ctx) {
     }
     CU(S.g_units.upload(grouped, ctx->stream));
   }
+  {  // units of the structured sensitivity sweep: columns of <= 15 x 11 owned nodes (16 x 12 elements), two CTAs per SM
+    std::vector<std::pair<int, int>> sx, sy;
+    chunks(nx + 1, kSensTileX, sx);
+    chunks(ny + 1, kSensTileY, sy);
+    const int64_t s_tiles = (int64_t)sx.size() * sy.size();
+    const int64_t sseg = pick_segments(s_tiles, (int64_t)ctx->sm_count * 2);
+    std::vector<StructUnit> su;
+    std::vector<int64_t> sc;
+    for (size_t ty = 0; ty < sy.size(); ++ty)
+      for (size_t tx = 0; tx < sx.size(); ++tx)
+        for (int64_t sg = 0; sg < sseg; ++sg) {
+          StructUnit u;
+          u.o0x = (int16_t)sx[tx].first; u.nox = (int16_t)sx[tx].second;
+          u.o0y = (int16_t)sy[ty].first; u.noy = (int16_t)sy[ty].second;
+          const int64_t e0x = std::max<int64_t>(u.o0x - 1, 0), e1x = std::min<int64_t>(u.o0x + u.nox, nx);
+          const int64_t e0y = std::max<int64_t>(u.o0y - 1, 0), e1y = std::min<int64_t>(u.o0y + u.noy, ny);
+          u.e0x = (int16_t)e0x; u.nex = (int16_t)(e1x - e0x);
+          u.e0y = (int16_t)e0y; u.ney = (int16_t)(e1y - e0y);
+          u.z0 = (int32_t)(oz0 + planes * sg / sseg); u.z1 = (int32_t)(oz0 + planes * (sg + 1) / sseg);
+          if (u.z1 <= u.z0) continue;
+          const int64_t s_begin = u.z0 > 0 ? u.z0 - 1 : 0;
+          su.push_back(u);
+          sc.push_back((int64_t)u.nex * u.ney * (u.z1 - s_begin));
+        }
+    std::vector<int32_t> so(su.size());
+    for (size_t i = 0; i < so.size(); ++i) so[i] = (int32_t)i;
+    std::stable_sort(so.begin(), so.end(), [&](int32_t a, int32_t b) { return sc[a] > sc[b]; });
+    std::vector<StructUnit> ss(su.size());
+    for (size_t i = 0; i < so.size(); ++i) ss[i] = su[so[i]];
+    CU(S.s_units.upload(ss, ctx->stream));
+    S.s_n_units = (int32_t)ss.size();
+  }
   // units of the register-accumulating march (3-dof system): columns of <= 16 x 4 owned nodes cut into z-segments.
   // Opt-in with MASTB200_STRUCT_KERNEL=march: parity-green but slower than the lock-step kernel so far
   // (profiles/r01h_hex8_march_ncu.md).
@@ -813,7 +845,7 @@ int run_density_sens(mastb200_context* ctx, const double* X, const double* adj, 
     const mastb200_context::StructPlan& S = ctx->splan;
     const mastb200_material& m = ctx->mat;
     StructParams sp;
-    sp.units = S.units.p; sp.n_units = S.n_units; sp.counter = ctx->d_tile_counter.p;
+    sp.units = S.s_units.p; sp.n_units = S.s_n_units; sp.counter = ctx->d_tile_counter.p;  // its own, larger tiles
     sp.nx = S.nx; sp.ny = S.ny; sp.nz = S.nz; sp.oz0 = S.oz0; sp.nv = 3;
     sp.xyz = ctx->d_xyz.p; sp.X = p.X; sp.adj = dadj; sp.G = dG;
     sp.cmask = ctx->has_constraints ? ctx->d_cmask.p : nullptr;

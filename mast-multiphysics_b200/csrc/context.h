@@ -139,6 +139,8 @@ struct mastb200_context {
     DevBuf<StructUnit> units;
     DevBuf<int32_t> arr_off;
     DevBuf<int64_t> nbr_ptr;
+    DevBuf<StructUnit> s_units;  // units of the structured sensitivity sweep (sweep_hex8_sens_struct.cu: larger tiles)
+    int32_t s_n_units = 0;
     DevBuf<double> zeros;     // source of the bulk copies (TMA) that clear the lock-step kernel's accumulators
     // units of the register-accumulating march (sweep_hex8_march.cu; 3-dof system)
     DevBuf<StructUnit> m_units;
@@ -152,7 +154,7 @@ struct mastb200_context {
     DevBuf<StructUnit> g_units;
     std::vector<int32_t> g_ptr, g_z0, g_z1;
     bool last_slots = false;
-    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); zeros.release(); m_units.release(); g_units.release(); g_ptr.clear(); g_z0.clear(); g_z1.clear(); }
+    void reset() { tried = ok = false; units.release(); arr_off.release(); nbr_ptr.release(); zeros.release(); s_units.release(); m_units.release(); g_units.release(); g_ptr.clear(); g_z0.clear(); g_z1.clear(); }
   } splan;
   cudaStream_t copy_stream = nullptr;  // second stream + events of the segmented host-buffer sweep (created on first use)
   cudaEvent_t seg_ev[66] = {};  // [g] planes of X for segment g are in, [32 + g] segment g is swept, [64], [65] fork / join

@@ -77,6 +77,7 @@ size_t hex8_march_smem_bytes();
 int hex8_march_threads();
 cudaError_t launch_hex8_march(const StructParams& p, int n_ctas, cudaStream_t stream);
 // density sensitivities alone on the same units (sweep_hex8_sens_struct.cu; 3-dof system, SIMP, linear strain)
+constexpr int kSensTileX = 15, kSensTileY = 11;   // owned node columns per unit (16 x 12 elements)
 size_t hex8_sens_struct_smem_bytes();
 cudaError_t launch_hex8_sens_struct(const StructParams& p, int sm_count, cudaStream_t stream);
 // element results in shared-memory slots, row-owner gather straight to the CSR (sweep_hex8_slots.cu; 3-dof system, same units

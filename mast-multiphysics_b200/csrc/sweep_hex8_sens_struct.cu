@@ -10,7 +10,7 @@
 //
 // The element-parallel kernels of stress_output.cu (sens_qp_hex8_kernel + sens_gather_kernel) read the eight nodes of
 // every (element, qp) from global memory (80 loads per thread) and pass 8 doubles per element through HBM.  Here the work
-// unit is the structured sweep's: a column of <= 7x7 owned nodes over a z-range with the <= 8x8 elements that touch it;
+// unit is the structured sweep's: a column of <= 15x11 owned nodes over a z-range with the <= 16x12 elements that touch it (its own unit list);
 // node planes (coordinates, state, adjoint, density) are staged once per plane with cp.async, lane = (element, qp) forms
 // s_q, the eight lanes of an element turn the point values into nodal sums by shuffles (q ascending) and leave them in a
 // per-element slot; one thread per owned node then adds its <= 8 corner values in ascending element id (the reference's
@@ -25,8 +25,13 @@ namespace {
 
 constexpr int SW = 8;                  // warps per CTA
 constexpr int ST = SW * 32;
-constexpr int TCX = 9, TCY = 9;        // node columns of a tile (8 x 8 elements)
+// Tile of EX x EY elements = (EX + 1) x (EY + 1) node columns, of which <= kSensTileX x kSensTileY are owned.  The kernel keeps
+// only node planes and one value per (element, node) in shared memory, so it affords a larger tile than the R / J sweeps:
+// 16 x 12 elements visit 1.16 elements per element where 8 x 8 visit 1.31 -- the kernel is fp64-bound, the halo is pure loss.
+constexpr int EX = kSensTileX + 1, EY = kSensTileY + 1, NE = EX * EY;
+constexpr int TCX = EX + 1, TCY = EY + 1;
 constexpr int NS = TCX * TCY;
+static_assert(EX == 16 && NE % 32 == 0 && NS <= ST && kSensTileX * kSensTileY <= ST, "tile shape vs. thread mapping");
 constexpr int NSB = (NS + 3) & ~3;
 constexpr double GP = 0.57735026918962576451;
 
@@ -35,9 +40,9 @@ struct SmemS {
   double u[3][3][NS];
   double adj[3][3][NS];
   double rho[3][NS];
-  double slot[3][64][8];   // [element plane % 3][element column][node in ijk order]: sum_q N_a(q) s_q
+  double slot[3][NE][8];   // [element plane % 3][element column][node in ijk order]: sum_q N_a(q) s_q
   uint8_t cm[3][NSB];
-  int2 node[64];           // owned nodes of the unit: in-plane node id, lx | ly << 4
+  int2 node[kSensTileX * kSensTileY];  // owned nodes of the unit: in-plane node id, lx | ly << 8
   int misc[4];
 };
 
@@ -168,7 +173,7 @@ __global__ void __launch_bounds__(ST, 2) hex8_sens_struct_kernel(const StructPar
     if (tid < n_own) {
       const int oyi = tid / u.nox, oxi = tid - oyi * u.nox;
       const int ax = u.o0x + oxi, ay = u.o0y + oyi;
-      sm.node[tid] = make_int2((int)(ax + ay * npx), (ax - u.e0x) | ((ay - u.e0y) << 4));
+      sm.node[tid] = make_int2((int)(ax + ay * npx), (ax - u.e0x) | ((ay - u.e0y) << 8));
     }
     load_plane(s_begin);
     if (s_begin + 1 <= p.nz) load_plane(s_begin + 1);
@@ -178,11 +183,12 @@ __global__ void __launch_bounds__(ST, 2) hex8_sens_struct_kernel(const StructPar
     for (int s = s_begin; s < u.z1; ++s) {
       if (s + 2 <= p.nz) load_plane(s + 2);  // fetched while this plane is processed (its slot held plane s - 1)
       if (s < p.nz) {
-        // element plane s: eight elements per warp in two passes of four
+        // element plane s: four elements per warp and pass (lane = (element, qp)), 32 per pass and CTA
 #pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-          const int el = warp * 8 + pass * 4 + (lane >> 3), q = lane & 7;
-          const int lex = el & 7, ley = el >> 3;
+        for (int pass = 0; pass < NE / (SW * 4); ++pass) {
+          const int el = pass * (SW * 4) + warp * 4 + (lane >> 3), q = lane & 7;
+          const int lex = el & (EX - 1), ley = el / EX;
+          if ((pass * (SW * 4)) / EX >= u.ney) break;  // the remaining rows of the tile hold no element of this unit
           const bool live = lex < u.nex && ley < u.ney;
           const double g = element_point(p, sm, s, ley * TCX + lex, q, live, same, lane);
           if (live) sm.slot[s % 3][el][q] = g;
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(ST, 2) hex8_sens_struct_kernel(const StructPar
       // barrier per plane: three slot buffers, so the next element plane is computed while these few threads add corners
       if (s >= u.z0 && tid < n_own) {
         const int2 ni = sm.node[tid];
-        const int lx = ni.y & 15, ly = (ni.y >> 4) & 15;
+        const int lx = ni.y & 255, ly = ni.y >> 8;
         double acc = 0.;
 #pragma unroll
         for (int cz = 0; cz < 2; ++cz) {
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(ST, 2) hex8_sens_struct_kernel(const StructPar
             for (int cx = 0; cx < 2; ++cx) {
               const int lex = lx - 1 + cx;
               if ((unsigned)lex >= (unsigned)u.nex) continue;
-              acc += sm.slot[layer % 3][ley * 8 + lex][(1 - cx) + 2 * (1 - cy) + 4 * (1 - cz)];
+              acc += sm.slot[layer % 3][ley * EX + lex][(1 - cx) + 2 * (1 - cy) + 4 * (1 - cz)];
             }
           }
         }
