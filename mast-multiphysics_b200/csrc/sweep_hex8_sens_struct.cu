@@ -12,7 +12,7 @@
 // every (element, qp) from global memory (80 loads per thread) and pass 8 doubles per element through HBM.  Here the work
 // unit is the structured sweep's: a column of <= 15x11 owned nodes over a z-range with the <= 16x12 elements that touch it (its own unit list);
 // node planes (coordinates, state, adjoint, density) are staged once per plane with cp.async, lane = (element, qp) forms
-// s_q, the eight lanes of an element turn the point values into nodal sums by shuffles (q ascending) and leave them in a
+// s_q, the eight lanes of an element turn the point values into nodal sums by a three-stage shuffle butterfly and leave them in a
 // per-element slot; one thread per owned node then adds its <= 8 corner values in ascending element id (the reference's
 // ADD order) and writes G -- while the other warps already compute the next element plane (three slot buffers, one CTA
 // barrier per plane).  Nothing but G leaves the SM; bitwise reproducible; ~33 KB of shared memory, two CTAs per SM.
@@ -122,16 +122,18 @@ __device__ __forceinline__ double element_point(const StructParams& p, const Sme
     const double rpow = pm1 == 3. ? rho_q * rho_q * rho_q : (pm1 == 2. ? rho_q * rho_q : (pm1 == 1. ? rho_q : (pm1 == 0. ? 1. : pow(rho_q, pm1))));
     sq = det * p.E0 * (1. - p.rho_min) * p.penalty * rpow * dens;
   }
-  // lane a of the element's eight lanes ends with sum_q N_a(q) s_q; a in ijk order (dx = a & 1, dy = (a >> 1) & 1, dz = a >> 2)
-  const int a = q;
-  double acc = 0.;
+  // lane a of the element's eight lanes ends with sum_q N_a(q) s_q (a in ijk order: dx = a & 1, dy = (a >> 1) & 1, dz = a >> 2).
+  // N_a(q) = prod_d (1 +- GP) / 2 is a tensor product, so the sum is three butterfly stages (x, y, z): v <- w_same v +
+  // w_other v(partner), partner = the lane whose bit d differs -- 6 shuffles and 6 fp64 operations instead of 16 and 24.
+  // The summation order is fixed (x, then y, then z), so runs stay bitwise reproducible.
+  double acc = sq;
+  {
+    const double ws = 0.5 * (1. + GP), wo = 0.5 * (1. - GP);
 #pragma unroll
-  for (int qq = 0; qq < 8; ++qq) {
-    const double sv = __shfl_sync(0xffffffffu, sq, (lane & ~7) | qq);
-    const double fx = ((qq & 1) != 0) == ((a & 1) != 0) ? 1. + GP : 1. - GP;
-    const double fy = ((qq & 2) != 0) == ((a & 2) != 0) ? 1. + GP : 1. - GP;
-    const double fz = ((qq & 4) != 0) == ((a & 4) != 0) ? 1. + GP : 1. - GP;
-    acc = fma(0.125 * fx * fy * fz, sv, acc);
+    for (int bit = 1; bit < 8; bit <<= 1) {
+      const double other = __shfl_xor_sync(0xffffffffu, acc, bit);
+      acc = ws * acc + wo * other;
+    }
   }
   return acc;
 }
