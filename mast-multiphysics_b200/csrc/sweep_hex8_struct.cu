@@ -333,16 +333,18 @@ __device__ __forceinline__ void geometry_phase(const StructParams& p, const Sm& 
       const double rpow = pm1 == 3. ? rho_q * rho_q * rho_q : (pm1 == 2. ? rho_q * rho_q : (pm1 == 1. ? rho_q : (pm1 == 0. ? 1. : pow(rho_q, pm1))));
       sq = det * p.E0 * (1. - p.rho_min) * p.penalty * rpow * dens;
     }
-    // lane a of the element's eight lanes ends with sum_q N_a(q) s_q; a in ijk order (dx = a & 1, dy = (a >> 1) & 1, dz = a >> 2)
-    const int a = q, lane = threadIdx.x & 31;
-    double acc = 0.;
+    // lane a of the element's eight lanes ends with sum_q N_a(q) s_q; a in ijk order (dx = a & 1, dy = (a >> 1) & 1, dz = a >> 2):
+    // the shape functions are a tensor product, so the sum is three butterfly stages (x, y, z) over the eight lanes
+    // (sweep_hex8_sens_struct.cu does the same); fixed order, bitwise reproducible
+    const int a = q;
+    double acc = sq;
+    {
+      const double ws = 0.5 * (1. + GP), wo = 0.5 * (1. - GP);
 #pragma unroll
-    for (int qq = 0; qq < 8; ++qq) {
-      const double sv = __shfl_sync(0xffffffffu, sq, (lane & ~7) | qq);
-      const double fx = ((qq & 1) != 0) == ((a & 1) != 0) ? 1. + GP : 1. - GP;
-      const double fy = ((qq & 2) != 0) == ((a & 2) != 0) ? 1. + GP : 1. - GP;
-      const double fz = ((qq & 4) != 0) == ((a & 4) != 0) ? 1. + GP : 1. - GP;
-      acc = fma(0.125 * fx * fy * fz, sv, acc);
+      for (int bit = 1; bit < 8; bit <<= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, acc, bit);
+        acc = ws * acc + wo * other;
+      }
     }
     if (live) gq[a] = acc;
   }
