@@ -608,14 +608,39 @@ int ensure_struct_plan(mastb200_context* ctx) {
   std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return cost[a] > cost[b]; });
   std::vector<StructUnit> sorted(units.size());
   for (size_t i = 0; i < order.size(); ++i) sorted[i] = units[order[i]];
-  {  // the same units by z-segment (ascending), cost-sorted inside a segment: the segmented sweep of host-buffer calls
+  {  // units of the segmented sweep of host-buffer calls, by z-segment (ascending), cost-sorted inside a segment.  Small
+     // meshes: the same units as above.  Tall meshes get their own, uneven split -- short segments at both ends (the planes of
+     // X the first kernel waits for and the rows of R that leave after the last one are the exposed copies), long ones in
+     // the middle (every segment is a launch with a partly idle tail), each at most 2.5 x its predecessor (the planes of a
+     // segment arrive over PCIe while the one before is swept: ~19 us against ~54 us per plane at 200^2 nodes).
+    std::vector<int32_t> zb;  // segment boundaries (node planes)
+    if (planes >= 96 && !getenv("MASTB200_SEG_UNIFORM")) {
+      const double f[7] = {0., 0.05, 0.175, 0.475, 0.775, 0.925, 1.};
+      for (int k = 0; k < 7; ++k) zb.push_back((int32_t)(oz0 + (int64_t)(planes * f[k] + 0.5)));
+    } else {
+      for (int64_t sg = 0; sg <= nseg; ++sg) zb.push_back((int32_t)(oz0 + planes * sg / nseg));
+    }
     std::vector<StructUnit> grouped;
     S.g_ptr.assign(1, 0); S.g_z0.clear(); S.g_z1.clear();
-    for (int64_t sg = 0; sg < nseg; ++sg) {
-      const int32_t z0 = (int32_t)(oz0 + planes * sg / nseg), z1 = (int32_t)(oz0 + planes * (sg + 1) / nseg);
+    for (size_t sg = 0; sg + 1 < zb.size(); ++sg) {
+      const int32_t z0 = zb[sg], z1 = zb[sg + 1];
       if (z1 <= z0) continue;
-      for (const StructUnit& u : sorted)
-        if (u.z0 == z0 && u.z1 == z1) grouped.push_back(u);
+      std::vector<StructUnit> seg_units;
+      for (size_t ty = 0; ty < cy.size(); ++ty)
+        for (size_t tx = 0; tx < cx.size(); ++tx) {
+          StructUnit u;
+          u.o0x = (int16_t)cx[tx].first; u.nox = (int16_t)cx[tx].second;
+          u.o0y = (int16_t)cy[ty].first; u.noy = (int16_t)cy[ty].second;
+          const int64_t e0x = std::max<int64_t>(u.o0x - 1, 0), e1x = std::min<int64_t>(u.o0x + u.nox, nx);
+          const int64_t e0y = std::max<int64_t>(u.o0y - 1, 0), e1y = std::min<int64_t>(u.o0y + u.noy, ny);
+          u.e0x = (int16_t)e0x; u.nex = (int16_t)(e1x - e0x);
+          u.e0y = (int16_t)e0y; u.ney = (int16_t)(e1y - e0y);
+          u.z0 = z0; u.z1 = z1;
+          seg_units.push_back(u);
+        }
+      std::stable_sort(seg_units.begin(), seg_units.end(),
+                       [](const StructUnit& a, const StructUnit& b) { return (int)a.nex * a.ney > (int)b.nex * b.ney; });
+      grouped.insert(grouped.end(), seg_units.begin(), seg_units.end());
       S.g_ptr.push_back((int32_t)grouped.size()); S.g_z0.push_back(z0); S.g_z1.push_back(z1);
     }
     CU(S.g_units.upload(grouped, ctx->stream));
