@@ -614,7 +614,7 @@ int ensure_struct_plan(mastb200_context* ctx) {
      // the middle (every segment is a launch with a partly idle tail), each at most 2.5 x its predecessor (the planes of a
      // segment arrive over PCIe while the one before is swept: ~19 us against ~54 us per plane at 200^2 nodes).
     std::vector<int32_t> zb;  // segment boundaries (node planes)
-    if (planes >= 96 && !getenv("MASTB200_SEG_UNIFORM")) {
+    if (planes >= 160 && !getenv("MASTB200_SEG_UNIFORM")) {  // (at 100 planes per rank on two GPUs the even split measured faster)
       const double f[7] = {0., 0.05, 0.175, 0.475, 0.775, 0.925, 1.};
       for (int k = 0; k < 7; ++k) zb.push_back((int32_t)(oz0 + (int64_t)(planes * f[k] + 0.5)));
     } else {
