@@ -721,19 +721,13 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
         rankpack |= rank << (2 * c);
       }
     }
-    // flush: warp w writes the owned nodes w, w + 16, ...; lane r < 4 fetches the CSR row pointer of the r-th of them
+    // flush: warp w writes the owned nodes 4 w .. 4 w + 3, eight lanes each (flush_plane)
     const int n_own = u.nox * u.noy;
     if (tid < n_own) {
       const int oyi = tid / u.nox, oxi = tid - oyi * u.nox;
       const int ax = u.o0x + oxi, ay = u.o0y + oyi;
       const int flags = (ax == 0 ? 1 : 0) | (ax == p.nx ? 2 : 0) | (ay == 0 ? 4 : 0) | (ay == p.ny ? 8 : 0);
       sm.node[tid] = make_int2((int)(ax + ay * npx), ((ay - u.e0y) * TCX + (ax - u.e0x)) | (flags << 8));
-    }
-    int64_t row0 = 0;
-    const bool row_on = lane < 4 && warp + SW * lane < n_own;
-    if (row_on) {
-      const int node = warp + SW * lane, oyi = node / u.nox, oxi = node - oyi * u.nox;
-      row0 = (u.o0x + oxi) + (u.o0y + oyi) * npx - (int64_t)p.oz0 * plane_nodes;
     }
 
     // prologue: clear the accumulators, stage the first two node planes
@@ -751,7 +745,7 @@ __global__ void __launch_bounds__(ST, kStructCtasPerSm) hex8_struct_kernel(const
     __syncthreads();
 
     for (int s = s_begin; s < u.z1; ++s) {
-      // fetched while this plane is processed: state of plane s+2, the CSR row pointer of this lane's flush node
+      // fetched while this plane is processed: state of plane s+2
       unsigned cmv = 0u;
       if (s + 2 <= p.nz) {
         load_plane(s + 2);
