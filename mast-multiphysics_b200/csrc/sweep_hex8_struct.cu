@@ -389,8 +389,14 @@ __device__ __forceinline__ void element_phase(const StructParams& p, const Sm& s
       const double trm = p.mu1 * (s0 + s1 + s2);
       mx = fmax(mx, fmax((p.lam1 + p.mu1) * s0 + trm, fmax((p.lam1 + p.mu1) * s1 + trm, (p.lam1 + p.mu1) * s2 + trm)));
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // warp maximum of non-negative doubles: their bit patterns order like unsigned integers, so two redux.sync (the high
+    // words, then the low words of the lanes that hold the maximal high word) replace a five-stage shuffle butterfly
+    {
+      const unsigned hi = (unsigned)__double2hiint(mx), lo = (unsigned)__double2loint(mx);
+      const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+      mx = __hiloint2double((int)mhi, (int)mlo);
+    }
   }
   // ordered accumulation: the (up to) four elements around a node column add in colour order
   const int base = ley * TCX + lex;
