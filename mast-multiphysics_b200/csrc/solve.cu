@@ -130,18 +130,28 @@ __global__ void __launch_bounds__(256) spmv_node_kernel(int64_t n_owned, const i
         a2 += j2[k] * xv[k];
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
-    }
-    if (lane == 0) {
-      const int64_t n = owned[r];
-      y[n * 3] = a0; y[n * 3 + 1] = a1; y[n * 3 + 2] = a2;
-      blocksum += x[n * 3] * a0 + x[n * 3 + 1] * a1 + x[n * 3 + 2] * a2;
+    // three sums over the warp in six 64-bit shuffles instead of fifteen: the first stage leaves (a0, a1) in the lower and
+    // (a2, 0) in the upper half-warp, the second one value per lane; lanes 0, 8, 16 end with the three components
+    {
+      const bool h4 = (lane & 16) != 0, h3 = (lane & 8) != 0;
+      const double r0 = __shfl_xor_sync(0xffffffffu, h4 ? a0 : a2, 16);
+      const double r1 = __shfl_xor_sync(0xffffffffu, h4 ? a1 : 0., 16);
+      const double v0 = (h4 ? a2 : a0) + r0, v1 = (h4 ? 0. : a1) + r1;
+      double w = (h3 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, h3 ? v0 : v1, 8);
+      w += __shfl_xor_sync(0xffffffffu, w, 4);
+      w += __shfl_xor_sync(0xffffffffu, w, 2);
+      w += __shfl_xor_sync(0xffffffffu, w, 1);
+      if ((lane & 7) == 0 && lane < 24) {
+        const int comp = lane >> 3;
+        const int64_t n = owned[r];
+        y[n * 3 + comp] = w;
+        blocksum += x[n * 3 + comp] * w;
+      }
     }
   }
+  // lanes 0, 8, 16 hold the warp's x . y partials
+  blocksum += __shfl_xor_sync(0xffffffffu, blocksum, 8);
+  blocksum += __shfl_xor_sync(0xffffffffu, blocksum, 16);
   if (partial) {
     if (lane == 0) red[warp] = blocksum;
     __syncthreads();
