@@ -386,3 +386,31 @@ def test_struct_store_paths_give_the_same_bits(built, monkeypatch, struct_kernel
     R1 = np.empty(prob.n_dof); J1 = np.empty(ctx2.nnz)
     ctx2.residual_and_jacobian(X, R1, J1)
     assert np.array_equal(J1, J0) and np.array_equal(R1, R0)
+
+
+def test_struct_tall_slab_uneven_host_segments(built, monkeypatch, struct_kernel):
+    # Host-buffer sweeps of a slab with >= 160 node planes run in UNEVEN z-segments (short ones at both ends, their copies
+    # of X / R overlapped with the kernels); the result must equal the oracle's and, bit for bit, the one-launch sweep with
+    # device buffers and the even split (MASTB200_SEG_UNIFORM=1).
+    import torch
+    if struct_kernel == "march":
+        pytest.skip("the march serves device buffers only")
+    prob = _problem(5, 4, 170)
+    X = O.state(prob.n_dof, 2)
+    ctx = prob.make_context(0)
+    R = np.full(prob.n_dof, np.nan); J = np.full(ctx.nnz, np.nan)
+    ctx.residual_and_jacobian(X, R, J)
+    assert _is_struct(ctx, struct_kernel)
+    Ro, Jo = prob.residual_and_jacobian(X)
+    _close(R, Ro); _close(J, Jo)
+    dX = torch.from_numpy(X).cuda()
+    dR = torch.empty(prob.n_dof, dtype=torch.float64, device="cuda")
+    dJ = torch.empty(ctx.nnz, dtype=torch.float64, device="cuda")
+    ctx.residual_and_jacobian(dX, dR, dJ)
+    torch.cuda.synchronize()
+    assert np.array_equal(dR.cpu().numpy(), R) and np.array_equal(dJ.cpu().numpy(), J)
+    monkeypatch.setenv("MASTB200_SEG_UNIFORM", "1")
+    ctx2 = prob.make_context(0)
+    R2 = np.full(prob.n_dof, np.nan); J2 = np.full(ctx2.nnz, np.nan)
+    ctx2.residual_and_jacobian(X, R2, J2)
+    assert np.array_equal(R2, R) and np.array_equal(J2, J)
